@@ -1,0 +1,192 @@
+/*
+ * n1gpu.h — C ABI of libn1gpu.so: the B200-native replacement for the N1QL data-parallel chain
+ *
+ *     PrimaryScan / Fetch -> Filter -> InitialGroup -> IntermediateGroup -> FinalGroup
+ *
+ * of pavel-paulau/query.  The reference has no FFI for this path (it is 100 % Go); the boundary it
+ * offers is a set of Go interfaces.  Each entry point below names the reference interface it stands
+ * in for (file:line under the reference tree); INTEGRATION.md shows the cgo binding a maintainer
+ * would add in package `execution`.
+ *
+ * Conventions: plain C types only; every function returns 0 (N1GPU_OK) or a negative status;
+ * the message for the last failure on the calling thread is n1gpu_last_error().  Handles are opaque.
+ * Output buffers are caller-owned.  Host pointers unless the name says `dev`.  Thread-safe per
+ * handle (one goroutine / OS thread drives one handle at a time).  No caller pointer is retained
+ * after a call returns, except where stated.
+ */
+#ifndef N1GPU_H
+#define N1GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------------ */
+#define N1GPU_OK 0
+#define N1GPU_E_INVALID (-1)      /* bad argument / handle */
+#define N1GPU_E_PARSE (-2)        /* expression / plan / JSON text could not be parsed */
+#define N1GPU_E_INELIGIBLE (-3)   /* plan is outside the substituted subset: caller keeps its own operators */
+#define N1GPU_E_CUDA (-4)         /* CUDA runtime / driver / NVRTC failure (there is NO CPU fallback) */
+#define N1GPU_E_IO (-5)           /* keyspace directory could not be read */
+#define N1GPU_E_CANCELLED (-6)    /* n1gpu_query_cancel() was called (execution.Operator.SendStop) */
+#define N1GPU_E_NOMEM (-7)
+
+/* ---- value classes (the per-row tag byte of a column; N1QL type order value/value.go:69-79) ------ */
+#define N1GPU_C_MISSING 0
+#define N1GPU_C_NULL 1
+#define N1GPU_C_FALSE 2
+#define N1GPU_C_TRUE 3
+#define N1GPU_C_INT 4    /* payload = int64 */
+#define N1GPU_C_FLOAT 5  /* payload = float64 bits (never integral when it came from a document) */
+#define N1GPU_C_STRING 6 /* payload = rank in the column's bytewise-sorted dictionary */
+#define N1GPU_C_OTHER 7  /* array / object / binary: referencing such a column makes a plan ineligible */
+
+typedef struct n1gpu_table n1gpu_table;   /* a shredded keyspace (columns + dictionaries), resident in HBM */
+typedef struct n1gpu_query n1gpu_query;   /* a compiled Filter + Group chain (one specialised sm_100a kernel) */
+typedef struct n1gpu_result n1gpu_result; /* finalised groups (what FinalGroup emits) or a partial state */
+
+/* ---- library ----------------------------------------------------------------------------------- */
+/* Selects the CUDA device of this process (one process per GPU).  device < 0: current device.
+ * Stands in for nothing in the reference; called from the shim's init().                           */
+int n1gpu_init(int device);
+int n1gpu_shutdown(void);
+const char* n1gpu_last_error(void);
+const char* n1gpu_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches evidence) */
+uint64_t n1gpu_launch_count(void);
+
+/* ---- columnar shredder: replaces PrimaryScan + Fetch over datastore/file ---------------------------
+ * Reference: execution/scan_primary.go:61-118, execution/fetch.go:54-153,
+ * datastore/file/file.go:312-353,711-743 (sorted ReadDir, one ReadFile per key),
+ * value/parsed.go:38-98,159-207 (type sniffing, lazy field find), value/value.go:367-430.          */
+int n1gpu_table_create(n1gpu_table** out);
+/* Declares a column for a field path below the document root; components separated by '\x1f'
+ * (e.g. "pricing\x1flist" for `pricing`.`list`).  Must precede any append.  Returns the index.      */
+int n1gpu_table_add_column(n1gpu_table* t, const char* path);
+int n1gpu_table_find_column(const n1gpu_table* t, const char* path); /* index or -1 */
+/* Appends ndocs documents: doc i is bytes [offsets[i], offsets[i+1]) of buf, in primary-key order.
+ * Shreds with `threads` host threads (0 = all cores).                                              */
+int n1gpu_table_append_json(n1gpu_table* t, const char* buf, const int64_t* offsets, int64_t ndocs, int threads);
+/* Reads a file-datastore keyspace directory <root>/<namespace>/<keyspace>: every non-directory entry,
+ * sorted by file name, is one document (file.go:711-730).                                           */
+int n1gpu_table_load_dir(n1gpu_table* t, const char* dir, int threads);
+/* Pre-shredded column (the "columns already resident" metric): nrows payload words of `width` bytes
+ * (8: int64 / float64 bits / string rank; 4: string rank) and nrows class bytes (NULL = all C_INT for
+ * width 8 / all C_STRING for width 4).  dict_blob/dict_offsets: the column's sorted dictionary
+ * (ndict strings, string i = blob[off[i], off[i+1])), or NULL.  Buffers are copied.                 */
+int n1gpu_table_set_column(n1gpu_table* t, int col, int width, const void* payload, const uint8_t* tags,
+                           int64_t nrows, const char* dict_blob, const int64_t* dict_offsets, int64_t ndict);
+/* Builds dictionaries and column statistics, uploads the columns to HBM.  After seal the table is
+ * immutable and may be shared by any number of queries.                                             */
+int n1gpu_table_seal(n1gpu_table* t);
+int64_t n1gpu_table_num_rows(const n1gpu_table* t);
+int n1gpu_table_num_columns(const n1gpu_table* t);
+/* HBM bytes per row of column `col` that a scan reads: payload width (+1 when its tag bytes vary). */
+int n1gpu_table_column_scan_bytes(const n1gpu_table* t, int col);
+/* Dictionary exchange for multi-GPU tables (one process per GPU; the dictionary must be global so
+ * that string ranks are comparable across ranks).  Before seal: export this rank's distinct strings
+ * of a column, then import the merged sorted global dictionary.                                      */
+int n1gpu_table_dict_export(n1gpu_table* t, int col, char* blob, int64_t blob_cap, int64_t* offsets,
+                            int64_t offsets_cap, int64_t* ndict, int64_t* blob_bytes);
+int n1gpu_table_dict_import(n1gpu_table* t, int col, const char* blob, const int64_t* offsets, int64_t ndict);
+/* Column statistics exchange (int range / class mask) so that every rank compiles the same kernel. */
+int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]);
+int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]);
+/* Copies a column's staged rows (before seal): payload[nrows] (int64 / float64 bits / dictionary rank)
+ * and tags[nrows].  For shredder parity tests; either pointer may be NULL.                           */
+int n1gpu_table_column_peek(n1gpu_table* t, int col, int64_t* payload, uint8_t* tags, int64_t nrows);
+int n1gpu_table_free(n1gpu_table* t);
+
+/* ---- query: replaces Filter + InitialGroup + IntermediateGroup + FinalGroup -------------------------
+ * Reference: execution/filter.go:49-61, group_util.go:18-35, group_initial.go:56-108,
+ * group_intermediate.go:56-104, group_final.go:55-118, algebra/agg_*.go.
+ * Expressions arrive in the reference's own serialised form: the Stringer text that plan JSON carries
+ * (plan/filter.go "condition", plan/group.go "group_keys"/"aggregates"; expression/stringer.go), e.g.
+ *   where      "((`d`.`n`) between 10 and 20)"          (NULL/"" = no Filter)
+ *   group key  "(`d`.`type`)"
+ *   aggregate  "sum((`d`.`n`))"  "count(*)"  "count(distinct (`d`.`x`))"
+ * alias = the keyspace term's alias (plan/fetch.go).  N1GPU_E_INELIGIBLE when the chain uses anything
+ * outside the subset of SURVEY.md section 8b; the caller then runs its own operators.                */
+int n1gpu_query_compile(n1gpu_table* t, const char* alias, const char* where, const char* const* group_keys,
+                        int nkeys, const char* const* aggregates, int naggs, n1gpu_query** out);
+/* Runs the chain over the whole table and finalises (FinalGroup).  Blocking.                        */
+int n1gpu_query_execute(n1gpu_query* q, n1gpu_result** out);
+/* Asynchronous pair for pipelined use: launch enqueues the scan on the query's stream and returns;
+ * collect waits and finalises.  One launch may be outstanding per query handle.                    */
+int n1gpu_query_launch(n1gpu_query* q);
+int n1gpu_query_collect(n1gpu_query* q, n1gpu_result** out);
+/* execution.Operator.SendStop (execution/base.go:313-338): makes a running execute return CANCELLED. */
+int n1gpu_query_cancel(n1gpu_query* q);
+/* The generated CUDA source / kernel facts, for EXPLAIN-style inspection and tests.                 */
+const char* n1gpu_query_kernel_source(const n1gpu_query* q);
+/* info[0]=mode (0 ungrouped, 1 dense shared-memory table, 2 HBM hash 64-bit keys, 3 HBM hash 128-bit)
+ * info[1]=accumulator words per group  info[2]=registers/thread  info[3]=grid  info[4]=block
+ * info[5]=scan bytes per row  info[6]=static shared bytes  info[7]=dense slots / hash capacity      */
+int n1gpu_query_info(const n1gpu_query* q, int64_t info[8]);
+/* Device time of the last scan (kernel(s) between CUDA events on the query's stream), nanoseconds.  */
+int64_t n1gpu_query_last_scan_ns(const n1gpu_query* q);
+/* Rebinds a compiled query to another sealed table with the same schema/dictionaries/statistics
+ * (bench.py rotates table copies so that no step finds its input in L2).                            */
+int n1gpu_query_rebind(n1gpu_query* q, n1gpu_table* t);
+int n1gpu_query_free(n1gpu_query* q);
+
+/* ---- multi-GPU: InitialGroup per GPU, IntermediateGroup merge across GPUs ----------------------------
+ * Reference: execution/group_intermediate.go:56-104 + the CumulateIntermediate methods of algebra/agg_count.go ... agg_avg_distinct.go.
+ * One process per GPU.  Each rank scans its row range and exports its partial groups as fixed-size
+ * records in DEVICE memory; the caller moves records between ranks (NCCL all-to-all / all-gather over
+ * NVLink - torch.distributed in this repo, ncclSend/Recv from Go); the owner imports and finalises.
+ * Record layout: record_words 64-bit words = [key_lo, key_hi, acc words...]; DISTINCT entries travel
+ * as 2-word records [lo, hi].  owner(record) = mix(key) % nranks, computed by partial_partition.     */
+int n1gpu_query_scan_partial(n1gpu_query* q);                       /* scan only, state stays on device */
+int n1gpu_query_partial_counts(n1gpu_query* q, int64_t* ngroups, int64_t* ndistinct, int* record_words);
+/* Writes the partial groups, bucketed by owner rank, into dev_records (capacity in records) and the
+ * per-owner record counts into counts[nranks] (host).  Same for DISTINCT entries.                   */
+int n1gpu_query_partial_export(n1gpu_query* q, int nranks, void* dev_records, int64_t cap_records,
+                               int64_t* counts, void* dev_distinct, int64_t cap_distinct, int64_t* dcounts);
+/* Clears the local state, then merges n records (from any ranks) into it.                           */
+int n1gpu_query_partial_reset(n1gpu_query* q);
+int n1gpu_query_partial_import(n1gpu_query* q, const void* dev_records, int64_t n, const void* dev_distinct, int64_t nd);
+int n1gpu_query_finalize(n1gpu_query* q, n1gpu_result** out);
+
+/* ---- result: what FinalGroup sends downstream ---------------------------------------------------------
+ * Per group: the group-key values and, per aggregate (in the order given to compile), the final value
+ * (algebra ComputeFinal).  A value is a class byte + 64-bit payload; string payloads index the result's
+ * string table.  Downstream contract: algebra/aggregate.go:97-118, execution/project_initial.go:98-144. */
+int64_t n1gpu_result_num_groups(const n1gpu_result* r);
+int n1gpu_result_num_keys(const n1gpu_result* r);
+int n1gpu_result_num_aggregates(const n1gpu_result* r);
+/* key_cls/key_val: [ngroups][nkeys]; agg_cls/agg_val: [ngroups][naggs] (row-major).                 */
+int n1gpu_result_fetch(const n1gpu_result* r, uint8_t* key_cls, int64_t* key_val, uint8_t* agg_cls, int64_t* agg_val);
+int n1gpu_result_string(const n1gpu_result* r, int64_t index, const char** ptr, int64_t* len);
+/* stats[0]=rows scanned (#itemsIn) stats[1]=groups (#itemsOut) stats[2]=scan ns (execTime)
+ * stats[3]=shred+upload ns (servTime) stats[4]=HBM bytes scanned stats[5]=kernel launches          */
+int n1gpu_result_stats(const n1gpu_result* r, int64_t stats[8]);
+int n1gpu_result_free(n1gpu_result* r);
+
+/* ---- plan level: the reference's plan.Visitor / execution.Operator contract ----------------------------
+ * Reference: plan/visitor.go:12-123, plan/op_registry.go:18-29 (plans round-trip through JSON),
+ * execution/build.go:22-45,473-491, execution/execution.go:26-64.
+ * n1gpu_plan_build takes the reference's own plan JSON (what EXPLAIN prints / PREPARE stores), looks for
+ *   Sequence[ PrimaryScan, Fetch, (Parallel(Sequence[Filter?, InitialGroup]) | Filter?, InitialGroup),
+ *             IntermediateGroup, FinalGroup, ...rest ]
+ * and, when eligible, returns an operator handle that replaces that prefix; `rest_index` receives the
+ * index of the first child the caller must still run.  datastore_root is cbq-engine's -datastore dir.  */
+typedef struct n1gpu_operator n1gpu_operator;
+int n1gpu_plan_build(const char* plan_json, const char* datastore_root, n1gpu_operator** out, int* rest_index);
+/* execution.Operator.RunOnce: scans, filters, groups; the result is what FinalGroup would have sent. */
+int n1gpu_operator_run_once(n1gpu_operator* op, n1gpu_result** out);
+int n1gpu_operator_send_stop(n1gpu_operator* op);
+/* The operator as plan JSON with "#stats" (execution/base.go:896-949 marshalTimes).                  */
+int n1gpu_operator_marshal_json(n1gpu_operator* op, char* buf, int64_t cap, int64_t* len);
+/* Rows as the JSON the downstream InitialProject would see: one object per group
+ * {"<alias>": {<key paths>}, "aggregates": {"<agg text>": value}}                                    */
+int n1gpu_result_to_json(const n1gpu_result* r, char* buf, int64_t cap, int64_t* len);
+int n1gpu_operator_free(n1gpu_operator* op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* N1GPU_H */

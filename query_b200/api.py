@@ -1,0 +1,381 @@
+"""Thin Python handles over the C ABI (include/n1gpu.h).  Everything that computes is in libn1gpu.so."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import struct
+
+import numpy as np
+
+from . import _lib
+from ._lib import C_FALSE, C_FLOAT, C_INT, C_MISSING, C_NULL, C_STRING, C_TRUE, check, lib
+
+PATH_SEP = "\x1f"
+
+
+class Missing:
+    """N1QL MISSING as a Python value (distinct from None == NULL)."""
+    _inst = None
+
+    def __new__(cls):
+        if cls._inst is None:
+            cls._inst = super().__new__(cls)
+        return cls._inst
+
+    def __repr__(self):
+        return "MISSING"
+
+    def __bool__(self):
+        return False
+
+
+MISSING = Missing()
+
+
+def _path(p):
+    if isinstance(p, (list, tuple)):
+        return PATH_SEP.join(p)
+    return p.replace(".", PATH_SEP) if PATH_SEP not in p else p
+
+
+def init(device=-1):
+    check(lib().n1gpu_init(int(device)))
+
+
+def launch_count():
+    return int(lib().n1gpu_launch_count())
+
+
+class Table:
+    """A shredded keyspace resident in HBM (n1gpu_table)."""
+
+    def __init__(self, columns=()):
+        self._h = C.c_void_p()
+        check(lib().n1gpu_table_create(C.byref(self._h)))
+        self.columns = []
+        for c in columns:
+            self.add_column(c)
+        self._keep = []
+
+    def add_column(self, path):
+        p = _path(path)
+        idx = check(lib().n1gpu_table_add_column(self._h, p.encode("utf-8")))
+        if p not in self.columns:
+            self.columns.append(p)
+        return idx
+
+    def find_column(self, path):
+        return lib().n1gpu_table_find_column(self._h, _path(path).encode("utf-8"))
+
+    def append_json(self, docs, threads=0):
+        """docs: iterable of JSON texts (str/bytes) in primary-key order, or (buffer, offsets)."""
+        if isinstance(docs, tuple):
+            buf, offsets = docs
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        else:
+            parts = [d.encode("utf-8") if isinstance(d, str) else bytes(d) for d in docs]
+            offsets = np.zeros(len(parts) + 1, dtype=np.int64)
+            if parts:
+                np.cumsum([len(p) for p in parts], out=offsets[1:])
+            buf = b"".join(parts)
+        if isinstance(buf, np.ndarray):
+            bufp = buf.ctypes.data_as(C.c_char_p)
+        else:
+            bufp = C.c_char_p(buf)
+        check(lib().n1gpu_table_append_json(self._h, bufp, offsets.ctypes.data_as(_lib._I64P), len(offsets) - 1, threads))
+        return self
+
+    def load_dir(self, path, threads=0):
+        check(lib().n1gpu_table_load_dir(self._h, path.encode("utf-8"), threads))
+        return self
+
+    def set_column(self, col, payload, tags=None, dictionary=None):
+        """Pre-shredded column: payload int64/float64 (width 8) or uint32 ranks (width 4); tags uint8 or None."""
+        idx = col if isinstance(col, int) else self.find_column(col)
+        a = np.ascontiguousarray(payload)
+        if a.dtype == np.float64 or a.dtype == np.int64 or a.dtype == np.uint64:
+            width = 8
+        elif a.dtype == np.uint32 or a.dtype == np.int32:
+            width = 4
+        else:
+            raise TypeError("payload dtype %s" % a.dtype)
+        t = None
+        if tags is not None:
+            t = np.ascontiguousarray(tags, dtype=np.uint8)
+        blob, offs, nd = None, None, 0
+        if dictionary is not None:
+            enc = [s.encode("utf-8") if isinstance(s, str) else s for s in dictionary]
+            offs = np.zeros(len(enc) + 1, dtype=np.int64)
+            if enc:
+                np.cumsum([len(e) for e in enc], out=offs[1:])
+            blob = b"".join(enc)
+            nd = len(enc)
+        check(lib().n1gpu_table_set_column(
+            self._h, idx, width, a.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p) if t is not None else None,
+            a.shape[0], blob, offs.ctypes.data_as(_lib._I64P) if offs is not None else None, nd))
+        return self
+
+    def peek(self, col):
+        """(payload int64[nrows], tags uint8[nrows]) of a staged column (before seal)."""
+        idx = col if isinstance(col, int) else self.find_column(col)
+        n = self.num_rows
+        pay = np.zeros(n, dtype=np.int64)
+        tg = np.zeros(n, dtype=np.uint8)
+        check(lib().n1gpu_table_column_peek(self._h, idx, pay.ctypes.data_as(_lib._I64P), tg.ctypes.data_as(_lib._U8P), n))
+        return pay, tg
+
+    def dictionary(self, col):
+        idx = col if isinstance(col, int) else self.find_column(col)
+        nd, nb = C.c_int64(), C.c_int64()
+        check(lib().n1gpu_table_dict_export(self._h, idx, None, 0, None, 0, C.byref(nd), C.byref(nb)))
+        blob = C.create_string_buffer(max(1, nb.value))
+        offs = np.zeros(nd.value + 1, dtype=np.int64)
+        check(lib().n1gpu_table_dict_export(self._h, idx, blob, nb.value, offs.ctypes.data_as(_lib._I64P), nd.value + 1,
+                                            C.byref(nd), C.byref(nb)))
+        raw = blob.raw
+        return [raw[offs[i]:offs[i + 1]] for i in range(nd.value)]
+
+    def import_dictionary(self, col, strings):
+        idx = col if isinstance(col, int) else self.find_column(col)
+        enc = [s.encode("utf-8") if isinstance(s, str) else s for s in strings]
+        offs = np.zeros(len(enc) + 1, dtype=np.int64)
+        if enc:
+            np.cumsum([len(e) for e in enc], out=offs[1:])
+        check(lib().n1gpu_table_dict_import(self._h, idx, b"".join(enc), offs.ctypes.data_as(_lib._I64P), len(enc)))
+
+    def stats(self, col):
+        idx = col if isinstance(col, int) else self.find_column(col)
+        s = np.zeros(8, dtype=np.int64)
+        check(lib().n1gpu_table_stats_get(self._h, idx, s.ctypes.data_as(_lib._I64P)))
+        return s
+
+    def set_stats(self, col, stats):
+        idx = col if isinstance(col, int) else self.find_column(col)
+        s = np.ascontiguousarray(stats, dtype=np.int64)
+        check(lib().n1gpu_table_stats_set(self._h, idx, s.ctypes.data_as(_lib._I64P)))
+
+    def seal(self):
+        check(lib().n1gpu_table_seal(self._h))
+        return self
+
+    @property
+    def num_rows(self):
+        return int(lib().n1gpu_table_num_rows(self._h))
+
+    def scan_bytes(self, col):
+        idx = col if isinstance(col, int) else self.find_column(col)
+        return lib().n1gpu_table_column_scan_bytes(self._h, idx)
+
+    def close(self):
+        if self._h:
+            lib().n1gpu_table_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _bits_to_float(b):
+    return struct.unpack("<d", struct.pack("<q", int(b)))[0]
+
+
+class Result:
+    """What FinalGroup sends downstream: per group the key values and the final aggregate values."""
+
+    def __init__(self, handle):
+        self._h = handle
+        L = lib()
+        self.num_groups = int(L.n1gpu_result_num_groups(handle))
+        self.num_keys = L.n1gpu_result_num_keys(handle)
+        self.num_aggregates = L.n1gpu_result_num_aggregates(handle)
+        g, k, a = self.num_groups, self.num_keys, self.num_aggregates
+        kc = np.zeros(max(1, g * k), dtype=np.uint8)
+        kv = np.zeros(max(1, g * k), dtype=np.int64)
+        ac = np.zeros(max(1, g * a), dtype=np.uint8)
+        av = np.zeros(max(1, g * a), dtype=np.int64)
+        check(L.n1gpu_result_fetch(handle, kc.ctypes.data_as(_lib._U8P), kv.ctypes.data_as(_lib._I64P),
+                                   ac.ctypes.data_as(_lib._U8P), av.ctypes.data_as(_lib._I64P)))
+        self.key_cls, self.key_val = kc[:g * k].reshape(g, k), kv[:g * k].reshape(g, k)
+        self.agg_cls, self.agg_val = ac[:g * a].reshape(g, a), av[:g * a].reshape(g, a)
+        st = np.zeros(8, dtype=np.int64)
+        check(L.n1gpu_result_stats(handle, st.ctypes.data_as(_lib._I64P)))
+        self.stats = {"rows": int(st[0]), "groups": int(st[1]), "scan_ns": int(st[2]), "shred_upload_ns": int(st[3]),
+                      "scan_bytes": int(st[4]), "launches": int(st[5])}
+
+    def _value(self, cls, val):
+        if cls == C_MISSING:
+            return MISSING
+        if cls == C_NULL:
+            return None
+        if cls == C_FALSE:
+            return False
+        if cls == C_TRUE:
+            return True
+        if cls == C_INT:
+            return int(val)
+        if cls == C_FLOAT:
+            return _bits_to_float(val)
+        if cls == C_STRING:
+            p, n = C.c_char_p(), C.c_int64()
+            check(lib().n1gpu_result_string(self._h, int(val), C.byref(p), C.byref(n)))
+            return C.string_at(p, n.value).decode("utf-8", "surrogateescape")
+        raise ValueError(cls)
+
+    def rows(self):
+        """[(keys list, aggregates list)] with python values (int / float / str / bool / None / MISSING)."""
+        out = []
+        for g in range(self.num_groups):
+            ks = [self._value(self.key_cls[g, k], self.key_val[g, k]) for k in range(self.num_keys)]
+            ag = [self._value(self.agg_cls[g, a], self.agg_val[g, a]) for a in range(self.num_aggregates)]
+            out.append((ks, ag))
+        return out
+
+    def to_json(self):
+        n = C.c_int64()
+        check(lib().n1gpu_result_to_json(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value + 1)
+        check(lib().n1gpu_result_to_json(self._h, buf, n.value + 1, C.byref(n)))
+        return json.loads(buf.value.decode("utf-8"))
+
+    def close(self):
+        if self._h:
+            lib().n1gpu_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+MODES = {0: "ungrouped", 1: "dense-shared-memory", 2: "hbm-hash-64", 3: "hbm-hash-128"}
+
+
+class Query:
+    """A compiled Filter + InitialGroup/IntermediateGroup/FinalGroup chain (n1gpu_query)."""
+
+    def __init__(self, table, alias, where, group_keys, aggregates):
+        self.table = table
+        self.aggregates = list(aggregates)
+        self.group_keys = list(group_keys)
+        self._h = C.c_void_p()
+        karr = (C.c_char_p * max(1, len(self.group_keys)))(*[k.encode("utf-8") for k in self.group_keys])
+        aarr = (C.c_char_p * max(1, len(self.aggregates)))(*[a.encode("utf-8") for a in self.aggregates])
+        check(lib().n1gpu_query_compile(table._h, alias.encode("utf-8"), where.encode("utf-8") if where else None,
+                                        karr, len(self.group_keys), aarr, len(self.aggregates), C.byref(self._h)))
+
+    def execute(self):
+        r = C.c_void_p()
+        check(lib().n1gpu_query_execute(self._h, C.byref(r)))
+        return Result(r)
+
+    def launch(self):
+        check(lib().n1gpu_query_launch(self._h))
+
+    def collect(self):
+        r = C.c_void_p()
+        check(lib().n1gpu_query_collect(self._h, C.byref(r)))
+        return Result(r)
+
+    def cancel(self):
+        check(lib().n1gpu_query_cancel(self._h))
+
+    def rebind(self, table):
+        check(lib().n1gpu_query_rebind(self._h, table._h))
+        self.table = table
+
+    @property
+    def kernel_source(self):
+        return lib().n1gpu_query_kernel_source(self._h).decode("utf-8")
+
+    @property
+    def info(self):
+        a = np.zeros(8, dtype=np.int64)
+        check(lib().n1gpu_query_info(self._h, a.ctypes.data_as(_lib._I64P)))
+        return {"mode": MODES[int(a[0])], "words": int(a[1]), "registers": int(a[2]), "grid": int(a[3]), "block": int(a[4]),
+                "scan_bytes_per_row": int(a[5]), "static_smem": int(a[6]), "slots": int(a[7])}
+
+    @property
+    def last_scan_ns(self):
+        return int(lib().n1gpu_query_last_scan_ns(self._h))
+
+    # ---- multi-GPU partial state (device pointers as ints) ----
+    def scan_partial(self):
+        check(lib().n1gpu_query_scan_partial(self._h))
+
+    def partial_counts(self):
+        g, d, w = C.c_int64(), C.c_int64(), C.c_int()
+        check(lib().n1gpu_query_partial_counts(self._h, C.byref(g), C.byref(d), C.byref(w)))
+        return g.value, d.value, w.value
+
+    def partial_export(self, nranks, dev_records, cap_records, dev_distinct, cap_distinct):
+        counts = np.zeros(nranks, dtype=np.int64)
+        dcounts = np.zeros(nranks, dtype=np.int64)
+        check(lib().n1gpu_query_partial_export(self._h, nranks, C.c_void_p(dev_records), cap_records,
+                                               counts.ctypes.data_as(_lib._I64P), C.c_void_p(dev_distinct), cap_distinct,
+                                               dcounts.ctypes.data_as(_lib._I64P)))
+        return counts, dcounts
+
+    def partial_reset(self):
+        check(lib().n1gpu_query_partial_reset(self._h))
+
+    def partial_import(self, dev_records, n, dev_distinct, nd):
+        check(lib().n1gpu_query_partial_import(self._h, C.c_void_p(dev_records), n, C.c_void_p(dev_distinct), nd))
+
+    def finalize(self):
+        r = C.c_void_p()
+        check(lib().n1gpu_query_finalize(self._h, C.byref(r)))
+        return Result(r)
+
+    def close(self):
+        if self._h:
+            lib().n1gpu_query_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Operator:
+    """execution.Operator handle built from the reference's plan JSON (n1gpu_plan_build)."""
+
+    def __init__(self, plan_json, datastore_root):
+        if not isinstance(plan_json, str):
+            plan_json = json.dumps(plan_json)
+        self._h = C.c_void_p()
+        rest = C.c_int()
+        check(lib().n1gpu_plan_build(plan_json.encode("utf-8"), datastore_root.encode("utf-8"), C.byref(self._h), C.byref(rest)))
+        self.rest_index = rest.value
+
+    def run_once(self):
+        r = C.c_void_p()
+        check(lib().n1gpu_operator_run_once(self._h, C.byref(r)))
+        return Result(r)
+
+    def send_stop(self):
+        check(lib().n1gpu_operator_send_stop(self._h))
+
+    def marshal_json(self):
+        n = C.c_int64()
+        check(lib().n1gpu_operator_marshal_json(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value + 1)
+        check(lib().n1gpu_operator_marshal_json(self._h, buf, n.value + 1, C.byref(n)))
+        return json.loads(buf.value.decode("utf-8"))
+
+    def close(self):
+        if self._h:
+            lib().n1gpu_operator_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

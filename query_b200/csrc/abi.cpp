@@ -1,0 +1,328 @@
+// abi.cpp — the extern "C" surface declared in include/n1gpu.h.  Exceptions never cross it.
+#include <cstring>
+#include <mutex>
+
+#include "execution.hpp"
+#include "query.hpp"
+#include "table.hpp"
+
+using namespace n1;
+
+struct n1gpu_table { Table t; };
+struct n1gpu_query { std::unique_ptr<Query> q; };
+struct n1gpu_result { std::unique_ptr<Result> r; };
+struct n1gpu_operator { std::unique_ptr<execution::GpuGroupAggregate> op; };
+
+static thread_local std::string g_last_error;
+
+template <class F> static int guard(F&& f) {
+    try {
+        f();
+        return N1GPU_OK;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return N1GPU_E_NOMEM;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return N1GPU_E_INVALID;
+    }
+}
+#define REQUIRE(p) do { if (!(p)) N1_THROW(N1GPU_E_INVALID, "null argument: %s", #p); } while (0)
+
+extern "C" {
+
+int n1gpu_init(int device) {
+    return guard([&] {
+        int n = 0;
+        CK(cudaGetDeviceCount(&n));
+        if (n == 0) N1_THROW(N1GPU_E_CUDA, "no CUDA device: libn1gpu has no CPU fallback");
+        if (device >= 0) CK(cudaSetDevice(device));
+        CK(cudaFree(0));
+    });
+}
+int n1gpu_shutdown(void) { return N1GPU_OK; }
+const char* n1gpu_last_error(void) { return g_last_error.c_str(); }
+const char* n1gpu_version(void) { return "n1gpu 0.1 (sm_100a)"; }
+uint64_t n1gpu_launch_count(void) { return (uint64_t)g_launches.load(); }
+
+// ---- table ----------------------------------------------------------------------------------------------
+int n1gpu_table_create(n1gpu_table** out) {
+    return guard([&] { REQUIRE(out); *out = new n1gpu_table(); });
+}
+int n1gpu_table_add_column(n1gpu_table* t, const char* path) {
+    int idx = -1;
+    int rc = guard([&] { REQUIRE(t); REQUIRE(path); idx = t->t.add_column(path); });
+    return rc == N1GPU_OK ? idx : rc;
+}
+int n1gpu_table_find_column(const n1gpu_table* t, const char* path) {
+    if (!t || !path) return -1;
+    return t->t.find_column(path);
+}
+int n1gpu_table_append_json(n1gpu_table* t, const char* buf, const int64_t* offsets, int64_t ndocs, int threads) {
+    return guard([&] { REQUIRE(t); REQUIRE(offsets); t->t.append_json(buf, (const i64*)offsets, ndocs, threads); });
+}
+int n1gpu_table_load_dir(n1gpu_table* t, const char* dir, int threads) {
+    return guard([&] { REQUIRE(t); REQUIRE(dir); t->t.load_dir(dir, threads); });
+}
+int n1gpu_table_set_column(n1gpu_table* t, int col, int width, const void* payload, const uint8_t* tags, int64_t nrows,
+                           const char* dict_blob, const int64_t* dict_offsets, int64_t ndict) {
+    return guard([&] { REQUIRE(t); REQUIRE(payload || nrows == 0); t->t.set_column(col, width, payload, tags, nrows, dict_blob, (const i64*)dict_offsets, ndict); });
+}
+int n1gpu_table_seal(n1gpu_table* t) {
+    return guard([&] { REQUIRE(t); t->t.seal(); });
+}
+int64_t n1gpu_table_num_rows(const n1gpu_table* t) { return t ? t->t.nrows : -1; }
+int n1gpu_table_num_columns(const n1gpu_table* t) { return t ? (int)t->t.cols.size() : -1; }
+int n1gpu_table_column_scan_bytes(const n1gpu_table* t, int col) {
+    if (!t || col < 0 || col >= (int)t->t.cols.size() || !t->t.sealed) return -1;
+    return t->t.scan_bytes(col);
+}
+int n1gpu_table_dict_export(n1gpu_table* t, int col, char* blob, int64_t blob_cap, int64_t* offsets, int64_t offsets_cap,
+                            int64_t* ndict, int64_t* blob_bytes) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(ndict); REQUIRE(blob_bytes);
+        if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
+        if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "dictionary exchange happens before seal");
+        t->t.build_dictionary(col);
+        const auto& d = t->t.cols[col].dict;
+        i64 bytes = 0;
+        for (auto& s : d) bytes += (i64)s.size();
+        *ndict = (int64_t)d.size();
+        *blob_bytes = bytes;
+        if (!blob || !offsets) return;
+        if (blob_cap < bytes || offsets_cap < (i64)d.size() + 1) N1_THROW(N1GPU_E_INVALID, "dictionary export buffers too small");
+        i64 at = 0;
+        for (size_t i = 0; i < d.size(); ++i) { offsets[i] = at; memcpy(blob + at, d[i].data(), d[i].size()); at += (i64)d[i].size(); }
+        offsets[d.size()] = at;
+    });
+}
+int n1gpu_table_dict_import(n1gpu_table* t, int col, const char* blob, const int64_t* offsets, int64_t ndict) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(offsets);
+        if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
+        if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "dictionary exchange happens before seal");
+        t->t.build_dictionary(col);
+        Column& c = t->t.cols[col];
+        std::vector<std::string> global;
+        global.reserve((size_t)ndict);
+        for (i64 i = 0; i < ndict; ++i) global.emplace_back(blob + offsets[i], blob + offsets[i + 1]);
+        for (size_t i = 1; i < global.size(); ++i)
+            if (!(global[i - 1] < global[i])) N1_THROW(N1GPU_E_INVALID, "global dictionary must be sorted bytewise and unique");
+        std::vector<u32> remap(c.dict.size());
+        for (size_t i = 0; i < c.dict.size(); ++i) {
+            auto it = std::lower_bound(global.begin(), global.end(), c.dict[i]);
+            if (it == global.end() || *it != c.dict[i]) N1_THROW(N1GPU_E_INVALID, "global dictionary lacks a local string");
+            remap[i] = (u32)(it - global.begin());
+        }
+        for (size_t r = 0; r < c.tags.size(); ++r) if (c.tags[r] == C_STRING) c.payload[r] = remap[(size_t)c.payload[r]];
+        c.dict.swap(global);
+        c.dict_global = true;
+    });
+}
+int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(stats);
+        if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
+        Column& c = t->t.cols[col];
+        ColumnStats st = c.stats;
+        if (!t->t.sealed) {  // compute from staging
+            st = ColumnStats();
+            for (size_t i = 0; i < c.tags.size(); ++i) {
+                u8 tg = c.tags[i];
+                if (tg == C_FLOAT) { double d; memcpy(&d, &c.payload[i], 8); if (f_is_int(d)) tg = C_INT; else st.has_float = true; }
+                if (tg == C_INT) {
+                    i64 v = c.tags[i] == C_INT ? c.payload[i] : go_i64(*(double*)&c.payload[i]);
+                    if (!st.has_int) { st.int_min = st.int_max = v; st.has_int = true; }
+                    else { st.int_min = std::min(st.int_min, v); st.int_max = std::max(st.int_max, v); }
+                }
+                st.class_mask |= bit(tg);
+            }
+            st.ndict = (i64)c.dict.size();
+        }
+        stats[0] = st.class_mask; stats[1] = st.has_int; stats[2] = st.int_min; stats[3] = st.int_max;
+        stats[4] = st.has_float; stats[5] = st.ndict; stats[6] = st.empty_rank; stats[7] = 0;
+    });
+}
+int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(stats);
+        if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
+        if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "statistics exchange happens before seal");
+        Column& c = t->t.cols[col];
+        c.stats.class_mask = (u32)stats[0]; c.stats.has_int = stats[1] != 0; c.stats.int_min = stats[2]; c.stats.int_max = stats[3];
+        c.stats.has_float = stats[4] != 0; c.stats.ndict = stats[5];
+        c.stats.empty_rank = (!c.dict.empty() && c.dict[0].empty()) ? 0 : -1;
+        c.stats_forced = true;
+    });
+}
+int n1gpu_table_column_peek(n1gpu_table* t, int col, int64_t* payload, uint8_t* tags, int64_t nrows) {
+    return guard([&] {
+        REQUIRE(t);
+        if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
+        if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "staged rows are released at seal");
+        t->t.build_dictionary(col);
+        Column& c = t->t.cols[col];
+        if (nrows != (i64)c.tags.size()) N1_THROW(N1GPU_E_INVALID, "column has %lld rows", (long long)c.tags.size());
+        if (payload) memcpy(payload, c.payload.data(), (size_t)nrows * 8);
+        if (tags) memcpy(tags, c.tags.data(), (size_t)nrows);
+    });
+}
+int n1gpu_table_free(n1gpu_table* t) { delete t; return N1GPU_OK; }
+
+// ---- query ------------------------------------------------------------------------------------------------
+int n1gpu_query_compile(n1gpu_table* t, const char* alias, const char* where, const char* const* group_keys, int nkeys,
+                        const char* const* aggregates, int naggs, n1gpu_query** out) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(alias); REQUIRE(out);
+        if (nkeys < 0 || naggs < 0) N1_THROW(N1GPU_E_INVALID, "negative count");
+        std::vector<std::string> keys, aggs;
+        for (int i = 0; i < nkeys; ++i) { REQUIRE(group_keys && group_keys[i]); keys.push_back(group_keys[i]); }
+        for (int i = 0; i < naggs; ++i) { REQUIRE(aggregates && aggregates[i]); aggs.push_back(aggregates[i]); }
+        auto q = Query::compile(&t->t, alias, where, keys, aggs);
+        *out = new n1gpu_query{std::move(q)};
+    });
+}
+int n1gpu_query_execute(n1gpu_query* q, n1gpu_result** out) {
+    return guard([&] {
+        REQUIRE(q); REQUIRE(out);
+        q->q->scan_blocking();
+        *out = new n1gpu_result{q->q->finalize()};
+    });
+}
+int n1gpu_query_launch(n1gpu_query* q) {
+    return guard([&] { REQUIRE(q); q->q->launch_scan(); });
+}
+int n1gpu_query_collect(n1gpu_query* q, n1gpu_result** out) {
+    return guard([&] {
+        REQUIRE(q); REQUIRE(out);
+        if (!q->q->wait_scan()) q->q->scan_blocking();  // a table was grown: rerun
+        *out = new n1gpu_result{q->q->finalize()};
+    });
+}
+int n1gpu_query_cancel(n1gpu_query* q) {
+    if (!q) return N1GPU_E_INVALID;
+    q->q->cancelled.store(true);
+    return N1GPU_OK;
+}
+const char* n1gpu_query_kernel_source(const n1gpu_query* q) { return q ? q->q->kp.source.c_str() : ""; }
+int n1gpu_query_info(const n1gpu_query* q, int64_t info[8]) {
+    return guard([&] {
+        REQUIRE(q); REQUIRE(info);
+        const Query& Q = *q->q;
+        info[0] = Q.kp.mode; info[1] = Q.ops.n; info[2] = Q.kernel ? Q.kernel->regs : 0; info[3] = Q.grid; info[4] = 256;
+        info[5] = Q.kp.scan_bytes_per_row; info[6] = Q.kernel ? Q.kernel->static_smem : 0;
+        info[7] = Q.kp.mode == MODE_DENSE ? Q.kp.dense_slots : (i64)Q.cap;
+    });
+}
+int64_t n1gpu_query_last_scan_ns(const n1gpu_query* q) { return q ? (int64_t)(q->q->last_scan_ms * 1e6) : -1; }
+int n1gpu_query_rebind(n1gpu_query* q, n1gpu_table* t) {
+    return guard([&] { REQUIRE(q); REQUIRE(t); q->q->rebind(&t->t); });
+}
+int n1gpu_query_free(n1gpu_query* q) { delete q; return N1GPU_OK; }
+
+// ---- multi-GPU partial state ----------------------------------------------------------------------------------
+int n1gpu_query_scan_partial(n1gpu_query* q) {
+    return guard([&] { REQUIRE(q); q->q->scan_blocking(); });
+}
+int n1gpu_query_partial_counts(n1gpu_query* q, int64_t* ngroups, int64_t* ndistinct, int* record_words) {
+    return guard([&] {
+        REQUIRE(q); REQUIRE(ngroups); REQUIRE(ndistinct); REQUIRE(record_words);
+        i64 g = 0, d = 0;
+        q->q->partial_counts(&g, &d);
+        *ngroups = g; *ndistinct = d; *record_words = 2 + q->q->ops.n;
+    });
+}
+int n1gpu_query_partial_export(n1gpu_query* q, int nranks, void* dev_records, int64_t cap_records, int64_t* counts,
+                               void* dev_distinct, int64_t cap_distinct, int64_t* dcounts) {
+    return guard([&] {
+        REQUIRE(q); REQUIRE(counts); REQUIRE(dcounts);
+        if (nranks < 1) N1_THROW(N1GPU_E_INVALID, "nranks must be >= 1");
+        q->q->partial_export(nranks, dev_records, cap_records, (i64*)counts, dev_distinct, cap_distinct, (i64*)dcounts);
+    });
+}
+int n1gpu_query_partial_reset(n1gpu_query* q) {
+    return guard([&] { REQUIRE(q); q->q->partial_reset(); });
+}
+int n1gpu_query_partial_import(n1gpu_query* q, const void* dev_records, int64_t n, const void* dev_distinct, int64_t nd) {
+    return guard([&] { REQUIRE(q); q->q->partial_import(dev_records, n, dev_distinct, nd); });
+}
+int n1gpu_query_finalize(n1gpu_query* q, n1gpu_result** out) {
+    return guard([&] { REQUIRE(q); REQUIRE(out); *out = new n1gpu_result{q->q->finalize()}; });
+}
+
+// ---- result ------------------------------------------------------------------------------------------------------
+int64_t n1gpu_result_num_groups(const n1gpu_result* r) { return r ? r->r->ngroups : -1; }
+int n1gpu_result_num_keys(const n1gpu_result* r) { return r ? r->r->nkeys : -1; }
+int n1gpu_result_num_aggregates(const n1gpu_result* r) { return r ? r->r->naggs : -1; }
+int n1gpu_result_fetch(const n1gpu_result* r, uint8_t* key_cls, int64_t* key_val, uint8_t* agg_cls, int64_t* agg_val) {
+    return guard([&] {
+        REQUIRE(r);
+        Result& R = *r->r;
+        R.strings.clear();
+        auto put = [&](const HValue& v, uint8_t* cls, int64_t* val, size_t i) {
+            if (cls) cls[i] = v.cls;
+            if (val) {
+                if (v.cls == C_STRING) { val[i] = (int64_t)R.strings.size(); R.strings.push_back(v.s); }
+                else val[i] = v.bits;
+            }
+        };
+        for (size_t i = 0; i < R.keys.size(); ++i) put(R.keys[i], key_cls, key_val, i);
+        for (size_t i = 0; i < R.aggs.size(); ++i) put(R.aggs[i], agg_cls, agg_val, i);
+    });
+}
+int n1gpu_result_string(const n1gpu_result* r, int64_t index, const char** ptr, int64_t* len) {
+    return guard([&] {
+        REQUIRE(r); REQUIRE(ptr); REQUIRE(len);
+        if (index < 0 || index >= (i64)r->r->strings.size()) N1_THROW(N1GPU_E_INVALID, "string index out of range");
+        *ptr = r->r->strings[(size_t)index].data();
+        *len = (int64_t)r->r->strings[(size_t)index].size();
+    });
+}
+int n1gpu_result_stats(const n1gpu_result* r, int64_t stats[8]) {
+    return guard([&] { REQUIRE(r); REQUIRE(stats); for (int i = 0; i < 8; ++i) stats[i] = r->r->stats[i]; });
+}
+int n1gpu_result_free(n1gpu_result* r) { delete r; return N1GPU_OK; }
+
+// ---- plan level -----------------------------------------------------------------------------------------------------
+int n1gpu_plan_build(const char* plan_json, const char* datastore_root, n1gpu_operator** out, int* rest_index) {
+    return guard([&] {
+        REQUIRE(plan_json); REQUIRE(datastore_root); REQUIRE(out);
+        int rest = 0;
+        auto op = execution::Build(plan_json, datastore_root, &rest);
+        if (rest_index) *rest_index = rest;
+        *out = new n1gpu_operator{std::move(op)};
+    });
+}
+int n1gpu_operator_run_once(n1gpu_operator* op, n1gpu_result** out) {
+    return guard([&] { REQUIRE(op); REQUIRE(out); *out = new n1gpu_result{op->op->RunOnce()}; });
+}
+int n1gpu_operator_send_stop(n1gpu_operator* op) {
+    if (!op) return N1GPU_E_INVALID;
+    op->op->SendStop();
+    return N1GPU_OK;
+}
+static int copy_out(const std::string& s, char* buf, int64_t cap, int64_t* len) {
+    if (len) *len = (int64_t)s.size();
+    if (buf && cap > 0) {
+        size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+        memcpy(buf, s.data(), n);
+        buf[n] = '\0';
+    }
+    return N1GPU_OK;
+}
+int n1gpu_operator_marshal_json(n1gpu_operator* op, char* buf, int64_t cap, int64_t* len) {
+    std::string s;
+    int rc = guard([&] { REQUIRE(op); s = op->op->MarshalJSON(); });
+    return rc == N1GPU_OK ? copy_out(s, buf, cap, len) : rc;
+}
+int n1gpu_result_to_json(const n1gpu_result* r, char* buf, int64_t cap, int64_t* len) {
+    std::string s;
+    int rc = guard([&] { REQUIRE(r); s = execution::ResultToJSON(*r->r); });
+    return rc == N1GPU_OK ? copy_out(s, buf, cap, len) : rc;
+}
+int n1gpu_operator_free(n1gpu_operator* op) { delete op; return N1GPU_OK; }
+
+}  // extern "C"

@@ -1,0 +1,515 @@
+// codegen.cpp — emits the specialised scan kernel for one Filter + Group chain.
+//
+// The kernel is straight-line CUDA over the hand-written device library n1ql_device.cuh: per thread and
+// iteration 4 consecutive rows are fetched with one 256-bit (8-byte columns), 128-bit (4-byte dictionary
+// ranks) or 32-bit (class bytes) coalesced load per referenced column, the Filter condition is evaluated
+// with N1QL's 4-valued logic, a warp ballot of the selection skips the aggregation when no lane passes,
+// and the aggregates are folded into
+//   MODE_UNGROUPED  per-thread registers -> deterministic block reduction -> per-block partials
+//   MODE_DENSE      a shared-memory table indexed by the bit-packed group key, flushed to HBM
+//   MODE_HASH64/128 an HBM open-addressing table claimed with 64-/128-bit CAS
+// Static type analysis (expr.cpp) and column statistics decide which accumulator words exist at all.
+#include "codegen.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+namespace n1 {
+
+namespace {
+
+struct StrCtx {
+    int dict_col = -1;
+    std::vector<std::string> locals;  // sorted constants when no dictionary is involved
+};
+
+std::string lit_i64(i64 v) { return strf("((i64)0x%016llxULL)", (unsigned long long)(u64)v); }
+const char* op_name(int op) {
+    static const char* n[] = {"OP_ADD_U64", "OP_ADD_F64", "OP_MIN_I64", "OP_MAX_I64", "OP_MIN_U64", "OP_MAX_U64", "OP_OR_U64"};
+    return n[op];
+}
+const char* cls_name(int c) {
+    static const char* n[] = {"C_MISSING", "C_NULL", "C_FALSE", "C_TRUE", "C_INT", "C_FLOAT", "C_STRING", "C_OTHER"};
+    return n[c];
+}
+
+struct Gen {
+    const Table& t;
+    std::string body;
+    std::string decls;  // column Val declarations, hoisted to the top of the row body
+    int tmp = 0;
+    std::string ind = "                ";
+    std::map<int, std::string> colvar;  // per-row cache of column Val variables
+    explicit Gen(const Table& tt) : t(tt) {}
+
+    std::string nv(const char* p = "v") { return strf("%s%d", p, tmp++); }
+    void line(const std::string& s) { body += ind + s + "\n"; }
+
+    i64 const_code(const std::string& s, const StrCtx* cx) {
+        if (cx && cx->dict_col >= 0) {
+            const auto& d = t.cols[cx->dict_col].dict;
+            auto it = std::lower_bound(d.begin(), d.end(), s);
+            i64 lb = it - d.begin();
+            if (it != d.end() && *it == s) return 2 * lb;
+            return 2 * lb - 1;  // absent: sorts strictly between its neighbours, equals nothing
+        }
+        if (cx) {
+            auto it = std::lower_bound(cx->locals.begin(), cx->locals.end(), s);
+            return 2 * (i64)(it - cx->locals.begin()) + 2;
+        }
+        return s.empty() ? 0 : 2;
+    }
+    // 2*rank of "" for the truth value of a string-capable operand (-1: cannot be empty)
+    i64 empty2_of(const Expr& e) {
+        if (!(e.ti.mask & bit(C_STRING))) return -1;
+        if (e.kind == EK::CONST) return 0;
+        if (e.ti.plain_col) { i64 r = t.cols[e.ti.dict_col].stats.empty_rank; return r < 0 ? -1 : 2 * r; }
+        N1_THROW(N1GPU_E_INELIGIBLE, "truth value of a computed string");
+    }
+
+    std::string colval(int c) {
+        auto it = colvar.find(c);
+        if (it != colvar.end()) return it->second;
+        const Column& col = t.cols[c];
+        u32 mask = col.stats.class_mask ? col.stats.class_mask : bit(C_MISSING);
+        std::string cls;
+        if (col.stats.uniform_tag() || col.stats.class_mask == 0) {
+            int only = 0;
+            for (int k = 0; k < 8; ++k) if (mask & bit(k)) only = k;
+            cls = cls_name(only);
+        } else {
+            // normalise the tag to the classes that occur so the compiler can prune the others
+            std::vector<int> cs;
+            for (int k = 0; k < 8; ++k) if (mask & bit(k)) cs.push_back(k);
+            std::string e = cls_name(cs.back());
+            for (int k = (int)cs.size() - 2; k >= 0; --k) e = strf("(t%d[j] == %s ? %s : %s)", c, cls_name(cs[k]), cls_name(cs[k]), e.c_str());
+            cls = e;
+        }
+        std::string pay;
+        bool has_str = mask & bit(C_STRING);
+        if (col.width == 8) {
+            if (has_str) pay = strf("(t%d[j] == C_STRING ? c%d[j] * 2 : c%d[j])", c, c, c);
+            else pay = strf("c%d[j]", c);
+        } else if (col.width == 4) pay = strf("((i64)c%d[j] * 2)", c);
+        else pay = "0";
+        std::string v = nv("col");
+        decls += strf("            const Val %s = mkv(%s, %s);\n", v.c_str(), cls.c_str(), pay.c_str());
+        colvar[c] = v;
+        return v;
+    }
+
+    StrCtx make_ctx(const Expr& e) {
+        StrCtx cx;
+        cx.dict_col = e.ti.dict_col;
+        if (cx.dict_col < 0) {
+            std::vector<const Expr*> flat;
+            for (auto& o : e.ops) {
+                if (o->kind == EK::ARRAY) for (auto& el : o->ops) flat.push_back(el.get()); else flat.push_back(o.get());
+            }
+            for (auto* x : flat) if (x->kind == EK::CONST && x->cval.cls == C_STRING) cx.locals.push_back(x->cval.s);
+            std::sort(cx.locals.begin(), cx.locals.end());
+            cx.locals.erase(std::unique(cx.locals.begin(), cx.locals.end()), cx.locals.end());
+        }
+        return cx;
+    }
+
+    std::string emit(const Expr& e, const StrCtx* cx) {
+        switch (e.kind) {
+            case EK::CONST: {
+                std::string v = nv();
+                const HValue& c = e.cval;
+                if (c.cls == C_STRING) line(strf("const Val %s = mkv(C_STRING, %lldLL);", v.c_str(), (long long)const_code(c.s, cx)));
+                else if (c.cls == C_INT || c.cls == C_FLOAT) line(strf("const Val %s = mkv(%s, %s);", v.c_str(), cls_name(c.cls), lit_i64(c.bits).c_str()));
+                else line(strf("const Val %s = mkv(%s, 0);", v.c_str(), cls_name(c.cls)));
+                return v;
+            }
+            case EK::FIELD: return colval(e.col);
+            case EK::ADD: case EK::MULT: {
+                std::string acc = nv("acc"), m = nv("m"), n = nv("n"), r = nv();
+                std::vector<std::string> args;
+                for (auto& o : e.ops) args.push_back(emit(*o, nullptr));
+                line(strf("Val %s = mkint(%d); bool %s = false, %s = false;", acc.c_str(), e.kind == EK::ADD ? 0 : 1, m.c_str(), n.c_str()));
+                for (auto& a : args) line(strf("%s(%s, %s, %s, %s);", e.kind == EK::ADD ? "add_arg" : "mult_arg", a.c_str(), acc.c_str(), m.c_str(), n.c_str()));
+                line(strf("const Val %s = arith_fin(%s, %s, %s);", r.c_str(), acc.c_str(), m.c_str(), n.c_str()));
+                return r;
+            }
+            case EK::SUB: case EK::DIV: case EK::MOD: {
+                std::string a = emit(*e.ops[0], nullptr), b = emit(*e.ops[1], nullptr), r = nv();
+                const char* f = e.kind == EK::SUB ? "v_sub" : (e.kind == EK::DIV ? "v_div" : "v_mod");
+                line(strf("const Val %s = %s(%s, %s);", r.c_str(), f, a.c_str(), b.c_str()));
+                return r;
+            }
+            case EK::NEG: {
+                std::string a = emit(*e.ops[0], nullptr), r = nv();
+                line(strf("const Val %s = v_neg(%s);", r.c_str(), a.c_str()));
+                return r;
+            }
+            case EK::EQ: case EK::LT: case EK::LE: {
+                StrCtx c2 = make_ctx(e);
+                std::string a = emit(*e.ops[0], &c2), b = emit(*e.ops[1], &c2), r = nv();
+                const char* f = e.kind == EK::EQ ? "v_eq" : (e.kind == EK::LT ? "v_lt" : "v_le");
+                line(strf("const Val %s = %s(%s, %s);", r.c_str(), f, a.c_str(), b.c_str()));
+                return r;
+            }
+            case EK::BETWEEN: {
+                StrCtx c2 = make_ctx(e);
+                std::string x = emit(*e.ops[0], &c2), lo = emit(*e.ops[1], &c2), hi = emit(*e.ops[2], &c2), r = nv();
+                line(strf("const Val %s = v_between(%s, %s, %s);", r.c_str(), x.c_str(), lo.c_str(), hi.c_str()));
+                return r;
+            }
+            case EK::IN: {
+                StrCtx c2 = make_ctx(e);
+                std::string x = emit(*e.ops[0], &c2);
+                std::string h = nv("h"), m = nv("m"), n = nv("n"), r = nv();
+                line(strf("bool %s = false, %s = false, %s = false;", h.c_str(), m.c_str(), n.c_str()));
+                for (auto& el : e.ops[1]->ops) {
+                    std::string ev = emit(*el, &c2);
+                    line(strf("in_arg(%s, %s, %s, %s, %s);", x.c_str(), ev.c_str(), h.c_str(), m.c_str(), n.c_str()));
+                }
+                line(strf("const Val %s = in_fin(%s, %s, %s, %s);", r.c_str(), x.c_str(), h.c_str(), m.c_str(), n.c_str()));
+                return r;
+            }
+            case EK::AND: case EK::OR: {
+                std::string f = nv("f"), m = nv("m"), n = nv("n"), r = nv();
+                std::vector<std::pair<std::string, i64>> args;
+                for (auto& o : e.ops) { std::string a = emit(*o, nullptr); args.emplace_back(a, empty2_of(*o)); }
+                line(strf("bool %s = false, %s = false, %s = false;", f.c_str(), m.c_str(), n.c_str()));
+                for (auto& a : args)
+                    line(strf("%s(%s, %lldLL, %s, %s, %s);", e.kind == EK::AND ? "and_arg" : "or_arg", a.first.c_str(), (long long)a.second, f.c_str(), m.c_str(), n.c_str()));
+                line(strf("const Val %s = %s(%s, %s, %s);", r.c_str(), e.kind == EK::AND ? "and_fin" : "or_fin", f.c_str(), m.c_str(), n.c_str()));
+                return r;
+            }
+            case EK::NOT: {
+                std::string a = emit(*e.ops[0], nullptr), r = nv();
+                line(strf("const Val %s = v_not(%s, %lldLL);", r.c_str(), a.c_str(), (long long)empty2_of(*e.ops[0])));
+                return r;
+            }
+            case EK::IS_NULL: case EK::IS_NOT_NULL: case EK::IS_MISSING: case EK::IS_NOT_MISSING: case EK::IS_VALUED: case EK::IS_NOT_VALUED: {
+                std::string a = emit(*e.ops[0], nullptr), r = nv();
+                const char* f = e.kind == EK::IS_NULL ? "v_is_null" : e.kind == EK::IS_NOT_NULL ? "v_is_not_null" : e.kind == EK::IS_MISSING ? "v_is_missing"
+                              : e.kind == EK::IS_NOT_MISSING ? "v_is_not_missing" : e.kind == EK::IS_VALUED ? "v_is_valued" : "v_is_not_valued";
+                line(strf("const Val %s = %s(%s);", r.c_str(), f, a.c_str()));
+                return r;
+            }
+            case EK::ARRAY: N1_THROW(N1GPU_E_INELIGIBLE, "array value outside IN");
+            case EK::AGG: N1_THROW(N1GPU_E_INELIGIBLE, "nested aggregate");
+            case EK::IDENT: N1_THROW(N1GPU_E_INELIGIBLE, "bare identifier");
+        }
+        N1_THROW(N1GPU_E_INVALID, "unhandled expression kind");
+    }
+};
+
+// Packed component for a value with TypeInfo ti (after canon_num when it is not a plain column).
+PackComp make_comp(const Table& t, const Expr& e, const char* what) {
+    PackComp pc;
+    TypeInfo ti = e.ti;
+    if (ti.mask & bit(C_STRING)) {
+        if (!ti.plain_col) N1_THROW(N1GPU_E_INELIGIBLE, "%s over a constant or computed string", what);
+        pc.dict_col = ti.dict_col;
+    }
+    if (!ti.plain_col && (ti.mask & bit(C_FLOAT))) { ti.mask |= bit(C_INT); ti.ranged = false; }  // canon_num
+    pc.mask = ti.mask;
+    for (int k = 0; k < 7; ++k) if (ti.mask & bit(k)) pc.classes.push_back(k);
+    pc.cbits = bits_for(pc.classes.size());
+    int pb = 0;
+    if (ti.mask & bit(C_INT)) {
+        if (ti.ranged && (u64)ti.hi - (u64)ti.lo < ((u64)1 << 62)) {
+            pc.biased = true; pc.bias = ti.lo;
+            pb = std::max(pb, bits_for((u64)ti.hi - (u64)ti.lo + 1));
+        } else pb = 64;
+    }
+    if (ti.mask & bit(C_FLOAT)) pb = 64;
+    if (ti.mask & bit(C_STRING)) pb = std::max(pb, bits_for((u64)std::max<i64>(1, t.cols[pc.dict_col].stats.ndict)));
+    pc.pbits = pb;
+    return pc;
+}
+
+// Emits code packing Val `v` as component pc into (lo,hi,pos) variables.
+void emit_pack(Gen& g, const PackComp& pc, const std::string& v, const char* lo, const char* hi, const char* pos) {
+    if (pc.cbits) {
+        std::string e = strf("%d", (int)pc.classes.size() - 1);
+        for (int k = (int)pc.classes.size() - 2; k >= 0; --k) e = strf("(%s.c == %s ? %d : %s)", v.c_str(), cls_name(pc.classes[k]), k, e.c_str());
+        g.line(strf("pack_bits(%s, %s, %s, (u64)%s, %d);", lo, hi, pos, e.c_str(), pc.cbits));
+    }
+    if (pc.pbits) {
+        std::string e = "0ULL";
+        if (pc.mask & bit(C_STRING)) e = strf("(%s.c == C_STRING ? ((u64)%s.b >> 1) : %s)", v.c_str(), v.c_str(), e.c_str());
+        if (pc.mask & bit(C_FLOAT)) e = strf("(%s.c == C_FLOAT ? (u64)%s.b : %s)", v.c_str(), v.c_str(), e.c_str());
+        if (pc.mask & bit(C_INT)) {
+            std::string iv = pc.biased ? strf("((u64)%s.b - (u64)%s)", v.c_str(), lit_i64(pc.bias).c_str()) : strf("(u64)%s.b", v.c_str());
+            e = strf("(%s.c == C_INT ? %s : %s)", v.c_str(), iv.c_str(), e.c_str());
+        }
+        g.line(strf("pack_bits(%s, %s, %s, %s, %d);", lo, hi, pos, e.c_str(), pc.pbits));
+    }
+}
+
+double comp_domain(const Table& t, const PackComp& pc) {
+    double d = 0;
+    for (int c : pc.classes) {
+        if (c == C_INT) d += pc.biased ? std::ldexp(1.0, std::min(pc.pbits, 62)) : 1e18;
+        else if (c == C_FLOAT) d += 1e18;
+        else if (c == C_STRING) d += (double)std::max<i64>(1, t.cols[pc.dict_col].stats.ndict);
+        else d += 1;
+    }
+    return d;
+}
+
+}  // namespace
+
+KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<ExprP>& keys,
+                           const std::vector<ExprP>& aggs, const std::vector<std::string>& agg_texts,
+                           double total_rows_bound) {
+    KernelPlan kp;
+    // ---- group key layout ------------------------------------------------------------------------------
+    double est = 1;
+    for (auto& k : keys) {
+        kp.keys.push_back(make_comp(t, *k, "GROUP BY"));
+        kp.key_bits += kp.keys.back().bits();
+        est *= comp_domain(t, kp.keys.back());
+    }
+    auto add_word = [&](int op) { kp.word_ops.push_back(op); return (int)kp.word_ops.size() - 1; };
+    int w_rows = -1;
+    if (!keys.empty()) w_rows = add_word(OP_ADD_U64);  // word 0: rows per group (group existence)
+
+    // ---- aggregate layout --------------------------------------------------------------------------------
+    for (size_t a = 0; a < aggs.size(); ++a) {
+        const Expr& e = *aggs[a];
+        if (e.kind != EK::AGG) N1_THROW(N1GPU_E_INELIGIBLE, "%s is not an aggregate", agg_texts[a].c_str());
+        AggPlan ap;
+        ap.kind = e.agg; ap.distinct = e.distinct; ap.star = e.star; ap.text = agg_texts[a];
+        const Expr* opnd = e.star ? nullptr : e.ops[0].get();
+        if (opnd && opnd->kind == EK::AGG) N1_THROW(N1GPU_E_INELIGIBLE, "nested aggregate");
+        ap.opmask = opnd ? opnd->ti.mask : 0;
+        if (opnd && (ap.opmask & bit(C_STRING)) && opnd->ti.plain_col) ap.dict_col = opnd->ti.dict_col;
+        if (ap.distinct) {
+            ap.distinct_id = kp.ndistinct++;
+            ap.dcomp = make_comp(t, *opnd, "DISTINCT");
+        } else if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) {
+            if (ap.star && w_rows >= 0) ap.w_cnt = w_rows; else ap.w_cnt = add_word(OP_ADD_U64);
+        } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
+            if (ap.opmask & bit(C_INT)) {
+                const TypeInfo& ti = opnd->ti;
+                bool exact1 = false;
+                if (ti.ranged) {
+                    double mx = std::max(std::fabs((double)ti.lo), std::fabs((double)ti.hi));
+                    exact1 = mx * std::max(1.0, total_rows_bound) < 2.3e18;  // < 2^61: no int64 overflow possible
+                }
+                if (exact1) ap.w_isum = add_word(OP_ADD_U64);
+                else { ap.w_ilo = add_word(OP_ADD_U64); ap.w_ihi = add_word(OP_ADD_U64); }
+                bool can_neg = !ti.ranged || ti.lo < 0, can_nonneg = !ti.ranged || ti.hi >= 0;
+                if (can_nonneg) ap.w_nonneg = add_word(OP_ADD_U64);
+                if (can_neg) ap.w_neg = add_word(OP_ADD_U64);
+            }
+            if (ap.opmask & bit(C_FLOAT)) { ap.w_fsum = add_word(OP_ADD_F64); ap.w_nflt = add_word(OP_ADD_U64); }
+        } else {  // MIN / MAX
+            bool mn = ap.kind == AggKind::MIN;
+            u32 m = ap.opmask;
+            if (m & bit(C_STRING)) { if (ap.dict_col < 0) N1_THROW(N1GPU_E_INELIGIBLE, "MIN/MAX over a constant or computed string"); }
+            if (opnd && !opnd->ti.plain_col && (m & bit(C_FLOAT))) m |= bit(C_INT);  // canon_num
+            ap.opmask = m;
+            ap.w_seen = add_word(OP_OR_U64);
+            if (m & bit(C_INT)) ap.w_mi = add_word(mn ? OP_MIN_I64 : OP_MAX_I64);
+            if (m & bit(C_FLOAT)) ap.w_mf = add_word(mn ? OP_MIN_U64 : OP_MAX_U64);
+            if (m & bit(C_STRING)) ap.w_ms = add_word(mn ? OP_MIN_U64 : OP_MAX_U64);
+        }
+        kp.aggs.push_back(ap);
+    }
+    if (kp.word_ops.empty()) add_word(OP_ADD_U64);  // keep at least one word (only DISTINCT aggregates)
+    const int W = (int)kp.word_ops.size();
+
+    // ---- mode ------------------------------------------------------------------------------------------------
+    if (keys.empty()) kp.mode = MODE_UNGROUPED;
+    else if (kp.key_bits <= 13 && ((i64)1 << kp.key_bits) * W * 8 <= 40 * 1024) { kp.mode = MODE_DENSE; kp.dense_slots = (i64)1 << kp.key_bits; }
+    else if (kp.key_bits <= 63) kp.mode = MODE_HASH64;
+    else if (kp.key_bits <= 127) kp.mode = MODE_HASH128;
+    else N1_THROW(N1GPU_E_INELIGIBLE, "group key needs %d bits (> 127) after packing", kp.key_bits);
+    kp.est_groups = (i64)std::min(est, 4e18);
+
+    // ---- DISTINCT entry layout ---------------------------------------------------------------------------------
+    if (kp.ndistinct) {
+        kp.abits = bits_for((u64)kp.ndistinct);
+        int mx = 0;
+        for (auto& ap : kp.aggs) if (ap.distinct) mx = std::max(mx, ap.dcomp.bits());
+        kp.entry_bits = kp.abits + kp.key_bits + mx;
+        if (kp.entry_bits > 127) N1_THROW(N1GPU_E_INELIGIBLE, "DISTINCT entry needs %d bits (> 127)", kp.entry_bits);
+        kp.set128 = kp.entry_bits > 63;
+    }
+
+    // ---- row code -----------------------------------------------------------------------------------------------
+    Gen g(t);
+    std::string passvar = "true";
+    if (where) {
+        std::string wv = g.emit(*where, nullptr);
+        g.line(strf("const bool w_true = v_truth(%s, %lldLL);", wv.c_str(), (long long)g.empty2_of(*where)));
+        passvar = "w_true";
+    }
+    std::string filter_code = g.body;
+    g.body.clear();
+
+    // aggregation code (executed under `if (pass)`)
+    g.ind = "                    ";
+    if (kp.mode != MODE_UNGROUPED) {
+        g.line("u64 klo = 0, khi = 0; int kpos = 0;");
+        for (size_t k = 0; k < keys.size(); ++k) {
+            std::string kv = g.emit(*keys[k], nullptr);
+            if (!keys[k]->ti.plain_col && (keys[k]->ti.mask & bit(C_FLOAT))) {
+                std::string cv = g.nv("k");
+                g.line(strf("const Val %s = canon_num(%s);", cv.c_str(), kv.c_str()));
+                kv = cv;
+            }
+            emit_pack(g, kp.keys[k], kv, "klo", "khi", "kpos");
+        }
+        if (kp.mode == MODE_DENSE) g.line("const i64 slot = (i64)klo;");
+        else if (kp.mode == MODE_HASH64) g.line("const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);");
+        else g.line("const i64 slot = table_insert128((ulonglong2*)p.keys, p.cap_mask, klo, khi, nullptr);");
+        if (kp.mode != MODE_DENSE) g.line("if (slot < 0) { p.status[0] = 1; continue; }");
+        g.line("ACC(0, OP_ADD_U64, 1);");
+    }
+    for (size_t a = 0; a < kp.aggs.size(); ++a) {
+        const AggPlan& ap = kp.aggs[a];
+        const Expr& e = *aggs[a];
+        g.line(strf("{ // %s", ap.text.c_str()));
+        std::string save_ind = g.ind;
+        g.ind += "    ";
+        std::string o;
+        if (!ap.star) o = g.emit(*e.ops[0], nullptr);
+        auto ACC = [&](int w, int op, const std::string& x) { g.line(strf("ACC(%d, %s, %s);", w, op_name(op), x.c_str())); };
+        if (ap.distinct) {
+            std::string cond = (ap.kind == AggKind::COUNT) ? strf("%s.c > C_NULL", o.c_str()) : strf("is_num(%s.c)", o.c_str());
+            g.line(strf("if (%s) {", cond.c_str()));
+            g.ind += "    ";
+            std::string cv = o;
+            if (!e.ops[0]->ti.plain_col && (e.ops[0]->ti.mask & bit(C_FLOAT))) { cv = g.nv("d"); g.line(strf("const Val %s = canon_num(%s);", cv.c_str(), o.c_str())); }
+            g.line("u64 elo = 0, ehi = 0; int epos = 0;");
+            if (kp.abits) g.line(strf("pack_bits(elo, ehi, epos, %dULL, %d);", ap.distinct_id, kp.abits));
+            if (kp.key_bits) {
+                g.line(strf("pack_bits(elo, ehi, epos, klo, %d);", std::min(64, kp.key_bits)));
+                if (kp.key_bits > 64) g.line(strf("pack_bits(elo, ehi, epos, khi, %d);", kp.key_bits - 64));
+            }
+            emit_pack(g, ap.dcomp, cv, "elo", "ehi", "epos");
+            if (kp.set128) g.line("if (table_insert128((ulonglong2*)p.set_keys, p.set_mask, elo, ehi, nullptr) < 0) p.status[0] = 2;");
+            else g.line("if (table_insert64(p.set_keys, p.set_mask, elo, nullptr) < 0) p.status[0] = 2;");
+            g.ind = save_ind + "    ";
+            g.line("}");
+        } else if (ap.kind == AggKind::COUNT) {
+            if (ap.star) { if (ap.w_cnt != 0 || kp.mode == MODE_UNGROUPED) ACC(ap.w_cnt, OP_ADD_U64, "1"); }
+            else { g.line(strf("if (%s.c > C_NULL)", o.c_str())); ACC(ap.w_cnt, OP_ADD_U64, "1"); }
+        } else if (ap.kind == AggKind::COUNTN) {
+            g.line(strf("if (is_num(%s.c))", o.c_str())); ACC(ap.w_cnt, OP_ADD_U64, "1");
+        } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
+            if (ap.opmask & bit(C_INT)) {
+                g.line(strf("if (%s.c == C_INT) {", o.c_str()));
+                g.ind += "    ";
+                if (ap.w_isum >= 0) ACC(ap.w_isum, OP_ADD_U64, strf("(u64)%s.b", o.c_str()));
+                else {
+                    ACC(ap.w_ilo, OP_ADD_U64, strf("((u64)%s.b & 0xffffffffULL)", o.c_str()));
+                    ACC(ap.w_ihi, OP_ADD_U64, strf("(u64)(%s.b >> 32)", o.c_str()));
+                }
+                if (ap.w_nonneg >= 0 && ap.w_neg >= 0) {
+                    g.line(strf("if (%s.b >= 0) { ACC(%d, OP_ADD_U64, 1); } else { ACC(%d, OP_ADD_U64, 1); }", o.c_str(), ap.w_nonneg, ap.w_neg));
+                } else if (ap.w_nonneg >= 0) ACC(ap.w_nonneg, OP_ADD_U64, "1");
+                else if (ap.w_neg >= 0) ACC(ap.w_neg, OP_ADD_U64, "1");
+                g.ind = save_ind + "    ";
+                g.line("}");
+            }
+            if (ap.opmask & bit(C_FLOAT)) {
+                g.line(strf("if (%s.c == C_FLOAT) {", o.c_str()));
+                g.ind += "    ";
+                ACC(ap.w_fsum, OP_ADD_F64, strf("(u64)%s.b", o.c_str()));
+                ACC(ap.w_nflt, OP_ADD_U64, "1");
+                g.ind = save_ind + "    ";
+                g.line("}");
+            }
+        } else {  // MIN / MAX
+            bool mn = ap.kind == AggKind::MIN;
+            std::string cv = o;
+            if (!e.ops[0]->ti.plain_col && (e.ops[0]->ti.mask & bit(C_FLOAT))) { cv = g.nv("mm"); g.line(strf("const Val %s = canon_num(%s);", cv.c_str(), o.c_str())); }
+            g.line(strf("if (%s.c > C_NULL) {", cv.c_str()));
+            g.ind += "    ";
+            ACC(ap.w_seen, OP_OR_U64, strf("(1ULL << %s.c)", cv.c_str()));
+            if (ap.w_mi >= 0) { g.line(strf("if (%s.c == C_INT)", cv.c_str())); ACC(ap.w_mi, mn ? OP_MIN_I64 : OP_MAX_I64, strf("(u64)%s.b", cv.c_str())); }
+            if (ap.w_mf >= 0) { g.line(strf("if (%s.c == C_FLOAT)", cv.c_str())); ACC(ap.w_mf, mn ? OP_MIN_U64 : OP_MAX_U64, strf("f64_ordered(as_f(%s.b))", cv.c_str())); }
+            if (ap.w_ms >= 0) { g.line(strf("if (%s.c == C_STRING)", cv.c_str())); ACC(ap.w_ms, mn ? OP_MIN_U64 : OP_MAX_U64, strf("((u64)%s.b >> 1)", cv.c_str())); }
+            g.ind = save_ind + "    ";
+            g.line("}");
+        }
+        g.ind = save_ind;
+        g.line("}");
+    }
+    std::string agg_code = g.body;
+
+    // ---- used columns -----------------------------------------------------------------------------------------
+    for (auto& kv : g.colvar) kp.used_cols.push_back(kv.first);
+    for (int c : kp.used_cols) kp.scan_bytes_per_row += t.scan_bytes(c);
+
+    // ---- assemble the kernel ------------------------------------------------------------------------------------
+    std::string s;
+    s += "// generated by libn1gpu codegen: one specialised scan kernel for this Filter + Group chain\n";
+    s += "#include \"n1ql_device.cuh\"\n";
+    s += strf("#define NQ_W %d\n", W);
+    if (kp.mode == MODE_DENSE) s += strf("#define NQ_G %lld\n", (long long)kp.dense_slots);
+    s += "__constant__ int nq_ops[NQ_W] = {";
+    for (int w = 0; w < W; ++w) s += strf("%s%d", w ? ", " : "", kp.word_ops[w]);
+    s += "};\n";
+    if (kp.mode == MODE_UNGROUPED) s += "#define ACC(k, OP, x) a##k = word_combine(OP, a##k, (u64)(x))\n";
+    else if (kp.mode == MODE_DENSE) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
+    else s += "#define ACC(k, OP, x) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) nq_scan(const NqParams p) {\n";
+    if (kp.mode == MODE_UNGROUPED) {
+        for (int w = 0; w < W; ++w) s += strf("    u64 a%d = word_identity(%s);\n", w, op_name(kp.word_ops[w]));
+    } else if (kp.mode == MODE_DENSE) {
+        s += "    __shared__ u64 s_tab[NQ_W * NQ_G];\n";
+        s += "    for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) s_tab[i] = word_identity(nq_ops[i / NQ_G]);\n";
+        s += "    __syncthreads();\n";
+    } else {
+        s += "    const u64 cap = p.cap_mask + 1;\n";
+    }
+    s += "    const i64 nrows = p.nrows;\n";
+    s += "    const int lane = threadIdx.x & 31;\n";
+    s += "    const i64 stride = (i64)gridDim.x * 1024;\n";
+    s += "    // warp-uniform trip count: every lane of a warp stays in the loop while the warp has rows\n";
+    s += "    for (i64 wbase = (i64)blockIdx.x * 1024 + (threadIdx.x >> 5) * 128; wbase < nrows; wbase += stride) {\n";
+    s += "        const i64 base = wbase + lane * 4;\n";
+    for (int c : kp.used_cols) {
+        const Column& col = t.cols[c];
+        if (col.width == 8) s += strf("        i64 c%d[4]; ld_rows4_b64((const i64*)p.col[%d] + base, c%d);\n", c, c, c);
+        else if (col.width == 4) s += strf("        u32 c%d[4]; ld_rows4_b32((const u32*)p.col[%d] + base, c%d);\n", c, c, c);
+        if (!col.stats.uniform_tag() && col.stats.class_mask) s += strf("        int t%d[4]; ld_rows4_b8(p.tag[%d] + base, t%d);\n", c, c, c);
+    }
+    s += "#pragma unroll\n";
+    s += "        for (int j = 0; j < 4; ++j) {\n";
+    s += "            bool pass = base + j < nrows;\n";
+    s += g.decls;
+    if (where) {
+        s += filter_code;
+        s += "                pass = pass && w_true;\n";
+    }
+    s += "            // warp-ballot selection mask: skip the aggregation when no lane selected its row\n";
+    s += "            const unsigned sel = __ballot_sync(0xffffffffu, pass);\n";
+    s += "            if (sel == 0) continue;\n";
+    s += "            if (pass) {\n";
+    s += agg_code;
+    s += "            }\n";
+    s += "        }\n";
+    s += "    }\n";
+    if (kp.mode == MODE_UNGROUPED) {
+        s += "    __shared__ u64 scratch[32];\n";
+        for (int w = 0; w < W; ++w) {
+            s += strf("    { u64 r = block_reduce_word<%s>(a%d, scratch); if (threadIdx.x == 0) p.acc[(u64)blockIdx.x * NQ_W + %d] = r; }\n",
+                      op_name(kp.word_ops[w]), w, w);
+        }
+    } else if (kp.mode == MODE_DENSE) {
+        s += "    __syncthreads();\n";
+        s += "    for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) {\n";
+        s += "        const int op = nq_ops[i / NQ_G];\n";
+        s += "        const u64 v = s_tab[i];\n";
+        s += "        if (v != word_identity(op)) atomic_word_dyn(op, &p.acc[i], v);\n";
+        s += "    }\n";
+    }
+    s += "}\n";
+    kp.source = s;
+    return kp;
+}
+
+}  // namespace n1

@@ -1,0 +1,64 @@
+// codegen.hpp — compiles a bound Filter + Group chain into (a) the CUDA source of one specialised
+// sm_100a scan kernel built from n1ql_device.cuh and (b) the layout needed to merge and finalise the
+// accumulator words it produces.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "expr.hpp"
+#include "table.hpp"
+
+namespace n1 {
+
+enum : int { MODE_UNGROUPED = 0, MODE_DENSE = 1, MODE_HASH64 = 2, MODE_HASH128 = 3 };
+
+// One bit-packed component: a group-key value or the value of a DISTINCT entry.
+struct PackComp {
+    u32 mask = 0;
+    std::vector<int> classes;  // class index -> class
+    int cbits = 0, pbits = 0;
+    bool biased = false;       // INT payload stored as (v - bias)
+    i64 bias = 0;
+    int dict_col = -1;         // STRING payload = rank in this column's dictionary
+    int bits() const { return cbits + pbits; }
+};
+
+struct AggPlan {
+    AggKind kind = AggKind::COUNT;
+    bool distinct = false, star = false;
+    std::string text;          // the aggregate's Stringer text (the key of the "aggregates" attachment)
+    u32 opmask = 0;            // classes the operand may take
+    // accumulator word indices (-1 = absent)
+    int w_cnt = -1;
+    int w_isum = -1;           // exact single-word int sum (range proves no overflow)
+    int w_ilo = -1, w_ihi = -1;  // split int sum: sum of low 32 bits / sum of (x >> 32)
+    int w_nonneg = -1, w_neg = -1;
+    int w_fsum = -1, w_nflt = -1;
+    int w_seen = -1, w_mi = -1, w_mf = -1, w_ms = -1;
+    int dict_col = -1;
+    int distinct_id = -1;      // index among DISTINCT aggregates
+    PackComp dcomp;
+};
+
+struct KernelPlan {
+    int mode = MODE_UNGROUPED;
+    std::vector<int> word_ops;   // accumulator words per group
+    std::vector<PackComp> keys;
+    int key_bits = 0;
+    i64 dense_slots = 0;
+    std::vector<AggPlan> aggs;
+    int ndistinct = 0, abits = 0, entry_bits = 0;
+    bool set128 = false;
+    std::vector<int> used_cols;
+    int scan_bytes_per_row = 0;
+    std::string source;
+    i64 est_groups = 0;          // estimate used to size the hash table
+};
+
+// where may be null; keys/aggs are bound + analysed expressions.  total_rows_bound: an upper bound on
+// the number of rows any single accumulator may see (all ranks), for the no-overflow proof of int sums.
+KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<ExprP>& keys,
+                           const std::vector<ExprP>& aggs, const std::vector<std::string>& agg_texts,
+                           double total_rows_bound);
+
+}  // namespace n1

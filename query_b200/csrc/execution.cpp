@@ -1,0 +1,389 @@
+// execution.cpp — see execution.hpp
+#include "execution.hpp"
+
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+
+namespace n1 {
+namespace plan {
+
+std::string node_to_json(const json::Node& n) {
+    std::string s;
+    switch (n.kind) {
+        case json::Node::NUL: return "null";
+        case json::Node::BOOL: return n.b ? "true" : "false";
+        case json::Node::INT: return std::to_string(n.i);
+        case json::Node::FLOAT: return json::format_float(n.d);
+        case json::Node::STR: json::quote(n.s, s); return s;
+        case json::Node::ARR:
+            s = "[";
+            for (size_t i = 0; i < n.arr.size(); ++i) { if (i) s += ","; s += node_to_json(n.arr[i]); }
+            return s + "]";
+        case json::Node::OBJ:
+            s = "{";
+            for (size_t i = 0; i < n.obj.size(); ++i) {
+                if (i) s += ",";
+                json::quote(n.obj[i].first, s);
+                s += ":";
+                s += node_to_json(n.obj[i].second);
+            }
+            return s + "}";
+    }
+    return s;
+}
+
+static std::string q(const std::string& s) { std::string o; json::quote(s, o); return o; }
+static std::string list(const std::vector<std::string>& v) {
+    std::string s = "[";
+    for (size_t i = 0; i < v.size(); ++i) { if (i) s += ","; s += q(v[i]); }
+    return s + "]";
+}
+static std::string term_fields(const KeyspaceTerm& t) {
+    std::string s = "\"keyspace\":" + q(t.keyspace) + ",\"namespace\":" + q(t.nspace);
+    if (!t.as.empty()) s += ",\"as\":" + q(t.as);
+    return s;
+}
+
+void PrimaryScan::Accept(Visitor& v) { v.VisitPrimaryScan(*this); }
+void Fetch::Accept(Visitor& v) { v.VisitFetch(*this); }
+void Filter::Accept(Visitor& v) { v.VisitFilter(*this); }
+void Group::Accept(Visitor& v) { if (phase == 0) v.VisitInitialGroup(*this); else if (phase == 1) v.VisitIntermediateGroup(*this); else v.VisitFinalGroup(*this); }
+void Parallel::Accept(Visitor& v) { v.VisitParallel(*this); }
+void Sequence::Accept(Visitor& v) { v.VisitSequence(*this); }
+void Authorize::Accept(Visitor& v) { v.VisitAuthorize(*this); }
+void Opaque::Accept(Visitor& v) { v.VisitOpaque(*this); }
+
+std::string PrimaryScan::MarshalJSON() const {
+    std::string s = "{\"#operator\":\"PrimaryScan\",\"index\":" + q(index) + "," + term_fields(term) + ",\"using\":" + q(using_);
+    if (!limit.empty()) s += ",\"limit\":" + q(limit);
+    return s + "}";
+}
+std::string Fetch::MarshalJSON() const { return "{\"#operator\":\"Fetch\"," + term_fields(term) + "}"; }
+std::string Filter::MarshalJSON() const { return "{\"#operator\":\"Filter\",\"condition\":" + q(condition) + "}"; }
+std::string Group::MarshalJSON() const {
+    return std::string("{\"#operator\":\"") + Name() + "\",\"aggregates\":" + list(aggregates) + ",\"group_keys\":" + list(keys) + "}";
+}
+std::string Parallel::MarshalJSON() const {
+    std::string s = "{\"#operator\":\"Parallel\"";
+    if (maxParallelism > 0) s += ",\"maxParallelism\":" + std::to_string(maxParallelism);
+    return s + ",\"~child\":" + child->MarshalJSON() + "}";
+}
+std::string Sequence::MarshalJSON() const {
+    std::string s = "{\"#operator\":\"Sequence\",\"~children\":[";
+    for (size_t i = 0; i < children.size(); ++i) { if (i) s += ","; s += children[i]->MarshalJSON(); }
+    return s + "]}";
+}
+std::string Authorize::MarshalJSON() const {
+    return "{\"#operator\":\"Authorize\",\"privileges\":" + (privileges_json.empty() ? std::string("null") : privileges_json) +
+           ",\"~child\":" + child->MarshalJSON() + "}";
+}
+
+static std::vector<std::string> str_list(const json::Node* n) {
+    std::vector<std::string> out;
+    if (n && n->kind == json::Node::ARR)
+        for (auto& e : n->arr) {
+            if (e.kind != json::Node::STR) N1_THROW(N1GPU_E_PARSE, "plan JSON: expected a list of expression strings");
+            out.push_back(e.s);
+        }
+    return out;
+}
+
+OperatorP MakeOperator(const json::Node& n) {
+    if (n.kind != json::Node::OBJ) N1_THROW(N1GPU_E_PARSE, "plan JSON: operator must be an object");
+    std::string name = n.str_or("#operator", "");
+    if (name.empty()) N1_THROW(N1GPU_E_PARSE, "plan JSON: missing #operator");
+    auto term = [&]() { KeyspaceTerm t; t.nspace = n.str_or("namespace", ""); t.keyspace = n.str_or("keyspace", ""); t.as = n.str_or("as", ""); return t; };
+    if (name == "PrimaryScan") {
+        auto* p = new PrimaryScan();
+        p->term = term(); p->index = n.str_or("index", ""); p->using_ = n.str_or("using", ""); p->limit = n.str_or("limit", "");
+        return OperatorP(p);
+    }
+    if (name == "Fetch") { auto* p = new Fetch(); p->term = term(); return OperatorP(p); }
+    if (name == "Filter") { auto* p = new Filter(); p->condition = n.str_or("condition", ""); return OperatorP(p); }
+    if (name == "InitialGroup" || name == "IntermediateGroup" || name == "FinalGroup") {
+        auto* p = new Group();
+        p->phase = name == "InitialGroup" ? 0 : (name == "IntermediateGroup" ? 1 : 2);
+        p->keys = str_list(n.get("group_keys"));
+        p->aggregates = str_list(n.get("aggregates"));
+        return OperatorP(p);
+    }
+    if (name == "Parallel") {
+        auto* p = new Parallel();
+        OperatorP hold(p);
+        const json::Node* c = n.get("~child");
+        if (!c) N1_THROW(N1GPU_E_PARSE, "plan JSON: Parallel without ~child");
+        p->child = MakeOperator(*c);
+        const json::Node* mp = n.get("maxParallelism");
+        if (mp && mp->kind == json::Node::INT) p->maxParallelism = (int)mp->i;
+        return hold;
+    }
+    if (name == "Sequence") {
+        auto* p = new Sequence();
+        OperatorP hold(p);
+        const json::Node* c = n.get("~children");
+        if (c && c->kind == json::Node::ARR) for (auto& e : c->arr) p->children.push_back(MakeOperator(e));
+        return hold;
+    }
+    if (name == "Authorize") {
+        auto* p = new Authorize();
+        OperatorP hold(p);
+        const json::Node* c = n.get("~child");
+        if (!c) N1_THROW(N1GPU_E_PARSE, "plan JSON: Authorize without ~child");
+        p->child = MakeOperator(*c);
+        if (const json::Node* pr = n.get("privileges")) p->privileges_json = node_to_json(*pr);
+        return hold;
+    }
+    auto* p = new Opaque();
+    p->name = name;
+    p->body = node_to_json(n);
+    return OperatorP(p);
+}
+
+}  // namespace plan
+
+namespace execution {
+
+namespace {
+
+struct CacheEntry { std::shared_ptr<Table> table; time_t mtime; };
+std::mutex g_cache_mu;
+std::map<std::string, CacheEntry> g_tables;  // keyspace dir + columns -> resident shredded table (A.9)
+
+std::shared_ptr<Table> resident_table(const std::string& dir, std::vector<std::string> paths) {
+    std::sort(paths.begin(), paths.end());
+    std::string key = dir;
+    for (auto& p : paths) { key.push_back('\n'); key += p; }
+    struct stat st;
+    if (stat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) N1_THROW(N1GPU_E_IO, "keyspace directory %s not found", dir.c_str());
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_tables.find(key);
+        if (it != g_tables.end() && it->second.mtime == st.st_mtime) return it->second.table;
+    }
+    auto t = std::make_shared<Table>();
+    for (auto& p : paths) t->add_column(p);
+    t->load_dir(dir, 0);
+    t->seal();
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_tables[key] = CacheEntry{t, st.st_mtime};
+    return t;
+}
+
+// plan.Visitor implementation: the builder of execution/build.go restricted to the substitution.
+struct Builder : plan::Visitor {
+    std::string root;
+    std::unique_ptr<GpuGroupAggregate> found;
+    int rest = 0;
+    std::string why = "plan holds no PrimaryScan/Fetch/Filter/InitialGroup/IntermediateGroup/FinalGroup chain";
+
+    void VisitPrimaryScan(plan::PrimaryScan&) override {}
+    void VisitFetch(plan::Fetch&) override {}
+    void VisitFilter(plan::Filter&) override {}
+    void VisitInitialGroup(plan::Group&) override {}
+    void VisitIntermediateGroup(plan::Group&) override {}
+    void VisitFinalGroup(plan::Group&) override {}
+    void VisitOpaque(plan::Opaque&) override {}
+    void VisitParallel(plan::Parallel& p) override { if (!found) p.child->Accept(*this); }
+    void VisitAuthorize(plan::Authorize& a) override { if (!found) a.child->Accept(*this); }
+
+    // Flattens [Filter?, InitialGroup] out of Parallel(Sequence[..]) / Sequence[..] / bare operators
+    // (execution/build.go:455-491 elides Parallel at parallelism 1 and single-child Sequences).
+    static void flatten(plan::Operator* op, std::vector<plan::Operator*>& out) {
+        if (auto* p = dynamic_cast<plan::Parallel*>(op)) { flatten(p->child.get(), out); return; }
+        if (auto* s = dynamic_cast<plan::Sequence*>(op)) { for (auto& c : s->children) flatten(c.get(), out); return; }
+        out.push_back(op);
+    }
+
+    void VisitSequence(plan::Sequence& s) override {
+        if (found) return;
+        auto& ch = s.children;
+        auto* scan = ch.size() > 0 ? dynamic_cast<plan::PrimaryScan*>(ch[0].get()) : nullptr;
+        auto* fetch = ch.size() > 1 ? dynamic_cast<plan::Fetch*>(ch[1].get()) : nullptr;
+        if (scan && fetch) {
+            // children[2..]: the Filter/InitialGroup part, then IntermediateGroup, FinalGroup
+            size_t i = 2;
+            std::vector<plan::Operator*> mid;
+            while (i < ch.size()) {
+                auto* g = dynamic_cast<plan::Group*>(ch[i].get());
+                if (g && g->phase >= 1) break;
+                if (dynamic_cast<plan::Opaque*>(ch[i].get())) break;
+                flatten(ch[i].get(), mid);
+                ++i;
+            }
+            plan::Filter* filter = nullptr;
+            plan::Group* initial = nullptr;
+            bool ok = true;
+            for (auto* m : mid) {
+                if (auto* f = dynamic_cast<plan::Filter*>(m)) { if (filter || initial) ok = false; filter = f; }
+                else if (auto* g = dynamic_cast<plan::Group*>(m)) { if (initial || g->phase != 0) ok = false; initial = g; }
+                else ok = false;  // Let, Join, Nest, Unnest, ... between Fetch and InitialGroup
+            }
+            auto* inter = i < ch.size() ? dynamic_cast<plan::Group*>(ch[i].get()) : nullptr;
+            auto* fin = i + 1 < ch.size() ? dynamic_cast<plan::Group*>(ch[i + 1].get()) : nullptr;
+            if (!ok || !initial) why = "operators between Fetch and InitialGroup are not just Filter";
+            else if (!inter || inter->phase != 1 || !fin || fin->phase != 2) why = "InitialGroup is not followed by IntermediateGroup, FinalGroup";
+            else if (inter->keys != initial->keys || fin->keys != initial->keys || inter->aggregates != initial->aggregates || fin->aggregates != initial->aggregates)
+                why = "group phases disagree on keys/aggregates";
+            else if (!scan->limit.empty()) why = "PrimaryScan carries a LIMIT";
+            else if (scan->term.keyspace != fetch->term.keyspace || scan->term.nspace != fetch->term.nspace) why = "scan and fetch keyspaces differ";
+            else {
+                std::unique_ptr<GpuGroupAggregate> op(new GpuGroupAggregate());
+                op->term = fetch->term;
+                if (op->term.as.empty()) op->term.as = scan->term.as;
+                op->keyspace_dir = root + "/" + fetch->term.nspace + "/" + fetch->term.keyspace;
+                if (filter) op->condition = filter->condition;
+                op->keys = initial->keys;
+                op->aggregates = initial->aggregates;
+                found = std::move(op);
+                rest = (int)i + 2;
+                return;
+            }
+        }
+        for (auto& c : ch) { if (found) return; c->Accept(*this); }
+    }
+};
+
+std::string dur(double sec) {  // time.Duration.String() style
+    if (sec <= 0) return "0s";
+    if (sec < 1e-6) return strf("%.0fns", sec * 1e9);
+    if (sec < 1e-3) return strf("%.3fµs", sec * 1e6);
+    if (sec < 1) return strf("%.6fms", sec * 1e3);
+    return strf("%.9fs", sec);
+}
+
+std::string value_json(const HValue& v) {
+    switch (v.cls) {
+        case C_NULL: return "null";
+        case C_FALSE: return "false";
+        case C_TRUE: return "true";
+        case C_INT: return std::to_string(v.bits);
+        case C_FLOAT: return json::format_float(v.f());
+        case C_STRING: { std::string s; json::quote(v.s, s); return s; }
+        default: return "null";
+    }
+}
+
+struct Tree {
+    std::map<std::string, Tree> kids;
+    std::string leaf;
+    bool has_leaf = false;
+    std::string render() const {
+        if (has_leaf) return leaf;
+        std::string s = "{";
+        bool first = true;
+        for (auto& kv : kids) {
+            if (!first) s += ",";
+            first = false;
+            json::quote(kv.first, s);
+            s += ":";
+            s += kv.second.render();
+        }
+        return s + "}";
+    }
+};
+
+}  // namespace
+
+std::unique_ptr<GpuGroupAggregate> Build(const std::string& plan_json, const std::string& datastore_root, int* rest_index) {
+    json::Node root;
+    if (!json::parse(plan_json, root)) N1_THROW(N1GPU_E_PARSE, "plan JSON does not parse");
+    const json::Node* pn = &root;
+    if (root.kind == json::Node::OBJ && !root.get("#operator") && root.get("plan")) pn = root.get("plan");  // EXPLAIN row {plan, text}
+    plan::OperatorP p = plan::MakeOperator(*pn);
+    Builder b;
+    b.root = datastore_root;
+    p->Accept(b);
+    if (!b.found) N1_THROW(N1GPU_E_INELIGIBLE, "not substituted: %s", b.why.c_str());
+    std::unique_ptr<GpuGroupAggregate> op = std::move(b.found);
+    // referenced field paths -> resident shredded table
+    std::string alias = op->term.Alias();
+    std::vector<std::string> paths;
+    if (!op->condition.empty()) collect_paths(*parse_expr(op->condition), alias, paths);
+    for (auto& k : op->keys) collect_paths(*parse_expr(k), alias, paths);
+    for (auto& a : op->aggregates) collect_paths(*parse_expr(a), alias, paths);
+    double t0 = now_sec();
+    op->table = resident_table(op->keyspace_dir, paths);
+    op->query = Query::compile(op->table.get(), alias, op->condition.empty() ? nullptr : op->condition.c_str(), op->keys, op->aggregates);
+    op->serv_sec = now_sec() - t0;
+    if (rest_index) *rest_index = b.rest;
+    return op;
+}
+
+std::unique_ptr<Result> GpuGroupAggregate::RunOnce() {
+    if (ran) N1_THROW(N1GPU_E_INVALID, "RunOnce executes exactly once per operator (util.Once); Build a new operator");
+    ran = true;
+    double t0 = now_sec();
+    query->scan_blocking();
+    std::unique_ptr<Result> r = query->finalize();
+    exec_sec = now_sec() - t0;
+    in_docs = table->nrows;
+    out_docs = r->ngroups;
+    return r;
+}
+
+void GpuGroupAggregate::SendStop() { if (query) query->cancelled.store(true); }
+
+std::string GpuGroupAggregate::MarshalJSON() const {
+    std::string s = "{\"#operator\":\"GpuGroupAggregate\"";
+    std::string stats;
+    if (in_docs) stats += "\"#itemsIn\":" + std::to_string(in_docs);
+    if (out_docs) stats += std::string(stats.empty() ? "" : ",") + "\"#itemsOut\":" + std::to_string(out_docs);
+    if (exec_sec > 0) { stats += std::string(stats.empty() ? "" : ",") + "\"execTime\":"; json::quote(dur(exec_sec), stats); }
+    if (serv_sec > 0) { stats += std::string(stats.empty() ? "" : ",") + "\"servTime\":"; json::quote(dur(serv_sec), stats); }
+    if (!stats.empty()) s += ",\"#stats\":{" + stats + "}";
+    s += ",\"aggregates\":[";
+    for (size_t i = 0; i < aggregates.size(); ++i) { if (i) s += ","; json::quote(aggregates[i], s); }
+    s += "]";
+    if (!term.as.empty()) { s += ",\"as\":"; json::quote(term.as, s); }
+    if (!condition.empty()) { s += ",\"condition\":"; json::quote(condition, s); }
+    s += ",\"group_keys\":[";
+    for (size_t i = 0; i < keys.size(); ++i) { if (i) s += ","; json::quote(keys[i], s); }
+    s += "],\"keyspace\":";
+    json::quote(term.keyspace, s);
+    s += ",\"namespace\":";
+    json::quote(term.nspace, s);
+    if (query) {
+        static const char* modes[] = {"ungrouped", "dense-shared-memory", "hbm-hash-64", "hbm-hash-128"};
+        s += std::string(",\"kernel\":{\"mode\":\"") + modes[query->kp.mode] + "\",\"accumulator_words\":" + std::to_string(query->ops.n) +
+             ",\"scan_bytes_per_row\":" + std::to_string(query->kp.scan_bytes_per_row) + "}";
+    }
+    return s + "}";
+}
+
+std::string ResultToJSON(const Result& r) {
+    std::string s = "[";
+    for (i64 g = 0; g < r.ngroups; ++g) {
+        if (g) s += ",";
+        Tree doc;
+        std::string keys = "[";
+        for (int k = 0; k < r.nkeys; ++k) {
+            const HValue& v = r.keys[(size_t)g * r.nkeys + k];
+            if (k) keys += ",";
+            keys += v.cls == C_MISSING ? "{\"#missing\":true}" : value_json(v);
+            if (v.cls == C_MISSING) continue;  // MISSING key: field absent (group_util.go:28-30)
+            const auto& path = r.key_paths[(size_t)k];
+            if (path.empty()) continue;
+            Tree* t = &doc;
+            for (auto& name : path) t = &t->kids[name];
+            t->has_leaf = true;
+            t->leaf = value_json(v);
+        }
+        keys += "]";
+        s += "{";
+        json::quote(r.alias, s);
+        s += ":" + doc.render() + ",\"aggregates\":{";
+        for (int a = 0; a < r.naggs; ++a) {
+            if (a) s += ",";
+            json::quote(r.agg_texts[(size_t)a], s);
+            s += ":" + value_json(r.aggs[(size_t)g * r.naggs + a]);
+        }
+        s += "},\"group_keys\":" + keys + "}";
+    }
+    return s + "]";
+}
+
+}  // namespace execution
+}  // namespace n1

@@ -1,0 +1,65 @@
+// expr.hpp — host-side mirror of the reference's `expression` / `algebra` node types for the eligible
+// subset, parsed from the Stringer text that plan JSON carries.
+//
+//   expression/stringer.go (text form)        expression/comp_gt.go:15-17 (a > b is LT(b, a))
+//   expression/comp_eq.go:92-94 (a != b is NOT(a = b))     algebra/agg_registry.go:41-62
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+
+namespace n1 {
+
+struct Table;
+
+enum class EK {
+    CONST, IDENT, FIELD,  // navigation
+    ADD, MULT, SUB, DIV, MOD, NEG,
+    EQ, LT, LE, BETWEEN, IN,
+    AND, OR, NOT,
+    IS_NULL, IS_NOT_NULL, IS_MISSING, IS_NOT_MISSING, IS_VALUED, IS_NOT_VALUED,
+    ARRAY,  // array construct (only as the right side of IN)
+    AGG     // aggregate call
+};
+
+enum class AggKind { COUNT, COUNTN, SUM, AVG, MIN, MAX };
+
+struct TypeInfo {
+    u32 mask = 0;          // classes the value may take
+    bool ranged = false;   // INT values proven within [lo, hi]
+    i64 lo = 0, hi = 0;
+    int dict_col = -1;     // STRING values are ranks in this column's dictionary (-1: none / constant)
+    bool plain_col = false;
+};
+
+struct Expr {
+    EK kind;
+    std::vector<std::unique_ptr<Expr>> ops;
+    HValue cval;             // CONST
+    std::string name;        // IDENT / FIELD name
+    AggKind agg = AggKind::COUNT;
+    bool distinct = false;
+    bool star = false;       // count(*)
+    // binding / analysis
+    int col = -1;            // FIELD chain bound to a table column
+    TypeInfo ti;
+
+    explicit Expr(EK k) : kind(k) {}
+    std::string str() const;  // Stringer text (expression/stringer.go)
+};
+typedef std::unique_ptr<Expr> ExprP;
+
+// Parses Stringer text; throws Error(N1GPU_E_PARSE) on malformed text and Error(N1GPU_E_INELIGIBLE)
+// on well-formed N1QL outside the subset (functions, CASE, ANY/EVERY, parameters, ...).
+ExprP parse_expr(const std::string& text);
+
+// Collects the field paths (joined with '\x1f') referenced below `alias`; throws INELIGIBLE for a bare
+// alias reference (whole document), foreign identifiers or navigation on non-identifiers.
+void collect_paths(const Expr& e, const std::string& alias, std::vector<std::string>& out);
+
+// Binds FIELD chains to columns of `t` and computes TypeInfo bottom-up.
+void bind_and_analyze(Expr& e, const std::string& alias, const Table& t);
+
+}  // namespace n1

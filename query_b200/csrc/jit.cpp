@@ -1,0 +1,217 @@
+// jit.cpp — see jit.hpp
+#include "jit.hpp"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <limits.h>
+#include <nvrtc.h>
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+
+#ifndef N1_CUDA_LIB
+#define N1_CUDA_LIB "/usr/local/cuda/lib64"
+#endif
+
+namespace n1 {
+
+// n1ql_device.cuh embedded at build time (Makefile: device_src.inc)
+static const char* k_device_header =
+#include "device_src.inc"
+    ;
+
+std::atomic<u64> g_launches{0};
+
+namespace {
+struct Driver {
+    decltype(&cuModuleLoadData) ModuleLoadData = nullptr;
+    decltype(&cuModuleUnload) ModuleUnload = nullptr;
+    decltype(&cuModuleGetFunction) ModuleGetFunction = nullptr;
+    decltype(&cuLaunchKernel) LaunchKernel = nullptr;
+    decltype(&cuFuncGetAttribute) FuncGetAttribute = nullptr;
+    decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) Occupancy = nullptr;
+    decltype(&cuGetErrorString) GetErrorString = nullptr;
+    bool ready = false;
+};
+Driver g_drv;
+std::mutex g_mu;
+std::map<std::string, std::shared_ptr<JitKernel>> g_cache;
+std::map<std::string, std::string> g_cubin_cache;
+
+template <class F> void resolve(F& fn, const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qr);
+    if (e != cudaSuccess || !p) N1_THROW(N1GPU_E_CUDA, "CUDA driver entry point %s unavailable: %s", name, cudaGetErrorString(e));
+    fn = (F)p;
+}
+
+Driver& driver() {
+    if (!g_drv.ready) {
+        CK(cudaFree(0));  // make sure the primary context exists and is current
+        resolve(g_drv.ModuleLoadData, "cuModuleLoadData");
+        resolve(g_drv.ModuleUnload, "cuModuleUnload");
+        resolve(g_drv.ModuleGetFunction, "cuModuleGetFunction");
+        resolve(g_drv.LaunchKernel, "cuLaunchKernel");
+        resolve(g_drv.FuncGetAttribute, "cuFuncGetAttribute");
+        resolve(g_drv.Occupancy, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+        resolve(g_drv.GetErrorString, "cuGetErrorString");
+        g_drv.ready = true;
+    }
+    return g_drv;
+}
+
+// NVRTC is bound at run time from the CUDA toolkit this library was built against, by ABSOLUTE path and
+// with RTLD_LOCAL | RTLD_DEEPBIND: a host process (e.g. one that imported torch) may already hold an older
+// libnvrtc.so.12 under the same soname, and symbol interposition would silently hand us that compiler.
+struct Nvrtc {
+    decltype(&nvrtcCreateProgram) CreateProgram = nullptr;
+    decltype(&nvrtcCompileProgram) CompileProgram = nullptr;
+    decltype(&nvrtcGetProgramLogSize) GetProgramLogSize = nullptr;
+    decltype(&nvrtcGetProgramLog) GetProgramLog = nullptr;
+    decltype(&nvrtcGetCUBINSize) GetCUBINSize = nullptr;
+    decltype(&nvrtcGetCUBIN) GetCUBIN = nullptr;
+    decltype(&nvrtcDestroyProgram) DestroyProgram = nullptr;
+    decltype(&nvrtcVersion) Version = nullptr;
+    int major = 0, minor = 0;
+    bool ready = false;
+};
+Nvrtc g_nvrtc;
+
+Nvrtc& nvrtc() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_nvrtc.ready) return g_nvrtc;
+    std::vector<std::string> tried;
+    void* h = nullptr;
+    const char* env = getenv("N1GPU_NVRTC");
+    std::vector<std::string> cands;
+    if (env && *env) cands.push_back(env);
+    cands.push_back(std::string(N1_CUDA_LIB) + "/libnvrtc.so");
+    cands.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+    cands.push_back("libnvrtc.so.12");
+    for (auto& c : cands) {
+        std::string path = c;
+        char real[PATH_MAX];
+        if (c.find('/') != std::string::npos && realpath(c.c_str(), real)) path = real;
+        // its builtins library is looked up by soname from inside NVRTC: load it first from the same directory
+        size_t slash = path.rfind('/');
+        if (slash != std::string::npos) {
+            std::string b = path.substr(0, slash) + "/libnvrtc-builtins.so";
+            char rb[PATH_MAX];
+            if (realpath(b.c_str(), rb)) dlopen(rb, RTLD_NOW | RTLD_GLOBAL);
+        }
+        h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND);
+        if (h) break;
+        tried.push_back(path + ": " + (dlerror() ? dlerror() : "?"));
+    }
+    if (!h) {
+        std::string all;
+        for (auto& t : tried) all += t + "; ";
+        N1_THROW(N1GPU_E_CUDA, "cannot load NVRTC (%s)", all.c_str());
+    }
+    auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) N1_THROW(N1GPU_E_CUDA, "NVRTC lacks %s", n); return p; };
+    g_nvrtc.CreateProgram = (decltype(g_nvrtc.CreateProgram))sym("nvrtcCreateProgram");
+    g_nvrtc.CompileProgram = (decltype(g_nvrtc.CompileProgram))sym("nvrtcCompileProgram");
+    g_nvrtc.GetProgramLogSize = (decltype(g_nvrtc.GetProgramLogSize))sym("nvrtcGetProgramLogSize");
+    g_nvrtc.GetProgramLog = (decltype(g_nvrtc.GetProgramLog))sym("nvrtcGetProgramLog");
+    g_nvrtc.GetCUBINSize = (decltype(g_nvrtc.GetCUBINSize))sym("nvrtcGetCUBINSize");
+    g_nvrtc.GetCUBIN = (decltype(g_nvrtc.GetCUBIN))sym("nvrtcGetCUBIN");
+    g_nvrtc.DestroyProgram = (decltype(g_nvrtc.DestroyProgram))sym("nvrtcDestroyProgram");
+    g_nvrtc.Version = (decltype(g_nvrtc.Version))sym("nvrtcVersion");
+    g_nvrtc.Version(&g_nvrtc.major, &g_nvrtc.minor);
+    g_nvrtc.ready = true;
+    return g_nvrtc;
+}
+
+void cu_check(CUresult r, const char* what) {
+    if (r == CUDA_SUCCESS) return;
+    const char* msg = "?";
+    if (g_drv.GetErrorString) g_drv.GetErrorString(r, &msg);
+    N1_THROW(N1GPU_E_CUDA, "%s failed: %s", what, msg);
+}
+}  // namespace
+
+JitKernel::~JitKernel() {
+    if (module && g_drv.ModuleUnload) g_drv.ModuleUnload((CUmodule)module);
+}
+
+std::string jit_compile_cubin(const std::string& source, std::string* log) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_cubin_cache.find(source);
+        if (it != g_cubin_cache.end()) return it->second;
+    }
+    Nvrtc& rt = nvrtc();
+    nvrtcProgram prog;
+    const char* hdr_names[] = {"n1ql_device.cuh"};
+    const char* hdr_srcs[] = {k_device_header};
+    if (rt.CreateProgram(&prog, source.c_str(), "nq_scan.cu", 1, hdr_srcs, hdr_names) != NVRTC_SUCCESS)
+        N1_THROW(N1GPU_E_CUDA, "nvrtcCreateProgram failed");
+    // -fmad=false: float64 arithmetic must round like the reference's separate Go operations.
+    // 256-bit global loads need the PTX ISA 8.8 assembler of CUDA >= 12.9; older NVRTC gets 2 x 128-bit.
+    bool ld256 = rt.major > 12 || (rt.major == 12 && rt.minor >= 9);
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=false", "-default-device", "--device-int128"};
+    if (!ld256) opts.push_back("-DNQ_NO_LD256=1");
+    nvrtcResult r = rt.CompileProgram(prog, (int)opts.size(), opts.data());
+    size_t ls = 0;
+    rt.GetProgramLogSize(prog, &ls);
+    std::string lg(ls, '\0');
+    if (ls) rt.GetProgramLog(prog, &lg[0]);
+    if (log) *log = lg;
+    if (r != NVRTC_SUCCESS) {
+        rt.DestroyProgram(&prog);
+        N1_THROW(N1GPU_E_CUDA, "NVRTC %d.%d compilation failed: %s\n--- source ---\n%s", rt.major, rt.minor, lg.c_str(), source.c_str());
+    }
+    size_t cs = 0;
+    rt.GetCUBINSize(prog, &cs);
+    std::string cubin(cs, '\0');
+    rt.GetCUBIN(prog, &cubin[0]);
+    rt.DestroyProgram(&prog);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_cubin_cache[source] = cubin;
+    return cubin;
+}
+
+std::shared_ptr<JitKernel> jit_load(const std::string& source) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_cache.find(source);
+        if (it != g_cache.end()) return it->second;
+    }
+    std::string cubin = jit_compile_cubin(source, nullptr);
+    Driver& d = driver();
+    auto k = std::make_shared<JitKernel>();
+    k->cubin = cubin;
+    CUmodule mod;
+    cu_check(d.ModuleLoadData(&mod, k->cubin.data()), "cuModuleLoadData");
+    k->module = mod;
+    CUfunction fn;
+    cu_check(d.ModuleGetFunction(&fn, mod, "nq_scan"), "cuModuleGetFunction(nq_scan)");
+    k->function = fn;
+    cu_check(d.FuncGetAttribute(&k->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn), "cuFuncGetAttribute");
+    cu_check(d.FuncGetAttribute(&k->static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, fn), "cuFuncGetAttribute");
+    cu_check(d.Occupancy(&k->max_blocks_per_sm, fn, 256, 0), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (k->max_blocks_per_sm < 1) k->max_blocks_per_sm = 1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_cache[source] = k;
+    return k;
+}
+
+void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t) {
+    void* args[] = {params};
+    cu_check(driver().LaunchKernel((CUfunction)k.function, (unsigned)grid, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr), "cuLaunchKernel(nq_scan)");
+    g_launches.fetch_add(1);
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return sms;
+}
+
+}  // namespace n1

@@ -1,0 +1,149 @@
+// kernels.cu — the static (query-independent) sm_100a kernels of libn1gpu.so: accumulator-table
+// initialisation, the deterministic reduction of per-block partials, table -> record compaction with
+// owner bucketing (the export side of the multi-GPU IntermediateGroup exchange) and record -> table
+// merging (CumulateIntermediate: algebra/agg_*.go, execution/group_intermediate.go:56-104).
+#include "kernels.hpp"
+#include "n1ql_device.cuh"
+
+namespace n1 {
+
+__global__ void k_init_words(u64* acc, u64 cap, OpsArr ops) {
+    u64 total = cap * (u64)ops.n;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x)
+        acc[i] = word_identity(ops.op[i / cap]);
+}
+
+__global__ void k_fill_u64(u64* p, u64 n, u64 v) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// partials[nblocks][W] -> out[W]; one block, fixed summation order => run-to-run identical float sums.
+__global__ void k_reduce_partials(const u64* __restrict__ partials, int nblocks, OpsArr ops, u64* __restrict__ out) {
+    __shared__ u64 sh[256];
+    for (int w = 0; w < ops.n; ++w) {
+        int op = ops.op[w];
+        u64 v = word_identity(op);
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v = word_combine(op, v, partials[(u64)b * ops.n + w]);
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) sh[threadIdx.x] = word_combine(op, sh[threadIdx.x], sh[threadIdx.x + s]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[w] = sh[0];
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void extract_bits(u64 lo, u64 hi, int pos, int n, u64& olo, u64& ohi) {
+    // bits [pos, pos+n) of the 128-bit (hi:lo), n <= 127
+    unsigned __int128 v = ((unsigned __int128)hi << 64) | lo;
+    v >>= pos;
+    if (n < 128) v &= (((unsigned __int128)1) << n) - 1;
+    olo = (u64)v;
+    ohi = (u64)(v >> 64);
+}
+
+__device__ __forceinline__ int owner_of(u64 lo, u64 hi, int nranks) {
+    return nranks <= 1 ? 0 : (int)(::mix64(lo ^ ::mix64(hi ^ 0x9e3779b97f4a7c15ULL)) % (u64)nranks);
+}
+
+// key of slot i and whether the slot holds a group.  kw: 0 dense (key = index, live iff word 0 > 0),
+// 1: u64 keys, 2: 128-bit keys, 3: single ungrouped slot (always live)
+__device__ __forceinline__ bool slot_key(int kw, const u64* keys, const u64* acc, u64 i, u64& lo, u64& hi) {
+    if (kw == 0) { lo = i; hi = 0; return acc[i] != 0; }
+    if (kw == 1) { lo = keys[i]; hi = 0; return lo != NQ_U64_MAX; }
+    if (kw == 2) { lo = keys[2 * i]; hi = keys[2 * i + 1]; return !(lo == NQ_U64_MAX && hi == NQ_U64_MAX); }
+    lo = 0; hi = 0; return true;
+}
+
+// pass 1: count live slots per owner.  gk_pos/gk_bits: where the group key sits inside the stored key
+// (DISTINCT entries embed it after the aggregate id; group tables store it at bit 0).
+__global__ void k_count_owners(int kw, const u64* keys, const u64* acc, u64 cap, int nranks, int gk_pos, int gk_bits,
+                               unsigned long long* counts) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
+        u64 lo, hi;
+        if (!slot_key(kw, keys, acc, i, lo, hi)) continue;
+        u64 glo, ghi;
+        extract_bits(lo, hi, gk_pos, gk_bits, glo, ghi);
+        atomicAdd(&counts[owner_of(glo, ghi, nranks)], 1ULL);
+    }
+}
+
+// pass 2: write records [lo, hi, words...] at cursor[owner]++ (cursor pre-loaded with bucket offsets).
+__global__ void k_export_records(int kw, const u64* keys, const u64* acc, u64 cap, int W, int nranks, int gk_pos, int gk_bits,
+                                 unsigned long long* cursor, u64* out, u64 out_cap) {
+    const int rw = 2 + W;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
+        u64 lo, hi;
+        if (!slot_key(kw, keys, acc, i, lo, hi)) continue;
+        u64 glo, ghi;
+        extract_bits(lo, hi, gk_pos, gk_bits, glo, ghi);
+        u64 at = atomicAdd(&cursor[owner_of(glo, ghi, nranks)], 1ULL);
+        if (at >= out_cap) continue;
+        u64* r = out + at * rw;
+        r[0] = lo; r[1] = hi;
+        for (int w = 0; w < W; ++w) r[2 + w] = acc[(u64)w * cap + i];
+    }
+}
+
+// merge: records -> table (IntermediateGroup).  kw as above.
+__global__ void k_merge_records(int kw, u64* keys, u64* acc, u64 cap, OpsArr ops, const u64* __restrict__ recs, u64 n, int* status) {
+    const int rw = 2 + ops.n;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64* r = recs + i * rw;
+        i64 slot;
+        if (kw == 0) slot = (i64)r[0];
+        else if (kw == 1) slot = table_insert64(keys, cap - 1, r[0], nullptr);
+        else if (kw == 2) slot = table_insert128((ulonglong2*)keys, cap - 1, r[0], r[1], nullptr);
+        else slot = 0;
+        if (slot < 0 || (u64)slot >= cap) { status[0] = 1; continue; }
+        for (int w = 0; w < ops.n; ++w) {
+            u64 v = r[2 + w];
+            if (v != word_identity(ops.op[w])) atomic_word_dyn(ops.op[w], &acc[(u64)w * cap + (u64)slot], v);
+        }
+    }
+}
+
+static int grid_for(u64 n) {
+    u64 g = (n + 255) / 256;
+    if (g < 1) g = 1;
+    if (g > 148 * 16) g = 148 * 16;
+    return (int)g;
+}
+
+void launch_init_words(u64* acc, u64 cap, const OpsArr& ops, cudaStream_t s) {
+    k_init_words<<<grid_for(cap * ops.n), 256, 0, s>>>(acc, cap, ops);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_fill_u64(u64* p, u64 n, u64 v, cudaStream_t s) {
+    k_fill_u64<<<grid_for(n), 256, 0, s>>>(p, n, v);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_reduce_partials(const u64* partials, int nblocks, const OpsArr& ops, u64* out, cudaStream_t s) {
+    k_reduce_partials<<<1, 256, 0, s>>>(partials, nblocks, ops, out);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_count_owners(int kw, const u64* keys, const u64* acc, u64 cap, int nranks, int gk_pos, int gk_bits,
+                         unsigned long long* counts, cudaStream_t s) {
+    k_count_owners<<<grid_for(cap), 256, 0, s>>>(kw, keys, acc, cap, nranks, gk_pos, gk_bits, counts);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_export_records(int kw, const u64* keys, const u64* acc, u64 cap, int W, int nranks, int gk_pos, int gk_bits,
+                           unsigned long long* cursor, u64* out, u64 out_cap, cudaStream_t s) {
+    k_export_records<<<grid_for(cap), 256, 0, s>>>(kw, keys, acc, cap, W, nranks, gk_pos, gk_bits, cursor, out, out_cap);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_merge_records(int kw, u64* keys, u64* acc, u64 cap, const OpsArr& ops, const u64* recs, u64 n, int* status, cudaStream_t s) {
+    if (n == 0) return;
+    k_merge_records<<<grid_for(n), 256, 0, s>>>(kw, keys, acc, cap, ops, recs, n, status);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+
+}  // namespace n1

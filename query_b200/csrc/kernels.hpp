@@ -1,0 +1,21 @@
+// kernels.hpp — host launchers of the static kernels in kernels.cu
+#pragma once
+#include "common.hpp"
+
+namespace n1 {
+
+struct OpsArr {
+    int n;
+    int op[64];
+};
+
+void launch_init_words(u64* acc, u64 cap, const OpsArr& ops, cudaStream_t s);
+void launch_fill_u64(u64* p, u64 n, u64 v, cudaStream_t s);
+void launch_reduce_partials(const u64* partials, int nblocks, const OpsArr& ops, u64* out, cudaStream_t s);
+void launch_count_owners(int kw, const u64* keys, const u64* acc, u64 cap, int nranks, int gk_pos, int gk_bits,
+                         unsigned long long* counts, cudaStream_t s);
+void launch_export_records(int kw, const u64* keys, const u64* acc, u64 cap, int W, int nranks, int gk_pos, int gk_bits,
+                           unsigned long long* cursor, u64* out, u64 out_cap, cudaStream_t s);
+void launch_merge_records(int kw, u64* keys, u64* acc, u64 cap, const OpsArr& ops, const u64* recs, u64 n, int* status, cudaStream_t s);
+
+}  // namespace n1

@@ -1,0 +1,480 @@
+// query.cpp — compile / scan / merge / finalise of one Filter + Group chain.
+//
+// Reference behaviour restated in finalize() (file:line under /root/reference):
+//   algebra/agg_count.go:95-149, agg_countn.go:77-129   counts are int64
+//   algebra/agg_sum.go:77-136 + value/integer.go:266-277  int64 sum stays int while every operand shares a
+//       sign class and the total fits, otherwise float64
+//   algebra/agg_avg.go:117-131   float64(sum)/float64(count), then value.NewValue (integral -> int)
+//   algebra/agg_min.go:76-127, agg_max.go:76-127   collation winner over any type, NULL when nothing counted
+//   algebra/agg_*_distinct.go + value/set.go:65-110  DISTINCT sets; SUM starts from int 0 (0 + negative -> float)
+//   execution/group_final.go:108-117   no keys and no input -> one row of Default() values
+#include "query.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <unordered_map>
+
+namespace n1 {
+
+namespace {
+// must mirror NqParams in n1ql_device.cuh
+struct NqParamsHost {
+    i64 nrows;
+    const void* col[16];
+    const u8* tag[16];
+    u64* acc;
+    u64* keys;
+    u64 cap_mask;
+    u64* set_keys;
+    u64 set_mask;
+    int* status;
+    u64 dense_groups;
+};
+static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 7, "NqParams layout");
+
+u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
+
+}  // namespace
+
+bool have_device() {
+    static int n = -1;
+    if (n < 0) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0; n = c; cudaGetLastError(); }
+    return n > 0;
+}
+
+Query::~Query() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const char* where,
+                                      const std::vector<std::string>& key_texts, const std::vector<std::string>& agg_texts) {
+    if (!t || !t->sealed) N1_THROW(N1GPU_E_INVALID, "table must be sealed before a query is compiled");
+    std::unique_ptr<Query> q(new Query());
+    q->table = t;
+    q->alias = alias;
+    q->key_texts = key_texts;
+    q->agg_texts = agg_texts;
+    if (where && *where) { q->where_text = where; q->where = parse_expr(where); }
+    for (auto& k : key_texts) q->keys.push_back(parse_expr(k));
+    for (auto& a : agg_texts) q->aggs.push_back(parse_expr(a));
+    if (q->where) bind_and_analyze(*q->where, alias, *t);
+    for (auto& k : q->keys) {
+        if (k->kind == EK::AGG) N1_THROW(N1GPU_E_INELIGIBLE, "aggregate as a group key");
+        bind_and_analyze(*k, alias, *t);
+    }
+    for (auto& a : q->aggs) bind_and_analyze(*a, alias, *t);
+    if (q->aggs.size() > 24) N1_THROW(N1GPU_E_INELIGIBLE, "more than 24 aggregates");
+    q->kp = generate_kernel(*t, q->where.get(), q->keys, q->aggs, agg_texts, (double)std::max<i64>(t->nrows, 1) * 16.0);
+    if (q->kp.word_ops.size() > 64) N1_THROW(N1GPU_E_INELIGIBLE, "more than 64 accumulator words per group");
+    q->ops.n = (int)q->kp.word_ops.size();
+    for (int w = 0; w < q->ops.n; ++w) q->ops.op[w] = q->kp.word_ops[w];
+    if (have_device()) {
+        q->kernel = jit_load(q->kp.source);
+        CK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&q->ev0));
+        CK(cudaEventCreate(&q->ev1));
+        q->alloc_state();
+    } else {
+        // no GPU in this process (build / CPU test container): still prove the kernel compiles for sm_100a
+        std::string log;
+        jit_compile_cubin(q->kp.source, &log);
+    }
+    return q;
+}
+
+void Query::rebind(Table* t) {
+    if (!t || !t->sealed) N1_THROW(N1GPU_E_INVALID, "rebind needs a sealed table");
+    if (t->cols.size() != table->cols.size() || t->nrows != table->nrows) N1_THROW(N1GPU_E_INVALID, "rebind: schema mismatch");
+    for (size_t c = 0; c < t->cols.size(); ++c) {
+        const Column &a = t->cols[c], &b = table->cols[c];
+        if (a.path != b.path || a.width != b.width || a.stats.class_mask != b.stats.class_mask || a.stats.int_min != b.stats.int_min ||
+            a.stats.int_max != b.stats.int_max || a.dict != b.dict)
+            N1_THROW(N1GPU_E_INVALID, "rebind: column %zu differs in layout, statistics or dictionary", c);
+    }
+    table = t;
+}
+
+void Query::alloc_state() {
+    const int W = ops.n;
+    i64 blocks_needed = std::max<i64>(1, (table->nrows + 1023) / 1024);
+    grid = (int)std::min<i64>(blocks_needed, (i64)device_sm_count() * kernel->max_blocks_per_sm);
+    if (kp.mode == MODE_UNGROUPED) { cap = 1; d_partials.ensure((size_t)grid * W * 8); }
+    else if (kp.mode == MODE_DENSE) cap = (u64)kp.dense_slots;
+    else {
+        if (cap <= 1) {
+            double want = 2.0 * std::min((double)std::max<i64>(table->nrows, 1), (double)std::max<i64>(kp.est_groups, 1));
+            cap = pow2_at_least((u64)std::min(std::max(want, 1024.0), 67108864.0));
+        }
+        d_keys.ensure((size_t)cap * (kp.mode == MODE_HASH128 ? 16 : 8));
+    }
+    d_acc.ensure((size_t)cap * W * 8);
+    if (kp.ndistinct) {
+        if (set_cap == 0) {
+            double want = 2.0 * (double)std::max<i64>(table->nrows, 1) * kp.ndistinct;
+            set_cap = pow2_at_least((u64)std::min(std::max(want, 1024.0), 33554432.0));
+        }
+        d_set.ensure((size_t)set_cap * (kp.set128 ? 16 : 8));
+    }
+    d_status.ensure(64);
+    h_status.ensure(64);
+    d_counts.ensure(4096);
+    h_counts.ensure(4096);
+    if (kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) h_records.ensure((size_t)cap * W * 8);
+}
+
+void Query::reset_state() {
+    CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
+    if (kp.mode != MODE_UNGROUPED) launch_init_words(d_acc.as<u64>(), cap, ops, stream);
+    if (kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128) CK(cudaMemsetAsync(d_keys.p, 0xff, (size_t)cap * (kp.mode == MODE_HASH128 ? 16 : 8), stream));
+    if (kp.ndistinct) CK(cudaMemsetAsync(d_set.p, 0xff, (size_t)set_cap * (kp.set128 ? 16 : 8), stream));
+}
+
+void Query::launch_scan() {
+    if (!kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device: libn1gpu has no CPU fallback");
+    if (launched) N1_THROW(N1GPU_E_INVALID, "a scan is already outstanding on this query");
+    launches_at_start = g_launches.load();
+    NqParamsHost p{};
+    p.nrows = table->nrows;
+    for (size_t c = 0; c < table->cols.size(); ++c) { p.col[c] = table->cols[c].d_payload.p; p.tag[c] = table->cols[c].d_tags.as<u8>(); }
+    p.acc = kp.mode == MODE_UNGROUPED ? d_partials.as<u64>() : d_acc.as<u64>();
+    p.keys = d_keys.as<u64>();
+    p.cap_mask = cap - 1;
+    p.set_keys = d_set.as<u64>();
+    p.set_mask = set_cap ? set_cap - 1 : 0;
+    p.status = d_status.as<int>();
+    p.dense_groups = (u64)kp.dense_slots;
+    reset_state();
+    CK(cudaEventRecord(ev0, stream));
+    jit_launch(*kernel, grid, stream, &p, sizeof p);
+    if (kp.mode == MODE_UNGROUPED) launch_reduce_partials(d_partials.as<u64>(), grid, ops, d_acc.as<u64>(), stream);
+    CK(cudaEventRecord(ev1, stream));
+    CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
+    if (kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE)
+        CK(cudaMemcpyAsync(h_records.p, d_acc.p, (size_t)cap * ops.n * 8, cudaMemcpyDeviceToHost, stream));
+    launched = true;
+    ungrouped_live = true;
+}
+
+bool Query::wait_scan() {
+    if (!launched) N1_THROW(N1GPU_E_INVALID, "no scan outstanding");
+    launched = false;
+    CK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_scan_ms = ms;
+    int st = h_status.as<int>()[0];
+    if (st == 1) {
+        if (cap >= ((u64)1 << 31)) N1_THROW(N1GPU_E_NOMEM, "group table would exceed 2^31 slots");
+        cap *= 4;
+        d_keys.alloc((size_t)cap * (kp.mode == MODE_HASH128 ? 16 : 8));
+        d_acc.alloc((size_t)cap * ops.n * 8);
+        return false;
+    }
+    if (st == 2) {
+        if (set_cap >= ((u64)1 << 32)) N1_THROW(N1GPU_E_NOMEM, "DISTINCT set would exceed 2^32 slots");
+        set_cap *= 4;
+        d_set.alloc((size_t)set_cap * (kp.set128 ? 16 : 8));
+        return false;
+    }
+    host_acc_valid = kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE;
+    return true;
+}
+
+void Query::scan_blocking() {
+    for (;;) {
+        if (cancelled.load()) N1_THROW(N1GPU_E_CANCELLED, "query cancelled");
+        launch_scan();
+        if (wait_scan()) return;
+    }
+}
+
+// ---- partial state exchange -------------------------------------------------------------------------------------
+static void count_and_export(Query& q, int kw, const u64* keys, const u64* acc, u64 cap, int W, int nranks, int gk_pos, int gk_bits,
+                             u64* dev_out, i64 out_cap, i64* counts) {
+    if (nranks > 256) N1_THROW(N1GPU_E_INVALID, "at most 256 ranks");
+    CK(cudaMemsetAsync(q.d_counts.p, 0, 4096, q.stream));
+    launch_count_owners(kw, keys, acc, cap, nranks, gk_pos, gk_bits, q.d_counts.as<unsigned long long>(), q.stream);
+    CK(cudaMemcpyAsync(q.h_counts.p, q.d_counts.p, (size_t)nranks * 8, cudaMemcpyDeviceToHost, q.stream));
+    CK(cudaStreamSynchronize(q.stream));
+    unsigned long long* hc = q.h_counts.as<unsigned long long>();
+    unsigned long long offs[256];
+    unsigned long long total = 0;
+    for (int r = 0; r < nranks; ++r) { counts[r] = (i64)hc[r]; offs[r] = total; total += hc[r]; }
+    if (!dev_out) return;
+    if ((i64)total > out_cap) N1_THROW(N1GPU_E_INVALID, "export buffer too small: %llu records > capacity %lld", total, (long long)out_cap);
+    CK(cudaMemcpyAsync(q.d_counts.p, offs, (size_t)nranks * 8, cudaMemcpyHostToDevice, q.stream));
+    launch_export_records(kw, keys, acc, cap, W, nranks, gk_pos, gk_bits, q.d_counts.as<unsigned long long>(), dev_out, (u64)out_cap, q.stream);
+    CK(cudaStreamSynchronize(q.stream));
+}
+
+void Query::partial_counts(i64* ngroups, i64* ndistinct) {
+    i64 c[1] = {0};
+    count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, ops.n, 1, 0, std::max(kp.key_bits, 0), nullptr, 0, c);
+    if (kp.mode == MODE_UNGROUPED && !ungrouped_live) c[0] = 0;
+    *ngroups = c[0];
+    i64 d[1] = {0};
+    if (kp.ndistinct) count_and_export(*this, kp.set128 ? 2 : 1, d_set.as<u64>(), nullptr, set_cap, 0, 1, kp.abits, kp.key_bits, nullptr, 0, d);
+    *ndistinct = d[0];
+}
+
+void Query::partial_export(int nranks, void* dev_records, i64 cap_records, i64* counts, void* dev_distinct, i64 cap_distinct, i64* dcounts) {
+    count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, ops.n, nranks, 0, kp.key_bits, (u64*)dev_records, cap_records, counts);
+    if (kp.ndistinct)
+        count_and_export(*this, kp.set128 ? 2 : 1, d_set.as<u64>(), nullptr, set_cap, 0, nranks, kp.abits, kp.key_bits, (u64*)dev_distinct, cap_distinct, dcounts);
+    else for (int r = 0; r < nranks; ++r) dcounts[r] = 0;
+}
+
+void Query::partial_reset() {
+    if (!kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
+    reset_state();
+    if (kp.mode == MODE_UNGROUPED) launch_init_words(d_acc.as<u64>(), cap, ops, stream);
+    CK(cudaStreamSynchronize(stream));
+    ungrouped_live = false;
+    host_acc_valid = false;
+}
+
+void Query::partial_import(const void* dev_records, i64 n, const void* dev_distinct, i64 nd) {
+    if (!kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
+    host_acc_valid = false;
+    for (;;) {
+        CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
+        if (n > 0) launch_merge_records(kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, ops, (const u64*)dev_records, (u64)n, d_status.as<int>(), stream);
+        if (nd > 0) {
+            OpsArr none{};
+            none.n = 0;
+            launch_merge_records(kp.set128 ? 2 : 1, d_set.as<u64>(), nullptr, set_cap, none, (const u64*)dev_distinct, (u64)nd, d_status.as<int>() + 1, stream);
+        }
+        CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        int s0 = h_status.as<int>()[0], s1 = h_status.as<int>()[1];
+        if (!s0 && !s1) break;
+        N1_THROW(N1GPU_E_NOMEM, "merge overflowed the %s table; reset with a larger capacity", s0 ? "group" : "DISTINCT");
+    }
+    if (n > 0) ungrouped_live = true;
+}
+
+// ---- finalisation (FinalGroup / ComputeFinal) -----------------------------------------------------------------------
+namespace {
+struct BitReader {
+    unsigned __int128 v;
+    explicit BitReader(u64 lo, u64 hi) : v(((unsigned __int128)hi << 64) | lo) {}
+    u64 take(int n) {
+        if (n == 0) return 0;
+        u64 r = n >= 64 ? (u64)v : ((u64)v & (((u64)1 << n) - 1));
+        v >>= n;
+        return r;
+    }
+};
+
+HValue decode_comp(const Table& t, const PackComp& pc, BitReader& br) {
+    u64 ci = br.take(pc.cbits);
+    u64 pv = br.take(pc.pbits);
+    int cls = ci < pc.classes.size() ? pc.classes[ci] : C_MISSING;
+    switch (cls) {
+        case C_INT: return HValue::integer(pc.biased ? (i64)(pv + (u64)pc.bias) : (i64)pv);
+        case C_FLOAT: { HValue v; v.cls = C_FLOAT; v.bits = (i64)pv; return v; }
+        case C_STRING: {
+            const auto& d = t.cols[pc.dict_col].dict;
+            return HValue::str(pv < d.size() ? d[pv] : std::string());
+        }
+        case C_NULL: return HValue::null();
+        case C_FALSE: return HValue::boolean(false);
+        case C_TRUE: return HValue::boolean(true);
+        default: return HValue::missing();
+    }
+}
+
+double f64_unordered(u64 k) {
+    u64 u = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+}
+
+bool fits_i64(__int128 v) { return v >= (__int128)INT64_MIN && v <= (__int128)INT64_MAX; }
+
+struct SumState {
+    __int128 itotal = 0;
+    u64 n_nonneg = 0, n_neg = 0, n_flt = 0;
+    double fsum = 0;
+};
+// the SUM value as the reference's NumberValue chain would leave it (see header comment)
+HValue sum_value(const SumState& s, bool from_zero) {
+    u64 nI = s.n_nonneg + s.n_neg;
+    if (nI + s.n_flt == 0) return HValue::null();
+    if (s.n_flt == 0) {
+        bool same_sign = from_zero ? (s.n_neg == 0) : (s.n_neg == 0 || s.n_nonneg == 0);
+        if (same_sign && fits_i64(s.itotal)) return HValue::integer((i64)s.itotal);
+        return HValue::flt((double)s.itotal);
+    }
+    if (nI == 0) return HValue::flt(s.fsum);
+    return HValue::flt((double)s.itotal + s.fsum);
+}
+
+struct DistinctAcc {
+    u64 count = 0;
+    SumState sum;
+};
+
+struct KeyHash {
+    size_t operator()(const std::pair<u64, u64>& k) const { return (size_t)mix64(k.first ^ mix64(k.second)); }
+};
+}  // namespace
+
+std::unique_ptr<Result> Query::finalize() {
+    const int W = ops.n;
+    const int rw = 2 + W;
+    std::vector<u64> recs;
+    i64 ngroups = 0;
+    if ((kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) && h_records.p && !import_dirty()) {
+        // small state: the scan already copied the table words to pinned host memory
+        const u64* h = h_records.as<u64>();
+        for (u64 i = 0; i < cap; ++i) {
+            if (kp.mode == MODE_DENSE && h[i] == 0) continue;  // word 0 = rows in group
+            if (kp.mode == MODE_UNGROUPED && !ungrouped_live) continue;
+            recs.push_back(i); recs.push_back(0);
+            for (int w = 0; w < W; ++w) recs.push_back(h[(u64)w * cap + i]);
+            ++ngroups;
+        }
+    } else {
+        i64 c[1];
+        count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, W, 1, 0, kp.key_bits, nullptr, 0, c);
+        if (kp.mode == MODE_UNGROUPED && !ungrouped_live) c[0] = 0;
+        ngroups = c[0];
+        if (ngroups) {
+            d_records.ensure((size_t)ngroups * rw * 8);
+            i64 c2[1];
+            count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, W, 1, 0, kp.key_bits, d_records.as<u64>(), ngroups, c2);
+            recs.resize((size_t)ngroups * rw);
+            CK(cudaMemcpy(recs.data(), d_records.p, recs.size() * 8, cudaMemcpyDeviceToHost));
+        }
+    }
+    // DISTINCT entries
+    std::vector<u64> ents;
+    if (kp.ndistinct) {
+        i64 d[1];
+        int skw = kp.set128 ? 2 : 1;
+        count_and_export(*this, skw, d_set.as<u64>(), nullptr, set_cap, 0, 1, kp.abits, kp.key_bits, nullptr, 0, d);
+        if (d[0]) {
+            d_drecords.ensure((size_t)d[0] * 16);
+            i64 d2[1];
+            count_and_export(*this, skw, d_set.as<u64>(), nullptr, set_cap, 0, 1, kp.abits, kp.key_bits, d_drecords.as<u64>(), d[0], d2);
+            ents.resize((size_t)d[0] * 2);
+            CK(cudaMemcpy(ents.data(), d_drecords.p, ents.size() * 8, cudaMemcpyDeviceToHost));
+        }
+    }
+
+    std::unique_ptr<Result> res(new Result());
+    res->nkeys = (int)keys.size();
+    res->naggs = (int)aggs.size();
+    res->ngroups = ngroups;
+    res->agg_texts = agg_texts;
+    res->key_texts = key_texts;
+    res->alias = alias;
+    for (auto& k : keys) {
+        std::vector<std::string> path;
+        if (k->kind == EK::FIELD && k->col >= 0) path = table->cols[k->col].path;
+        res->key_paths.push_back(path);
+    }
+    res->keys.resize((size_t)ngroups * res->nkeys);
+    res->aggs.resize((size_t)ngroups * res->naggs);
+
+    // group index by packed key, for DISTINCT entries
+    std::unordered_map<std::pair<u64, u64>, i64, KeyHash> index;
+    std::vector<DistinctAcc> dacc;
+    if (kp.ndistinct) {
+        index.reserve((size_t)ngroups * 2);
+        for (i64 g = 0; g < ngroups; ++g) index.emplace(std::make_pair(recs[(size_t)g * rw], recs[(size_t)g * rw + 1]), g);
+        dacc.resize((size_t)ngroups * kp.ndistinct);
+        std::vector<const AggPlan*> by_id((size_t)kp.ndistinct, nullptr);
+        for (auto& ap : kp.aggs) if (ap.distinct) by_id[(size_t)ap.distinct_id] = &ap;
+        for (size_t e = 0; e + 1 < ents.size(); e += 2) {
+            BitReader br(ents[e], ents[e + 1]);
+            u64 aid = br.take(kp.abits);
+            u64 klo = br.take(std::min(64, kp.key_bits));
+            u64 khi = kp.key_bits > 64 ? br.take(kp.key_bits - 64) : 0;
+            if (aid >= (u64)kp.ndistinct) continue;
+            auto it = index.find(std::make_pair(klo, khi));
+            if (it == index.end()) continue;  // entry of a group this rank does not own
+            HValue v = decode_comp(*table, by_id[aid]->dcomp, br);
+            DistinctAcc& da = dacc[(size_t)it->second * kp.ndistinct + aid];
+            da.count++;
+            if (v.cls == C_INT) { da.sum.itotal += v.bits; if (v.bits >= 0) da.sum.n_nonneg++; else da.sum.n_neg++; }
+            else if (v.cls == C_FLOAT) { da.sum.fsum += v.f(); da.sum.n_flt++; }
+        }
+    }
+
+    for (i64 g = 0; g < ngroups; ++g) {
+        const u64* r = &recs[(size_t)g * rw];
+        const u64* w = r + 2;
+        BitReader br(r[0], r[1]);
+        for (int k = 0; k < res->nkeys; ++k) res->keys[(size_t)g * res->nkeys + k] = decode_comp(*table, kp.keys[k], br);
+        for (int a = 0; a < res->naggs; ++a) {
+            const AggPlan& ap = kp.aggs[a];
+            HValue out;
+            if (ap.distinct) {
+                const DistinctAcc& da = dacc[(size_t)g * kp.ndistinct + ap.distinct_id];
+                if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) out = HValue::integer((i64)da.count);
+                else if (da.count == 0) out = HValue::null();
+                else {
+                    HValue s = sum_value(da.sum, true);
+                    if (ap.kind == AggKind::SUM) out = s;
+                    else out = new_num(s.num() / (double)da.count);
+                }
+            } else if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) {
+                out = HValue::integer((i64)w[ap.w_cnt]);
+            } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
+                SumState s;
+                if (ap.w_isum >= 0) s.itotal = (i64)w[ap.w_isum];
+                else if (ap.w_ilo >= 0) s.itotal = (((__int128)(i64)w[ap.w_ihi]) << 32) + (__int128)w[ap.w_ilo];
+                if (ap.w_nonneg >= 0) s.n_nonneg = w[ap.w_nonneg];
+                if (ap.w_neg >= 0) s.n_neg = w[ap.w_neg];
+                if (ap.w_nflt >= 0) s.n_flt = w[ap.w_nflt];
+                if (ap.w_fsum >= 0) memcpy(&s.fsum, &w[ap.w_fsum], 8);
+                HValue sv = sum_value(s, false);
+                if (ap.kind == AggKind::SUM || sv.cls == C_NULL) out = sv;
+                else out = new_num(sv.num() / (double)(s.n_nonneg + s.n_neg + s.n_flt));
+            } else {
+                bool mn = ap.kind == AggKind::MIN;
+                u64 seen = w[ap.w_seen];
+                auto number = [&]() -> HValue {
+                    bool hi = seen & bit(C_INT), hf = seen & bit(C_FLOAT);
+                    i64 iv = ap.w_mi >= 0 ? (i64)w[ap.w_mi] : 0;
+                    double fv = ap.w_mf >= 0 ? f64_unordered(w[ap.w_mf]) : 0;
+                    if (hi && hf) {
+                        double a = (double)iv;  // intValue.Collate(floatValue): float64 compare (value/integer.go:100-118)
+                        bool pick_int = mn ? (a <= fv) : (a >= fv);
+                        return pick_int ? HValue::integer(iv) : HValue::flt(fv);
+                    }
+                    return hi ? HValue::integer(iv) : HValue::flt(fv);
+                };
+                auto str = [&]() { const auto& d = table->cols[ap.dict_col].dict; u64 c = w[ap.w_ms]; return HValue::str(c < d.size() ? d[c] : std::string()); };
+                if (seen == 0) out = HValue::null();
+                else if (mn) {
+                    if (seen & bit(C_FALSE)) out = HValue::boolean(false);
+                    else if (seen & bit(C_TRUE)) out = HValue::boolean(true);
+                    else if (seen & M_NUM) out = number();
+                    else out = str();
+                } else {
+                    if (seen & bit(C_STRING)) out = str();
+                    else if (seen & M_NUM) out = number();
+                    else if (seen & bit(C_TRUE)) out = HValue::boolean(true);
+                    else out = HValue::boolean(false);
+                }
+            }
+            res->aggs[(size_t)g * res->naggs + a] = out;
+        }
+    }
+    i64 scan_bytes = (i64)kp.scan_bytes_per_row * table->nrows;
+    res->stats[0] = table->nrows;
+    res->stats[1] = ngroups;
+    res->stats[2] = (i64)(last_scan_ms * 1e6);
+    res->stats[3] = (i64)((table->shred_sec + table->upload_sec) * 1e9);
+    res->stats[4] = scan_bytes;
+    res->stats[5] = (i64)(g_launches.load() - launches_at_start);
+    return res;
+}
+
+}  // namespace n1

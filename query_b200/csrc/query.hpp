@@ -1,0 +1,68 @@
+// query.hpp — a compiled Filter + InitialGroup/IntermediateGroup/FinalGroup chain bound to a table.
+#pragma once
+#include <atomic>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "codegen.hpp"
+#include "jit.hpp"
+#include "kernels.hpp"
+
+namespace n1 {
+
+struct Result {
+    int nkeys = 0, naggs = 0;
+    i64 ngroups = 0;
+    std::vector<HValue> keys;  // [ngroups][nkeys]
+    std::vector<HValue> aggs;  // [ngroups][naggs]
+    std::vector<std::string> strings;  // string table filled by fetch()
+    std::vector<std::string> agg_texts, key_texts;
+    std::vector<std::vector<std::string>> key_paths;  // field path of each key (empty: computed key)
+    std::string alias;
+    i64 stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct Query {
+    Table* table = nullptr;
+    std::string alias, where_text;
+    std::vector<std::string> key_texts, agg_texts;
+    ExprP where;
+    std::vector<ExprP> keys, aggs;
+    KernelPlan kp;
+    std::shared_ptr<JitKernel> kernel;
+    OpsArr ops{};
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int grid = 0;
+    u64 cap = 1;      // group slots (1 / dense slots / hash capacity)
+    u64 set_cap = 0;  // DISTINCT entry set capacity
+    DevBuf d_partials, d_acc, d_keys, d_set, d_status, d_counts, d_records, d_drecords;
+    PinnedBuf h_status, h_counts, h_records, h_drecords;
+    std::atomic<bool> cancelled{false};
+    bool launched = false;
+    bool ungrouped_live = true;
+    bool host_acc_valid = false;  // h_records holds the table words of the last scan (small-state modes)
+    bool import_dirty() const { return !host_acc_valid; }
+    double last_scan_ms = 0;
+    u64 launches_at_start = 0;
+
+    ~Query();
+    static std::unique_ptr<Query> compile(Table* t, const std::string& alias, const char* where,
+                                          const std::vector<std::string>& keys, const std::vector<std::string>& aggs);
+    int kw() const { return kp.mode == MODE_UNGROUPED ? 3 : (kp.mode == MODE_DENSE ? 0 : (kp.mode == MODE_HASH64 ? 1 : 2)); }
+    void alloc_state();
+    void reset_state();               // clears tables (async on stream)
+    void launch_scan();               // enqueue reset + scan (+ partial reduction)
+    bool wait_scan();                 // sync; returns false when a table overflowed and was grown (caller relaunches)
+    void scan_blocking();             // launch + wait, growing tables as needed
+    void partial_counts(i64* ngroups, i64* ndistinct);
+    void partial_export(int nranks, void* dev_records, i64 cap_records, i64* counts, void* dev_distinct, i64 cap_distinct, i64* dcounts);
+    void partial_reset();
+    void partial_import(const void* dev_records, i64 n, const void* dev_distinct, i64 nd);
+    std::unique_ptr<Result> finalize();
+    void rebind(Table* t);
+};
+
+}  // namespace n1

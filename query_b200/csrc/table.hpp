@@ -1,0 +1,63 @@
+// table.hpp — a shredded keyspace: typed columns + per-column sorted dictionaries, resident in HBM.
+#pragma once
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.hpp"
+
+namespace n1 {
+
+const i64 ROW_PAD = 4096;  // device arrays are padded to a multiple of this many rows (vector loads never fault)
+
+struct ColumnStats {
+    u32 class_mask = 0;  // classes that occur (bit per C_*)
+    bool has_int = false;
+    i64 int_min = 0, int_max = 0;
+    bool has_float = false;
+    double flt_min = 0, flt_max = 0;
+    i64 ndict = 0;
+    i64 empty_rank = -1;  // rank of "" in the dictionary, -1 if absent
+    bool uniform_tag() const { return class_mask != 0 && (class_mask & (class_mask - 1)) == 0; }
+};
+
+struct Column {
+    std::vector<std::string> path;       // field names below the document root
+    // host staging (dropped after seal unless keep_host)
+    std::vector<i64> payload;            // 8 bytes per row while staging
+    std::vector<u8> tags;
+    std::vector<std::string> dict;       // sorted, unique (after seal / import)
+    bool dict_global = false;            // dictionary imported (multi-GPU): do not rebuild at seal
+    std::vector<std::string> local_strings;  // staging: distinct strings, codes index this until seal
+    bool codes_are_ranks = false;        // set_column supplied ranks into `dict` already
+    ColumnStats stats;
+    bool stats_forced = false;
+    int width = 8;                       // device payload width: 8, 4 or 0
+    DevBuf d_payload, d_tags;
+};
+
+struct Table {
+    std::vector<Column> cols;
+    i64 nrows = 0;
+    bool sealed = false;
+    bool appended = false;
+    double shred_sec = 0, upload_sec = 0;
+    i64 json_bytes = 0;
+
+    int add_column(const std::string& path);
+    int find_column(const std::string& path) const;
+    void append_json(const char* buf, const i64* offsets, i64 ndocs, int threads);
+    void load_dir(const std::string& dir, int threads);
+    void set_column(int col, int width, const void* payload, const u8* tags, i64 nrows, const char* blob,
+                    const i64* offs, i64 ndict);
+    void build_dictionary(int col);  // local strings -> sorted dict, codes -> ranks
+    void seal();
+    int scan_bytes(int col) const;
+    i64 padded_rows() const { return (nrows + ROW_PAD - 1) / ROW_PAD * ROW_PAD; }
+};
+
+std::vector<std::string> split_path(const std::string& path);
+std::string join_path(const std::vector<std::string>& p, char sep);
+
+}  // namespace n1

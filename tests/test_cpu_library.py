@@ -1,0 +1,179 @@
+"""CPU-side checks of libn1gpu.so (no GPU needed): the C ABI loads and exports every declared symbol,
+the shredder matches the oracle's document model, every query of the matrix compiles to an sm_100a
+cubin through NVRTC, and the error contract (parse / ineligible / no-device) holds."""
+import json
+
+import numpy as np
+import pytest
+
+import query_b200 as q
+from gen_n1 import QUERIES, F, make_docs
+from golden_plans import CASES, WHERE_CASES, keyspaces
+from oracle import n1ql_oracle as O
+from util_n1 import make_table, oracle_rows, paths_of
+
+
+def test_library_exports_every_declared_symbol():
+    L = q.lib()
+    names = q.declared_symbols()
+    assert len(names) >= 50
+    for n in names:
+        assert hasattr(L, n), n
+    assert b"sm_100a" in L.n1gpu_version()
+
+
+def _shred_check(docs, paths):
+    t = q.Table([list(p) for p in paths])
+    t.append_json(docs, threads=3)
+    parsed = [O.parse_document(d) for d in docs]
+    for p in paths:
+        pay, tags = t.peek(list(p))
+        d = t.dictionary(list(p))
+        for r, doc in enumerate(parsed):
+            v = doc
+            for name in p:
+                v = O.field(v, name)
+            ty = O.vtype(v)
+            if ty == O.T_MISSING:
+                assert tags[r] == 0, (p, r)
+            elif ty == O.T_NULL:
+                assert tags[r] == 1
+            elif ty == O.T_BOOLEAN:
+                assert tags[r] == (3 if v else 2)
+            elif ty == O.T_NUMBER and isinstance(v, int):
+                assert tags[r] == 4 and int(pay[r]) == v, (p, r, v, int(pay[r]))
+            elif ty == O.T_NUMBER:
+                assert tags[r] == 5 and O.float_bits(v) == int(pay[r])
+            elif ty == O.T_STRING:
+                assert tags[r] == 6 and d[int(pay[r])] == v.encode("utf-8")
+            else:
+                assert tags[r] == 7
+        assert d == sorted(d), "dictionary must be bytewise sorted"
+
+
+def test_shredder_matches_oracle_on_synthetic_docs():
+    docs = make_docs(3000, seed=11)
+    _shred_check(docs, [("i",), ("n",), ("f",), ("s",), ("b",), ("m",), ("nest", "k"), ("nest", "deep", "x"), ("nest",), ("absent",)])
+
+
+@pytest.mark.parametrize("name", ["filestore/mixed", "filestore/catalog", "filestore/non-json", "filestore/orders",
+                                  "multistore/integers/orders", "filestore/user_profile"])
+def test_shredder_matches_oracle_on_reference_fixtures(name):
+    docs = [t for _k, t in keyspaces()[name]]
+    paths = set()
+    for d in docs:
+        v = O.parse_document(d)
+        if isinstance(v, dict):
+            for k, x in v.items():
+                paths.add((k,))
+                if isinstance(x, dict):
+                    for k2 in x:
+                        paths.add((k, k2))
+    _shred_check(docs, sorted(paths)[:16])
+
+
+def test_shredder_edge_documents():
+    docs = ['{"a": 1, "a": 2}',            # duplicate name: first wins (FirstFind)
+            '  \n\t{"a": 1.0}',            # leading whitespace, integral float -> int
+            '"hello"', '[1,2]', '17',      # non-object documents: all MISSING
+            '{"a": 1} trailing',           # invalid JSON -> BINARY -> MISSING
+            '{"a": 1e2}', '{"a": -0.0}', '{"a": 9223372036854775807}', '{"a": 9223372036854775808}',
+            '{"a": "\\u00e9\\ud83d\\ude00"}', '{"\\u0061": 5}', '{"a": {"b": 1}}', '{"a": tru}', '']
+    t = q.Table(["a"])
+    t.append_json(docs, threads=1)
+    pay, tags = t.peek("a")
+    d = t.dictionary("a")
+    assert list(tags[:2]) == [4, 4] and list(pay[:2]) == [1, 1]
+    assert list(tags[2:6]) == [0, 0, 0, 0]
+    assert tags[6] == 4 and pay[6] == 100
+    assert tags[7] == 4 and pay[7] == 0
+    assert tags[8] == 4 and pay[8] == 9223372036854775807
+    assert tags[9] == 5 and O.float_bits(9223372036854775808.0) == int(pay[9])
+    assert tags[10] == 6 and d[int(pay[10])] == "é\U0001F600".encode("utf-8")
+    assert tags[11] == 4 and pay[11] == 5
+    assert tags[12] == 7
+    assert tags[13] == 0 and tags[14] == 0
+    # and the oracle's document model agrees
+    for r, doc in enumerate(docs):
+        v = O.field(O.parse_document(doc), "a")
+        assert (O.vtype(v) == O.T_MISSING) == (tags[r] == 0), (r, doc)
+
+
+@pytest.mark.parametrize("name,where,keys,aggs", QUERIES, ids=[x[0] for x in QUERIES])
+def test_every_matrix_query_compiles_for_sm100a_and_oracle_runs(name, where, keys, aggs):
+    docs = make_docs(400, seed=5)
+    t = make_table(docs, where, keys, aggs)
+    t.seal()
+    qq = q.Query(t, "d", where, keys, aggs)
+    src = qq.kernel_source
+    assert "nq_scan" in src and "__ballot_sync" in src
+    assert qq.info["words"] >= 1
+    assert oracle_rows(docs, "d", where, keys, aggs) is not None
+
+
+@pytest.mark.parametrize("case", CASES + WHERE_CASES, ids=lambda c: c.id)
+def test_every_golden_plan_compiles(case):
+    docs = [t for _k, t in case.docs()]
+    t = make_table(docs, case.where, case.keys, case.aggs)
+    t.seal()
+    qq = q.Query(t, case.alias, case.where, case.keys, case.aggs)
+    assert qq.info["mode"] in ("ungrouped", "dense-shared-memory", "hbm-hash-64", "hbm-hash-128")
+
+
+def _expect(code, fn):
+    with pytest.raises(q.N1GpuError) as ei:
+        fn()
+    assert ei.value.code == code, ei.value
+    return ei.value
+
+
+def test_error_contract():
+    docs = ['{"a": 1, "arr": [1,2], "s": "x", "s2": "y"}', '{"a": 2, "arr": [3], "s": "z", "s2": "w"}']
+    t = q.Table(["a", "arr", "s", "s2"])
+    t.append_json(docs)
+    t.seal()
+    E = q._lib
+    _expect(E.E_PARSE, lambda: q.Query(t, "d", "((`d`.`a`) <", [], ["count(*)"]))
+    # outside the subset -> INELIGIBLE (the caller keeps its Go operators); never a silent fallback
+    for where in ["((`d`.`s`) like \"x%\")", "(length((`d`.`s`)) < 3)", "any `x` in (`d`.`arr`) satisfies (`x` = 1) end",
+                  "((`d`.`arr`) = [1, 2])", "((`d`.`s`) < (`d`.`s2`))", "(`d` is valued)", "((`e`.`a`) = 1)"]:
+        e = _expect(E.E_INELIGIBLE, lambda: q.Query(t, "d", where, [], ["count(*)"]))
+        assert isinstance(e, q.Ineligible)
+    _expect(E.E_INELIGIBLE, lambda: q.Query(t, "d", None, ["(`d`.`arr`)"], ["count(*)"]))
+    _expect(E.E_INELIGIBLE, lambda: q.Query(t, "d", None, [], ["array_agg((`d`.`a`))"]))
+    _expect(E.E_INELIGIBLE, lambda: q.Query(t, "d", None, [], ["min(distinct (`d`.`a`))"]))
+    _expect(E.E_INVALID, lambda: q.Query(t, "d", "((`d`.`unknown`) = 1)", [], ["count(*)"]))
+    t2 = q.Table(["a"])
+    t2.append_json(docs)
+    _expect(E.E_INVALID, lambda: q.Query(t2, "d", None, [], ["count(*)"]))  # not sealed
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    t = q.Table(["a"])
+    t.append_json(['{"a": 1}'])
+    t.seal()
+    qq = q.Query(t, "d", None, [], ["count(*)"])
+    e = _expect(q._lib.E_CUDA, qq.execute)
+    assert "no CPU fallback" in str(e)
+    _expect(q._lib.E_CUDA, lambda: q.init(0))
+
+
+def test_plan_build_substitution_rules(tmp_path):
+    from util_n1 import write_keyspace
+    write_keyspace(str(tmp_path), "default", "game", keyspaces()["filestore/game"])
+    from plans_n1 import explain_plan
+    plan = explain_plan("default", "game", None, None, [], ["count(*)", "min((`game`.`score`))"])
+    import torch
+    if torch.cuda.is_available():
+        op = q.Operator(plan, str(tmp_path))
+        assert op.rest_index == 5
+    # ineligible shapes are refused with INELIGIBLE whatever the device situation
+    bad = json.loads(json.dumps(plan))
+    bad["~children"][0]["~children"][0]["limit"] = "10"
+    _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(bad, str(tmp_path)))
+    nogroup = {"#operator": "Sequence", "~children": [plan["~children"][0]["~children"][0], plan["~children"][0]["~children"][1]]}
+    _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(nogroup, str(tmp_path)))
+    _expect(q._lib.E_PARSE, lambda: q.Operator("{not json", str(tmp_path)))

@@ -1,0 +1,259 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, driven through the C ABI, against
+(a) the reference's golden vectors, (b) the oracle on seeded synthetic documents, bit-exact for
+COUNT / MIN / MAX / integer SUM / group keys / DISTINCT sets and <= 1e-12 relative for float SUM/AVG."""
+import json
+
+import numpy as np
+import pytest
+
+import query_b200 as q
+from gen_n1 import QUERIES, F, make_docs
+from golden_plans import CASES, WHERE_CASES, _MISSING, keyspaces, normalise
+from plans_n1 import explain_plan
+from util_n1 import assert_same, gpu_rows, make_table, oracle_rows, run_both, write_keyspace
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    q.init(0)
+
+
+def _groups_for_projection(result, aggs):
+    out = []
+    for ks, ag in result.rows():
+        keys = [_MISSING if k is q.MISSING else k for k in ks]
+        out.append((keys, {a: normalise(v) for a, v in zip(aggs, ag)}))
+    return out
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.id)
+def test_golden_through_query_abi(case):
+    docs = [t for _k, t in case.docs()]
+    aggs = sorted(set(case.aggs))
+    qq, res = run_both(docs, case.alias, case.where, case.keys, aggs, case.id)
+    got = case.project(_groups_for_projection(res, aggs))
+    assert normalise(got) == normalise(case.golden["results"]), case.golden["statements"]
+
+
+@pytest.mark.parametrize("case", WHERE_CASES, ids=lambda c: c.id)
+def test_golden_filters_through_query_abi(case):
+    docs = [t for _k, t in case.docs()]
+    qq, res = run_both(docs, case.alias, case.where, case.keys, case.aggs, case.id)
+    assert res.rows() == [([], [len(case.golden["results"])])]
+
+
+@pytest.mark.parametrize("case", CASES[:6] + CASES[10:14], ids=lambda c: c.id)
+def test_golden_through_plan_operator(case, tmp_path):
+    """The reference-facing entry: plan JSON in EXPLAIN shape + a file-datastore directory."""
+    ns, ks = "default", case.keyspace.split("/")[-1]
+    write_keyspace(str(tmp_path), ns, ks, case.docs())
+    aggs = sorted(set(case.aggs))
+    plan = explain_plan(ns, ks, case.alias, case.where, case.keys, aggs)
+    op = q.Operator(plan, str(tmp_path))
+    assert op.rest_index == 5  # the caller still runs the projection Parallel
+    res = op.run_once()
+    got = case.project(_groups_for_projection(res, aggs))
+    assert normalise(got) == normalise(case.golden["results"])
+    m = op.marshal_json()
+    assert m["#operator"] == "GpuGroupAggregate" and m["#stats"]["#itemsIn"] == len(case.docs())
+    rows = res.to_json()
+    assert len(rows) == res.num_groups
+    for r in rows:
+        assert set(r["aggregates"].keys()) == set(aggs)
+    with pytest.raises(q.N1GpuError):
+        op.run_once()  # util.Once
+
+
+@pytest.mark.parametrize("name,where,keys,aggs", QUERIES, ids=[x[0] for x in QUERIES])
+def test_matrix_against_oracle(name, where, keys, aggs):
+    docs = make_docs(3000, seed=21)
+    qq, res = run_both(docs, "d", where, keys, aggs, name)
+    assert res.stats["rows"] == 3000
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 127, 128, 129, 1023, 1024, 1025, 4097])
+def test_ragged_sizes(n):
+    docs = make_docs(n, seed=100 + n)
+    for name, where, keys, aggs in [QUERIES[0], QUERIES[6], QUERIES[33], QUERIES[41], QUERIES[50]]:
+        run_both(docs, "d", where, keys, aggs, "%s n=%d" % (name, n))
+
+
+def test_empty_table_defaults_row():
+    """group_final.go:108-117: no keys and no input -> one row of Default() values; with keys -> nothing."""
+    t = q.Table(["n"])
+    t.append_json([])
+    t.seal()
+    r = q.Query(t, "d", None, [], ["count(*)", "sum((`d`.`n`))", "avg((`d`.`n`))", "min((`d`.`n`))", "count(distinct (`d`.`n`))"]).execute()
+    assert r.rows() == [([], [0, None, None, None, 0])]
+    assert q.Query(t, "d", None, ["(`d`.`n`)"], ["count(*)"]).execute().rows() == []
+
+
+def test_int_sum_overflow_and_sign_semantics():
+    """value/integer.go:266-277 through SUM: exact int64 near MaxInt64 (golden integers/case_select.json:33-40),
+    overflow -> float64, mixed signs -> float64 (integral, renders as an integer)."""
+    def s(xs):
+        t = q.Table(["n"])
+        t.append_json([json.dumps({"n": x}) for x in xs])
+        t.seal()
+        return q.Query(t, "d", None, [], ["sum((`d`.`n`))"]).execute().rows()[0][1][0]
+    assert s([9223372036854775707, 99, 1]) == 9223372036854775807 and isinstance(s([9223372036854775707, 99, 1]), int)
+    v = s([9223372036854775807, 1])
+    assert isinstance(v, float) and v == 9.223372036854775808e18
+    v = s([5, -3])
+    assert isinstance(v, float) and v == 2.0
+    assert s([-5, -6]) == -11 and isinstance(s([-5, -6]), int)
+    v = s([-9223372036854775808, -1])
+    assert isinstance(v, float) and v == -9.223372036854775808e18
+
+
+def test_preshredded_columns_properties_10m():
+    """BASELINE config 2 at full size through size-independent properties: counts add up, SUM is linear over a
+    partition of the predicate, MIN/MAX bound the selection, exact against numpy int64 arithmetic."""
+    n = 10_000_000
+    rng = np.random.default_rng(1)
+    nn = rng.integers(0, 1_000_000, n, dtype=np.int64)
+    ff = rng.random(n)
+    t = q.Table(["n", "f"])
+    t.set_column("n", nn)
+    t.set_column("f", ff, tags=np.full(n, 5, dtype=np.uint8))
+    t.seal()
+    aggs = ["count(*)", "count((`d`.`n`))", "sum((`d`.`n`))", "avg((`d`.`n`))", "min((`d`.`n`))", "max((`d`.`n`))", "sum((`d`.`f`))"]
+    tot = None
+    parts = []
+    for lo, hi in [(0, 999_999), (0, 9_999), (10_000, 499_999), (500_000, 999_999)]:
+        r = q.Query(t, "d", "((`d`.`n`) between %d and %d)" % (lo, hi), [], aggs).execute().rows()[0][1]
+        m = (nn >= lo) & (nn <= hi)
+        assert r[0] == int(m.sum()) and r[1] == r[0]
+        assert r[2] == int(nn[m].sum())
+        assert r[4] == int(nn[m].min()) and r[5] == int(nn[m].max())
+        exp_avg = float(int(nn[m].sum())) / float(int(m.sum()))
+        assert r[3] == (int(exp_avg) if exp_avg == int(exp_avg) else exp_avg)
+        fs = float(np.sum(ff[m]))
+        assert abs(r[6] - fs) <= 1e-12 * abs(fs)
+        if tot is None:
+            tot = r
+        else:
+            parts.append(r)
+    assert sum(p[0] for p in parts) == tot[0]
+    assert sum(p[2] for p in parts) == tot[2]
+    assert abs(sum(p[6] for p in parts) - tot[6]) <= 1e-12 * tot[6]
+    # run-to-run determinism of the float sum (fixed reduction order)
+    qq = q.Query(t, "d", None, [], ["sum((`d`.`f`))"])
+    a = qq.execute().rows()[0][1][0]
+    b = qq.execute().rows()[0][1][0]
+    assert a == b
+
+
+def test_preshredded_group_by_high_cardinality_2m():
+    """1M-group style GROUP BY (BASELINE config 4 shape) checked against numpy: exact counts / int sums / DISTINCT."""
+    n = 2_000_000
+    rng = np.random.default_rng(3)
+    g = rng.integers(0, 200_000, n, dtype=np.int64)
+    x = rng.integers(0, 1000, n, dtype=np.int64)
+    t = q.Table(["g", "x"])
+    t.set_column("g", g)
+    t.set_column("x", x)
+    t.seal()
+    aggs = ["count(*)", "sum((`d`.`x`))", "count(distinct (`d`.`x`))", "sum(distinct (`d`.`x`))", "max((`d`.`x`))"]
+    qq = q.Query(t, "d", None, ["(`d`.`g`)"], aggs)
+    assert qq.info["mode"] == "hbm-hash-64"
+    res = qq.execute()
+    rows = res.rows()
+    order = np.argsort(g, kind="stable")
+    gs, xs = g[order], x[order]
+    uniq, start = np.unique(gs, return_index=True)
+    assert len(rows) == len(uniq)
+    cnt = np.diff(np.append(start, n))
+    sums = np.add.reduceat(xs, start)
+    maxs = np.maximum.reduceat(xs, start)
+    pair = np.unique(gs * 1000 + xs)
+    pg = pair // 1000
+    pv = pair % 1000
+    dcount = np.bincount(np.searchsorted(uniq, pg), minlength=len(uniq))
+    dsum = np.bincount(np.searchsorted(uniq, pg), weights=pv.astype(np.float64), minlength=len(uniq)).astype(np.int64)
+    idx = {int(k): i for i, k in enumerate(uniq)}
+    for ks, ag in rows:
+        i = idx[ks[0]]
+        assert ag == [int(cnt[i]), int(sums[i]), int(dcount[i]), int(dsum[i]), int(maxs[i])]
+
+
+def test_launch_collect_pipeline_and_rebind():
+    n = 100_000
+    rng = np.random.default_rng(5)
+    tabs = []
+    for k in range(2):
+        t = q.Table(["n"])
+        t.set_column("n", np.arange(n, dtype=np.int64) if k == 0 else np.arange(n, dtype=np.int64)[::-1].copy())
+        t.seal()
+        tabs.append(t)
+    qq = q.Query(tabs[0], "d", "((`d`.`n`) < 1000)", [], ["count(*)", "sum((`d`.`n`))"])
+    before = q.launch_count()
+    qq.launch()
+    r0 = qq.collect().rows()
+    qq.rebind(tabs[1])
+    r1 = qq.execute().rows()
+    assert r0 == r1 == [([], [1000, 499500])]
+    assert q.launch_count() - before >= 4
+    assert qq.last_scan_ns > 0
+
+
+def test_multi_rank_partial_merge_single_gpu():
+    """The Intermediate->Final exchange (group_intermediate.go:56-104) emulated on one GPU: two 'ranks' scan
+    half the rows each, export owner-bucketed records to device buffers, the owners import and finalise; the
+    union of the owners' groups equals the single-scan result.  (NCCL only moves the buffers.)"""
+    import torch
+    docs = make_docs(6000, seed=77)
+    for name, where, keys, aggs in [QUERIES[0], QUERIES[33], QUERIES[40], QUERIES[41], QUERIES[43], QUERIES[49], QUERIES[50], QUERIES[53]]:
+        full = make_table(docs, where, keys, aggs)
+        halves = [make_table(docs[:3000], where, keys, aggs), make_table(docs[3000:], where, keys, aggs)]
+        # global dictionaries + statistics so every rank compiles the same kernel (n1gpu_table_dict_*/stats_*)
+        for c in range(len(full.columns)):
+            merged = sorted(set(halves[0].dictionary(c)) | set(halves[1].dictionary(c)))
+            st = [h.stats(c) for h in halves]
+            g = st[0].copy()
+            g[0] = st[0][0] | st[1][0]
+            has = [s[1] != 0 for s in st]
+            g[1] = int(any(has))
+            mins = [s[2] for s, h in zip(st, has) if h]
+            maxs = [s[3] for s, h in zip(st, has) if h]
+            g[2] = min(mins) if mins else 0
+            g[3] = max(maxs) if maxs else 0
+            g[4] = st[0][4] | st[1][4]
+            g[5] = len(merged)
+            for h in halves:
+                h.import_dictionary(c, merged)
+                h.set_stats(c, g)
+        full.seal()
+        exp = gpu_rows(q.Query(full, "d", where, keys, aggs).execute(), aggs)
+        assert_same(oracle_rows(docs, "d", where, keys, aggs), exp, name)
+        qs = []
+        for h in halves:
+            h.seal()
+            qq = q.Query(h, "d", where, keys, aggs)
+            qq.scan_partial()
+            qs.append(qq)
+        nranks = 2
+        exported = []
+        for qq in qs:
+            ng, nd, rw = qq.partial_counts()
+            recs = torch.zeros(max(1, ng) * rw, dtype=torch.int64, device="cuda")
+            dents = torch.zeros(max(1, nd) * 2, dtype=torch.int64, device="cuda")
+            counts, dcounts = qq.partial_export(nranks, recs.data_ptr(), ng, dents.data_ptr(), nd)
+            assert counts.sum() == ng and dcounts.sum() == nd
+            exported.append((recs, dents, counts, dcounts, rw))
+        got = {}
+        for owner in range(nranks):
+            qq = qs[owner]
+            qq.partial_reset()
+            for recs, dents, counts, dcounts, rw in exported:
+                o = int(counts[:owner].sum())
+                do = int(dcounts[:owner].sum())
+                r = recs[o * rw:(o + int(counts[owner])) * rw].contiguous()
+                d = dents[do * 2:(do + int(dcounts[owner])) * 2].contiguous()
+                qq.partial_import(r.data_ptr() if counts[owner] else 0, int(counts[owner]), d.data_ptr() if dcounts[owner] else 0, int(dcounts[owner]))
+            part = gpu_rows(qq.finalize(), aggs)
+            assert not (set(part) & set(got)), "a group was finalised by two owners"
+            got.update(part)
+        assert_same(exp, got, name + " (2-rank merge)")
