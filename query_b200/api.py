@@ -187,11 +187,18 @@ class Result:
 
     def __init__(self, handle):
         self._h = handle
+        self._fetched = False
+
+    def _fetch(self):
+        """Values are copied out of the library on first use (a pipelined caller may never look at most results)."""
+        if self._fetched:
+            return
+        handle = self._h
         L = lib()
-        self.num_groups = int(L.n1gpu_result_num_groups(handle))
+        self._num_groups = int(L.n1gpu_result_num_groups(handle))
         self.num_keys = L.n1gpu_result_num_keys(handle)
         self.num_aggregates = L.n1gpu_result_num_aggregates(handle)
-        g, k, a = self.num_groups, self.num_keys, self.num_aggregates
+        g, k, a = self._num_groups, self.num_keys, self.num_aggregates
         kc = np.zeros(max(1, g * k), dtype=np.uint8)
         kv = np.zeros(max(1, g * k), dtype=np.int64)
         ac = np.zeros(max(1, g * a), dtype=np.uint8)
@@ -202,8 +209,18 @@ class Result:
         self.agg_cls, self.agg_val = ac[:g * a].reshape(g, a), av[:g * a].reshape(g, a)
         st = np.zeros(8, dtype=np.int64)
         check(L.n1gpu_result_stats(handle, st.ctypes.data_as(_lib._I64P)))
-        self.stats = {"rows": int(st[0]), "groups": int(st[1]), "scan_ns": int(st[2]), "shred_upload_ns": int(st[3]),
-                      "scan_bytes": int(st[4]), "launches": int(st[5])}
+        self._stats = {"rows": int(st[0]), "groups": int(st[1]), "scan_ns": int(st[2]), "shred_upload_ns": int(st[3]),
+                       "scan_bytes": int(st[4]), "launches": int(st[5])}
+        self._fetched = True
+
+    @property
+    def num_groups(self):
+        return int(lib().n1gpu_result_num_groups(self._h))
+
+    @property
+    def stats(self):
+        self._fetch()
+        return self._stats
 
     def _value(self, cls, val):
         if cls == C_MISSING:
@@ -226,8 +243,9 @@ class Result:
 
     def rows(self):
         """[(keys list, aggregates list)] with python values (int / float / str / bool / None / MISSING)."""
+        self._fetch()
         out = []
-        for g in range(self.num_groups):
+        for g in range(self._num_groups):
             ks = [self._value(self.key_cls[g, k], self.key_val[g, k]) for k in range(self.num_keys)]
             ag = [self._value(self.agg_cls[g, a], self.agg_val[g, a]) for a in range(self.num_aggregates)]
             out.append((ks, ag))
@@ -287,6 +305,10 @@ class Query:
     def rebind(self, table):
         check(lib().n1gpu_query_rebind(self._h, table._h))
         self.table = table
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: a cudaStream_t as int (e.g. torch.cuda.current_stream().cuda_stream), or 0 for the own stream."""
+        check(lib().n1gpu_query_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
     @property
     def kernel_source(self):

@@ -221,6 +221,13 @@ int64_t n1gpu_query_last_scan_ns(const n1gpu_query* q) { return q ? (int64_t)(q-
 int n1gpu_query_rebind(n1gpu_query* q, n1gpu_table* t) {
     return guard([&] { REQUIRE(q); REQUIRE(t); q->q->rebind(&t->t); });
 }
+int n1gpu_query_set_stream(n1gpu_query* q, void* cuda_stream) {
+    return guard([&] {
+        REQUIRE(q);
+        if (q->q->launched) N1_THROW(N1GPU_E_INVALID, "a scan is outstanding");
+        q->q->stream = cuda_stream ? (cudaStream_t)cuda_stream : q->q->own_stream;
+    });
+}
 int n1gpu_query_free(n1gpu_query* q) { delete q; return N1GPU_OK; }
 
 // ---- multi-GPU partial state ----------------------------------------------------------------------------------

@@ -45,7 +45,7 @@ bool have_device() {
 Query::~Query() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    if (own_stream) cudaStreamDestroy(own_stream);
 }
 
 std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const char* where,
@@ -72,7 +72,8 @@ std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const 
     for (int w = 0; w < q->ops.n; ++w) q->ops.op[w] = q->kp.word_ops[w];
     if (have_device()) {
         q->kernel = jit_load(q->kp.source);
-        CK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&q->own_stream, cudaStreamNonBlocking));
+        q->stream = q->own_stream;
         CK(cudaEventCreate(&q->ev0));
         CK(cudaEventCreate(&q->ev1));
         q->alloc_state();

@@ -34,6 +34,7 @@ struct Query {
     OpsArr ops{};
 
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int grid = 0;
     u64 cap = 1;      // group slots (1 / dense slots / hash capacity)

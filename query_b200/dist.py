@@ -1,0 +1,144 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): the Intermediate -> Final exchange of partial
+group tables (execution/group_intermediate.go:56-104) and the global dictionary / statistics agreement that
+makes string ranks and packed keys comparable across ranks.
+
+Only the *movement* of records happens here (NCCL over NVLink via torch.distributed; gloo on CPU in tests);
+producing the owner-bucketed records and merging them are CUDA kernels in libn1gpu.so
+(k_count_owners / k_export_records / k_merge_records).
+
+  small state (ungrouped, dense tables): all_gather of every rank's few records, merged on every rank
+                                         (rank 0 reports);
+  hash tables / DISTINCT sets:          all_to_all by owner = mix(group key) % world; each owner merges and
+                                         finalises its share of the groups.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def row_range(nrows, r=None, w=None):
+    """Contiguous range partition of the key-sorted document sequence (datastore/file/file.go:711-730 order)."""
+    r = rank() if r is None else r
+    w = world() if w is None else w
+    return nrows * r // w, nrows * (r + 1) // w
+
+
+def exchange_by_owner(records: torch.Tensor, counts, words_per_record: int, group=None):
+    """records: int64 tensor holding sum(counts) records of `words_per_record` words, bucketed by owner rank in rank
+    order; counts[r] = records destined to rank r.  Returns (received records tensor, per-source counts)."""
+    w = world()
+    counts = [int(c) for c in counts]
+    if w == 1:
+        return records[: counts[0] * words_per_record], counts
+    dev = records.device
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=dev)
+    recv_counts = torch.empty(w, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    rc = [int(c) for c in recv_counts.tolist()]
+    out = torch.empty(max(1, sum(rc)) * words_per_record, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(out[: sum(rc) * words_per_record], records[: sum(counts) * words_per_record].contiguous(),
+                           output_split_sizes=[c * words_per_record for c in rc],
+                           input_split_sizes=[c * words_per_record for c in counts], group=group)
+    return out[: sum(rc) * words_per_record], rc
+
+
+def gather_all(records: torch.Tensor, count: int, words_per_record: int, group=None):
+    """Every rank contributes `count` records (counts may differ); every rank receives all of them."""
+    w = world()
+    if w == 1:
+        return records[: count * words_per_record], [count]
+    dev = records.device
+    cnt = torch.tensor([count], dtype=torch.int64, device=dev)
+    allc = torch.empty(w, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, cnt, group=group)
+    cs = [int(c) for c in allc.tolist()]
+    mx = max(1, max(cs))
+    padded = torch.zeros(mx * words_per_record, dtype=torch.int64, device=dev)
+    padded[: count * words_per_record] = records[: count * words_per_record]
+    out = torch.empty(w * mx * words_per_record, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    parts = [out[r * mx * words_per_record: r * mx * words_per_record + cs[r] * words_per_record] for r in range(w)]
+    return torch.cat(parts) if parts else out[:0], cs
+
+
+def agree_dictionaries_and_stats(table, group=None):
+    """Before seal: merge every column's dictionary across ranks into the global sorted dictionary and take
+    the union of the statistics, so that all ranks compile the same kernel and pack keys identically."""
+    w = world()
+    if w == 1:
+        return
+    for c in range(len(table.columns)):
+        local = table.dictionary(c)
+        gathered = [None] * w
+        dist.all_gather_object(gathered, local, group=group)
+        merged = sorted(set().union(*[set(g) for g in gathered]))
+        st = table.stats(c)
+        allst = [None] * w
+        dist.all_gather_object(allst, st.tolist(), group=group)
+        g = np.array(allst[0], dtype=np.int64)
+        has = [s[1] != 0 for s in allst]
+        g[0] = int(np.bitwise_or.reduce([s[0] for s in allst]))
+        g[1] = int(any(has))
+        mins = [s[2] for s, h in zip(allst, has) if h]
+        maxs = [s[3] for s, h in zip(allst, has) if h]
+        g[2] = min(mins) if mins else 0
+        g[3] = max(maxs) if maxs else 0
+        g[4] = int(any(s[4] != 0 for s in allst))
+        g[5] = len(merged)
+        table.import_dictionary(c, merged)
+        table.set_stats(c, g)
+
+
+class DistributedQuery:
+    """Runs a compiled query on this rank's row range and merges the partial groups across ranks."""
+
+    def __init__(self, query, group=None):
+        self.q = query
+        self.group = group
+        self.small = query.info["mode"] in ("ungrouped", "dense-shared-memory")
+        self._recs = None
+        self._dents = None
+
+    def _buffers(self, ng, nd, rw):
+        need = max(1, ng) * rw
+        if self._recs is None or self._recs.numel() < need:
+            self._recs = torch.zeros(need, dtype=torch.int64, device="cuda")
+        need = max(1, nd) * 2
+        if self._dents is None or self._dents.numel() < need:
+            self._dents = torch.zeros(need, dtype=torch.int64, device="cuda")
+
+    def execute(self):
+        """Returns a Result holding this rank's share of the groups (small state: rank 0 holds all, others none)."""
+        q = self.q
+        w = world()
+        q.scan_partial()
+        if w == 1:
+            return q.finalize()
+        ng, nd, rw = q.partial_counts()
+        self._buffers(ng, nd, rw)
+        has_distinct = nd > 0 or "distinct" in " ".join(q.aggregates)
+        if self.small and not has_distinct:
+            counts, _ = q.partial_export(1, self._recs.data_ptr(), ng, self._dents.data_ptr(), nd)
+            allrec, cs = gather_all(self._recs, int(counts[0]), rw, self.group)
+            q.partial_reset()
+            if rank() == 0:
+                n = sum(cs)
+                q.partial_import(allrec.data_ptr() if n else 0, n, 0, 0)
+            return q.finalize()
+        counts, dcounts = q.partial_export(w, self._recs.data_ptr(), ng, self._dents.data_ptr(), nd)
+        got, rc = exchange_by_owner(self._recs, counts, rw, self.group)
+        dgot, drc = exchange_by_owner(self._dents, dcounts, 2, self.group)
+        q.partial_reset()
+        n, ndg = sum(rc), sum(drc)
+        q.partial_import(got.data_ptr() if n else 0, n, dgot.data_ptr() if ndg else 0, ndg)
+        return q.finalize()
