@@ -131,8 +131,9 @@ int64_t n1gpu_query_last_scan_ns(const n1gpu_query* q);
 /* Rebinds a compiled query to another sealed table with the same schema/dictionaries/statistics
  * (bench.py rotates table copies so that no step finds its input in L2).                            */
 int n1gpu_query_rebind(n1gpu_query* q, n1gpu_table* t);
-/* Makes the query enqueue its work on a caller-owned CUDA stream (cudaStream_t as void*; NULL = back to the
- * query's own stream), so that callers can bracket scans with their own CUDA events (bench.py).           */
+/* Makes the query enqueue its work on a caller-owned CUDA stream (cudaStream_t as void*; NULL = the legacy
+ * default stream; (void*)-1 = back to the query's own stream), so that callers can bracket scans with their
+ * own CUDA events (bench.py).                                                                              */
 int n1gpu_query_set_stream(n1gpu_query* q, void* cuda_stream);
 int n1gpu_query_free(n1gpu_query* q);
 

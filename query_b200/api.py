@@ -307,8 +307,9 @@ class Query:
         self.table = table
 
     def set_stream(self, cuda_stream):
-        """cuda_stream: a cudaStream_t as int (e.g. torch.cuda.current_stream().cuda_stream), or 0 for the own stream."""
-        check(lib().n1gpu_query_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """cuda_stream: a cudaStream_t as int (torch.cuda.current_stream().cuda_stream; 0 = the legacy default
+        stream), or None for the query's own non-blocking stream."""
+        check(lib().n1gpu_query_set_stream(self._h, C.c_void_p(-1 if cuda_stream is None else int(cuda_stream))))
 
     @property
     def kernel_source(self):

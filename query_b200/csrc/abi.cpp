@@ -128,7 +128,7 @@ int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]) {
         if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
         Column& c = t->t.cols[col];
         ColumnStats st = c.stats;
-        if (!t->t.sealed) {  // compute from staging
+        if (!t->t.sealed && !c.stats_forced) {  // compute from staging
             st = ColumnStats();
             for (size_t i = 0; i < c.tags.size(); ++i) {
                 u8 tg = c.tags[i];
@@ -225,7 +225,9 @@ int n1gpu_query_set_stream(n1gpu_query* q, void* cuda_stream) {
     return guard([&] {
         REQUIRE(q);
         if (q->q->launched) N1_THROW(N1GPU_E_INVALID, "a scan is outstanding");
-        q->q->stream = cuda_stream ? (cudaStream_t)cuda_stream : q->q->own_stream;
+        // NULL is a real stream (the legacy default stream, which is what torch.cuda.current_stream() is
+        // unless the caller changed it); (void*)-1 restores the query's own non-blocking stream
+        q->q->stream = (cuda_stream == (void*)-1) ? q->q->own_stream : (cudaStream_t)cuda_stream;
     });
 }
 int n1gpu_query_free(n1gpu_query* q) { delete q; return N1GPU_OK; }

@@ -499,12 +499,27 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += strf("    { u64 r = block_reduce_word<%s>(a%d, scratch); if (threadIdx.x == 0) p.acc[(u64)blockIdx.x * NQ_W + %d] = r; }\n",
                       op_name(kp.word_ops[w]), w, w);
         }
+        // the last block to finish folds the per-block partials in a fixed order (deterministic float sums)
+        // and publishes the final words to HBM and, zero-copy, to mapped pinned host memory
+        s += "    if (last_block_arrives(p.ticket)) {\n";
+        s += "        const int warp = threadIdx.x >> 5;\n";
+        s += "        for (int w = warp; w < NQ_W; w += 8) {\n";
+        s += "            const int op = nq_ops[w];\n";
+        s += "            u64 v = word_identity(op);\n";
+        s += "            for (unsigned b = lane; b < gridDim.x; b += 32) v = word_combine(op, v, __ldcg(&p.acc[(u64)b * NQ_W + w]));\n";
+        s += "            v = warp_reduce_dyn(op, v);\n";
+        s += "            if (lane == 0) { p.final_dev[w] = v; p.final_host[w] = v; }\n";
+        s += "        }\n";
+        s += "    }\n";
     } else if (kp.mode == MODE_DENSE) {
         s += "    __syncthreads();\n";
         s += "    for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) {\n";
         s += "        const int op = nq_ops[i / NQ_G];\n";
         s += "        const u64 v = s_tab[i];\n";
         s += "        if (v != word_identity(op)) atomic_word_dyn(op, &p.acc[i], v);\n";
+        s += "    }\n";
+        s += "    if (last_block_arrives(p.ticket)) {\n";
+        s += "        for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) p.final_host[i] = __ldcg(&p.acc[i]);\n";
         s += "    }\n";
     }
     s += "}\n";

@@ -401,4 +401,29 @@ struct NqParams {
     u64 set_mask;
     int* status;           // [0] != 0: a table overflowed (host grows it and reruns)
     u64 dense_groups;      // DENSE: number of dense slots
+    u64* final_dev;        // UNGROUPED: final words [nwords] in HBM (written by the last block to finish)
+    u64* final_host;       // UNGROUPED/DENSE: the same words in mapped pinned host memory (zero-copy result)
+    unsigned* ticket;      // blocks-done counter for the last-block pattern (self-resetting)
 };
+
+// Dynamic-op warp reduction (the final, fixed-order fold of per-block partials by the last block).
+NQ_DEV u64 warp_reduce_dyn(int op, u64 v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = word_combine(op, v, shfl_xor_u64(v, m));
+    return v;
+}
+// Returns true in every thread of exactly one block per launch: the last one to arrive.  All global writes the
+// other blocks made before their arrival are visible to it.
+NQ_DEV bool last_block_arrives(unsigned* ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *ticket = 0;  // ready for the next launch on this stream
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}

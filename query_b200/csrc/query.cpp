@@ -29,8 +29,11 @@ struct NqParamsHost {
     u64 set_mask;
     int* status;
     u64 dense_groups;
+    u64* final_dev;
+    u64* final_host;
+    unsigned* ticket;
 };
-static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 7, "NqParams layout");
+static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 10, "NqParams layout");
 
 u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
 
@@ -120,13 +123,17 @@ void Query::alloc_state() {
     }
     d_status.ensure(64);
     h_status.ensure(64);
+    memset(h_status.p, 0, 64);
+    if (!d_ticket.p) { d_ticket.alloc(64); CK(cudaMemset(d_ticket.p, 0, 64)); }
     d_counts.ensure(4096);
     h_counts.ensure(4096);
     if (kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) h_records.ensure((size_t)cap * W * 8);
 }
 
+bool Query::uses_status() const { return kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128 || kp.ndistinct > 0; }
+
 void Query::reset_state() {
-    CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
+    if (uses_status()) CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
     if (kp.mode != MODE_UNGROUPED) launch_init_words(d_acc.as<u64>(), cap, ops, stream);
     if (kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128) CK(cudaMemsetAsync(d_keys.p, 0xff, (size_t)cap * (kp.mode == MODE_HASH128 ? 16 : 8), stream));
     if (kp.ndistinct) CK(cudaMemsetAsync(d_set.p, 0xff, (size_t)set_cap * (kp.set128 ? 16 : 8), stream));
@@ -146,14 +153,14 @@ void Query::launch_scan() {
     p.set_mask = set_cap ? set_cap - 1 : 0;
     p.status = d_status.as<int>();
     p.dense_groups = (u64)kp.dense_slots;
+    p.final_dev = d_acc.as<u64>();
+    p.final_host = h_records.as<u64>();  // pinned memory is device-addressable under UVA: zero-copy result
+    p.ticket = d_ticket.as<unsigned>();
     reset_state();
     CK(cudaEventRecord(ev0, stream));
-    jit_launch(*kernel, grid, stream, &p, sizeof p);
-    if (kp.mode == MODE_UNGROUPED) launch_reduce_partials(d_partials.as<u64>(), grid, ops, d_acc.as<u64>(), stream);
+    jit_launch(*kernel, grid, stream, &p, sizeof p);  // ungrouped / dense: the whole step is this one launch
     CK(cudaEventRecord(ev1, stream));
-    CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
-    if (kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE)
-        CK(cudaMemcpyAsync(h_records.p, d_acc.p, (size_t)cap * ops.n * 8, cudaMemcpyDeviceToHost, stream));
+    if (uses_status()) CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
     launched = true;
     ungrouped_live = true;
 }

@@ -39,7 +39,7 @@ struct Query {
     int grid = 0;
     u64 cap = 1;      // group slots (1 / dense slots / hash capacity)
     u64 set_cap = 0;  // DISTINCT entry set capacity
-    DevBuf d_partials, d_acc, d_keys, d_set, d_status, d_counts, d_records, d_drecords;
+    DevBuf d_partials, d_acc, d_keys, d_set, d_status, d_counts, d_records, d_drecords, d_ticket;
     PinnedBuf h_status, h_counts, h_records, h_drecords;
     std::atomic<bool> cancelled{false};
     bool launched = false;
@@ -54,6 +54,7 @@ struct Query {
                                           const std::vector<std::string>& keys, const std::vector<std::string>& aggs);
     int kw() const { return kp.mode == MODE_UNGROUPED ? 3 : (kp.mode == MODE_DENSE ? 0 : (kp.mode == MODE_HASH64 ? 1 : 2)); }
     void alloc_state();
+    bool uses_status() const;         // hash tables / DISTINCT sets can overflow and report it
     void reset_state();               // clears tables (async on stream)
     void launch_scan();               // enqueue reset + scan (+ partial reduction)
     bool wait_scan();                 // sync; returns false when a table overflowed and was grown (caller relaunches)

@@ -1,0 +1,97 @@
+"""world_size-2 gloo tests (CPU) of the host-side exchange logic of query_b200.dist: owner-bucketed all-to-all,
+all-gather of small states, row-range partitioning and the dictionary / statistics agreement before seal."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def _exchange(rank, world):
+    from query_b200 import dist as qd
+    rw = 3
+    # rank r sends (r+1) records to rank 0 and (r+2) records to rank 1; record = [src, dst, seq]
+    counts = [rank + 1, rank + 2]
+    recs = []
+    for dst, c in enumerate(counts):
+        for i in range(c):
+            recs += [rank, dst, i]
+    got, rc = qd.exchange_by_owner(torch.tensor(recs, dtype=torch.int64), counts, rw)
+    return got.tolist(), rc
+
+
+def test_exchange_by_owner_routes_every_record_to_its_owner():
+    out = _run(_exchange)
+    for owner, (flat, rc) in enumerate(out):
+        recs = [tuple(flat[i:i + 3]) for i in range(0, len(flat), 3)]
+        assert rc == [0 + 1 + owner, 1 + 1 + owner]
+        assert all(r[1] == owner for r in recs)
+        assert sorted(recs) == sorted((src, owner, i) for src in range(2) for i in range(src + 1 + owner))
+
+
+def _gather(rank, world):
+    from query_b200 import dist as qd
+    rw = 2
+    n = 3 if rank == 0 else 1
+    recs = torch.tensor([v for i in range(n) for v in (rank, i)], dtype=torch.int64)
+    allrec, cs = qd.gather_all(recs, n, rw)
+    return allrec.tolist(), cs, qd.row_range(10)
+
+
+def test_gather_all_with_ragged_counts_and_row_ranges():
+    out = _run(_gather)
+    for flat, cs, rr in out:
+        assert cs == [3, 1]
+        assert flat == [0, 0, 0, 1, 0, 2, 1, 0]
+    assert out[0][2] == (0, 5) and out[1][2] == (5, 10)
+
+
+def _agree(rank, world):
+    import query_b200 as q
+    from query_b200 import dist as qd
+    docs = ['{"s":"b","n":5}', '{"s":"a","n":-2}'] if rank == 0 else ['{"s":"c","n":40}', '{"s":"a"}', '{"n":1.5}']
+    t = q.Table(["s", "n"])
+    t.append_json(docs)
+    qd.agree_dictionaries_and_stats(t)
+    pay, tags = t.peek("s")
+    d = t.dictionary("s")
+    st = t.stats("n")
+    t.seal()
+    qq = q.Query(t, "d", "((`d`.`s`) <= \"b\")", ["(`d`.`s`)"], ["count(*)", "sum((`d`.`n`))"])
+    return [x.decode() for x in d], [int(p) for p, g in zip(pay, tags) if g == 6], st.tolist(), qq.kernel_source
+
+
+def test_dictionary_and_statistics_agreement_gives_identical_kernels():
+    out = _run(_agree)
+    assert out[0][0] == out[1][0] == ["a", "b", "c"]
+    assert out[0][1] == [1, 0] and out[1][1] == [2, 0]
+    assert out[0][2][:5] == out[1][2][:5] == [(1 << 0) | (1 << 4) | (1 << 5), 1, -2, 40, 1]
+    assert out[0][3] == out[1][3], "ranks must compile the same kernel (same packing, same constants)"
