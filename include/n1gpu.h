@@ -68,7 +68,11 @@ int n1gpu_table_create(n1gpu_table** out);
 int n1gpu_table_add_column(n1gpu_table* t, const char* path);
 int n1gpu_table_find_column(const n1gpu_table* t, const char* path); /* index or -1 */
 /* Appends ndocs documents: doc i is bytes [offsets[i], offsets[i+1]) of buf, in primary-key order.
- * Shreds with `threads` host threads (0 = all cores).                                              */
+ * threads >= 0: shreds with that many host threads (0 = all cores).
+ * threads == -1: the device shredder - the raw JSON is copied to HBM once and parsed there, one thread per
+ * document (shred.cu); only documents it cannot decide exactly (escapes in a wanted name/value, numbers
+ * outside the exactly-rounded fast path) are re-shredded on the host.  Takes the whole keyspace in one call.
+ * Both produce identical columns.                                                                    */
 int n1gpu_table_append_json(n1gpu_table* t, const char* buf, const int64_t* offsets, int64_t ndocs, int threads);
 /* Reads a file-datastore keyspace directory <root>/<namespace>/<keyspace>: every non-directory entry,
  * sorted by file name, is one document (file.go:711-730).                                           */

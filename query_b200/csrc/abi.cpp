@@ -104,6 +104,8 @@ int n1gpu_table_dict_import(n1gpu_table* t, int col, const char* blob, const int
         REQUIRE(t); REQUIRE(offsets);
         if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
         if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "dictionary exchange happens before seal");
+        if (t->t.device_shredded && !t->t.cols[col].dict.empty())
+            N1_THROW(N1GPU_E_INVALID, "dictionary import into a device-shredded string column is not supported yet (shred with host threads)");
         t->t.build_dictionary(col);
         Column& c = t->t.cols[col];
         std::vector<std::string> global;
@@ -128,7 +130,7 @@ int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]) {
         if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
         Column& c = t->t.cols[col];
         ColumnStats st = c.stats;
-        if (!t->t.sealed && !c.stats_forced) {  // compute from staging
+        if (!t->t.sealed && !c.stats_forced && !t->t.device_shredded) {  // compute from staging
             st = ColumnStats();
             for (size_t i = 0; i < c.tags.size(); ++i) {
                 u8 tg = c.tags[i];

@@ -182,8 +182,26 @@ struct Shredder {
 };
 }  // namespace
 
+void host_shred_docs(const std::vector<Column>& cols, const char* buf, const i64* offs, const i64* rows, i64 n,
+                     std::vector<HostShredOut>& out) {
+    Trie trie;
+    for (size_t c = 0; c < cols.size(); ++c) trie.add(cols[c].path, (int)c);
+    std::vector<ChunkCol> cc(cols.size());
+    for (auto& c : cc) { c.payload.assign((size_t)n, 0); c.tags.assign((size_t)n, C_MISSING); }
+    Shredder sh(trie, cc);
+    for (i64 i = 0; i < n; ++i) sh.document(buf + offs[rows[i]], buf + offs[rows[i] + 1]);
+    out.resize(cols.size());
+    for (size_t c = 0; c < cols.size(); ++c) {
+        out[c].tags.swap(cc[c].tags);
+        out[c].payload.swap(cc[c].payload);
+        out[c].strings.swap(cc[c].strings);
+    }
+}
+
 void Table::append_json(const char* buf, const i64* offsets, i64 ndocs, int threads) {
     if (sealed) N1_THROW(N1GPU_E_INVALID, "table is sealed");
+    if (threads == -1) { append_json_device(buf, offsets, ndocs); return; }
+    if (device_shredded) N1_THROW(N1GPU_E_INVALID, "table already holds device-shredded rows");
     for (auto& col : cols)
         if (col.dict_global || col.codes_are_ranks) N1_THROW(N1GPU_E_INVALID, "append after dictionary import / pre-shredded columns is not supported");
     if (ndocs < 0) N1_THROW(N1GPU_E_INVALID, "negative document count");
@@ -330,6 +348,7 @@ int Table::scan_bytes(int c) const {
 
 void Table::seal() {
     if (sealed) return;
+    if (device_shredded) { sealed = true; return; }  // columns, dictionaries and statistics already final in HBM
     double t0 = now_sec();
     for (auto& col : cols)
         if ((i64)col.tags.size() != nrows) N1_THROW(N1GPU_E_INVALID, "column %s has %lld rows, table has %lld",

@@ -45,6 +45,10 @@ struct Table {
     double shred_sec = 0, upload_sec = 0;
     i64 json_bytes = 0;
 
+    bool device_shredded = false;  // columns were produced in HBM by shred.cu (no host staging exists)
+
+    // threads >= 0: host threads (0 = all cores); threads == -1: the device shredder (shred.cu)
+    void append_json_device(const char* buf, const i64* offsets, i64 ndocs);
     int add_column(const std::string& path);
     int find_column(const std::string& path) const;
     void append_json(const char* buf, const i64* offsets, i64 ndocs, int threads);
@@ -56,6 +60,16 @@ struct Table {
     int scan_bytes(int col) const;
     i64 padded_rows() const { return (nrows + ROW_PAD - 1) / ROW_PAD * ROW_PAD; }
 };
+
+// The host shredder applied to selected documents (the device shredder's fix-up rows).  Per column: tags[n],
+// payload[n] (STRING: index into strings).
+struct HostShredOut {
+    std::vector<u8> tags;
+    std::vector<i64> payload;
+    std::vector<std::string> strings;
+};
+void host_shred_docs(const std::vector<Column>& cols, const char* buf, const i64* offs, const i64* rows, i64 n,
+                     std::vector<HostShredOut>& out);
 
 std::vector<std::string> split_path(const std::string& path);
 std::string join_path(const std::vector<std::string>& p, char sep);

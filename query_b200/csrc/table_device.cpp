@@ -1,0 +1,255 @@
+// table_device.cpp — host orchestration of the device-side shredder (shred.cu): raw JSON goes to HBM once, the
+// columns are produced there (no column H2D at all), dictionaries are built from a device hash set of distinct
+// strings whose (few) members the host sorts bytewise, and only the documents the device could not decide exactly
+// are re-shredded on the host (fix-up rows) and patched in.
+#include <algorithm>
+#include <map>
+
+#include "shred.hpp"
+#include "table.hpp"
+
+namespace n1 {
+
+namespace {
+
+void build_trie(const std::vector<Column>& cols, ShredTrie& T) {
+    // adjacency first (node -> list of (name, child)), then flatten so that every node's kids are contiguous
+    struct N { std::vector<std::pair<std::string, int>> kids; int col = -1; };
+    std::vector<N> nodes(1);
+    for (size_t c = 0; c < cols.size(); ++c) {
+        int n = 0;
+        for (auto& name : cols[c].path) {
+            int next = -1;
+            for (auto& k : nodes[n].kids) if (k.first == name) next = k.second;
+            if (next < 0) { nodes.emplace_back(); next = (int)nodes.size() - 1; nodes[n].kids.emplace_back(name, next); }
+            n = next;
+        }
+        nodes[n].col = (int)c;
+    }
+    if (nodes.size() > 64) N1_THROW(N1GPU_E_INELIGIBLE, "device shredder: more than 64 path nodes");
+    memset(&T, 0, sizeof T);
+    T.nnodes = (int)nodes.size();
+    int kid = 0, name_at = 0;
+    for (size_t n = 0; n < nodes.size(); ++n) {
+        T.col[n] = nodes[n].col;
+        T.kid_begin[n] = kid;
+        for (auto& k : nodes[n].kids) {
+            if (kid >= 64) N1_THROW(N1GPU_E_INELIGIBLE, "device shredder: more than 64 field names");
+            if (name_at + (int)k.first.size() > (int)sizeof T.names) N1_THROW(N1GPU_E_INELIGIBLE, "device shredder: field names too long");
+            T.name_off[kid] = name_at;
+            T.name_len[kid] = (int)k.first.size();
+            memcpy(T.names + name_at, k.first.data(), k.first.size());
+            name_at += (int)k.first.size();
+            T.kid_node[kid] = k.second;
+            ++kid;
+        }
+        T.kid_end[n] = kid;
+    }
+    T.nkids = kid;
+}
+
+u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
+
+}  // namespace
+
+void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
+    if (sealed) N1_THROW(N1GPU_E_INVALID, "table is sealed");
+    if (!have_device()) N1_THROW(N1GPU_E_CUDA, "the device shredder needs a CUDA device (there is no CPU fallback for it; use host threads explicitly)");
+    if (appended || nrows != 0) N1_THROW(N1GPU_E_INVALID, "the device shredder takes the whole keyspace in one append");
+    if (cols.empty()) N1_THROW(N1GPU_E_INVALID, "no columns declared");
+    if (ndocs < 0) N1_THROW(N1GPU_E_INVALID, "negative document count");
+    double t0 = now_sec();
+    const i64 base_off = ndocs ? offsets[0] : 0;
+    const i64 nbytes = ndocs ? offsets[ndocs] - base_off : 0;
+    const int ncols = (int)cols.size();
+    cudaStream_t s = nullptr;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+
+    ShredTrie trie;
+    build_trie(cols, trie);
+    DevBuf d_trie, d_buf, d_offs, d_fixcount, d_fixrows, d_ptrs;
+    d_trie.alloc(sizeof trie);
+    CK(cudaMemcpyAsync(d_trie.p, &trie, sizeof trie, cudaMemcpyHostToDevice, s));
+    d_buf.alloc((size_t)nbytes + 64);
+    d_offs.alloc((size_t)(ndocs + 1) * 8);
+    if (nbytes) CK(cudaMemcpyAsync(d_buf.p, buf + base_off, (size_t)nbytes, cudaMemcpyHostToDevice, s));
+    std::vector<i64> rel;
+    const i64* offs_src = offsets;
+    if (base_off != 0) {  // device offsets are relative to d_buf
+        rel.resize((size_t)ndocs + 1);
+        for (i64 i = 0; i <= ndocs; ++i) rel[(size_t)i] = offsets[i] - base_off;
+        offs_src = rel.data();
+    }
+    if (ndocs) CK(cudaMemcpyAsync(d_offs.p, offs_src, (size_t)(ndocs + 1) * 8, cudaMemcpyHostToDevice, s));
+    else { i64 z = 0; CK(cudaMemcpyAsync(d_offs.p, &z, 8, cudaMemcpyHostToDevice, s)); }
+
+    nrows = ndocs;
+    i64 pad = padded_rows();
+    if (pad == 0) pad = ROW_PAD;
+    std::vector<DevBuf> pay8((size_t)ncols);
+    std::vector<u8*> h_tags((size_t)ncols);
+    std::vector<i64*> h_pay((size_t)ncols);
+    for (int c = 0; c < ncols; ++c) {
+        cols[c].d_tags.alloc((size_t)pad);
+        CK(cudaMemsetAsync(cols[c].d_tags.p, C_MISSING, (size_t)pad, s));
+        pay8[c].alloc((size_t)pad * 8);
+        CK(cudaMemsetAsync(pay8[c].p, 0, (size_t)pad * 8, s));
+        h_tags[c] = cols[c].d_tags.as<u8>();
+        h_pay[c] = pay8[c].as<i64>();
+    }
+    d_ptrs.alloc((size_t)ncols * 16);
+    CK(cudaMemcpyAsync(d_ptrs.p, h_tags.data(), (size_t)ncols * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync((char*)d_ptrs.p + (size_t)ncols * 8, h_pay.data(), (size_t)ncols * 8, cudaMemcpyHostToDevice, s));
+    const i64 fix_cap = std::max<i64>(1024, std::min<i64>(ndocs, 1 << 22));
+    d_fixcount.alloc(64);
+    CK(cudaMemsetAsync(d_fixcount.p, 0, 64, s));
+    d_fixrows.alloc((size_t)fix_cap * 8);
+
+    if (ndocs)
+        launch_shred_json((const unsigned char*)d_buf.p, d_offs.as<i64>(), ndocs, (const ShredTrie*)d_trie.p, (u8* const*)d_ptrs.p,
+                          (i64* const*)((char*)d_ptrs.p + (size_t)ncols * 8), ncols, d_fixcount.as<unsigned>(), d_fixrows.as<i64>(), fix_cap, s);
+    unsigned nfix = 0;
+    CK(cudaMemcpyAsync(&nfix, d_fixcount.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if ((i64)nfix > fix_cap)
+        N1_THROW(N1GPU_E_INVALID, "device shredder: %u documents need host handling (escapes / long numbers); shred this keyspace with host threads", nfix);
+
+    // ---- fix-up rows: the host shredder decides these documents -----------------------------------------------------
+    std::string extra;  // unescaped string values of fix-up rows (device refs carry REF_EXTRA_BIT)
+    DevBuf d_extra;
+    if (nfix) {
+        std::vector<i64> rows(nfix);
+        CK(cudaMemcpy(rows.data(), d_fixrows.p, (size_t)nfix * 8, cudaMemcpyDeviceToHost));
+        std::sort(rows.begin(), rows.end());
+        std::vector<HostShredOut> fx;
+        host_shred_docs(cols, buf, offsets, rows.data(), (i64)nfix, fx);
+        std::vector<std::vector<i64>> pays((size_t)ncols);
+        for (int c = 0; c < ncols; ++c) {
+            pays[c] = fx[c].payload;
+            for (size_t i = 0; i < rows.size(); ++i) {
+                if (fx[c].tags[i] != C_STRING) continue;
+                const std::string& str = fx[c].strings[(size_t)fx[c].payload[i]];
+                if (str.size() >= (1u << 24)) N1_THROW(N1GPU_E_INELIGIBLE, "string value longer than 16 MiB");
+                pays[c][i] = (i64)(0x8000000000000000ULL | ((u64)extra.size() << 24) | (u64)str.size());
+                extra += str;
+            }
+        }
+        d_extra.alloc(extra.size() + 64);
+        if (!extra.empty()) CK(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size(), cudaMemcpyHostToDevice, s));
+        DevBuf d_rows, d_pt, d_pp;
+        d_rows.alloc((size_t)nfix * 8);
+        d_pt.alloc((size_t)nfix);
+        d_pp.alloc((size_t)nfix * 8);
+        CK(cudaMemcpyAsync(d_rows.p, rows.data(), (size_t)nfix * 8, cudaMemcpyHostToDevice, s));
+        for (int c = 0; c < ncols; ++c) {
+            CK(cudaMemcpyAsync(d_pt.p, fx[c].tags.data(), (size_t)nfix, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_pp.p, pays[c].data(), (size_t)nfix * 8, cudaMemcpyHostToDevice, s));
+            launch_patch(cols[c].d_tags.as<u8>(), pay8[c].as<i64>(), d_rows.as<i64>(), d_pt.as<u8>(), d_pp.as<i64>(), (i64)nfix, s);
+            CK(cudaStreamSynchronize(s));  // d_pt / d_pp are reused by the next column
+        }
+    } else d_extra.alloc(64);
+
+    // ---- statistics (class mask, int range) -------------------------------------------------------------------------
+    DevBuf d_stats;
+    d_stats.alloc((size_t)ncols * 32);
+    std::vector<u64> h_stats((size_t)ncols * 4);
+    for (int c = 0; c < ncols; ++c) { h_stats[c * 4 + 0] = 0; h_stats[c * 4 + 1] = (u64)INT64_MAX; h_stats[c * 4 + 2] = (u64)INT64_MIN; h_stats[c * 4 + 3] = 0; }
+    CK(cudaMemcpyAsync(d_stats.p, h_stats.data(), h_stats.size() * 8, cudaMemcpyHostToDevice, s));
+    if (ndocs)
+        for (int c = 0; c < ncols; ++c) launch_col_stats(cols[c].d_tags.as<u8>(), pay8[c].as<i64>(), ndocs, d_stats.as<u64>() + c * 4, s);
+    CK(cudaMemcpyAsync(h_stats.data(), d_stats.p, h_stats.size() * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+
+    // ---- dictionaries + final payload width ------------------------------------------------------------------------------
+    DevBuf d_slots, d_keys, d_status, d_count, d_oslots, d_orefs, d_rank;
+    d_status.alloc(64);
+    d_count.alloc(64);
+    for (int c = 0; c < ncols; ++c) {
+        Column& col = cols[c];
+        ColumnStats st;
+        st.class_mask = (u32)h_stats[c * 4 + 0];
+        st.has_int = (st.class_mask & bit(C_INT)) != 0;
+        st.int_min = st.has_int ? (i64)h_stats[c * 4 + 1] : 0;
+        st.int_max = st.has_int ? (i64)h_stats[c * 4 + 2] : 0;
+        st.has_float = h_stats[c * 4 + 3] != 0;
+        col.dict.clear();
+        const bool has_str = st.class_mask & bit(C_STRING);
+        col.width = (st.class_mask & M_NUM) ? 8 : (has_str ? 4 : 0);
+        if (has_str) {
+            d_slots.ensure((size_t)pad * 8);
+            u64 cap = 1 << 16;
+            std::vector<u64> oslots, orefs;
+            for (;;) {
+                d_keys.ensure((size_t)cap * 8);
+                CK(cudaMemsetAsync(d_keys.p, 0xff, (size_t)cap * 8, s));
+                CK(cudaMemsetAsync(d_status.p, 0, 64, s));
+                launch_dict_insert((const unsigned char*)d_buf.p, (const unsigned char*)d_extra.p, col.d_tags.as<u8>(), pay8[c].as<i64>(),
+                                   d_slots.as<i64>(), ndocs, d_keys.as<u64>(), cap, d_status.as<int>(), s);
+                int status = 0;
+                CK(cudaMemcpyAsync(&status, d_status.p, 4, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                if (status == 0) {
+                    // the table must stay sparse enough for cheap probing; a dense one means high cardinality: grow
+                    d_oslots.ensure((size_t)cap * 8);
+                    d_orefs.ensure((size_t)cap * 8);
+                    CK(cudaMemsetAsync(d_count.p, 0, 64, s));
+                    launch_dict_collect(d_keys.as<u64>(), cap, d_count.as<unsigned>(), d_oslots.as<u64>(), d_orefs.as<u64>(), cap, s);
+                    unsigned m = 0;
+                    CK(cudaMemcpyAsync(&m, d_count.p, 4, cudaMemcpyDeviceToHost, s));
+                    CK(cudaStreamSynchronize(s));
+                    if ((u64)m * 2 <= cap || cap >= pow2_at_least((u64)ndocs * 2)) {
+                        oslots.resize(m);
+                        orefs.resize(m);
+                        if (m) {
+                            CK(cudaMemcpy(oslots.data(), d_oslots.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
+                            CK(cudaMemcpy(orefs.data(), d_orefs.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
+                        }
+                        break;
+                    }
+                }
+                if (cap > ((u64)1 << 33)) N1_THROW(N1GPU_E_NOMEM, "dictionary table too large");
+                cap *= 8;
+            }
+            // sort the distinct strings bytewise on the host: rank = N1QL collation order (value/string.go:116-126)
+            struct Ent { const char* p; u32 len; u64 slot; };
+            std::vector<Ent> ents(oslots.size());
+            for (size_t i = 0; i < oslots.size(); ++i) {
+                const u64 ref = orefs[i];
+                const u64 off = (ref & ~0x8000000000000000ULL) >> 24;
+                ents[i].p = (ref >> 63) ? extra.data() + off : buf + base_off + off;
+                ents[i].len = (u32)(ref & 0xffffff);
+                ents[i].slot = oslots[i];
+            }
+            std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) {
+                const int c = memcmp(a.p, b.p, std::min(a.len, b.len));
+                return c != 0 ? c < 0 : a.len < b.len;
+            });
+            std::vector<u32> rank((size_t)cap, 0);
+            col.dict.reserve(ents.size());
+            for (size_t r = 0; r < ents.size(); ++r) { rank[(size_t)ents[r].slot] = (u32)r; col.dict.emplace_back(ents[r].p, ents[r].len); }
+            d_rank.ensure((size_t)cap * 4);
+            CK(cudaMemcpyAsync(d_rank.p, rank.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, s));
+            u32* out32 = nullptr;
+            if (col.width == 4) {
+                col.d_payload.alloc((size_t)pad * 4);
+                CK(cudaMemsetAsync(col.d_payload.p, 0, (size_t)pad * 4, s));
+                out32 = col.d_payload.as<u32>();
+            }
+            launch_dict_remap(col.d_tags.as<u8>(), d_slots.as<i64>(), pay8[c].as<i64>(), out32, ndocs, d_rank.as<u32>(), s);
+            CK(cudaStreamSynchronize(s));
+        }
+        if (col.width == 8) col.d_payload = std::move(pay8[c]);
+        else { pay8[c].release(); if (col.width == 0) col.d_payload.alloc(256); }
+        st.ndict = (i64)col.dict.size();
+        st.empty_rank = (!col.dict.empty() && col.dict[0].empty()) ? 0 : -1;
+        if (!col.stats_forced) col.stats = st;
+        col.codes_are_ranks = true;
+    }
+    appended = true;
+    device_shredded = true;
+    json_bytes += nbytes;
+    shred_sec += now_sec() - t0;
+}
+
+}  // namespace n1

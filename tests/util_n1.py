@@ -61,7 +61,7 @@ def _norm(v):
     """What json.loads of the rendered value holds: an integral float renders as an integer."""
     if isinstance(v, float) and not isinstance(v, bool):
         if math.isfinite(v) and v == int(v):
-            return int(v)
+            return O.to_python(v)  # the integer the shortest-digits rendering reads back as
     return v
 
 
@@ -87,8 +87,9 @@ def assert_same(expected, got, what=""):
                 assert type(v) is type(w) and v == w, msg
 
 
-def run_both(docs, alias, where, keys, aggs, what=""):
-    t = make_table(docs, where, keys, aggs)
+def run_both(docs, alias, where, keys, aggs, what="", threads=0):
+    """threads=-1 shreds on the device (shred.cu), >= 0 with host threads"""
+    t = make_table(docs, where, keys, aggs, threads=threads)
     t.seal()
     qq = q.Query(t, alias, where, keys, aggs)
     res = qq.execute()
