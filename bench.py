@@ -235,13 +235,22 @@ def run_ours(args):
     hoffs = pinned_offs.numpy()
     e2e_steps = max(1, min(args.e2e_steps, K))
 
+    trace = bool(os.environ.get("N1GPU_TRACE"))
+
     def e2e_step():
+        ts = [time.perf_counter()]
         t = q.Table(["n", "f"])
         t.append_json((hbuf, hoffs), threads=args.shred_threads)
+        ts.append(time.perf_counter())
         t.seal()
         qq = q.Query(t, ALIAS, WHERE, KEYS, AGGS)
+        ts.append(time.perf_counter())
         res = qd.DistributedQuery(qq).execute()
         rows = res.rows()
+        ts.append(time.perf_counter())
+        if trace:
+            sys.stderr.write("[bench e2e] shred %.2f ms, seal+compile %.2f ms, scan+result %.2f ms\n" % tuple(
+                (b - a) * 1e3 for a, b in zip(ts, ts[1:])))
         if args.shred_threads < 0:
             h2d = int(hoffs[-1]) + 8 * (e2e_rows + 1)          # raw JSON + document offsets
         else:

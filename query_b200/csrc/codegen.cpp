@@ -452,6 +452,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     s += "__constant__ int nq_ops[NQ_W] = {";
     for (int w = 0; w < W; ++w) s += strf("%s%d", w ? ", " : "", kp.word_ops[w]);
     s += "};\n";
+    s += "__constant__ int nq_fidx[NQ_W] = {";  // float64-sum words keep per-block partials: their partial row
+    for (int w = 0, fi = 0; w < W; ++w) s += strf("%s%d", w ? ", " : "", kp.word_ops[w] == OP_ADD_F64 ? fi++ : -1);
+    s += "};\n";
     if (kp.mode == MODE_UNGROUPED) s += "#define ACC(k, OP, x) a##k = word_combine(OP, a##k, (u64)(x))\n";
     else if (kp.mode == MODE_DENSE) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
     else s += "#define ACC(k, OP, x) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
@@ -494,22 +497,47 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     s += "        }\n";
     s += "    }\n";
     if (kp.mode == MODE_UNGROUPED) {
+        // Block epilogue: warp-shuffle reduce every word, one barrier, then thread w folds word w's 8 warp values in
+        // order.  Order-independent words (integer add / min / max / or) go straight into persistent accumulators
+        // with one atomic per block; float64 sums are kept as per-block partials and folded in a fixed order by the
+        // last block to finish, so float results are run-to-run identical.  That block also publishes the final
+        // words to HBM and, zero-copy, to mapped pinned host memory, and re-arms the accumulators.
+        s += "    __shared__ u64 s_part[NQ_W][8];\n";
         s += "    __shared__ u64 scratch[32];\n";
-        for (int w = 0; w < W; ++w) {
-            s += strf("    { u64 r = block_reduce_word<%s>(a%d, scratch); if (threadIdx.x == 0) p.acc[(u64)blockIdx.x * NQ_W + %d] = r; }\n",
-                      op_name(kp.word_ops[w]), w, w);
-        }
-        // the last block to finish folds the per-block partials in a fixed order (deterministic float sums)
-        // and publishes the final words to HBM and, zero-copy, to mapped pinned host memory
+        s += "    {\n        const int warp = threadIdx.x >> 5;\n";
+        for (int w = 0; w < W; ++w)
+            s += strf("        { const u64 r = warp_reduce_word<%s>(a%d); if (lane == 0) s_part[%d][warp] = r; }\n", op_name(kp.word_ops[w]), w, w);
+        s += "    }\n";
+        s += "    __syncthreads();\n";
+        s += "    if (threadIdx.x < NQ_W) {\n";
+        s += "        const int w = threadIdx.x, op = nq_ops[w];\n";
+        s += "        u64 r = s_part[w][0];\n";
+        s += "        for (int k = 1; k < 8; ++k) r = word_combine(op, r, s_part[w][k]);\n";
+        s += "        if (op == OP_ADD_F64) p.partials[(u64)nq_fidx[w] * gridDim.x + blockIdx.x] = r;\n";
+        s += "        else if (r != word_identity(op)) atomic_word_dyn(op, &p.acc[w], r);\n";
+        s += "    }\n";
         s += "    if (last_block_arrives(p.ticket)) {\n";
-        s += "        const int warp = threadIdx.x >> 5;\n";
-        s += "        for (int w = warp; w < NQ_W; w += 8) {\n";
-        s += "            const int op = nq_ops[w];\n";
-        s += "            u64 v = word_identity(op);\n";
-        s += "            for (unsigned b = lane; b < gridDim.x; b += 32) v = word_combine(op, v, __ldcg(&p.acc[(u64)b * NQ_W + w]));\n";
-        s += "            v = warp_reduce_dyn(op, v);\n";
-        s += "            if (lane == 0) { p.final_dev[w] = v; p.final_host[w] = v; }\n";
+        s += "        if (threadIdx.x < NQ_W && nq_ops[threadIdx.x] != OP_ADD_F64) {\n";
+        s += "            const u64 v = atomicExch(&p.acc[threadIdx.x], word_identity(nq_ops[threadIdx.x]));\n";
+        s += "            p.final_dev[threadIdx.x] = v; p.final_host[threadIdx.x] = v;\n";
         s += "        }\n";
+        {
+            int fi = 0;
+            for (int w = 0; w < W; ++w) {
+                if (kp.word_ops[w] != OP_ADD_F64) continue;
+                s += "        {\n";
+                s += "            u64 t[5];\n";
+                s += "#pragma unroll\n";
+                s += strf("            for (int k = 0; k < 5; ++k) { const unsigned b = threadIdx.x + k * 256; t[k] = b < gridDim.x ? __ldcg(&p.partials[(u64)%d * gridDim.x + b]) : 0ULL; }\n", fi);
+                s += "            u64 v = t[0];\n";
+                s += "#pragma unroll\n";
+                s += "            for (int k = 1; k < 5; ++k) v = word_combine(OP_ADD_F64, v, t[k]);\n";
+                s += "            v = block_reduce_word<OP_ADD_F64>(v, scratch);\n";
+                s += strf("            if (threadIdx.x == 0) { p.final_dev[%d] = v; p.final_host[%d] = v; }\n", w, w);
+                s += "        }\n";
+                ++fi;
+            }
+        }
         s += "    }\n";
     } else if (kp.mode == MODE_DENSE) {
         s += "    __syncthreads();\n";

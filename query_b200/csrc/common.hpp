@@ -78,7 +78,14 @@ inline bool f_is_int(double d) { return d == (double)go_i64(d); }
 // value.NewValue(float64) (value/value.go:377-382)
 inline HValue new_num(double d) { return f_is_int(d) ? HValue::integer(go_i64(d)) : HValue::flt(d); }
 
-// Device buffer (cudaMalloc) with RAII.
+// caching allocators (mem.cpp)
+void* dev_alloc(size_t n, size_t* actual);
+void dev_free(void* p, size_t n);
+void dev_pool_trim();
+void* pin_alloc(size_t n, size_t* actual);
+void pin_free(void* p, size_t n);
+
+// Device buffer (pooled cudaMalloc) with RAII.
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -90,12 +97,10 @@ struct DevBuf {
     ~DevBuf() { release(); }
     void alloc(size_t n) {
         release();
-        if (n == 0) n = 256;
-        CK(cudaMalloc(&p, n));
-        bytes = n;
+        p = dev_alloc(n, &bytes);  // bytes = the (rounded-up) size actually held
     }
     void ensure(size_t n) { if (n > bytes) alloc(n); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p) dev_free(p, bytes); p = nullptr; bytes = 0; }
     template <class T> T* as() const { return (T*)p; }
 };
 
@@ -105,13 +110,12 @@ struct PinnedBuf {
     PinnedBuf() {}
     PinnedBuf(const PinnedBuf&) = delete;
     PinnedBuf& operator=(const PinnedBuf&) = delete;
-    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    ~PinnedBuf() { if (p) pin_free(p, bytes); }
     void ensure(size_t n) {
         if (n <= bytes) return;
-        if (p) cudaFreeHost(p);
+        if (p) pin_free(p, bytes);
         p = nullptr;
-        CK(cudaMallocHost(&p, n));
-        bytes = n;
+        p = pin_alloc(n, &bytes);
     }
     template <class T> T* as() const { return (T*)p; }
 };

@@ -404,6 +404,7 @@ struct NqParams {
     u64* final_dev;        // UNGROUPED: final words [nwords] in HBM (written by the last block to finish)
     u64* final_host;       // UNGROUPED/DENSE: the same words in mapped pinned host memory (zero-copy result)
     unsigned* ticket;      // blocks-done counter for the last-block pattern (self-resetting)
+    u64* partials;         // UNGROUPED: per-block partials of the float64-sum words [nfloat][grid]
 };
 
 // Dynamic-op warp reduction (the final, fixed-order fold of per-block partials by the last block).

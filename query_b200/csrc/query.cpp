@@ -32,8 +32,9 @@ struct NqParamsHost {
     u64* final_dev;
     u64* final_host;
     unsigned* ticket;
+    u64* partials;
 };
-static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 10, "NqParams layout");
+static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 11, "NqParams layout");
 
 u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
 
@@ -104,7 +105,16 @@ void Query::alloc_state() {
     const int W = ops.n;
     i64 blocks_needed = std::max<i64>(1, (table->nrows + 1023) / 1024);
     grid = (int)std::min<i64>(blocks_needed, (i64)device_sm_count() * kernel->max_blocks_per_sm);
-    if (kp.mode == MODE_UNGROUPED) { cap = 1; d_partials.ensure((size_t)grid * W * 8); }
+    if (grid > 1280) grid = 1280;  // the last block folds at most 5 x 256 float partials per word
+    if (kp.mode == MODE_UNGROUPED) {
+        cap = 1;
+        d_partials.ensure((size_t)grid * W * 8);
+        if (!d_accum.p) {  // persistent order-independent accumulators, re-armed by the kernel's last block
+            d_accum.alloc((size_t)W * 8);
+            launch_init_words(d_accum.as<u64>(), 1, ops, nullptr);
+            CK(cudaDeviceSynchronize());
+        }
+    }
     else if (kp.mode == MODE_DENSE) cap = (u64)kp.dense_slots;
     else {
         if (cap <= 1) {
@@ -146,7 +156,8 @@ void Query::launch_scan() {
     NqParamsHost p{};
     p.nrows = table->nrows;
     for (size_t c = 0; c < table->cols.size(); ++c) { p.col[c] = table->cols[c].d_payload.p; p.tag[c] = table->cols[c].d_tags.as<u8>(); }
-    p.acc = kp.mode == MODE_UNGROUPED ? d_partials.as<u64>() : d_acc.as<u64>();
+    p.acc = kp.mode == MODE_UNGROUPED ? d_accum.as<u64>() : d_acc.as<u64>();
+    p.partials = d_partials.as<u64>();
     p.keys = d_keys.as<u64>();
     p.cap_mask = cap - 1;
     p.set_keys = d_set.as<u64>();

@@ -39,7 +39,7 @@ struct Query {
     int grid = 0;
     u64 cap = 1;      // group slots (1 / dense slots / hash capacity)
     u64 set_cap = 0;  // DISTINCT entry set capacity
-    DevBuf d_partials, d_acc, d_keys, d_set, d_status, d_counts, d_records, d_drecords, d_ticket;
+    DevBuf d_partials, d_acc, d_accum, d_keys, d_set, d_status, d_counts, d_records, d_drecords, d_ticket;
     PinnedBuf h_status, h_counts, h_records, h_drecords;
     std::atomic<bool> cancelled{false};
     bool launched = false;

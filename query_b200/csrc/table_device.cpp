@@ -3,6 +3,7 @@
 // strings whose (few) members the host sorts bytewise, and only the documents the device could not decide exactly
 // are re-shredded on the host (fix-up rows) and patched in.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 
 #include "shred.hpp"
@@ -56,9 +57,17 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     if (sealed) N1_THROW(N1GPU_E_INVALID, "table is sealed");
     if (!have_device()) N1_THROW(N1GPU_E_CUDA, "the device shredder needs a CUDA device (there is no CPU fallback for it; use host threads explicitly)");
     if (appended || nrows != 0) N1_THROW(N1GPU_E_INVALID, "the device shredder takes the whole keyspace in one append");
-    if (cols.empty()) N1_THROW(N1GPU_E_INVALID, "no columns declared");
     if (ndocs < 0) N1_THROW(N1GPU_E_INVALID, "negative document count");
+    if (cols.empty()) {  // a chain that references no field (COUNT(*) only): rows are all that matters
+        nrows = ndocs;
+        appended = true;
+        device_shredded = true;
+        return;
+    }
     double t0 = now_sec();
+    const bool trace = getenv("N1GPU_TRACE") != nullptr;
+    double tp = t0;
+    auto phase = [&](const char* name) { if (trace) { double t = now_sec(); fprintf(stderr, "[n1gpu shred] %-22s %8.3f ms\n", name, (t - tp) * 1e3); tp = t; } };
     const i64 base_off = ndocs ? offsets[0] : 0;
     const i64 nbytes = ndocs ? offsets[ndocs] - base_off : 0;
     const int ncols = (int)cols.size();
@@ -115,6 +124,7 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     if ((i64)nfix > fix_cap)
         N1_THROW(N1GPU_E_INVALID, "device shredder: %u documents need host handling (escapes / long numbers); shred this keyspace with host threads", nfix);
 
+    phase("alloc+h2d+parse kernel");
     // ---- fix-up rows: the host shredder decides these documents -----------------------------------------------------
     std::string extra;  // unescaped string values of fix-up rows (device refs carry REF_EXTRA_BIT)
     DevBuf d_extra;
@@ -150,6 +160,7 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
         }
     } else d_extra.alloc(64);
 
+    phase("fix-up rows");
     // ---- statistics (class mask, int range) -------------------------------------------------------------------------
     DevBuf d_stats;
     d_stats.alloc((size_t)ncols * 32);
@@ -161,6 +172,7 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     CK(cudaMemcpyAsync(h_stats.data(), d_stats.p, h_stats.size() * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
 
+    phase("statistics");
     // ---- dictionaries + final payload width ------------------------------------------------------------------------------
     DevBuf d_slots, d_keys, d_status, d_count, d_oslots, d_orefs, d_rank;
     d_status.alloc(64);
@@ -246,6 +258,7 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
         if (!col.stats_forced) col.stats = st;
         col.codes_are_ranks = true;
     }
+    phase("dictionaries");
     appended = true;
     device_shredded = true;
     json_bytes += nbytes;

@@ -195,7 +195,7 @@ def test_launch_collect_pipeline_and_rebind():
     qq.rebind(tabs[1])
     r1 = qq.execute().rows()
     assert r0 == r1 == [([], [1000, 499500])]
-    assert q.launch_count() - before >= 4
+    assert q.launch_count() - before >= 2  # an ungrouped step is exactly one kernel launch (nq_scan)
     assert qq.last_scan_ns > 0
 
 

@@ -41,7 +41,7 @@ EDGE_DOCS = [
     '{"a": -9223372036854775808}', '{"a": 0.1}', '{"a": 123456789.123456789}', '{"a": 1e-7}', '{"a": 2.5e10}',
     '{"a": 1.7976931348623157e308}', '{"a": 4.9e-324}', '{"a": 12345678901234567890}', '{"a": 0.30000000000000004}',
     '{"s": "\\u00e9\\ud83d\\ude00", "a": 3}', '{"\\u0061": 5}', '{"s": "tab\\there"}', '{"s": ""}',
-    '{"a": {"b": 1}, "s": "obj"}', '{"a": [1, {"a": 5}], "s": "arr"}', '{"n": {"a": 7, "deep": {"a": 8}}, "a": 9}',
+    '{"c": {"b": 1}, "s": "obj"}', '{"c": [1, {"a": 5}], "s": "arr"}', '{"n": {"a": 7, "deep": {"a": 8}}, "a": 9}',
     '{"x": {"y": [1, 2, {"z": "q"}]}, "a": true, "s": null}', '{"a": false}', '{"a": null}',
     '{"s": "a"}', '{"s": "b"}', '{"s": "a"}', '{"s": "ab"}', '{"s": "B"}',
     '{ "a" : 4 , "s" : "spaced" }', '{"a":5,"s":"\\/"}',
