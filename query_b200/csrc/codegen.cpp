@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 
 namespace n1 {
@@ -458,7 +459,13 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     if (kp.mode == MODE_UNGROUPED) s += "#define ACC(k, OP, x) a##k = word_combine(OP, a##k, (u64)(x))\n";
     else if (kp.mode == MODE_DENSE) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
     else s += "#define ACC(k, OP, x) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
-    s += "extern \"C\" __global__ void __launch_bounds__(256) nq_scan(const NqParams p) {\n";
+    {
+        // resident blocks per SM the register allocator must allow (tuning knob N1GPU_MIN_BLOCKS; 0 = compiler's choice)
+        const char* lb = getenv("N1GPU_MIN_BLOCKS");
+        int minb = lb ? atoi(lb) : 0;
+        if (minb > 0) s += strf("extern \"C\" __global__ void __launch_bounds__(256, %d) nq_scan(const NqParams p) {\n", minb);
+        else s += "extern \"C\" __global__ void __launch_bounds__(256) nq_scan(const NqParams p) {\n";
+    }
     if (kp.mode == MODE_UNGROUPED) {
         for (int w = 0; w < W; ++w) s += strf("    u64 a%d = word_identity(%s);\n", w, op_name(kp.word_ops[w]));
     } else if (kp.mode == MODE_DENSE) {
