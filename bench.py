@@ -146,7 +146,7 @@ def run_ours(args):
         qq = q.Query(tables[i % NT], ALIAS, WHERE, KEYS, AGGS)
         qq.set_stream(side[i % NS].cuda_stream)
         queries.append(qq)
-    dqs = [qd.DistributedQuery(qq) for qq in queries]
+    dqs = [qd.DistributedQuery(qq, stream=side[i % NS]) for i, qq in enumerate(queries)]
     info = queries[0].info
     bytes_per_row = info["scan_bytes_per_row"]
 
@@ -162,9 +162,17 @@ def run_ours(args):
     # soak: keep scanning for ~1 s (untimed warm-up) so that clocks are ramped and nvidia-smi has samples under load
     t_soak = time.perf_counter()
     soak_steps = 0
-    while time.perf_counter() - t_soak < args.soak:
-        r = step_sync(soak_steps)
-        soak_steps += 1
+    while args.soak > 0:
+        for _ in range(50):
+            r = step_sync(soak_steps)
+            soak_steps += 1
+        done = time.perf_counter() - t_soak >= args.soak
+        if world > 1:  # every rank must run the same number of (collective) steps: rank 0 decides
+            flag = torch.tensor([1 if done else 0], device="cuda")
+            dist.broadcast(flag, 0)
+            done = bool(flag.item())
+        if done:
+            break
     W += soak_steps
     check_rows = r.rows() if rank == 0 else None
     torch.cuda.synchronize()
@@ -178,24 +186,20 @@ def run_ours(args):
     ev0.record(main)
     for s_ in side:
         s_.wait_event(ev0)   # device-side bracket: no scan starts before ev0 ...
-    if world == 1:
-        # pipelined: up to NQ scans in flight on the stream; results are collected in order
-        inflight = []
-        for s in range(K):
-            h = s % NQ
-            if len(inflight) == NQ:
-                j = inflight.pop(0)
-                queries[j].collect()
-                scan_ns.append(queries[j].last_scan_ns)
-            queries[h].launch()
-            inflight.append(h)
-        for j in inflight:
-            queries[j].collect()
+    # pipelined: up to NQ steps in flight over the streams; results are collected in order.  For N > 1 a step is
+    # scan -> all_gather of the accumulator words (NCCL, stream-ordered) -> merge kernel: no host round trip.
+    inflight = []
+    for s in range(K):
+        h = s % NQ
+        if len(inflight) == NQ:
+            j = inflight.pop(0)
+            dqs[j].collect()
             scan_ns.append(queries[j].last_scan_ns)
-    else:
-        for s in range(K):
-            step_sync(s)
-            scan_ns.append(queries[s % NQ].last_scan_ns)
+        dqs[h].launch()
+        inflight.append(h)
+    for j in inflight:
+        dqs[j].collect()
+        scan_ns.append(queries[j].last_scan_ns)
     for s_ in side:
         main.wait_stream(s_)  # ... and ev1 is recorded after every stream drained
     ev1.record(main)
@@ -309,7 +313,7 @@ def run_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64+f64", "data": "synthetic", "config": dict(CONFIG, kernel_mode=info["mode"], registers=info["registers"],
                                                                    grid=info["grid"], scan_bytes_per_row=bytes_per_row,
-                                                                   survey_bytes_per_row=18, merge="all_gather of partial records" if world > 1 else "none"),
+                                                                   survey_bytes_per_row=18, merge="per step: NCCL all_gather of the accumulator words + merge kernel, stream-ordered" if world > 1 else "none"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "rows_per_step": e2e_rows, "includes": ("H2D of the raw JSON + device shredder (shred.cu) + scan + result on the host" if args.shred_threads < 0
                              else "JSON shredding on host threads + column H2D + scan + result on the host"),

@@ -158,6 +158,16 @@ int n1gpu_query_partial_export(n1gpu_query* q, int nranks, void* dev_records, in
 int n1gpu_query_partial_reset(n1gpu_query* q);
 int n1gpu_query_partial_import(n1gpu_query* q, const void* dev_records, int64_t n, const void* dev_distinct, int64_t nd);
 int n1gpu_query_finalize(n1gpu_query* q, n1gpu_result** out);
+/* Small-state chains (no GROUP BY, or a dense shared-memory table; no DISTINCT): the whole partial state is
+ * nwords 64-bit accumulator words at *dev_words.  Pipelined multi-GPU step without host round trips:
+ *   n1gpu_query_launch(q);                       enqueue the scan on the query's stream
+ *   ncclAllGather(*dev_words -> all, nwords)      on the same stream (every rank's words, in rank order)
+ *   n1gpu_query_merge_words(q, all, nranks);      enqueue the fold over ranks (result also lands, zero-copy, in
+ *                                                 pinned host memory)
+ *   n1gpu_query_collect(q, &res);                 wait + FinalGroup
+ * n1gpu_query_state_words fails with N1GPU_E_INVALID for hash-table / DISTINCT chains (use partial_export).  */
+int n1gpu_query_state_words(n1gpu_query* q, void** dev_words, int64_t* nwords);
+int n1gpu_query_merge_words(n1gpu_query* q, const void* dev_all_words, int nranks);
 
 /* ---- result: what FinalGroup sends downstream ---------------------------------------------------------
  * Per group: the group-key values and, per aggregate (in the order given to compile), the final value

@@ -69,6 +69,8 @@ _SIGS = {
     "n1gpu_query_partial_reset": (C.c_int, [_P]),
     "n1gpu_query_partial_import": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64]),
     "n1gpu_query_finalize": (C.c_int, [_P, C.POINTER(_P)]),
+    "n1gpu_query_state_words": (C.c_int, [_P, C.POINTER(_P), _I64P]),
+    "n1gpu_query_merge_words": (C.c_int, [_P, _P, C.c_int]),
     "n1gpu_result_num_groups": (C.c_int64, [_P]),
     "n1gpu_result_num_keys": (C.c_int, [_P]),
     "n1gpu_result_num_aggregates": (C.c_int, [_P]),

@@ -354,6 +354,15 @@ class Query:
         check(lib().n1gpu_query_finalize(self._h, C.byref(r)))
         return Result(r)
 
+    def state_words(self):
+        """(device pointer, nwords) of the whole partial state of a small-state chain (ungrouped / dense, no DISTINCT)."""
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib().n1gpu_query_state_words(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def merge_words(self, dev_all_words, nranks):
+        check(lib().n1gpu_query_merge_words(self._h, C.c_void_p(dev_all_words), nranks))
+
     def close(self):
         if self._h:
             lib().n1gpu_query_free(self._h)

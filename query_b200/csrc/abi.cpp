@@ -260,6 +260,27 @@ int n1gpu_query_partial_reset(n1gpu_query* q) {
 int n1gpu_query_partial_import(n1gpu_query* q, const void* dev_records, int64_t n, const void* dev_distinct, int64_t nd) {
     return guard([&] { REQUIRE(q); q->q->partial_import(dev_records, n, dev_distinct, nd); });
 }
+int n1gpu_query_state_words(n1gpu_query* q, void** dev_words, int64_t* nwords) {
+    return guard([&] {
+        REQUIRE(q); REQUIRE(dev_words); REQUIRE(nwords);
+        Query& Q = *q->q;
+        if (!Q.kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
+        if (!(Q.kp.mode == MODE_UNGROUPED || Q.kp.mode == MODE_DENSE) || Q.kp.ndistinct)
+            N1_THROW(N1GPU_E_INVALID, "state_words is for ungrouped / dense chains without DISTINCT; use partial_export");
+        *dev_words = Q.d_acc.p;
+        *nwords = (int64_t)(Q.cap * (u64)Q.ops.n);
+    });
+}
+int n1gpu_query_merge_words(n1gpu_query* q, const void* dev_all_words, int nranks) {
+    return guard([&] {
+        REQUIRE(q); REQUIRE(dev_all_words);
+        Query& Q = *q->q;
+        if (!Q.kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
+        if (!(Q.kp.mode == MODE_UNGROUPED || Q.kp.mode == MODE_DENSE) || Q.kp.ndistinct) N1_THROW(N1GPU_E_INVALID, "not a small-state chain");
+        if (nranks < 1) N1_THROW(N1GPU_E_INVALID, "nranks must be >= 1");
+        launch_merge_words((const u64*)dev_all_words, nranks, Q.cap, Q.ops, Q.d_acc.as<u64>(), Q.h_records.as<u64>(), Q.stream);
+    });
+}
 int n1gpu_query_finalize(n1gpu_query* q, n1gpu_result** out) {
     return guard([&] { REQUIRE(q); REQUIRE(out); *out = new n1gpu_result{q->q->finalize()}; });
 }

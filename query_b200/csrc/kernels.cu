@@ -105,6 +105,19 @@ __global__ void k_merge_records(int kw, u64* keys, u64* acc, u64 cap, OpsArr ops
     }
 }
 
+// Small-state IntermediateGroup merge: all[r][w][slot] (the accumulator words of every rank, gathered by one
+// all_gather) folded over ranks in rank order (deterministic) into out_dev / out_host (zero-copy result).
+__global__ void k_merge_words(const u64* __restrict__ all, int nranks, u64 cap, OpsArr ops, u64* out_dev, u64* out_host) {
+    const u64 n = cap * (u64)ops.n;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const int op = ops.op[i / cap];
+        u64 v = all[i];
+        for (int r = 1; r < nranks; ++r) v = word_combine(op, v, all[(u64)r * n + i]);
+        out_dev[i] = v;
+        if (out_host) out_host[i] = v;
+    }
+}
+
 static int grid_for(u64 n) {
     u64 g = (n + 255) / 256;
     if (g < 1) g = 1;
@@ -112,6 +125,11 @@ static int grid_for(u64 n) {
     return (int)g;
 }
 
+void launch_merge_words(const u64* all, int nranks, u64 cap, const OpsArr& ops, u64* out_dev, u64* out_host, cudaStream_t s) {
+    k_merge_words<<<grid_for(cap * ops.n), 256, 0, s>>>(all, nranks, cap, ops, out_dev, out_host);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
 void launch_init_words(u64* acc, u64 cap, const OpsArr& ops, cudaStream_t s) {
     k_init_words<<<grid_for(cap * ops.n), 256, 0, s>>>(acc, cap, ops);
     g_launches.fetch_add(1);

@@ -9,6 +9,7 @@ struct OpsArr {
     int op[64];
 };
 
+void launch_merge_words(const u64* all, int nranks, u64 cap, const OpsArr& ops, u64* out_dev, u64* out_host, cudaStream_t s);
 void launch_init_words(u64* acc, u64 cap, const OpsArr& ops, cudaStream_t s);
 void launch_fill_u64(u64* p, u64 n, u64 v, cudaStream_t s);
 void launch_reduce_partials(const u64* partials, int nblocks, const OpsArr& ops, u64* out, cudaStream_t s);

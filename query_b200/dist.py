@@ -18,6 +18,14 @@ import torch
 import torch.distributed as dist
 
 
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
@@ -99,15 +107,55 @@ def agree_dictionaries_and_stats(table, group=None):
         table.set_stats(c, g)
 
 
-class DistributedQuery:
-    """Runs a compiled query on this rank's row range and merges the partial groups across ranks."""
+class _DevWords:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
 
-    def __init__(self, query, group=None):
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+class DistributedQuery:
+    """Runs a compiled query on this rank's row range and merges the partial groups across ranks.
+
+    launch()/collect() pipeline small-state chains without host round trips: scan -> all_gather of the
+    accumulator words (NCCL, stream-ordered) -> k_merge_words, all enqueued on `stream`; several steps can be in
+    flight on different streams.  Hash-table / DISTINCT chains use the blocking owner exchange in collect()."""
+
+    def __init__(self, query, group=None, stream=None):
         self.q = query
         self.group = group
-        self.small = query.info["mode"] in ("ungrouped", "dense-shared-memory")
+        self.stream = stream  # torch.cuda.Stream the query was bound to with set_stream (None: current stream)
+        self.small = query.info["mode"] in ("ungrouped", "dense-shared-memory") and "distinct" not in " ".join(query.aggregates)
         self._recs = None
         self._dents = None
+        self._all = None
+        self._view = None
+        self._launched = False
+
+    def launch(self):
+        q = self.q
+        w = world()
+        if w == 1 or not self.small:
+            if w == 1:
+                q.launch()
+            self._launched = True
+            return
+        q.launch()
+        if self._view is None:
+            ptr, n = q.state_words()
+            self._view = torch.as_tensor(_DevWords(ptr, n), device="cuda")
+            self._all = torch.empty(w * n, dtype=torch.int64, device="cuda")
+        ctx = torch.cuda.stream(self.stream) if self.stream is not None else _null()
+        with ctx:
+            dist.all_gather_into_tensor(self._all, self._view, group=self.group)  # stream-ordered after the scan
+        q.merge_words(self._all.data_ptr(), w)
+        self._launched = True
+
+    def collect(self):
+        self._launched = False
+        if world() == 1 or self.small:
+            return self.q.collect()
+        return self.execute()
 
     def _buffers(self, ng, nd, rw):
         need = max(1, ng) * rw
@@ -121,6 +169,9 @@ class DistributedQuery:
         """Returns a Result holding this rank's share of the groups (small state: rank 0 holds all, others none)."""
         q = self.q
         w = world()
+        if w > 1 and self.small:
+            self.launch()
+            return self.q.collect()
         q.scan_partial()
         if w == 1:
             return q.finalize()
