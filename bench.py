@@ -124,6 +124,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     q.init(local)
     K, W = args.steps, max(args.warmup, 3)
@@ -146,7 +148,10 @@ def run_ours(args):
         qq = q.Query(tables[i % NT], ALIAS, WHERE, KEYS, AGGS)
         qq.set_stream(side[i % NS].cuda_stream)
         queries.append(qq)
-    dqs = [qd.DistributedQuery(qq, stream=side[i % NS]) for i, qq in enumerate(queries)]
+    # N > 1: the Intermediate->Final merge is fused into the scan kernel (peer stores over NVLink into every rank's
+    # mailbox + a 1-block fold); --merge nccl switches to the NCCL all_gather of the accumulator words instead
+    mailbox = qd.make_mailbox(max_words=1024) if (world > 1 and args.merge == "fused") else None
+    dqs = [qd.DistributedQuery(qq, stream=side[i % NS], mailbox=mailbox) for i, qq in enumerate(queries)]
     info = queries[0].info
     bytes_per_row = info["scan_bytes_per_row"]
 
@@ -249,7 +254,7 @@ def run_ours(args):
         t.seal()
         qq = q.Query(t, ALIAS, WHERE, KEYS, AGGS)
         ts.append(time.perf_counter())
-        res = qd.DistributedQuery(qq).execute()
+        res = qd.DistributedQuery(qq, mailbox=mailbox).execute()
         rows = res.rows()
         ts.append(time.perf_counter())
         if trace:
@@ -313,7 +318,8 @@ def run_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64+f64", "data": "synthetic", "config": dict(CONFIG, kernel_mode=info["mode"], registers=info["registers"],
                                                                    grid=info["grid"], scan_bytes_per_row=bytes_per_row,
-                                                                   survey_bytes_per_row=18, merge="per step: NCCL all_gather of the accumulator words + merge kernel, stream-ordered" if world > 1 else "none"),
+                                                                   survey_bytes_per_row=18, merge=("none" if world == 1 else "fused into nq_scan: peer stores over NVLink into every rank's mailbox + 1-block fold"
+                                                                          if args.merge == "fused" else "NCCL all_gather of the accumulator words + merge kernel, stream-ordered")),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "rows_per_step": e2e_rows, "includes": ("H2D of the raw JSON + device shredder (shred.cu) + scan + result on the host" if args.shred_threads < 0
                              else "JSON shredding on host threads + column H2D + scan + result on the host"),
@@ -373,6 +379,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--shred-threads", type=int, default=-1, help="-1: device shredder (shred.cu); >= 0: host threads (0 = all cores)")
+    ap.add_argument("--merge", default="fused", choices=["fused", "nccl"], help="N > 1: how the per-step partial states are merged")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the resident-column steps are pipelined over")
     ap.add_argument("--soak", type=float, default=1.0, help="seconds of untimed scanning before the timed region")
     args = ap.parse_args()

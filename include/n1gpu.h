@@ -169,6 +169,20 @@ int n1gpu_query_finalize(n1gpu_query* q, n1gpu_result** out);
 int n1gpu_query_state_words(n1gpu_query* q, void** dev_words, int64_t* nwords);
 int n1gpu_query_merge_words(n1gpu_query* q, const void* dev_all_words, int nranks);
 
+/* Fused merge for small-state chains: instead of a collective, the scan kernel's last block stores this rank's
+ * accumulator words straight into every peer's mailbox over NVLink (peer stores + a release flag), and a 1-block
+ * kernel on each rank folds its own mailbox once all flags arrived.  A step is then launch + collect, no NCCL.
+ * Setup, once per process: create (HBM buffer of 64 slots x nranks cells of max_words+1 words), exchange the
+ * 64-byte CUDA IPC handles between the ranks (any transport), open_peers(handles of all ranks, rank-major),
+ * then n1gpu_query_set_mailbox on every query that should use it.  All ranks must launch the same sequence of
+ * steps on a mailbox.  A peer that never delivers makes collect fail with N1GPU_E_CUDA after ~10 s.           */
+typedef struct n1gpu_mailbox n1gpu_mailbox;
+int n1gpu_mailbox_create(int nranks, int rank, int64_t max_words, n1gpu_mailbox** out);
+int n1gpu_mailbox_ipc_handle(n1gpu_mailbox* mb, uint8_t handle[64]);
+int n1gpu_mailbox_open_peers(n1gpu_mailbox* mb, const uint8_t* handles);
+int n1gpu_mailbox_free(n1gpu_mailbox* mb);
+int n1gpu_query_set_mailbox(n1gpu_query* q, n1gpu_mailbox* mb);
+
 /* ---- result: what FinalGroup sends downstream ---------------------------------------------------------
  * Per group: the group-key values and, per aggregate (in the order given to compile), the final value
  * (algebra ComputeFinal).  A value is a class byte + 64-bit payload; string payloads index the result's

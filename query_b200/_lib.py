@@ -71,6 +71,11 @@ _SIGS = {
     "n1gpu_query_finalize": (C.c_int, [_P, C.POINTER(_P)]),
     "n1gpu_query_state_words": (C.c_int, [_P, C.POINTER(_P), _I64P]),
     "n1gpu_query_merge_words": (C.c_int, [_P, _P, C.c_int]),
+    "n1gpu_mailbox_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
+    "n1gpu_mailbox_ipc_handle": (C.c_int, [_P, C.c_char_p]),
+    "n1gpu_mailbox_open_peers": (C.c_int, [_P, C.c_char_p]),
+    "n1gpu_mailbox_free": (C.c_int, [_P]),
+    "n1gpu_query_set_mailbox": (C.c_int, [_P, _P]),
     "n1gpu_result_num_groups": (C.c_int64, [_P]),
     "n1gpu_result_num_keys": (C.c_int, [_P]),
     "n1gpu_result_num_aggregates": (C.c_int, [_P]),

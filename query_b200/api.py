@@ -363,6 +363,10 @@ class Query:
     def merge_words(self, dev_all_words, nranks):
         check(lib().n1gpu_query_merge_words(self._h, C.c_void_p(dev_all_words), nranks))
 
+    def set_mailbox(self, mailbox):
+        check(lib().n1gpu_query_set_mailbox(self._h, mailbox._h if mailbox is not None else None))
+        self._mailbox = mailbox
+
     def close(self):
         if self._h:
             lib().n1gpu_query_free(self._h)
@@ -373,6 +377,31 @@ class Query:
             self.close()
         except Exception:
             pass
+
+
+class Mailbox:
+    """Peer mailbox for the fused small-state multi-GPU merge (n1gpu_mailbox_*)."""
+
+    def __init__(self, nranks, rank, max_words=8192):
+        self._h = C.c_void_p()
+        self.nranks, self.rank = nranks, rank
+        check(lib().n1gpu_mailbox_create(nranks, rank, max_words, C.byref(self._h)))
+
+    def ipc_handle(self):
+        buf = C.create_string_buffer(64)
+        check(lib().n1gpu_mailbox_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def open_peers(self, handles):
+        """handles: list of nranks 64-byte handles in rank order (the own one is ignored)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.nranks
+        check(lib().n1gpu_mailbox_open_peers(self._h, blob))
+
+    def close(self):
+        if self._h:
+            lib().n1gpu_mailbox_free(self._h)
+            self._h = C.c_void_p()
 
 
 class Operator:

@@ -234,6 +234,60 @@ int n1gpu_query_set_stream(n1gpu_query* q, void* cuda_stream) {
 }
 int n1gpu_query_free(n1gpu_query* q) { delete q; return N1GPU_OK; }
 
+// ---- peer mailbox (fused small-state all-gather over NVLink) ----------------------------------------------------
+struct n1gpu_mailbox { Mailbox m; };
+int n1gpu_mailbox_create(int nranks, int rank, int64_t max_words, n1gpu_mailbox** out) {
+    return guard([&] {
+        REQUIRE(out);
+        if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks || max_words < 1) N1_THROW(N1GPU_E_INVALID, "bad mailbox geometry");
+        if (!have_device()) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
+        std::unique_ptr<n1gpu_mailbox> mb(new n1gpu_mailbox());
+        Mailbox& m = mb->m;
+        m.nranks = nranks; m.rank = rank; m.stride = (u64)max_words + 1;
+        m.bytes = (size_t)m.slots * nranks * m.stride * 8;
+        CK(cudaMalloc(&m.base, m.bytes));
+        CK(cudaMemset(m.base, 0, m.bytes));
+        CK(cudaDeviceSynchronize());
+        m.peers.assign((size_t)nranks, nullptr);
+        m.peers[(size_t)rank] = m.base;
+        *out = mb.release();
+    });
+}
+int n1gpu_mailbox_ipc_handle(n1gpu_mailbox* mb, uint8_t handle[64]) {
+    return guard([&] {
+        REQUIRE(mb); REQUIRE(handle);
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, mb->m.base));
+        memcpy(handle, &h, 64);
+    });
+}
+int n1gpu_mailbox_open_peers(n1gpu_mailbox* mb, const uint8_t* handles) {
+    return guard([&] {
+        REQUIRE(mb); REQUIRE(handles);
+        Mailbox& m = mb->m;
+        for (int r = 0; r < m.nranks; ++r) {
+            if (r == m.rank) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)r * 64, 64);
+            void* p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            m.peers[(size_t)r] = p;
+        }
+        m.d_peers.alloc((size_t)m.nranks * 8);
+        CK(cudaMemcpy(m.d_peers.p, m.peers.data(), (size_t)m.nranks * 8, cudaMemcpyHostToDevice));
+    });
+}
+int n1gpu_mailbox_free(n1gpu_mailbox* mb) { delete mb; return N1GPU_OK; }
+int n1gpu_query_set_mailbox(n1gpu_query* q, n1gpu_mailbox* mb) {
+    return guard([&] {
+        REQUIRE(q);
+        if (q->q->launched) N1_THROW(N1GPU_E_INVALID, "a scan is outstanding");
+        if (mb && mb->m.nranks > 1 && !mb->m.d_peers.p) N1_THROW(N1GPU_E_INVALID, "mailbox peers are not opened");
+        q->q->mailbox = mb ? &mb->m : nullptr;
+    });
+}
+
 // ---- multi-GPU partial state ----------------------------------------------------------------------------------
 int n1gpu_query_scan_partial(n1gpu_query* q) {
     return guard([&] { REQUIRE(q); q->q->scan_blocking(); });

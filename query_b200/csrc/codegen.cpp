@@ -545,6 +545,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 ++fi;
             }
         }
+        s += "        if (p.peer_mail) mailbox_push(p, p.final_dev);  // fused all-gather: peer stores over NVLink\n";
         s += "    }\n";
     } else if (kp.mode == MODE_DENSE) {
         s += "    __syncthreads();\n";
@@ -555,6 +556,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "    }\n";
         s += "    if (last_block_arrives(p.ticket)) {\n";
         s += "        for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) p.final_host[i] = __ldcg(&p.acc[i]);\n";
+        s += "        if (p.peer_mail) mailbox_push(p, p.acc);\n";
         s += "    }\n";
     }
     s += "}\n";

@@ -118,6 +118,36 @@ __global__ void k_merge_words(const u64* __restrict__ all, int nranks, u64 cap, 
     }
 }
 
+// Mailbox merge (the receive side of the scan kernel's fused all-gather): waits until every rank's words of
+// this step have landed (sequence flag, acquire at system scope; bounded spin -> status 3 on timeout), then
+// folds them in rank order.  One block; runs on this GPU while the senders are kernels on OTHER GPUs.
+__global__ void k_merge_mailbox(const u64* mail, int nranks, u64 slot_base, u64 stride, u64 words, u64 seq, u64 cap, OpsArr ops,
+                                u64* out_dev, u64* out_host, int* status) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < nranks) {
+        const u64* flag = mail + slot_base + (u64)threadIdx.x * stride + words;
+        u64 v = 0;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if (v == seq) break;
+            if (clock64() - t0 > 20000000000LL) { s_ok = 0; break; }  // ~10 s at 2 GHz: a peer never arrived
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (!s_ok) { if (threadIdx.x == 0) status[0] = 3; return; }
+    for (u64 i = threadIdx.x; i < words; i += blockDim.x) {
+        const int op = ops.op[i / cap];
+        u64 v = __ldcg(&mail[slot_base + i]);
+        for (int r = 1; r < nranks; ++r) v = word_combine(op, v, __ldcg(&mail[slot_base + (u64)r * stride + i]));
+        out_dev[i] = v;
+        if (out_host) out_host[i] = v;
+    }
+}
+
 static int grid_for(u64 n) {
     u64 g = (n + 255) / 256;
     if (g < 1) g = 1;
@@ -125,6 +155,12 @@ static int grid_for(u64 n) {
     return (int)g;
 }
 
+void launch_merge_mailbox(const u64* mail, int nranks, u64 slot_base, u64 stride, u64 words, u64 seq, u64 cap, const OpsArr& ops,
+                          u64* out_dev, u64* out_host, int* status, cudaStream_t s) {
+    k_merge_mailbox<<<1, 256, 0, s>>>(mail, nranks, slot_base, stride, words, seq, cap, ops, out_dev, out_host, status);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
 void launch_merge_words(const u64* all, int nranks, u64 cap, const OpsArr& ops, u64* out_dev, u64* out_host, cudaStream_t s) {
     k_merge_words<<<grid_for(cap * ops.n), 256, 0, s>>>(all, nranks, cap, ops, out_dev, out_host);
     g_launches.fetch_add(1);

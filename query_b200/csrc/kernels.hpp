@@ -9,6 +9,8 @@ struct OpsArr {
     int op[64];
 };
 
+void launch_merge_mailbox(const u64* mail, int nranks, u64 slot_base, u64 stride, u64 words, u64 seq, u64 cap, const OpsArr& ops,
+                          u64* out_dev, u64* out_host, int* status, cudaStream_t s);
 void launch_merge_words(const u64* all, int nranks, u64 cap, const OpsArr& ops, u64* out_dev, u64* out_host, cudaStream_t s);
 void launch_init_words(u64* acc, u64 cap, const OpsArr& ops, cudaStream_t s);
 void launch_fill_u64(u64* p, u64 n, u64 v, cudaStream_t s);

@@ -405,7 +405,31 @@ struct NqParams {
     u64* final_host;       // UNGROUPED/DENSE: the same words in mapped pinned host memory (zero-copy result)
     unsigned* ticket;      // blocks-done counter for the last-block pattern (self-resetting)
     u64* partials;         // UNGROUPED: per-block partials of the float64-sum words [nfloat][grid]
+    // multi-GPU small-state merge fused into the scan: the last block pushes this rank's final words straight into
+    // every peer's mailbox over NVLink (peer stores), then publishes a sequence flag (release, system scope)
+    u64* const* peer_mail; // [nranks] mailbox base of every rank (peer-mapped; own entry = local pointer), or null
+    int nranks, rank;
+    u64 mail_base;         // word offset of (slot, this rank) inside a mailbox
+    u64 mail_words;        // words pushed per step (accumulator words x slots of the dense table)
+    u64 mail_seq;          // sequence number of this step (never 0)
 };
+
+// Pushes `words` final words at src to every peer's mailbox and raises the flag word behind them.
+NQ_DEV void mailbox_push(const NqParams& p, const u64* src) {
+    __threadfence();
+    __syncthreads();
+    const u64 total = p.mail_words * (u64)p.nranks;
+    for (u64 i = threadIdx.x; i < total; i += blockDim.x) {
+        const u64 r = i / p.mail_words, w = i % p.mail_words;
+        p.peer_mail[r][p.mail_base + w] = __ldcg(&src[w]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < p.nranks) {
+        u64* flag = &p.peer_mail[threadIdx.x][p.mail_base + p.mail_words];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.mail_seq) : "memory");
+    }
+}
 
 // Dynamic-op warp reduction (the final, fixed-order fold of per-block partials by the last block).
 NQ_DEV u64 warp_reduce_dyn(int op, u64 v) {

@@ -33,8 +33,13 @@ struct NqParamsHost {
     u64* final_host;
     unsigned* ticket;
     u64* partials;
+    u64* const* peer_mail;
+    int nranks, rank;
+    u64 mail_base;
+    u64 mail_words;
+    u64 mail_seq;
 };
-static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 11, "NqParams layout");
+static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 16, "NqParams layout");
 
 u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
 
@@ -140,7 +145,13 @@ void Query::alloc_state() {
     if (kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) h_records.ensure((size_t)cap * W * 8);
 }
 
-bool Query::uses_status() const { return kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128 || kp.ndistinct > 0; }
+bool Query::uses_status() const { return kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128 || kp.ndistinct > 0 || mailbox != nullptr; }
+
+Mailbox::~Mailbox() {
+    for (int r = 0; r < (int)peers.size(); ++r)
+        if (r != rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
+    if (base) cudaFree(base);
+}
 
 void Query::reset_state() {
     if (uses_status()) CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
@@ -167,10 +178,28 @@ void Query::launch_scan() {
     p.final_dev = d_acc.as<u64>();
     p.final_host = h_records.as<u64>();  // pinned memory is device-addressable under UVA: zero-copy result
     p.ticket = d_ticket.as<unsigned>();
+    const bool small = (kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) && kp.ndistinct == 0;
+    u64 mb_slot_base = 0, mb_seq = 0;
+    if (mailbox && small && mailbox->nranks > 1) {
+        const u64 words = cap * (u64)ops.n;
+        if (words + 1 > mailbox->stride) N1_THROW(N1GPU_E_INVALID, "mailbox cells hold %llu words, the chain needs %llu", mailbox->stride - 1, words);
+        mb_seq = ++mailbox->seq;
+        const u64 slot = mb_seq % (u64)mailbox->slots;
+        mb_slot_base = slot * (u64)mailbox->nranks * mailbox->stride;
+        p.peer_mail = (u64* const*)mailbox->d_peers.p;
+        p.nranks = mailbox->nranks;
+        p.rank = mailbox->rank;
+        p.mail_base = mb_slot_base + (u64)mailbox->rank * mailbox->stride;
+        p.mail_words = words;
+        p.mail_seq = mb_seq;
+    }
     reset_state();
     CK(cudaEventRecord(ev0, stream));
     jit_launch(*kernel, grid, stream, &p, sizeof p);  // ungrouped / dense: the whole step is this one launch
     CK(cudaEventRecord(ev1, stream));
+    if (mb_seq)  // receive side of the fused all-gather: fold every rank's words once they have landed
+        launch_merge_mailbox((const u64*)mailbox->base, mailbox->nranks, mb_slot_base, mailbox->stride, cap * (u64)ops.n, mb_seq, cap, ops,
+                             d_acc.as<u64>(), h_records.as<u64>(), d_status.as<int>(), stream);
     if (uses_status()) CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
     launched = true;
     ungrouped_live = true;
@@ -183,7 +212,8 @@ bool Query::wait_scan() {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     last_scan_ms = ms;
-    int st = h_status.as<int>()[0];
+    int st = uses_status() ? h_status.as<int>()[0] : 0;
+    if (st == 3) N1_THROW(N1GPU_E_CUDA, "multi-GPU merge timed out: a peer rank never delivered its partial state");
     if (st == 1) {
         if (cap >= ((u64)1 << 31)) N1_THROW(N1GPU_E_NOMEM, "group table would exceed 2^31 slots");
         cap *= 4;

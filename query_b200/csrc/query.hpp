@@ -23,8 +23,23 @@ struct Result {
     i64 stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
+// Peer mailbox for the fused small-state all-gather: every rank owns slots x nranks cells of (stride) words in
+// HBM, exported to the other ranks' processes through CUDA IPC; scan kernels store into the peers' cells over
+// NVLink, k_merge_mailbox folds the own mailbox.
+struct Mailbox {
+    int nranks = 1, rank = 0, slots = 64;
+    u64 stride = 0;              // words per cell = max_words + 1 (sequence flag)
+    void* base = nullptr;        // own buffer (plain cudaMalloc: IPC-exported, never pooled)
+    size_t bytes = 0;
+    std::vector<void*> peers;    // [nranks], own entry = base
+    DevBuf d_peers;              // the same pointers in device memory
+    u64 seq = 0;
+    ~Mailbox();
+};
+
 struct Query {
     Table* table = nullptr;
+    Mailbox* mailbox = nullptr;
     std::string alias, where_text;
     std::vector<std::string> key_texts, agg_texts;
     ExprP where;

@@ -107,6 +107,21 @@ def agree_dictionaries_and_stats(table, group=None):
         table.set_stats(c, g)
 
 
+def make_mailbox(max_words=8192, group=None):
+    """Creates this rank's peer mailbox and wires it to every other rank's (CUDA IPC handles exchanged through
+    torch.distributed).  Returns None for a single rank."""
+    from .api import Mailbox
+    w = world()
+    if w == 1:
+        return None
+    mb = Mailbox(w, rank(), max_words)
+    handles = [None] * w
+    dist.all_gather_object(handles, mb.ipc_handle(), group=group)
+    mb.open_peers(handles)
+    dist.barrier(group=group)  # nobody pushes before every mailbox is mapped everywhere
+    return mb
+
+
 class _DevWords:
     """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
 
@@ -121,11 +136,15 @@ class DistributedQuery:
     accumulator words (NCCL, stream-ordered) -> k_merge_words, all enqueued on `stream`; several steps can be in
     flight on different streams.  Hash-table / DISTINCT chains use the blocking owner exchange in collect()."""
 
-    def __init__(self, query, group=None, stream=None):
+    def __init__(self, query, group=None, stream=None, mailbox=None):
         self.q = query
         self.group = group
         self.stream = stream  # torch.cuda.Stream the query was bound to with set_stream (None: current stream)
         self.small = query.info["mode"] in ("ungrouped", "dense-shared-memory") and "distinct" not in " ".join(query.aggregates)
+        # with a peer mailbox the merge of a small-state chain is fused into the scan: launch()/collect() only
+        self.fused = bool(mailbox is not None and self.small and world() > 1)
+        if self.fused:
+            query.set_mailbox(mailbox)
         self._recs = None
         self._dents = None
         self._all = None
@@ -141,6 +160,9 @@ class DistributedQuery:
             self._launched = True
             return
         q.launch()
+        if self.fused:  # peer stores + mailbox merge are already enqueued by the library
+            self._launched = True
+            return
         if self._view is None:
             ptr, n = q.state_words()
             self._view = torch.as_tensor(_DevWords(ptr, n), device="cuda")

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun on N GPUs; `gpurun --gpus 2 -- python -m torch.distributed.run
+--nproc-per-node 2 --master-addr 127.0.0.1 tests/mgpu_check.py`): every merge strategy of query_b200.dist -
+fused peer-mailbox, NCCL all_gather of accumulator words, owner-bucketed all_to_all of records and DISTINCT
+entries - must reproduce what ONE rank computes over the whole keyspace, which in turn equals the oracle."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import query_b200 as q  # noqa: E402
+from gen_n1 import QUERIES, make_docs  # noqa: E402
+from query_b200 import dist as qd  # noqa: E402
+from util_n1 import assert_same, gpu_rows, make_table, oracle_rows  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    q.init(local)
+    mailbox = qd.make_mailbox(max_words=8192)
+    docs = make_docs(8000, seed=5)
+    lo, hi = qd.row_range(len(docs))
+    mine = docs[lo:hi]
+    names = ["ungrouped_all_i", "ungrouped_all_f", "ungrouped_all_mixed", "between_ints", "arith_float", "group_small_int", "group_string",
+             "group_two_keys", "group_high_card", "group_wide_keys_128", "group_float_key", "distinct_ungrouped", "distinct_grouped",
+             "distinct_high_card_group", "where_false_ungrouped", "group_mixed_key", "nested_paths"]
+    checked = 0
+    for name, where, keys, aggs in QUERIES:
+        if name not in names:
+            continue
+        exp = oracle_rows(docs, "d", where, keys, aggs) if rank == 0 else None
+        for strategy in ("fused", "nccl"):
+            t = make_table(mine, where, keys, aggs)
+            qd.agree_dictionaries_and_stats(t)
+            t.seal()
+            qq = q.Query(t, "d", where, keys, aggs)
+            dq = qd.DistributedQuery(qq, mailbox=mailbox if strategy == "fused" else None)
+            res = dq.execute()
+            part = gpu_rows(res, aggs)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, {json.dumps(k): v for k, v in part.items()})
+            if rank == 0:
+                if dq.small:  # small state is merged on every rank: each holds the complete (replicated) result
+                    for g in gathered:
+                        assert_same(exp, {tuple(json.loads(k)): v for k, v in g.items()}, "%s [%s, replicated]" % (name, strategy))
+                else:         # hash tables / DISTINCT: every group is finalised by exactly one owner
+                    got = {}
+                    for g in gathered:
+                        for k, v in g.items():
+                            kk = tuple(json.loads(k))
+                            assert kk not in got, "group %r finalised by two ranks (%s, %s)" % (kk, name, strategy)
+                            got[kk] = v
+                    assert_same(exp, got, "%s [%s, %d ranks]" % (name, strategy, world))
+            checked += 1
+    # pipelined fused steps on several streams: results stay correct and ordered
+    name, where, keys, aggs = QUERIES[0]
+    t = make_table(mine, where, keys, aggs)
+    qd.agree_dictionaries_and_stats(t)
+    t.seal()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    dqs = []
+    for i in range(6):
+        qq = q.Query(t, "d", where, keys, aggs)
+        qq.set_stream(streams[i % 3].cuda_stream)
+        dqs.append(qd.DistributedQuery(qq, stream=streams[i % 3], mailbox=mailbox))
+    exp = oracle_rows(docs, "d", where, keys, aggs)
+    for rep in range(20):
+        for d in dqs:
+            d.launch()
+        for d in dqs:
+            assert_same(exp, gpu_rows(d.collect(), aggs), "pipelined fused step")
+    dist.barrier()
+    if rank == 0:
+        print("mgpu_check ok: %d (query, strategy) combinations on %d ranks + 120 pipelined fused steps" % (checked, world))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
