@@ -383,6 +383,12 @@ def main():
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the resident-column steps are pipelined over")
     ap.add_argument("--soak", type=float, default=1.0, help="seconds of untimed scanning before the timed region")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print banners to fd 1 (NCCL's version line) are sent to
+    # stderr for the duration of the run, and the JSON line goes to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:

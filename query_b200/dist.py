@@ -145,6 +145,9 @@ class DistributedQuery:
         self.fused = bool(mailbox is not None and self.small and world() > 1)
         if self.fused:
             query.set_mailbox(mailbox)
+        elif self.small and world() > 1 and stream is None:
+            # the NCCL all_gather is ordered against torch's current stream: the scan must run on that stream too
+            query.set_stream(torch.cuda.current_stream().cuda_stream)
         self._recs = None
         self._dents = None
         self._all = None
@@ -211,6 +214,7 @@ class DistributedQuery:
         counts, dcounts = q.partial_export(w, self._recs.data_ptr(), ng, self._dents.data_ptr(), nd)
         got, rc = exchange_by_owner(self._recs, counts, rw, self.group)
         dgot, drc = exchange_by_owner(self._dents, dcounts, 2, self.group)
+        torch.cuda.current_stream().synchronize()  # the import kernels run on the query's stream: records must have landed
         q.partial_reset()
         n, ndg = sum(rc), sum(drc)
         q.partial_import(got.data_ptr() if n else 0, n, dgot.data_ptr() if ndg else 0, ndg)
