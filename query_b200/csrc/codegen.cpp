@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <map>
+#include <set>
 
 namespace n1 {
 
@@ -269,9 +270,20 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         kp.key_bits += kp.keys.back().bits();
         est *= comp_domain(t, kp.keys.back());
     }
-    auto add_word = [&](int op) { kp.word_ops.push_back(op); return (int)kp.word_ops.size() - 1; };
+    // Accumulator words are shared between aggregates wherever they would hold the same value: SUM(x), AVG(x),
+    // COUNT(x), COUNTN(x) over the same operand text use one sum word / one count word, and a count that provably
+    // equals the number of selected rows (operand never MISSING/NULL/non-number) is the rows word itself.
+    std::map<std::string, int> shared;
+    auto add_word = [&](int op, const std::string& key) {
+        auto it = shared.find(key);
+        if (it != shared.end()) return it->second;
+        kp.word_ops.push_back(op);
+        shared[key] = (int)kp.word_ops.size() - 1;
+        return (int)kp.word_ops.size() - 1;
+    };
     int w_rows = -1;
-    if (!keys.empty()) w_rows = add_word(OP_ADD_U64);  // word 0: rows per group (group existence)
+    if (!keys.empty()) w_rows = add_word(OP_ADD_U64, "rows");  // word 0: rows per group (group existence)
+    auto rows_word = [&]() { if (w_rows < 0) w_rows = add_word(OP_ADD_U64, "rows"); return w_rows; };
 
     // ---- aggregate layout --------------------------------------------------------------------------------
     for (size_t a = 0; a < aggs.size(); ++a) {
@@ -287,8 +299,12 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             ap.distinct_id = kp.ndistinct++;
             ap.dcomp = make_comp(t, *opnd, "DISTINCT");
         } else if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) {
-            if (ap.star && w_rows >= 0) ap.w_cnt = w_rows; else ap.w_cnt = add_word(OP_ADD_U64);
+            const std::string ot = opnd ? opnd->str() : std::string("*");
+            const u32 counted = ap.kind == AggKind::COUNT ? ~(bit(C_MISSING) | bit(C_NULL)) : M_NUM;
+            if (ap.star || (ap.opmask & ~counted) == 0) ap.w_cnt = rows_word();  // every selected row counts
+            else ap.w_cnt = add_word(OP_ADD_U64, (ap.kind == AggKind::COUNT ? "cnt:" : "cntn:") + ot);
         } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
+            const std::string ot = opnd->str();
             if (ap.opmask & bit(C_INT)) {
                 const TypeInfo& ti = opnd->ti;
                 bool exact1 = false;
@@ -296,32 +312,45 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                     double mx = std::max(std::fabs((double)ti.lo), std::fabs((double)ti.hi));
                     exact1 = mx * std::max(1.0, total_rows_bound) < 2.3e18;  // < 2^61: no int64 overflow possible
                 }
-                if (exact1) ap.w_isum = add_word(OP_ADD_U64);
-                else { ap.w_ilo = add_word(OP_ADD_U64); ap.w_ihi = add_word(OP_ADD_U64); }
+                if (exact1) ap.w_isum = add_word(OP_ADD_U64, "isum:" + ot);
+                else { ap.w_ilo = add_word(OP_ADD_U64, "ilo:" + ot); ap.w_ihi = add_word(OP_ADD_U64, "ihi:" + ot); }
                 bool can_neg = !ti.ranged || ti.lo < 0, can_nonneg = !ti.ranged || ti.hi >= 0;
-                if (can_nonneg) ap.w_nonneg = add_word(OP_ADD_U64);
-                if (can_neg) ap.w_neg = add_word(OP_ADD_U64);
+                const bool always_int = ap.opmask == bit(C_INT);
+                if (can_nonneg) ap.w_nonneg = (always_int && !can_neg) ? rows_word() : add_word(OP_ADD_U64, "nnn:" + ot);
+                if (can_neg) ap.w_neg = (always_int && !can_nonneg) ? rows_word() : add_word(OP_ADD_U64, "nneg:" + ot);
             }
-            if (ap.opmask & bit(C_FLOAT)) { ap.w_fsum = add_word(OP_ADD_F64); ap.w_nflt = add_word(OP_ADD_U64); }
+            if (ap.opmask & bit(C_FLOAT)) {
+                ap.w_fsum = add_word(OP_ADD_F64, "fsum:" + ot);
+                ap.w_nflt = ap.opmask == bit(C_FLOAT) ? rows_word() : add_word(OP_ADD_U64, "nflt:" + ot);
+            }
         } else {  // MIN / MAX
             bool mn = ap.kind == AggKind::MIN;
+            const std::string ot = (mn ? "min:" : "max:") + opnd->str();
             u32 m = ap.opmask;
             if (m & bit(C_STRING)) { if (ap.dict_col < 0) N1_THROW(N1GPU_E_INELIGIBLE, "MIN/MAX over a constant or computed string"); }
             if (opnd && !opnd->ti.plain_col && (m & bit(C_FLOAT))) m |= bit(C_INT);  // canon_num
             ap.opmask = m;
-            ap.w_seen = add_word(OP_OR_U64);
-            if (m & bit(C_INT)) ap.w_mi = add_word(mn ? OP_MIN_I64 : OP_MAX_I64);
-            if (m & bit(C_FLOAT)) ap.w_mf = add_word(mn ? OP_MIN_U64 : OP_MAX_U64);
-            if (m & bit(C_STRING)) ap.w_ms = add_word(mn ? OP_MIN_U64 : OP_MAX_U64);
+            ap.w_seen = add_word(OP_OR_U64, "seen:" + opnd->str());  // MIN and MAX of one operand see the same classes
+            if (m & bit(C_INT)) ap.w_mi = add_word(mn ? OP_MIN_I64 : OP_MAX_I64, "i:" + ot);
+            if (m & bit(C_FLOAT)) ap.w_mf = add_word(mn ? OP_MIN_U64 : OP_MAX_U64, "f:" + ot);
+            if (m & bit(C_STRING)) ap.w_ms = add_word(mn ? OP_MIN_U64 : OP_MAX_U64, "s:" + ot);
         }
         kp.aggs.push_back(ap);
     }
-    if (kp.word_ops.empty()) add_word(OP_ADD_U64);  // keep at least one word (only DISTINCT aggregates)
+    if (kp.word_ops.empty()) rows_word();  // keep at least one word (only DISTINCT aggregates)
     const int W = (int)kp.word_ops.size();
 
     // ---- mode ------------------------------------------------------------------------------------------------
     if (keys.empty()) kp.mode = MODE_UNGROUPED;
-    else if (kp.key_bits <= 13 && ((i64)1 << kp.key_bits) * W * 8 <= 40 * 1024) { kp.mode = MODE_DENSE; kp.dense_slots = (i64)1 << kp.key_bits; }
+    else if (kp.key_bits <= 13 && ((i64)1 << kp.key_bits) * W * 8 <= 40 * 1024) {
+        kp.mode = MODE_DENSE;
+        kp.dense_slots = (i64)1 << kp.key_bits;
+        // A handful of groups (TPC-H Q1: 6) would serialise every row on the same few shared-memory words.  When the
+        // whole table is <= 48 words, every thread keeps its own copy in shared memory (bank = thread: conflict-free
+        // plain read-modify-write, no atomics) and the copies are folded once per block.
+        const char* np = getenv("N1GPU_NO_PRIV");
+        if (kp.dense_slots * W <= 48 && !(np && *np == '1')) { kp.dense_priv = true; kp.dyn_smem = (int)(kp.dense_slots * W * 256 * 8); }
+    }
     else if (kp.key_bits <= 63) kp.mode = MODE_HASH64;
     else if (kp.key_bits <= 127) kp.mode = MODE_HASH128;
     else N1_THROW(N1GPU_E_INELIGIBLE, "group key needs %d bits (> 127) after packing", kp.key_bits);
@@ -365,8 +394,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         else if (kp.mode == MODE_HASH64) g.line("const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);");
         else g.line("const i64 slot = table_insert128((ulonglong2*)p.keys, p.cap_mask, klo, khi, nullptr);");
         if (kp.mode != MODE_DENSE) g.line("if (slot < 0) { p.status[0] = 1; continue; }");
-        g.line("ACC(0, OP_ADD_U64, 1);");
     }
+    std::set<int> emitted;  // a shared word is updated once per row, by the first aggregate that owns it
+    if (w_rows >= 0) { g.line(strf("ACC(%d, OP_ADD_U64, 1);  // rows", w_rows)); emitted.insert(w_rows); }
     for (size_t a = 0; a < kp.aggs.size(); ++a) {
         const AggPlan& ap = kp.aggs[a];
         const Expr& e = *aggs[a];
@@ -375,7 +405,14 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         g.ind += "    ";
         std::string o;
         if (!ap.star) o = g.emit(*e.ops[0], nullptr);
-        auto ACC = [&](int w, int op, const std::string& x) { g.line(strf("ACC(%d, %s, %s);", w, op_name(op), x.c_str())); };
+        auto ACC = [&](int w, int op, const std::string& x) {
+            if (!emitted.insert(w).second) return;  // another aggregate over the same operand already feeds this word
+            g.line(strf("ACC(%d, %s, %s);", w, op_name(op), x.c_str()));
+        };
+        auto ACCIF = [&](const std::string& cond, int w, int op, const std::string& x) {
+            if (!emitted.insert(w).second) return;
+            g.line(strf("if (%s) { ACC(%d, %s, %s); }", cond.c_str(), w, op_name(op), x.c_str()));
+        };
         if (ap.distinct) {
             std::string cond = (ap.kind == AggKind::COUNT) ? strf("%s.c > C_NULL", o.c_str()) : strf("is_num(%s.c)", o.c_str());
             g.line(strf("if (%s) {", cond.c_str()));
@@ -394,10 +431,10 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             g.ind = save_ind + "    ";
             g.line("}");
         } else if (ap.kind == AggKind::COUNT) {
-            if (ap.star) { if (ap.w_cnt != 0 || kp.mode == MODE_UNGROUPED) ACC(ap.w_cnt, OP_ADD_U64, "1"); }
-            else { g.line(strf("if (%s.c > C_NULL)", o.c_str())); ACC(ap.w_cnt, OP_ADD_U64, "1"); }
+            if (ap.star) ACC(ap.w_cnt, OP_ADD_U64, "1");
+            else ACCIF(strf("%s.c > C_NULL", o.c_str()), ap.w_cnt, OP_ADD_U64, "1");
         } else if (ap.kind == AggKind::COUNTN) {
-            g.line(strf("if (is_num(%s.c))", o.c_str())); ACC(ap.w_cnt, OP_ADD_U64, "1");
+            ACCIF(strf("is_num(%s.c)", o.c_str()), ap.w_cnt, OP_ADD_U64, "1");
         } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
             if (ap.opmask & bit(C_INT)) {
                 g.line(strf("if (%s.c == C_INT) {", o.c_str()));
@@ -408,7 +445,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                     ACC(ap.w_ihi, OP_ADD_U64, strf("(u64)(%s.b >> 32)", o.c_str()));
                 }
                 if (ap.w_nonneg >= 0 && ap.w_neg >= 0) {
-                    g.line(strf("if (%s.b >= 0) { ACC(%d, OP_ADD_U64, 1); } else { ACC(%d, OP_ADD_U64, 1); }", o.c_str(), ap.w_nonneg, ap.w_neg));
+                    ACCIF(strf("%s.b >= 0", o.c_str()), ap.w_nonneg, OP_ADD_U64, "1");
+                    ACCIF(strf("%s.b < 0", o.c_str()), ap.w_neg, OP_ADD_U64, "1");
                 } else if (ap.w_nonneg >= 0) ACC(ap.w_nonneg, OP_ADD_U64, "1");
                 else if (ap.w_neg >= 0) ACC(ap.w_neg, OP_ADD_U64, "1");
                 g.ind = save_ind + "    ";
@@ -429,9 +467,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             g.line(strf("if (%s.c > C_NULL) {", cv.c_str()));
             g.ind += "    ";
             ACC(ap.w_seen, OP_OR_U64, strf("(1ULL << %s.c)", cv.c_str()));
-            if (ap.w_mi >= 0) { g.line(strf("if (%s.c == C_INT)", cv.c_str())); ACC(ap.w_mi, mn ? OP_MIN_I64 : OP_MAX_I64, strf("(u64)%s.b", cv.c_str())); }
-            if (ap.w_mf >= 0) { g.line(strf("if (%s.c == C_FLOAT)", cv.c_str())); ACC(ap.w_mf, mn ? OP_MIN_U64 : OP_MAX_U64, strf("f64_ordered(as_f(%s.b))", cv.c_str())); }
-            if (ap.w_ms >= 0) { g.line(strf("if (%s.c == C_STRING)", cv.c_str())); ACC(ap.w_ms, mn ? OP_MIN_U64 : OP_MAX_U64, strf("((u64)%s.b >> 1)", cv.c_str())); }
+            if (ap.w_mi >= 0) ACCIF(strf("%s.c == C_INT", cv.c_str()), ap.w_mi, mn ? OP_MIN_I64 : OP_MAX_I64, strf("(u64)%s.b", cv.c_str()));
+            if (ap.w_mf >= 0) ACCIF(strf("%s.c == C_FLOAT", cv.c_str()), ap.w_mf, mn ? OP_MIN_U64 : OP_MAX_U64, strf("f64_ordered(as_f(%s.b))", cv.c_str()));
+            if (ap.w_ms >= 0) ACCIF(strf("%s.c == C_STRING", cv.c_str()), ap.w_ms, mn ? OP_MIN_U64 : OP_MAX_U64, strf("((u64)%s.b >> 1)", cv.c_str()));
             g.ind = save_ind + "    ";
             g.line("}");
         }
@@ -457,6 +495,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     for (int w = 0, fi = 0; w < W; ++w) s += strf("%s%d", w ? ", " : "", kp.word_ops[w] == OP_ADD_F64 ? fi++ : -1);
     s += "};\n";
     if (kp.mode == MODE_UNGROUPED) s += "#define ACC(k, OP, x) a##k = word_combine(OP, a##k, (u64)(x))\n";
+    else if (kp.mode == MODE_DENSE && kp.dense_priv)
+        s += "#define ACC(k, OP, val_) { u64* c_ = &s_priv[(((k) * NQ_G + slot) << 8) + threadIdx.x]; *c_ = word_combine(OP, *c_, (u64)(val_)); }\n";
     else if (kp.mode == MODE_DENSE) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
     else s += "#define ACC(k, OP, x) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
     {
@@ -468,6 +508,10 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     }
     if (kp.mode == MODE_UNGROUPED) {
         for (int w = 0; w < W; ++w) s += strf("    u64 a%d = word_identity(%s);\n", w, op_name(kp.word_ops[w]));
+    } else if (kp.mode == MODE_DENSE && kp.dense_priv) {
+        s += "    extern __shared__ u64 s_priv[];  // [NQ_W * NQ_G cells][256 threads]: cell c of thread t at (c << 8) + t\n";
+        s += "#pragma unroll\n";
+        s += "    for (int c = 0; c < NQ_W * NQ_G; ++c) s_priv[(c << 8) + threadIdx.x] = word_identity(nq_ops[c / NQ_G]);\n";
     } else if (kp.mode == MODE_DENSE) {
         s += "    __shared__ u64 s_tab[NQ_W * NQ_G];\n";
         s += "    for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) s_tab[i] = word_identity(nq_ops[i / NQ_G]);\n";
@@ -548,12 +592,29 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "        if (p.peer_mail) mailbox_push(p, p.final_dev);  // fused all-gather: peer stores over NVLink\n";
         s += "    }\n";
     } else if (kp.mode == MODE_DENSE) {
-        s += "    __syncthreads();\n";
-        s += "    for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) {\n";
-        s += "        const int op = nq_ops[i / NQ_G];\n";
-        s += "        const u64 v = s_tab[i];\n";
-        s += "        if (v != word_identity(op)) atomic_word_dyn(op, &p.acc[i], v);\n";
-        s += "    }\n";
+        if (kp.dense_priv) {
+            // fold the 256 private copies of every cell: 8 warp-shuffle reductions per cell, then thread c folds cell c's
+            // 8 warp values in order and applies one global atomic per (block, cell)
+            s += "    __shared__ u64 s_wpart[NQ_W * NQ_G][8];\n";
+            s += "    for (int c = 0; c < NQ_W * NQ_G; ++c) {\n";
+            s += "        const u64 r = warp_reduce_dyn(nq_ops[c / NQ_G], s_priv[(c << 8) + threadIdx.x]);\n";
+            s += "        if (lane == 0) s_wpart[c][threadIdx.x >> 5] = r;\n";
+            s += "    }\n";
+            s += "    __syncthreads();\n";
+            s += "    if (threadIdx.x < NQ_W * NQ_G) {\n";
+            s += "        const int op = nq_ops[threadIdx.x / NQ_G];\n";
+            s += "        u64 v = s_wpart[threadIdx.x][0];\n";
+            s += "        for (int k = 1; k < 8; ++k) v = word_combine(op, v, s_wpart[threadIdx.x][k]);\n";
+            s += "        if (v != word_identity(op)) atomic_word_dyn(op, &p.acc[threadIdx.x], v);\n";
+            s += "    }\n";
+        } else {
+            s += "    __syncthreads();\n";
+            s += "    for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) {\n";
+            s += "        const int op = nq_ops[i / NQ_G];\n";
+            s += "        const u64 v = s_tab[i];\n";
+            s += "        if (v != word_identity(op)) atomic_word_dyn(op, &p.acc[i], v);\n";
+            s += "    }\n";
+        }
         s += "    if (last_block_arrives(p.ticket)) {\n";
         s += "        for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) p.final_host[i] = __ldcg(&p.acc[i]);\n";
         s += "        if (p.peer_mail) mailbox_push(p, p.acc);\n";

@@ -46,6 +46,8 @@ struct KernelPlan {
     std::vector<PackComp> keys;
     int key_bits = 0;
     i64 dense_slots = 0;
+    bool dense_priv = false;     // tiny dense table: one private copy per THREAD in shared memory (no atomics at all)
+    int dyn_smem = 0;            // dynamic shared memory the kernel is launched with
     std::vector<AggPlan> aggs;
     int ndistinct = 0, abits = 0, entry_bits = 0;
     bool set128 = false;

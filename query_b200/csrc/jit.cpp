@@ -30,6 +30,7 @@ struct Driver {
     decltype(&cuModuleGetFunction) ModuleGetFunction = nullptr;
     decltype(&cuLaunchKernel) LaunchKernel = nullptr;
     decltype(&cuFuncGetAttribute) FuncGetAttribute = nullptr;
+    decltype(&cuFuncSetAttribute) FuncSetAttribute = nullptr;
     decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) Occupancy = nullptr;
     decltype(&cuGetErrorString) GetErrorString = nullptr;
     bool ready = false;
@@ -55,6 +56,7 @@ Driver& driver() {
         resolve(g_drv.ModuleGetFunction, "cuModuleGetFunction");
         resolve(g_drv.LaunchKernel, "cuLaunchKernel");
         resolve(g_drv.FuncGetAttribute, "cuFuncGetAttribute");
+        resolve(g_drv.FuncSetAttribute, "cuFuncSetAttribute");
         resolve(g_drv.Occupancy, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
         resolve(g_drv.GetErrorString, "cuGetErrorString");
         g_drv.ready = true;
@@ -173,7 +175,7 @@ std::string jit_compile_cubin(const std::string& source, std::string* log) {
     return cubin;
 }
 
-std::shared_ptr<JitKernel> jit_load(const std::string& source) {
+std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem) {
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_cache.find(source);
@@ -191,7 +193,10 @@ std::shared_ptr<JitKernel> jit_load(const std::string& source) {
     k->function = fn;
     cu_check(d.FuncGetAttribute(&k->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn), "cuFuncGetAttribute");
     cu_check(d.FuncGetAttribute(&k->static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, fn), "cuFuncGetAttribute");
-    cu_check(d.Occupancy(&k->max_blocks_per_sm, fn, 256, 0), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    k->dyn_smem = dyn_smem;
+    if (dyn_smem > 48 * 1024)
+        cu_check(d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, dyn_smem), "cuFuncSetAttribute(max dynamic shared memory)");
+    cu_check(d.Occupancy(&k->max_blocks_per_sm, fn, 256, (size_t)dyn_smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     if (k->max_blocks_per_sm < 1) k->max_blocks_per_sm = 1;
     std::lock_guard<std::mutex> lk(g_mu);
     g_cache[source] = k;
@@ -200,7 +205,7 @@ std::shared_ptr<JitKernel> jit_load(const std::string& source) {
 
 void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t) {
     void* args[] = {params};
-    cu_check(driver().LaunchKernel((CUfunction)k.function, (unsigned)grid, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr), "cuLaunchKernel(nq_scan)");
+    cu_check(driver().LaunchKernel((CUfunction)k.function, (unsigned)grid, 1, 1, 256, 1, 1, (unsigned)k.dyn_smem, (CUstream)stream, args, nullptr), "cuLaunchKernel(nq_scan)");
     g_launches.fetch_add(1);
 }
 

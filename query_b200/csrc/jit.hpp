@@ -14,6 +14,7 @@ struct JitKernel {
     void* function = nullptr;  // CUfunction
     int regs = 0;
     int static_smem = 0;
+    int dyn_smem = 0;
     int max_blocks_per_sm = 0;  // occupancy at 256 threads
     std::string cubin;
     ~JitKernel();
@@ -22,7 +23,7 @@ struct JitKernel {
 // Compiles `source` (which #includes "n1ql_device.cuh") to an sm_100a cubin.  Works without a GPU.
 std::string jit_compile_cubin(const std::string& source, std::string* log);
 // Compiles (cached per process by source text) and loads the kernel `nq_scan` on the current device.
-std::shared_ptr<JitKernel> jit_load(const std::string& source);
+std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem = 0);
 // Launches nq_scan<<<grid, 256, 0, stream>>>(params) where params is a by-value struct of `bytes` bytes.
 void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t bytes);
 

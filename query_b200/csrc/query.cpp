@@ -80,7 +80,7 @@ std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const 
     q->ops.n = (int)q->kp.word_ops.size();
     for (int w = 0; w < q->ops.n; ++w) q->ops.op[w] = q->kp.word_ops[w];
     if (have_device()) {
-        q->kernel = jit_load(q->kp.source);
+        q->kernel = jit_load(q->kp.source, q->kp.dyn_smem);
         CK(cudaStreamCreateWithFlags(&q->own_stream, cudaStreamNonBlocking));
         q->stream = q->own_stream;
         CK(cudaEventCreate(&q->ev0));
