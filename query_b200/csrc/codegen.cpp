@@ -351,7 +351,17 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         const char* np = getenv("N1GPU_NO_PRIV");
         if (kp.dense_slots * W <= 48 && !(np && *np == '1')) { kp.dense_priv = true; kp.dyn_smem = (int)(kp.dense_slots * W * 256 * 8); }
     }
-    else if (kp.key_bits <= 63) kp.mode = MODE_HASH64;
+    else if (kp.key_bits <= 63) {
+        kp.mode = MODE_HASH64;
+        // shared-memory front cache for hot keys (Zipf-skewed GROUP BY): as many slots as fit ~56 KiB
+        const char* nc = getenv("N1GPU_NO_CACHE");
+        if (!(nc && *nc == '1')) {
+            int cs = 2048;
+            while (cs > 64 && (i64)cs * (1 + W) * 8 > 56 * 1024) cs >>= 1;
+            kp.cache_slots = cs;
+            kp.dyn_smem = cs * (1 + W) * 8;
+        }
+    }
     else if (kp.key_bits <= 127) kp.mode = MODE_HASH128;
     else N1_THROW(N1GPU_E_INELIGIBLE, "group key needs %d bits (> 127) after packing", kp.key_bits);
     kp.est_groups = (i64)std::min(est, 4e18);
@@ -391,6 +401,12 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             emit_pack(g, kp.keys[k], kv, "klo", "khi", "kpos");
         }
         if (kp.mode == MODE_DENSE) g.line("const i64 slot = (i64)klo;");
+        else if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+            g.line("++nlook;");
+            g.line("const int cslot = cache_on ? cache_claim(s_ckey, NQ_CS - 1, klo) : -1;");
+            g.line("nhit += cslot >= 0;");
+            g.line("const i64 slot = cslot >= 0 ? 0 : table_insert64(p.keys, p.cap_mask, klo, nullptr);");
+        }
         else if (kp.mode == MODE_HASH64) g.line("const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);");
         else g.line("const i64 slot = table_insert128((ulonglong2*)p.keys, p.cap_mask, klo, khi, nullptr);");
         if (kp.mode != MODE_DENSE) g.line("if (slot < 0) { p.status[0] = 1; continue; }");
@@ -498,6 +514,11 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     else if (kp.mode == MODE_DENSE && kp.dense_priv)
         s += "#define ACC(k, OP, val_) { u64* c_ = &s_priv[(((k) * NQ_G + slot) << 8) + threadIdx.x]; *c_ = word_combine(OP, *c_, (u64)(val_)); }\n";
     else if (kp.mode == MODE_DENSE) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
+    else if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+        s += strf("#define NQ_CS %d\n", kp.cache_slots);
+        s += "#define ACC(k, OP, val_) { if (cslot >= 0) atomic_word<OP>(&s_cacc[(k) * NQ_CS + cslot], (u64)(val_)); "
+             "else atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(val_)); }\n";
+    }
     else s += "#define ACC(k, OP, x) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
     {
         // resident blocks per SM the register allocator must allow (tuning knob N1GPU_MIN_BLOCKS; 0 = compiler's choice)
@@ -518,6 +539,16 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "    __syncthreads();\n";
     } else {
         s += "    const u64 cap = p.cap_mask + 1;\n";
+        if (kp.cache_slots) {
+            s += "    extern __shared__ u64 s_dyn[];\n";
+            s += "    u64* const s_ckey = s_dyn;            // [NQ_CS] cached group keys (all ones = empty)\n";
+            s += "    u64* const s_cacc = s_dyn + NQ_CS;    // [NQ_W][NQ_CS] their accumulator words\n";
+            s += "    for (int i = threadIdx.x; i < NQ_CS; i += 256) s_ckey[i] = NQ_U64_MAX;\n";
+            s += "    for (int i = threadIdx.x; i < NQ_W * NQ_CS; i += 256) s_cacc[i] = word_identity(nq_ops[i / NQ_CS]);\n";
+            s += "    __syncthreads();\n";
+            s += "    bool cache_on = true;  // per warp: switched off after 16 tiles when fewer than 1 in 4 rows hit\n";
+            s += "    unsigned nlook = 0, nhit = 0; int tiles = 0;\n";
+        }
     }
     s += "    const i64 nrows = p.nrows;\n";
     s += "    const int lane = threadIdx.x & 31;\n";
@@ -546,7 +577,28 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     s += agg_code;
     s += "            }\n";
     s += "        }\n";
+    if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+        s += "        if (cache_on && ++tiles == 16) {  // warp-uniform: is the front cache earning its probes?\n";
+        s += "            const unsigned L = __reduce_add_sync(0xffffffffu, nlook), H = __reduce_add_sync(0xffffffffu, nhit);\n";
+        s += "            if (H * 4 < L) cache_on = false;\n";
+        s += "        }\n";
+    }
     s += "    }\n";
+    if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+        // flush the block's cached groups into the HBM table: one insert + one atomic per word per cached key
+        s += "    __syncthreads();\n";
+        s += "    for (int i = threadIdx.x; i < NQ_CS; i += 256) {\n";
+        s += "        const u64 key = s_ckey[i];\n";
+        s += "        if (key == NQ_U64_MAX) continue;\n";
+        s += "        const i64 slot = table_insert64(p.keys, p.cap_mask, key, nullptr);\n";
+        s += "        if (slot < 0) { p.status[0] = 1; continue; }\n";
+        s += "#pragma unroll\n";
+        s += "        for (int w = 0; w < NQ_W; ++w) {\n";
+        s += "            const u64 v = s_cacc[w * NQ_CS + i];\n";
+        s += "            if (v != word_identity(nq_ops[w])) atomic_word_dyn(nq_ops[w], &p.acc[(u64)w * cap + (u64)slot], v);\n";
+        s += "        }\n";
+        s += "    }\n";
+    }
     if (kp.mode == MODE_UNGROUPED) {
         // Block epilogue: warp-shuffle reduce every word, one barrier, then thread w folds word w's 8 warp values in
         // order.  Order-independent words (integer add / min / max / or) go straight into persistent accumulators

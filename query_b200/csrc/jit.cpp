@@ -194,7 +194,7 @@ std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem) {
     cu_check(d.FuncGetAttribute(&k->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn), "cuFuncGetAttribute");
     cu_check(d.FuncGetAttribute(&k->static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, fn), "cuFuncGetAttribute");
     k->dyn_smem = dyn_smem;
-    if (dyn_smem > 48 * 1024)
+    if (dyn_smem > 0)  // static + dynamic may cross the 48 KiB default even when the dynamic part alone does not
         cu_check(d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, dyn_smem), "cuFuncSetAttribute(max dynamic shared memory)");
     cu_check(d.Occupancy(&k->max_blocks_per_sm, fn, 256, (size_t)dyn_smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     if (k->max_blocks_per_sm < 1) k->max_blocks_per_sm = 1;
