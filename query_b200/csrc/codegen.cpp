@@ -296,8 +296,20 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         ap.opmask = opnd ? opnd->ti.mask : 0;
         if (opnd && (ap.opmask & bit(C_STRING)) && opnd->ti.plain_col) ap.dict_col = opnd->ti.dict_col;
         if (ap.distinct) {
+            // result words, filled at finalisation by k_distinct_finalize from the set entries (never during the scan)
             ap.distinct_id = kp.ndistinct++;
+            if (kp.ndistinct > 16) N1_THROW(N1GPU_E_INELIGIBLE, "more than 16 DISTINCT aggregates");
             ap.dcomp = make_comp(t, *opnd, "DISTINCT");
+            const std::string dk = strf("d%d:", ap.distinct_id);
+            ap.w_cnt = add_word(OP_ADD_U64, dk + "cnt");
+            if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
+                if (ap.dcomp.mask & bit(C_INT)) {
+                    ap.w_ilo = add_word(OP_ADD_U64, dk + "ilo");
+                    ap.w_ihi = add_word(OP_ADD_U64, dk + "ihi");
+                    ap.w_neg = add_word(OP_ADD_U64, dk + "neg");
+                }
+                if (ap.dcomp.mask & bit(C_FLOAT)) { ap.w_fsum = add_word(OP_ADD_F64, dk + "fsum"); ap.w_nflt = add_word(OP_ADD_U64, dk + "nflt"); }
+            }
         } else if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) {
             const std::string ot = opnd ? opnd->str() : std::string("*");
             const u32 counted = ap.kind == AggKind::COUNT ? ~(bit(C_MISSING) | bit(C_NULL)) : M_NUM;
@@ -353,11 +365,11 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     }
     else if (kp.key_bits <= 63) {
         kp.mode = MODE_HASH64;
-        // shared-memory front cache for hot keys (Zipf-skewed GROUP BY): as many slots as fit ~56 KiB
+        // shared-memory front cache for hot keys (Zipf-skewed GROUP BY): as many slots as fit 32 KiB
         const char* nc = getenv("N1GPU_NO_CACHE");
         if (!(nc && *nc == '1')) {
             int cs = 2048;
-            while (cs > 64 && (i64)cs * (1 + W) * 8 > 56 * 1024) cs >>= 1;
+            while (cs > 64 && (i64)cs * (1 + W) * 8 > 32 * 1024) cs >>= 1;  // <= 32 KiB: keeps 6 blocks per SM resident
             kp.cache_slots = cs;
             kp.dyn_smem = cs * (1 + W) * 8;
         }
@@ -546,7 +558,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += "    for (int i = threadIdx.x; i < NQ_CS; i += 256) s_ckey[i] = NQ_U64_MAX;\n";
             s += "    for (int i = threadIdx.x; i < NQ_W * NQ_CS; i += 256) s_cacc[i] = word_identity(nq_ops[i / NQ_CS]);\n";
             s += "    __syncthreads();\n";
-            s += "    bool cache_on = true;  // per warp: switched off after 16 tiles when fewer than 1 in 4 rows hit\n";
+            s += "    bool cache_on = true;  // per warp: switched off after 4 tiles when fewer than 1 in 4 rows hit\n";
             s += "    unsigned nlook = 0, nhit = 0; int tiles = 0;\n";
         }
     }
@@ -578,7 +590,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     s += "            }\n";
     s += "        }\n";
     if (kp.mode == MODE_HASH64 && kp.cache_slots) {
-        s += "        if (cache_on && ++tiles == 16) {  // warp-uniform: is the front cache earning its probes?\n";
+        s += "        if (cache_on && ++tiles == 4) {  // warp-uniform: is the front cache earning its probes?\n";
         s += "            const unsigned L = __reduce_add_sync(0xffffffffu, nlook), H = __reduce_add_sync(0xffffffffu, nhit);\n";
         s += "            if (H * 4 < L) cache_on = false;\n";
         s += "        }\n";

@@ -105,6 +105,50 @@ __global__ void k_merge_records(int kw, u64* keys, u64* acc, u64 cap, OpsArr ops
     }
 }
 
+// DISTINCT finalisation (ComputeFinal of count/countn/sum/avg DISTINCT: algebra/agg_*_distinct.go): every entry of the
+// (aggregate, group, value) set adds 1 to its group's distinct count and, for SUM/AVG, its value to the group's exact
+// split integer sum / float sum.  kw: how the group slot is found (3 ungrouped, 0 dense, 1 / 2 hash 64 / 128).
+__device__ __forceinline__ u64 take_bits(unsigned __int128& v, int n) {
+    if (n == 0) return 0;
+    const u64 r = n >= 64 ? (u64)v : ((u64)v & ((1ULL << n) - 1));
+    v >>= n;
+    return r;
+}
+__global__ void k_distinct_finalize(const u64* __restrict__ set_keys, u64 set_cap, int set128, int abits, int key_bits, int kw,
+                                    const u64* __restrict__ keys, u64 cap, u64* acc, DistinctDescs D) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < set_cap; i += (u64)gridDim.x * blockDim.x) {
+        u64 lo, hi;
+        if (set128) { lo = set_keys[2 * i]; hi = set_keys[2 * i + 1]; if (lo == NQ_U64_MAX && hi == NQ_U64_MAX) continue; }
+        else { lo = set_keys[i]; hi = 0; if (lo == NQ_U64_MAX) continue; }
+        unsigned __int128 v = ((unsigned __int128)hi << 64) | lo;
+        const int aid = (int)take_bits(v, abits);
+        if (aid >= D.n) continue;
+        const u64 klo = take_bits(v, key_bits < 64 ? key_bits : 64);
+        const u64 khi = key_bits > 64 ? take_bits(v, key_bits - 64) : 0;
+        i64 slot;
+        if (kw == 3) slot = 0;
+        else if (kw == 0) slot = (i64)klo;
+        else if (kw == 1) slot = table_find64(keys, cap - 1, klo);
+        else slot = table_find128((const ulonglong2*)keys, cap - 1, klo, khi);
+        if (slot < 0 || (u64)slot >= cap) continue;  // group owned by another rank
+        const DistinctDesc& d = D.d[aid];
+        atomicAdd(&acc[(u64)d.w_cnt * cap + (u64)slot], 1ULL);
+        if (d.w_ilo < 0 && d.w_fsum < 0) continue;
+        const int ci = (int)take_bits(v, d.cbits);
+        const u64 pv = take_bits(v, d.pbits);
+        const int cls = ci < 8 ? d.classes[ci] : C_MISSING;
+        if (cls == C_INT && d.w_ilo >= 0) {
+            const i64 x = d.biased ? (i64)(pv + (u64)d.bias) : (i64)pv;
+            atomicAdd(&acc[(u64)d.w_ilo * cap + (u64)slot], (u64)x & 0xffffffffULL);
+            atomicAdd(&acc[(u64)d.w_ihi * cap + (u64)slot], (u64)(x >> 32));
+            if (x < 0) atomicAdd(&acc[(u64)d.w_neg * cap + (u64)slot], 1ULL);
+        } else if (cls == C_FLOAT && d.w_fsum >= 0) {
+            atomicAdd((double*)&acc[(u64)d.w_fsum * cap + (u64)slot], __longlong_as_double((i64)pv));
+            atomicAdd(&acc[(u64)d.w_nflt * cap + (u64)slot], 1ULL);
+        }
+    }
+}
+
 // Small-state IntermediateGroup merge: all[r][w][slot] (the accumulator words of every rank, gathered by one
 // all_gather) folded over ranks in rank order (deterministic) into out_dev / out_host (zero-copy result).
 __global__ void k_merge_words(const u64* __restrict__ all, int nranks, u64 cap, OpsArr ops, u64* out_dev, u64* out_host) {
@@ -155,6 +199,12 @@ static int grid_for(u64 n) {
     return (int)g;
 }
 
+void launch_distinct_finalize(const u64* set_keys, u64 set_cap, int set128, int abits, int key_bits, int kw, const u64* keys, u64 cap,
+                              u64* acc, const DistinctDescs& D, cudaStream_t s) {
+    k_distinct_finalize<<<grid_for(set_cap), 256, 0, s>>>(set_keys, set_cap, set128, abits, key_bits, kw, keys, cap, acc, D);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
 void launch_merge_mailbox(const u64* mail, int nranks, u64 slot_base, u64 stride, u64 words, u64 seq, u64 cap, const OpsArr& ops,
                           u64* out_dev, u64* out_host, int* status, cudaStream_t s) {
     k_merge_mailbox<<<1, 256, 0, s>>>(mail, nranks, slot_base, stride, words, seq, cap, ops, out_dev, out_host, status);

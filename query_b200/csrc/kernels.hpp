@@ -9,6 +9,19 @@ struct OpsArr {
     int op[64];
 };
 
+// one DISTINCT aggregate: where its result words live and how its value component is packed in a set entry
+struct DistinctDesc {
+    int w_cnt, w_ilo, w_ihi, w_neg, w_fsum, w_nflt;  // word indices (-1 = not needed)
+    int cbits, pbits, biased;
+    i64 bias;
+    int classes[8];
+};
+struct DistinctDescs {
+    int n;
+    DistinctDesc d[16];
+};
+void launch_distinct_finalize(const u64* set_keys, u64 set_cap, int set128, int abits, int key_bits, int kw, const u64* keys, u64 cap,
+                              u64* acc, const DistinctDescs& D, cudaStream_t s);
 void launch_merge_mailbox(const u64* mail, int nranks, u64 slot_base, u64 stride, u64 words, u64 seq, u64 cap, const OpsArr& ops,
                           u64* out_dev, u64* out_host, int* status, cudaStream_t s);
 void launch_merge_words(const u64* all, int nranks, u64 cap, const OpsArr& ops, u64* out_dev, u64* out_host, cudaStream_t s);

@@ -377,8 +377,25 @@ std::unique_ptr<Result> Query::finalize() {
     const int rw = 2 + W;
     std::vector<u64> recs;
     i64 ngroups = 0;
-    if ((kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) && h_records.p && !import_dirty()) {
-        // small state: the scan already copied the table words to pinned host memory
+    if (kp.ndistinct) {
+        // DISTINCT aggregates are finalised on the device: every set entry adds itself to its group's result words
+        DistinctDescs D{};
+        D.n = kp.ndistinct;
+        for (auto& ap : kp.aggs) {
+            if (!ap.distinct) continue;
+            DistinctDesc& d = D.d[ap.distinct_id];
+            d.w_cnt = ap.w_cnt; d.w_ilo = ap.w_ilo; d.w_ihi = ap.w_ihi; d.w_neg = ap.w_neg; d.w_fsum = ap.w_fsum; d.w_nflt = ap.w_nflt;
+            d.cbits = ap.dcomp.cbits; d.pbits = ap.dcomp.pbits; d.biased = ap.dcomp.biased; d.bias = ap.dcomp.bias;
+            for (int k = 0; k < 8; ++k) d.classes[k] = k < (int)ap.dcomp.classes.size() ? ap.dcomp.classes[k] : C_MISSING;
+            for (int w : {ap.w_cnt, ap.w_ilo, ap.w_ihi, ap.w_neg, ap.w_fsum, ap.w_nflt})
+                if (w >= 0) launch_fill_u64(d_acc.as<u64>() + (u64)w * cap, cap, 0, stream);  // idempotent finalize
+        }
+        launch_distinct_finalize(d_set.as<u64>(), set_cap, kp.set128 ? 1 : 0, kp.abits, kp.key_bits, kw(), d_keys.as<u64>(), cap,
+                                 d_acc.as<u64>(), D, stream);
+        CK(cudaStreamSynchronize(stream));
+    }
+    if ((kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) && h_records.p && !import_dirty() && !kp.ndistinct) {
+        // small state: the scan already published the table words to pinned host memory
         const u64* h = h_records.as<u64>();
         for (u64 i = 0; i < cap; ++i) {
             if (kp.mode == MODE_DENSE && h[i] == 0) continue;  // word 0 = rows in group
@@ -400,20 +417,6 @@ std::unique_ptr<Result> Query::finalize() {
             CK(cudaMemcpy(recs.data(), d_records.p, recs.size() * 8, cudaMemcpyDeviceToHost));
         }
     }
-    // DISTINCT entries
-    std::vector<u64> ents;
-    if (kp.ndistinct) {
-        i64 d[1];
-        int skw = kp.set128 ? 2 : 1;
-        count_and_export(*this, skw, d_set.as<u64>(), nullptr, set_cap, 0, 1, kp.abits, kp.key_bits, nullptr, 0, d);
-        if (d[0]) {
-            d_drecords.ensure((size_t)d[0] * 16);
-            i64 d2[1];
-            count_and_export(*this, skw, d_set.as<u64>(), nullptr, set_cap, 0, 1, kp.abits, kp.key_bits, d_drecords.as<u64>(), d[0], d2);
-            ents.resize((size_t)d[0] * 2);
-            CK(cudaMemcpy(ents.data(), d_drecords.p, ents.size() * 8, cudaMemcpyDeviceToHost));
-        }
-    }
 
     std::unique_ptr<Result> res(new Result());
     res->nkeys = (int)keys.size();
@@ -430,31 +433,6 @@ std::unique_ptr<Result> Query::finalize() {
     res->keys.resize((size_t)ngroups * res->nkeys);
     res->aggs.resize((size_t)ngroups * res->naggs);
 
-    // group index by packed key, for DISTINCT entries
-    std::unordered_map<std::pair<u64, u64>, i64, KeyHash> index;
-    std::vector<DistinctAcc> dacc;
-    if (kp.ndistinct) {
-        index.reserve((size_t)ngroups * 2);
-        for (i64 g = 0; g < ngroups; ++g) index.emplace(std::make_pair(recs[(size_t)g * rw], recs[(size_t)g * rw + 1]), g);
-        dacc.resize((size_t)ngroups * kp.ndistinct);
-        std::vector<const AggPlan*> by_id((size_t)kp.ndistinct, nullptr);
-        for (auto& ap : kp.aggs) if (ap.distinct) by_id[(size_t)ap.distinct_id] = &ap;
-        for (size_t e = 0; e + 1 < ents.size(); e += 2) {
-            BitReader br(ents[e], ents[e + 1]);
-            u64 aid = br.take(kp.abits);
-            u64 klo = br.take(std::min(64, kp.key_bits));
-            u64 khi = kp.key_bits > 64 ? br.take(kp.key_bits - 64) : 0;
-            if (aid >= (u64)kp.ndistinct) continue;
-            auto it = index.find(std::make_pair(klo, khi));
-            if (it == index.end()) continue;  // entry of a group this rank does not own
-            HValue v = decode_comp(*table, by_id[aid]->dcomp, br);
-            DistinctAcc& da = dacc[(size_t)it->second * kp.ndistinct + aid];
-            da.count++;
-            if (v.cls == C_INT) { da.sum.itotal += v.bits; if (v.bits >= 0) da.sum.n_nonneg++; else da.sum.n_neg++; }
-            else if (v.cls == C_FLOAT) { da.sum.fsum += v.f(); da.sum.n_flt++; }
-        }
-    }
-
     for (i64 g = 0; g < ngroups; ++g) {
         const u64* r = &recs[(size_t)g * rw];
         const u64* w = r + 2;
@@ -464,13 +442,19 @@ std::unique_ptr<Result> Query::finalize() {
             const AggPlan& ap = kp.aggs[a];
             HValue out;
             if (ap.distinct) {
-                const DistinctAcc& da = dacc[(size_t)g * kp.ndistinct + ap.distinct_id];
-                if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) out = HValue::integer((i64)da.count);
-                else if (da.count == 0) out = HValue::null();
+                const u64 count = w[ap.w_cnt];
+                if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) out = HValue::integer((i64)count);
+                else if (count == 0) out = HValue::null();
                 else {
-                    HValue s = sum_value(da.sum, true);
-                    if (ap.kind == AggKind::SUM) out = s;
-                    else out = new_num(s.num() / (double)da.count);
+                    SumState s;  // entries of SUM/AVG DISTINCT are numbers only
+                    if (ap.w_ilo >= 0) s.itotal = (((__int128)(i64)w[ap.w_ihi]) << 32) + (__int128)w[ap.w_ilo];
+                    if (ap.w_neg >= 0) s.n_neg = w[ap.w_neg];
+                    if (ap.w_nflt >= 0) s.n_flt = w[ap.w_nflt];
+                    if (ap.w_fsum >= 0) memcpy(&s.fsum, &w[ap.w_fsum], 8);
+                    s.n_nonneg = count - s.n_neg - s.n_flt;
+                    HValue sv = sum_value(s, true);
+                    if (ap.kind == AggKind::SUM) out = sv;
+                    else out = new_num(sv.num() / (double)count);
                 }
             } else if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) {
                 out = HValue::integer((i64)w[ap.w_cnt]);
