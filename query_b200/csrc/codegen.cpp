@@ -281,6 +281,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         shared[key] = (int)kp.word_ops.size() - 1;
         return (int)kp.word_ops.size() - 1;
     };
+    std::map<std::string, int> dset_of;  // DISTINCT operand text -> entry-set id
+    std::vector<bool> dset_any;          // set id -> holds every value > NULL (else numbers only)
+    int ndistinct_aggs = 0;
     int w_rows = -1;
     if (!keys.empty()) w_rows = add_word(OP_ADD_U64, "rows");  // word 0: rows per group (group existence)
     auto rows_word = [&]() { if (w_rows < 0) w_rows = add_word(OP_ADD_U64, "rows"); return w_rows; };
@@ -297,10 +300,15 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         if (opnd && (ap.opmask & bit(C_STRING)) && opnd->ti.plain_col) ap.dict_col = opnd->ti.dict_col;
         if (ap.distinct) {
             // result words, filled at finalisation by k_distinct_finalize from the set entries (never during the scan)
-            ap.distinct_id = kp.ndistinct++;
-            if (kp.ndistinct > 16) N1_THROW(N1GPU_E_INELIGIBLE, "more than 16 DISTINCT aggregates");
+            // DISTINCT aggregates over the same operand share one entry set: COUNT(DISTINCT x) and SUM(DISTINCT x)
+            // insert x once; the set holds every non-NULL value when one of them is a COUNT, numbers only otherwise
+            const std::string ot = opnd->str();
+            if (!dset_of.count(ot)) { dset_of[ot] = kp.ndistinct++; dset_any.push_back(false); }
+            ap.distinct_id = dset_of[ot];
+            if (ap.kind == AggKind::COUNT) dset_any[ap.distinct_id] = true;
+            if (++ndistinct_aggs > 16) N1_THROW(N1GPU_E_INELIGIBLE, "more than 16 DISTINCT aggregates");
             ap.dcomp = make_comp(t, *opnd, "DISTINCT");
-            const std::string dk = strf("d%d:", ap.distinct_id);
+            const std::string dk = strf("d%d:", ndistinct_aggs);
             ap.w_cnt = add_word(OP_ADD_U64, dk + "cnt");
             if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
                 if (ap.dcomp.mask & bit(C_INT)) {
@@ -423,6 +431,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         else g.line("const i64 slot = table_insert128((ulonglong2*)p.keys, p.cap_mask, klo, khi, nullptr);");
         if (kp.mode != MODE_DENSE) g.line("if (slot < 0) { p.status[0] = 1; continue; }");
     }
+    std::set<int> emitted_sets;
     std::set<int> emitted;  // a shared word is updated once per row, by the first aggregate that owns it
     if (w_rows >= 0) { g.line(strf("ACC(%d, OP_ADD_U64, 1);  // rows", w_rows)); emitted.insert(w_rows); }
     for (size_t a = 0; a < kp.aggs.size(); ++a) {
@@ -441,8 +450,10 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             if (!emitted.insert(w).second) return;
             g.line(strf("if (%s) { ACC(%d, %s, %s); }", cond.c_str(), w, op_name(op), x.c_str()));
         };
-        if (ap.distinct) {
-            std::string cond = (ap.kind == AggKind::COUNT) ? strf("%s.c > C_NULL", o.c_str()) : strf("is_num(%s.c)", o.c_str());
+        if (ap.distinct && !emitted_sets.insert(ap.distinct_id).second) {
+            // the entry set of this operand is already fed by an earlier aggregate
+        } else if (ap.distinct) {
+            std::string cond = dset_any[ap.distinct_id] ? strf("%s.c > C_NULL", o.c_str()) : strf("is_num(%s.c)", o.c_str());
             g.line(strf("if (%s) {", cond.c_str()));
             g.ind += "    ";
             std::string cv = o;

@@ -121,8 +121,7 @@ __global__ void k_distinct_finalize(const u64* __restrict__ set_keys, u64 set_ca
         if (set128) { lo = set_keys[2 * i]; hi = set_keys[2 * i + 1]; if (lo == NQ_U64_MAX && hi == NQ_U64_MAX) continue; }
         else { lo = set_keys[i]; hi = 0; if (lo == NQ_U64_MAX) continue; }
         unsigned __int128 v = ((unsigned __int128)hi << 64) | lo;
-        const int aid = (int)take_bits(v, abits);
-        if (aid >= D.n) continue;
+        const int sid = (int)take_bits(v, abits);
         const u64 klo = take_bits(v, key_bits < 64 ? key_bits : 64);
         const u64 khi = key_bits > 64 ? take_bits(v, key_bits - 64) : 0;
         i64 slot;
@@ -131,20 +130,29 @@ __global__ void k_distinct_finalize(const u64* __restrict__ set_keys, u64 set_ca
         else if (kw == 1) slot = table_find64(keys, cap - 1, klo);
         else slot = table_find128((const ulonglong2*)keys, cap - 1, klo, khi);
         if (slot < 0 || (u64)slot >= cap) continue;  // group owned by another rank
-        const DistinctDesc& d = D.d[aid];
-        atomicAdd(&acc[(u64)d.w_cnt * cap + (u64)slot], 1ULL);
-        if (d.w_ilo < 0 && d.w_fsum < 0) continue;
-        const int ci = (int)take_bits(v, d.cbits);
-        const u64 pv = take_bits(v, d.pbits);
-        const int cls = ci < 8 ? d.classes[ci] : C_MISSING;
-        if (cls == C_INT && d.w_ilo >= 0) {
-            const i64 x = d.biased ? (i64)(pv + (u64)d.bias) : (i64)pv;
-            atomicAdd(&acc[(u64)d.w_ilo * cap + (u64)slot], (u64)x & 0xffffffffULL);
-            atomicAdd(&acc[(u64)d.w_ihi * cap + (u64)slot], (u64)(x >> 32));
-            if (x < 0) atomicAdd(&acc[(u64)d.w_neg * cap + (u64)slot], 1ULL);
-        } else if (cls == C_FLOAT && d.w_fsum >= 0) {
-            atomicAdd((double*)&acc[(u64)d.w_fsum * cap + (u64)slot], __longlong_as_double((i64)pv));
-            atomicAdd(&acc[(u64)d.w_nflt * cap + (u64)slot], 1ULL);
+        bool decoded = false;
+        int cls = C_MISSING;
+        u64 pv = 0;
+        for (int a = 0; a < D.n; ++a) {
+            const DistinctDesc& d = D.d[a];
+            if (d.sid != sid) continue;
+            if (!decoded) {  // the value component is packed identically for every aggregate of the set
+                const int ci = (int)take_bits(v, d.cbits);
+                pv = take_bits(v, d.pbits);
+                cls = ci < 8 ? d.classes[ci] : C_MISSING;
+                decoded = true;
+            }
+            if (d.numbers_only && !(cls == C_INT || cls == C_FLOAT)) continue;
+            atomicAdd(&acc[(u64)d.w_cnt * cap + (u64)slot], 1ULL);
+            if (cls == C_INT && d.w_ilo >= 0) {
+                const i64 x = d.biased ? (i64)(pv + (u64)d.bias) : (i64)pv;
+                atomicAdd(&acc[(u64)d.w_ilo * cap + (u64)slot], (u64)x & 0xffffffffULL);
+                atomicAdd(&acc[(u64)d.w_ihi * cap + (u64)slot], (u64)(x >> 32));
+                if (x < 0) atomicAdd(&acc[(u64)d.w_neg * cap + (u64)slot], 1ULL);
+            } else if (cls == C_FLOAT && d.w_fsum >= 0) {
+                atomicAdd((double*)&acc[(u64)d.w_fsum * cap + (u64)slot], __longlong_as_double((i64)pv));
+                atomicAdd(&acc[(u64)d.w_nflt * cap + (u64)slot], 1ULL);
+            }
         }
     }
 }

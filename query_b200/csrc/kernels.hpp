@@ -11,6 +11,8 @@ struct OpsArr {
 
 // one DISTINCT aggregate: where its result words live and how its value component is packed in a set entry
 struct DistinctDesc {
+    int sid;           // entry set this aggregate reads (aggregates over the same operand share one)
+    int numbers_only;  // COUNTN / SUM / AVG DISTINCT: only numeric entries count (COUNT: every entry)
     int w_cnt, w_ilo, w_ihi, w_neg, w_fsum, w_nflt;  // word indices (-1 = not needed)
     int cbits, pbits, biased;
     i64 bias;

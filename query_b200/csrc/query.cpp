@@ -132,7 +132,7 @@ void Query::alloc_state() {
     if (kp.ndistinct) {
         if (set_cap == 0) {
             double want = 2.0 * (double)std::max<i64>(table->nrows, 1) * kp.ndistinct;
-            set_cap = pow2_at_least((u64)std::min(std::max(want, 1024.0), 33554432.0));
+            set_cap = pow2_at_least((u64)std::min(std::max(want, 1024.0), 268435456.0));
         }
         d_set.ensure((size_t)set_cap * (kp.set128 ? 16 : 8));
     }
@@ -380,10 +380,12 @@ std::unique_ptr<Result> Query::finalize() {
     if (kp.ndistinct) {
         // DISTINCT aggregates are finalised on the device: every set entry adds itself to its group's result words
         DistinctDescs D{};
-        D.n = kp.ndistinct;
+        D.n = 0;
         for (auto& ap : kp.aggs) {
             if (!ap.distinct) continue;
-            DistinctDesc& d = D.d[ap.distinct_id];
+            DistinctDesc& d = D.d[D.n++];
+            d.sid = ap.distinct_id;
+            d.numbers_only = ap.kind != AggKind::COUNT;
             d.w_cnt = ap.w_cnt; d.w_ilo = ap.w_ilo; d.w_ihi = ap.w_ihi; d.w_neg = ap.w_neg; d.w_fsum = ap.w_fsum; d.w_nflt = ap.w_nflt;
             d.cbits = ap.dcomp.cbits; d.pbits = ap.dcomp.pbits; d.biased = ap.dcomp.biased; d.bias = ap.dcomp.bias;
             for (int k = 0; k < 8; ++k) d.classes[k] = k < (int)ap.dcomp.classes.size() ? ap.dcomp.classes[k] : C_MISSING;
