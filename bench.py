@@ -147,6 +147,7 @@ def run_ours(args):
     for i in range(NQ):
         qq = q.Query(tables[i % NT], ALIAS, WHERE, KEYS, AGGS)
         qq.set_stream(side[i % NS].cuda_stream)
+        qq.set_timing(False)  # the timed region is bracketed by our own events; per-launch events only cost front-end time
         queries.append(qq)
     # N > 1: the Intermediate->Final merge is fused into the scan kernel (peer stores over NVLink into every rank's
     # mailbox + a 1-block fold); --merge nccl switches to the NCCL all_gather of the accumulator words instead
@@ -223,16 +224,44 @@ def run_ours(args):
     # the dominant kernel alone: serialised steps on one stream, CUDA events around the nq_scan launch itself
     # (launches are queued NQ deep on ONE stream so that the events bracket the kernel, not the launch latency
     # of an idle queue; the kernels themselves run strictly one after another)
-    kern_ns = []
-    for qq in queries:
-        qq.set_stream(side[0].cuda_stream)
-    for rep in range(max(1, min(K, 200) // NQ)):
-        for qq in queries:
-            qq.launch()
-        for qq in queries:
-            qq.collect()
-            kern_ns.append(qq.last_scan_ns)
-    scan_ns = kern_ns
+    # NK independent query handles are launched back to back on ONE stream with no per-launch events (an event
+    # record costs the GPU front-end several microseconds - a tiny kernel between two events measures 8-10 us on
+    # this system); two events bracket the whole run, the kernels execute strictly one after another, and the
+    # average launch duration is elapsed / launches.  Tables rotate, so no launch finds its input in L2.
+    # Measured twice: as shipped (ungrouped scans are launched with programmatic stream serialization, so the
+    # ramp-up of launch i+1 fills the SMs that launch i's tail has left idle), and with N1GPU_NO_PDL=1 (every launch
+    # waits for the full completion of the one before: the fixed launch/ramp/tail cost shows up in every launch).
+    NK = 32
+    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def kernel_alone():
+        kq = []
+        for i in range(NK):
+            qq = q.Query(tables[i % NT], ALIAS, WHERE, KEYS, AGGS)
+            qq.set_stream(side[0].cuda_stream)
+            qq.set_timing(False)
+            kq.append(qq)
+        for qq in kq:
+            qq.execute()
+        out = []
+        for rep in range(5):
+            torch.cuda.synchronize()
+            ka.record(side[0])
+            for qq in kq:
+                qq.launch()
+            kb.record(side[0])
+            for qq in kq:
+                qq.collect()
+            torch.cuda.synchronize()
+            out.append(ka.elapsed_time(kb) * 1e6 / NK)
+        return out
+
+    scan_ns = kernel_alone()
+    os.environ["N1GPU_NO_PDL"] = "1"
+    try:
+        serial_ns = kernel_alone()
+    finally:
+        del os.environ["N1GPU_NO_PDL"]
 
     # ---- end to end from host JSON ---------------------------------------------------------------------------------
     from oracle import cref  # document generator + CPU baseline only (never the measured path of this arm)
@@ -328,6 +357,9 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "nq_scan (filter + aggregation + fused final reduction), timed alone", "peak_source": peak_src, "mean_kernel_us": mean_ns / 1e3,
+                     "timing": "32 launches back to back on one stream between two CUDA events, elapsed / 32, 5 repetitions; launches use programmatic stream serialization (PDL)",
+                     "serialized_kernel_us": sum(serial_ns) / len(serial_ns) / 1e3,
+                     "frac_serialized": bytes_per_row * ROWS / (sum(serial_ns) / len(serial_ns)) / peak,
                      "algorithmic_bytes_per_launch": bytes_per_row * ROWS},
         "cpu_baseline": {"value": sample / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d of the same config2 documents, oracle/oracle_ref.c (reference-shaped C restatement), %d threads" % (sample, cores)},

@@ -139,6 +139,10 @@ int n1gpu_query_rebind(n1gpu_query* q, n1gpu_table* t);
  * default stream; (void*)-1 = back to the query's own stream), so that callers can bracket scans with their
  * own CUDA events (bench.py).                                                                              */
 int n1gpu_query_set_stream(n1gpu_query* q, void* cuda_stream);
+/* The scan is bracketed by two CUDA events (n1gpu_query_last_scan_ns, "#stats" execTime).  Each record costs the
+ * GPU front-end a few microseconds - as much as a third of a 10 M-row scan - so throughput-critical callers that
+ * time whole regions themselves switch it off.  Default: on.                                                    */
+int n1gpu_query_set_timing(n1gpu_query* q, int enable);
 int n1gpu_query_free(n1gpu_query* q);
 
 /* ---- multi-GPU: InitialGroup per GPU, IntermediateGroup merge across GPUs ----------------------------

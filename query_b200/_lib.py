@@ -62,6 +62,7 @@ _SIGS = {
     "n1gpu_query_last_scan_ns": (C.c_int64, [_P]),
     "n1gpu_query_rebind": (C.c_int, [_P, _P]),
     "n1gpu_query_set_stream": (C.c_int, [_P, _P]),
+    "n1gpu_query_set_timing": (C.c_int, [_P, C.c_int]),
     "n1gpu_query_free": (C.c_int, [_P]),
     "n1gpu_query_scan_partial": (C.c_int, [_P]),
     "n1gpu_query_partial_counts": (C.c_int, [_P, _I64P, _I64P, C.POINTER(C.c_int)]),

@@ -306,6 +306,9 @@ class Query:
         check(lib().n1gpu_query_rebind(self._h, table._h))
         self.table = table
 
+    def set_timing(self, enable):
+        check(lib().n1gpu_query_set_timing(self._h, 1 if enable else 0))
+
     def set_stream(self, cuda_stream):
         """cuda_stream: a cudaStream_t as int (torch.cuda.current_stream().cuda_stream; 0 = the legacy default
         stream), or None for the query's own non-blocking stream."""

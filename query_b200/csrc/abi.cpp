@@ -232,6 +232,11 @@ int n1gpu_query_set_stream(n1gpu_query* q, void* cuda_stream) {
         q->q->stream = (cuda_stream == (void*)-1) ? q->q->own_stream : (cudaStream_t)cuda_stream;
     });
 }
+int n1gpu_query_set_timing(n1gpu_query* q, int enable) {
+    if (!q) return N1GPU_E_INVALID;
+    q->q->timing = enable != 0;
+    return N1GPU_OK;
+}
 int n1gpu_query_free(n1gpu_query* q) { delete q; return N1GPU_OK; }
 
 // ---- peer mailbox (fused small-state all-gather over NVLink) ----------------------------------------------------

@@ -550,6 +550,14 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         if (minb > 0) s += strf("extern \"C\" __global__ void __launch_bounds__(256, %d) nq_scan(const NqParams p) {\n", minb);
         else s += "extern \"C\" __global__ void __launch_bounds__(256) nq_scan(const NqParams p) {\n";
     }
+    {
+        // An ungrouped scan consumes nothing that a stream-preceding kernel produces (its table was sealed with a
+        // device synchronisation, its state belongs to this query handle alone), so the next kernel of the stream
+        // may be scheduled as soon as SMs free up: programmatic dependent launch.
+        const char* np = getenv("N1GPU_NO_PDL");
+        kp.pdl = kp.mode == MODE_UNGROUPED && !(np && *np == '1');
+        if (kp.pdl) s += "    asm volatile(\"griddepcontrol.launch_dependents;\");\n";
+    }
     if (kp.mode == MODE_UNGROUPED) {
         for (int w = 0; w < W; ++w) s += strf("    u64 a%d = word_identity(%s);\n", w, op_name(kp.word_ops[w]));
     } else if (kp.mode == MODE_DENSE && kp.dense_priv) {
@@ -622,6 +630,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "        }\n";
         s += "    }\n";
     }
+    const char* nhw = getenv("N1GPU_NO_HOSTWRITE");  // experiment knob: skip the zero-copy result store
+    const bool hostw = !(nhw && *nhw == '1');
     if (kp.mode == MODE_UNGROUPED) {
         // Block epilogue: warp-shuffle reduce every word, one barrier, then thread w folds word w's 8 warp values in
         // order.  Order-independent words (integer add / min / max / or) go straight into persistent accumulators
@@ -645,7 +655,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "    if (last_block_arrives(p.ticket)) {\n";
         s += "        if (threadIdx.x < NQ_W && nq_ops[threadIdx.x] != OP_ADD_F64) {\n";
         s += "            const u64 v = atomicExch(&p.acc[threadIdx.x], word_identity(nq_ops[threadIdx.x]));\n";
-        s += "            p.final_dev[threadIdx.x] = v; p.final_host[threadIdx.x] = v;\n";
+        s += hostw ? "            p.final_dev[threadIdx.x] = v; p.final_host[threadIdx.x] = v;\n" : "            p.final_dev[threadIdx.x] = v;\n";
         s += "        }\n";
         {
             int fi = 0;
@@ -659,7 +669,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 s += "#pragma unroll\n";
                 s += "            for (int k = 1; k < 5; ++k) v = word_combine(OP_ADD_F64, v, t[k]);\n";
                 s += "            v = block_reduce_word<OP_ADD_F64>(v, scratch);\n";
-                s += strf("            if (threadIdx.x == 0) { p.final_dev[%d] = v; p.final_host[%d] = v; }\n", w, w);
+                s += hostw ? strf("            if (threadIdx.x == 0) { p.final_dev[%d] = v; p.final_host[%d] = v; }\n", w, w)
+                           : strf("            if (threadIdx.x == 0) { p.final_dev[%d] = v; }\n", w);
                 s += "        }\n";
                 ++fi;
             }
@@ -695,6 +706,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "        if (p.peer_mail) mailbox_push(p, p.acc);\n";
         s += "    }\n";
     }
+    if (kp.pdl) s += "    asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");  // complete in stream order\n";
     s += "}\n";
     kp.source = s;
     return kp;

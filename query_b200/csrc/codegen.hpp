@@ -47,6 +47,7 @@ struct KernelPlan {
     int key_bits = 0;
     i64 dense_slots = 0;
     bool dense_priv = false;     // tiny dense table: one private copy per THREAD in shared memory (no atomics at all)
+    bool pdl = false;            // launched with programmatic stream serialization (ungrouped scans)
     int dyn_smem = 0;            // dynamic shared memory the kernel is launched with
     int cache_slots = 0;         // HASH64: slots of the per-block shared-memory front cache (0 = none)
     std::vector<AggPlan> aggs;

@@ -29,6 +29,7 @@ struct Driver {
     decltype(&cuModuleUnload) ModuleUnload = nullptr;
     decltype(&cuModuleGetFunction) ModuleGetFunction = nullptr;
     decltype(&cuLaunchKernel) LaunchKernel = nullptr;
+    decltype(&cuLaunchKernelEx) LaunchKernelEx = nullptr;
     decltype(&cuFuncGetAttribute) FuncGetAttribute = nullptr;
     decltype(&cuFuncSetAttribute) FuncSetAttribute = nullptr;
     decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) Occupancy = nullptr;
@@ -55,6 +56,7 @@ Driver& driver() {
         resolve(g_drv.ModuleUnload, "cuModuleUnload");
         resolve(g_drv.ModuleGetFunction, "cuModuleGetFunction");
         resolve(g_drv.LaunchKernel, "cuLaunchKernel");
+        resolve(g_drv.LaunchKernelEx, "cuLaunchKernelEx");
         resolve(g_drv.FuncGetAttribute, "cuFuncGetAttribute");
         resolve(g_drv.FuncSetAttribute, "cuFuncSetAttribute");
         resolve(g_drv.Occupancy, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
@@ -203,9 +205,28 @@ std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem) {
     return k;
 }
 
-void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t) {
+void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t, bool pdl) {
     void* args[] = {params};
-    cu_check(driver().LaunchKernel((CUfunction)k.function, (unsigned)grid, 1, 1, 256, 1, 1, (unsigned)k.dyn_smem, (CUstream)stream, args, nullptr), "cuLaunchKernel(nq_scan)");
+    if (pdl && driver().LaunchKernelEx) {
+        // Programmatic dependent launch: this grid may start while the previous kernel of the stream drains (that
+        // kernel executed griddepcontrol.launch_dependents), so the launch ramp and the tail of back-to-back scans
+        // overlap; the scan itself ends with griddepcontrol.wait, which keeps completion in stream order.
+        CUlaunchConfig cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDimX = (unsigned)grid; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+        cfg.blockDimX = 256; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+        cfg.sharedMemBytes = (unsigned)k.dyn_smem;
+        cfg.hStream = (CUstream)stream;
+        CUlaunchAttribute attr;
+        memset(&attr, 0, sizeof attr);
+        attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+        attr.value.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        cu_check(driver().LaunchKernelEx(&cfg, (CUfunction)k.function, args, nullptr), "cuLaunchKernelEx(nq_scan)");
+    } else {
+        cu_check(driver().LaunchKernel((CUfunction)k.function, (unsigned)grid, 1, 1, 256, 1, 1, (unsigned)k.dyn_smem, (CUstream)stream, args, nullptr), "cuLaunchKernel(nq_scan)");
+    }
     g_launches.fetch_add(1);
 }
 

@@ -25,7 +25,7 @@ std::string jit_compile_cubin(const std::string& source, std::string* log);
 // Compiles (cached per process by source text) and loads the kernel `nq_scan` on the current device.
 std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem = 0);
 // Launches nq_scan<<<grid, 256, 0, stream>>>(params) where params is a by-value struct of `bytes` bytes.
-void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t bytes);
+void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t bytes, bool pdl = false);
 
 int device_sm_count();
 

@@ -194,9 +194,12 @@ void Query::launch_scan() {
         p.mail_seq = mb_seq;
     }
     reset_state();
-    CK(cudaEventRecord(ev0, stream));
-    jit_launch(*kernel, grid, stream, &p, sizeof p);  // ungrouped / dense: the whole step is this one launch
-    CK(cudaEventRecord(ev1, stream));
+    if (timing) CK(cudaEventRecord(ev0, stream));
+    // ungrouped / dense: the whole step is this one launch.  Programmatic dependent launch only when nothing this
+    // step enqueued before the scan (status / DISTINCT set clears) has to be complete when its first block starts.
+    jit_launch(*kernel, grid, stream, &p, sizeof p, kp.pdl && !uses_status());
+    if (timing) CK(cudaEventRecord(ev1, stream));
+    timed_launch = timing;
     if (mb_seq)  // receive side of the fused all-gather: fold every rank's words once they have landed
         launch_merge_mailbox((const u64*)mailbox->base, mailbox->nranks, mb_slot_base, mailbox->stride, cap * (u64)ops.n, mb_seq, cap, ops,
                              d_acc.as<u64>(), h_records.as<u64>(), d_status.as<int>(), stream);
@@ -209,9 +212,11 @@ bool Query::wait_scan() {
     if (!launched) N1_THROW(N1GPU_E_INVALID, "no scan outstanding");
     launched = false;
     CK(cudaStreamSynchronize(stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, ev0, ev1));
-    last_scan_ms = ms;
+    if (timed_launch) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        last_scan_ms = ms;
+    }
     int st = uses_status() ? h_status.as<int>()[0] : 0;
     if (st == 3) N1_THROW(N1GPU_E_CUDA, "multi-GPU merge timed out: a peer rank never delivered its partial state");
     if (st == 1) {

@@ -58,6 +58,8 @@ struct Query {
     PinnedBuf h_status, h_counts, h_records, h_drecords;
     std::atomic<bool> cancelled{false};
     bool launched = false;
+    bool timing = true;        // record CUDA events around the scan (each record costs GPU front-end time)
+    bool timed_launch = false;
     bool ungrouped_live = true;
     bool host_acc_valid = false;  // h_records holds the table words of the last scan (small-state modes)
     bool import_dirty() const { return !host_acc_valid; }
