@@ -274,19 +274,23 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     // COUNT(x), COUNTN(x) over the same operand text use one sum word / one count word, and a count that provably
     // equals the number of selected rows (operand never MISSING/NULL/non-number) is the rows word itself.
     std::map<std::string, int> shared;
-    auto add_word = [&](int op, const std::string& key) {
+    auto add_word = [&](int op, const std::string& key, bool counter = false, i64 lo = 1, i64 hi = 0) {
         auto it = shared.find(key);
         if (it != shared.end()) return it->second;
         kp.word_ops.push_back(op);
+        kp.word_count.push_back(counter);
+        kp.word_lo.push_back(lo);
+        kp.word_hi.push_back(hi);
         shared[key] = (int)kp.word_ops.size() - 1;
         return (int)kp.word_ops.size() - 1;
     };
+    const u32 M_ABSENT = bit(C_MISSING) | bit(C_NULL);
     std::map<std::string, int> dset_of;  // DISTINCT operand text -> entry-set id
     std::vector<bool> dset_any;          // set id -> holds every value > NULL (else numbers only)
     int ndistinct_aggs = 0;
     int w_rows = -1;
-    if (!keys.empty()) w_rows = add_word(OP_ADD_U64, "rows");  // word 0: rows per group (group existence)
-    auto rows_word = [&]() { if (w_rows < 0) w_rows = add_word(OP_ADD_U64, "rows"); return w_rows; };
+    if (!keys.empty()) w_rows = add_word(OP_ADD_U64, "rows", true);  // word 0: rows per group (group existence)
+    auto rows_word = [&]() { if (w_rows < 0) w_rows = add_word(OP_ADD_U64, "rows", true); return w_rows; };
 
     // ---- aggregate layout --------------------------------------------------------------------------------
     for (size_t a = 0; a < aggs.size(); ++a) {
@@ -309,7 +313,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             if (++ndistinct_aggs > 16) N1_THROW(N1GPU_E_INELIGIBLE, "more than 16 DISTINCT aggregates");
             ap.dcomp = make_comp(t, *opnd, "DISTINCT");
             const std::string dk = strf("d%d:", ndistinct_aggs);
-            ap.w_cnt = add_word(OP_ADD_U64, dk + "cnt");
+            ap.w_cnt = add_word(OP_ADD_U64, dk + "cnt", true);
             if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
                 if (ap.dcomp.mask & bit(C_INT)) {
                     ap.w_ilo = add_word(OP_ADD_U64, dk + "ilo");
@@ -322,7 +326,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             const std::string ot = opnd ? opnd->str() : std::string("*");
             const u32 counted = ap.kind == AggKind::COUNT ? ~(bit(C_MISSING) | bit(C_NULL)) : M_NUM;
             if (ap.star || (ap.opmask & ~counted) == 0) ap.w_cnt = rows_word();  // every selected row counts
-            else ap.w_cnt = add_word(OP_ADD_U64, (ap.kind == AggKind::COUNT ? "cnt:" : "cntn:") + ot);
+            else ap.w_cnt = add_word(OP_ADD_U64, (ap.kind == AggKind::COUNT ? "cnt:" : "cntn:") + ot, true);
         } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
             const std::string ot = opnd->str();
             if (ap.opmask & bit(C_INT)) {
@@ -334,14 +338,18 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 }
                 if (exact1) ap.w_isum = add_word(OP_ADD_U64, "isum:" + ot);
                 else { ap.w_ilo = add_word(OP_ADD_U64, "ilo:" + ot); ap.w_ihi = add_word(OP_ADD_U64, "ihi:" + ot); }
+                // how many ints were summed, and how many of them were negative; the int counter is whichever existing
+                // counter provably counts the same rows (every selected row / rows > NULL / numbers), else its own word
                 bool can_neg = !ti.ranged || ti.lo < 0, can_nonneg = !ti.ranged || ti.hi >= 0;
-                const bool always_int = ap.opmask == bit(C_INT);
-                if (can_nonneg) ap.w_nonneg = (always_int && !can_neg) ? rows_word() : add_word(OP_ADD_U64, "nnn:" + ot);
-                if (can_neg) ap.w_neg = (always_int && !can_nonneg) ? rows_word() : add_word(OP_ADD_U64, "nneg:" + ot);
+                if (ap.opmask == bit(C_INT)) ap.w_nint = rows_word();
+                else if ((ap.opmask & ~(M_ABSENT | bit(C_INT))) == 0) ap.w_nint = add_word(OP_ADD_U64, "cnt:" + ot, true);
+                else if ((ap.opmask & bit(C_FLOAT)) == 0) ap.w_nint = add_word(OP_ADD_U64, "cntn:" + ot, true);
+                else ap.w_nint = add_word(OP_ADD_U64, "nint:" + ot, true);
+                if (can_neg) ap.w_neg = can_nonneg ? add_word(OP_ADD_U64, "nneg:" + ot, true) : ap.w_nint;
             }
             if (ap.opmask & bit(C_FLOAT)) {
                 ap.w_fsum = add_word(OP_ADD_F64, "fsum:" + ot);
-                ap.w_nflt = ap.opmask == bit(C_FLOAT) ? rows_word() : add_word(OP_ADD_U64, "nflt:" + ot);
+                ap.w_nflt = ap.opmask == bit(C_FLOAT) ? rows_word() : add_word(OP_ADD_U64, "nflt:" + ot, true);
             }
         } else {  // MIN / MAX
             bool mn = ap.kind == AggKind::MIN;
@@ -350,10 +358,19 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             if (m & bit(C_STRING)) { if (ap.dict_col < 0) N1_THROW(N1GPU_E_INELIGIBLE, "MIN/MAX over a constant or computed string"); }
             if (opnd && !opnd->ti.plain_col && (m & bit(C_FLOAT))) m |= bit(C_INT);  // canon_num
             ap.opmask = m;
-            ap.w_seen = add_word(OP_OR_U64, "seen:" + opnd->str());  // MIN and MAX of one operand see the same classes
-            if (m & bit(C_INT)) ap.w_mi = add_word(mn ? OP_MIN_I64 : OP_MAX_I64, "i:" + ot);
+            // which classes were seen: MIN and MAX of one operand share the word; an operand with a single class above
+            // NULL needs no class bits at all, only "was there any" = a counter other aggregates usually keep anyway
+            const u32 above = m & ~M_ABSENT;
+            if (above && (above & (above - 1)) == 0) {
+                for (int c = 0; c < 8; ++c) if (above == bit(c)) ap.seen_class = c;
+                ap.w_seen_cnt = (m & M_ABSENT) == 0 ? rows_word() : add_word(OP_ADD_U64, "cnt:" + opnd->str(), true);
+            } else ap.w_seen = add_word(OP_OR_U64, "seen:" + opnd->str());
+            const TypeInfo& ti = opnd->ti;
+            const bool r = ti.ranged;
+            if (m & bit(C_INT)) ap.w_mi = add_word(mn ? OP_MIN_I64 : OP_MAX_I64, "i:" + ot, false, r ? ti.lo : 1, r ? ti.hi : 0);
             if (m & bit(C_FLOAT)) ap.w_mf = add_word(mn ? OP_MIN_U64 : OP_MAX_U64, "f:" + ot);
-            if (m & bit(C_STRING)) ap.w_ms = add_word(mn ? OP_MIN_U64 : OP_MAX_U64, "s:" + ot);
+            if (m & bit(C_STRING)) ap.w_ms = add_word(mn ? OP_MIN_U64 : OP_MAX_U64, "s:" + ot, false, 0,
+                                                    std::max<i64>(t.cols[ap.dict_col].stats.ndict, (i64)t.cols[ap.dict_col].dict.size()));
         }
         kp.aggs.push_back(ap);
     }
@@ -376,10 +393,30 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         // shared-memory front cache for hot keys (Zipf-skewed GROUP BY): as many slots as fit 32 KiB
         const char* nc = getenv("N1GPU_NO_CACHE");
         if (!(nc && *nc == '1')) {
-            int cs = 2048;
-            while (cs > 64 && (i64)cs * (1 + W) * 8 > 32 * 1024) cs >>= 1;  // <= 32 KiB: keeps 6 blocks per SM resident
-            kp.cache_slots = cs;
-            kp.dyn_smem = cs * (1 + W) * 8;
+            // cell layout (see n1ql_device.cuh "Cells of the front cache")
+            for (int w = 0; w < W; ++w) {
+                const int op = kp.word_ops[w];
+                int kind = CK_64;
+                if (op == OP_ADD_U64) kind = kp.word_count[w] ? CK_CNT : CK_WIDE;
+                else if (op == OP_OR_U64) kind = CK_OR32;
+                else if (op != OP_ADD_F64 && kp.word_lo[w] <= kp.word_hi[w] && (u64)kp.word_hi[w] - (u64)kp.word_lo[w] <= 0xfffffffcULL) kind = CK_MM32;
+                kp.cell_kind.push_back(kind);
+                if (kind == CK_64) kp.cell_idx.push_back(kp.cache_n64++);
+                else { kp.cell_idx.push_back(kp.cache_n32); kp.cache_n32 += kind == CK_WIDE ? 2 : 1; }
+            }
+            const int slot_bytes = 8 + 8 * kp.cache_n64 + 4 * kp.cache_n32;
+            // Measured on B200 (tools/scan_perf.py config5, 40 M rows): 256 threads + 36 KiB (five blocks per SM) 510 us,
+            // 512 + 72 KiB 537 us, 1024 + 150 KiB 518 us: a larger cache raises the hit rate but the lost occupancy
+            // costs as much, so the small block stays the default; both remain tuning knobs.
+            const char* kb = getenv("N1GPU_CACHE_KB");      // shared memory per block spent on the cache
+            const char* bt = getenv("N1GPU_CACHE_BLOCK");   // threads per block
+            kp.block = bt && atoi(bt) >= 64 ? atoi(bt) / 32 * 32 : 256;
+            const i64 budget = (kb && atoi(kb) > 0 ? atoi(kb) : 36) * 1024;
+            i64 cs = budget / slot_bytes / 64 * 64;
+            const i64 need = (i64)std::min(4.0 * std::max(est, 1.0), 1e9);  // never more than the groups need
+            if (cs > need) cs = std::max<i64>(64, (need + 63) / 64 * 64);
+            kp.cache_slots = (int)cs;
+            kp.dyn_smem = (int)cs * slot_bytes;
         }
     }
     else if (kp.key_bits <= 127) kp.mode = MODE_HASH128;
@@ -408,6 +445,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     g.body.clear();
 
     // aggregation code (executed under `if (pass)`)
+    std::string key_code;
     g.ind = "                    ";
     if (kp.mode != MODE_UNGROUPED) {
         g.line("u64 klo = 0, khi = 0; int kpos = 0;");
@@ -422,14 +460,14 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         }
         if (kp.mode == MODE_DENSE) g.line("const i64 slot = (i64)klo;");
         else if (kp.mode == MODE_HASH64 && kp.cache_slots) {
-            g.line("++nlook;");
-            g.line("const int cslot = cache_on ? cache_claim(s_ckey, NQ_CS - 1, klo) : -1;");
-            g.line("nhit += cslot >= 0;");
-            g.line("const i64 slot = cslot >= 0 ? 0 : table_insert64(p.keys, p.cap_mask, klo, nullptr);");
+            // the kernel is assembled in phases (keys + cache probe / cached updates / table updates, see below):
+            // the key code ends here, the update code starts from an empty body
+            key_code = g.body;
+            g.body.clear();
         }
         else if (kp.mode == MODE_HASH64) g.line("const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);");
         else g.line("const i64 slot = table_insert128((ulonglong2*)p.keys, p.cap_mask, klo, khi, nullptr);");
-        if (kp.mode != MODE_DENSE) g.line("if (slot < 0) { p.status[0] = 1; continue; }");
+        if (kp.mode != MODE_DENSE && !(kp.mode == MODE_HASH64 && kp.cache_slots)) g.line("if (slot < 0) { p.status[0] = 1; continue; }");
     }
     std::set<int> emitted_sets;
     std::set<int> emitted;  // a shared word is updated once per row, by the first aggregate that owns it
@@ -483,11 +521,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                     ACC(ap.w_ilo, OP_ADD_U64, strf("((u64)%s.b & 0xffffffffULL)", o.c_str()));
                     ACC(ap.w_ihi, OP_ADD_U64, strf("(u64)(%s.b >> 32)", o.c_str()));
                 }
-                if (ap.w_nonneg >= 0 && ap.w_neg >= 0) {
-                    ACCIF(strf("%s.b >= 0", o.c_str()), ap.w_nonneg, OP_ADD_U64, "1");
-                    ACCIF(strf("%s.b < 0", o.c_str()), ap.w_neg, OP_ADD_U64, "1");
-                } else if (ap.w_nonneg >= 0) ACC(ap.w_nonneg, OP_ADD_U64, "1");
-                else if (ap.w_neg >= 0) ACC(ap.w_neg, OP_ADD_U64, "1");
+                ACC(ap.w_nint, OP_ADD_U64, "1");
+                if (ap.w_neg >= 0 && ap.w_neg != ap.w_nint) ACCIF(strf("%s.b < 0", o.c_str()), ap.w_neg, OP_ADD_U64, "1");
                 g.ind = save_ind + "    ";
                 g.line("}");
             }
@@ -505,7 +540,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             if (!e.ops[0]->ti.plain_col && (e.ops[0]->ti.mask & bit(C_FLOAT))) { cv = g.nv("mm"); g.line(strf("const Val %s = canon_num(%s);", cv.c_str(), o.c_str())); }
             g.line(strf("if (%s.c > C_NULL) {", cv.c_str()));
             g.ind += "    ";
-            ACC(ap.w_seen, OP_OR_U64, strf("(1ULL << %s.c)", cv.c_str()));
+            if (ap.w_seen >= 0) ACC(ap.w_seen, OP_OR_U64, strf("(1ULL << %s.c)", cv.c_str()));
+            else ACC(ap.w_seen_cnt, OP_ADD_U64, "1");
             if (ap.w_mi >= 0) ACCIF(strf("%s.c == C_INT", cv.c_str()), ap.w_mi, mn ? OP_MIN_I64 : OP_MAX_I64, strf("(u64)%s.b", cv.c_str()));
             if (ap.w_mf >= 0) ACCIF(strf("%s.c == C_FLOAT", cv.c_str()), ap.w_mf, mn ? OP_MIN_U64 : OP_MAX_U64, strf("f64_ordered(as_f(%s.b))", cv.c_str()));
             if (ap.w_ms >= 0) ACCIF(strf("%s.c == C_STRING", cv.c_str()), ap.w_ms, mn ? OP_MIN_U64 : OP_MAX_U64, strf("((u64)%s.b >> 1)", cv.c_str()));
@@ -539,16 +575,28 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     else if (kp.mode == MODE_DENSE) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
     else if (kp.mode == MODE_HASH64 && kp.cache_slots) {
         s += strf("#define NQ_CS %d\n", kp.cache_slots);
-        s += "#define ACC(k, OP, val_) { if (cslot >= 0) atomic_word<OP>(&s_cacc[(k) * NQ_CS + cslot], (u64)(val_)); "
-             "else atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(val_)); }\n";
+        s += "#define ACCM(k, OP, val_) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(val_))\n";
+        for (int w = 0; w < W; ++w) {
+            std::string hit;
+            const int ci = kp.cell_idx[w];
+            switch (kp.cell_kind[w]) {
+                case CK_CNT: hit = strf("atomicAdd(&s_c32[%d * NQ_CS + cslot], (u32)(val_))", ci); break;
+                case CK_WIDE: hit = strf("cache_add_wide(&s_c32[%d * NQ_CS + cslot], &s_c32[%d * NQ_CS + cslot], (u64)(val_))", ci, ci + 1); break;
+                case CK_MM32: hit = strf("cache_mm32<OP>(&s_c32[%d * NQ_CS + cslot], (u64)(val_), %lluULL)", ci, (unsigned long long)kp.word_lo[w]); break;
+                case CK_OR32: hit = strf("cache_or32(&s_c32[%d * NQ_CS + cslot], (u32)(val_))", ci); break;
+                default: hit = strf("cache_word64<OP>(&s_c64[%d * NQ_CS + cslot], (u64)(val_))", ci); break;
+            }
+            s += strf("#define ACCH_%d(OP, val_) %s\n", w, hit.c_str());
+        }
     }
     else s += "#define ACC(k, OP, x) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
     {
         // resident blocks per SM the register allocator must allow (tuning knob N1GPU_MIN_BLOCKS; 0 = compiler's choice)
         const char* lb = getenv("N1GPU_MIN_BLOCKS");
         int minb = lb ? atoi(lb) : 0;
-        if (minb > 0) s += strf("extern \"C\" __global__ void __launch_bounds__(256, %d) nq_scan(const NqParams p) {\n", minb);
-        else s += "extern \"C\" __global__ void __launch_bounds__(256) nq_scan(const NqParams p) {\n";
+        s += strf("#define NQ_BLOCK %d\n", kp.block);
+        if (minb > 0) s += strf("extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, %d) nq_scan(const NqParams p) {\n", minb);
+        else s += "extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK) nq_scan(const NqParams p) {\n";
     }
     {
         // An ungrouped scan consumes nothing that a stream-preceding kernel produces (its table was sealed with a
@@ -573,9 +621,20 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         if (kp.cache_slots) {
             s += "    extern __shared__ u64 s_dyn[];\n";
             s += "    u64* const s_ckey = s_dyn;            // [NQ_CS] cached group keys (all ones = empty)\n";
-            s += "    u64* const s_cacc = s_dyn + NQ_CS;    // [NQ_W][NQ_CS] their accumulator words\n";
-            s += "    for (int i = threadIdx.x; i < NQ_CS; i += 256) s_ckey[i] = NQ_U64_MAX;\n";
-            s += "    for (int i = threadIdx.x; i < NQ_W * NQ_CS; i += 256) s_cacc[i] = word_identity(nq_ops[i / NQ_CS]);\n";
+            s += strf("    u64* const s_c64 = s_dyn + NQ_CS;     // [%d][NQ_CS] 64-bit cells\n", kp.cache_n64);
+            s += strf("    u32* const s_c32 = (u32*)(s_dyn + %d * NQ_CS);  // [%d][NQ_CS] 32-bit cells\n", 1 + kp.cache_n64, kp.cache_n32);
+            s += "    for (int i = threadIdx.x; i < NQ_CS; i += NQ_BLOCK) {\n";
+            s += "        s_ckey[i] = NQ_U64_MAX;\n";
+            for (int w = 0; w < W; ++w) {
+                const int ci = kp.cell_idx[w], op = kp.word_ops[w];
+                switch (kp.cell_kind[w]) {
+                    case CK_WIDE: s += strf("        s_c32[%d * NQ_CS + i] = 0; s_c32[%d * NQ_CS + i] = 0;\n", ci, ci + 1); break;
+                    case CK_MM32: s += strf("        s_c32[%d * NQ_CS + i] = %s;\n", ci, (op == OP_MIN_I64 || op == OP_MIN_U64) ? "0xffffffffu" : "0u"); break;
+                    case CK_64: s += strf("        s_c64[%d * NQ_CS + i] = word_identity(%s);\n", ci, op_name(op)); break;
+                    default: s += strf("        s_c32[%d * NQ_CS + i] = 0;\n", ci); break;
+                }
+            }
+            s += "    }\n";
             s += "    __syncthreads();\n";
             s += "    bool cache_on = true;  // per warp: switched off after 4 tiles when fewer than 1 in 4 rows hit\n";
             s += "    unsigned nlook = 0, nhit = 0; int tiles = 0;\n";
@@ -583,9 +642,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     }
     s += "    const i64 nrows = p.nrows;\n";
     s += "    const int lane = threadIdx.x & 31;\n";
-    s += "    const i64 stride = (i64)gridDim.x * 1024;\n";
+    s += "    const i64 stride = (i64)gridDim.x * (NQ_BLOCK * 4);\n";
     s += "    // warp-uniform trip count: every lane of a warp stays in the loop while the warp has rows\n";
-    s += "    for (i64 wbase = (i64)blockIdx.x * 1024 + (threadIdx.x >> 5) * 128; wbase < nrows; wbase += stride) {\n";
+    s += "    for (i64 wbase = (i64)blockIdx.x * (NQ_BLOCK * 4) + (threadIdx.x >> 5) * 128; wbase < nrows; wbase += stride) {\n";
     s += "        const i64 base = wbase + lane * 4;\n";
     for (int c : kp.used_cols) {
         const Column& col = t.cols[c];
@@ -593,21 +652,73 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         else if (col.width == 4) s += strf("        u32 c%d[4]; ld_rows4_b32((const u32*)p.col[%d] + base, c%d);\n", c, c, c);
         if (!col.stats.uniform_tag() && col.stats.class_mask) s += strf("        int t%d[4]; ld_rows4_b8(p.tag[%d] + base, t%d);\n", c, c, c);
     }
-    s += "#pragma unroll\n";
-    s += "        for (int j = 0; j < 4; ++j) {\n";
-    s += "            bool pass = base + j < nrows;\n";
-    s += g.decls;
-    if (where) {
-        s += filter_code;
-        s += "                pass = pass && w_true;\n";
+    if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+        // Three phases per 4 rows, so that the lanes of a warp diverge once per phase instead of once per accumulator
+        // word: (1) filter, group key and front-cache probe of all four rows (the four probes are independent: their
+        // shared-memory latencies overlap); (2) rows whose key is cached update shared-memory cells; (3) the others
+        // insert into the HBM table and update it with L2 atomics.
+        s += "        u64 kk[4]; int cs[4];  // group key / cache slot (-1: not cached, -2: row not selected)\n";
+        s += "        __syncwarp();\n";
+        s += "#pragma unroll\n";
+        s += "        for (int j = 0; j < 4; ++j) {\n";
+        s += "            bool pass = base + j < nrows;\n";
+        s += g.decls;
+        if (where) {
+            s += filter_code;
+            s += "                pass = pass && w_true;\n";
+        }
+        s += "            cs[j] = -2; kk[j] = 0;\n";
+        s += "            if (pass) {\n";
+        s += key_code;
+        s += "                    kk[j] = klo;\n";
+        s += "                    ++nlook;\n";
+        if (kp.key_bits <= 32) s += "                    cs[j] = cache_on ? cache_claim_n(s_ckey, NQ_CS, (u32)klo * 0x9E3779B1u, klo) : -1;\n";
+        else s += "                    cs[j] = cache_on ? cache_claim_n(s_ckey, NQ_CS, (u32)(mix64(klo) >> 32), klo) : -1;\n";
+        s += "                    nhit += cs[j] >= 0;\n";
+        s += "            }\n";
+        s += "        }\n";
+        s += "#define ACC(k, OP, val_) ACCH_##k(OP, val_)\n";
+        s += "#pragma unroll\n";
+        s += "        for (int j = 0; j < 4; ++j) {\n";
+        s += "            // warp-ballot selection mask (also the point where the lanes of the warp reconverge)\n";
+        s += "            if (__ballot_sync(0xffffffffu, cs[j] >= 0) == 0) continue;\n";
+        s += "            if (cs[j] >= 0) {\n";
+        s += "                    const int cslot = cs[j]; const u64 klo = kk[j]; (void)klo;\n";
+        s += g.decls;
+        s += agg_code;
+        s += "            }\n";
+        s += "        }\n";
+        s += "#undef ACC\n";
+        s += "#define ACC(k, OP, val_) ACCM(k, OP, val_)\n";
+        s += "#pragma unroll\n";
+        s += "        for (int j = 0; j < 4; ++j) {\n";
+        s += "            if (__ballot_sync(0xffffffffu, cs[j] == -1) == 0) continue;\n";
+        s += "            if (cs[j] == -1) {\n";
+        s += "                    const u64 klo = kk[j];\n";
+        s += "                    const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);\n";
+        s += "                    if (slot < 0) { p.status[0] = 1; continue; }\n";
+        s += g.decls;
+        s += agg_code;
+        s += "            }\n";
+        s += "        }\n";
+        s += "#undef ACC\n";
+    } else {
+        s += "#pragma unroll\n";
+        s += "        for (int j = 0; j < 4; ++j) {\n";
+        s += "            bool pass = base + j < nrows;\n";
+        s += g.decls;
+        if (where) {
+            s += filter_code;
+            s += "                pass = pass && w_true;\n";
+        }
+        s += "            // warp-ballot selection mask: skip the aggregation when no lane selected its row\n";
+        s += "            const unsigned sel = __ballot_sync(0xffffffffu, pass);\n";
+        s += "            if (sel == 0) continue;\n";
+        s += "            if (pass) {\n";
+        s += agg_code;
+        s += "            }\n";
+        s += "        }\n";
     }
-    s += "            // warp-ballot selection mask: skip the aggregation when no lane selected its row\n";
-    s += "            const unsigned sel = __ballot_sync(0xffffffffu, pass);\n";
-    s += "            if (sel == 0) continue;\n";
-    s += "            if (pass) {\n";
-    s += agg_code;
-    s += "            }\n";
-    s += "        }\n";
     if (kp.mode == MODE_HASH64 && kp.cache_slots) {
         s += "        if (cache_on && ++tiles == 4) {  // warp-uniform: is the front cache earning its probes?\n";
         s += "            const unsigned L = __reduce_add_sync(0xffffffffu, nlook), H = __reduce_add_sync(0xffffffffu, nhit);\n";
@@ -618,16 +729,32 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     if (kp.mode == MODE_HASH64 && kp.cache_slots) {
         // flush the block's cached groups into the HBM table: one insert + one atomic per word per cached key
         s += "    __syncthreads();\n";
-        s += "    for (int i = threadIdx.x; i < NQ_CS; i += 256) {\n";
+        s += "    for (int i = threadIdx.x; i < NQ_CS; i += NQ_BLOCK) {\n";
         s += "        const u64 key = s_ckey[i];\n";
         s += "        if (key == NQ_U64_MAX) continue;\n";
         s += "        const i64 slot = table_insert64(p.keys, p.cap_mask, key, nullptr);\n";
         s += "        if (slot < 0) { p.status[0] = 1; continue; }\n";
-        s += "#pragma unroll\n";
-        s += "        for (int w = 0; w < NQ_W; ++w) {\n";
-        s += "            const u64 v = s_cacc[w * NQ_CS + i];\n";
-        s += "            if (v != word_identity(nq_ops[w])) atomic_word_dyn(nq_ops[w], &p.acc[(u64)w * cap + (u64)slot], v);\n";
-        s += "        }\n";
+        for (int w = 0; w < W; ++w) {
+            const int ci = kp.cell_idx[w], op = kp.word_ops[w];
+            const std::string dst = strf("&p.acc[%dULL * cap + (u64)slot]", w);
+            switch (kp.cell_kind[w]) {
+                case CK_WIDE:
+                    s += strf("        { const u64 v = ((u64)s_c32[%d * NQ_CS + i] << 32) + (u64)s_c32[%d * NQ_CS + i]; if (v) atomic_word<%s>(%s, v); }\n",
+                              ci + 1, ci, op_name(op), dst.c_str());
+                    break;
+                case CK_MM32:
+                    s += strf("        { const u32 c = s_c32[%d * NQ_CS + i]; if (c != %s) atomic_word<%s>(%s, (u64)(c - 1u) + %lluULL); }\n", ci,
+                              (op == OP_MIN_I64 || op == OP_MIN_U64) ? "0xffffffffu" : "0u", op_name(op), dst.c_str(), (unsigned long long)kp.word_lo[w]);
+                    break;
+                case CK_64:
+                    s += strf("        { const u64 v = s_c64[%d * NQ_CS + i]; if (v != word_identity(%s)) atomic_word<%s>(%s, v); }\n", ci, op_name(op),
+                              op_name(op), dst.c_str());
+                    break;
+                default:
+                    s += strf("        { const u64 v = s_c32[%d * NQ_CS + i]; if (v) atomic_word<%s>(%s, v); }\n", ci, op_name(op), dst.c_str());
+                    break;
+            }
+        }
         s += "    }\n";
     }
     const char* nhw = getenv("N1GPU_NO_HOSTWRITE");  // experiment knob: skip the zero-copy result store

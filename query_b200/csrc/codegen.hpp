@@ -11,6 +11,7 @@
 namespace n1 {
 
 enum : int { MODE_UNGROUPED = 0, MODE_DENSE = 1, MODE_HASH64 = 2, MODE_HASH128 = 3 };
+enum : int { CK_CNT = 0, CK_WIDE = 1, CK_MM32 = 2, CK_OR32 = 3, CK_64 = 4 };
 
 // One bit-packed component: a group-key value or the value of a DISTINCT entry.
 struct PackComp {
@@ -32,9 +33,10 @@ struct AggPlan {
     int w_cnt = -1;
     int w_isum = -1;           // exact single-word int sum (range proves no overflow)
     int w_ilo = -1, w_ihi = -1;  // split int sum: sum of low 32 bits / sum of (x >> 32)
-    int w_nonneg = -1, w_neg = -1;
+    int w_nint = -1, w_neg = -1;  // ints summed / negative ints among them (intValue.Add: mixed signs -> float64)
     int w_fsum = -1, w_nflt = -1;
     int w_seen = -1, w_mi = -1, w_mf = -1, w_ms = -1;
+    int w_seen_cnt = -1, seen_class = -1;  // single-class operand: "seen" = (this count word > 0) ? bit(seen_class) : 0
     int dict_col = -1;
     int distinct_id = -1;      // index among DISTINCT aggregates
     PackComp dcomp;
@@ -43,13 +45,19 @@ struct AggPlan {
 struct KernelPlan {
     int mode = MODE_UNGROUPED;
     std::vector<int> word_ops;   // accumulator words per group
+    std::vector<bool> word_count;  // word only ever receives +1 (a row counter): bounded by the rows one block scans
+    std::vector<i64> word_lo, word_hi;  // min/max words: proven value range (lo > hi: unknown)
     std::vector<PackComp> keys;
     int key_bits = 0;
     i64 dense_slots = 0;
     bool dense_priv = false;     // tiny dense table: one private copy per THREAD in shared memory (no atomics at all)
     bool pdl = false;            // launched with programmatic stream serialization (ungrouped scans)
     int dyn_smem = 0;            // dynamic shared memory the kernel is launched with
+    int block = 256;             // threads per block (a block scans block * 4 rows per iteration)
     int cache_slots = 0;         // HASH64: slots of the per-block shared-memory front cache (0 = none)
+    // front-cache cell of every word: kind (CK_*) and index of its first cell among the 32-bit / 64-bit cell arrays
+    std::vector<int> cell_kind, cell_idx;
+    int cache_n32 = 0, cache_n64 = 0;
     std::vector<AggPlan> aggs;
     int ndistinct = 0, abits = 0, entry_bits = 0;
     bool set128 = false;

@@ -177,7 +177,7 @@ std::string jit_compile_cubin(const std::string& source, std::string* log) {
     return cubin;
 }
 
-std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem) {
+std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem, int block) {
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_cache.find(source);
@@ -196,9 +196,10 @@ std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem) {
     cu_check(d.FuncGetAttribute(&k->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn), "cuFuncGetAttribute");
     cu_check(d.FuncGetAttribute(&k->static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, fn), "cuFuncGetAttribute");
     k->dyn_smem = dyn_smem;
+    k->block = block;
     if (dyn_smem > 0)  // static + dynamic may cross the 48 KiB default even when the dynamic part alone does not
         cu_check(d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, dyn_smem), "cuFuncSetAttribute(max dynamic shared memory)");
-    cu_check(d.Occupancy(&k->max_blocks_per_sm, fn, 256, (size_t)dyn_smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    cu_check(d.Occupancy(&k->max_blocks_per_sm, fn, block, (size_t)dyn_smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     if (k->max_blocks_per_sm < 1) k->max_blocks_per_sm = 1;
     std::lock_guard<std::mutex> lk(g_mu);
     g_cache[source] = k;
@@ -214,7 +215,7 @@ void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params,
         CUlaunchConfig cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDimX = (unsigned)grid; cfg.gridDimY = 1; cfg.gridDimZ = 1;
-        cfg.blockDimX = 256; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+        cfg.blockDimX = (unsigned)k.block; cfg.blockDimY = 1; cfg.blockDimZ = 1;
         cfg.sharedMemBytes = (unsigned)k.dyn_smem;
         cfg.hStream = (CUstream)stream;
         CUlaunchAttribute attr;
@@ -225,7 +226,7 @@ void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params,
         cfg.numAttrs = 1;
         cu_check(driver().LaunchKernelEx(&cfg, (CUfunction)k.function, args, nullptr), "cuLaunchKernelEx(nq_scan)");
     } else {
-        cu_check(driver().LaunchKernel((CUfunction)k.function, (unsigned)grid, 1, 1, 256, 1, 1, (unsigned)k.dyn_smem, (CUstream)stream, args, nullptr), "cuLaunchKernel(nq_scan)");
+        cu_check(driver().LaunchKernel((CUfunction)k.function, (unsigned)grid, 1, 1, (unsigned)k.block, 1, 1, (unsigned)k.dyn_smem, (CUstream)stream, args, nullptr), "cuLaunchKernel(nq_scan)");
     }
     g_launches.fetch_add(1);
 }

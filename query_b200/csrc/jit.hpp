@@ -15,7 +15,8 @@ struct JitKernel {
     int regs = 0;
     int static_smem = 0;
     int dyn_smem = 0;
-    int max_blocks_per_sm = 0;  // occupancy at 256 threads
+    int block = 256;            // threads per block the source was generated for (NQ_BLOCK)
+    int max_blocks_per_sm = 0;  // occupancy at `block` threads
     std::string cubin;
     ~JitKernel();
 };
@@ -23,8 +24,8 @@ struct JitKernel {
 // Compiles `source` (which #includes "n1ql_device.cuh") to an sm_100a cubin.  Works without a GPU.
 std::string jit_compile_cubin(const std::string& source, std::string* log);
 // Compiles (cached per process by source text) and loads the kernel `nq_scan` on the current device.
-std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem = 0);
-// Launches nq_scan<<<grid, 256, 0, stream>>>(params) where params is a by-value struct of `bytes` bytes.
+std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem = 0, int block = 256);
+// Launches nq_scan<<<grid, k.block, k.dyn_smem, stream>>>(params) where params is a by-value struct of `bytes` bytes.
 void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t bytes, bool pdl = false);
 
 int device_sm_count();

@@ -394,6 +394,51 @@ NQ_DEV int cache_claim(u64* ckeys, u32 mask, u64 key) {
     return -1;
 }
 
+// Same for any slot count (not only powers of two): the slot is the high part of hash * slots.
+NQ_DEV int cache_claim_n(u64* ckeys, u32 slots, u32 hash, u64 key) {
+    u32 h = __umulhi(hash, slots);
+#pragma unroll
+    for (int probe = 0; probe < 4; ++probe) {
+        const u64 cur = ((volatile u64*)ckeys)[h];
+        if (cur == key) return (int)h;
+        if (cur == NQ_U64_MAX) {
+            const u64 old = atomicCAS(&ckeys[h], NQ_U64_MAX, key);
+            if (old == NQ_U64_MAX || old == key) return (int)h;
+        }
+        h = h + 1 == slots ? 0 : h + 1;
+    }
+    return -1;
+}
+
+// Cells of the front cache.  Shared memory has native 32-bit atomics only (a 64-bit atomicAdd/Min/Max on shared
+// memory compiles to a compare-and-swap loop, 3-9x slower and collapsing under same-key contention), so a cached
+// accumulator word is kept in 32-bit cells wherever its per-block value provably fits or can be split:
+//   row counters        one cell (a block scans far fewer than 2^32 rows)
+//   integer sums        two cells, low word + high word with the carry propagated by the adding thread
+//   ranged min / max    one cell holding (value - lo + 1); 0 (max) / all ones (min) = nothing seen
+//   class-seen bits     one cell
+// anything else (float64 sums, unranged or float min/max) keeps a 64-bit cell and checks before it swaps.
+NQ_DEV void cache_add_wide(u32* lo, u32* hi, u64 x) {
+    const u32 xl = (u32)x;
+    const u32 old = atomicAdd(lo, xl);
+    const u32 h = (u32)(x >> 32) + ((u32)(old + xl) < xl ? 1u : 0u);
+    if (h) atomicAdd(hi, h);
+}
+template <int OP> NQ_DEV void cache_mm32(u32* c, u64 x, u64 bias) {
+    const u32 v = (u32)(x - bias) + 1u;
+    if (OP == OP_MIN_I64 || OP == OP_MIN_U64) atomicMin(c, v); else atomicMax(c, v);
+}
+NQ_DEV void cache_or32(u32* c, u32 bits) {
+    if ((*(volatile u32*)c & bits) != bits) atomicOr(c, bits);
+}
+template <int OP> NQ_DEV void cache_word64(u64* c, u64 x) {
+    if (OP == OP_MIN_I64) { if ((i64)x < *(volatile i64*)c) atomicMin((i64*)c, (i64)x); }
+    else if (OP == OP_MAX_I64) { if ((i64)x > *(volatile i64*)c) atomicMax((i64*)c, (i64)x); }
+    else if (OP == OP_MIN_U64) { if (x < *(volatile u64*)c) atomicMin(c, x); }
+    else if (OP == OP_MAX_U64) { if (x > *(volatile u64*)c) atomicMax(c, x); }
+    else atomic_word<OP>(c, x);
+}
+
 // bit packing of group-key / DISTINCT-entry components into a 128-bit (lo,hi) key
 NQ_DEV void pack_bits(u64& lo, u64& hi, int& pos, u64 v, int nbits) {
     if (nbits == 0) return;

@@ -80,7 +80,7 @@ std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const 
     q->ops.n = (int)q->kp.word_ops.size();
     for (int w = 0; w < q->ops.n; ++w) q->ops.op[w] = q->kp.word_ops[w];
     if (have_device()) {
-        q->kernel = jit_load(q->kp.source, q->kp.dyn_smem);
+        q->kernel = jit_load(q->kp.source, q->kp.dyn_smem, q->kp.block);
         CK(cudaStreamCreateWithFlags(&q->own_stream, cudaStreamNonBlocking));
         q->stream = q->own_stream;
         CK(cudaEventCreate(&q->ev0));
@@ -108,7 +108,8 @@ void Query::rebind(Table* t) {
 
 void Query::alloc_state() {
     const int W = ops.n;
-    i64 blocks_needed = std::max<i64>(1, (table->nrows + 1023) / 1024);
+    const i64 tile = (i64)kp.block * 4;
+    i64 blocks_needed = std::max<i64>(1, (table->nrows + tile - 1) / tile);
     grid = (int)std::min<i64>(blocks_needed, (i64)device_sm_count() * kernel->max_blocks_per_sm);
     if (grid > 1280) grid = 1280;  // the last block folds at most 5 x 256 float partials per word
     if (kp.mode == MODE_UNGROUPED) {
@@ -469,8 +470,8 @@ std::unique_ptr<Result> Query::finalize() {
                 SumState s;
                 if (ap.w_isum >= 0) s.itotal = (i64)w[ap.w_isum];
                 else if (ap.w_ilo >= 0) s.itotal = (((__int128)(i64)w[ap.w_ihi]) << 32) + (__int128)w[ap.w_ilo];
-                if (ap.w_nonneg >= 0) s.n_nonneg = w[ap.w_nonneg];
                 if (ap.w_neg >= 0) s.n_neg = w[ap.w_neg];
+                if (ap.w_nint >= 0) s.n_nonneg = w[ap.w_nint] - s.n_neg;
                 if (ap.w_nflt >= 0) s.n_flt = w[ap.w_nflt];
                 if (ap.w_fsum >= 0) memcpy(&s.fsum, &w[ap.w_fsum], 8);
                 HValue sv = sum_value(s, false);
@@ -478,7 +479,7 @@ std::unique_ptr<Result> Query::finalize() {
                 else out = new_num(sv.num() / (double)(s.n_nonneg + s.n_neg + s.n_flt));
             } else {
                 bool mn = ap.kind == AggKind::MIN;
-                u64 seen = w[ap.w_seen];
+                const u64 seen = ap.w_seen >= 0 ? w[ap.w_seen] : (w[ap.w_seen_cnt] ? bit(ap.seen_class) : 0);
                 auto number = [&]() -> HValue {
                     bool hi = seen & bit(C_INT), hf = seen & bit(C_FLOAT);
                     i64 iv = ap.w_mi >= 0 ? (i64)w[ap.w_mi] : 0;

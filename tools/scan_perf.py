@@ -110,8 +110,8 @@ def main():
             info = qs[0].info
             us = sorted(ns)[len(ns) // 2] / 1e3
             gbs = info["scan_bytes_per_row"] * n / (us * 1e3)
-            print("%-20s rows=%-10d mode=%-20s regs=%-3d grid=%-5d B/row=%-3d kernel=%9.1f us  %7.1f GB/s  %.3e rows/s  wall/step=%.1f us groups=%d" % (
-                name, n, info["mode"], info["registers"], info["grid"], info["scan_bytes_per_row"], us, gbs, n / (us * 1e-6), wall * 1e6, r.num_groups))
+            print("%-20s rows=%-10d mode=%-20s regs=%-3d grid=%-5d blk=%-4d B/row=%-3d kernel=%9.1f us  %7.1f GB/s  %.3e rows/s  wall/step=%.1f us groups=%d" % (
+                name, n, info["mode"], info["registers"], info["grid"], info["block"], info["scan_bytes_per_row"], us, gbs, n / (us * 1e-6), wall * 1e6, r.num_groups))
             sys.stdout.flush()
             del qs, tabs
 
