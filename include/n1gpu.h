@@ -83,6 +83,12 @@ int n1gpu_table_load_dir(n1gpu_table* t, const char* dir, int threads);
  * (ndict strings, string i = blob[off[i], off[i+1])), or NULL.  Buffers are copied.                 */
 int n1gpu_table_set_column(n1gpu_table* t, int col, int width, const void* payload, const uint8_t* tags,
                            int64_t nrows, const char* dict_blob, const int64_t* dict_offsets, int64_t ndict);
+/* The same for a column that already lives in DEVICE memory (dev_payload / dev_tags are device pointers of the
+ * current device; copied device-to-device into the table's padded arrays).  Integral floats are canonicalised
+ * and the column statistics computed by kernels; there is no host staging.  All columns of a table must be set
+ * the same way (host or device).  The dictionary still comes from host memory.                        */
+int n1gpu_table_set_column_device(n1gpu_table* t, int col, int width, const void* dev_payload, const uint8_t* dev_tags,
+                                  int64_t nrows, const char* dict_blob, const int64_t* dict_offsets, int64_t ndict);
 /* Builds dictionaries and column statistics, uploads the columns to HBM.  After seal the table is
  * immutable and may be shared by any number of queries.                                             */
 int n1gpu_table_seal(n1gpu_table* t);

@@ -41,6 +41,7 @@ _SIGS = {
     "n1gpu_table_append_json": (C.c_int, [_P, C.c_char_p, _I64P, C.c_int64, C.c_int]),
     "n1gpu_table_load_dir": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "n1gpu_table_set_column": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int64, C.c_char_p, _I64P, C.c_int64]),
+    "n1gpu_table_set_column_device": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int64, C.c_char_p, _I64P, C.c_int64]),
     "n1gpu_table_seal": (C.c_int, [_P]),
     "n1gpu_table_num_rows": (C.c_int64, [_P]),
     "n1gpu_table_num_columns": (C.c_int, [_P]),

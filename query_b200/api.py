@@ -115,6 +115,32 @@ class Table:
             a.shape[0], blob, offs.ctypes.data_as(_lib._I64P) if offs is not None else None, nd))
         return self
 
+    def set_column_device(self, col, payload, tags=None, dictionary=None):
+        """Pre-shredded column held in device memory: payload / tags are CUDA tensors (torch) of dtype int64 / float64
+        (width 8) or int32 (width 4: string ranks) and uint8; copied device-to-device, no host staging."""
+        idx = col if isinstance(col, int) else self.find_column(col)
+        if not payload.is_cuda or not payload.is_contiguous():
+            raise TypeError("payload must be a contiguous CUDA tensor")
+        width = {8: 8, 4: 4}.get(payload.element_size())
+        if width is None:
+            raise TypeError("payload dtype %s" % payload.dtype)
+        if tags is not None and (not tags.is_cuda or not tags.is_contiguous() or tags.element_size() != 1):
+            raise TypeError("tags must be a contiguous CUDA uint8 tensor")
+        blob, offs, nd = None, None, 0
+        if dictionary is not None:
+            enc = [s.encode("utf-8") if isinstance(s, str) else s for s in dictionary]
+            offs = np.zeros(len(enc) + 1, dtype=np.int64)
+            if enc:
+                np.cumsum([len(e) for e in enc], out=offs[1:])
+            blob = b"".join(enc)
+            nd = len(enc)
+        import torch
+        torch.cuda.current_stream().synchronize()  # the producer of the tensors has finished
+        check(lib().n1gpu_table_set_column_device(
+            self._h, idx, width, C.c_void_p(payload.data_ptr()), C.c_void_p(tags.data_ptr()) if tags is not None else None,
+            payload.shape[0], blob, offs.ctypes.data_as(_lib._I64P) if offs is not None else None, nd))
+        return self
+
     def peek(self, col):
         """(payload int64[nrows], tags uint8[nrows]) of a staged column (before seal)."""
         idx = col if isinstance(col, int) else self.find_column(col)

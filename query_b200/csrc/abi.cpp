@@ -71,6 +71,13 @@ int n1gpu_table_set_column(n1gpu_table* t, int col, int width, const void* paylo
                            const char* dict_blob, const int64_t* dict_offsets, int64_t ndict) {
     return guard([&] { REQUIRE(t); REQUIRE(payload || nrows == 0); t->t.set_column(col, width, payload, tags, nrows, dict_blob, (const i64*)dict_offsets, ndict); });
 }
+int n1gpu_table_set_column_device(n1gpu_table* t, int col, int width, const void* dev_payload, const uint8_t* dev_tags, int64_t nrows,
+                                  const char* dict_blob, const int64_t* dict_offsets, int64_t ndict) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(dev_payload || nrows == 0);
+        t->t.set_column_device(col, width, dev_payload, dev_tags, nrows, dict_blob, (const i64*)dict_offsets, ndict);
+    });
+}
 int n1gpu_table_seal(n1gpu_table* t) {
     return guard([&] { REQUIRE(t); t->t.seal(); });
 }

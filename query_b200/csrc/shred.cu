@@ -305,7 +305,7 @@ __global__ void k_col_stats(const u8* __restrict__ tags, const i64* __restrict__
     for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (i64)gridDim.x * blockDim.x) {
         const int t = tags[row];
         mask |= 1ULL << t;
-        if (t == C_INT) { const i64 v = payload[row]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+        if (t == C_INT && payload) { const i64 v = payload[row]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
         else if (t == C_FLOAT) hasf = 1;
     }
     __shared__ u64 scratch[32];
@@ -318,6 +318,14 @@ __global__ void k_col_stats(const u8* __restrict__ tags, const i64* __restrict__
         atomicMin((i64*)&stats[1], (i64)rmn);
         atomicMax((i64*)&stats[2], (i64)rmx);
         atomicOr(&stats[3], hasf);
+    }
+}
+// pre-shredded input may hold integral floats: value.NewValue turns them into ints (value/value.go:377-382)
+__global__ void k_canon_floats(u8* tags, i64* payload, i64 nrows) {
+    for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (i64)gridDim.x * blockDim.x) {
+        if (tags[row] != C_FLOAT) continue;
+        const double d = __longlong_as_double(payload[row]);
+        if (::f_is_int(d)) { tags[row] = C_INT; payload[row] = ::go_i64(d); }
     }
 }
 // host fix-ups: (row, tag, payload) triples for one column
@@ -359,6 +367,12 @@ void launch_dict_remap(const u8* tags, const i64* slots, i64* payload, u32* out3
 }
 void launch_col_stats(const u8* tags, const i64* payload, i64 nrows, u64* stats, cudaStream_t s) {
     k_col_stats<<<sgrid(nrows, 256) > 592 ? 592 : sgrid(nrows, 256), 256, 0, s>>>(tags, payload, nrows, stats);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_canon_floats(u8* tags, i64* payload, i64 nrows, cudaStream_t s) {
+    if (nrows == 0) return;
+    k_canon_floats<<<sgrid(nrows, 256), 256, 0, s>>>(tags, payload, nrows);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }

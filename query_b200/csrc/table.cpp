@@ -306,6 +306,8 @@ void Table::set_column(int c, int width, const void* payload, const u8* tags, i6
     if (n < 0) N1_THROW(N1GPU_E_INVALID, "negative row count");
     if (appended) N1_THROW(N1GPU_E_INVALID, "cannot mix appended documents and pre-shredded columns");
     for (auto& other : cols)
+        if (other.device_set) N1_THROW(N1GPU_E_INVALID, "cannot mix host and device columns in one table");
+    for (auto& other : cols)
         if (&other != &cols[c] && !other.tags.empty() && (i64)other.tags.size() != n)
             N1_THROW(N1GPU_E_INVALID, "column lengths differ (%lld vs %lld)", (long long)other.tags.size(), (long long)n);
     Column& col = cols[c];
@@ -348,7 +350,15 @@ int Table::scan_bytes(int c) const {
 
 void Table::seal() {
     if (sealed) return;
-    if (device_shredded) { sealed = true; return; }  // columns, dictionaries and statistics already final in HBM
+    if (device_shredded) {  // columns, dictionaries and statistics already final in HBM
+        bool any_set = false;
+        for (auto& col : cols) any_set = any_set || col.device_set;
+        if (any_set)
+            for (auto& col : cols)
+                if (!col.device_set) N1_THROW(N1GPU_E_INVALID, "column %s was never set", join_path(col.path, '.').c_str());
+        sealed = true;
+        return;
+    }
     double t0 = now_sec();
     for (auto& col : cols)
         if ((i64)col.tags.size() != nrows) N1_THROW(N1GPU_E_INVALID, "column %s has %lld rows, table has %lld",

@@ -35,6 +35,7 @@ struct Column {
     bool stats_forced = false;
     int width = 8;                       // device payload width: 8, 4 or 0
     DevBuf d_payload, d_tags;
+    bool device_set = false;             // filled by set_column_device
 };
 
 struct Table {
@@ -55,6 +56,11 @@ struct Table {
     void load_dir(const std::string& dir, int threads);
     void set_column(int col, int width, const void* payload, const u8* tags, i64 nrows, const char* blob,
                     const i64* offs, i64 ndict);
+    // The same for a column that already lives in device memory (caller-owned device pointers, copied device to
+    // device): no host staging at all; statistics are computed by a kernel.  Every column of the table must then
+    // be set this way.
+    void set_column_device(int col, int width, const void* dev_payload, const u8* dev_tags, i64 nrows, const char* blob,
+                           const i64* offs, i64 ndict);
     void build_dictionary(int col);  // local strings -> sorted dict, codes -> ranks
     void seal();
     int scan_bytes(int col) const;

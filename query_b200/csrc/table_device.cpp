@@ -265,4 +265,66 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     shred_sec += now_sec() - t0;
 }
 
+void Table::set_column_device(int c, int width, const void* dev_payload, const u8* dev_tags, i64 n, const char* blob,
+                              const i64* offs, i64 ndict) {
+    if (!have_device()) N1_THROW(N1GPU_E_CUDA, "no CUDA device: device columns need one");
+    if (sealed) N1_THROW(N1GPU_E_INVALID, "table is sealed");
+    if (c < 0 || c >= (int)cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column %d", c);
+    if (width != 8 && width != 4) N1_THROW(N1GPU_E_INVALID, "payload width must be 8 or 4");
+    if (n < 0) N1_THROW(N1GPU_E_INVALID, "negative row count");
+    if (appended) N1_THROW(N1GPU_E_INVALID, "cannot mix appended documents and pre-shredded columns");
+    for (auto& other : cols) {
+        if (&other == &cols[c]) continue;
+        if (!other.tags.empty()) N1_THROW(N1GPU_E_INVALID, "cannot mix host and device columns in one table");
+        if (other.device_set && nrows != n) N1_THROW(N1GPU_E_INVALID, "column lengths differ (%lld vs %lld)", (long long)nrows, (long long)n);
+    }
+    Column& col = cols[c];
+    nrows = n;
+    i64 pad = padded_rows();
+    if (pad == 0) pad = ROW_PAD;
+    col.d_tags.alloc((size_t)pad);
+    CK(cudaMemset(col.d_tags.p, C_MISSING, (size_t)pad));
+    if (n) {
+        if (dev_tags) CK(cudaMemcpy(col.d_tags.p, dev_tags, (size_t)n, cudaMemcpyDeviceToDevice));
+        else CK(cudaMemset(col.d_tags.p, width == 8 ? C_INT : C_STRING, (size_t)n));
+    }
+    col.d_payload.alloc((size_t)pad * width);
+    CK(cudaMemset(col.d_payload.p, 0, (size_t)pad * width));
+    if (n) CK(cudaMemcpy(col.d_payload.p, dev_payload, (size_t)n * width, cudaMemcpyDeviceToDevice));
+    col.dict.clear();
+    if (blob && offs) {
+        for (i64 i = 0; i < ndict; ++i) col.dict.emplace_back(blob + offs[i], blob + offs[i + 1]);
+        for (size_t i = 1; i < col.dict.size(); ++i)
+            if (!(col.dict[i - 1] < col.dict[i])) N1_THROW(N1GPU_E_INVALID, "dictionary must be sorted bytewise and unique");
+    }
+    col.codes_are_ranks = true;
+    // canonical numbers + statistics, on the device
+    if (width == 8) launch_canon_floats(col.d_tags.as<u8>(), col.d_payload.as<i64>(), n, nullptr);
+    DevBuf d_stats;
+    d_stats.alloc(32);
+    u64 h_stats[4] = {0, (u64)INT64_MAX, (u64)INT64_MIN, 0};
+    CK(cudaMemcpy(d_stats.p, h_stats, 32, cudaMemcpyHostToDevice));
+    // a 4-byte column holds string ranks only: the kernel reads payload words of INT rows, of which there are none
+    if (n) launch_col_stats(col.d_tags.as<u8>(), width == 8 ? col.d_payload.as<i64>() : nullptr, n, d_stats.as<u64>(), nullptr);
+    CK(cudaMemcpy(h_stats, d_stats.p, 32, cudaMemcpyDeviceToHost));
+    ColumnStats st;
+    st.class_mask = (u32)h_stats[0];
+    if (st.class_mask >> (C_OTHER + 1)) N1_THROW(N1GPU_E_INVALID, "bad class byte in column %d", c);
+    if (width == 4 && (st.class_mask & M_NUM)) N1_THROW(N1GPU_E_INVALID, "a 4-byte column cannot hold numbers");
+    if (width == 8 && !(st.class_mask & M_NUM) && (st.class_mask & bit(C_STRING)))
+        N1_THROW(N1GPU_E_INVALID, "a column of strings only must be passed as 4-byte ranks");
+    st.has_int = (st.class_mask & bit(C_INT)) != 0;
+    st.int_min = st.has_int ? (i64)h_stats[1] : 0;
+    st.int_max = st.has_int ? (i64)h_stats[2] : 0;
+    st.has_float = h_stats[3] != 0;
+    st.ndict = (i64)col.dict.size();
+    st.empty_rank = (!col.dict.empty() && col.dict[0].empty()) ? 0 : -1;
+    if (!col.stats_forced) col.stats = st;
+    const u32 m = col.stats.class_mask;
+    col.width = (m & M_NUM) ? 8 : ((m & bit(C_STRING)) ? 4 : 0);
+    if (col.width == 0) col.d_payload.alloc(256);
+    col.device_set = true;
+    device_shredded = true;  // nothing left to do at seal
+}
+
 }  // namespace n1
