@@ -358,17 +358,11 @@ int n1gpu_result_num_aggregates(const n1gpu_result* r) { return r ? r->r->naggs 
 int n1gpu_result_fetch(const n1gpu_result* r, uint8_t* key_cls, int64_t* key_val, uint8_t* agg_cls, int64_t* agg_val) {
     return guard([&] {
         REQUIRE(r);
-        Result& R = *r->r;
-        R.strings.clear();
-        auto put = [&](const HValue& v, uint8_t* cls, int64_t* val, size_t i) {
-            if (cls) cls[i] = v.cls;
-            if (val) {
-                if (v.cls == C_STRING) { val[i] = (int64_t)R.strings.size(); R.strings.push_back(v.s); }
-                else val[i] = v.bits;
-            }
-        };
-        for (size_t i = 0; i < R.keys.size(); ++i) put(R.keys[i], key_cls, key_val, i);
-        for (size_t i = 0; i < R.aggs.size(); ++i) put(R.aggs[i], agg_cls, agg_val, i);
+        const Result& R = *r->r;
+        if (key_cls && !R.key_cls.empty()) memcpy(key_cls, R.key_cls.data(), R.key_cls.size());
+        if (key_val && !R.key_val.empty()) memcpy(key_val, R.key_val.data(), R.key_val.size() * 8);
+        if (agg_cls && !R.agg_cls.empty()) memcpy(agg_cls, R.agg_cls.data(), R.agg_cls.size());
+        if (agg_val && !R.agg_val.empty()) memcpy(agg_val, R.agg_val.data(), R.agg_val.size() * 8);
     });
 }
 int n1gpu_result_string(const n1gpu_result* r, int64_t index, const char** ptr, int64_t* len) {

@@ -431,6 +431,13 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         kp.entry_bits = kp.abits + kp.key_bits + mx;
         if (kp.entry_bits > 127) N1_THROW(N1GPU_E_INELIGIBLE, "DISTINCT entry needs %d bits (> 127)", kp.entry_bits);
         kp.set128 = kp.entry_bits > 63;
+        // An entry of few bits indexes a bitmap directly: one fire-and-forget atomicOr per row instead of a hash probe
+        // with a dependent compare-and-swap, and 2^bits / 8 bytes instead of 16 bytes per row - config 4's 2^30
+        // entries are 128 MiB, about the size of the L2, where the hash set is 4 GiB of random DRAM sectors.
+        // Chosen when the bitmap is no larger than the hash set would be.
+        const char* nb = getenv("N1GPU_NO_BITMAP");
+        const double bitmap_bytes = kp.entry_bits <= 36 ? (double)((u64)1 << kp.entry_bits) / 8.0 : 1e30;
+        kp.set_bitmap = !(nb && *nb == '1') && bitmap_bytes <= std::max(65536.0, 16.0 * (double)std::max<i64>(t.nrows, 1) * kp.ndistinct);
     }
 
     // ---- row code -----------------------------------------------------------------------------------------------
@@ -503,7 +510,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 if (kp.key_bits > 64) g.line(strf("pack_bits(elo, ehi, epos, khi, %d);", kp.key_bits - 64));
             }
             emit_pack(g, ap.dcomp, cv, "elo", "ehi", "epos");
-            if (kp.set128) g.line("if (table_insert128((ulonglong2*)p.set_keys, p.set_mask, elo, ehi, nullptr) < 0) p.status[0] = 2;");
+            if (kp.set_bitmap) g.line("atomicOr(&((u32*)p.set_keys)[elo >> 5], 1u << (elo & 31));  // DISTINCT bitmap");
+            else if (kp.set128) g.line("if (table_insert128((ulonglong2*)p.set_keys, p.set_mask, elo, ehi, nullptr) < 0) p.status[0] = 2;");
             else g.line("if (table_insert64(p.set_keys, p.set_mask, elo, nullptr) < 0) p.status[0] = 2;");
             g.ind = save_ind + "    ";
             g.line("}");

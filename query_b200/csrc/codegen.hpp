@@ -61,6 +61,7 @@ struct KernelPlan {
     std::vector<AggPlan> aggs;
     int ndistinct = 0, abits = 0, entry_bits = 0;
     bool set128 = false;
+    bool set_bitmap = false;     // DISTINCT entries are few bits: the set is a bitmap indexed by the entry (no hashing)
     std::vector<int> used_cols;
     int scan_bytes_per_row = 0;
     std::string source;

@@ -360,7 +360,7 @@ std::string ResultToJSON(const Result& r) {
         Tree doc;
         std::string keys = "[";
         for (int k = 0; k < r.nkeys; ++k) {
-            const HValue& v = r.keys[(size_t)g * r.nkeys + k];
+            const HValue v = r.key(g, k);
             if (k) keys += ",";
             keys += v.cls == C_MISSING ? "{\"#missing\":true}" : value_json(v);
             if (v.cls == C_MISSING) continue;  // MISSING key: field absent (group_util.go:28-30)
@@ -378,7 +378,7 @@ std::string ResultToJSON(const Result& r) {
         for (int a = 0; a < r.naggs; ++a) {
             if (a) s += ",";
             json::quote(r.agg_texts[(size_t)a], s);
-            s += ":" + value_json(r.aggs[(size_t)g * r.naggs + a]);
+            s += ":" + value_json(r.agg(g, a));
         }
         s += "},\"group_keys\":" + keys + "}";
     }

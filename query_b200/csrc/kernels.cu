@@ -59,8 +59,23 @@ __device__ __forceinline__ bool slot_key(int kw, const u64* keys, const u64* acc
 
 // pass 1: count live slots per owner.  gk_pos/gk_bits: where the group key sits inside the stored key
 // (DISTINCT entries embed it after the aggregate id; group tables store it at bit 0).
+// kw == 4: `keys` is a DISTINCT bitmap of `cap` bits (a multiple of 64); bit e set = entry e present.
 __global__ void k_count_owners(int kw, const u64* keys, const u64* acc, u64 cap, int nranks, int gk_pos, int gk_bits,
                                unsigned long long* counts) {
+    if (kw == 4) {
+        for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < (cap >> 6); w += (u64)gridDim.x * blockDim.x) {
+            u64 bits = keys[w];
+            if (nranks <= 1) { if (bits) atomicAdd(&counts[0], (unsigned long long)__popcll(bits)); continue; }
+            while (bits) {
+                const u64 lo = (w << 6) | (u64)(__ffsll((long long)bits) - 1);
+                bits &= bits - 1;
+                u64 glo, ghi;
+                extract_bits(lo, 0, gk_pos, gk_bits, glo, ghi);
+                atomicAdd(&counts[owner_of(glo, ghi, nranks)], 1ULL);
+            }
+        }
+        return;
+    }
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
         u64 lo, hi;
         if (!slot_key(kw, keys, acc, i, lo, hi)) continue;
@@ -74,6 +89,21 @@ __global__ void k_count_owners(int kw, const u64* keys, const u64* acc, u64 cap,
 __global__ void k_export_records(int kw, const u64* keys, const u64* acc, u64 cap, int W, int nranks, int gk_pos, int gk_bits,
                                  unsigned long long* cursor, u64* out, u64 out_cap) {
     const int rw = 2 + W;
+    if (kw == 4) {
+        for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < (cap >> 6); w += (u64)gridDim.x * blockDim.x) {
+            u64 bits = keys[w];
+            while (bits) {
+                const u64 lo = (w << 6) | (u64)(__ffsll((long long)bits) - 1);
+                bits &= bits - 1;
+                u64 glo, ghi;
+                extract_bits(lo, 0, gk_pos, gk_bits, glo, ghi);
+                const u64 at = atomicAdd(&cursor[owner_of(glo, ghi, nranks)], 1ULL);
+                if (at >= out_cap) continue;
+                out[at * rw] = lo; out[at * rw + 1] = 0;
+            }
+        }
+        return;
+    }
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
         u64 lo, hi;
         if (!slot_key(kw, keys, acc, i, lo, hi)) continue;
@@ -92,6 +122,11 @@ __global__ void k_merge_records(int kw, u64* keys, u64* acc, u64 cap, OpsArr ops
     const int rw = 2 + ops.n;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const u64* r = recs + i * rw;
+        if (kw == 4) {  // DISTINCT bitmap: the entry is its own index
+            if (r[0] >= cap || r[1] != 0) { status[0] = 1; continue; }
+            atomicOr(&keys[r[0] >> 6], 1ULL << (r[0] & 63));
+            continue;
+        }
         i64 slot;
         if (kw == 0) slot = (i64)r[0];
         else if (kw == 1) slot = table_insert64(keys, cap - 1, r[0], nullptr);
@@ -114,12 +149,9 @@ __device__ __forceinline__ u64 take_bits(unsigned __int128& v, int n) {
     v >>= n;
     return r;
 }
-__global__ void k_distinct_finalize(const u64* __restrict__ set_keys, u64 set_cap, int set128, int abits, int key_bits, int kw,
-                                    const u64* __restrict__ keys, u64 cap, u64* acc, DistinctDescs D) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < set_cap; i += (u64)gridDim.x * blockDim.x) {
-        u64 lo, hi;
-        if (set128) { lo = set_keys[2 * i]; hi = set_keys[2 * i + 1]; if (lo == NQ_U64_MAX && hi == NQ_U64_MAX) continue; }
-        else { lo = set_keys[i]; hi = 0; if (lo == NQ_U64_MAX) continue; }
+__device__ __forceinline__ void distinct_entry(u64 lo, u64 hi, int abits, int key_bits, int kw, const u64* __restrict__ keys, u64 cap,
+                                               u64* acc, const DistinctDescs& D) {
+    {
         unsigned __int128 v = ((unsigned __int128)hi << 64) | lo;
         const int sid = (int)take_bits(v, abits);
         const u64 klo = take_bits(v, key_bits < 64 ? key_bits : 64);
@@ -129,7 +161,7 @@ __global__ void k_distinct_finalize(const u64* __restrict__ set_keys, u64 set_ca
         else if (kw == 0) slot = (i64)klo;
         else if (kw == 1) slot = table_find64(keys, cap - 1, klo);
         else slot = table_find128((const ulonglong2*)keys, cap - 1, klo, khi);
-        if (slot < 0 || (u64)slot >= cap) continue;  // group owned by another rank
+        if (slot < 0 || (u64)slot >= cap) return;  // group owned by another rank
         bool decoded = false;
         int cls = C_MISSING;
         u64 pv = 0;
@@ -154,6 +186,27 @@ __global__ void k_distinct_finalize(const u64* __restrict__ set_keys, u64 set_ca
                 atomicAdd(&acc[(u64)d.w_nflt * cap + (u64)slot], 1ULL);
             }
         }
+    }
+}
+// set_kind: 0 hash set of 64-bit entries, 1 of 128-bit entries, 2 bitmap of set_cap bits
+__global__ void k_distinct_finalize(const u64* __restrict__ set_keys, u64 set_cap, int set_kind, int abits, int key_bits, int kw,
+                                    const u64* __restrict__ keys, u64 cap, u64* acc, DistinctDescs D) {
+    if (set_kind == 2) {
+        for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < (set_cap >> 6); w += (u64)gridDim.x * blockDim.x) {
+            u64 bits = set_keys[w];
+            while (bits) {
+                const u64 lo = (w << 6) | (u64)(__ffsll((long long)bits) - 1);
+                bits &= bits - 1;
+                distinct_entry(lo, 0, abits, key_bits, kw, keys, cap, acc, D);
+            }
+        }
+        return;
+    }
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < set_cap; i += (u64)gridDim.x * blockDim.x) {
+        u64 lo, hi;
+        if (set_kind == 1) { lo = set_keys[2 * i]; hi = set_keys[2 * i + 1]; if (lo == NQ_U64_MAX && hi == NQ_U64_MAX) continue; }
+        else { lo = set_keys[i]; hi = 0; if (lo == NQ_U64_MAX) continue; }
+        distinct_entry(lo, hi, abits, key_bits, kw, keys, cap, acc, D);
     }
 }
 
@@ -209,7 +262,7 @@ static int grid_for(u64 n) {
 
 void launch_distinct_finalize(const u64* set_keys, u64 set_cap, int set128, int abits, int key_bits, int kw, const u64* keys, u64 cap,
                               u64* acc, const DistinctDescs& D, cudaStream_t s) {
-    k_distinct_finalize<<<grid_for(set_cap), 256, 0, s>>>(set_keys, set_cap, set128, abits, key_bits, kw, keys, cap, acc, D);
+    k_distinct_finalize<<<grid_for(set128 == 2 ? set_cap >> 6 : set_cap), 256, 0, s>>>(set_keys, set_cap, set128, abits, key_bits, kw, keys, cap, acc, D);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }
@@ -241,13 +294,13 @@ void launch_reduce_partials(const u64* partials, int nblocks, const OpsArr& ops,
 }
 void launch_count_owners(int kw, const u64* keys, const u64* acc, u64 cap, int nranks, int gk_pos, int gk_bits,
                          unsigned long long* counts, cudaStream_t s) {
-    k_count_owners<<<grid_for(cap), 256, 0, s>>>(kw, keys, acc, cap, nranks, gk_pos, gk_bits, counts);
+    k_count_owners<<<grid_for(kw == 4 ? cap >> 6 : cap), 256, 0, s>>>(kw, keys, acc, cap, nranks, gk_pos, gk_bits, counts);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }
 void launch_export_records(int kw, const u64* keys, const u64* acc, u64 cap, int W, int nranks, int gk_pos, int gk_bits,
                            unsigned long long* cursor, u64* out, u64 out_cap, cudaStream_t s) {
-    k_export_records<<<grid_for(cap), 256, 0, s>>>(kw, keys, acc, cap, W, nranks, gk_pos, gk_bits, cursor, out, out_cap);
+    k_export_records<<<grid_for(kw == 4 ? cap >> 6 : cap), 256, 0, s>>>(kw, keys, acc, cap, W, nranks, gk_pos, gk_bits, cursor, out, out_cap);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }

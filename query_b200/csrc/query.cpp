@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
 #include <unordered_map>
 
 namespace n1 {
@@ -131,11 +132,14 @@ void Query::alloc_state() {
     }
     d_acc.ensure((size_t)cap * W * 8);
     if (kp.ndistinct) {
-        if (set_cap == 0) {
+        if (kp.set_bitmap) set_cap = std::max<u64>(64, (u64)1 << kp.entry_bits);  // bits
+        else if (set_cap == 0) {
+            // every row can add one entry per set: at least twice as many slots (load <= 0.5 keeps linear probing to
+            // ~1.5 slots per insert; at 0.7 it is over 5, each a DRAM sector) - HBM is plentiful, probes are not
             double want = 2.0 * (double)std::max<i64>(table->nrows, 1) * kp.ndistinct;
-            set_cap = pow2_at_least((u64)std::min(std::max(want, 1024.0), 268435456.0));
+            set_cap = pow2_at_least((u64)std::min(std::max(want, 1024.0), 4294967296.0));
         }
-        d_set.ensure((size_t)set_cap * (kp.set128 ? 16 : 8));
+        d_set.ensure(set_bytes());
     }
     d_status.ensure(64);
     h_status.ensure(64);
@@ -158,7 +162,7 @@ void Query::reset_state() {
     if (uses_status()) CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
     if (kp.mode != MODE_UNGROUPED) launch_init_words(d_acc.as<u64>(), cap, ops, stream);
     if (kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128) CK(cudaMemsetAsync(d_keys.p, 0xff, (size_t)cap * (kp.mode == MODE_HASH128 ? 16 : 8), stream));
-    if (kp.ndistinct) CK(cudaMemsetAsync(d_set.p, 0xff, (size_t)set_cap * (kp.set128 ? 16 : 8), stream));
+    if (kp.ndistinct) CK(cudaMemsetAsync(d_set.p, kp.set_bitmap ? 0 : 0xff, set_bytes(), stream));
 }
 
 void Query::launch_scan() {
@@ -230,7 +234,7 @@ bool Query::wait_scan() {
     if (st == 2) {
         if (set_cap >= ((u64)1 << 32)) N1_THROW(N1GPU_E_NOMEM, "DISTINCT set would exceed 2^32 slots");
         set_cap *= 4;
-        d_set.alloc((size_t)set_cap * (kp.set128 ? 16 : 8));
+        d_set.alloc(set_bytes());
         return false;
     }
     host_acc_valid = kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE;
@@ -270,14 +274,14 @@ void Query::partial_counts(i64* ngroups, i64* ndistinct) {
     if (kp.mode == MODE_UNGROUPED && !ungrouped_live) c[0] = 0;
     *ngroups = c[0];
     i64 d[1] = {0};
-    if (kp.ndistinct) count_and_export(*this, kp.set128 ? 2 : 1, d_set.as<u64>(), nullptr, set_cap, 0, 1, kp.abits, kp.key_bits, nullptr, 0, d);
+    if (kp.ndistinct) count_and_export(*this, set_kw(), d_set.as<u64>(), nullptr, set_cap, 0, 1, kp.abits, kp.key_bits, nullptr, 0, d);
     *ndistinct = d[0];
 }
 
 void Query::partial_export(int nranks, void* dev_records, i64 cap_records, i64* counts, void* dev_distinct, i64 cap_distinct, i64* dcounts) {
     count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, ops.n, nranks, 0, kp.key_bits, (u64*)dev_records, cap_records, counts);
     if (kp.ndistinct)
-        count_and_export(*this, kp.set128 ? 2 : 1, d_set.as<u64>(), nullptr, set_cap, 0, nranks, kp.abits, kp.key_bits, (u64*)dev_distinct, cap_distinct, dcounts);
+        count_and_export(*this, set_kw(), d_set.as<u64>(), nullptr, set_cap, 0, nranks, kp.abits, kp.key_bits, (u64*)dev_distinct, cap_distinct, dcounts);
     else for (int r = 0; r < nranks; ++r) dcounts[r] = 0;
 }
 
@@ -299,7 +303,7 @@ void Query::partial_import(const void* dev_records, i64 n, const void* dev_disti
         if (nd > 0) {
             OpsArr none{};
             none.n = 0;
-            launch_merge_records(kp.set128 ? 2 : 1, d_set.as<u64>(), nullptr, set_cap, none, (const u64*)dev_distinct, (u64)nd, d_status.as<int>() + 1, stream);
+            launch_merge_records(set_kw(), d_set.as<u64>(), nullptr, set_cap, none, (const u64*)dev_distinct, (u64)nd, d_status.as<int>() + 1, stream);
         }
         CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -323,6 +327,9 @@ struct BitReader {
     }
 };
 
+// a string of a result, until finalize() resolves it: (dictionary column, rank)
+HValue str_ref(int col, u64 rank) { HValue v; v.cls = C_STRING; v.bits = (i64)(((u64)col << 40) | (rank & 0xffffffffffULL)); return v; }
+
 HValue decode_comp(const Table& t, const PackComp& pc, BitReader& br) {
     u64 ci = br.take(pc.cbits);
     u64 pv = br.take(pc.pbits);
@@ -330,10 +337,7 @@ HValue decode_comp(const Table& t, const PackComp& pc, BitReader& br) {
     switch (cls) {
         case C_INT: return HValue::integer(pc.biased ? (i64)(pv + (u64)pc.bias) : (i64)pv);
         case C_FLOAT: { HValue v; v.cls = C_FLOAT; v.bits = (i64)pv; return v; }
-        case C_STRING: {
-            const auto& d = t.cols[pc.dict_col].dict;
-            return HValue::str(pv < d.size() ? d[pv] : std::string());
-        }
+        case C_STRING: return str_ref(pc.dict_col, pv);
         case C_NULL: return HValue::null();
         case C_FALSE: return HValue::boolean(false);
         case C_TRUE: return HValue::boolean(true);
@@ -383,6 +387,9 @@ std::unique_ptr<Result> Query::finalize() {
     const int rw = 2 + W;
     std::vector<u64> recs;
     i64 ngroups = 0;
+    const bool trace = getenv("N1GPU_TRACE") != nullptr;
+    double tp = now_sec();
+    auto phase = [&](const char* name) { if (trace) { double t = now_sec(); fprintf(stderr, "[n1gpu finalize] %-22s %8.3f ms\n", name, (t - tp) * 1e3); tp = t; } };
     if (kp.ndistinct) {
         // DISTINCT aggregates are finalised on the device: every set entry adds itself to its group's result words
         DistinctDescs D{};
@@ -398,7 +405,7 @@ std::unique_ptr<Result> Query::finalize() {
             for (int w : {ap.w_cnt, ap.w_ilo, ap.w_ihi, ap.w_neg, ap.w_fsum, ap.w_nflt})
                 if (w >= 0) launch_fill_u64(d_acc.as<u64>() + (u64)w * cap, cap, 0, stream);  // idempotent finalize
         }
-        launch_distinct_finalize(d_set.as<u64>(), set_cap, kp.set128 ? 1 : 0, kp.abits, kp.key_bits, kw(), d_keys.as<u64>(), cap,
+        launch_distinct_finalize(d_set.as<u64>(), set_cap, kp.set_bitmap ? 2 : (kp.set128 ? 1 : 0), kp.abits, kp.key_bits, kw(), d_keys.as<u64>(), cap,
                                  d_acc.as<u64>(), D, stream);
         CK(cudaStreamSynchronize(stream));
     }
@@ -426,6 +433,7 @@ std::unique_ptr<Result> Query::finalize() {
         }
     }
 
+    phase("distinct + export");
     std::unique_ptr<Result> res(new Result());
     res->nkeys = (int)keys.size();
     res->naggs = (int)aggs.size();
@@ -438,14 +446,23 @@ std::unique_ptr<Result> Query::finalize() {
         if (k->kind == EK::FIELD && k->col >= 0) path = table->cols[k->col].path;
         res->key_paths.push_back(path);
     }
-    res->keys.resize((size_t)ngroups * res->nkeys);
-    res->aggs.resize((size_t)ngroups * res->naggs);
+    res->key_cls.resize((size_t)ngroups * res->nkeys);
+    res->key_val.resize((size_t)ngroups * res->nkeys);
+    res->agg_cls.resize((size_t)ngroups * res->naggs);
+    res->agg_val.resize((size_t)ngroups * res->naggs);
 
-    for (i64 g = 0; g < ngroups; ++g) {
+    phase("result allocation");
+    // ComputeFinal of every group; a large group table (config 4: 10^6 groups) is finalised by all host cores
+    auto final_range = [&](i64 g0, i64 g1) {
+    for (i64 g = g0; g < g1; ++g) {
         const u64* r = &recs[(size_t)g * rw];
         const u64* w = r + 2;
         BitReader br(r[0], r[1]);
-        for (int k = 0; k < res->nkeys; ++k) res->keys[(size_t)g * res->nkeys + k] = decode_comp(*table, kp.keys[k], br);
+        for (int k = 0; k < res->nkeys; ++k) {
+            const HValue kv = decode_comp(*table, kp.keys[k], br);
+            res->key_cls[(size_t)g * res->nkeys + k] = kv.cls;
+            res->key_val[(size_t)g * res->nkeys + k] = kv.bits;
+        }
         for (int a = 0; a < res->naggs; ++a) {
             const AggPlan& ap = kp.aggs[a];
             HValue out;
@@ -491,7 +508,7 @@ std::unique_ptr<Result> Query::finalize() {
                     }
                     return hi ? HValue::integer(iv) : HValue::flt(fv);
                 };
-                auto str = [&]() { const auto& d = table->cols[ap.dict_col].dict; u64 c = w[ap.w_ms]; return HValue::str(c < d.size() ? d[c] : std::string()); };
+                auto str = [&]() { return str_ref(ap.dict_col, w[ap.w_ms]); };
                 if (seen == 0) out = HValue::null();
                 else if (mn) {
                     if (seen & bit(C_FALSE)) out = HValue::boolean(false);
@@ -505,9 +522,44 @@ std::unique_ptr<Result> Query::finalize() {
                     else out = HValue::boolean(false);
                 }
             }
-            res->aggs[(size_t)g * res->naggs + a] = out;
+            res->agg_cls[(size_t)g * res->naggs + a] = out.cls;
+            res->agg_val[(size_t)g * res->naggs + a] = out.bits;
         }
     }
+    };
+    {
+        const int nthr = ngroups < 32768 ? 1 : (int)std::min<i64>(std::max(1u, std::thread::hardware_concurrency()), 32);
+        if (nthr <= 1) final_range(0, ngroups);
+        else {
+            std::vector<std::thread> pool;
+            std::vector<std::string> errs((size_t)nthr);
+            for (int t = 0; t < nthr; ++t)
+                pool.emplace_back([&, t] {
+                    try { final_range(ngroups * t / nthr, ngroups * (t + 1) / nthr); } catch (const std::exception& e) { errs[(size_t)t] = e.what(); }
+                });
+            for (auto& th : pool) th.join();
+            for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_INVALID, "%s", e.c_str());
+        }
+    }
+    {   // strings: (column, rank) references -> the result's own string table (it may outlive the table)
+        std::unordered_map<i64, i64> pool;
+        auto resolve = [&](std::vector<u8>& cls, std::vector<i64>& val) {
+            for (size_t i = 0; i < cls.size(); ++i) {
+                if (cls[i] != C_STRING) continue;
+                auto it = pool.find(val[i]);
+                if (it == pool.end()) {
+                    const auto& d = table->cols[(size_t)((u64)val[i] >> 40)].dict;
+                    const u64 rank = (u64)val[i] & 0xffffffffffULL;
+                    it = pool.emplace(val[i], (i64)res->strings.size()).first;
+                    res->strings.push_back(rank < d.size() ? d[rank] : std::string());
+                }
+                val[i] = it->second;
+            }
+        };
+        resolve(res->key_cls, res->key_val);
+        resolve(res->agg_cls, res->agg_val);
+    }
+    phase("ComputeFinal");
     i64 scan_bytes = (i64)kp.scan_bytes_per_row * table->nrows;
     res->stats[0] = table->nrows;
     res->stats[1] = ngroups;

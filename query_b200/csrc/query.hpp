@@ -14,9 +14,19 @@ namespace n1 {
 struct Result {
     int nkeys = 0, naggs = 0;
     i64 ngroups = 0;
-    std::vector<HValue> keys;  // [ngroups][nkeys]
-    std::vector<HValue> aggs;  // [ngroups][naggs]
-    std::vector<std::string> strings;  // string table filled by fetch()
+    // [ngroups][nkeys] / [ngroups][naggs] as class byte + 64-bit payload (int / float bits / index into `strings`):
+    // flat arrays, so that a million-group result costs two allocations, not four million string-carrying objects
+    std::vector<u8> key_cls, agg_cls;
+    std::vector<i64> key_val, agg_val;
+    std::vector<std::string> strings;
+    HValue value(u8 cls, i64 val) const {
+        HValue v;
+        v.cls = cls;
+        if (cls == C_STRING) v.s = strings[(size_t)val]; else v.bits = val;
+        return v;
+    }
+    HValue key(i64 g, int k) const { const size_t i = (size_t)g * nkeys + k; return value(key_cls[i], key_val[i]); }
+    HValue agg(i64 g, int a) const { const size_t i = (size_t)g * naggs + a; return value(agg_cls[i], agg_val[i]); }
     std::vector<std::string> agg_texts, key_texts;
     std::vector<std::vector<std::string>> key_paths;  // field path of each key (empty: computed key)
     std::string alias;
@@ -53,7 +63,9 @@ struct Query {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int grid = 0;
     u64 cap = 1;      // group slots (1 / dense slots / hash capacity)
-    u64 set_cap = 0;  // DISTINCT entry set capacity
+    u64 set_cap = 0;  // DISTINCT entry set capacity: hash slots, or bits when the set is a bitmap
+    size_t set_bytes() const { return kp.set_bitmap ? (size_t)(set_cap >> 3) : (size_t)set_cap * (kp.set128 ? 16 : 8); }
+    int set_kw() const { return kp.set_bitmap ? 4 : (kp.set128 ? 2 : 1); }  // how kernels.cu enumerates the set
     DevBuf d_partials, d_acc, d_accum, d_keys, d_set, d_status, d_counts, d_records, d_drecords, d_ticket;
     PinnedBuf h_status, h_counts, h_records, h_drecords;
     std::atomic<bool> cancelled{false};

@@ -20,11 +20,12 @@ __device__ __forceinline__ u32 draw(u32 h, u32 n, int skew) {
     return r < n ? r : n - 1;
 }
 
-enum { S_ADD32, S_ADD64, S_MIN32, S_MIN64, S_RMW64, S_RMW32, S_MATCH, S_CHECKMIN64, G_RED64, G_RED32, G_MIN64, G_ATOM64, G_CHECKMIN64, G_LD64, NKIND };
+enum { S_ADD32, S_ADD64, S_MIN32, S_MIN64, S_RMW64, S_RMW32, S_MATCH, S_CHECKMIN64, G_RED64, G_RED32, G_MIN64, G_ATOM64, G_CHECKMIN64, G_LD64, G_RED64_G4, G_RED64_G8, G_LD256, NKIND };
 const char* kname[NKIND] = {"smem atomicAdd u32", "smem atomicAdd u64 (CAS loop)", "smem atomicMin s32", "smem atomicMin s64 (CAS loop)",
                             "smem plain RMW u64 (racy)", "smem plain RMW u32 (racy)", "match_any + plain RMW u64", "smem load+compare, atomicMin s64 if smaller",
                             "global red.add u64", "global red.add u32", "global red.min s64", "global atom.add u64 (returning)",
-                            "global load+compare, red.min s64 if smaller", "global ld u64 (reference)"};
+                            "global load+compare, red.min s64 if smaller", "global ld u64 (reference)", "global red.add u64, 4 lanes on 4 adjacent words", "global red.add u64, 8 lanes on 8 adjacent words",
+                            "global ld 256-bit (one 32 B sector per lane)"};
 
 template <int KIND>
 __global__ void __launch_bounds__(256) probe(u64* g, u32 n, int skew, int iters, int smem_words, u64* sink) {
@@ -58,6 +59,16 @@ __global__ void __launch_bounds__(256) probe(u64* g, u32 n, int skew, int iters,
         if (KIND == G_ATOM64) acc += atomicAdd(&g[draw(h, n, skew)], (u64)v);
         if (KIND == G_CHECKMIN64) { long long* p = (long long*)&g[draw(h, n, skew)]; if ((long long)v < __ldcg(p)) atomicMin(p, (long long)v); }
         if (KIND == G_LD64) acc += __ldcg(&g[draw(h, n, skew)]);
+        if (KIND == G_RED64_G4 || KIND == G_RED64_G8) {  // a group of lanes updates adjacent words of ONE random slot
+            const int G = KIND == G_RED64_G4 ? 4 : 8;
+            const u32 lane = threadIdx.x & 31;
+            const u32 slot = __shfl_sync(0xffffffffu, draw(h, n / G, skew), lane & ~(G - 1));
+            atomicAdd(&g[(size_t)slot * G + (lane & (G - 1))], (u64)v);
+        }
+        if (KIND == G_LD256) {
+            const ulonglong4 x = *(const ulonglong4*)&g[(size_t)draw(h, n / 4, skew) * 4];
+            acc += x.x + x.y + x.z + x.w;
+        }
     }
     __syncthreads();
     if (KIND < G_RED64) for (int i = threadIdx.x; i < smem_words; i += 256) acc += s[i];
@@ -112,6 +123,9 @@ int main() {
             run<G_CHECKMIN64>(g, gn, skew, 16, sink, sms);
             run<G_ATOM64>(g, gn, skew, 16, sink, sms);
             run<G_LD64>(g, gn, skew, 16, sink, sms);
+            run<G_RED64_G4>(g, gn, skew, 16, sink, sms);
+            run<G_RED64_G8>(g, gn, skew, 16, sink, sms);
+            run<G_LD256>(g, gn, skew, 16, sink, sms);
         }
     }
     return 0;
