@@ -296,7 +296,7 @@ class Result:
             pass
 
 
-MODES = {0: "ungrouped", 1: "dense-shared-memory", 2: "hbm-hash-64", 3: "hbm-hash-128"}
+MODES = {0: "ungrouped", 1: "dense-shared-memory", 2: "hbm-hash-64", 3: "hbm-hash-128", 4: "hbm-direct"}
 
 
 class Query:

@@ -221,7 +221,7 @@ int n1gpu_query_info(const n1gpu_query* q, int64_t info[8]) {
     return guard([&] {
         REQUIRE(q); REQUIRE(info);
         const Query& Q = *q->q;
-        info[0] = Q.kp.mode; info[1] = Q.ops.n; info[2] = Q.kernel ? Q.kernel->regs : 0; info[3] = Q.grid; info[4] = Q.kp.block;
+        info[0] = Q.kp.dense_global ? 4 : Q.kp.mode; info[1] = Q.ops.n; info[2] = Q.kernel ? Q.kernel->regs : 0; info[3] = Q.grid; info[4] = Q.kp.block;
         info[5] = Q.kp.scan_bytes_per_row; info[6] = Q.kernel ? Q.kernel->static_smem : 0;
         info[7] = Q.kp.mode == MODE_DENSE ? Q.kp.dense_slots : (i64)Q.cap;
     });

@@ -389,8 +389,17 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         if (kp.dense_slots * W <= 48 && !(np && *np == '1')) { kp.dense_priv = true; kp.dyn_smem = (int)(kp.dense_slots * W * 256 * 8); }
     }
     else if (kp.key_bits <= 63) {
-        kp.mode = MODE_HASH64;
-        // shared-memory front cache for hot keys (Zipf-skewed GROUP BY): as many slots as fit 32 KiB
+        // A packed key of few bits indexes the HBM table directly: no key array, no hash probe, no insert race, the
+        // table (config 5: 2^19 slots x 6 words = 25 MB) stays in L2, and because slot == key on every rank the
+        // multi-GPU merge is element-wise (all_gather + k_merge_words, stream-ordered) instead of a record exchange.
+        const char* nd = getenv("N1GPU_NO_DIRECT");
+        const double slots = kp.key_bits <= 22 ? (double)((i64)1 << kp.key_bits) : 1e30;
+        if (!(nd && *nd == '1') && slots * W * 8 <= 256.0 * 1024 * 1024 && slots <= 8.0 * std::max<double>((double)t.nrows, 131072.0)) {
+            kp.mode = MODE_DENSE;
+            kp.dense_global = true;
+            kp.dense_slots = (i64)1 << kp.key_bits;
+        } else kp.mode = MODE_HASH64;
+        // shared-memory front cache for hot keys (Zipf-skewed GROUP BY)
         const char* nc = getenv("N1GPU_NO_CACHE");
         if (!(nc && *nc == '1')) {
             // cell layout (see n1ql_device.cuh "Cells of the front cache")
@@ -452,6 +461,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     g.body.clear();
 
     // aggregation code (executed under `if (pass)`)
+    const bool cached = kp.cache_slots > 0;                             // HBM table (hashed or direct) behind the front cache
+    const bool smem_dense = kp.mode == MODE_DENSE && !kp.dense_global;  // the table itself lives in shared memory
     std::string key_code;
     g.ind = "                    ";
     if (kp.mode != MODE_UNGROUPED) {
@@ -465,8 +476,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             }
             emit_pack(g, kp.keys[k], kv, "klo", "khi", "kpos");
         }
-        if (kp.mode == MODE_DENSE) g.line("const i64 slot = (i64)klo;");
-        else if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+        if (kp.mode == MODE_DENSE && !cached) g.line("const i64 slot = (i64)klo;");
+        else if (cached) {
             // the kernel is assembled in phases (keys + cache probe / cached updates / table updates, see below):
             // the key code ends here, the update code starts from an empty body
             key_code = g.body;
@@ -474,7 +485,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         }
         else if (kp.mode == MODE_HASH64) g.line("const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);");
         else g.line("const i64 slot = table_insert128((ulonglong2*)p.keys, p.cap_mask, klo, khi, nullptr);");
-        if (kp.mode != MODE_DENSE && !(kp.mode == MODE_HASH64 && kp.cache_slots)) g.line("if (slot < 0) { p.status[0] = 1; continue; }");
+        if (kp.mode != MODE_DENSE && !cached) g.line("if (slot < 0) { p.status[0] = 1; continue; }");
     }
     std::set<int> emitted_sets;
     std::set<int> emitted;  // a shared word is updated once per row, by the first aggregate that owns it
@@ -570,7 +581,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     s += "// generated by libn1gpu codegen: one specialised scan kernel for this Filter + Group chain\n";
     s += "#include \"n1ql_device.cuh\"\n";
     s += strf("#define NQ_W %d\n", W);
-    if (kp.mode == MODE_DENSE) s += strf("#define NQ_G %lld\n", (long long)kp.dense_slots);
+    if (smem_dense) s += strf("#define NQ_G %lld\n", (long long)kp.dense_slots);
     s += "__constant__ int nq_ops[NQ_W] = {";
     for (int w = 0; w < W; ++w) s += strf("%s%d", w ? ", " : "", kp.word_ops[w]);
     s += "};\n";
@@ -578,10 +589,10 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     for (int w = 0, fi = 0; w < W; ++w) s += strf("%s%d", w ? ", " : "", kp.word_ops[w] == OP_ADD_F64 ? fi++ : -1);
     s += "};\n";
     if (kp.mode == MODE_UNGROUPED) s += "#define ACC(k, OP, x) a##k = word_combine(OP, a##k, (u64)(x))\n";
-    else if (kp.mode == MODE_DENSE && kp.dense_priv)
+    else if (smem_dense && kp.dense_priv)
         s += "#define ACC(k, OP, val_) { u64* c_ = &s_priv[(((k) * NQ_G + slot) << 8) + threadIdx.x]; *c_ = word_combine(OP, *c_, (u64)(val_)); }\n";
-    else if (kp.mode == MODE_DENSE) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
-    else if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+    else if (smem_dense) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
+    else if (cached) {
         s += strf("#define NQ_CS %d\n", kp.cache_slots);
         s += "#define ACCM(k, OP, val_) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(val_))\n";
         for (int w = 0; w < W; ++w) {
@@ -616,11 +627,11 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     }
     if (kp.mode == MODE_UNGROUPED) {
         for (int w = 0; w < W; ++w) s += strf("    u64 a%d = word_identity(%s);\n", w, op_name(kp.word_ops[w]));
-    } else if (kp.mode == MODE_DENSE && kp.dense_priv) {
+    } else if (smem_dense && kp.dense_priv) {
         s += "    extern __shared__ u64 s_priv[];  // [NQ_W * NQ_G cells][256 threads]: cell c of thread t at (c << 8) + t\n";
         s += "#pragma unroll\n";
         s += "    for (int c = 0; c < NQ_W * NQ_G; ++c) s_priv[(c << 8) + threadIdx.x] = word_identity(nq_ops[c / NQ_G]);\n";
-    } else if (kp.mode == MODE_DENSE) {
+    } else if (smem_dense) {
         s += "    __shared__ u64 s_tab[NQ_W * NQ_G];\n";
         s += "    for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) s_tab[i] = word_identity(nq_ops[i / NQ_G]);\n";
         s += "    __syncthreads();\n";
@@ -660,7 +671,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         else if (col.width == 4) s += strf("        u32 c%d[4]; ld_rows4_b32((const u32*)p.col[%d] + base, c%d);\n", c, c, c);
         if (!col.stats.uniform_tag() && col.stats.class_mask) s += strf("        int t%d[4]; ld_rows4_b8(p.tag[%d] + base, t%d);\n", c, c, c);
     }
-    if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+    if (cached) {
         // Three phases per 4 rows, so that the lanes of a warp diverge once per phase instead of once per accumulator
         // word: (1) filter, group key and front-cache probe of all four rows (the four probes are independent: their
         // shared-memory latencies overlap); (2) rows whose key is cached update shared-memory cells; (3) the others
@@ -703,8 +714,11 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "            if (__ballot_sync(0xffffffffu, cs[j] == -1) == 0) continue;\n";
         s += "            if (cs[j] == -1) {\n";
         s += "                    const u64 klo = kk[j];\n";
-        s += "                    const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);\n";
-        s += "                    if (slot < 0) { p.status[0] = 1; continue; }\n";
+        if (kp.dense_global) s += "                    const i64 slot = (i64)klo;  // direct-indexed table\n";
+        else {
+            s += "                    const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);\n";
+            s += "                    if (slot < 0) { p.status[0] = 1; continue; }\n";
+        }
         s += g.decls;
         s += agg_code;
         s += "            }\n";
@@ -727,21 +741,24 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "            }\n";
         s += "        }\n";
     }
-    if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+    if (cached) {
         s += "        if (cache_on && ++tiles == 4) {  // warp-uniform: is the front cache earning its probes?\n";
         s += "            const unsigned L = __reduce_add_sync(0xffffffffu, nlook), H = __reduce_add_sync(0xffffffffu, nhit);\n";
         s += "            if (H * 4 < L) cache_on = false;\n";
         s += "        }\n";
     }
     s += "    }\n";
-    if (kp.mode == MODE_HASH64 && kp.cache_slots) {
+    if (cached) {
         // flush the block's cached groups into the HBM table: one insert + one atomic per word per cached key
         s += "    __syncthreads();\n";
         s += "    for (int i = threadIdx.x; i < NQ_CS; i += NQ_BLOCK) {\n";
         s += "        const u64 key = s_ckey[i];\n";
         s += "        if (key == NQ_U64_MAX) continue;\n";
-        s += "        const i64 slot = table_insert64(p.keys, p.cap_mask, key, nullptr);\n";
-        s += "        if (slot < 0) { p.status[0] = 1; continue; }\n";
+        if (kp.dense_global) s += "        const i64 slot = (i64)key;\n";
+        else {
+            s += "        const i64 slot = table_insert64(p.keys, p.cap_mask, key, nullptr);\n";
+            s += "        if (slot < 0) { p.status[0] = 1; continue; }\n";
+        }
         for (int w = 0; w < W; ++w) {
             const int ci = kp.cell_idx[w], op = kp.word_ops[w];
             const std::string dst = strf("&p.acc[%dULL * cap + (u64)slot]", w);
@@ -812,7 +829,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         }
         s += "        if (p.peer_mail) mailbox_push(p, p.final_dev);  // fused all-gather: peer stores over NVLink\n";
         s += "    }\n";
-    } else if (kp.mode == MODE_DENSE) {
+    } else if (smem_dense) {
         if (kp.dense_priv) {
             // fold the 256 private copies of every cell: 8 warp-shuffle reductions per cell, then thread c folds cell c's
             // 8 warp values in order and applies one global atomic per (block, cell)

@@ -50,6 +50,8 @@ struct KernelPlan {
     std::vector<PackComp> keys;
     int key_bits = 0;
     i64 dense_slots = 0;
+    bool dense_global = false;   // MODE_DENSE whose table is too large for shared memory: direct-indexed in HBM (slot = packed
+                                 // key, no key array, no probing) behind the shared-memory front cache of the hash mode
     bool dense_priv = false;     // tiny dense table: one private copy per THREAD in shared memory (no atomics at all)
     bool pdl = false;            // launched with programmatic stream serialization (ungrouped scans)
     int dyn_smem = 0;            // dynamic shared memory the kernel is launched with

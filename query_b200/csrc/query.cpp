@@ -147,7 +147,7 @@ void Query::alloc_state() {
     if (!d_ticket.p) { d_ticket.alloc(64); CK(cudaMemset(d_ticket.p, 0, 64)); }
     d_counts.ensure(4096);
     h_counts.ensure(4096);
-    if (kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) h_records.ensure((size_t)cap * W * 8);
+    if (small_state()) h_records.ensure((size_t)cap * W * 8);
 }
 
 bool Query::uses_status() const { return kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128 || kp.ndistinct > 0 || mailbox != nullptr; }
@@ -183,7 +183,7 @@ void Query::launch_scan() {
     p.final_dev = d_acc.as<u64>();
     p.final_host = h_records.as<u64>();  // pinned memory is device-addressable under UVA: zero-copy result
     p.ticket = d_ticket.as<unsigned>();
-    const bool small = (kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) && kp.ndistinct == 0;
+    const bool small = small_state() && kp.ndistinct == 0;
     u64 mb_slot_base = 0, mb_seq = 0;
     if (mailbox && small && mailbox->nranks > 1) {
         const u64 words = cap * (u64)ops.n;
@@ -237,7 +237,7 @@ bool Query::wait_scan() {
         d_set.alloc(set_bytes());
         return false;
     }
-    host_acc_valid = kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE;
+    host_acc_valid = small_state();
     return true;
 }
 
@@ -409,7 +409,7 @@ std::unique_ptr<Result> Query::finalize() {
                                  d_acc.as<u64>(), D, stream);
         CK(cudaStreamSynchronize(stream));
     }
-    if ((kp.mode == MODE_UNGROUPED || kp.mode == MODE_DENSE) && h_records.p && !import_dirty() && !kp.ndistinct) {
+    if (small_state() && h_records.p && !import_dirty() && !kp.ndistinct) {
         // small state: the scan already published the table words to pinned host memory
         const u64* h = h_records.as<u64>();
         for (u64 i = 0; i < cap; ++i) {

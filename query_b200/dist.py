@@ -140,9 +140,11 @@ class DistributedQuery:
         self.q = query
         self.group = group
         self.stream = stream  # torch.cuda.Stream the query was bound to with set_stream (None: current stream)
-        self.small = query.info["mode"] in ("ungrouped", "dense-shared-memory") and "distinct" not in " ".join(query.aggregates)
+        # slot == group key on every rank (one slot / dense table / direct-indexed HBM table): the merge is element-wise
+        self.small = query.info["mode"] in ("ungrouped", "dense-shared-memory", "hbm-direct") and "distinct" not in " ".join(query.aggregates)
         # with a peer mailbox the merge of a small-state chain is fused into the scan: launch()/collect() only
-        self.fused = bool(mailbox is not None and self.small and world() > 1)
+        # (a direct-indexed HBM table is megabytes: it takes the all_gather + merge-kernel path)
+        self.fused = bool(mailbox is not None and self.small and world() > 1 and query.info["mode"] != "hbm-direct")
         if self.fused:
             query.set_mailbox(mailbox)
         elif self.small and world() > 1 and stream is None:

@@ -117,7 +117,7 @@ def test_every_golden_plan_compiles(case):
     t = make_table(docs, case.where, case.keys, case.aggs)
     t.seal()
     qq = q.Query(t, case.alias, case.where, case.keys, case.aggs)
-    assert qq.info["mode"] in ("ungrouped", "dense-shared-memory", "hbm-hash-64", "hbm-hash-128")
+    assert qq.info["mode"] in ("ungrouped", "dense-shared-memory", "hbm-direct", "hbm-hash-64", "hbm-hash-128")
 
 
 def _expect(code, fn):

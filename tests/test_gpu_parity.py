@@ -146,8 +146,14 @@ def test_preshredded_columns_properties_10m():
     assert a == b
 
 
-def test_preshredded_group_by_high_cardinality_2m():
-    """1M-group style GROUP BY (BASELINE config 4 shape) checked against numpy: exact counts / int sums / DISTINCT."""
+@pytest.mark.parametrize("table_kind,set_kind", [("direct", "bitmap"), ("hash", "bitmap"), ("hash", "hash"), ("direct", "hash")])
+def test_preshredded_group_by_high_cardinality_2m(table_kind, set_kind, monkeypatch):
+    """1M-group style GROUP BY (BASELINE config 4 shape) checked against numpy: exact counts / int sums / DISTINCT,
+    through both group-table layouts (direct-indexed / open addressing) and both DISTINCT set layouts (bitmap / hash)."""
+    if table_kind == "hash":
+        monkeypatch.setenv("N1GPU_NO_DIRECT", "1")
+    if set_kind == "hash":
+        monkeypatch.setenv("N1GPU_NO_BITMAP", "1")
     n = 2_000_000
     rng = np.random.default_rng(3)
     g = rng.integers(0, 200_000, n, dtype=np.int64)
@@ -158,7 +164,7 @@ def test_preshredded_group_by_high_cardinality_2m():
     t.seal()
     aggs = ["count(*)", "sum((`d`.`x`))", "count(distinct (`d`.`x`))", "sum(distinct (`d`.`x`))", "max((`d`.`x`))"]
     qq = q.Query(t, "d", None, ["(`d`.`g`)"], aggs)
-    assert qq.info["mode"] == "hbm-hash-64"
+    assert qq.info["mode"] == ("hbm-direct" if table_kind == "direct" else "hbm-hash-64")
     res = qq.execute()
     rows = res.rows()
     order = np.argsort(g, kind="stable")
