@@ -420,7 +420,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             const char* kb = getenv("N1GPU_CACHE_KB");      // shared memory per block spent on the cache
             const char* bt = getenv("N1GPU_CACHE_BLOCK");   // threads per block
             kp.block = bt && atoi(bt) >= 64 ? atoi(bt) / 32 * 32 : 256;
-            const i64 budget = (kb && atoi(kb) > 0 ? atoi(kb) : 36) * 1024;
+            const i64 budget = (kb && atoi(kb) > 0 ? atoi(kb) : 44) * 1024;  // x 5 blocks = 220 of the SM's 227 KiB
             i64 cs = budget / slot_bytes / 64 * 64;
             const i64 need = (i64)std::min(4.0 * std::max(est, 1.0), 1e9);  // never more than the groups need
             if (cs > need) cs = std::max<i64>(64, (need + 63) / 64 * 64);
@@ -614,6 +614,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         const char* lb = getenv("N1GPU_MIN_BLOCKS");
         int minb = lb ? atoi(lb) : 0;
         s += strf("#define NQ_BLOCK %d\n", kp.block);
+        if (minb == 0 && cached && kp.block == 256) minb = 5;  // the front cache is sized for five resident blocks
         if (minb > 0) s += strf("extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, %d) nq_scan(const NqParams p) {\n", minb);
         else s += "extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK) nq_scan(const NqParams p) {\n";
     }

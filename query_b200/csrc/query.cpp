@@ -542,18 +542,23 @@ std::unique_ptr<Result> Query::finalize() {
         }
     }
     {   // strings: (column, rank) references -> the result's own string table (it may outlive the table)
-        std::unordered_map<i64, i64> pool;
+        std::vector<std::vector<i64>> pool(table->cols.size());  // [column][rank] -> index in res->strings, -1 = not yet
+        i64 empty_at = -1;
         auto resolve = [&](std::vector<u8>& cls, std::vector<i64>& val) {
             for (size_t i = 0; i < cls.size(); ++i) {
                 if (cls[i] != C_STRING) continue;
-                auto it = pool.find(val[i]);
-                if (it == pool.end()) {
-                    const auto& d = table->cols[(size_t)((u64)val[i] >> 40)].dict;
-                    const u64 rank = (u64)val[i] & 0xffffffffffULL;
-                    it = pool.emplace(val[i], (i64)res->strings.size()).first;
-                    res->strings.push_back(rank < d.size() ? d[rank] : std::string());
+                const size_t col = (size_t)((u64)val[i] >> 40);
+                const u64 rank = (u64)val[i] & 0xffffffffffULL;
+                const auto& d = table->cols[col].dict;
+                if (rank >= d.size()) {
+                    if (empty_at < 0) { empty_at = (i64)res->strings.size(); res->strings.emplace_back(); }
+                    val[i] = empty_at;
+                    continue;
                 }
-                val[i] = it->second;
+                auto& slots = pool[col];
+                if (slots.empty()) slots.assign(d.size(), -1);
+                if (slots[rank] < 0) { slots[rank] = (i64)res->strings.size(); res->strings.push_back(d[rank]); }
+                val[i] = slots[rank];
             }
         };
         resolve(res->key_cls, res->key_val);
