@@ -178,6 +178,12 @@ int n1gpu_query_finalize(n1gpu_query* q, n1gpu_result** out);
  * n1gpu_query_state_words fails with N1GPU_E_INVALID for hash-table / DISTINCT chains (use partial_export).  */
 int n1gpu_query_state_words(n1gpu_query* q, void** dev_words, int64_t* nwords);
 int n1gpu_query_merge_words(n1gpu_query* q, const void* dev_all_words, int nranks);
+/* The combine operation of every accumulator word (N1GPU_OP_*: 0 add u64, 1 add f64, 2 min i64, 3 max i64, 4 min u64,
+ * 5 max u64, 6 or u64), word w occupying dev_words[w * slots, (w + 1) * slots).  Returns the number of words (also
+ * when ops is NULL or cap is too small).  A caller whose collective library reduces with these operations (NCCL:
+ * sum / min / max) can merge a direct-indexed table in place with one all-reduce per run of equal operations
+ * instead of all-gather + merge_words.                                                                  */
+int n1gpu_query_word_ops(const n1gpu_query* q, int* ops, int cap);
 
 /* Fused merge for small-state chains: instead of a collective, the scan kernel's last block stores this rank's
  * accumulator words straight into every peer's mailbox over NVLink (peer stores + a release flag), and a 1-block

@@ -72,6 +72,7 @@ _SIGS = {
     "n1gpu_query_partial_import": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64]),
     "n1gpu_query_finalize": (C.c_int, [_P, C.POINTER(_P)]),
     "n1gpu_query_state_words": (C.c_int, [_P, C.POINTER(_P), _I64P]),
+    "n1gpu_query_word_ops": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
     "n1gpu_query_merge_words": (C.c_int, [_P, _P, C.c_int]),
     "n1gpu_mailbox_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
     "n1gpu_mailbox_ipc_handle": (C.c_int, [_P, C.c_char_p]),

@@ -389,6 +389,12 @@ class Query:
         check(lib().n1gpu_query_state_words(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def word_ops(self):
+        """combine operation of every accumulator word (0 add u64, 1 add f64, 2 min i64, 3 max i64, 4 min u64, 5 max u64, 6 or)"""
+        ops = (C.c_int * 64)()
+        n = lib().n1gpu_query_word_ops(self._h, ops, 64)
+        return [int(ops[i]) for i in range(n)]
+
     def merge_words(self, dev_all_words, nranks):
         check(lib().n1gpu_query_merge_words(self._h, C.c_void_p(dev_all_words), nranks))
 

@@ -347,6 +347,12 @@ int n1gpu_query_merge_words(n1gpu_query* q, const void* dev_all_words, int nrank
         launch_merge_words((const u64*)dev_all_words, nranks, Q.cap, Q.ops, Q.d_acc.as<u64>(), Q.h_records.as<u64>(), Q.stream);
     });
 }
+int n1gpu_query_word_ops(const n1gpu_query* q, int* ops, int cap) {
+    if (!q) return -1;
+    const Query& Q = *q->q;
+    for (int w = 0; ops && w < Q.ops.n && w < cap; ++w) ops[w] = Q.ops.op[w];
+    return Q.ops.n;
+}
 int n1gpu_query_finalize(n1gpu_query* q, n1gpu_result** out) {
     return guard([&] { REQUIRE(q); REQUIRE(out); *out = new n1gpu_result{q->q->finalize()}; });
 }

@@ -224,11 +224,40 @@ PackComp make_comp(const Table& t, const Expr& e, const char* what) {
     if (ti.mask & bit(C_FLOAT)) pb = 64;
     if (ti.mask & bit(C_STRING)) pb = std::max(pb, bits_for((u64)std::max<i64>(1, t.cols[pc.dict_col].stats.ndict)));
     pc.pbits = pb;
+    // offset packing: exactly one payload class, bounded
+    {
+        const bool has_i = ti.mask & bit(C_INT), has_f = ti.mask & bit(C_FLOAT), has_s = ti.mask & bit(C_STRING);
+        const char* no = getenv("N1GPU_NO_OFFSET_PACK");
+        if (!(no && *no == '1') && pc.classes.size() > 1 && !has_f && (has_i != has_s) && (!has_i || pc.biased) && pb < 62) {
+            const int pcls = has_i ? C_INT : C_STRING;
+            const u64 range = has_i ? (u64)ti.hi - (u64)ti.lo + 1 : (u64)std::max<i64>(1, t.cols[pc.dict_col].stats.ndict);
+            const int nfree = (int)pc.classes.size() - 1;
+            const int nb = bits_for((u64)nfree + range);
+            if (nb < pc.cbits + pc.pbits) {
+                std::vector<int> order;
+                for (int c : pc.classes) if (c != pcls) order.push_back(c);
+                order.push_back(pcls);
+                pc.classes = order;
+                pc.nfree = nfree;
+                pc.range = range;
+                pc.cbits = 0;
+                pc.pbits = nb;
+            }
+        }
+    }
     return pc;
 }
 
 // Emits code packing Val `v` as component pc into (lo,hi,pos) variables.
 void emit_pack(Gen& g, const PackComp& pc, const std::string& v, const char* lo, const char* hi, const char* pos) {
+    if (pc.nfree >= 0) {
+        const int pcls = pc.classes.back();
+        std::string pay = pcls == C_STRING ? strf("((u64)%s.b >> 1)", v.c_str()) : strf("((u64)%s.b - (u64)%s)", v.c_str(), lit_i64(pc.bias).c_str());
+        std::string e = strf("(%dULL + %s)", pc.nfree, pay.c_str());
+        for (int k = pc.nfree - 1; k >= 0; --k) e = strf("(%s.c == %s ? %dULL : %s)", v.c_str(), cls_name(pc.classes[k]), k, e.c_str());
+        g.line(strf("pack_bits(%s, %s, %s, %s, %d);", lo, hi, pos, e.c_str(), pc.pbits));
+        return;
+    }
     if (pc.cbits) {
         std::string e = strf("%d", (int)pc.classes.size() - 1);
         for (int k = (int)pc.classes.size() - 2; k >= 0; --k) e = strf("(%s.c == %s ? %d : %s)", v.c_str(), cls_name(pc.classes[k]), k, e.c_str());
@@ -249,7 +278,7 @@ void emit_pack(Gen& g, const PackComp& pc, const std::string& v, const char* lo,
 double comp_domain(const Table& t, const PackComp& pc) {
     double d = 0;
     for (int c : pc.classes) {
-        if (c == C_INT) d += pc.biased ? std::ldexp(1.0, std::min(pc.pbits, 62)) : 1e18;
+        if (c == C_INT) d += pc.nfree >= 0 ? (double)pc.range : (pc.biased ? std::ldexp(1.0, std::min(pc.pbits, 62)) : 1e18);
         else if (c == C_FLOAT) d += 1e18;
         else if (c == C_STRING) d += (double)std::max<i64>(1, t.cols[pc.dict_col].stats.ndict);
         else d += 1;

@@ -18,9 +18,15 @@ struct PackComp {
     u32 mask = 0;
     std::vector<int> classes;  // class index -> class
     int cbits = 0, pbits = 0;
+    // "offset" packing (one field, no class bits): when a single class carries a bounded payload (a dictionary rank or a
+    // ranged int) the classes without payload take the values 0 .. nfree-1 and the payload class nfree + payload;
+    // `classes` then lists the payload-free classes first and the payload class last.  A string key with NULL and
+    // MISSING groups packs into bits_for(2 + ndict) bits instead of 2 + bits_for(ndict): a 4x smaller direct table.
+    int nfree = -1;            // >= 0: offset packing with this many payload-free classes
     bool biased = false;       // INT payload stored as (v - bias)
     i64 bias = 0;
     int dict_col = -1;         // STRING payload = rank in this column's dictionary
+    u64 range = 0;             // offset packing: payload values are 0 .. range-1
     int bits() const { return cbits + pbits; }
 };
 

@@ -169,8 +169,12 @@ __device__ __forceinline__ void distinct_entry(u64 lo, u64 hi, int abits, int ke
             const DistinctDesc& d = D.d[a];
             if (d.sid != sid) continue;
             if (!decoded) {  // the value component is packed identically for every aggregate of the set
-                const int ci = (int)take_bits(v, d.cbits);
+                int ci = (int)take_bits(v, d.cbits);
                 pv = take_bits(v, d.pbits);
+                if (d.nfree >= 0) {  // offset packing: one field
+                    ci = pv < (u64)d.nfree ? (int)pv : d.nfree;
+                    pv = pv < (u64)d.nfree ? 0 : pv - (u64)d.nfree;
+                }
                 cls = ci < 8 ? d.classes[ci] : C_MISSING;
                 decoded = true;
             }

@@ -15,6 +15,7 @@ struct DistinctDesc {
     int numbers_only;  // COUNTN / SUM / AVG DISTINCT: only numeric entries count (COUNT: every entry)
     int w_cnt, w_ilo, w_ihi, w_neg, w_fsum, w_nflt;  // word indices (-1 = not needed)
     int cbits, pbits, biased;
+    int nfree;         // >= 0: offset packing (PackComp::nfree)
     i64 bias;
     int classes[8];
 };

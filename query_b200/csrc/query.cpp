@@ -333,6 +333,10 @@ HValue str_ref(int col, u64 rank) { HValue v; v.cls = C_STRING; v.bits = (i64)((
 HValue decode_comp(const Table& t, const PackComp& pc, BitReader& br) {
     u64 ci = br.take(pc.cbits);
     u64 pv = br.take(pc.pbits);
+    if (pc.nfree >= 0) {  // offset packing: one field
+        ci = pv < (u64)pc.nfree ? pv : (u64)pc.nfree;
+        pv = pv < (u64)pc.nfree ? 0 : pv - (u64)pc.nfree;
+    }
     int cls = ci < pc.classes.size() ? pc.classes[ci] : C_MISSING;
     switch (cls) {
         case C_INT: return HValue::integer(pc.biased ? (i64)(pv + (u64)pc.bias) : (i64)pv);
@@ -401,6 +405,7 @@ std::unique_ptr<Result> Query::finalize() {
             d.numbers_only = ap.kind != AggKind::COUNT;
             d.w_cnt = ap.w_cnt; d.w_ilo = ap.w_ilo; d.w_ihi = ap.w_ihi; d.w_neg = ap.w_neg; d.w_fsum = ap.w_fsum; d.w_nflt = ap.w_nflt;
             d.cbits = ap.dcomp.cbits; d.pbits = ap.dcomp.pbits; d.biased = ap.dcomp.biased; d.bias = ap.dcomp.bias;
+            d.nfree = ap.dcomp.nfree;
             for (int k = 0; k < 8; ++k) d.classes[k] = k < (int)ap.dcomp.classes.size() ? ap.dcomp.classes[k] : C_MISSING;
             for (int w : {ap.w_cnt, ap.w_ilo, ap.w_ihi, ap.w_neg, ap.w_fsum, ap.w_nflt})
                 if (w >= 0) launch_fill_u64(d_acc.as<u64>() + (u64)w * cap, cap, 0, stream);  // idempotent finalize

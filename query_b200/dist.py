@@ -155,6 +155,7 @@ class DistributedQuery:
         self._dents = None
         self._all = None
         self._view = None
+        self._runs = None
         self._launched = False
 
     def launch(self):
@@ -172,12 +173,40 @@ class DistributedQuery:
         if self._view is None:
             ptr, n = q.state_words()
             self._view = torch.as_tensor(_DevWords(ptr, n), device="cuda")
-            self._all = torch.empty(w * n, dtype=torch.int64, device="cuda")
+            self._runs = self._reduce_runs(n) if q.info["mode"] == "hbm-direct" else None
+            if self._runs is None:
+                self._all = torch.empty(w * n, dtype=torch.int64, device="cuda")
         ctx = torch.cuda.stream(self.stream) if self.stream is not None else _null()
         with ctx:
-            dist.all_gather_into_tensor(self._all, self._view, group=self.group)  # stream-ordered after the scan
-        q.merge_words(self._all.data_ptr(), w)
+            if self._runs is not None:
+                # megabytes of direct-indexed table: reduce in place, one NCCL all-reduce per run of words that combine
+                # the same way (sum / min / max; NVLS reduces inside the switch) - every rank ends with the merged table
+                for view, op in self._runs:
+                    dist.all_reduce(view, op=op, group=self.group)
+            else:
+                dist.all_gather_into_tensor(self._all, self._view, group=self.group)  # stream-ordered after the scan
+        if self._runs is None:
+            q.merge_words(self._all.data_ptr(), w)
         self._launched = True
+
+    def _reduce_runs(self, nwords):
+        """[(tensor view over consecutive word planes, ReduceOp)] when every word's combine operation is one NCCL has
+        (add u64 as int64 sum - two's complement; add f64; min / max i64), else None (all_gather + merge kernel)."""
+        ops = self.q.word_ops()
+        if not ops or nwords % len(ops):
+            return None
+        slots = nwords // len(ops)
+        kind = {0: ("i", dist.ReduceOp.SUM), 1: ("f", dist.ReduceOp.SUM), 2: ("i", dist.ReduceOp.MIN), 3: ("i", dist.ReduceOp.MAX)}
+        if any(o not in kind for o in ops):
+            return None
+        runs, w0 = [], 0
+        for w in range(1, len(ops) + 1):
+            if w == len(ops) or kind[ops[w]] != kind[ops[w0]]:
+                view = self._view[w0 * slots: w * slots]
+                dt, op = kind[ops[w0]]
+                runs.append((view.view(torch.float64) if dt == "f" else view, op))
+                w0 = w
+        return runs
 
     def collect(self):
         self._launched = False

@@ -5,7 +5,7 @@ ranks (STRONG scaling: the total is fixed), columns resident in HBM.  Run under 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/scale_config5.py
 
 A step = this rank's scan + the Intermediate merge (the group table is direct-indexed, so the merge is an NCCL
-all_gather of the accumulator words + one merge kernel, all stream-ordered) ; timed with CUDA events, max over ranks.
+in-place NCCL all-reduce of the accumulator words, one call per run of sum / min / max words, stream-ordered); timed with CUDA events, max over ranks.
 The finalisation on the host (ComputeFinal of 100 002 groups) is timed separately.  Rank 0 checks the merged result
 against torch reductions all-reduced over the ranks' tensors, and prints one JSON line.
 FS_SCALE shrinks the row count; FS_WEAK=1 keeps 1 B x FS_SCALE rows PER RANK instead (weak scaling)."""
@@ -128,7 +128,7 @@ def main():
         print(json.dumps({"config": "config5", "n_gpus": world, "scaling": "weak" if weak else "strong", "total_rows": total,
                           "rows_per_gpu": n, "mode": info["mode"], "scan_plus_merge_ms": ms, "rows_per_s": total / (ms * 1e-3),
                           "gb_per_s": info["scan_bytes_per_row"] * total / (ms * 1e6), "finalize_host_ms": fms, "groups": ng,
-                          "merge": "none" if world == 1 else "NCCL all_gather of the direct-indexed table words + k_merge_words, stream-ordered",
+                          "merge": "none" if world == 1 else "in-place NCCL all-reduce of the direct-indexed table, one call per run of sum / min / max words, stream-ordered",
                           "check": "every group exact vs all-reduced torch reductions"}))
     if world > 1:
         dist.barrier()
