@@ -5,10 +5,15 @@
 // ranks) or 32-bit (class bytes) coalesced load per referenced column, the Filter condition is evaluated
 // with N1QL's 4-valued logic, a warp ballot of the selection skips the aggregation when no lane passes,
 // and the aggregates are folded into
-//   MODE_UNGROUPED  per-thread registers -> deterministic block reduction -> per-block partials
-//   MODE_DENSE      a shared-memory table indexed by the bit-packed group key, flushed to HBM
-//   MODE_HASH64/128 an HBM open-addressing table claimed with 64-/128-bit CAS
-// Static type analysis (expr.cpp) and column statistics decide which accumulator words exist at all.
+//   MODE_UNGROUPED  per-thread registers -> block reduction -> persistent accumulators / ordered float partials,
+//                   folded and published by the last block (one launch per step, programmatic dependent launch)
+//   MODE_DENSE      a table indexed by the bit-packed group key: in shared memory when it fits (thread-private
+//                   copies for a handful of groups), else direct-indexed in HBM (dense_global) behind the
+//                   shared-memory front cache
+//   MODE_HASH64/128 an HBM open-addressing table claimed with 64-/128-bit CAS (64: behind the front cache)
+// DISTINCT aggregates add bit-packed (set, group, value) entries to a bitmap or an HBM hash set.
+// Static type analysis (expr.cpp) and column statistics decide which accumulator words exist at all, how wide
+// keys and entries are, and which of the layouts above is generated.
 #include "codegen.hpp"
 
 #include <algorithm>

@@ -1,7 +1,8 @@
 // kernels.cu — the static (query-independent) sm_100a kernels of libn1gpu.so: accumulator-table
-// initialisation, the deterministic reduction of per-block partials, table -> record compaction with
-// owner bucketing (the export side of the multi-GPU IntermediateGroup exchange) and record -> table
-// merging (CumulateIntermediate: algebra/agg_*.go, execution/group_intermediate.go:56-104).
+// initialisation, table / DISTINCT set -> record compaction with owner bucketing (the export side of the
+// multi-GPU IntermediateGroup exchange, also the compaction step of finalisation), record -> table merging
+// (CumulateIntermediate: algebra/agg_*.go, execution/group_intermediate.go:56-104), the element-wise merges of
+// small-state chains and the device-side ComputeFinal of DISTINCT aggregates.
 #include "kernels.hpp"
 #include "n1ql_device.cuh"
 
@@ -15,24 +16,6 @@ __global__ void k_init_words(u64* acc, u64 cap, OpsArr ops) {
 
 __global__ void k_fill_u64(u64* p, u64 n, u64 v) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
-}
-
-// partials[nblocks][W] -> out[W]; one block, fixed summation order => run-to-run identical float sums.
-__global__ void k_reduce_partials(const u64* __restrict__ partials, int nblocks, OpsArr ops, u64* __restrict__ out) {
-    __shared__ u64 sh[256];
-    for (int w = 0; w < ops.n; ++w) {
-        int op = ops.op[w];
-        u64 v = word_identity(op);
-        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v = word_combine(op, v, partials[(u64)b * ops.n + w]);
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) sh[threadIdx.x] = word_combine(op, sh[threadIdx.x], sh[threadIdx.x + s]);
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) out[w] = sh[0];
-        __syncthreads();
-    }
 }
 
 __device__ __forceinline__ void extract_bits(u64 lo, u64 hi, int pos, int n, u64& olo, u64& ohi) {
@@ -288,11 +271,6 @@ void launch_init_words(u64* acc, u64 cap, const OpsArr& ops, cudaStream_t s) {
 }
 void launch_fill_u64(u64* p, u64 n, u64 v, cudaStream_t s) {
     k_fill_u64<<<grid_for(n), 256, 0, s>>>(p, n, v);
-    g_launches.fetch_add(1);
-    CK(cudaGetLastError());
-}
-void launch_reduce_partials(const u64* partials, int nblocks, const OpsArr& ops, u64* out, cudaStream_t s) {
-    k_reduce_partials<<<1, 256, 0, s>>>(partials, nblocks, ops, out);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }

@@ -30,7 +30,6 @@ void launch_merge_mailbox(const u64* mail, int nranks, u64 slot_base, u64 stride
 void launch_merge_words(const u64* all, int nranks, u64 cap, const OpsArr& ops, u64* out_dev, u64* out_host, cudaStream_t s);
 void launch_init_words(u64* acc, u64 cap, const OpsArr& ops, cudaStream_t s);
 void launch_fill_u64(u64* p, u64 n, u64 v, cudaStream_t s);
-void launch_reduce_partials(const u64* partials, int nblocks, const OpsArr& ops, u64* out, cudaStream_t s);
 void launch_count_owners(int kw, const u64* keys, const u64* acc, u64 cap, int nranks, int gk_pos, int gk_bits,
                          unsigned long long* counts, cudaStream_t s);
 void launch_export_records(int kw, const u64* keys, const u64* acc, u64 cap, int W, int nranks, int gk_pos, int gk_bits,

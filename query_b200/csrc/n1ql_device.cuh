@@ -379,22 +379,7 @@ NQ_DEV i64 table_find128(const ulonglong2* __restrict__ keys, u64 cap_mask, u64 
 
 // Per-block shared-memory front cache of the HBM group table (hot keys of a skewed GROUP BY are aggregated with
 // shared-memory atomics and reach HBM once per block): claims or finds `key` within 4 probes, else -1 (miss).
-NQ_DEV int cache_claim(u64* ckeys, u32 mask, u64 key) {
-    u32 h = (u32)mix64(key) & mask;
-#pragma unroll
-    for (int probe = 0; probe < 4; ++probe) {
-        const u64 cur = ((volatile u64*)ckeys)[h];
-        if (cur == key) return (int)h;
-        if (cur == NQ_U64_MAX) {
-            const u64 old = atomicCAS(&ckeys[h], NQ_U64_MAX, key);
-            if (old == NQ_U64_MAX || old == key) return (int)h;
-        }
-        h = (h + 1) & mask;
-    }
-    return -1;
-}
-
-// Same for any slot count (not only powers of two): the slot is the high part of hash * slots.
+// (any slot count, not only powers of two: the slot is the high part of hash * slots)
 NQ_DEV int cache_claim_n(u64* ckeys, u32 slots, u32 hash, u64 key) {
     u32 h = __umulhi(hash, slots);
 #pragma unroll

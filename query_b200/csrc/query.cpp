@@ -376,14 +376,7 @@ HValue sum_value(const SumState& s, bool from_zero) {
     return HValue::flt((double)s.itotal + s.fsum);
 }
 
-struct DistinctAcc {
-    u64 count = 0;
-    SumState sum;
-};
 
-struct KeyHash {
-    size_t operator()(const std::pair<u64, u64>& k) const { return (size_t)mix64(k.first ^ mix64(k.second)); }
-};
 }  // namespace
 
 std::unique_ptr<Result> Query::finalize() {

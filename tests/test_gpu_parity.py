@@ -73,6 +73,20 @@ def test_matrix_against_oracle(name, where, keys, aggs):
     assert res.stats["rows"] == 3000
 
 
+_GROUPED = [x for x in QUERIES if x[2]]
+
+
+@pytest.mark.parametrize("knob", ["N1GPU_NO_DIRECT", "N1GPU_NO_BITMAP", "N1GPU_NO_OFFSET_PACK", "N1GPU_NO_CACHE"])
+@pytest.mark.parametrize("name,where,keys,aggs", _GROUPED, ids=[x[0] for x in _GROUPED])
+def test_grouped_matrix_through_the_alternate_layouts(name, where, keys, aggs, knob, monkeypatch):
+    """The planner picks direct-indexed tables, DISTINCT bitmaps, offset-packed keys and the shared-memory front cache
+    whenever statistics allow; the layouts they replace (open addressing, hash sets, class-bits packing, uncached
+    updates) stay reachable for wider keys and are kept under test by switching each choice off."""
+    monkeypatch.setenv(knob, "1")
+    docs = make_docs(3000, seed=22)
+    run_both(docs, "d", where, keys, aggs, "%s %s" % (name, knob))
+
+
 @pytest.mark.parametrize("n", [0, 1, 3, 127, 128, 129, 1023, 1024, 1025, 4097])
 def test_ragged_sizes(n):
     docs = make_docs(n, seed=100 + n)
