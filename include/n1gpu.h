@@ -105,6 +105,12 @@ int n1gpu_table_dict_import(n1gpu_table* t, int col, const char* blob, const int
 /* Column statistics exchange (int range / class mask) so that every rank compiles the same kernel. */
 int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]);
 int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]);
+/* Declares how many rows the whole keyspace holds over ALL partitions (ranks) whose partial group states will be
+ * merged with this table's (>= this partition's rows; a single-partition keyspace declares its own row count).
+ * Queries compiled afterwards size their overflow proofs with it: exact one-word integer sums, and two row counters
+ * sharing one 64-bit table word (needs < 2^32 rows).  Undeclared, a query assumes up to 16 partitions of this size.
+ * The reference has no counterpart: its counters are boxed int64 values (algebra/agg_count.go:95-149).             */
+int n1gpu_table_set_global_rows(n1gpu_table* t, int64_t rows);
 /* Copies a column's staged rows (before seal): payload[nrows] (int64 / float64 bits / dictionary rank)
  * and tags[nrows].  For shredder parity tests; either pointer may be NULL.                           */
 int n1gpu_table_column_peek(n1gpu_table* t, int col, int64_t* payload, uint8_t* tags, int64_t nrows);

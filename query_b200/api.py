@@ -180,6 +180,11 @@ class Table:
         s = np.ascontiguousarray(stats, dtype=np.int64)
         check(lib().n1gpu_table_stats_set(self._h, idx, s.ctypes.data_as(_lib._I64P)))
 
+    def set_global_rows(self, rows):
+        """Rows of the whole keyspace over all partitions whose partial states get merged (include/n1gpu.h)."""
+        check(lib().n1gpu_table_set_global_rows(self._h, int(rows)))
+        return self
+
     def seal(self):
         check(lib().n1gpu_table_seal(self._h))
         return self

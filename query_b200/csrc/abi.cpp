@@ -167,6 +167,13 @@ int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]) {
         c.stats_forced = true;
     });
 }
+int n1gpu_table_set_global_rows(n1gpu_table* t, int64_t rows) {
+    return guard([&] {
+        REQUIRE(t);
+        if (rows < 0) N1_THROW(N1GPU_E_INVALID, "negative row count");
+        t->t.global_rows = rows;
+    });
+}
 int n1gpu_table_column_peek(n1gpu_table* t, int col, int64_t* payload, uint8_t* tags, int64_t nrows) {
     return guard([&] {
         REQUIRE(t);

@@ -307,6 +307,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     // Accumulator words are shared between aggregates wherever they would hold the same value: SUM(x), AVG(x),
     // COUNT(x), COUNTN(x) over the same operand text use one sum word / one count word, and a count that provably
     // equals the number of selected rows (operand never MISSING/NULL/non-number) is the rows word itself.
+    int cache_blocks = 0;  // resident blocks per SM the front cache is sized for
     std::map<std::string, int> shared;
     auto add_word = [&](int op, const std::string& key, bool counter = false, i64 lo = 1, i64 hi = 0) {
         auto it = shared.find(key);
@@ -453,8 +454,11 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             // costs as much, so the small block stays the default; both remain tuning knobs.
             const char* kb = getenv("N1GPU_CACHE_KB");      // shared memory per block spent on the cache
             const char* bt = getenv("N1GPU_CACHE_BLOCK");   // threads per block
+            const char* lb = getenv("N1GPU_MIN_BLOCKS");    // resident blocks per SM
             kp.block = bt && atoi(bt) >= 64 ? atoi(bt) / 32 * 32 : 256;
-            const i64 budget = (kb && atoi(kb) > 0 ? atoi(kb) : 44) * 1024;  // x 5 blocks = 220 of the SM's 227 KiB
+            cache_blocks = lb && atoi(lb) > 0 ? atoi(lb) : std::max(1, 1280 / kp.block);
+            // the resident blocks of an SM share 220 of its 227 KiB (each block also pays 1 KiB of system shared memory)
+            const i64 budget = (kb && atoi(kb) > 0 ? atoi(kb) : 220 / cache_blocks) * 1024;
             i64 cs = budget / slot_bytes / 64 * 64;
             const i64 need = (i64)std::min(4.0 * std::max(est, 1.0), 1e9);  // never more than the groups need
             if (cs > need) cs = std::max<i64>(64, (need + 63) / 64 * 64);
@@ -465,6 +469,30 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     else if (kp.key_bits <= 127) kp.mode = MODE_HASH128;
     else N1_THROW(N1GPU_E_INELIGIBLE, "group key needs %d bits (> 127) after packing", kp.key_bits);
     kp.est_groups = (i64)std::min(est, 4e18);
+
+    // ---- physical words ------------------------------------------------------------------------------------------
+    // Behind the front cache a miss pays one L2 reduction per word it touches, and the request path SM -> L2 is what
+    // bounds a skewed GROUP BY (profiles/r01_atomic_probe.txt: 190 G scattered RED/s whatever their width).  Row
+    // counters are therefore packed two per 64-bit word (32-bit fields) when no counter can reach 2^32 over all ranks.
+    {
+        const char* np = getenv("N1GPU_NO_PACK");
+        const bool pack = kp.cache_slots > 0 && kp.ndistinct == 0 && !(np && *np == '1') && total_rows_bound < 4294967295.0;
+        kp.phys_of.assign(W, -1); kp.shift_of.assign(W, 0); kp.bits_of.assign(W, 64);
+        int pending = -1;  // counter waiting for a partner
+        for (int w = 0; w < W; ++w) {
+            if (pack && kp.word_count[w] && kp.word_ops[w] == OP_ADD_U64) {
+                if (pending >= 0) {
+                    kp.phys_of[w] = kp.phys_of[pending]; kp.shift_of[w] = 32; kp.bits_of[w] = 32; kp.bits_of[pending] = 32;
+                    pending = -1;
+                    continue;
+                }
+                pending = w;
+            }
+            kp.phys_of[w] = (int)kp.phys_ops.size();
+            kp.phys_ops.push_back(kp.word_ops[w]);
+        }
+    }
+    const int PW = (int)kp.phys_ops.size();
 
     // ---- DISTINCT entry layout ---------------------------------------------------------------------------------
     if (kp.ndistinct) {
@@ -611,6 +639,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     for (int c : kp.used_cols) kp.scan_bytes_per_row += t.scan_bytes(c);
 
     // ---- assemble the kernel ------------------------------------------------------------------------------------
+    std::vector<int> pre_words;  // physical min / max / or words whose current value a miss reads ahead (direct table)
     std::string s;
     s += "// generated by libn1gpu codegen: one specialised scan kernel for this Filter + Group chain\n";
     s += "#include \"n1ql_device.cuh\"\n";
@@ -628,7 +657,25 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     else if (smem_dense) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
     else if (cached) {
         s += strf("#define NQ_CS %d\n", kp.cache_slots);
-        s += "#define ACCM(k, OP, val_) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(val_))\n";
+        // table update of a cache miss, per logical word: packed counters gather in a register (one RED per physical
+        // word and row, issued after the row's aggregate code); min / max / or words read the slot first (an L2 load is
+        // cheaper than a reduction and, once a group has settled, almost every row leaves them unchanged)
+        // In the direct-indexed table the slot is the key itself, so those reads are issued for all four rows before
+        // the cached rows are updated (phase 2): their L2 latency overlaps that work instead of stalling every row.
+        const char* nm = getenv("N1GPU_NO_MMCHECK");
+        const char* npf = getenv("N1GPU_NO_MMPREFETCH");
+        const bool mmcheck = !(nm && *nm == '1');
+        const bool mmpre = mmcheck && kp.dense_global && !(npf && *npf == '1');
+        for (int w = 0; w < W; ++w) {
+            const int P = kp.phys_of[w], op = kp.word_ops[w];
+            const bool chk = mmcheck && op != OP_ADD_U64 && op != OP_ADD_F64;
+            if (kp.bits_of[w] != 64) s += strf("#define ACCM_%d(OP, val_) pk%d += (u64)(val_) << %d\n", w, P, kp.shift_of[w]);
+            else if (chk && mmpre) {
+                s += strf("#define ACCM_%d(OP, val_) table_word_known<OP>(&p.acc[%dULL * cap + (u64)slot], (u64)(val_), mm[j][%d])\n", w, P, (int)pre_words.size());
+                pre_words.push_back(P);
+            }
+            else s += strf("#define ACCM_%d(OP, val_) %s<OP>(&p.acc[%dULL * cap + (u64)slot], (u64)(val_))\n", w, chk ? "table_word_checked" : "atomic_word", P);
+        }
         for (int w = 0; w < W; ++w) {
             std::string hit;
             const int ci = kp.cell_idx[w];
@@ -648,7 +695,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         const char* lb = getenv("N1GPU_MIN_BLOCKS");
         int minb = lb ? atoi(lb) : 0;
         s += strf("#define NQ_BLOCK %d\n", kp.block);
-        if (minb == 0 && cached && kp.block == 256) minb = 5;  // the front cache is sized for five resident blocks
+        if (minb == 0 && cached) minb = cache_blocks;  // the front cache is sized for this many resident blocks
         if (minb > 0) s += strf("extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, %d) nq_scan(const NqParams p) {\n", minb);
         else s += "extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK) nq_scan(const NqParams p) {\n";
     }
@@ -731,6 +778,16 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "                    nhit += cs[j] >= 0;\n";
         s += "            }\n";
         s += "        }\n";
+        if (!pre_words.empty()) {
+            s += strf("        u64 mm[4][%d];  // current table value of the min / max / or words of a missed row\n", (int)pre_words.size());
+            s += "#pragma unroll\n";
+            s += "        for (int j = 0; j < 4; ++j) {\n";
+            for (size_t i = 0; i < pre_words.size(); ++i) s += strf("            mm[j][%d] = 0;\n", (int)i);
+            s += "            if (cs[j] == -1) {\n";
+            for (size_t i = 0; i < pre_words.size(); ++i) s += strf("                mm[j][%d] = __ldcg(&p.acc[%dULL * cap + kk[j]]);\n", (int)i, pre_words[i]);
+            s += "            }\n";
+            s += "        }\n";
+        }
         s += "#define ACC(k, OP, val_) ACCH_##k(OP, val_)\n";
         s += "#pragma unroll\n";
         s += "        for (int j = 0; j < 4; ++j) {\n";
@@ -743,7 +800,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "            }\n";
         s += "        }\n";
         s += "#undef ACC\n";
-        s += "#define ACC(k, OP, val_) ACCM(k, OP, val_)\n";
+        s += "#define ACC(k, OP, val_) ACCM_##k(OP, val_)\n";
         s += "#pragma unroll\n";
         s += "        for (int j = 0; j < 4; ++j) {\n";
         s += "            if (__ballot_sync(0xffffffffu, cs[j] == -1) == 0) continue;\n";
@@ -754,8 +811,12 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += "                    const i64 slot = table_insert64(p.keys, p.cap_mask, klo, nullptr);\n";
             s += "                    if (slot < 0) { p.status[0] = 1; continue; }\n";
         }
+        std::set<int> packed_phys;
+        for (int w = 0; w < W; ++w) if (kp.bits_of[w] != 64) packed_phys.insert(kp.phys_of[w]);
+        for (int P : packed_phys) s += strf("                    u64 pk%d = 0;\n", P);
         s += g.decls;
         s += agg_code;
+        for (int P : packed_phys) s += strf("                    if (pk%d) atomicAdd(&p.acc[%dULL * cap + (u64)slot], pk%d);\n", P, P, P);
         s += "            }\n";
         s += "        }\n";
         s += "#undef ACC\n";
@@ -794,9 +855,17 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += "        const i64 slot = table_insert64(p.keys, p.cap_mask, key, nullptr);\n";
             s += "        if (slot < 0) { p.status[0] = 1; continue; }\n";
         }
+        for (int P = 0; P < PW; ++P) {  // packed counters: both fields leave in one reduction
+            std::string v;
+            for (int w = 0; w < W; ++w)
+                if (kp.phys_of[w] == P && kp.bits_of[w] != 64)
+                    v += strf("%s((u64)s_c32[%d * NQ_CS + i] << %d)", v.empty() ? "" : " | ", kp.cell_idx[w], kp.shift_of[w]);
+            if (!v.empty()) s += strf("        { const u64 v = %s; if (v) atomicAdd(&p.acc[%dULL * cap + (u64)slot], v); }\n", v.c_str(), P);
+        }
         for (int w = 0; w < W; ++w) {
+            if (kp.bits_of[w] != 64) continue;
             const int ci = kp.cell_idx[w], op = kp.word_ops[w];
-            const std::string dst = strf("&p.acc[%dULL * cap + (u64)slot]", w);
+            const std::string dst = strf("&p.acc[%dULL * cap + (u64)slot]", kp.phys_of[w]);
             switch (kp.cell_kind[w]) {
                 case CK_WIDE:
                     s += strf("        { const u64 v = ((u64)s_c32[%d * NQ_CS + i] << 32) + (u64)s_c32[%d * NQ_CS + i]; if (v) atomic_word<%s>(%s, v); }\n",

@@ -53,6 +53,13 @@ struct KernelPlan {
     std::vector<int> word_ops;   // accumulator words per group
     std::vector<bool> word_count;  // word only ever receives +1 (a row counter): bounded by the rows one block scans
     std::vector<i64> word_lo, word_hi;  // min/max words: proven value range (lo > hi: unknown)
+    // Physical layout of the group table.  The words above are LOGICAL (what the aggregates read); in the HBM modes
+    // behind the front cache two row counters share one 64-bit physical word as 32-bit fields when the row bound proves
+    // that neither can overflow: a cache miss then costs one L2 reduction for both.  Everything that moves or merges
+    // table state (init, export, merge, all-reduce) works on the physical words; only finalize() decodes the fields.
+    std::vector<int> phys_ops;           // op of every physical word (what Query::ops holds)
+    std::vector<int> phys_of, shift_of;  // logical word -> physical word, bit offset of its field
+    std::vector<int> bits_of;            // field width (64 = the whole word)
     std::vector<PackComp> keys;
     int key_bits = 0;
     i64 dense_slots = 0;

@@ -166,6 +166,7 @@ std::shared_ptr<Table> resident_table(const std::string& dir, std::vector<std::s
     auto t = std::make_shared<Table>();
     for (auto& p : paths) t->add_column(p);
     t->load_dir(dir, 0);
+    t->global_rows = t->nrows;  // the operator runs the whole keyspace in this process: one partition
     t->seal();
     std::lock_guard<std::mutex> lk(g_cache_mu);
     g_tables[key] = CacheEntry{t, st.st_mtime};

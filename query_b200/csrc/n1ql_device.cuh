@@ -301,6 +301,19 @@ template <int OP> NQ_DEV void atomic_word(u64* p, u64 x) {
     else if (OP == OP_MAX_U64) atomicMax(p, x);
     else atomicOr(p, x);
 }
+// Min / max / or into an HBM table word that is read first: an L2 load costs the SM -> L2 request path less than a
+// reduction, and a settled group leaves the word unchanged for almost every row.  The load may be stale; these words
+// only ever move one way, so a stale value can only cause a reduction that was not needed, never skip one that was.
+template <int OP> NQ_DEV void table_word_known(u64* p, u64 x, u64 cur);
+template <int OP> NQ_DEV void table_word_checked(u64* p, u64 x) { table_word_known<OP>(p, x, __ldcg(p)); }
+template <int OP> NQ_DEV void table_word_known(u64* p, u64 x, u64 cur) {  // `cur`: a value the word held earlier
+    if (OP == OP_MIN_I64) { if ((i64)x < (i64)cur) atomicMin((i64*)p, (i64)x); }
+    else if (OP == OP_MAX_I64) { if ((i64)x > (i64)cur) atomicMax((i64*)p, (i64)x); }
+    else if (OP == OP_MIN_U64) { if (x < cur) atomicMin(p, x); }
+    else if (OP == OP_MAX_U64) { if (x > cur) atomicMax(p, x); }
+    else if (OP == OP_OR_U64) { if ((cur & x) != x) atomicOr(p, x); }
+    else atomic_word<OP>(p, x);
+}
 NQ_DEV void atomic_word_dyn(int op, u64* p, u64 x) {
     switch (op) {
         case OP_ADD_U64: atomic_word<OP_ADD_U64>(p, x); break;

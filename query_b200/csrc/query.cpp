@@ -76,10 +76,12 @@ std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const 
     }
     for (auto& a : q->aggs) bind_and_analyze(*a, alias, *t);
     if (q->aggs.size() > 24) N1_THROW(N1GPU_E_INELIGIBLE, "more than 24 aggregates");
-    q->kp = generate_kernel(*t, q->where.get(), q->keys, q->aggs, agg_texts, (double)std::max<i64>(t->nrows, 1) * 16.0);
+    // rows any one accumulator can see over all partitions: declared (n1gpu_table_set_global_rows), else room for 16 ranks
+    const double rows_bound = t->global_rows > 0 ? (double)std::max<i64>(t->global_rows, t->nrows) : (double)std::max<i64>(t->nrows, 1) * 16.0;
+    q->kp = generate_kernel(*t, q->where.get(), q->keys, q->aggs, agg_texts, rows_bound);
     if (q->kp.word_ops.size() > 64) N1_THROW(N1GPU_E_INELIGIBLE, "more than 64 accumulator words per group");
-    q->ops.n = (int)q->kp.word_ops.size();
-    for (int w = 0; w < q->ops.n; ++w) q->ops.op[w] = q->kp.word_ops[w];
+    q->ops.n = (int)q->kp.phys_ops.size();  // physical words: what the table holds and every merge moves
+    for (int w = 0; w < q->ops.n; ++w) q->ops.op[w] = q->kp.phys_ops[w];
     if (have_device()) {
         q->kernel = jit_load(q->kp.source, q->kp.dyn_smem, q->kp.block);
         CK(cudaStreamCreateWithFlags(&q->own_stream, cudaStreamNonBlocking));
@@ -381,6 +383,7 @@ HValue sum_value(const SumState& s, bool from_zero) {
 
 std::unique_ptr<Result> Query::finalize() {
     const int W = ops.n;
+    const int LW = (int)kp.word_ops.size();
     const int rw = 2 + W;
     std::vector<u64> recs;
     i64 ngroups = 0;
@@ -454,7 +457,11 @@ std::unique_ptr<Result> Query::finalize() {
     auto final_range = [&](i64 g0, i64 g1) {
     for (i64 g = g0; g < g1; ++g) {
         const u64* r = &recs[(size_t)g * rw];
-        const u64* w = r + 2;
+        u64 w[64];  // logical words: packed counter fields decoded
+        for (int l = 0; l < LW; ++l) {
+            const u64 v = r[2 + kp.phys_of[l]];
+            w[l] = kp.bits_of[l] == 64 ? v : (v >> kp.shift_of[l]) & 0xffffffffULL;
+        }
         BitReader br(r[0], r[1]);
         for (int k = 0; k < res->nkeys; ++k) {
             const HValue kv = decode_comp(*table, kp.keys[k], br);

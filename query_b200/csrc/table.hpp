@@ -41,6 +41,7 @@ struct Column {
 struct Table {
     std::vector<Column> cols;
     i64 nrows = 0;
+    i64 global_rows = 0;  // rows of the whole keyspace over all partitions (0 = not declared)
     bool sealed = false;
     bool appended = false;
     double shred_sec = 0, upload_sec = 0;

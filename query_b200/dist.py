@@ -84,7 +84,11 @@ def agree_dictionaries_and_stats(table, group=None):
     the union of the statistics, so that all ranks compile the same kernel and pack keys identically."""
     w = world()
     if w == 1:
+        table.set_global_rows(table.num_rows)
         return
+    rows = [None] * w
+    dist.all_gather_object(rows, int(table.num_rows), group=group)
+    table.set_global_rows(sum(rows))  # exact bound for the overflow proofs (packed counters, one-word int sums)
     for c in range(len(table.columns)):
         local = table.dictionary(c)
         gathered = [None] * w

@@ -111,6 +111,32 @@ def test_every_matrix_query_compiles_for_sm100a_and_oracle_runs(name, where, key
     assert oracle_rows(docs, "d", where, keys, aggs) is not None
 
 
+def test_row_counters_share_a_table_word_only_under_a_row_bound():
+    """Behind the front cache two row counters are packed into one 64-bit table word (32-bit fields) when the declared
+    row count of the whole keyspace proves that neither field can overflow; 2^32 rows or more keep one word each."""
+    import numpy as np
+    n = 5000
+    rng = np.random.default_rng(3)
+    words = ["w%05d" % i for i in range(3000)]
+    vt = np.full(n, 4, dtype=np.uint8)
+    vt[::7] = 1
+    aggs = ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))"]
+    seen = {}
+    for rows in (None, n, 1 << 33):
+        t = q.Table(["k", "v"])
+        t.set_column("k", rng.integers(0, len(words), n).astype(np.uint32), dictionary=words)
+        t.set_column("v", rng.integers(-5, 1000, n, dtype=np.int64), tags=vt)
+        if rows is not None:
+            t.set_global_rows(rows)
+        t.seal()
+        qq = q.Query(t, "d", None, ["(`d`.`k`)"], aggs)
+        assert qq.info["mode"] == "hbm-direct"
+        seen[rows] = (qq.info["words"], "pk0" in qq.kernel_source)
+    # logical words: rows, count(v), sum(v), negatives, min, max
+    assert seen[None] == (5, True) and seen[n] == (5, True)
+    assert seen[1 << 33][1] is False and seen[1 << 33][0] >= 6
+
+
 @pytest.mark.parametrize("case", CASES + WHERE_CASES, ids=lambda c: c.id)
 def test_every_golden_plan_compiles(case):
     docs = [t for _k, t in case.docs()]

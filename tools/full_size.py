@@ -156,8 +156,11 @@ def tags_of(r, present):
 
 
 # ---- config 5: Zipf string keys, 20 % MISSING/NULL -----------------------------------------------------------------------
-def config5():
-    n = int(1_000_000_000 * SCALE)
+CONFIG5_AGGS = ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))"]
+
+
+def config5_table(n):
+    """The config-5 keyspace partition of n rows, generated on the device: (table, words, device tensors)."""
     vocab = 100_000
     words = sorted("w%06d-%x" % (i, (i * 2654435761) & 0xffffff) for i in range(vocab))
     g = torch.Generator(device=DEV).manual_seed(4)
@@ -184,11 +187,15 @@ def config5():
     t = q.Table(["k", "v"])
     t.set_column_device("k", code, tags=ktag, dictionary=words)
     t.set_column_device("v", v, tags=vtag)
+    t.set_global_rows(n)  # one partition: the exact row bound lets two row counters share a table word
     t.seal()
-    qq = q.Query(t, "d", "((`d`.`v`) is not missing)", ["(`d`.`k`)"],
-                 ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))"])
-    res, scan_ns, wall, ng = timed(qq)
-    # torch reference: group id 0 = MISSING key, 1 = NULL key, 2 + code = string
+    return t, words, (code, ktag, v, vtag)
+
+
+def config5_reference(words, tensors):
+    """torch reductions over the same device tensors: group id 0 = MISSING key, 1 = NULL key, 2 + code = string"""
+    code, ktag, v, vtag = tensors
+    vocab = len(words)
     passing = vtag != C_MISSING
     gid = torch.where(ktag == C_STRING, code.long() + 2, ktag.long())[passing]
     isint = (vtag == C_INT)[passing]
@@ -200,7 +207,11 @@ def config5():
     nneg = torch.bincount(gid[isint & (vv < 0)], minlength=G)
     mn = torch.full((G,), 2 ** 62, dtype=torch.int64, device=DEV).scatter_reduce_(0, gid[isint], vv[isint], "amin")
     mx = torch.full((G,), -2 ** 62, dtype=torch.int64, device=DEV).scatter_reduce_(0, gid[isint], vv[isint], "amax")
-    cnt, cntv, sm, nneg, mn, mx = (a.cpu().numpy() for a in (cnt, cntv, sm, nneg, mn, mx))
+    return tuple(a.cpu().numpy() for a in (cnt, cntv, sm, nneg, mn, mx))
+
+
+def config5_check(res, words, ref):
+    cnt, cntv, sm, nneg, mn, mx = ref
     index = {wd: i + 2 for i, wd in enumerate(words)}
     rows = res.rows()
     assert len(rows) == int((cnt > 0).sum()), (len(rows), int((cnt > 0).sum()))
@@ -217,6 +228,16 @@ def config5():
         else:
             assert float(a[2]) == float(sm[i]), (k, a, sm[i])
         assert a[3] == mn[i] and a[4] == mx[i], (k, a, mn[i], mx[i])
+
+
+def config5():
+    n = int(1_000_000_000 * SCALE)
+    t, words, tensors = config5_table(n)
+    qq = q.Query(t, "d", "((`d`.`v`) is not missing)", ["(`d`.`k`)"], CONFIG5_AGGS)
+    res, scan_ns, wall, ng = timed(qq)
+    ref = config5_reference(words, tensors)
+    config5_check(res, words, ref)
+    cnt, cntv = ref[0], ref[1]
     line("config5", n, qq, res, scan_ns, wall,
          {"accumulator_updates_per_s": float(cnt.sum() + 4 * cntv.sum()) / (scan_ns * 1e-9),
           "check": "every group: COUNT(*), COUNT(v), SUM(v), MIN(v), MAX(v) exact vs torch bincount/index_add_/scatter_reduce_ on the same tensors"})

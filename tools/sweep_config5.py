@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Variant sweep of the config-5 scan kernel (Zipf string keys, direct-indexed HBM table behind the front cache):
+the table is generated once on the device, then the query is compiled under each set of N1GPU_* knobs (they are
+read at compile time), timed, and every variant's groups are checked against torch reductions over the same tensors.
+
+Usage: ROWS=200000000 python tools/sweep_config5.py            (one JSON line per variant)"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import full_size as fs  # noqa: E402
+import query_b200 as q  # noqa: E402
+
+KNOBS = ["N1GPU_NO_PACK", "N1GPU_NO_MMCHECK", "N1GPU_NO_MMPREFETCH", "N1GPU_CACHE_BLOCK", "N1GPU_MIN_BLOCKS", "N1GPU_CACHE_KB", "N1GPU_NO_CACHE"]
+VARIANTS = [
+    ("round-1 kernel: one RED per word", {"N1GPU_NO_PACK": "1", "N1GPU_NO_MMCHECK": "1"}),
+    ("packed counters", {"N1GPU_NO_MMCHECK": "1"}),
+    ("packed + checked min/max", {"N1GPU_NO_MMPREFETCH": "1"}),
+    ("packed + checked, reads issued ahead (5 blocks)", {}),
+    ("same, 4 blocks x 256", {"N1GPU_MIN_BLOCKS": "4"}),
+    ("same, 3 blocks x 384", {"N1GPU_CACHE_BLOCK": "384", "N1GPU_MIN_BLOCKS": "3"}),
+    ("same, 2 blocks x 512", {"N1GPU_CACHE_BLOCK": "512"}),
+    ("same, 1 block x 1024", {"N1GPU_CACHE_BLOCK": "1024"}),
+    ("1 block x 1024, no read-ahead", {"N1GPU_CACHE_BLOCK": "1024", "N1GPU_NO_MMPREFETCH": "1"}),
+]
+
+
+def main():
+    q.init(0)
+    n = int(os.environ.get("ROWS", "200000000"))
+    t, words, tensors = fs.config5_table(n)
+    ref = fs.config5_reference(words, tensors)
+    only = os.environ.get("ONLY")
+    for name, env in VARIANTS:
+        if only and only not in name:
+            continue
+        for k in KNOBS:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        qq = q.Query(t, "d", "((`d`.`v`) is not missing)", ["(`d`.`k`)"], fs.CONFIG5_AGGS)
+        res, scan_ns, wall, ng = fs.timed(qq, reps=5)
+        fs.config5_check(res, words, ref)
+        info = qq.info
+        gbs = info["scan_bytes_per_row"] * n / scan_ns
+        print(json.dumps({"variant": name, "knobs": env, "rows": n, "words": info["words"], "registers": info["registers"], "grid": info["grid"],
+                          "block": info["block"], "scan_us": round(scan_ns / 1e3, 1), "rows_per_s": n / (scan_ns * 1e-9), "gb_per_s": round(gbs, 1),
+                          "roofline_frac": round(gbs / fs.PEAK, 3), "groups": ng, "check": "every group exact vs torch"}))
+        sys.stdout.flush()
+        del qq, res
+
+
+if __name__ == "__main__":
+    main()
