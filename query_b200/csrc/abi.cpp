@@ -148,11 +148,12 @@ int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]) {
                     else { st.int_min = std::min(st.int_min, v); st.int_max = std::max(st.int_max, v); }
                 }
                 st.class_mask |= bit(tg);
+                st.absent_rows += tg <= C_NULL;
             }
             st.ndict = (i64)c.dict.size();
         }
         stats[0] = st.class_mask; stats[1] = st.has_int; stats[2] = st.int_min; stats[3] = st.int_max;
-        stats[4] = st.has_float; stats[5] = st.ndict; stats[6] = st.empty_rank; stats[7] = 0;
+        stats[4] = st.has_float; stats[5] = st.ndict; stats[6] = st.empty_rank; stats[7] = st.absent_rows;
     });
 }
 int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]) {
@@ -162,7 +163,7 @@ int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]) {
         if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "statistics exchange happens before seal");
         Column& c = t->t.cols[col];
         c.stats.class_mask = (u32)stats[0]; c.stats.has_int = stats[1] != 0; c.stats.int_min = stats[2]; c.stats.int_max = stats[3];
-        c.stats.has_float = stats[4] != 0; c.stats.ndict = stats[5];
+        c.stats.has_float = stats[4] != 0; c.stats.ndict = stats[5]; c.stats.absent_rows = stats[7];
         c.stats.empty_rank = (!c.dict.empty() && c.dict[0].empty()) ? 0 : -1;
         c.stats_forced = true;
     });

@@ -411,6 +411,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     }
     if (kp.word_ops.empty()) rows_word();  // keep at least one word (only DISTINCT aggregates)
     const int W = (int)kp.word_ops.size();
+    kp.word_complement.assign(W, false);
+    std::vector<const Expr*> complement_opnd((size_t)W, nullptr);
 
     // ---- mode ------------------------------------------------------------------------------------------------
     if (keys.empty()) kp.mode = MODE_UNGROUPED;
@@ -448,7 +450,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 if (kind == CK_64) kp.cell_idx.push_back(kp.cache_n64++);
                 else { kp.cell_idx.push_back(kp.cache_n32); kp.cache_n32 += kind == CK_WIDE ? 2 : 1; }
             }
-            const int slot_bytes = 8 + 8 * kp.cache_n64 + 4 * kp.cache_n32;
+            const char* nk = getenv("N1GPU_NO_KEY32");
+            kp.cache_key32 = kp.key_bits <= 31 && !(nk && *nk == '1');  // u32 keys in buckets of four (cache_claim_b4)
+            const int slot_bytes = (kp.cache_key32 ? 4 : 8) + 8 * kp.cache_n64 + 4 * kp.cache_n32;
             // Measured on B200 (tools/scan_perf.py config5, 40 M rows): 256 threads + 36 KiB (five blocks per SM) 510 us,
             // 512 + 72 KiB 537 us, 1024 + 150 KiB 518 us: a larger cache raises the hit rate but the lost occupancy
             // costs as much, so the small block stays the default; both remain tuning knobs.
@@ -469,6 +473,27 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     else if (kp.key_bits <= 127) kp.mode = MODE_HASH128;
     else N1_THROW(N1GPU_E_INELIGIBLE, "group key needs %d bits (> 127) after packing", kp.key_bits);
     kp.est_groups = (i64)std::min(est, 4e18);
+
+    // ---- complemented counters --------------------------------------------------------------------------------------
+    // Behind the front cache every accumulator update of a cached row is a shared-memory atomic, the unit the kernel
+    // runs out of first.  "cnt:x" (rows where x > NULL) over a plain column counts the other rows when the column
+    // statistics say those are the minority.  Every partition must decide alike, so the decision only uses agreed
+    // numbers: the declared keyspace rows with exchanged statistics, this table's own rows otherwise.
+    if (kp.cache_slots > 0 && w_rows == 0) {
+        const char* nc = getenv("N1GPU_NO_COMPLEMENT");
+        bool forced = false;
+        for (auto& c : t.cols) forced = forced || c.stats_forced;
+        const i64 denom = t.global_rows > 0 ? std::max(t.global_rows, t.nrows) : (forced ? 0 : t.nrows);
+        for (size_t a = 0; a < aggs.size() && !(nc && *nc == '1') && denom > 0; ++a) {
+            const Expr& e = *aggs[a];
+            if (e.star || e.distinct || e.ops.empty()) continue;
+            const Expr* opnd = e.ops[0].get();
+            if (opnd->kind != EK::FIELD || opnd->col < 0) continue;
+            auto it = shared.find("cnt:" + opnd->str());
+            if (it == shared.end() || it->second == w_rows) continue;
+            if (t.cols[opnd->col].stats.absent_rows * 2 < denom) { kp.word_complement[it->second] = true; complement_opnd[it->second] = opnd; }
+        }
+    }
 
     // ---- physical words ------------------------------------------------------------------------------------------
     // Behind the front cache a miss pays one L2 reduction per word it touches, and the request path SM -> L2 is what
@@ -552,6 +577,12 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     std::set<int> emitted_sets;
     std::set<int> emitted;  // a shared word is updated once per row, by the first aggregate that owns it
     if (w_rows >= 0) { g.line(strf("ACC(%d, OP_ADD_U64, 1);  // rows", w_rows)); emitted.insert(w_rows); }
+    for (int w = 0; w < W; ++w) {
+        if (!kp.word_complement[w]) continue;
+        const std::string o = g.emit(*complement_opnd[w], nullptr);
+        g.line(strf("if (%s.c <= C_NULL) { ACC(%d, OP_ADD_U64, 1); }  // rows NOT counted by count(%s)", o.c_str(), w, complement_opnd[w]->str().c_str()));
+        emitted.insert(w);
+    }
     for (size_t a = 0; a < kp.aggs.size(); ++a) {
         const AggPlan& ap = kp.aggs[a];
         const Expr& e = *aggs[a];
@@ -642,6 +673,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     std::vector<int> pre_words;  // physical min / max / or words whose current value a miss reads ahead (direct table)
     std::string s;
     s += "// generated by libn1gpu codegen: one specialised scan kernel for this Filter + Group chain\n";
+    { const char* nc = getenv("N1GPU_NO_CELL_CHECK"); if (nc && *nc == '1') s += "#define NQ_NO_CELL_CHECK 1\n"; }
     s += "#include \"n1ql_device.cuh\"\n";
     s += strf("#define NQ_W %d\n", W);
     if (smem_dense) s += strf("#define NQ_G %lld\n", (long long)kp.dense_slots);
@@ -721,11 +753,18 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "    const u64 cap = p.cap_mask + 1;\n";
         if (kp.cache_slots) {
             s += "    extern __shared__ u64 s_dyn[];\n";
-            s += "    u64* const s_ckey = s_dyn;            // [NQ_CS] cached group keys (all ones = empty)\n";
-            s += strf("    u64* const s_c64 = s_dyn + NQ_CS;     // [%d][NQ_CS] 64-bit cells\n", kp.cache_n64);
-            s += strf("    u32* const s_c32 = (u32*)(s_dyn + %d * NQ_CS);  // [%d][NQ_CS] 32-bit cells\n", 1 + kp.cache_n64, kp.cache_n32);
+            if (kp.cache_key32) {
+                s += strf("    u64* const s_c64 = s_dyn;             // [%d][NQ_CS] 64-bit cells\n", kp.cache_n64);
+                s += strf("    u32* const s_ckey = (u32*)(s_dyn + %d * NQ_CS);  // [NQ_CS] cached group keys in buckets of four (all ones = empty)\n", kp.cache_n64);
+                s += strf("    u32* const s_c32 = s_ckey + NQ_CS;    // [%d][NQ_CS] 32-bit cells\n", kp.cache_n32);
+            } else {
+                s += "    u64* const s_ckey = s_dyn;            // [NQ_CS] cached group keys (all ones = empty)\n";
+                s += strf("    u64* const s_c64 = s_dyn + NQ_CS;     // [%d][NQ_CS] 64-bit cells\n", kp.cache_n64);
+                s += strf("    u32* const s_c32 = (u32*)(s_dyn + %d * NQ_CS);  // [%d][NQ_CS] 32-bit cells\n", 1 + kp.cache_n64, kp.cache_n32);
+            }
+            s += "    (void)s_c64; (void)s_c32;\n";
             s += "    for (int i = threadIdx.x; i < NQ_CS; i += NQ_BLOCK) {\n";
-            s += "        s_ckey[i] = NQ_U64_MAX;\n";
+            s += kp.cache_key32 ? "        s_ckey[i] = 0xffffffffu;\n" : "        s_ckey[i] = NQ_U64_MAX;\n";
             for (int w = 0; w < W; ++w) {
                 const int ci = kp.cell_idx[w], op = kp.word_ops[w];
                 switch (kp.cell_kind[w]) {
@@ -773,7 +812,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += key_code;
         s += "                    kk[j] = klo;\n";
         s += "                    ++nlook;\n";
-        if (kp.key_bits <= 32) s += "                    cs[j] = cache_on ? cache_claim_n(s_ckey, NQ_CS, (u32)klo * 0x9E3779B1u, klo) : -1;\n";
+        if (kp.cache_key32) s += "                    cs[j] = cache_on ? cache_claim_b4(s_ckey, NQ_CS / 4, (u32)klo * 0x9E3779B1u, (u32)klo) : -1;\n";
+        else if (kp.key_bits <= 32) s += "                    cs[j] = cache_on ? cache_claim_n(s_ckey, NQ_CS, (u32)klo * 0x9E3779B1u, klo) : -1;\n";
         else s += "                    cs[j] = cache_on ? cache_claim_n(s_ckey, NQ_CS, (u32)(mix64(klo) >> 32), klo) : -1;\n";
         s += "                    nhit += cs[j] >= 0;\n";
         s += "            }\n";
@@ -849,7 +889,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "    __syncthreads();\n";
         s += "    for (int i = threadIdx.x; i < NQ_CS; i += NQ_BLOCK) {\n";
         s += "        const u64 key = s_ckey[i];\n";
-        s += "        if (key == NQ_U64_MAX) continue;\n";
+        s += kp.cache_key32 ? "        if (key == 0xffffffffULL) continue;\n" : "        if (key == NQ_U64_MAX) continue;\n";
         if (kp.dense_global) s += "        const i64 slot = (i64)key;\n";
         else {
             s += "        const i64 slot = table_insert64(p.keys, p.cap_mask, key, nullptr);\n";

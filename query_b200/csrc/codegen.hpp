@@ -60,6 +60,9 @@ struct KernelPlan {
     std::vector<int> phys_ops;           // op of every physical word (what Query::ops holds)
     std::vector<int> phys_of, shift_of;  // logical word -> physical word, bit offset of its field
     std::vector<int> bits_of;            // field width (64 = the whole word)
+    // A COUNT(x) counter over a column whose values are mostly present counts the rows where x is MISSING / NULL instead
+    // (the rarer event: fewer shared-memory atomics per row); finalize() reads it as rows-in-group minus the word.
+    std::vector<bool> word_complement;
     std::vector<PackComp> keys;
     int key_bits = 0;
     i64 dense_slots = 0;
@@ -69,6 +72,7 @@ struct KernelPlan {
     bool pdl = false;            // launched with programmatic stream serialization (ungrouped scans)
     int dyn_smem = 0;            // dynamic shared memory the kernel is launched with
     int block = 256;             // threads per block (a block scans block * 4 rows per iteration)
+    bool cache_key32 = false;    // front-cache keys are u32 in 16-byte buckets of four (packed key <= 31 bits)
     int cache_slots = 0;         // HASH64: slots of the per-block shared-memory front cache (0 = none)
     // front-cache cell of every word: kind (CK_*) and index of its first cell among the 32-bit / 64-bit cell arrays
     std::vector<int> cell_kind, cell_idx;

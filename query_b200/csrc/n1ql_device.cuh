@@ -408,6 +408,30 @@ NQ_DEV int cache_claim_n(u64* ckeys, u32 slots, u32 hash, u64 key) {
     return -1;
 }
 
+// The same for packed keys of <= 31 bits: u32 keys in 16-byte buckets of four.  One 128-bit shared-memory load
+// fetches the whole bucket, so a lookup costs one instruction and one latency where the linear probe above pays up to
+// four dependent 64-bit loads - once the cache is full, every row of a key that is not cached walked all four.
+// Slots only ever change from empty to a key and every thread tries the slots of a bucket in the same order, so a key
+// settles in exactly one slot (and the block-end flush is additive, so even a duplicate would be harmless).
+NQ_DEV int cache_claim_b4(u32* ckeys, u32 nbuckets, u32 hash, u32 key) {
+    const u32 b = __umulhi(hash, nbuckets) * 4u;
+    u32 k[4];
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]) : "r"((u32)__cvta_generic_to_shared(ckeys + b)) : "memory");
+    if (k[0] == key) return (int)b;
+    if (k[1] == key) return (int)b + 1;
+    if (k[2] == key) return (int)b + 2;
+    if (k[3] == key) return (int)b + 3;
+    if (k[3] != 0xffffffffu) return -1;  // slots fill in order: the last one taken means the bucket is full
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (k[i] != 0xffffffffu) continue;
+        const u32 old = atomicCAS(&ckeys[b + i], 0xffffffffu, key);
+        if (old == 0xffffffffu || old == key) return (int)b + i;
+    }
+    return -1;
+}
+
 // Cells of the front cache.  Shared memory has native 32-bit atomics only (a 64-bit atomicAdd/Min/Max on shared
 // memory compiles to a compare-and-swap loop, 3-9x slower and collapsing under same-key contention), so a cached
 // accumulator word is kept in 32-bit cells wherever its per-block value provably fits or can be split:
@@ -422,9 +446,16 @@ NQ_DEV void cache_add_wide(u32* lo, u32* hi, u64 x) {
     const u32 h = (u32)(x >> 32) + ((u32)(old + xl) < xl ? 1u : 0u);
     if (h) atomicAdd(hi, h);
 }
+// (read first: a shared-memory load costs about half an atomic, and a group's min / max settle after a few rows; a
+// stale read can only cause an atomic that was not needed)
 template <int OP> NQ_DEV void cache_mm32(u32* c, u64 x, u64 bias) {
     const u32 v = (u32)(x - bias) + 1u;
-    if (OP == OP_MIN_I64 || OP == OP_MIN_U64) atomicMin(c, v); else atomicMax(c, v);
+#ifdef NQ_NO_CELL_CHECK
+    const u32 cur = (OP == OP_MIN_I64 || OP == OP_MIN_U64) ? 0xffffffffu : 0u;
+#else
+    const u32 cur = *(volatile u32*)c;
+#endif
+    if (OP == OP_MIN_I64 || OP == OP_MIN_U64) { if (v < cur) atomicMin(c, v); } else { if (v > cur) atomicMax(c, v); }
 }
 NQ_DEV void cache_or32(u32* c, u32 bits) {
     if ((*(volatile u32*)c & bits) != bits) atomicOr(c, bits);

@@ -462,6 +462,7 @@ std::unique_ptr<Result> Query::finalize() {
             const u64 v = r[2 + kp.phys_of[l]];
             w[l] = kp.bits_of[l] == 64 ? v : (v >> kp.shift_of[l]) & 0xffffffffULL;
         }
+        for (int l = 0; l < LW; ++l) if (kp.word_complement[l]) w[l] = w[0] - w[l];  // word 0 = rows in the group
         BitReader br(r[0], r[1]);
         for (int k = 0; k < res->nkeys; ++k) {
             const HValue kv = decode_comp(*table, kp.keys[k], br);

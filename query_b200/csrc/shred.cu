@@ -298,13 +298,14 @@ __global__ void k_dict_remap(const u8* __restrict__ tags, const i64* __restrict_
         if (out32) out32[row] = r;
     }
 }
-// column statistics: stats[0] class mask, [1] int min, [2] int max (as i64), [3] has float
+// column statistics: stats[0] class mask, [1] int min, [2] int max (as i64), [3] has float, [4] MISSING / NULL rows
 __global__ void k_col_stats(const u8* __restrict__ tags, const i64* __restrict__ payload, i64 nrows, u64* stats) {
-    u64 mask = 0, hasf = 0;
+    u64 mask = 0, hasf = 0, absent = 0;
     i64 mn = NQ_I64_MAX, mx = NQ_I64_MIN;
     for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (i64)gridDim.x * blockDim.x) {
         const int t = tags[row];
         mask |= 1ULL << t;
+        absent += t <= C_NULL;
         if (t == C_INT && payload) { const i64 v = payload[row]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
         else if (t == C_FLOAT) hasf = 1;
     }
@@ -313,7 +314,9 @@ __global__ void k_col_stats(const u8* __restrict__ tags, const i64* __restrict__
     hasf = block_reduce_word<OP_OR_U64>(hasf, scratch);
     u64 rmn = block_reduce_word<OP_MIN_I64>((u64)mn, scratch);
     u64 rmx = block_reduce_word<OP_MAX_I64>((u64)mx, scratch);
+    absent = block_reduce_word<OP_ADD_U64>(absent, scratch);
     if (threadIdx.x == 0) {
+        atomicAdd(&stats[4], absent);
         atomicOr(&stats[0], mask);
         atomicMin((i64*)&stats[1], (i64)rmn);
         atomicMax((i64*)&stats[2], (i64)rmx);

@@ -384,6 +384,7 @@ void Table::seal() {
             }
             if (t > C_OTHER) N1_THROW(N1GPU_E_INVALID, "bad class byte %d", (int)t);
             st.class_mask |= bit(t);
+            st.absent_rows += t <= C_NULL;
         }
         st.ndict = (i64)col.dict.size();
         st.empty_rank = (!col.dict.empty() && col.dict[0].empty()) ? 0 : -1;

@@ -19,6 +19,7 @@ struct ColumnStats {
     double flt_min = 0, flt_max = 0;
     i64 ndict = 0;
     i64 empty_rank = -1;  // rank of "" in the dictionary, -1 if absent
+    i64 absent_rows = 0;  // rows whose class is MISSING or NULL (decides which way a COUNT(x) counter counts)
     bool uniform_tag() const { return class_mask != 0 && (class_mask & (class_mask - 1)) == 0; }
 };
 

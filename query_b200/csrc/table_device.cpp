@@ -163,12 +163,12 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     phase("fix-up rows");
     // ---- statistics (class mask, int range) -------------------------------------------------------------------------
     DevBuf d_stats;
-    d_stats.alloc((size_t)ncols * 32);
-    std::vector<u64> h_stats((size_t)ncols * 4);
-    for (int c = 0; c < ncols; ++c) { h_stats[c * 4 + 0] = 0; h_stats[c * 4 + 1] = (u64)INT64_MAX; h_stats[c * 4 + 2] = (u64)INT64_MIN; h_stats[c * 4 + 3] = 0; }
+    d_stats.alloc((size_t)ncols * 64);
+    std::vector<u64> h_stats((size_t)ncols * 8, 0);
+    for (int c = 0; c < ncols; ++c) { h_stats[c * 8 + 1] = (u64)INT64_MAX; h_stats[c * 8 + 2] = (u64)INT64_MIN; }
     CK(cudaMemcpyAsync(d_stats.p, h_stats.data(), h_stats.size() * 8, cudaMemcpyHostToDevice, s));
     if (ndocs)
-        for (int c = 0; c < ncols; ++c) launch_col_stats(cols[c].d_tags.as<u8>(), pay8[c].as<i64>(), ndocs, d_stats.as<u64>() + c * 4, s);
+        for (int c = 0; c < ncols; ++c) launch_col_stats(cols[c].d_tags.as<u8>(), pay8[c].as<i64>(), ndocs, d_stats.as<u64>() + c * 8, s);
     CK(cudaMemcpyAsync(h_stats.data(), d_stats.p, h_stats.size() * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
 
@@ -180,11 +180,12 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     for (int c = 0; c < ncols; ++c) {
         Column& col = cols[c];
         ColumnStats st;
-        st.class_mask = (u32)h_stats[c * 4 + 0];
+        st.class_mask = (u32)h_stats[c * 8 + 0];
         st.has_int = (st.class_mask & bit(C_INT)) != 0;
-        st.int_min = st.has_int ? (i64)h_stats[c * 4 + 1] : 0;
-        st.int_max = st.has_int ? (i64)h_stats[c * 4 + 2] : 0;
-        st.has_float = h_stats[c * 4 + 3] != 0;
+        st.int_min = st.has_int ? (i64)h_stats[c * 8 + 1] : 0;
+        st.int_max = st.has_int ? (i64)h_stats[c * 8 + 2] : 0;
+        st.has_float = h_stats[c * 8 + 3] != 0;
+        st.absent_rows = (i64)h_stats[c * 8 + 4];
         col.dict.clear();
         const bool has_str = st.class_mask & bit(C_STRING);
         col.width = (st.class_mask & M_NUM) ? 8 : (has_str ? 4 : 0);
@@ -301,12 +302,12 @@ void Table::set_column_device(int c, int width, const void* dev_payload, const u
     // canonical numbers + statistics, on the device
     if (width == 8) launch_canon_floats(col.d_tags.as<u8>(), col.d_payload.as<i64>(), n, nullptr);
     DevBuf d_stats;
-    d_stats.alloc(32);
-    u64 h_stats[4] = {0, (u64)INT64_MAX, (u64)INT64_MIN, 0};
-    CK(cudaMemcpy(d_stats.p, h_stats, 32, cudaMemcpyHostToDevice));
+    d_stats.alloc(64);
+    u64 h_stats[8] = {0, (u64)INT64_MAX, (u64)INT64_MIN, 0, 0, 0, 0, 0};
+    CK(cudaMemcpy(d_stats.p, h_stats, 64, cudaMemcpyHostToDevice));
     // a 4-byte column holds string ranks only: the kernel reads payload words of INT rows, of which there are none
     if (n) launch_col_stats(col.d_tags.as<u8>(), width == 8 ? col.d_payload.as<i64>() : nullptr, n, d_stats.as<u64>(), nullptr);
-    CK(cudaMemcpy(h_stats, d_stats.p, 32, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_stats, d_stats.p, 64, cudaMemcpyDeviceToHost));
     ColumnStats st;
     st.class_mask = (u32)h_stats[0];
     if (st.class_mask >> (C_OTHER + 1)) N1_THROW(N1GPU_E_INVALID, "bad class byte in column %d", c);
@@ -317,6 +318,7 @@ void Table::set_column_device(int c, int width, const void* dev_payload, const u
     st.int_min = st.has_int ? (i64)h_stats[1] : 0;
     st.int_max = st.has_int ? (i64)h_stats[2] : 0;
     st.has_float = h_stats[3] != 0;
+    st.absent_rows = (i64)h_stats[4];
     st.ndict = (i64)col.dict.size();
     st.empty_rank = (!col.dict.empty() && col.dict[0].empty()) ? 0 : -1;
     if (!col.stats_forced) col.stats = st;

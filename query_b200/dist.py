@@ -107,6 +107,7 @@ def agree_dictionaries_and_stats(table, group=None):
         g[3] = max(maxs) if maxs else 0
         g[4] = int(any(s[4] != 0 for s in allst))
         g[5] = len(merged)
+        g[7] = sum(s[7] for s in allst)  # MISSING / NULL rows of the whole keyspace
         if merged != list(local):  # identical dictionaries (e.g. handed in with the columns): nothing to remap
             table.import_dictionary(c, merged)
         table.set_stats(c, g)

@@ -12,17 +12,32 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import full_size as fs  # noqa: E402
 import query_b200 as q  # noqa: E402
 
-KNOBS = ["N1GPU_NO_PACK", "N1GPU_NO_MMCHECK", "N1GPU_NO_MMPREFETCH", "N1GPU_CACHE_BLOCK", "N1GPU_MIN_BLOCKS", "N1GPU_CACHE_KB", "N1GPU_NO_CACHE"]
+KNOBS = ["N1GPU_NO_PACK", "N1GPU_NO_MMCHECK", "N1GPU_NO_MMPREFETCH", "N1GPU_CACHE_BLOCK", "N1GPU_MIN_BLOCKS", "N1GPU_CACHE_KB", "N1GPU_NO_CACHE",
+         "N1GPU_NO_KEY32", "N1GPU_NO_COMPLEMENT", "N1GPU_NO_CELL_CHECK"]
+R1 = {"N1GPU_NO_PACK": "1", "N1GPU_NO_MMCHECK": "1", "N1GPU_NO_KEY32": "1", "N1GPU_NO_COMPLEMENT": "1", "N1GPU_NO_CELL_CHECK": "1"}
+
+
+def r1_plus(*on, **extra):
+    """the round-1 kernel with the named improvements switched on"""
+    env = {k: v for k, v in R1.items() if k not in on}
+    env.update(extra)
+    return env
+
+
 VARIANTS = [
-    ("round-1 kernel: one RED per word", {"N1GPU_NO_PACK": "1", "N1GPU_NO_MMCHECK": "1"}),
-    ("packed counters", {"N1GPU_NO_MMCHECK": "1"}),
-    ("packed + checked min/max", {"N1GPU_NO_MMPREFETCH": "1"}),
-    ("packed + checked, reads issued ahead (5 blocks)", {}),
-    ("same, 4 blocks x 256", {"N1GPU_MIN_BLOCKS": "4"}),
-    ("same, 3 blocks x 384", {"N1GPU_CACHE_BLOCK": "384", "N1GPU_MIN_BLOCKS": "3"}),
-    ("same, 2 blocks x 512", {"N1GPU_CACHE_BLOCK": "512"}),
-    ("same, 1 block x 1024", {"N1GPU_CACHE_BLOCK": "1024"}),
-    ("1 block x 1024, no read-ahead", {"N1GPU_CACHE_BLOCK": "1024", "N1GPU_NO_MMPREFETCH": "1"}),
+    ("round-1 kernel", dict(R1)),
+    ("+ bucketed u32 cache keys", r1_plus("N1GPU_NO_KEY32")),
+    ("+ cached min/max read before the atomic", r1_plus("N1GPU_NO_CELL_CHECK")),
+    ("+ complemented count(v)", r1_plus("N1GPU_NO_COMPLEMENT")),
+    ("all three shared-memory changes", r1_plus("N1GPU_NO_KEY32", "N1GPU_NO_CELL_CHECK", "N1GPU_NO_COMPLEMENT")),
+    ("all three + packed table counters", r1_plus("N1GPU_NO_KEY32", "N1GPU_NO_CELL_CHECK", "N1GPU_NO_COMPLEMENT", "N1GPU_NO_PACK")),
+    ("everything (table min/max read ahead)", {}),
+    ("everything, reads not ahead", {"N1GPU_NO_MMPREFETCH": "1"}),
+    ("everything, 4 blocks x 256", {"N1GPU_MIN_BLOCKS": "4"}),
+    ("everything, 2 blocks x 512", {"N1GPU_CACHE_BLOCK": "512"}),
+    ("everything, 1 block x 1024", {"N1GPU_CACHE_BLOCK": "1024"}),
+    ("all three, 1 block x 1024", r1_plus("N1GPU_NO_KEY32", "N1GPU_NO_CELL_CHECK", "N1GPU_NO_COMPLEMENT", N1GPU_CACHE_BLOCK="1024")),
+    ("all three, 2 blocks x 512", r1_plus("N1GPU_NO_KEY32", "N1GPU_NO_CELL_CHECK", "N1GPU_NO_COMPLEMENT", N1GPU_CACHE_BLOCK="512")),
 ]
 
 
