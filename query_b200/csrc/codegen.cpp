@@ -580,7 +580,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     for (int w = 0; w < W; ++w) {
         if (!kp.word_complement[w]) continue;
         const std::string o = g.emit(*complement_opnd[w], nullptr);
-        g.line(strf("if (%s.c <= C_NULL) { ACC(%d, OP_ADD_U64, 1); }  // rows NOT counted by count(%s)", o.c_str(), w, complement_opnd[w]->str().c_str()));
+        g.line(strf("ACCIF(%d, OP_ADD_U64, 1, %s.c <= C_NULL);  // rows NOT counted by count(%s)", w, o.c_str(), complement_opnd[w]->str().c_str()));
         emitted.insert(w);
     }
     for (size_t a = 0; a < kp.aggs.size(); ++a) {
@@ -597,7 +597,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         };
         auto ACCIF = [&](const std::string& cond, int w, int op, const std::string& x) {
             if (!emitted.insert(w).second) return;
-            g.line(strf("if (%s) { ACC(%d, %s, %s); }", cond.c_str(), w, op_name(op), x.c_str()));
+            g.line(strf("ACCIF(%d, %s, %s, %s);", w, op_name(op), x.c_str(), cond.c_str()));
         };
         if (ap.distinct && !emitted_sets.insert(ap.distinct_id).second) {
             // the entry set of this operand is already fed by an earlier aggregate
@@ -676,6 +676,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     { const char* nc = getenv("N1GPU_NO_CELL_CHECK"); if (nc && *nc == '1') s += "#define NQ_NO_CELL_CHECK 1\n"; }
     s += "#include \"n1ql_device.cuh\"\n";
     s += strf("#define NQ_W %d\n", W);
+    s += "#define ACCIF(k, OP, x, c) if (c) { ACC(k, OP, x); }\n";
     if (smem_dense) s += strf("#define NQ_G %lld\n", (long long)kp.dense_slots);
     s += "__constant__ int nq_ops[NQ_W] = {";
     for (int w = 0; w < W; ++w) s += strf("%s%d", w ? ", " : "", kp.word_ops[w]);
@@ -690,14 +691,15 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     else if (cached) {
         s += strf("#define NQ_CS %d\n", kp.cache_slots);
         // table update of a cache miss, per logical word: packed counters gather in a register (one RED per physical
-        // word and row, issued after the row's aggregate code); min / max / or words read the slot first (an L2 load is
-        // cheaper than a reduction and, once a group has settled, almost every row leaves them unchanged)
-        // In the direct-indexed table the slot is the key itself, so those reads are issued for all four rows before
-        // the cached rows are updated (phase 2): their L2 latency overlaps that work instead of stalling every row.
-        const char* nm = getenv("N1GPU_NO_MMCHECK");
-        const char* npf = getenv("N1GPU_NO_MMPREFETCH");
-        const bool mmcheck = !(nm && *nm == '1');
-        const bool mmpre = mmcheck && kp.dense_global && !(npf && *npf == '1');
+        // word and row, issued after the row's aggregate code); min / max / or words can read the slot first
+        // (in the direct-indexed table the slot is the key itself, so those reads can be issued for all four rows
+        // before the cached rows are updated)
+        // Measured on config 5 (tools/sweep_config5.py, 200 M rows): reading first LOSES 20 % (1 277 -> 1 563 us; read ahead
+        // 1 766 us) - the kernel is bound by LSU wavefronts, and a scattered load costs as many as the reduction it
+        // saves.  Both stay experiment knobs: N1GPU_MMCHECK=1 (read first), N1GPU_MMCHECK=2 (read ahead).
+        const char* nm = getenv("N1GPU_MMCHECK");
+        const bool mmcheck = nm && (*nm == '1' || *nm == '2');
+        const bool mmpre = mmcheck && kp.dense_global && *nm == '2';
         for (int w = 0; w < W; ++w) {
             const int P = kp.phys_of[w], op = kp.word_ops[w];
             const bool chk = mmcheck && op != OP_ADD_U64 && op != OP_ADD_F64;

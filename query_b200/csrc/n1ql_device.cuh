@@ -418,11 +418,12 @@ NQ_DEV int cache_claim_b4(u32* ckeys, u32 nbuckets, u32 hash, u32 key) {
     u32 k[4];
     asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]) : "r"((u32)__cvta_generic_to_shared(ckeys + b)) : "memory");
-    if (k[0] == key) return (int)b;
-    if (k[1] == key) return (int)b + 1;
-    if (k[2] == key) return (int)b + 2;
-    if (k[3] == key) return (int)b + 3;
-    if (k[3] != 0xffffffffu) return -1;  // slots fill in order: the last one taken means the bucket is full
+    int s = -1;  // select chain, not branches: the lanes of a warp match in different slots
+    s = k[3] == key ? (int)b + 3 : s;
+    s = k[2] == key ? (int)b + 2 : s;
+    s = k[1] == key ? (int)b + 1 : s;
+    s = k[0] == key ? (int)b : s;
+    if (s >= 0 || k[3] != 0xffffffffu) return s;  // found, or full (slots fill in order: the last one taken = full)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (k[i] != 0xffffffffu) continue;

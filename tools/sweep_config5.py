@@ -12,32 +12,30 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import full_size as fs  # noqa: E402
 import query_b200 as q  # noqa: E402
 
-KNOBS = ["N1GPU_NO_PACK", "N1GPU_NO_MMCHECK", "N1GPU_NO_MMPREFETCH", "N1GPU_CACHE_BLOCK", "N1GPU_MIN_BLOCKS", "N1GPU_CACHE_KB", "N1GPU_NO_CACHE",
+KNOBS = ["N1GPU_NO_PACK", "N1GPU_MMCHECK", "N1GPU_CACHE_BLOCK", "N1GPU_MIN_BLOCKS", "N1GPU_CACHE_KB", "N1GPU_NO_CACHE",
          "N1GPU_NO_KEY32", "N1GPU_NO_COMPLEMENT", "N1GPU_NO_CELL_CHECK"]
-R1 = {"N1GPU_NO_PACK": "1", "N1GPU_NO_MMCHECK": "1", "N1GPU_NO_KEY32": "1", "N1GPU_NO_COMPLEMENT": "1", "N1GPU_NO_CELL_CHECK": "1"}
+R1 = {"N1GPU_NO_PACK": "1", "N1GPU_NO_KEY32": "1", "N1GPU_NO_COMPLEMENT": "1", "N1GPU_NO_CELL_CHECK": "1"}
 
 
 def r1_plus(*on, **extra):
-    """the round-1 kernel with the named improvements switched on"""
+    """the round-1 layout with the named improvements switched on"""
     env = {k: v for k, v in R1.items() if k not in on}
     env.update(extra)
     return env
 
 
 VARIANTS = [
-    ("round-1 kernel", dict(R1)),
+    ("round-1 layout", dict(R1)),
     ("+ bucketed u32 cache keys", r1_plus("N1GPU_NO_KEY32")),
     ("+ cached min/max read before the atomic", r1_plus("N1GPU_NO_CELL_CHECK")),
     ("+ complemented count(v)", r1_plus("N1GPU_NO_COMPLEMENT")),
-    ("all three shared-memory changes", r1_plus("N1GPU_NO_KEY32", "N1GPU_NO_CELL_CHECK", "N1GPU_NO_COMPLEMENT")),
-    ("all three + packed table counters", r1_plus("N1GPU_NO_KEY32", "N1GPU_NO_CELL_CHECK", "N1GPU_NO_COMPLEMENT", "N1GPU_NO_PACK")),
-    ("everything (table min/max read ahead)", {}),
-    ("everything, reads not ahead", {"N1GPU_NO_MMPREFETCH": "1"}),
-    ("everything, 4 blocks x 256", {"N1GPU_MIN_BLOCKS": "4"}),
-    ("everything, 2 blocks x 512", {"N1GPU_CACHE_BLOCK": "512"}),
-    ("everything, 1 block x 1024", {"N1GPU_CACHE_BLOCK": "1024"}),
-    ("all three, 1 block x 1024", r1_plus("N1GPU_NO_KEY32", "N1GPU_NO_CELL_CHECK", "N1GPU_NO_COMPLEMENT", N1GPU_CACHE_BLOCK="1024")),
-    ("all three, 2 blocks x 512", r1_plus("N1GPU_NO_KEY32", "N1GPU_NO_CELL_CHECK", "N1GPU_NO_COMPLEMENT", N1GPU_CACHE_BLOCK="512")),
+    ("+ packed table counters", r1_plus("N1GPU_NO_PACK")),
+    ("default (all four)", {}),
+    ("default, table min/max read first", {"N1GPU_MMCHECK": "1"}),
+    ("default, 4 blocks x 256", {"N1GPU_MIN_BLOCKS": "4"}),
+    ("default, 2 blocks x 512", {"N1GPU_CACHE_BLOCK": "512"}),
+    ("default, 1 block x 1024", {"N1GPU_CACHE_BLOCK": "1024"}),
+    ("default, 6 blocks x 192", {"N1GPU_CACHE_BLOCK": "192", "N1GPU_MIN_BLOCKS": "6"}),
 ]
 
 
