@@ -453,13 +453,17 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             const char* nk = getenv("N1GPU_NO_KEY32");
             kp.cache_key32 = kp.key_bits <= 31 && !(nk && *nk == '1');  // u32 keys in buckets of four (cache_claim_b4)
             const int slot_bytes = (kp.cache_key32 ? 4 : 8) + 8 * kp.cache_n64 + 4 * kp.cache_n32;
-            // Measured on B200 (tools/scan_perf.py config5, 40 M rows): 256 threads + 36 KiB (five blocks per SM) 510 us,
-            // 512 + 72 KiB 537 us, 1024 + 150 KiB 518 us: a larger cache raises the hit rate but the lost occupancy
-            // costs as much, so the small block stays the default; both remain tuning knobs.
+            // The five 256-thread blocks of an SM each cache the same hot keys in their own 44 KiB; one 1024-thread block
+            // caches five times as many distinct keys in the SM's 220 KiB.  Measured on config 5 (Zipf over 100 k keys,
+            // tools/sweep_config5.py, 200 M rows): 5 x 256 1 242 us, 2 x 512 1 201 us, 1 x 1024 1 161 us - every miss is
+            // 3-4 scattered L2 reductions, one LSU wavefront each, and LSU wavefronts are what the kernel runs out of.
+            // So: the small block when its cache holds every group anyway or the key domain is far beyond any cache
+            // (uniform high-cardinality keys: occupancy matters more), the large block in between.
             const char* kb = getenv("N1GPU_CACHE_KB");      // shared memory per block spent on the cache
             const char* bt = getenv("N1GPU_CACHE_BLOCK");   // threads per block
             const char* lb = getenv("N1GPU_MIN_BLOCKS");    // resident blocks per SM
-            kp.block = bt && atoi(bt) >= 64 ? atoi(bt) / 32 * 32 : 256;
+            const double slots_small = 44.0 * 1024 / slot_bytes, slots_large = 220.0 * 1024 / slot_bytes;
+            kp.block = bt && atoi(bt) >= 64 ? atoi(bt) / 32 * 32 : (est > 0.8 * slots_small && est <= 64.0 * slots_large ? 1024 : 256);
             cache_blocks = lb && atoi(lb) > 0 ? atoi(lb) : std::max(1, 1280 / kp.block);
             // the resident blocks of an SM share 220 of its 227 KiB (each block also pays 1 KiB of system shared memory)
             const i64 budget = (kb && atoi(kb) > 0 ? atoi(kb) : 220 / cache_blocks) * 1024;

@@ -76,15 +76,49 @@ def test_matrix_against_oracle(name, where, keys, aggs):
 _GROUPED = [x for x in QUERIES if x[2]]
 
 
-@pytest.mark.parametrize("knob", ["N1GPU_NO_DIRECT", "N1GPU_NO_BITMAP", "N1GPU_NO_OFFSET_PACK", "N1GPU_NO_CACHE"])
+@pytest.mark.parametrize("knob", ["N1GPU_NO_DIRECT", "N1GPU_NO_BITMAP", "N1GPU_NO_OFFSET_PACK", "N1GPU_NO_CACHE", "N1GPU_NO_PACK",
+                                  "N1GPU_NO_KEY32", "N1GPU_NO_COMPLEMENT", "N1GPU_CACHE_BLOCK=1024", "N1GPU_CACHE_BLOCK=256",
+                                  "N1GPU_MMCHECK=1", "N1GPU_MMCHECK=2"])
 @pytest.mark.parametrize("name,where,keys,aggs", _GROUPED, ids=[x[0] for x in _GROUPED])
 def test_grouped_matrix_through_the_alternate_layouts(name, where, keys, aggs, knob, monkeypatch):
-    """The planner picks direct-indexed tables, DISTINCT bitmaps, offset-packed keys and the shared-memory front cache
-    whenever statistics allow; the layouts they replace (open addressing, hash sets, class-bits packing, uncached
-    updates) stay reachable for wider keys and are kept under test by switching each choice off."""
-    monkeypatch.setenv(knob, "1")
+    """The planner picks direct-indexed tables, DISTINCT bitmaps, offset-packed keys, the shared-memory front cache
+    (u32 keys in buckets, one large or five small blocks per SM), packed table counters and complemented COUNT(x)
+    counters whenever statistics allow; the layouts they replace (open addressing, hash sets, class-bits packing,
+    uncached updates, 64-bit cache keys, one counter per word) stay reachable for wider keys / larger keyspaces and are
+    kept under test by switching each choice off (or, for the tuning knobs, on)."""
+    k, _, v = knob.partition("=")
+    monkeypatch.setenv(k, v or "1")
     docs = make_docs(3000, seed=22)
     run_both(docs, "d", where, keys, aggs, "%s %s" % (name, knob))
+
+
+@pytest.mark.parametrize("block", ["256", "1024"])
+def test_skewed_string_keys_with_missing_and_null(block, monkeypatch):
+    """BASELINE config 5 shape at oracle size: Zipf-skewed string keys, MISSING / NULL keys and values, more groups than
+    the front cache holds (misses take the table path), both block shapes; bit-exact against the oracle."""
+    monkeypatch.setenv("N1GPU_CACHE_BLOCK", block)
+    monkeypatch.setenv("N1GPU_CACHE_KB", "2")  # a 2 KiB cache: most of the 3 000 keys miss
+    rng = np.random.default_rng(11)
+    n, vocab = 20000, 3000
+    w = np.arange(1, vocab + 1, dtype=np.float64) ** -1.1
+    ranks = rng.choice(vocab, size=n, p=w / w.sum())
+    perm = rng.permutation(vocab)
+    docs = []
+    for i in range(n):
+        parts = []
+        r = rng.integers(0, 10)
+        if r == 1:
+            parts.append('"k": null')
+        elif r > 1:
+            parts.append('"k": "w%05d"' % perm[ranks[i]])
+        r = rng.integers(0, 10)
+        if r == 1:
+            parts.append('"v": null')
+        elif r > 1:
+            parts.append('"v": %d' % rng.integers(-1000, 1000000))
+        docs.append("{" + ", ".join(parts) + "}")
+    run_both(docs, "d", "((`d`.`v`) is not missing)", ["(`d`.`k`)"],
+             ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))", "avg((`d`.`v`))"], "config5 shape block=" + block)
 
 
 @pytest.mark.parametrize("n", [0, 1, 3, 127, 128, 129, 1023, 1024, 1025, 4097])
