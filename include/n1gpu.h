@@ -230,6 +230,31 @@ int n1gpu_result_free(n1gpu_result* r);
  * index of the first child the caller must still run.  datastore_root is cbq-engine's -datastore dir.  */
 typedef struct n1gpu_operator n1gpu_operator;
 int n1gpu_plan_build(const char* plan_json, const char* datastore_root, n1gpu_operator** out, int* rest_index);
+/* The same, also taking over the operators BEHIND FinalGroup when every one of them up to FinalProject is within the
+ * subset: Let (LETTING, plan/let.go), Filter (HAVING, plan/filter.go), InitialProject and
+ * FinalProject (plan/project.go; no star, raw or DISTINCT projection), Order / Offset / Limit (plan/order.go,
+ * plan/offset.go, plan/limit.go) of the enclosing Sequence.  Their expressions may use group keys, the aggregates of
+ * the group operators, LETTING variables, explicit projection aliases (ORDER BY) and the operators of Filter.
+ * `rest_index` then points behind the consumed children of the chain's Sequence, `outer_rest_index` behind those
+ * consumed from the enclosing Sequence (0: none).  A plan whose tail is not eligible builds like n1gpu_plan_build
+ * (n1gpu_operator_tail_operators reports an empty list) and the caller keeps its own operators after FinalGroup.
+ * Replaces: execution/let.go:50-62, filter.go:49-61, project_initial.go:52-144, project_final.go:51-59,
+ * order.go:50-170 (ties: the reference's sort.Sort is not stable, here they keep group order), offset.go:53-83,
+ * limit.go:53-85.                                                                                                  */
+int n1gpu_plan_build_tail(const char* plan_json, const char* datastore_root, n1gpu_operator** out, int* rest_index,
+                          int* outer_rest_index);
+/* Comma-separated names of the consumed tail operators, in execution order ("" = none).              */
+int n1gpu_operator_tail_operators(const n1gpu_operator* op, char* buf, int64_t cap, int64_t* len);
+/* Runs the tail over the result of run_once: the rows FinalProject sends, as a JSON array of objects
+ * (field names sorted, MISSING values left out: value/object.go:246-255); *rows = number of rows.    */
+int n1gpu_operator_run_tail(n1gpu_operator* op, const n1gpu_result* r, char* buf, int64_t cap, int64_t* len, int64_t* rows);
+/* Builds a result for this operator from flat arrays in n1gpu_result_fetch layout (string payloads index the
+ * nstrings strings blob[offsets[i] .. offsets[i+1])): the groups of several ranks gathered in one place - each
+ * owner finalises its share of the groups and ORDER BY / LIMIT need all of them - or groups that a
+ * caller's own operators produced.  The tail runs over it like over the result of run_once.          */
+int n1gpu_operator_import_result(const n1gpu_operator* op, int64_t ngroups, const uint8_t* key_cls, const int64_t* key_val,
+                                 const uint8_t* agg_cls, const int64_t* agg_val, const char* blob, const int64_t* offsets,
+                                 int64_t nstrings, n1gpu_result** out);
 /* execution.Operator.RunOnce: scans, filters, groups; the result is what FinalGroup would have sent. */
 int n1gpu_operator_run_once(n1gpu_operator* op, n1gpu_result** out);
 int n1gpu_operator_send_stop(n1gpu_operator* op);

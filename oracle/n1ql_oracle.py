@@ -783,6 +783,9 @@ class Aggregate(Expr):
         return "%s(%s%s)" % (self.name, "distinct " if self.distinct else "",
                              "*" if self.operand is None else str(self.operand))
 
+    def evaluate(self, item):  # algebra/aggregate.go:97-118: the value FinalGroup left under the aggregate's text
+        return item[AGGREGATES][str(self)]
+
     def default(self):
         return None
 
@@ -1211,11 +1214,15 @@ def group_key(item, keys):
     return tuple(parts)
 
 
-class GroupRow:
-    __slots__ = ("keys", "aggregates")
+AGGREGATES = "\x00aggregates"  # the "aggregates" attachment of a group item (never a valid field name of an item)
 
-    def __init__(self, keys, aggregates):
-        self.keys, self.aggregates = keys, aggregates
+
+class GroupRow:
+    __slots__ = ("keys", "aggregates", "item")
+
+    def __init__(self, keys, aggregates, item=None):
+        # item: the group's representative, the first item that reached InitialGroup (group_initial.go:82-88)
+        self.keys, self.aggregates, self.item = keys, aggregates, item
 
     def __repr__(self):
         return "GroupRow(%r, %r)" % (self.keys, self.aggregates)
@@ -1247,7 +1254,7 @@ def run_chain(docs, alias, where, group_keys, aggregates, streams=1):
         g = groups.get(gk)
         if g is None:
             g = groups[gk] = GroupRow([k.evaluate(item) for k in group_keys],
-                                      {str(a): a.default() for a in agg_list})
+                                      {str(a): a.default() for a in agg_list}, item)
         for a in agg_list:
             g.aggregates[str(a)] = a.initial(item, g.aggregates[str(a)])
 
@@ -1267,7 +1274,94 @@ def run_chain(docs, alias, where, group_keys, aggregates, streams=1):
             g.aggregates[str(a)] = a.final(g.aggregates[str(a)])
         out.append(g)
     if not group_keys and not out:  # group_final.go:108-117
-        out.append(GroupRow([], {str(a): a.default() for a in agg_list}))
+        out.append(GroupRow([], {str(a): a.default() for a in agg_list}, {}))
+    return out
+
+
+def expr_alias(e):
+    """Expression.Alias(): nav_field.go:55-57,260-262 (last field name), identifier.go:66-68, else "" (base.go:163-165)."""
+    if isinstance(e, (Field, Identifier)):
+        return e.name
+    return ""
+
+
+def run_tail(groups, letting=(), having=None, terms=None, order=(), offset=None, limit=None, with_sort_keys=False):
+    """The operators behind FinalGroup (planner/build_select_sub.go:217-235,276-296; build_select.go:75-110), one item
+    at a time over run_chain's GroupRows:
+      Let      execution/let.go:50-62          every binding evaluated on the incoming item, set on a copy
+      Filter   execution/filter.go:49-61       HAVING: forward when Truth()
+      InitialProject  execution/project_initial.go:98-144   projection object by alias (algebra/result.go:358-374:
+                      AS, else the expression's Alias(), else $1, $2 ...); a MISSING value leaves the field out
+                      (value/object.go:246-255); explicit AS names are also set on the scope the sort sees
+      Order    execution/order.go:119-166      Collate per sort term, descending flips it (sort.Sort: ties unordered)
+      Offset / Limit  execution/offset.go:53-83, limit.go:53-85 (operands: numbers equal to their Trunc)
+      FinalProject    execution/project_final.go:51-59      the projection object is the row
+    letting: [(variable, expr)], terms: [(expr, as or None)], order: [(expr, descending)].  Expressions are Expr
+    objects or Stringer text.  Returns the list of row dicts (python values); with_sort_keys=True returns
+    (rows, sort-key tuples) so that a caller can compare modulo the order of ties."""
+    P = lambda e: parse(e) if isinstance(e, str) else e
+    letting = [(v, P(e)) for v, e in letting]
+    having = P(having) if having is not None else None
+    terms = [(P(e), a or "") for e, a in (terms or [])]
+    order = [(P(e), bool(d)) for e, d in order]
+    aliases, n = [], 1
+    for e, a in terms:
+        al = a or expr_alias(e)
+        if not al:
+            al, n = "$%d" % n, n + 1
+        aliases.append(al)
+    rows = []
+    for g in groups:
+        item = dict(g.item or {})
+        item[AGGREGATES] = g.aggregates
+        lv = dict(item)
+        for var, e in letting:
+            v = e.evaluate(item)
+            if v is MISSING:
+                lv.pop(var, None)
+            else:
+                lv[var] = v
+        if having is not None and not truth(having.evaluate(lv)):
+            continue
+        proj, scope = {}, dict(lv)
+        for (e, a), al in zip(terms, aliases):
+            v = e.evaluate(lv)
+            if v is MISSING:
+                proj.pop(al, None)
+            else:
+                proj[al] = v
+            if a:
+                if v is MISSING:
+                    scope.pop(a, None)  # ScopeValue.SetField(MISSING) unsets its own field: the parent's shows through
+                    if a in lv:
+                        scope[a] = lv[a]
+                else:
+                    scope[a] = v
+        keys = tuple(e.evaluate(scope) for e, _d in order)
+        rows.append((proj, keys))
+    if order:
+        import functools
+
+        def cmp(x, y):
+            for (e, desc), a, b in zip(order, x[1], y[1]):
+                c = collate(a, b)
+                if c:
+                    return -c if desc else c
+            return 0
+        rows.sort(key=functools.cmp_to_key(cmp))
+
+    def operand(e, what):
+        v = P(e).evaluate({}) if not isinstance(e, (int, float)) else e
+        if vtype(v) != T_NUMBER or math.trunc(v) != v:
+            raise ValueError("Invalid %s value %r." % (what, v))
+        return int(v)
+    if offset is not None:
+        rows = rows[max(operand(offset, "OFFSET"), 0):]
+    if limit is not None:
+        rows = rows[:max(operand(limit, "LIMIT"), 0)]
+    out = [{k: to_python(v) for k, v in p.items()} for p, _k in rows]
+    if with_sort_keys:
+        return out, [tuple("\x00MISSING" if v is MISSING else to_python(v) for v in k) for _p, k in rows]
     return out
 
 

@@ -447,13 +447,79 @@ class Mailbox:
 class Operator:
     """execution.Operator handle built from the reference's plan JSON (n1gpu_plan_build)."""
 
-    def __init__(self, plan_json, datastore_root):
+    def __init__(self, plan_json, datastore_root, tail=False):
+        """tail=True also takes over the eligible operators behind FinalGroup (n1gpu_plan_build_tail)."""
         if not isinstance(plan_json, str):
             plan_json = json.dumps(plan_json)
         self._h = C.c_void_p()
-        rest = C.c_int()
-        check(lib().n1gpu_plan_build(plan_json.encode("utf-8"), datastore_root.encode("utf-8"), C.byref(self._h), C.byref(rest)))
+        rest, outer = C.c_int(), C.c_int()
+        if tail:
+            check(lib().n1gpu_plan_build_tail(plan_json.encode("utf-8"), datastore_root.encode("utf-8"), C.byref(self._h), C.byref(rest), C.byref(outer)))
+        else:
+            check(lib().n1gpu_plan_build(plan_json.encode("utf-8"), datastore_root.encode("utf-8"), C.byref(self._h), C.byref(rest)))
         self.rest_index = rest.value
+        self.outer_rest_index = outer.value
+
+    @property
+    def tail_operators(self):
+        n = C.c_int64()
+        check(lib().n1gpu_operator_tail_operators(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value + 1)
+        check(lib().n1gpu_operator_tail_operators(self._h, buf, n.value + 1, C.byref(n)))
+        text = buf.value.decode("utf-8")
+        return text.split(",") if text else []
+
+    def import_result(self, groups):
+        """groups: list of (key values, aggregate values) as Result.rows() yields them (MISSING / None / bool / int /
+        float / str; aggregates in the order given to the group operators) -> a Result the tail can run over
+        (n1gpu_operator_import_result)."""
+        strings, index = [], {}
+
+        def enc(v):
+            if v is MISSING:
+                return 0, 0
+            if v is None:
+                return 1, 0
+            if v is False:
+                return 2, 0
+            if v is True:
+                return 3, 0
+            if isinstance(v, int):
+                return 4, v
+            if isinstance(v, float):
+                return 5, int(np.float64(v).view(np.int64))
+            if isinstance(v, str):
+                if v not in index:
+                    index[v] = len(strings)
+                    strings.append(v.encode("utf-8"))
+                return 6, index[v]
+            raise TypeError("not a scalar value: %r" % (v,))
+        n = len(groups)
+        nk = len(groups[0][0]) if n else 0
+        na = len(groups[0][1]) if n else 0
+        kc, kv = np.zeros(n * nk, dtype=np.uint8), np.zeros(n * nk, dtype=np.int64)
+        ac, av = np.zeros(n * na, dtype=np.uint8), np.zeros(n * na, dtype=np.int64)
+        for g, (ks, ag) in enumerate(groups):
+            for k, v in enumerate(ks):
+                kc[g * nk + k], kv[g * nk + k] = enc(v)
+            for a, v in enumerate(ag):
+                ac[g * na + a], av[g * na + a] = enc(v)
+        offs = np.zeros(len(strings) + 1, dtype=np.int64)
+        if strings:
+            np.cumsum([len(b) for b in strings], out=offs[1:])
+        r = C.c_void_p()
+        check(lib().n1gpu_operator_import_result(self._h, n, kc.ctypes.data_as(_lib._U8P), kv.ctypes.data_as(_lib._I64P),
+                                                 ac.ctypes.data_as(_lib._U8P), av.ctypes.data_as(_lib._I64P), b"".join(strings),
+                                                 offs.ctypes.data_as(_lib._I64P), len(strings), C.byref(r)))
+        return Result(r)
+
+    def run_tail(self, result):
+        """The rows FinalProject sends (HAVING / projection / ORDER BY / OFFSET / LIMIT applied): list of dicts."""
+        n, rows = C.c_int64(), C.c_int64()
+        check(lib().n1gpu_operator_run_tail(self._h, result._h, None, 0, C.byref(n), C.byref(rows)))
+        buf = C.create_string_buffer(n.value + 1)
+        check(lib().n1gpu_operator_run_tail(self._h, result._h, buf, n.value + 1, C.byref(n), C.byref(rows)))
+        return json.loads(buf.value.decode("utf-8"))
 
     def run_once(self):
         r = C.c_void_p()

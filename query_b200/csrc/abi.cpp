@@ -392,6 +392,15 @@ int n1gpu_result_stats(const n1gpu_result* r, int64_t stats[8]) {
 }
 int n1gpu_result_free(n1gpu_result* r) { delete r; return N1GPU_OK; }
 
+static int copy_out(const std::string& s, char* buf, int64_t cap, int64_t* len) {
+    if (len) *len = (int64_t)s.size();
+    if (buf && cap > 0) {
+        size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+        memcpy(buf, s.data(), n);
+        buf[n] = '\0';
+    }
+    return N1GPU_OK;
+}
 // ---- plan level -----------------------------------------------------------------------------------------------------
 int n1gpu_plan_build(const char* plan_json, const char* datastore_root, n1gpu_operator** out, int* rest_index) {
     return guard([&] {
@@ -402,21 +411,77 @@ int n1gpu_plan_build(const char* plan_json, const char* datastore_root, n1gpu_op
         *out = new n1gpu_operator{std::move(op)};
     });
 }
+int n1gpu_plan_build_tail(const char* plan_json, const char* datastore_root, n1gpu_operator** out, int* rest_index, int* outer_rest_index) {
+    return guard([&] {
+        REQUIRE(plan_json); REQUIRE(datastore_root); REQUIRE(out);
+        int rest = 0, outer = 0;
+        auto op = execution::BuildWithTail(plan_json, datastore_root, true, &rest, &outer);
+        if (rest_index) *rest_index = rest;
+        if (outer_rest_index) *outer_rest_index = outer;
+        *out = new n1gpu_operator{std::move(op)};
+    });
+}
+int n1gpu_operator_tail_operators(const n1gpu_operator* op, char* buf, int64_t cap, int64_t* len) {
+    std::string s;
+    int rc = guard([&] {
+        REQUIRE(op);
+        for (auto& n : op->op->tail.operators) { if (!s.empty()) s += ","; s += n; }
+    });
+    return rc == N1GPU_OK ? copy_out(s, buf, cap, len) : rc;
+}
+int n1gpu_operator_run_tail(n1gpu_operator* op, const n1gpu_result* r, char* buf, int64_t cap, int64_t* len, int64_t* rows) {
+    std::string s;
+    int rc = guard([&] {
+        REQUIRE(op); REQUIRE(r);
+        if (op->op->tail.empty()) N1_THROW(N1GPU_E_INVALID, "the operator was built without a tail (n1gpu_plan_build_tail, eligible plan)");
+        i64 n = 0;
+        s = op->op->tail.Run(*r->r, &n);
+        if (rows) *rows = n;
+    });
+    return rc == N1GPU_OK ? copy_out(s, buf, cap, len) : rc;
+}
+int n1gpu_operator_import_result(const n1gpu_operator* op, int64_t ngroups, const uint8_t* key_cls, const int64_t* key_val,
+                                 const uint8_t* agg_cls, const int64_t* agg_val, const char* blob, const int64_t* offsets,
+                                 int64_t nstrings, n1gpu_result** out) {
+    return guard([&] {
+        REQUIRE(op); REQUIRE(out);
+        if (ngroups < 0 || nstrings < 0) N1_THROW(N1GPU_E_INVALID, "negative count");
+        const Query& Q = *op->op->query;
+        std::unique_ptr<Result> r(new Result());
+        r->nkeys = (int)Q.keys.size();
+        r->naggs = (int)Q.aggs.size();
+        r->ngroups = ngroups;
+        r->agg_texts = Q.agg_texts;
+        r->key_texts = Q.key_texts;
+        r->alias = Q.alias;
+        for (auto& k : Q.keys) {
+            std::vector<std::string> path;
+            if (k->kind == EK::FIELD && k->col >= 0) path = Q.table->cols[k->col].path;
+            r->key_paths.push_back(path);
+        }
+        const size_t nk = (size_t)ngroups * r->nkeys, na = (size_t)ngroups * r->naggs;
+        if ((nk && (!key_cls || !key_val)) || (na && (!agg_cls || !agg_val))) N1_THROW(N1GPU_E_INVALID, "missing value arrays");
+        r->key_cls.assign(key_cls, key_cls + nk); r->key_val.assign(key_val, key_val + nk);
+        r->agg_cls.assign(agg_cls, agg_cls + na); r->agg_val.assign(agg_val, agg_val + na);
+        for (int64_t i = 0; i < nstrings; ++i) r->strings.emplace_back(blob + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
+        auto check = [&](const std::vector<u8>& cls, const std::vector<i64>& val) {
+            for (size_t i = 0; i < cls.size(); ++i) {
+                if (cls[i] > C_STRING) N1_THROW(N1GPU_E_INVALID, "value class %d is not a scalar class", (int)cls[i]);
+                if (cls[i] == C_STRING && (val[i] < 0 || val[i] >= nstrings)) N1_THROW(N1GPU_E_INVALID, "string index out of range");
+            }
+        };
+        check(r->key_cls, r->key_val);
+        check(r->agg_cls, r->agg_val);
+        r->stats[1] = ngroups;
+        *out = new n1gpu_result{std::move(r)};
+    });
+}
 int n1gpu_operator_run_once(n1gpu_operator* op, n1gpu_result** out) {
     return guard([&] { REQUIRE(op); REQUIRE(out); *out = new n1gpu_result{op->op->RunOnce()}; });
 }
 int n1gpu_operator_send_stop(n1gpu_operator* op) {
     if (!op) return N1GPU_E_INVALID;
     op->op->SendStop();
-    return N1GPU_OK;
-}
-static int copy_out(const std::string& s, char* buf, int64_t cap, int64_t* len) {
-    if (len) *len = (int64_t)s.size();
-    if (buf && cap > 0) {
-        size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
-        memcpy(buf, s.data(), n);
-        buf[n] = '\0';
-    }
     return N1GPU_OK;
 }
 int n1gpu_operator_marshal_json(n1gpu_operator* op, char* buf, int64_t cap, int64_t* len) {

@@ -178,6 +178,11 @@ struct Builder : plan::Visitor {
     std::string root;
     std::unique_ptr<GpuGroupAggregate> found;
     int rest = 0;
+    plan::Sequence* chain_seq = nullptr;   // the Sequence that holds the chain
+    plan::Sequence* outer_seq = nullptr;   // the Sequence that holds chain_seq as a direct child (ORDER BY / LIMIT plans)
+    size_t outer_index = 0;                // ... at this position
+    plan::Sequence* cur_parent = nullptr;  // direct-parent bookkeeping while descending
+    size_t cur_index = 0;
     std::string why = "plan holds no PrimaryScan/Fetch/Filter/InitialGroup/IntermediateGroup/FinalGroup chain";
 
     void VisitPrimaryScan(plan::PrimaryScan&) override {}
@@ -187,8 +192,8 @@ struct Builder : plan::Visitor {
     void VisitIntermediateGroup(plan::Group&) override {}
     void VisitFinalGroup(plan::Group&) override {}
     void VisitOpaque(plan::Opaque&) override {}
-    void VisitParallel(plan::Parallel& p) override { if (!found) p.child->Accept(*this); }
-    void VisitAuthorize(plan::Authorize& a) override { if (!found) a.child->Accept(*this); }
+    void VisitParallel(plan::Parallel& p) override { if (!found) { cur_parent = nullptr; p.child->Accept(*this); } }
+    void VisitAuthorize(plan::Authorize& a) override { if (!found) { cur_parent = nullptr; a.child->Accept(*this); } }
 
     // Flattens [Filter?, InitialGroup] out of Parallel(Sequence[..]) / Sequence[..] / bare operators
     // (execution/build.go:455-491 elides Parallel at parallelism 1 and single-child Sequences).
@@ -200,6 +205,8 @@ struct Builder : plan::Visitor {
 
     void VisitSequence(plan::Sequence& s) override {
         if (found) return;
+        plan::Sequence* const my_parent = cur_parent;
+        const size_t my_index = cur_index;
         auto& ch = s.children;
         auto* scan = ch.size() > 0 ? dynamic_cast<plan::PrimaryScan*>(ch[0].get()) : nullptr;
         auto* fetch = ch.size() > 1 ? dynamic_cast<plan::Fetch*>(ch[1].get()) : nullptr;
@@ -240,10 +247,18 @@ struct Builder : plan::Visitor {
                 op->aggregates = initial->aggregates;
                 found = std::move(op);
                 rest = (int)i + 2;
+                chain_seq = &s;
+                outer_seq = my_parent;
+                outer_index = my_index;
                 return;
             }
         }
-        for (auto& c : ch) { if (found) return; c->Accept(*this); }
+        for (size_t c = 0; c < ch.size(); ++c) {
+            if (found) return;
+            cur_parent = &s;
+            cur_index = c;
+            ch[c]->Accept(*this);
+        }
     }
 };
 
@@ -289,6 +304,11 @@ struct Tree {
 }  // namespace
 
 std::unique_ptr<GpuGroupAggregate> Build(const std::string& plan_json, const std::string& datastore_root, int* rest_index) {
+    return BuildWithTail(plan_json, datastore_root, false, rest_index, nullptr);
+}
+
+std::unique_ptr<GpuGroupAggregate> BuildWithTail(const std::string& plan_json, const std::string& datastore_root, bool want_tail,
+                                                 int* rest_index, int* outer_rest) {
     json::Node root;
     if (!json::parse(plan_json, root)) N1_THROW(N1GPU_E_PARSE, "plan JSON does not parse");
     const json::Node* pn = &root;
@@ -309,6 +329,42 @@ std::unique_ptr<GpuGroupAggregate> Build(const std::string& plan_json, const std
     op->table = resident_table(op->keyspace_dir, paths);
     op->query = Query::compile(op->table.get(), alias, op->condition.empty() ? nullptr : op->condition.c_str(), op->keys, op->aggregates);
     op->serv_sec = now_sec() - t0;
+    if (outer_rest) *outer_rest = 0;
+    if (want_tail) {
+        // The operators behind FinalGroup: whole children of the chain's Sequence (a Parallel(Sequence[...]) counts as
+        // one), then plain operators of the enclosing Sequence.  All or nothing up to FinalProject.
+        GroupTail t;
+        t.keyspace_alias = alias;
+        auto as_node = [](plan::Operator* o, json::Node& n) { return json::parse(o->MarshalJSON(), n); };
+        bool ok = true;
+        size_t c = (size_t)b.rest;
+        for (; c < b.chain_seq->children.size(); ++c) {
+            std::vector<plan::Operator*> flat;
+            Builder::flatten(b.chain_seq->children[c].get(), flat);
+            size_t k = 0;
+            for (; k < flat.size(); ++k) {
+                json::Node n;
+                if (!as_node(flat[k], n) || !t.add(n, op->keys, op->aggregates)) break;
+            }
+            if (k == flat.size()) continue;
+            ok = k == 0 && t.final_project;  // a foreign operator behind a finished tail ends it; anything else voids it
+            break;
+        }
+        t.inner_consumed = ok ? (int)(c - (size_t)b.rest) : 0;
+        if (ok && b.outer_seq && c == b.chain_seq->children.size()) {
+            for (size_t k = b.outer_index + 1; k < b.outer_seq->children.size(); ++k) {
+                plan::Operator* o = b.outer_seq->children[k].get();
+                json::Node n;
+                if (dynamic_cast<plan::Parallel*>(o) || dynamic_cast<plan::Sequence*>(o) || !as_node(o, n) || !t.add(n, op->keys, op->aggregates)) break;
+                ++t.outer_consumed;
+            }
+        }
+        if (ok && t.final_project) {
+            if (outer_rest) *outer_rest = t.outer_consumed ? (int)b.outer_index + 1 + t.outer_consumed : 0;
+            b.rest += t.inner_consumed;
+            op->tail = std::move(t);
+        }
+    }
     if (rest_index) *rest_index = b.rest;
     return op;
 }
@@ -346,6 +402,11 @@ std::string GpuGroupAggregate::MarshalJSON() const {
     json::quote(term.keyspace, s);
     s += ",\"namespace\":";
     json::quote(term.nspace, s);
+    if (!tail.empty()) {  // the operators behind FinalGroup this operator also stands for
+        s += ",\"tail\":[";
+        for (size_t i = 0; i < tail.operators.size(); ++i) { if (i) s += ","; json::quote(tail.operators[i], s); }
+        s += "]";
+    }
     if (query) {
         static const char* modes[] = {"ungrouped", "dense-shared-memory", "hbm-hash-64", "hbm-hash-128"};
         s += std::string(",\"kernel\":{\"mode\":\"") + modes[query->kp.mode] + "\",\"accumulator_words\":" + std::to_string(query->ops.n) +

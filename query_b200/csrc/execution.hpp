@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "group_tail.hpp"
 #include "json.hpp"
 #include "query.hpp"
 
@@ -116,6 +117,9 @@ class GpuGroupAggregate {
     i64 in_docs = 0, out_docs = 0;
     double exec_sec = 0, serv_sec = 0;
     bool ran = false;
+    // The operators after FinalGroup that this operator also replaces when all of them are within the subset
+    // (SURVEY.md 8f rows 1-2): Let / Filter (LETTING, HAVING), InitialProject, FinalProject, Order, Offset, Limit.
+    GroupTail tail;
 
     std::unique_ptr<Result> RunOnce();  // execution.Operator.RunOnce (once per operator: util.Once)
     void SendStop();                    // execution.Operator.SendStop
@@ -126,6 +130,11 @@ class GpuGroupAggregate {
 // in the plan, builds the GPU operator for its prefix; *rest_index = first child of that Sequence the
 // caller still runs.  Throws Error(N1GPU_E_INELIGIBLE) when the plan does not contain the chain.
 std::unique_ptr<GpuGroupAggregate> Build(const std::string& plan_json, const std::string& datastore_root, int* rest_index);
+// The same, also taking over the operators after FinalGroup (op->tail) when the whole run up to FinalProject is eligible.
+// rest_index then points behind the consumed operators of the chain's Sequence and *outer_rest behind those consumed
+// from the enclosing Sequence (0: none).  want_tail = false builds exactly what Build does.
+std::unique_ptr<GpuGroupAggregate> BuildWithTail(const std::string& plan_json, const std::string& datastore_root, bool want_tail,
+                                                 int* rest_index, int* outer_rest);
 
 std::string ResultToJSON(const Result& r);
 

@@ -49,11 +49,15 @@ def round_float(x, prec):
 
 class Case:
     def __init__(self, cid, ref, casefile, index, keyspace, alias, where, keys, aggs, select,
-                 having=None, order=None, limit=None, key_names=None):
+                 having=None, order=None, limit=None, key_names=None, tail=None):
         self.id, self.ref, self.casefile, self.index = cid, ref, casefile, index
         self.keyspace, self.alias = keyspace, alias
         self.where, self.keys, self.aggs = where, keys, aggs
         self.select, self.having, self.order, self.limit = select, having, order, limit
+        # the same HAVING / projection / ORDER BY / LIMIT as the reference planner formalises them (Stringer text of the
+        # operators behind FinalGroup): dict(having=, terms=[(expr, as)], order=[(expr, desc)], limit=).  None: the
+        # statement uses a scalar function (ROUND) or a stand-in aggregate, which keeps its tail off the substituted path.
+        self.tail = tail
 
     @property
     def golden(self):
@@ -147,25 +151,29 @@ CASES = [
     Case("fs_groupby_count", "test/filestore/json/default/cases/case_group_by_having.json:3-15",
          "filestore/case_group_by_having", 0, "filestore/catalog", "catalog",
          None, ["(`catalog`.`type`)"], ["count(*)"],
-         [("type", K(0)), ("count", A("count(*)"))], order=["type"]),
+         [("type", K(0)), ("count", A("count(*)"))], order=["type"],
+         tail=dict(terms=[("(`catalog`.`type`)", None), ("count(*)", "count")], order=[("(`catalog`.`type`)", False)])),
     Case("fs_all_aggs_nogroup", "test/filestore/json/default/cases/case_group_by_having.json:17-29",
          "filestore/case_group_by_having", 1, "filestore/catalog", "catalog",
          None, [], ["min(%s)" % PLIST, "max(%s)" % PLIST, "avg(%s)" % PLIST, "sum(%s)" % PLIST, "count(%s)" % PLIST],
          [("min", A("min(%s)" % PLIST)), ("max", A("max(%s)" % PLIST)), ("avg", A("avg(%s)" % PLIST)),
-          ("sum", A("sum(%s)" % PLIST)), ("count", A("count(%s)" % PLIST))]),
+          ("sum", A("sum(%s)" % PLIST)), ("count", A("count(%s)" % PLIST))],
+         tail=dict(terms=[("min(%s)" % PLIST, "min"), ("max(%s)" % PLIST, "max"), ("avg(%s)" % PLIST, "avg"), ("sum(%s)" % PLIST, "sum"), ("count(%s)" % PLIST, "count")])),
     Case("fs_all_aggs_group", "test/filestore/json/default/cases/case_group_by_having.json:31-52",
          "filestore/case_group_by_having", 2, "filestore/catalog", "catalog",
          None, ["(`catalog`.`type`)"],
          ["min(%s)" % PLIST, "max(%s)" % PLIST, "avg(%s)" % PLIST, "sum(%s)" % PLIST, "count(%s)" % PLIST],
          [("type", K(0)), ("min", A("min(%s)" % PLIST)), ("max", A("max(%s)" % PLIST)), ("avg", A("avg(%s)" % PLIST)),
-          ("sum", A("sum(%s)" % PLIST)), ("count", A("count(%s)" % PLIST))], order=["type"]),
+          ("sum", A("sum(%s)" % PLIST)), ("count", A("count(%s)" % PLIST))], order=["type"],
+         tail=dict(terms=[("(`catalog`.`type`)", None)] + [("min(%s)" % PLIST, "min"), ("max(%s)" % PLIST, "max"), ("avg(%s)" % PLIST, "avg"), ("sum(%s)" % PLIST, "sum"), ("count(%s)" % PLIST, "count")], order=[("(`catalog`.`type`)", False)])),
     Case("fs_all_aggs_having", "test/filestore/json/default/cases/case_group_by_having.json:54-67",
          "filestore/case_group_by_having", 3, "filestore/catalog", "catalog",
          None, ["(`catalog`.`type`)"],
          ["min(%s)" % PLIST, "max(%s)" % PLIST, "avg(%s)" % PLIST, "sum(%s)" % PLIST, "count(%s)" % PLIST],
          [("type", K(0)), ("min", A("min(%s)" % PLIST)), ("max", A("max(%s)" % PLIST)), ("avg", A("avg(%s)" % PLIST)),
           ("sum", A("sum(%s)" % PLIST)), ("count", A("count(%s)" % PLIST))],
-         having=lambda k, a: a["count(%s)" % PLIST] > 1, order=["type"]),
+         having=lambda k, a: a["count(%s)" % PLIST] > 1, order=["type"],
+         tail=dict(having="(1 < count(%s))" % PLIST, terms=[("(`catalog`.`type`)", None)] + [("min(%s)" % PLIST, "min"), ("max(%s)" % PLIST, "max"), ("avg(%s)" % PLIST, "avg"), ("sum(%s)" % PLIST, "sum"), ("count(%s)" % PLIST, "count")], order=[("(`catalog`.`type`)", False)])),
     # case :161-180 has an ANY ... SATISFIES term (ineligible); all 3 catalog docs satisfy it, so the
     # eligible remainder of the predicate is checked instead.
     Case("fs_float_filter_sum", "test/filestore/json/default/cases/case_group_by_having.json:161-180",
@@ -175,30 +183,36 @@ CASES = [
          [("title", K(0)), ("$1", A("sum(((`catalog`.`dimensions`).`length`))")),
           ("$2", A("sum(((`catalog`.`dimensions`).`width`))"))],
          having=lambda k, a: a["sum(((`catalog`.`dimensions`).`width`))"] > 1 and a["sum(((`catalog`.`dimensions`).`length`))"] > 1,
-         order=["title"]),
+         order=["title"],
+         tail=dict(having="((1 < %s) and (1 < %s))" % ("sum(((`catalog`.`dimensions`).`width`))", "sum(((`catalog`.`dimensions`).`length`))"), terms=[("(`catalog`.`title`)", None), ("sum(((`catalog`.`dimensions`).`length`))", None), ("sum(((`catalog`.`dimensions`).`width`))", None)], order=[("(`catalog`.`title`)", False)])),
     Case("fs_two_keys", "test/filestore/json/default/cases/case_group_by_having.json:182-208",
          "filestore/case_group_by_having", 9, "filestore/user_profile", "user_profile",
          None, ["((`user_profile`.`personal_details`).`state`)",
                 "(((`user_profile`.`profile_details`).`loyalty`).`membership_type`)"], ["count(*)"],
          [("state", K(0)), ("membership_type", K(1)), ("gold_members", A("count(*)"))],
-         having=lambda k, a: k[1] == "Gold", order=["state"]),
+         having=lambda k, a: k[1] == "Gold", order=["state"],
+         tail=dict(having="(%s = \"Gold\")" % "(((`user_profile`.`profile_details`).`loyalty`).`membership_type`)", terms=[("((`user_profile`.`personal_details`).`state`)", None), ("(((`user_profile`.`profile_details`).`loyalty`).`membership_type`)", None), ("count(*)", "gold_members")], order=[("((`user_profile`.`personal_details`).`state`)", False)])),
     Case("fs_theme", "test/filestore/json/default/cases/case_group_by_having.json:210-237",
          "filestore/case_group_by_having", 10, "filestore/user_profile", "user_profile",
          None, ["(((`user_profile`.`profile_details`).`prefs`).`ui_theme`)"], ["count(*)"],
-         [("ui_theme", K(0)), ("theme_usage", A("count(*)"))], order=["ui_theme"]),
+         [("ui_theme", K(0)), ("theme_usage", A("count(*)"))], order=["ui_theme"],
+         tail=dict(terms=[("(((`user_profile`.`profile_details`).`prefs`).`ui_theme`)", None), ("count(*)", "theme_usage")], order=[("(((`user_profile`.`profile_details`).`prefs`).`ui_theme`)", False)])),
     Case("fs_count_distinct", "test/filestore/json/default/cases/case_group_by_having.json:239-252",
          "filestore/case_group_by_having", 11, "filestore/jobs", "jobs",
          None, ["(`jobs`.`join_yr`)"], ["count(distinct (`jobs`.`job_title`))"],
-         [("distinct_title_count", A("count(distinct (`jobs`.`job_title`))")), ("join_yr", K(0))], order=["join_yr"]),
+         [("distinct_title_count", A("count(distinct (`jobs`.`job_title`))")), ("join_yr", K(0))], order=["join_yr"],
+         tail=dict(terms=[("count(distinct (`jobs`.`job_title`))", "distinct_title_count"), ("(`jobs`.`join_yr`)", None)], order=[("(`jobs`.`join_yr`)", False)])),
     Case("fs_count_distinct_and_count", "test/filestore/json/default/cases/case_group_by_having.json:277-292",
          "filestore/case_group_by_having", 13, "filestore/jobs", "jobs",
          None, ["(`jobs`.`join_yr`)"], ["count(distinct (`jobs`.`job_title`))", "count((`jobs`.`job_title`))"],
          [("distinct_title_count", A("count(distinct (`jobs`.`job_title`))")),
-          ("title_count", A("count((`jobs`.`job_title`))")), ("join_yr", K(0))], order=["join_yr"]),
+          ("title_count", A("count((`jobs`.`job_title`))")), ("join_yr", K(0))], order=["join_yr"],
+         tail=dict(terms=[("count(distinct (`jobs`.`job_title`))", "distinct_title_count"), ("count((`jobs`.`job_title`))", "title_count"), ("(`jobs`.`join_yr`)", None)], order=[("(`jobs`.`join_yr`)", False)])),
     Case("fs_theme_order2", "test/filestore/json/default/cases/case_group_by_having.json:328-356",
          "filestore/case_group_by_having", 15, "filestore/user_profile", "user_profile",
          None, ["(((`user_profile`.`profile_details`).`prefs`).`ui_theme`)"], ["count(*)"],
-         [("ui_theme", K(0)), ("theme_usage", A("count(*)"))], order=["theme_usage", "ui_theme"]),
+         [("ui_theme", K(0)), ("theme_usage", A("count(*)"))], order=["theme_usage", "ui_theme"],
+         tail=dict(terms=[("(((`user_profile`.`profile_details`).`prefs`).`ui_theme`)", None), ("count(*)", "theme_usage")], order=[("`theme_usage`", False), ("(((`user_profile`.`profile_details`).`prefs`).`ui_theme`)", False)])),
     # multistore aggregate goldens == BASELINE.json config 1 known answers
     Case("ms_product_all", "test/multistore/test_cases/aggregate_functions/case_group_by_having.json:24-36",
          "multistore/aggregate_functions/case_group_by_having", 1, "multistore/aggregate_functions/product", "product",
@@ -219,7 +233,8 @@ CASES = [
     Case("ms_custid_count", "test/multistore/test_cases/aggregate_functions/case_group_by_having.json:2-22",
          "multistore/aggregate_functions/case_group_by_having", 0, "multistore/aggregate_functions/orders", "orders",
          "((`orders`.`test_id`) = \"agg_func\")", ["(`orders`.`custId`)"], ["count(*)"],
-         [("custId", K(0)), ("c", A("count(*)"))], order=["c", "custId"]),
+         [("custId", K(0)), ("c", A("count(*)"))], order=["c", "custId"],
+         tail=dict(terms=[("(`orders`.`custId`)", None), ("count(*)", "c")], order=[("`c`", False), ("(`orders`.`custId`)", False)])),
     Case("ms_totcolors", "test/multistore/test_cases/aggregate_functions/case_distinct.json:115-124",
          "multistore/aggregate_functions/case_distinct", 3, "multistore/aggregate_functions/product", "product",
          TID, [], ["count(distinct (`product`.`color`))", "count((`product`.`test_id`))"],
@@ -232,16 +247,19 @@ CASES = [
          ["countn((`orders`.`cntn`))", "countn(distinct (`orders`.`cntn`))", "count((`orders`.`cntn`))",
           "count(distinct (`orders`.`cntn`))"],
          [("cntn", A("countn((`orders`.`cntn`))")), ("dcntn", A("countn(distinct (`orders`.`cntn`))")),
-          ("cnt", A("count((`orders`.`cntn`))")), ("dcnt", A("count(distinct (`orders`.`cntn`))"))]),
+          ("cnt", A("count((`orders`.`cntn`))")), ("dcnt", A("count(distinct (`orders`.`cntn`))"))],
+         tail=dict(terms=[("countn((`orders`.`cntn`))", "cntn"), ("countn(distinct (`orders`.`cntn`))", "dcntn"), ("count((`orders`.`cntn`))", "cnt"), ("count(distinct (`orders`.`cntn`))", "dcnt")])),
     Case("ms_bigint_sum", "test/multistore/test_cases/integers/case_select.json:33-40",
          "multistore/integers/case_select", 4, "multistore/integers/orders", "orders",
          "(((`orders`.`test_id`) = \"select_big_int\") and ((`orders`.`type`) = \"aggr\"))", ["(`orders`.`type`)"],
          ["sum((`orders`.`num`))"],
-         [("total", A("sum((`orders`.`num`))")), ("type", K(0))]),
+         [("total", A("sum((`orders`.`num`))")), ("type", K(0))],
+         tail=dict(terms=[("sum((`orders`.`num`))", "total"), ("(`orders`.`type`)", None)])),
     Case("ms_bigint_count", "test/multistore/test_cases/integers/case_select.json:42-49",
          "multistore/integers/case_select", 5, "multistore/integers/orders", "orders",
          "(((`orders`.`test_id`) = \"select_big_int\") and (90 < (`orders`.`num`)))", [], ["count(1)"],
-         [("total", A("count(1)"))]),
+         [("total", A("count(1)"))],
+         tail=dict(terms=[("count(1)", "total")])),
 ]
 
 

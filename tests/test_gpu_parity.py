@@ -66,6 +66,20 @@ def test_golden_through_plan_operator(case, tmp_path):
         op.run_once()  # util.Once
 
 
+@pytest.mark.parametrize("case", [c for c in CASES if c.tail is not None], ids=lambda c: c.id)
+def test_golden_statement_end_to_end_with_tail(case, tmp_path):
+    """the whole statement - scan, filter, groups on the device, then HAVING / projection /
+    ORDER BY / LIMIT in the operator's tail - from the reference's plan JSON to the reference's golden rows."""
+    ns, ks = "default", case.keyspace.split("/")[-1]
+    write_keyspace(str(tmp_path), ns, ks, case.docs())
+    aggs = sorted(set(case.aggs))
+    op = q.Operator(explain_plan(ns, ks, case.alias, case.where, case.keys, aggs, tail=case.tail), str(tmp_path), tail=True)
+    assert op.tail_operators and op.rest_index == 6
+    res = op.run_once()
+    got = op.run_tail(res)
+    assert normalise(got) == normalise(case.golden["results"]), case.golden["statements"]
+
+
 @pytest.mark.parametrize("name,where,keys,aggs", QUERIES, ids=[x[0] for x in QUERIES])
 def test_matrix_against_oracle(name, where, keys, aggs):
     docs = make_docs(3000, seed=21)

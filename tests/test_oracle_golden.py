@@ -112,3 +112,25 @@ def test_stringer_round_trip():
                  "((`d`.`n`) in [1, 2, 3])", "(-(`d`.`n`))", "count(distinct (`d`.`x`))", "count(*)",
                  "(((`d`.`a`).`b`) is not valued)", "sum(((`d`.`p`) * (1 - (`d`.`q`))))"]:
         assert str(O.parse(text)) == text.replace("[1, 2, 3]", "[1,2,3]")
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.tail is not None], ids=lambda c: c.id)
+def test_oracle_tail_against_golden_rows(case):
+    """the oracle's restatement of Let / Filter / InitialProject / Order / Offset / Limit /
+    FinalProject (O.run_tail), fed with the operators' Stringer text, reproduces the reference's golden rows - order
+    included.  This is what pins the checker of query_b200/csrc/group_tail.cpp."""
+    docs = [O.parse_document(t) for _k, t in case.docs()]
+    groups = O.run_chain(docs, case.alias, case.where, case.keys, sorted(set(case.aggs)))
+    rows = O.run_tail(groups, having=case.tail.get("having"), terms=case.tail["terms"], order=case.tail.get("order", ()),
+                      limit=case.tail.get("limit"))
+    assert normalise(rows) == normalise(case.golden["results"]), case.golden["statements"]
+
+
+def test_oracle_tail_scope_rules():
+    """project_initial.go:98-117 + let.go:53-60: LETTING bindings see the item, not each other; an explicit alias is
+    visible to ORDER BY; a MISSING projection value leaves its field out (object.go:246-255)."""
+    docs = [{"k": "a", "x": 1}, {"k": "a", "x": 5}, {"k": "b", "x": 2}, {"x": 9}]
+    groups = O.run_chain(docs, "d", None, ["(`d`.`k`)"], ["count(*)", "sum((`d`.`x`))"])
+    rows = O.run_tail(groups, letting=[("n", "count(*)"), ("m", "(`n` + 1)")], terms=[("(`d`.`k`)", None), ("`n`", None), ("`m`", "mm"),
+                                                                                     ("sum((`d`.`x`))", "s")], order=[("`s`", True)])
+    assert rows == [{"n": 1, "s": 9}, {"k": "a", "n": 2, "s": 6}, {"k": "b", "n": 1, "s": 2}]  # `m` saw no `n`: MISSING + 1
