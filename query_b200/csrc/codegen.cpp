@@ -538,6 +538,20 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         const char* nb = getenv("N1GPU_NO_BITMAP");
         const double bitmap_bytes = kp.entry_bits <= 36 ? (double)((u64)1 << kp.entry_bits) / 8.0 : 1e30;
         kp.set_bitmap = !(nb && *nb == '1') && bitmap_bytes <= std::max(65536.0, 16.0 * (double)std::max<i64>(t.nrows, 1) * kp.ndistinct);
+        // A bitmap the size of the L2 (config 4: 128 MiB) turns every row into a random DRAM sector read-modify-write.
+        // The scan then runs in passes over slices of the entry range small enough to stay L2-resident: the columns
+        // are streamed once per pass (cheap next to random DRAM), the bits land in L2.
+        if (kp.set_bitmap) {
+            const char* sp = getenv("N1GPU_SET_PASSES");
+            int passes = 1;
+            if (sp && atoi(sp) >= 1) passes = atoi(sp);
+            else if (bitmap_bytes > 48.0 * 1024 * 1024) while (passes < 8 && bitmap_bytes / passes > 32.0 * 1024 * 1024) passes *= 2;
+            while (passes & (passes - 1)) passes &= passes - 1;                          // a power of two ...
+            while (passes > 1 && bits_for((u64)passes) > kp.entry_bits - 6) passes /= 2;  // ... of slices of >= 64 bits
+            // only where the kernel has no epilogue that publishes and re-arms state (the HBM table modes)
+            const bool hbm_table = kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128 || (kp.mode == MODE_DENSE && kp.dense_global);
+            kp.set_passes = hbm_table ? passes : 1;
+        }
     }
 
     // ---- row code -----------------------------------------------------------------------------------------------
@@ -618,7 +632,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 if (kp.key_bits > 64) g.line(strf("pack_bits(elo, ehi, epos, khi, %d);", kp.key_bits - 64));
             }
             emit_pack(g, ap.dcomp, cv, "elo", "ehi", "epos");
-            if (kp.set_bitmap) g.line("atomicOr(&((u32*)p.set_keys)[elo >> 5], 1u << (elo & 31));  // DISTINCT bitmap");
+            if (kp.set_bitmap && kp.set_passes > 1)
+                g.line("if ((int)(elo >> p.set_shift) == p.set_pass) atomicOr(&((u32*)p.set_keys)[elo >> 5], 1u << (elo & 31));  // DISTINCT bitmap, this pass's slice");
+            else if (kp.set_bitmap) g.line("atomicOr(&((u32*)p.set_keys)[elo >> 5], 1u << (elo & 31));  // DISTINCT bitmap");
             else if (kp.set128) g.line("if (table_insert128((ulonglong2*)p.set_keys, p.set_mask, elo, ehi, nullptr) < 0) p.status[0] = 2;");
             else g.line("if (table_insert64(p.set_keys, p.set_mask, elo, nullptr) < 0) p.status[0] = 2;");
             g.ind = save_ind + "    ";
@@ -727,7 +743,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += strf("#define ACCH_%d(OP, val_) %s\n", w, hit.c_str());
         }
     }
-    else s += "#define ACC(k, OP, x) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
+    else s += "#define ACC(k, OP, x) if (nq_first) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
     {
         // resident blocks per SM the register allocator must allow (tuning knob N1GPU_MIN_BLOCKS; 0 = compiler's choice)
         const char* lb = getenv("N1GPU_MIN_BLOCKS");
@@ -745,6 +761,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         kp.pdl = kp.mode == MODE_UNGROUPED && !(np && *np == '1');
         if (kp.pdl) s += "    asm volatile(\"griddepcontrol.launch_dependents;\");\n";
     }
+    // later passes over a sliced DISTINCT bitmap only set bits: the group table was fed by pass 0
+    s += kp.set_passes > 1 ? "    const bool nq_first = p.set_pass == 0;\n" : "    const bool nq_first = true; (void)nq_first;\n";
     if (kp.mode == MODE_UNGROUPED) {
         for (int w = 0; w < W; ++w) s += strf("    u64 a%d = word_identity(%s);\n", w, op_name(kp.word_ops[w]));
     } else if (smem_dense && kp.dense_priv) {
@@ -782,7 +800,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             }
             s += "    }\n";
             s += "    __syncthreads();\n";
-            s += "    bool cache_on = true;  // per warp: switched off after 4 tiles when fewer than 1 in 4 rows hit\n";
+            s += "    bool cache_on = nq_first;  // per warp: switched off after 4 tiles when fewer than 1 in 4 rows hit\n";
             s += "    unsigned nlook = 0, nhit = 0; int tiles = 0;\n";
         }
     }
@@ -834,7 +852,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += "            }\n";
             s += "        }\n";
         }
-        s += "#define ACC(k, OP, val_) ACCH_##k(OP, val_)\n";
+        s += "#define ACC(k, OP, val_) if (nq_first) ACCH_##k(OP, val_)\n";
         s += "#pragma unroll\n";
         s += "        for (int j = 0; j < 4; ++j) {\n";
         s += "            // warp-ballot selection mask (also the point where the lanes of the warp reconverge)\n";
@@ -846,7 +864,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "            }\n";
         s += "        }\n";
         s += "#undef ACC\n";
-        s += "#define ACC(k, OP, val_) ACCM_##k(OP, val_)\n";
+        s += "#define ACC(k, OP, val_) if (nq_first) ACCM_##k(OP, val_)\n";
         s += "#pragma unroll\n";
         s += "        for (int j = 0; j < 4; ++j) {\n";
         s += "            if (__ballot_sync(0xffffffffu, cs[j] == -1) == 0) continue;\n";

@@ -80,6 +80,7 @@ struct KernelPlan {
     std::vector<AggPlan> aggs;
     int ndistinct = 0, abits = 0, entry_bits = 0;
     bool set128 = false;
+    int set_passes = 1;          // bitmap beyond what the L2 keeps: scan passes, each filling one L2-resident slice of it
     bool set_bitmap = false;     // DISTINCT entries are few bits: the set is a bitmap indexed by the entry (no hashing)
     std::vector<int> used_cols;
     int scan_bytes_per_row = 0;

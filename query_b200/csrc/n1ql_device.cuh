@@ -504,6 +504,10 @@ struct NqParams {
     u64 mail_base;         // word offset of (slot, this rank) inside a mailbox
     u64 mail_words;        // words pushed per step (accumulator words x slots of the dense table)
     u64 mail_seq;          // sequence number of this step (never 0)
+    // DISTINCT bitmap larger than the L2 keeps: the scan runs in passes, pass k sets the bits of entries whose high
+    // bits (entry >> set_shift) equal k - a slice of the bitmap that stays L2-resident - and only pass 0 feeds the
+    // group table
+    int set_pass, set_shift;
 };
 
 // Pushes `words` final words at src to every peer's mailbox and raises the flag word behind them.

@@ -39,8 +39,9 @@ struct NqParamsHost {
     u64 mail_base;
     u64 mail_words;
     u64 mail_seq;
+    int set_pass, set_shift;
 };
-static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 16, "NqParams layout");
+static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 17, "NqParams layout");
 
 u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
 
@@ -204,7 +205,13 @@ void Query::launch_scan() {
     if (timing) CK(cudaEventRecord(ev0, stream));
     // ungrouped / dense: the whole step is this one launch.  Programmatic dependent launch only when nothing this
     // step enqueued before the scan (status / DISTINCT set clears) has to be complete when its first block starts.
+    p.set_pass = 0;
+    p.set_shift = kp.set_passes > 1 ? kp.entry_bits - bits_for((u64)kp.set_passes) : 63;
     jit_launch(*kernel, grid, stream, &p, sizeof p, kp.pdl && !uses_status());
+    for (int pass = 1; pass < kp.set_passes; ++pass) {  // the other slices of the DISTINCT bitmap (see NqParams)
+        p.set_pass = pass;
+        jit_launch(*kernel, grid, stream, &p, sizeof p, false);
+    }
     if (timing) CK(cudaEventRecord(ev1, stream));
     timed_launch = timing;
     if (mb_seq)  // receive side of the fused all-gather: fold every rank's words once they have landed

@@ -92,7 +92,7 @@ _GROUPED = [x for x in QUERIES if x[2]]
 
 @pytest.mark.parametrize("knob", ["N1GPU_NO_DIRECT", "N1GPU_NO_BITMAP", "N1GPU_NO_OFFSET_PACK", "N1GPU_NO_CACHE", "N1GPU_NO_PACK",
                                   "N1GPU_NO_KEY32", "N1GPU_NO_COMPLEMENT", "N1GPU_CACHE_BLOCK=1024", "N1GPU_CACHE_BLOCK=256",
-                                  "N1GPU_MMCHECK=1", "N1GPU_MMCHECK=2"])
+                                  "N1GPU_MMCHECK=1", "N1GPU_MMCHECK=2", "N1GPU_SET_PASSES=4"])
 @pytest.mark.parametrize("name,where,keys,aggs", _GROUPED, ids=[x[0] for x in _GROUPED])
 def test_grouped_matrix_through_the_alternate_layouts(name, where, keys, aggs, knob, monkeypatch):
     """The planner picks direct-indexed tables, DISTINCT bitmaps, offset-packed keys, the shared-memory front cache
@@ -208,7 +208,8 @@ def test_preshredded_columns_properties_10m():
     assert a == b
 
 
-@pytest.mark.parametrize("table_kind,set_kind", [("direct", "bitmap"), ("hash", "bitmap"), ("hash", "hash"), ("direct", "hash")])
+@pytest.mark.parametrize("table_kind,set_kind", [("direct", "bitmap"), ("hash", "bitmap"), ("hash", "hash"), ("direct", "hash"),
+                                                 ("direct", "bitmap-8-passes"), ("hash", "bitmap-2-passes")])
 def test_preshredded_group_by_high_cardinality_2m(table_kind, set_kind, monkeypatch):
     """1M-group style GROUP BY (BASELINE config 4 shape) checked against numpy: exact counts / int sums / DISTINCT,
     through both group-table layouts (direct-indexed / open addressing) and both DISTINCT set layouts (bitmap / hash)."""
@@ -216,6 +217,8 @@ def test_preshredded_group_by_high_cardinality_2m(table_kind, set_kind, monkeypa
         monkeypatch.setenv("N1GPU_NO_DIRECT", "1")
     if set_kind == "hash":
         monkeypatch.setenv("N1GPU_NO_BITMAP", "1")
+    if set_kind.endswith("passes"):  # the sliced bitmap a 200 M-row scan uses, forced at test size
+        monkeypatch.setenv("N1GPU_SET_PASSES", set_kind.split("-")[1])
     n = 2_000_000
     rng = np.random.default_rng(3)
     g = rng.integers(0, 200_000, n, dtype=np.int64)
