@@ -545,7 +545,10 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             const char* sp = getenv("N1GPU_SET_PASSES");
             int passes = 1;
             if (sp && atoi(sp) >= 1) passes = atoi(sp);
-            else if (bitmap_bytes > 48.0 * 1024 * 1024) while (passes < 8 && bitmap_bytes / passes > 32.0 * 1024 * 1024) passes *= 2;
+            // measured (config 4, 200 M rows, 128 MiB bitmap; profiles/r01_config4_bitmap_passes.jsonl): 1 pass 5.58 ms,
+            // 2 passes 3.23 ms, 4 passes 3.45 ms, 8 passes 5.41 ms - a pass costs ~0.65 ms of streaming and key work, so
+            // the slices are made just small enough (<= 64 MiB) for most of their sectors to stay in the 126 MB L2
+            else if (bitmap_bytes > 96.0 * 1024 * 1024) while (passes < 8 && bitmap_bytes / passes > 64.0 * 1024 * 1024) passes *= 2;
             while (passes & (passes - 1)) passes &= passes - 1;                          // a power of two ...
             while (passes > 1 && bits_for((u64)passes) > kp.entry_bits - 6) passes /= 2;  // ... of slices of >= 64 bits
             // only where the kernel has no epilogue that publishes and re-arms state (the HBM table modes)
