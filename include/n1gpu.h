@@ -105,6 +105,24 @@ int n1gpu_table_dict_import(n1gpu_table* t, int col, const char* blob, const int
 /* Column statistics exchange (int range / class mask) so that every rank compiles the same kernel. */
 int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]);
 int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]);
+/* A packed document source: `path` holds one JSON document per line (NDJSON) in primary-key order - what a keyspace of
+ * more than a few million documents is kept as when one file per document (datastore/file/file.go:312-353) stops being
+ * practical.  Same shredding and `threads` meaning as n1gpu_table_load_dir (-1: device shredder); blank lines skipped. */
+int n1gpu_table_load_ndjson(n1gpu_table* t, const char* path, int threads);
+/* Persistent columnar segments: the shredded form of a keyspace for this table's columns - typed
+ * columns, class bytes, sorted dictionaries - written once and loaded instead of reading and parsing every document.
+ * set_segment_output: n1gpu_table_seal also writes the (host-shredded) columns to `path` under `source_tag`.
+ * load_segment: fills the empty table from `path` when it was written for the same columns under the very same tag
+ * (*loaded = 1; the caller seals); absent, foreign, truncated or stale files give *loaded = 0 and an untouched table.
+ * The tag is the caller's change detector for the keyspace (the plan-level operator uses directory mtime, document
+ * count, newest document mtime and total bytes); it plays the part of the reference's invalidation on
+ * performOp / Delete (datastore/file/file.go:375-471).  Never place segments inside a keyspace directory: every plain
+ * file there is a document (file.go:715-729).                                                                     */
+int n1gpu_table_set_segment_output(n1gpu_table* t, const char* path, const char* source_tag);
+int n1gpu_table_load_segment(n1gpu_table* t, const char* path, const char* source_tag, int* loaded);
+/* Directory in which n1gpu_plan_build keeps one segment per (keyspace, column set); NULL or "" = none (the default,
+ * or the N1GPU_SEGMENT_DIR environment variable).                                                                  */
+int n1gpu_set_segment_dir(const char* dir);
 /* Declares how many rows the whole keyspace holds over ALL partitions (ranks) whose partial group states will be
  * merged with this table's (>= this partition's rows; a single-partition keyspace declares its own row count).
  * Queries compiled afterwards size their overflow proofs with it: exact one-word integer sums, and two row counters

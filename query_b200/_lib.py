@@ -51,6 +51,10 @@ _SIGS = {
     "n1gpu_table_stats_get": (C.c_int, [_P, C.c_int, _I64P]),
     "n1gpu_table_stats_set": (C.c_int, [_P, C.c_int, _I64P]),
     "n1gpu_table_set_global_rows": (C.c_int, [_P, C.c_int64]),
+    "n1gpu_table_load_ndjson": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "n1gpu_table_set_segment_output": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
+    "n1gpu_table_load_segment": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]),
+    "n1gpu_set_segment_dir": (C.c_int, [C.c_char_p]),
     "n1gpu_table_column_peek": (C.c_int, [_P, C.c_int, _I64P, _U8P, C.c_int64]),
     "n1gpu_table_free": (C.c_int, [_P]),
     "n1gpu_query_compile": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int,

@@ -46,6 +46,11 @@ def launch_count():
     return int(lib().n1gpu_launch_count())
 
 
+def set_segment_dir(path):
+    """Directory in which plan-level operators keep persistent columnar segments ("" = none)."""
+    check(lib().n1gpu_set_segment_dir(path.encode("utf-8") if path else None))
+
+
 class Table:
     """A shredded keyspace resident in HBM (n1gpu_table)."""
 
@@ -179,6 +184,22 @@ class Table:
         idx = col if isinstance(col, int) else self.find_column(col)
         s = np.ascontiguousarray(stats, dtype=np.int64)
         check(lib().n1gpu_table_stats_set(self._h, idx, s.ctypes.data_as(_lib._I64P)))
+
+    def load_ndjson(self, path, threads=0):
+        """One JSON document per line, in primary-key order (threads=-1: device shredder)."""
+        check(lib().n1gpu_table_load_ndjson(self._h, path.encode("utf-8"), threads))
+        return self
+
+    def set_segment_output(self, path, source_tag=""):
+        """seal() also writes the shredded columns to `path` (persistent columnar segment)."""
+        check(lib().n1gpu_table_set_segment_output(self._h, path.encode("utf-8"), source_tag.encode("utf-8")))
+        return self
+
+    def load_segment(self, path, source_tag=""):
+        """True when the segment was written for the same columns under the same tag and is now loaded (then seal())."""
+        ok = C.c_int()
+        check(lib().n1gpu_table_load_segment(self._h, path.encode("utf-8"), source_tag.encode("utf-8"), C.byref(ok)))
+        return bool(ok.value)
 
     def set_global_rows(self, rows):
         """Rows of the whole keyspace over all partitions whose partial states get merged (include/n1gpu.h)."""

@@ -168,6 +168,26 @@ int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]) {
         c.stats_forced = true;
     });
 }
+int n1gpu_table_load_ndjson(n1gpu_table* t, const char* path, int threads) {
+    return guard([&] { REQUIRE(t); REQUIRE(path); t->t.load_ndjson(path, threads); });
+}
+int n1gpu_table_set_segment_output(n1gpu_table* t, const char* path, const char* source_tag) {
+    return guard([&] {
+        REQUIRE(t);
+        if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "the segment is written by seal");
+        t->t.segment_out = path ? path : "";
+        t->t.segment_source = source_tag ? source_tag : "";
+    });
+}
+int n1gpu_table_load_segment(n1gpu_table* t, const char* path, const char* source_tag, int* loaded) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(path); REQUIRE(loaded);
+        *loaded = t->t.load_segment(path, source_tag ? source_tag : "") ? 1 : 0;
+    });
+}
+int n1gpu_set_segment_dir(const char* dir) {
+    return guard([&] { execution::set_segment_dir(dir ? dir : ""); });
+}
 int n1gpu_table_set_global_rows(n1gpu_table* t, int64_t rows) {
     return guard([&] {
         REQUIRE(t);

@@ -1,6 +1,7 @@
 // execution.cpp — see execution.hpp
 #include "execution.hpp"
 
+#include <dirent.h>
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -148,9 +149,40 @@ namespace execution {
 
 namespace {
 
-struct CacheEntry { std::shared_ptr<Table> table; time_t mtime; };
+struct CacheEntry { std::shared_ptr<Table> table; std::string source; };
 std::mutex g_cache_mu;
 std::map<std::string, CacheEntry> g_tables;  // keyspace dir + columns -> resident shredded table (A.9)
+
+std::string g_segment_dir;
+bool g_segment_dir_set = false;
+
+std::string segment_dir() {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (!g_segment_dir_set) { const char* e = getenv("N1GPU_SEGMENT_DIR"); g_segment_dir = e ? e : ""; g_segment_dir_set = true; }
+    return g_segment_dir;
+}
+
+// What a segment is valid for: the keyspace directory as the file datastore sees it (file.go:711-749) - modification
+// time of the directory (documents added / removed), number of documents, newest document (rewritten in place by
+// UPDATE, file.go:375-471) and their total size.  One stat per document; no document is opened.
+std::string keyspace_source_tag(const std::string& dir) {
+    DIR* d = opendir(dir.c_str());
+    if (!d) N1_THROW(N1GPU_E_IO, "cannot open keyspace directory %s", dir.c_str());
+    struct stat ds;
+    long long files = 0, bytes = 0, newest_s = 0, newest_ns = 0, dir_s = 0, dir_ns = 0;
+    if (stat(dir.c_str(), &ds) == 0) { dir_s = ds.st_mtim.tv_sec; dir_ns = ds.st_mtim.tv_nsec; }
+    while (dirent* e = readdir(d)) {
+        const std::string n = e->d_name;
+        if (n == "." || n == "..") continue;
+        struct stat st;
+        if (stat((dir + "/" + n).c_str(), &st) != 0 || S_ISDIR(st.st_mode)) continue;
+        ++files;
+        bytes += (long long)st.st_size;
+        if (st.st_mtim.tv_sec > newest_s || (st.st_mtim.tv_sec == newest_s && st.st_mtim.tv_nsec > newest_ns)) { newest_s = st.st_mtim.tv_sec; newest_ns = st.st_mtim.tv_nsec; }
+    }
+    closedir(d);
+    return strf("dir=%lld.%09lld files=%lld newest=%lld.%09lld bytes=%lld", dir_s, dir_ns, files, newest_s, newest_ns, bytes);
+}
 
 std::shared_ptr<Table> resident_table(const std::string& dir, std::vector<std::string> paths) {
     std::sort(paths.begin(), paths.end());
@@ -158,18 +190,26 @@ std::shared_ptr<Table> resident_table(const std::string& dir, std::vector<std::s
     for (auto& p : paths) { key.push_back('\n'); key += p; }
     struct stat st;
     if (stat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) N1_THROW(N1GPU_E_IO, "keyspace directory %s not found", dir.c_str());
+    const std::string tag = keyspace_source_tag(dir);  // the resident table and the segment live as long as this holds
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_tables.find(key);
-        if (it != g_tables.end() && it->second.mtime == st.st_mtime) return it->second.table;
+        if (it != g_tables.end() && it->second.source == tag) return it->second.table;
     }
     auto t = std::make_shared<Table>();
     for (auto& p : paths) t->add_column(p);
-    t->load_dir(dir, 0);
+    const std::string segs = segment_dir();
+    bool from_segment = false;
+    if (!segs.empty()) {  // persistent columnar segment: skip reading and parsing the documents while nothing changed
+        const std::string file = segs + "/" + strf("%016llx", (unsigned long long)mix64(std::hash<std::string>()(key))) + ".n1seg";
+        from_segment = t->load_segment(file, tag);
+        if (!from_segment) { t->segment_out = file; t->segment_source = tag; }
+    }
+    if (!from_segment) t->load_dir(dir, 0);
     t->global_rows = t->nrows;  // the operator runs the whole keyspace in this process: one partition
     t->seal();
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    g_tables[key] = CacheEntry{t, st.st_mtime};
+    g_tables[key] = CacheEntry{t, tag};
     return t;
 }
 
@@ -413,6 +453,12 @@ std::string GpuGroupAggregate::MarshalJSON() const {
              ",\"scan_bytes_per_row\":" + std::to_string(query->kp.scan_bytes_per_row) + "}";
     }
     return s + "}";
+}
+
+void set_segment_dir(const std::string& dir) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_segment_dir = dir;
+    g_segment_dir_set = true;
 }
 
 std::string ResultToJSON(const Result& r) {

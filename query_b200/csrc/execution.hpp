@@ -137,6 +137,8 @@ std::unique_ptr<GpuGroupAggregate> BuildWithTail(const std::string& plan_json, c
                                                  int* rest_index, int* outer_rest);
 
 std::string ResultToJSON(const Result& r);
+// Directory for the operator's persistent segments ("" = none); also read from N1GPU_SEGMENT_DIR.
+void set_segment_dir(const std::string& dir);
 
 }  // namespace execution
 }  // namespace n1

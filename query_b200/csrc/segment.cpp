@@ -1,0 +1,158 @@
+// segment.cpp — persistent columnar segments and the packed document source.
+//
+// The reference's file datastore keeps one JSON file per document (datastore/file/file.go:312-353,711-749): a scan
+// opens, reads and validates every file, every time.  A segment is the shredded form of a keyspace for one set of
+// field paths - typed columns, class bytes, sorted dictionaries - written once next to (never inside: every plain file
+// of a keyspace directory is a document, file.go:715-729) the datastore and loaded instead of parsing while the
+// keyspace has not changed.  What "not changed" means is the caller's business: a segment carries an opaque source
+// tag (the operator uses directory mtime + file count + newest file mtime + total bytes, see execution.cpp) and only
+// loads under the very same tag - the counterpart of the invalidation on performOp / Delete (file.go:375-471).
+//
+// Layout (little endian): "N1SEG01\n" | u64 header bytes | header JSON | per column: dictionary offsets i64[ndict+1],
+// dictionary bytes, payload (nrows x width bytes: int64 / float64 bits, or u32 ranks), class bytes (nrows).
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <fstream>
+
+#include "json.hpp"
+#include "table.hpp"
+
+namespace n1 {
+
+namespace {
+const char MAGIC[8] = {'N', '1', 'S', 'E', 'G', '0', '1', '\n'};
+
+void put(std::ofstream& f, const void* p, size_t n) { f.write((const char*)p, (std::streamsize)n); }
+bool get(std::ifstream& f, void* p, size_t n) { f.read((char*)p, (std::streamsize)n); return (size_t)f.gcount() == n; }
+}  // namespace
+
+// Called by seal() once dictionaries are sorted and payloads hold ranks, before the host staging is dropped.
+void Table::write_segment() const {
+    const std::string tmp = segment_out + ".tmp";
+    std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+    if (!f) N1_THROW(N1GPU_E_IO, "cannot write segment %s", tmp.c_str());
+    std::string h = "{\"version\":1,\"nrows\":" + std::to_string(nrows) + ",\"source\":";
+    json::quote(segment_source, h);
+    h += ",\"columns\":[";
+    for (size_t c = 0; c < cols.size(); ++c) {
+        const Column& col = cols[c];
+        size_t dict_bytes = 0;
+        for (auto& s : col.dict) dict_bytes += s.size();
+        if (c) h += ",";
+        h += "{\"path\":";
+        json::quote(join_path(col.path, '\x1f'), h);
+        h += ",\"width\":" + std::to_string(col.width) + ",\"ndict\":" + std::to_string(col.dict.size()) + ",\"dict_bytes\":" + std::to_string(dict_bytes) + "}";
+    }
+    h += "]}";
+    const u64 hl = h.size();
+    put(f, MAGIC, 8);
+    put(f, &hl, 8);
+    put(f, h.data(), h.size());
+    for (auto& col : cols) {
+        std::vector<i64> offs(col.dict.size() + 1, 0);
+        for (size_t i = 0; i < col.dict.size(); ++i) offs[i + 1] = offs[i] + (i64)col.dict[i].size();
+        put(f, offs.data(), offs.size() * 8);
+        for (auto& s : col.dict) put(f, s.data(), s.size());
+        if (col.width == 8) put(f, col.payload.data(), (size_t)nrows * 8);
+        else if (col.width == 4) {
+            std::vector<u32> narrow((size_t)nrows);
+            for (i64 i = 0; i < nrows; ++i) narrow[(size_t)i] = (u32)col.payload[(size_t)i];
+            put(f, narrow.data(), narrow.size() * 4);
+        }
+        put(f, col.tags.data(), (size_t)nrows);
+    }
+    f.close();
+    if (!f || rename(tmp.c_str(), segment_out.c_str()) != 0) { remove(tmp.c_str()); N1_THROW(N1GPU_E_IO, "cannot write segment %s", segment_out.c_str()); }
+}
+
+// Fills the (unsealed, empty) table from a segment written for the same columns under the same source tag.
+// Returns false - and leaves the table untouched - when the file is absent, foreign, truncated or stale.
+bool Table::load_segment(const std::string& file, const std::string& source) {
+    if (sealed || appended || nrows) N1_THROW(N1GPU_E_INVALID, "a segment loads into an empty, unsealed table");
+    std::ifstream f(file, std::ios::binary);
+    if (!f) return false;
+    char magic[8];
+    u64 hl = 0;
+    if (!get(f, magic, 8) || memcmp(magic, MAGIC, 8) != 0 || !get(f, &hl, 8) || hl > (64u << 20)) return false;
+    std::string h((size_t)hl, '\0');
+    if (!get(f, &h[0], h.size())) return false;
+    json::Node root;
+    if (!json::parse(h, root) || root.kind != json::Node::OBJ) return false;
+    const json::Node* ver = root.get("version");
+    const json::Node* nr = root.get("nrows");
+    const json::Node* cs = root.get("columns");
+    if (!ver || ver->kind != json::Node::INT || ver->i != 1 || !nr || nr->kind != json::Node::INT || nr->i < 0) return false;
+    if (root.str_or("source", "\x01") != source) return false;  // the keyspace changed since the segment was written
+    if (!cs || cs->kind != json::Node::ARR || cs->arr.size() != cols.size()) return false;
+    const i64 n = nr->i;
+    struct Staged { std::vector<std::string> dict; std::vector<i64> payload; std::vector<u8> tags; };
+    std::vector<Staged> staged(cols.size());
+    for (size_t c = 0; c < cols.size(); ++c) {
+        const json::Node& cn = cs->arr[c];
+        if (cn.kind != json::Node::OBJ || cn.str_or("path", "\x01") != join_path(cols[c].path, '\x1f')) return false;
+        const json::Node *w = cn.get("width"), *nd = cn.get("ndict"), *db = cn.get("dict_bytes");
+        if (!w || !nd || !db || w->kind != json::Node::INT || nd->kind != json::Node::INT || db->kind != json::Node::INT) return false;
+        if ((w->i != 8 && w->i != 4 && w->i != 0) || nd->i < 0 || db->i < 0) return false;
+        Staged& st = staged[c];
+        std::vector<i64> offs((size_t)nd->i + 1);
+        if (!get(f, offs.data(), offs.size() * 8) || offs[0] != 0 || offs.back() != db->i) return false;
+        std::string blob((size_t)db->i, '\0');
+        if (db->i && !get(f, &blob[0], blob.size())) return false;
+        st.dict.reserve((size_t)nd->i);
+        for (i64 i = 0; i < nd->i; ++i) {
+            if (offs[(size_t)i + 1] < offs[(size_t)i] || offs[(size_t)i + 1] > db->i) return false;
+            st.dict.emplace_back(blob.data() + offs[(size_t)i], (size_t)(offs[(size_t)i + 1] - offs[(size_t)i]));
+        }
+        st.payload.assign((size_t)n, 0);
+        if (w->i == 8) { if (n && !get(f, st.payload.data(), (size_t)n * 8)) return false; }
+        else if (w->i == 4) {
+            std::vector<u32> narrow((size_t)n);
+            if (n && !get(f, narrow.data(), narrow.size() * 4)) return false;
+            for (i64 i = 0; i < n; ++i) st.payload[(size_t)i] = narrow[(size_t)i];
+        }
+        st.tags.resize((size_t)n);
+        if (n && !get(f, st.tags.data(), (size_t)n)) return false;
+        for (i64 i = 0; i < n; ++i) {
+            const u8 t = st.tags[(size_t)i];
+            if (t > C_OTHER || (t == C_STRING && (u64)st.payload[(size_t)i] >= (u64)nd->i)) return false;
+        }
+    }
+    for (size_t c = 0; c < cols.size(); ++c) {
+        Column& col = cols[c];
+        col.dict = std::move(staged[c].dict);
+        col.payload = std::move(staged[c].payload);
+        col.tags = std::move(staged[c].tags);
+        col.local_strings.clear();
+        col.codes_are_ranks = true;
+    }
+    nrows = n;
+    appended = true;  // like appended documents: no further input may be mixed in
+    return true;
+}
+
+// A packed document source: one JSON document per line (NDJSON), in primary-key order - the form a keyspace of more
+// than a few million documents takes when one file per document (file.go) stops being practical.
+void Table::load_ndjson(const std::string& file, int threads) {
+    std::ifstream f(file, std::ios::binary);
+    if (!f) N1_THROW(N1GPU_E_IO, "cannot read %s", file.c_str());
+    std::string buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<i64> offsets;
+    std::string packed;
+    packed.reserve(buf.size());
+    offsets.push_back(0);
+    size_t i = 0;
+    while (i < buf.size()) {
+        size_t e = buf.find('\n', i);
+        if (e == std::string::npos) e = buf.size();
+        size_t a = i, b = e;
+        while (a < b && (buf[a] == ' ' || buf[a] == '\t' || buf[a] == '\r')) ++a;
+        while (b > a && (buf[b - 1] == ' ' || buf[b - 1] == '\t' || buf[b - 1] == '\r')) --b;
+        if (b > a) { packed.append(buf, a, b - a); offsets.push_back((i64)packed.size()); }  // blank lines are not documents
+        i = e + 1;
+    }
+    if (threads < 0) append_json_device(packed.data(), offsets.data(), (i64)offsets.size() - 1);
+    else append_json(packed.data(), offsets.data(), (i64)offsets.size() - 1, threads);
+}
+
+}  // namespace n1

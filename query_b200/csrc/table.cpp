@@ -401,6 +401,7 @@ void Table::seal() {
         for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_INVALID, "%s", e.c_str());
     }
     shred_sec += now_sec() - t0;
+    if (!segment_out.empty()) write_segment();
     t0 = now_sec();
     if (!have_device()) {
         // build / CPU-test container: dictionaries and statistics only; queries can still be compiled

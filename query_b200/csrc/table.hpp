@@ -48,6 +48,12 @@ struct Table {
     double shred_sec = 0, upload_sec = 0;
     i64 json_bytes = 0;
 
+    // persistent segment (segment.cpp): when set, seal() writes the shredded columns to this file under this source tag
+    std::string segment_out, segment_source;
+    void write_segment() const;
+    bool load_segment(const std::string& file, const std::string& source);
+    void load_ndjson(const std::string& file, int threads);  // one document per line; threads as for load_dir
+
     bool device_shredded = false;  // columns were produced in HBM by shred.cu (no host staging exists)
 
     // threads >= 0: host threads (0 = all cores); threads == -1: the device shredder (shred.cu)
