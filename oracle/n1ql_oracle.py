@@ -1278,6 +1278,39 @@ def run_chain(docs, alias, where, group_keys, aggregates, streams=1):
     return out
 
 
+def run_distinct(docs, alias, where, terms):
+    """SELECT DISTINCT <terms> FROM ks [WHERE]: Fetch -> Filter -> InitialProject -> Distinct -> FinalProject
+    (planner/build_select_sub.go:217-243).  execution/distinct.go:60-72 keeps the first item per projection object
+    (value.Set: numbers by canonical value, set.go:83-99).  terms: [(expr, as or None)].  Returns the projection rows in
+    first-appearance order (the reference's order is that of its parallel streams)."""
+    P = lambda e: parse(e) if isinstance(e, str) else e
+    where = P(where) if where is not None else None
+    terms = [(P(e), a or "") for e, a in terms]
+    names, n = [], 1
+    for e, a in terms:
+        al = a or expr_alias(e)
+        if not al:
+            al, n = "$%d" % n, n + 1
+        names.append(al)
+    seen, out = set(), []
+    for doc in docs:
+        item = {alias: doc}
+        if where is not None and not truth(where.evaluate(item)):
+            continue
+        proj = {}
+        for (e, _a), al in zip(terms, names):
+            v = e.evaluate(item)
+            if v is MISSING:
+                proj.pop(al, None)
+            else:
+                proj[al] = v
+        k = tuple(sorted((name, marshal(v)) for name, v in proj.items()))
+        if k not in seen:
+            seen.add(k)
+            out.append({name: to_python(v) for name, v in proj.items()})
+    return out
+
+
 def expr_alias(e):
     """Expression.Alias(): nav_field.go:55-57,260-262 (last field name), identifier.go:66-68, else "" (base.go:163-165)."""
     if isinstance(e, (Field, Identifier)):

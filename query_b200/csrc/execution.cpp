@@ -218,6 +218,7 @@ struct Builder : plan::Visitor {
     std::string root;
     std::unique_ptr<GpuGroupAggregate> found;
     int rest = 0;
+    bool want_tail = false;                // the caller can run a tail (n1gpu_plan_build_tail): SELECT DISTINCT needs one
     plan::Sequence* chain_seq = nullptr;   // the Sequence that holds the chain
     plan::Sequence* outer_seq = nullptr;   // the Sequence that holds chain_seq as a direct child (ORDER BY / LIMIT plans)
     size_t outer_index = 0;                // ... at this position
@@ -271,6 +272,46 @@ struct Builder : plan::Visitor {
             }
             auto* inter = i < ch.size() ? dynamic_cast<plan::Group*>(ch[i].get()) : nullptr;
             auto* fin = i + 1 < ch.size() ? dynamic_cast<plan::Group*>(ch[i + 1].get()) : nullptr;
+            // SELECT DISTINCT <terms> FROM ks [WHERE]: [.., Parallel(Sequence[Filter?, InitialProject(distinct), Distinct,
+            // FinalProject?]), Distinct, ..] (planner/build_select_sub.go:217-243).  Grouping by the projected terms
+            // with no aggregates yields exactly the distinct rows; the projection itself is the operator's tail.
+            if (want_tail && !initial && ok == false) {
+                plan::Filter* f2 = nullptr;
+                plan::Opaque* proj = nullptr;
+                bool shape = true;
+                for (auto* m : mid) {
+                    if (auto* f = dynamic_cast<plan::Filter*>(m)) { if (f2 || proj) shape = false; f2 = f; }
+                    else if (auto* o = dynamic_cast<plan::Opaque*>(m)) {
+                        if (o->name == "InitialProject" && !proj) proj = o;
+                        else if (!(proj && (o->name == "Distinct" || o->name == "FinalProject"))) shape = false;
+                    } else shape = false;
+                }
+                json::Node pn;
+                std::vector<std::string> terms;
+                if (shape && proj && json::parse(proj->body, pn)) {
+                    const json::Node* d = pn.get("distinct");
+                    const json::Node* ts = pn.get("result_terms");
+                    if (d && d->kind == json::Node::BOOL && d->b && ts && ts->kind == json::Node::ARR)
+                        for (auto& t : ts->arr) { const std::string e = t.str_or("expr", ""); if (e.empty() || t.get("star")) { terms.clear(); break; } terms.push_back(e); }
+                }
+                if (!terms.empty() && scan->limit.empty() && scan->term.keyspace == fetch->term.keyspace && scan->term.nspace == fetch->term.nspace) {
+                    std::unique_ptr<GpuGroupAggregate> op(new GpuGroupAggregate());
+                    op->term = fetch->term;
+                    if (op->term.as.empty()) op->term.as = scan->term.as;
+                    op->keyspace_dir = root + "/" + fetch->term.nspace + "/" + fetch->term.keyspace;
+                    if (f2) op->condition = f2->condition;
+                    op->keys = terms;  // duplicates collapse below: a key per distinct term text
+                    std::sort(op->keys.begin(), op->keys.end());
+                    op->keys.erase(std::unique(op->keys.begin(), op->keys.end()), op->keys.end());
+                    op->tail.distinct_by_keys = true;
+                    found = std::move(op);
+                    rest = 2;  // the tail starts at the Parallel that holds the projection
+                    chain_seq = &s;
+                    outer_seq = my_parent;
+                    outer_index = my_index;
+                    return;
+                }
+            }
             if (!ok || !initial) why = "operators between Fetch and InitialGroup are not just Filter";
             else if (!inter || inter->phase != 1 || !fin || fin->phase != 2) why = "InitialGroup is not followed by IntermediateGroup, FinalGroup";
             else if (inter->keys != initial->keys || fin->keys != initial->keys || inter->aggregates != initial->aggregates || fin->aggregates != initial->aggregates)
@@ -356,6 +397,7 @@ std::unique_ptr<GpuGroupAggregate> BuildWithTail(const std::string& plan_json, c
     plan::OperatorP p = plan::MakeOperator(*pn);
     Builder b;
     b.root = datastore_root;
+    b.want_tail = want_tail;
     p->Accept(b);
     if (!b.found) N1_THROW(N1GPU_E_INELIGIBLE, "not substituted: %s", b.why.c_str());
     std::unique_ptr<GpuGroupAggregate> op = std::move(b.found);
@@ -375,6 +417,7 @@ std::unique_ptr<GpuGroupAggregate> BuildWithTail(const std::string& plan_json, c
         // one), then plain operators of the enclosing Sequence.  All or nothing up to FinalProject.
         GroupTail t;
         t.keyspace_alias = alias;
+        t.distinct_by_keys = op->tail.distinct_by_keys;
         auto as_node = [](plan::Operator* o, json::Node& n) { return json::parse(o->MarshalJSON(), n); };
         bool ok = true;
         size_t c = (size_t)b.rest;
@@ -382,6 +425,8 @@ std::unique_ptr<GpuGroupAggregate> BuildWithTail(const std::string& plan_json, c
             std::vector<plan::Operator*> flat;
             Builder::flatten(b.chain_seq->children[c].get(), flat);
             size_t k = 0;
+            // SELECT DISTINCT: the Filter in front of the projection is the WHERE the scan already applied, not a HAVING
+            if (t.distinct_by_keys && c == (size_t)b.rest && !flat.empty() && dynamic_cast<plan::Filter*>(flat[0])) flat.erase(flat.begin());
             for (; k < flat.size(); ++k) {
                 json::Node n;
                 if (!as_node(flat[k], n) || !t.add(n, op->keys, op->aggregates)) break;
@@ -403,7 +448,8 @@ std::unique_ptr<GpuGroupAggregate> BuildWithTail(const std::string& plan_json, c
             if (outer_rest) *outer_rest = t.outer_consumed ? (int)b.outer_index + 1 + t.outer_consumed : 0;
             b.rest += t.inner_consumed;
             op->tail = std::move(t);
-        }
+        } else if (op->tail.distinct_by_keys)
+            N1_THROW(N1GPU_E_INELIGIBLE, "not substituted: the projection of this SELECT DISTINCT is outside the subset");
     }
     if (rest_index) *rest_index = b.rest;
     return op;

@@ -308,7 +308,7 @@ bool GroupTail::add(const json::Node& op, const std::vector<std::string>& key_te
             if (has_project) return false;
             const json::Node* d = op.get("distinct");
             const json::Node* raw = op.get("raw");
-            if ((d && d->kind == json::Node::BOOL && d->b) || (raw && raw->kind == json::Node::BOOL && raw->b)) return false;
+            if ((d && d->kind == json::Node::BOOL && d->b && !distinct_by_keys) || (raw && raw->kind == json::Node::BOOL && raw->b)) return false;
             const json::Node* ts = op.get("result_terms");
             if (!ts || ts->kind != json::Node::ARR || ts->arr.empty()) return false;
             std::vector<TailTerm> fresh;
@@ -328,10 +328,14 @@ bool GroupTail::add(const json::Node& op, const std::vector<std::string>& key_te
                 if (!tt.as.empty() && (tt.as == keyspace_alias || index_of(sc.let_vars, tt.as) >= 0)) return false;
                 if (tt.alias.empty()) tt.alias = "$" + std::to_string(next++);
                 bind(*tt.e, sc);
+                // DISTINCT rows are the groups only while no two terms share an output name (a later one overrides)
+                if (distinct_by_keys) for (auto& o : fresh) if (o.alias == tt.alias) return false;
                 fresh.push_back(std::move(tt));
             }
             terms = std::move(fresh);
             has_project = true;
+        } else if (name == "Distinct") {
+            if (!distinct_by_keys || !has_project || !order.empty() || has_offset || has_limit) return false;  // already distinct: nothing to do
         } else if (name == "FinalProject") {
             if (!has_project || final_project) return false;
             final_project = true;

@@ -45,6 +45,10 @@ class GroupTail {
     int outer_consumed = 0;  // operators taken from the enclosing Sequence (Order, Offset, Limit, FinalProject)
     std::vector<std::string> operators;  // names, in execution order (for MarshalJSON / tests)
     std::string keyspace_alias;          // the item's own field: an explicit projection alias must not shadow it
+    // SELECT DISTINCT: the operator groups by the projected terms, so its groups ARE the distinct
+    // rows (execution/distinct.go:60-72 keys its set by the projection object); the InitialProject may then carry
+    // "distinct": true and the Distinct operators that follow it are absorbed
+    bool distinct_by_keys = false;
 
     bool empty() const { return operators.empty(); }
     // Adds one plan operator (already parsed JSON); returns false - and adds nothing - when the operator or one of its

@@ -52,3 +52,34 @@ def explain_plan(namespace, keyspace, alias, where, keys, aggs, parallel=True, t
         outer.append({"#operator": "FinalProject"})
     outer.append({"#operator": "Stream"})
     return {"#operator": "Sequence", "~children": outer}
+
+
+def distinct_plan(namespace, keyspace, alias, where, terms, order=None, limit=None):
+    """EXPLAIN shape of SELECT DISTINCT <terms> FROM ks [WHERE] [ORDER BY] [LIMIT] (planner/build_select_sub.go:217-243:
+    the parallel part projects and de-duplicates per stream, a serial Distinct follows; planner/build_select.go:75-110)."""
+    term = {"keyspace": keyspace, "namespace": namespace}
+    if alias and alias != keyspace:
+        term["as"] = alias
+    sub = []
+    if where:
+        sub.append({"#operator": "Filter", "condition": where})
+    sub.append({"#operator": "InitialProject", "distinct": True,
+                "result_terms": [dict({"expr": e}, **({"as": a} if a else {})) for e, a in terms]})
+    sub.append({"#operator": "Distinct"})
+    if not order:
+        sub.append({"#operator": "FinalProject"})
+    children = [
+        dict({"#operator": "PrimaryScan", "index": "#primary", "using": "default"}, **term),
+        dict({"#operator": "Fetch"}, **term),
+        {"#operator": "Parallel", "~child": {"#operator": "Sequence", "~children": sub}},
+        {"#operator": "Distinct"},
+    ]
+    outer = [{"#operator": "Sequence", "~children": children}]
+    if order:
+        outer.append({"#operator": "Order", "sort_terms": [dict({"expr": e}, **({"desc": True} if d else {})) for e, d in order]})
+    if limit is not None:
+        outer.append({"#operator": "Limit", "expr": str(limit)})
+    if order:
+        outer.append({"#operator": "FinalProject"})
+    outer.append({"#operator": "Stream"})
+    return {"#operator": "Sequence", "~children": outer}

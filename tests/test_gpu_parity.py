@@ -9,7 +9,7 @@ import pytest
 import query_b200 as q
 from gen_n1 import QUERIES, F, make_docs
 from golden_plans import CASES, WHERE_CASES, _MISSING, keyspaces, normalise
-from plans_n1 import explain_plan
+from plans_n1 import distinct_plan, explain_plan
 from util_n1 import assert_same, gpu_rows, make_table, oracle_rows, run_both, write_keyspace
 
 pytestmark = pytest.mark.gpu
@@ -78,6 +78,21 @@ def test_golden_statement_end_to_end_with_tail(case, tmp_path):
     res = op.run_once()
     got = op.run_tail(res)
     assert normalise(got) == normalise(case.golden["results"]), case.golden["statements"]
+
+
+@pytest.mark.parametrize("where,terms", [(None, [(F("t"), None)]), ("(%s < 500)" % F("p"), [(F("t"), "kind"), (F("h"), None)]),
+                                         (None, [("(%s %% 5)" % F("p"), "m"), (F("s"), None)])], ids=["one", "two_where", "computed"])
+def test_select_distinct_end_to_end(where, terms, tmp_path):
+    """SELECT DISTINCT runs as GROUP BY <terms> with no aggregates on the device, its projection in
+    the operator's tail; the rows equal the oracle's Filter -> InitialProject -> Distinct."""
+    from oracle import n1ql_oracle as O
+    docs = make_docs(3000, seed=61)
+    write_keyspace(str(tmp_path), "default", "d", [("k%06d" % i, t) for i, t in enumerate(docs)])
+    op = q.Operator(distinct_plan("default", "d", "d", where, terms), str(tmp_path), tail=True)
+    got = op.run_tail(op.run_once())
+    want = O.run_distinct([O.parse_document(d) for d in docs], "d", where, terms)
+    canon = lambda rows: sorted(json.dumps(normalise(r), sort_keys=True) for r in rows)
+    assert canon(got) == canon(want)
 
 
 @pytest.mark.parametrize("name,where,keys,aggs", QUERIES, ids=[x[0] for x in QUERIES])

@@ -13,7 +13,7 @@ import query_b200 as q
 from gen_n1 import F, make_docs
 from golden_plans import CASES, normalise
 from oracle import n1ql_oracle as O
-from plans_n1 import explain_plan
+from plans_n1 import distinct_plan, explain_plan
 from util_n1 import write_keyspace
 
 TAILED = [c for c in CASES if c.tail is not None]
@@ -143,3 +143,45 @@ def test_ineligible_tail_shapes(tmp_path):
     assert ops(dict(terms=[(F("t"), None)]), lambda p: proj(p)[0]["result_terms"].append({"star": True})) == []
     # an alias that shadows the keyspace alias would change what a MISSING value resolves to in ORDER BY
     assert ops(dict(terms=[(F("t"), "d")], order=[("`d`", False)])) == []
+
+
+DISTINCTS = [
+    ("one_string", None, [(F("t"), None)], None, None),
+    ("two_terms_where", "(%s < 500)" % F("p"), [(F("t"), "kind"), (F("h"), None)], None, None),
+    ("computed_term_ordered", None, [("(%s %% 5)" % F("p"), "m"), (F("t"), None)], [("`m`", True), (F("t"), False)], 7),
+    ("mixed_types_ordered", "(%s is not missing)" % F("p"), [(F("h"), "h")], [("`h`", False)], None),
+]
+
+
+@pytest.mark.parametrize("name,where,terms,order,limit", DISTINCTS, ids=[d[0] for d in DISTINCTS])
+def test_select_distinct_is_a_group_by_over_the_projected_terms(name, where, terms, order, limit, tmp_path):
+    """SELECT DISTINCT substituted as GROUP BY <terms> with no aggregates + the projection tail."""
+    terms = [(e.replace("%%", "%"), a) for e, a in terms]
+    docs = make_docs(700, seed=51)
+    write_keyspace(str(tmp_path), "default", "d", [("k%06d" % i, t) for i, t in enumerate(docs)])
+    plan = distinct_plan("default", "d", "d", where, terms, order=order, limit=limit)
+    with pytest.raises(q.Ineligible):
+        q.Operator(plan, str(tmp_path))  # without a tail there is nothing this operator could hand downstream
+    op = q.Operator(plan, str(tmp_path), tail=True)
+    assert op.tail_operators[0] == "InitialProject" and op.tail_operators.count("Distinct") == 2 and "FinalProject" in op.tail_operators
+    assert op.rest_index == 4  # the parallel projection and the serial Distinct are both absorbed
+    keys = sorted({e for e, _a in terms})
+    groups = oracle_groups(docs, "d", where, keys, [])
+    got = op.run_tail(op.import_result(as_rows(groups, [])))
+    want = O.run_distinct([O.parse_document(d) for d in docs], "d", where, terms)
+    canon = lambda rows: sorted(json.dumps(normalise(r), sort_keys=True) for r in rows)
+    if limit is None:
+        assert canon(got) == canon(want)
+    else:
+        assert len(got) == min(limit, len(want)) and set(canon(got)) <= set(canon(want))
+    if order:  # sorted by the sort terms (all of them projected under explicit aliases or their own names here)
+        names = [e.strip("`") if e.startswith("`") else [a or e for e2, a in terms if e2 == e][0] for e, _d in order]
+        import functools
+        from golden_plans import _cmp, _MISSING
+        def cmp(a, b):
+            for n_, (_e, desc) in zip(names, order):
+                c = _cmp(a.get(n_, _MISSING), b.get(n_, _MISSING))
+                if c:
+                    return -c if desc else c
+            return 0
+        assert all(cmp(got[i], got[i + 1]) <= 0 for i in range(len(got) - 1))
