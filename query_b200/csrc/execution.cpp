@@ -495,7 +495,7 @@ std::string GpuGroupAggregate::MarshalJSON() const {
     }
     if (query) {
         static const char* modes[] = {"ungrouped", "dense-shared-memory", "hbm-hash-64", "hbm-hash-128"};
-        s += std::string(",\"kernel\":{\"mode\":\"") + modes[query->kp.mode] + "\",\"accumulator_words\":" + std::to_string(query->ops.n) +
+        s += std::string(",\"kernel\":{\"mode\":\"") + (query->kp.dense_global ? "hbm-direct" : modes[query->kp.mode]) + "\",\"accumulator_words\":" + std::to_string(query->ops.n) +
              ",\"scan_bytes_per_row\":" + std::to_string(query->kp.scan_bytes_per_row) + "}";
     }
     return s + "}";
