@@ -252,7 +252,8 @@ int n1gpu_plan_build(const char* plan_json, const char* datastore_root, n1gpu_op
  * subset: Let (LETTING, plan/let.go), Filter (HAVING, plan/filter.go), InitialProject and
  * FinalProject (plan/project.go; no star, raw or DISTINCT projection), Order / Offset / Limit (plan/order.go,
  * plan/offset.go, plan/limit.go) of the enclosing Sequence.  Their expressions may use group keys, the aggregates of
- * the group operators, LETTING variables, explicit projection aliases (ORDER BY) and the operators of Filter.
+ * the group operators, LETTING variables, explicit projection aliases (ORDER BY), the operators of Filter and ROUND
+ * (expression/func_num.go:1304-1336).
  * `rest_index` then points behind the consumed children of the chain's Sequence, `outer_rest_index` behind those
  * consumed from the enclosing Sequence (0: none).  A plan whose tail is not eligible builds like n1gpu_plan_build
  * (n1gpu_operator_tail_operators reports an empty list) and the caller keeps its own operators after FinalGroup.

@@ -1088,6 +1088,12 @@ class _P:
             return Constant(None)
         if w == "missing":
             return Constant(MISSING)
+        if w == "round" and self.eat("("):
+            ops = [self.expr()]
+            if self.eat(","):
+                ops.append(self.expr())
+            self.expect(")")
+            return Round(*ops)
         if self.eat("("):
             distinct = False
             if self.eat_word("distinct"):
@@ -1196,6 +1202,48 @@ def parse(text: str) -> Expr:
     if p.i != len(p.s):
         raise ParseError("trailing text at %d in %r" % (p.i, text))
     return e
+
+
+class Round(Expr):
+    """round(x [, digits]) - the scalar function of the reference's aggregate goldens (ROUND(AVG(unitPrice), 5)); only the
+    operators behind FinalGroup evaluate it.  expression/func_num.go:1304-1336 (Apply), :1715-1736 (roundFloat: half to
+    even on the scaled value), value.NewValue (integral -> int)."""
+
+    def __init__(self, *ops):
+        self.ops = list(ops)
+
+    def children(self):
+        return list(self.ops)
+
+    def evaluate(self, item):
+        a = self.ops[0].evaluate(item)
+        if a is MISSING:
+            return MISSING
+        if vtype(a) != T_NUMBER:
+            return None
+        prec = 0
+        if len(self.ops) > 1:
+            p = self.ops[1].evaluate(item)
+            if p is MISSING:
+                return MISSING
+            if vtype(p) != T_NUMBER or float(p) != math.trunc(float(p)):
+                return None
+            prec = int(p)
+        x = float(a)
+        if math.isnan(x) or math.isinf(x):
+            return new_value(x)
+        sign = 1.0
+        if x < 0:
+            sign, x = -1.0, -x
+        pw = math.pow(10, float(prec))
+        inter = x * pw + 0.5
+        r = math.floor(inter)
+        if r == inter and math.fmod(r, 2) != 0:
+            r -= 1
+        return new_value(sign * r / pw)
+
+    def __str__(self):  # stringer.go:581-604
+        return "round(" + ", ".join(str(o) for o in self.ops) + ")"
 
 
 # --------------------------------------------------------------------------------------

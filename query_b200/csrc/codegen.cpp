@@ -202,6 +202,7 @@ struct Gen {
             case EK::ARRAY: N1_THROW(N1GPU_E_INELIGIBLE, "array value outside IN");
             case EK::AGG: N1_THROW(N1GPU_E_INELIGIBLE, "nested aggregate");
             case EK::IDENT: N1_THROW(N1GPU_E_INELIGIBLE, "bare identifier");
+            case EK::ROUND: N1_THROW(N1GPU_E_INELIGIBLE, "round() on the GPU path");
         }
         N1_THROW(N1GPU_E_INVALID, "unhandled expression kind");
     }

@@ -21,7 +21,8 @@ enum class EK {
     AND, OR, NOT,
     IS_NULL, IS_NOT_NULL, IS_MISSING, IS_NOT_MISSING, IS_VALUED, IS_NOT_VALUED,
     ARRAY,  // array construct (only as the right side of IN)
-    AGG     // aggregate call
+    AGG,    // aggregate call
+    ROUND   // round(x [, digits]) - host only: the operators behind FinalGroup (group_tail.cpp); never reaches a kernel
 };
 
 enum class AggKind { COUNT, COUNTN, SUM, AVG, MIN, MAX };

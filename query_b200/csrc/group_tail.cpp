@@ -214,6 +214,26 @@ HValue eval(const Expr& e, const Env& env) {
             const HValue a = eval(*e.ops[0], env);
             return a.cls <= C_NULL ? a : HValue::boolean(!truth(a));
         }
+        case EK::ROUND: {  // expression/func_num.go:1304-1336 (Round.Apply) + :1715-1736 (roundFloat: half to even)
+            const HValue a = eval(*e.ops[0], env);
+            if (a.cls == C_MISSING) return a;
+            if (!is_num(a)) return null();
+            int prec = 0;
+            if (e.ops.size() > 1) {
+                const HValue p = eval(*e.ops[1], env);
+                if (p.cls == C_MISSING) return p;
+                if (!is_num(p) || p.num() != std::trunc(p.num())) return null();
+                prec = (int)p.num();
+            }
+            double x = a.num();
+            if (x != x || std::isinf(x)) return new_num(x);
+            double sign = 1.0;
+            if (x < 0) { sign = -1.0; x = -x; }
+            const double pw = std::pow(10.0, (double)prec), inter = x * pw + 0.5;
+            double r = std::floor(inter);
+            if (r == inter && std::fmod(r, 2.0) != 0) r -= 1;
+            return new_num(sign * r / pw);
+        }
         case EK::IS_NULL: { const HValue a = eval(*e.ops[0], env); return a.cls == C_NULL ? HValue::boolean(true) : (a.cls == C_MISSING ? a : HValue::boolean(false)); }
         case EK::IS_NOT_NULL: { const HValue a = eval(*e.ops[0], env); return a.cls == C_NULL ? HValue::boolean(false) : (a.cls == C_MISSING ? a : HValue::boolean(true)); }
         case EK::IS_MISSING: return HValue::boolean(eval(*e.ops[0], env).cls == C_MISSING);

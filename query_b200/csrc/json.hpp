@@ -284,13 +284,29 @@ inline void quote(const std::string& s, std::string& out) {  // JSON string, no 
 }
 
 // strconv.FormatFloat(f,'f',-1,64) with -0 -> 0 (value/float.go:31-48): shortest round-trip digits, no exponent.
+// Number text of a floatValue: Go's strconv.FormatFloat(f, 'f', -1, 64) - the shortest digits that read back as f, laid
+// out in fixed notation (value/float.go:31-48; "-0" is written "0").  std::to_chars' own fixed format prints the exact
+// binary value for large magnitudes (1e300 -> 301 exact digits), so the shortest digits are taken from its scientific
+// form and laid out here.
 inline std::string format_float(double f) {
     if (std::isnan(f)) return "\"NaN\"";
     if (std::isinf(f)) return f > 0 ? "\"+Infinity\"" : "\"-Infinity\"";
-    if (f == 0) f = 0;
-    char buf[400];
-    auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::fixed);
-    return std::string(buf, r.ptr);
+    if (f == 0) return "0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::scientific);
+    std::string sci(buf, r.ptr), digits, out;
+    size_t i = 0;
+    if (sci[i] == '-') { out = "-"; ++i; }
+    for (; i < sci.size() && sci[i] != 'e'; ++i) if (sci[i] != '.') digits.push_back(sci[i]);
+    const int exp10 = std::atoi(sci.c_str() + i + 1);
+    if (exp10 >= 0) {
+        const size_t int_len = (size_t)exp10 + 1;
+        if (digits.size() <= int_len) out += digits + std::string(int_len - digits.size(), '0');
+        else out += digits.substr(0, int_len) + "." + digits.substr(int_len);
+    } else {
+        out += "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+    }
+    return out;
 }
 
 }  // namespace json
