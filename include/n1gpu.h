@@ -274,6 +274,9 @@ int n1gpu_operator_run_tail(n1gpu_operator* op, const n1gpu_result* r, char* buf
 int n1gpu_operator_import_result(const n1gpu_operator* op, int64_t ngroups, const uint8_t* key_cls, const int64_t* key_val,
                                  const uint8_t* agg_cls, const int64_t* agg_val, const char* blob, const int64_t* offsets,
                                  int64_t nstrings, n1gpu_result** out);
+/* Group keys / aggregates of the operator's group operators (the row widths of import_result).       */
+int n1gpu_operator_num_keys(const n1gpu_operator* op);
+int n1gpu_operator_num_aggregates(const n1gpu_operator* op);
 /* execution.Operator.RunOnce: scans, filters, groups; the result is what FinalGroup would have sent. */
 int n1gpu_operator_run_once(n1gpu_operator* op, n1gpu_result** out);
 int n1gpu_operator_send_stop(n1gpu_operator* op);

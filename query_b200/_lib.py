@@ -100,6 +100,8 @@ _SIGS = {
     "n1gpu_plan_build_tail": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "n1gpu_operator_tail_operators": (C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
     "n1gpu_operator_import_result": (C.c_int, [_P, C.c_int64, _U8P, _I64P, _U8P, _I64P, C.c_char_p, _I64P, C.c_int64, C.POINTER(C.c_void_p)]),
+    "n1gpu_operator_num_keys": (C.c_int, [_P]),
+    "n1gpu_operator_num_aggregates": (C.c_int, [_P]),
     "n1gpu_operator_run_tail": (C.c_int, [_P, _P, C.c_char_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 

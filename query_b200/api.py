@@ -293,6 +293,20 @@ class Result:
             return C.string_at(p, n.value).decode("utf-8", "surrogateescape")
         raise ValueError(cls)
 
+    def arrays(self):
+        """(key_cls, key_val, agg_cls, agg_val, strings): the flat result arrays and the string table (utf-8 bytes) that
+        string payloads index - what Operator.import_arrays takes."""
+        self._fetch()
+        strings = []
+        for cls, val in ((self.key_cls, self.key_val), (self.agg_cls, self.agg_val)):
+            if cls.size and (cls == C_STRING).any():
+                top = int(val[cls == C_STRING].max())
+                while len(strings) <= top:
+                    p, n = C.c_char_p(), C.c_int64()
+                    check(lib().n1gpu_result_string(self._h, len(strings), C.byref(p), C.byref(n)))
+                    strings.append(C.string_at(p, n.value))
+        return self.key_cls.copy(), self.key_val.copy(), self.agg_cls.copy(), self.agg_val.copy(), strings
+
     def rows(self):
         """[(keys list, aggregates list)] with python values (int / float / str / bool / None / MISSING)."""
         self._fetch()
@@ -525,6 +539,19 @@ class Operator:
                 kc[g * nk + k], kv[g * nk + k] = enc(v)
             for a, v in enumerate(ag):
                 ac[g * na + a], av[g * na + a] = enc(v)
+        return self.import_arrays(kc, kv, ac, av, strings)
+
+    def import_arrays(self, key_cls, key_val, agg_cls, agg_val, strings):
+        """The same from flat arrays in n1gpu_result_fetch layout ([ngroups * nkeys] / [ngroups * naggs], row-major; string
+        payloads index `strings`, a list of utf-8 bytes) - what Result.arrays() returns, e.g. gathered from several ranks."""
+        kc = np.ascontiguousarray(key_cls, dtype=np.uint8).reshape(-1)
+        kv = np.ascontiguousarray(key_val, dtype=np.int64).reshape(-1)
+        ac = np.ascontiguousarray(agg_cls, dtype=np.uint8).reshape(-1)
+        av = np.ascontiguousarray(agg_val, dtype=np.int64).reshape(-1)
+        nk, na = self.num_keys, self.num_aggregates
+        n = len(kc) // nk if nk else (len(ac) // na if na else 0)
+        if len(kc) != n * nk or len(ac) != n * na or len(kv) != len(kc) or len(av) != len(ac):
+            raise ValueError("array sizes do not describe %d groups of %d keys and %d aggregates" % (n, nk, na))
         offs = np.zeros(len(strings) + 1, dtype=np.int64)
         if strings:
             np.cumsum([len(b) for b in strings], out=offs[1:])
@@ -533,6 +560,14 @@ class Operator:
                                                  ac.ctypes.data_as(_lib._U8P), av.ctypes.data_as(_lib._I64P), b"".join(strings),
                                                  offs.ctypes.data_as(_lib._I64P), len(strings), C.byref(r)))
         return Result(r)
+
+    @property
+    def num_keys(self):
+        return int(lib().n1gpu_operator_num_keys(self._h))
+
+    @property
+    def num_aggregates(self):
+        return int(lib().n1gpu_operator_num_aggregates(self._h))
 
     def run_tail(self, result):
         """The rows FinalProject sends (HAVING / projection / ORDER BY / OFFSET / LIMIT applied): list of dicts."""

@@ -496,6 +496,8 @@ int n1gpu_operator_import_result(const n1gpu_operator* op, int64_t ngroups, cons
         *out = new n1gpu_result{std::move(r)};
     });
 }
+int n1gpu_operator_num_keys(const n1gpu_operator* op) { return op && op->op->query ? (int)op->op->query->keys.size() : N1GPU_E_INVALID; }
+int n1gpu_operator_num_aggregates(const n1gpu_operator* op) { return op && op->op->query ? (int)op->op->query->aggs.size() : N1GPU_E_INVALID; }
 int n1gpu_operator_run_once(n1gpu_operator* op, n1gpu_result** out) {
     return guard([&] { REQUIRE(op); REQUIRE(out); *out = new n1gpu_result{op->op->RunOnce()}; });
 }

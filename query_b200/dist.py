@@ -256,3 +256,26 @@ class DistributedQuery:
         n, ndg = sum(rc), sum(drc)
         q.partial_import(got.data_ptr() if n else 0, n, dgot.data_ptr() if ndg else 0, ndg)
         return q.finalize()
+
+
+def gather_results(operator, result, group=None):
+    """Groups finalised by several ranks (every owner holds its share) -> ONE result on every rank, so that
+    the operator's tail (HAVING / projection / ORDER BY / LIMIT need all groups) can run over it:
+    Result.arrays() of every rank, string tables concatenated and the string payloads re-based, Operator.import_arrays."""
+    kc, kv, ac, av, strings = result.arrays()
+    w = world()
+    if w == 1:
+        return operator.import_arrays(kc, kv, ac, av, strings)
+    parts = [None] * w
+    dist.all_gather_object(parts, (kc, kv, ac, av, strings), group=group)
+    all_strings, out = [], [[], [], [], []]
+    for pkc, pkv, pac, pav, pstr in parts:
+        base = len(all_strings)
+        pkv, pav = pkv.copy(), pav.copy()
+        pkv[pkc == 6] += base  # C_STRING payloads index this rank's string table
+        pav[pac == 6] += base
+        all_strings += list(pstr)
+        for dst, a in zip(out, (pkc, pkv, pac, pav)):
+            dst.append(a.reshape(-1))
+    cat = [np.concatenate(a) if a else np.zeros(0) for a in out]
+    return operator.import_arrays(cat[0], cat[1], cat[2], cat[3], all_strings)

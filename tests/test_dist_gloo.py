@@ -95,3 +95,37 @@ def test_dictionary_and_statistics_agreement_gives_identical_kernels():
     assert out[0][1] == [1, 0] and out[1][1] == [2, 0]
     assert out[0][2][:5] == out[1][2][:5] == [(1 << 0) | (1 << 4) | (1 << 5), 1, -2, 40, 1]
     assert out[0][3] == out[1][3], "ranks must compile the same kernel (same packing, same constants)"
+
+
+def _gathered_tail(rank, world):
+    """Each rank holds the groups whose key hashes to it (what the owner-bucketed merge leaves); the tail runs over the
+    gathered result on every rank."""
+    import sys
+    import tempfile
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import query_b200 as q
+    from gen_n1 import F, make_docs
+    from oracle import n1ql_oracle as O
+    from plans_n1 import explain_plan
+    from query_b200 import dist as qd
+    from util_n1 import write_keyspace
+    docs = make_docs(400, seed=71)
+    keys, aggs = [F("t"), F("h")], sorted({"count(*)", "sum(%s)" % F("p"), "max(%s)" % F("s")})
+    tail = dict(having="(count(*) > 1)", terms=[(F("t"), None), (F("h"), "h"), ("count(*)", "c"), ("max(%s)" % F("s"), "top")],
+                order=[("`c`", True), (F("t"), False), ("`h`", False)], limit=9)
+    root = tempfile.mkdtemp()
+    write_keyspace(root, "default", "d", [("k%05d" % i, t) for i, t in enumerate(docs)])
+    op = q.Operator(explain_plan("default", "d", "d", None, keys, aggs, tail=tail), root, tail=True)
+    groups = O.run_chain([O.parse_document(d) for d in docs], "d", None, keys, aggs)
+    conv = lambda v: q.MISSING if v is O.MISSING else v
+    rows = [([conv(k) for k in g.keys], [conv(g.aggregates[a]) for a in aggs]) for g in groups]
+    mine = [r for i, r in enumerate(rows) if i % world == rank]  # this rank's share of the groups
+    merged = qd.gather_results(op, op.import_result(mine))
+    got = op.run_tail(merged)
+    want = O.run_tail(groups, having=tail["having"], terms=tail["terms"], order=tail["order"], limit=tail["limit"])
+    return merged.num_groups == len(rows), got == want or [got, want]
+
+
+def test_tail_over_groups_gathered_from_all_ranks():
+    for complete, same in _run(_gathered_tail):
+        assert complete and same is True, same

@@ -52,8 +52,12 @@ def table_config5(n, seed):
     rng = np.random.default_rng(seed)
     vocab = 100_000
     words = sorted("w%06d-%x" % (i, (i * 2654435761) & 0xffffff) for i in range(vocab))
-    u = rng.random(n)
-    rank = (np.power(float(vocab), u) - 1).astype(np.uint32)
+    # Zipf(s = 1.1) over the vocabulary by inverse CDF, popularity rank -> dictionary code through a fixed permutation
+    # (the distribution tools/full_size.py and tools/sweep_config5.py use for BASELINE config 5)
+    w = np.arange(1, vocab + 1, dtype=np.float64) ** -1.1
+    cdf = np.cumsum(w / w.sum())
+    perm = np.random.default_rng(4).permutation(vocab).astype(np.uint32)
+    rank = perm[np.minimum(np.searchsorted(cdf, rng.random(n)), vocab - 1)]
     ktag = np.full(n, 6, dtype=np.uint8)
     r = rng.integers(0, 10, n)
     ktag[r == 0] = 0
