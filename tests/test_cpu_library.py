@@ -203,3 +203,23 @@ def test_plan_build_substitution_rules(tmp_path):
     nogroup = {"#operator": "Sequence", "~children": [plan["~children"][0]["~children"][0], plan["~children"][0]["~children"][1]]}
     _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(nogroup, str(tmp_path)))
     _expect(q._lib.E_PARSE, lambda: q.Operator("{not json", str(tmp_path)))
+
+
+@pytest.mark.parametrize("ks,where,keys,aggs,ref", [
+    ("catalog", None, [], ["array_agg((`catalog`.`asin`))"], "case_group_by_having.json:69-81 ARRAY_AGG"),
+    ("orders", None, ["((`orders`.`orderlines`)[1])"], ["count(*)"], "case_group_by_having.json:83-110 array element key"),
+    ("orders", None, ["(`orders`.`orderlines`)"], ["count(*)"], "case_group_by_having.json:112-146 array-valued key"),
+    ("catalog", "any `director` in ((`catalog`.`details`).`director`) satisfies `director` end", ["((`catalog`.`details`).`director`)"],
+     ["count(*)"], "case_group_by_having.json:148-159 ANY ... SATISFIES"),
+    ("jobs", None, ["(`jobs`.`join_yr`)"], ["array_agg(distinct (`jobs`.`job_title`))"], "case_group_by_having.json:254-275 ARRAY_AGG DISTINCT"),
+], ids=["array_agg", "element_key", "array_key", "any_satisfies", "array_agg_distinct"])
+def test_golden_statements_outside_the_subset_are_not_substituted(ks, where, keys, aggs, ref, tmp_path):
+    """SURVEY.md 8c lists these goldens as "must stay on the Go path": the plan builder answers INELIGIBLE (the caller
+    keeps its operators) - at parse time for constructs outside the subset, at bind time for a column holding arrays."""
+    from plans_n1 import explain_plan
+    from util_n1 import write_keyspace
+    write_keyspace(str(tmp_path), "default", ks, keyspaces()["filestore/" + ks])
+    plan = explain_plan("default", ks, None, where, keys, aggs)
+    for tail in (False, True):
+        e = _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(plan, str(tmp_path), tail=tail))
+        assert isinstance(e, q.Ineligible), ref
