@@ -5,6 +5,7 @@ No GPU needed: the groups come from the oracle's chain and enter through n1gpu_o
 the host evaluator against (a) the reference's golden results and (b) the oracle's restatement of the same operators.
 tests/test_gpu_parity.py runs the same plans end to end on the device."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -211,3 +212,18 @@ def test_select_distinct_is_a_group_by_over_the_projected_terms(name, where, ter
                     return -c if desc else c
             return 0
         assert all(cmp(got[i], got[i + 1]) <= 0 for i in range(len(got) - 1))
+
+
+def test_tail_over_empty_input(tmp_path):
+    """group_final.go:108-117 + the tail: no documents and no GROUP BY still give one row of Default() values, which
+    HAVING may drop; with GROUP BY there is no row at all."""
+    os.makedirs(str(tmp_path / "default" / "d"))
+    aggs = sorted({"count(*)", "sum((`d`.`p`))", "min((`d`.`p`))"})
+    terms = [("count(*)", "n"), ("sum((`d`.`p`))", "s"), ("(min((`d`.`p`)) is null)", "nomin"), ("(count(*) + 1)", None)]
+    for keys, having, want in (([], None, [{"n": 0, "s": None, "nomin": True, "$1": 1}]), ([], "(count(*) > 0)", []),
+                               (["(`d`.`t`)"], None, [])):
+        tail = dict(having=having, terms=terms, order=[("`n`", False)])
+        op = q.Operator(explain_plan("default", "d", "d", None, keys, aggs, tail=tail), str(tmp_path), tail=True)
+        groups = oracle_groups([], "d", None, keys, aggs)
+        got = op.run_tail(op.import_result(as_rows(groups, aggs)))
+        assert got == want == O.run_tail(groups, having=having, terms=terms, order=tail["order"])
