@@ -45,6 +45,8 @@ def main():
     t, words, tensors = fs.config5_table(n)
     ref = fs.config5_reference(words, tensors)
     only = os.environ.get("ONLY")
+    if os.environ.get("EXTRA"):  # ad-hoc variants: EXTRA='[["name", {"N1GPU_...": "..."}], ...]' replaces the list
+        VARIANTS[:] = [(n_, e_) for n_, e_ in json.loads(os.environ["EXTRA"])]
     for name, env in VARIANTS:
         if only and only not in name:
             continue
