@@ -1226,21 +1226,32 @@ class Round(Expr):
             p = self.ops[1].evaluate(item)
             if p is MISSING:
                 return MISSING
-            if vtype(p) != T_NUMBER or float(p) != math.trunc(float(p)):
+            if vtype(p) != T_NUMBER:
                 return None
-            prec = int(p)
+            pf = float(p)
+            if math.isnan(pf) or (not math.isinf(pf) and pf != math.trunc(pf)):  # Go: pf != math.Trunc(pf)
+                return None
+            prec = _go_int64_of_float(pf)  # Go: p = int(pf)
         x = float(a)
         if math.isnan(x) or math.isinf(x):
             return new_value(x)
         sign = 1.0
         if x < 0:
             sign, x = -1.0, -x
-        pw = math.pow(10, float(prec))
+        # IEEE arithmetic as Go's math package does it (Python raises where Go yields Inf / NaN)
+        try:
+            pw = math.pow(10.0, float(prec))
+        except OverflowError:
+            pw = math.inf
         inter = x * pw + 0.5
-        r = math.floor(inter)
-        if r == inter and math.fmod(r, 2) != 0:
+        r = inter if (math.isinf(inter) or math.isnan(inter)) else float(math.floor(inter))
+        odd = True if (math.isinf(r) or math.isnan(r)) else math.fmod(r, 2) != 0  # Mod(Inf, 2) = NaN, and NaN != 0
+        if r == inter and odd:
             r -= 1
-        return new_value(sign * r / pw)
+        try:
+            return new_value(sign * r / pw)
+        except ZeroDivisionError:
+            return new_value(math.nan if r == 0 or math.isnan(r) else math.copysign(math.inf, sign * r))
 
     def __str__(self):  # stringer.go:581-604
         return "round(" + ", ".join(str(o) for o in self.ops) + ")"

@@ -218,12 +218,12 @@ HValue eval(const Expr& e, const Env& env) {
             const HValue a = eval(*e.ops[0], env);
             if (a.cls == C_MISSING) return a;
             if (!is_num(a)) return null();
-            int prec = 0;
+            i64 prec = 0;
             if (e.ops.size() > 1) {
                 const HValue p = eval(*e.ops[1], env);
                 if (p.cls == C_MISSING) return p;
                 if (!is_num(p) || p.num() != std::trunc(p.num())) return null();
-                prec = (int)p.num();
+                prec = go_i64(p.num());  // Go: p = int(pf)
             }
             double x = a.num();
             if (x != x || std::isinf(x)) return new_num(x);
