@@ -134,9 +134,39 @@ bool Table::load_segment(const std::string& file, const std::string& source) {
 // A packed document source: one JSON document per line (NDJSON), in primary-key order - the form a keyspace of more
 // than a few million documents takes when one file per document (file.go) stops being practical.
 void Table::load_ndjson(const std::string& file, int threads) {
-    std::ifstream f(file, std::ios::binary);
-    if (!f) N1_THROW(N1GPU_E_IO, "cannot read %s", file.c_str());
-    std::string buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    FILE* fp = fopen(file.c_str(), "rb");
+    if (!fp) N1_THROW(N1GPU_E_IO, "cannot read %s", file.c_str());
+    std::string buf;
+    struct stat st;
+    if (fstat(fileno(fp), &st) == 0 && st.st_size > 0) buf.resize((size_t)st.st_size);
+    size_t got = buf.empty() ? 0 : fread(&buf[0], 1, buf.size(), fp);
+    buf.resize(got);
+    for (char chunk[1 << 16];;) {  // whatever a growing file (or a pipe) still holds
+        size_t n = fread(chunk, 1, sizeof chunk, fp);
+        if (n == 0) break;
+        buf.append(chunk, n);
+    }
+    fclose(fp);
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r'; };
+    if (threads >= 0) {
+        // host shredder, in place: document i = [start of its line, start of the next non-blank line) - the line end and
+        // blank lines are trailing white space of the document (value/parsed.go:76-98 skips leading ' ', '\t', '\n')
+        std::vector<i64> offsets;
+        size_t i = 0;
+        while (i < buf.size()) {
+            size_t e = buf.find('\n', i);
+            if (e == std::string::npos) e = buf.size();
+            size_t a = i;
+            while (a < e && blank(buf[a])) ++a;
+            if (a < e) offsets.push_back((i64)i);
+            i = e + 1;
+        }
+        const i64 ndocs = (i64)offsets.size();
+        offsets.push_back((i64)buf.size());
+        if (ndocs == 0) offsets.assign(1, 0);
+        append_json(buf.data(), offsets.data(), ndocs, threads);
+        return;
+    }
     std::vector<i64> offsets;
     std::string packed;
     packed.reserve(buf.size());
@@ -146,13 +176,12 @@ void Table::load_ndjson(const std::string& file, int threads) {
         size_t e = buf.find('\n', i);
         if (e == std::string::npos) e = buf.size();
         size_t a = i, b = e;
-        while (a < b && (buf[a] == ' ' || buf[a] == '\t' || buf[a] == '\r')) ++a;
-        while (b > a && (buf[b - 1] == ' ' || buf[b - 1] == '\t' || buf[b - 1] == '\r')) --b;
+        while (a < b && blank(buf[a])) ++a;
+        while (b > a && blank(buf[b - 1])) --b;
         if (b > a) { packed.append(buf, a, b - a); offsets.push_back((i64)packed.size()); }  // blank lines are not documents
         i = e + 1;
     }
-    if (threads < 0) append_json_device(packed.data(), offsets.data(), (i64)offsets.size() - 1);
-    else append_json(packed.data(), offsets.data(), (i64)offsets.size() - 1, threads);
+    append_json_device(packed.data(), offsets.data(), (i64)offsets.size() - 1);
 }
 
 }  // namespace n1

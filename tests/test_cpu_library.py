@@ -99,6 +99,19 @@ def test_shredder_edge_documents():
         assert (O.vtype(v) == O.T_MISSING) == (tags[r] == 0), (r, doc)
 
 
+def test_numbers_nobody_reads_are_only_checked_for_syntax():
+    """json.Validate (value/parsed.go:38-67) looks at syntax: an unreferenced 1e999 keeps its document valid, a malformed
+    number makes every field of the document MISSING.  (The device shredder treats skipped numbers the same way.)"""
+    docs = ['{"a": 1, "q": 1e999}', '{"a": 2, "q": -1E+400, "z": [1e999, {"y": 2e-999}]}', '{"a": 3, "q": 1e}', '{"a": 4, "q": 01}',
+            '{"a": 5, "q": 1.}', '{"a": 6, "q": -}', '{"a": 7, "q": 1.5e-3}', '{"a": 8, "q": .5}', '{"a": 9, "q": +1}']
+    t = q.Table(["a"])
+    t.append_json(docs)
+    pay, tags = t.peek(0)
+    assert list(tags) == [4, 4, 0, 0, 0, 0, 4, 0, 0] and [int(pay[i]) for i in (0, 1, 6)] == [1, 2, 7]
+    for r, doc in enumerate(docs):  # and the oracle's document model agrees on which documents are valid
+        assert (O.vtype(O.field(O.parse_document(doc), "a")) == O.T_MISSING) == (tags[r] == 0), doc
+
+
 @pytest.mark.parametrize("name,where,keys,aggs", QUERIES, ids=[x[0] for x in QUERIES])
 def test_every_matrix_query_compiles_for_sm100a_and_oracle_runs(name, where, keys, aggs):
     docs = make_docs(400, seed=5)
