@@ -85,7 +85,7 @@ def _agree(rank, world):
     d = t.dictionary("s")
     st = t.stats("n")
     t.seal()
-    qq = q.Query(t, "d", "((`d`.`s`) <= \"b\")", ["(`d`.`s`)"], ["count(*)", "sum((`d`.`n`))"])
+    qq = q.Query(t, "d", "((`d`.`s`) <= \"b\")", ["(`d`.`s`)"], ["count(*)", "count((`d`.`n`))", "sum((`d`.`n`))"])
     return [x.decode() for x in d], [int(p) for p, g in zip(pay, tags) if g == 6], st.tolist(), qq.kernel_source
 
 
@@ -94,6 +94,7 @@ def test_dictionary_and_statistics_agreement_gives_identical_kernels():
     assert out[0][0] == out[1][0] == ["a", "b", "c"]
     assert out[0][1] == [1, 0] and out[1][1] == [2, 0]
     assert out[0][2][:5] == out[1][2][:5] == [(1 << 0) | (1 << 4) | (1 << 5), 1, -2, 40, 1]
+    assert out[0][2][7] == out[1][2][7] == 1  # MISSING / NULL rows of `n` over the whole keyspace (rank 1 holds the one)
     assert out[0][3] == out[1][3], "ranks must compile the same kernel (same packing, same constants)"
 
 
