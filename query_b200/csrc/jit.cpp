@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <limits.h>
 #include <nvrtc.h>
 #include <stdlib.h>
@@ -147,6 +148,34 @@ std::string jit_compile_cubin(const std::string& source, std::string* log) {
         if (it != g_cubin_cache.end()) return it->second;
     }
     Nvrtc& rt = nvrtc();
+    // Optional on-disk kernel cache (N1GPU_KERNEL_CACHE_DIR): NVRTC + ptxas cost 0.25-0.45 s per new query shape, which a
+    // restarted server would otherwise pay again for every prepared statement.  The key covers everything the cubin
+    // depends on: generated source, device library, NVRTC version, target.
+    std::string cache_file;
+    if (const char* dir = getenv("N1GPU_KERNEL_CACHE_DIR")) {
+        if (*dir) {
+            u64 h = 1469598103934665603ULL;
+            auto mix = [&](const char* p, size_t n) { for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ULL; } };
+            mix(source.data(), source.size());
+            mix(k_device_header, strlen(k_device_header));
+            const std::string ver = strf("nvrtc %d.%d sm_100a fmad=false v1", rt.major, rt.minor);
+            mix(ver.data(), ver.size());
+            cache_file = std::string(dir) + strf("/nq_%016llx_%zu.cubin", (unsigned long long)h, source.size());
+            FILE* f = fopen(cache_file.c_str(), "rb");
+            if (f) {
+                std::string cubin;
+                char buf[1 << 16];
+                for (size_t n; (n = fread(buf, 1, sizeof buf, f)) > 0;) cubin.append(buf, n);
+                fclose(f);
+                if (cubin.size() > 64 && memcmp(cubin.data(), "\x7f" "ELF", 4) == 0) {
+                    if (log) log->clear();
+                    std::lock_guard<std::mutex> lk(g_mu);
+                    g_cubin_cache[source] = cubin;
+                    return cubin;
+                }
+            }
+        }
+    }
     nvrtcProgram prog;
     const char* hdr_names[] = {"n1ql_device.cuh"};
     const char* hdr_srcs[] = {k_device_header};
@@ -172,6 +201,14 @@ std::string jit_compile_cubin(const std::string& source, std::string* log) {
     std::string cubin(cs, '\0');
     rt.GetCUBIN(prog, &cubin[0]);
     rt.DestroyProgram(&prog);
+    if (!cache_file.empty()) {  // best effort: a cache that cannot be written only costs the next compile
+        const std::string tmp = cache_file + strf(".%d.tmp", (int)getpid());
+        FILE* f = fopen(tmp.c_str(), "wb");
+        if (f) {
+            const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            if (fclose(f) != 0 || !ok || rename(tmp.c_str(), cache_file.c_str()) != 0) remove(tmp.c_str());
+        }
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     g_cubin_cache[source] = cubin;
     return cubin;

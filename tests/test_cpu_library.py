@@ -2,6 +2,7 @@
 the shredder matches the oracle's document model, every query of the matrix compiles to an sm_100a
 cubin through NVRTC, and the error contract (parse / ineligible / no-device) holds."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -236,3 +237,26 @@ def test_golden_statements_outside_the_subset_are_not_substituted(ks, where, key
     for tail in (False, True):
         e = _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(plan, str(tmp_path), tail=tail))
         assert isinstance(e, q.Ineligible), ref
+
+
+def test_on_disk_kernel_cache(tmp_path):
+    """N1GPU_KERNEL_CACHE_DIR: a query shape compiled once (NVRTC + ptxas, 0.25-0.45 s) is an ELF cubin on disk that a
+    restarted process loads instead of compiling; the key covers source, device library, NVRTC version and target."""
+    import subprocess
+    import sys
+    prog = (
+        "import sys, time; sys.path.insert(0, %r)\n"
+        "import numpy as np, query_b200 as q\n"
+        "t = q.Table(['n']); t.set_column('n', np.arange(1000, dtype=np.int64)); t.seal()\n"
+        "t0 = time.time(); qq = q.Query(t, 'd', '((`d`.`n`) between 31 and 415)', [], ['count(*)', 'sum((`d`.`n`))'])\n"
+        "print(time.time() - t0)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, N1GPU_KERNEL_CACHE_DIR=str(tmp_path))
+    cold = float(subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True).stdout.split()[-1])
+    files = [f for f in os.listdir(str(tmp_path)) if f.endswith(".cubin")]
+    assert len(files) == 1 and open(os.path.join(str(tmp_path), files[0]), "rb").read(4) == b"\x7fELF"
+    warm = float(subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True).stdout.split()[-1])
+    assert len(os.listdir(str(tmp_path))) == 1 and warm < cold / 3, (cold, warm)
+    # a damaged file is ignored and replaced
+    open(os.path.join(str(tmp_path), files[0]), "wb").write(b"garbage")
+    subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True)
+    assert open(os.path.join(str(tmp_path), files[0]), "rb").read(4) == b"\x7fELF"
