@@ -119,6 +119,14 @@ void bind(Expr& e, const Scope& sc) {
         N1_THROW(N1GPU_E_INELIGIBLE, "identifier `%s` is neither a group key, a LETTING variable nor a projection alias", e.name.c_str());
     }
     if (e.kind == EK::FIELD) N1_THROW(N1GPU_E_INELIGIBLE, "%s is not a group key", e.str().c_str());
+    if (e.kind == EK::ARRAY) N1_THROW(N1GPU_E_INELIGIBLE, "an array construct is only evaluated as the right side of IN");
+    if (e.kind == EK::IN) {
+        if (e.ops[1]->kind != EK::ARRAY) N1_THROW(N1GPU_E_INELIGIBLE, "IN over something other than an array construct");
+        bind(*e.ops[0], sc);
+        e.ops[1]->col = R_EVAL << 16;
+        for (auto& el : e.ops[1]->ops) bind(*el, sc);
+        return;
+    }
     for (auto& o : e.ops) bind(*o, sc);
 }
 

@@ -163,6 +163,8 @@ def test_ineligible_tail_shapes(tmp_path):
     assert ops(dict(terms=[(F("p"), None)])) == []                       # not a group key
     assert ops(dict(terms=[("max(%s)" % F("p"), None)])) == []           # aggregate the group operators do not compute
     assert ops(dict(terms=[("`d`", None)])) == []                        # the whole document
+    assert ops(dict(terms=[("(count(*) in %s)" % F("t"), "x")])) == []   # IN over a non-constructed array: decided at build time
+    assert ops(dict(terms=[("[1, 2]", "x")])) == []                      # an array value of its own
     assert ops(dict(terms=[(F("t"), None)], limit="1.5")) == ["InitialProject", "FinalProject"]  # not integral: Limit stays with the caller
     proj = lambda p: p["~children"][0]["~children"][5]["~child"]["~children"]
     assert ops(dict(terms=[(F("t"), None)]), lambda p: proj(p)[0].update(distinct=True)) == []
