@@ -260,3 +260,28 @@ def test_on_disk_kernel_cache(tmp_path):
     open(os.path.join(str(tmp_path), files[0]), "wb").write(b"garbage")
     subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True)
     assert open(os.path.join(str(tmp_path), files[0]), "rb").read(4) == b"\x7fELF"
+
+
+def test_random_expression_trees_compile_for_sm100a():
+    """The generator of tools/where_fuzz.py (the device differential fuzz, run under -m gpu): every random Filter /
+    operand tree it produces is either outside the subset (INELIGIBLE) or turns into a kernel NVRTC accepts."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import where_fuzz as wf
+    rng = random.Random(7)
+    docs = make_docs(300, seed=77)
+    compiled = 0
+    for _ in range(24):
+        where = str(O.parse(wf.cond(rng, 2)))
+        aggs = sorted({str(O.parse(a)) for a in ["count(*)", "count(%s)" % wf.arith(rng, 2, wf.ANY), "min(%s)" % wf.arith(rng, 2, wf.NUM + ["b"]),
+                                                 "max(%s)" % wf.arith(rng, 2, wf.NUM), "sum(%s)" % wf.arith(rng, 1, ["i", "p", "g", "f"])]})
+        keys = [wf.arith(rng, 1, ["g", "t", "b", "i"])] if rng.random() < 0.5 else []
+        try:
+            t = make_table(docs, where, keys, aggs)
+            t.seal()
+            q.Query(t, "d", where, keys, aggs)
+            compiled += 1
+        except q.Ineligible:
+            pass
+    assert compiled >= 12
