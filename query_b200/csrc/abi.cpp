@@ -11,7 +11,13 @@ using namespace n1;
 struct n1gpu_table { Table t; };
 struct n1gpu_query { std::unique_ptr<Query> q; };
 struct n1gpu_result { std::unique_ptr<Result> r; };
-struct n1gpu_operator { std::unique_ptr<execution::GpuGroupAggregate> op; };
+struct n1gpu_operator {
+    std::unique_ptr<execution::GpuGroupAggregate> op;
+    // the rows of the last run_tail, kept between the size query and the call that fills the caller's buffer
+    const void* tail_of = nullptr;
+    std::string tail_rows;
+    int64_t tail_count = 0;
+};
 
 static thread_local std::string g_last_error;
 
@@ -454,11 +460,18 @@ int n1gpu_operator_run_tail(n1gpu_operator* op, const n1gpu_result* r, char* buf
     int rc = guard([&] {
         REQUIRE(op); REQUIRE(r);
         if (op->op->tail.empty()) N1_THROW(N1GPU_E_INVALID, "the operator was built without a tail (n1gpu_plan_build_tail, eligible plan)");
-        i64 n = 0;
-        s = op->op->tail.Run(*r->r, &n);
-        if (rows) *rows = n;
+        if (op->tail_of != (const void*)r->r.get()) {
+            i64 n = 0;
+            op->tail_rows = op->op->tail.Run(*r->r, &n);
+            op->tail_count = n;
+            op->tail_of = (const void*)r->r.get();
+        }
+        if (rows) *rows = op->tail_count;
     });
-    return rc == N1GPU_OK ? copy_out(s, buf, cap, len) : rc;
+    if (rc != N1GPU_OK) return rc;
+    rc = copy_out(op->tail_rows, buf, cap, len);
+    if (buf && cap > (int64_t)op->tail_rows.size()) { op->tail_of = nullptr; std::string().swap(op->tail_rows); }  // delivered in full
+    return rc;
 }
 int n1gpu_operator_import_result(const n1gpu_operator* op, int64_t ngroups, const uint8_t* key_cls, const int64_t* key_val,
                                  const uint8_t* agg_cls, const int64_t* agg_val, const char* blob, const int64_t* offsets,

@@ -5,7 +5,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
 #include <map>
+#include <thread>
 
 namespace n1 {
 namespace execution {
@@ -406,58 +408,128 @@ bool GroupTail::add(const json::Node& op, const std::vector<std::string>& key_te
 }
 
 std::string GroupTail::Run(const Result& r, i64* rows_out) const {
-    struct Row {
-        std::map<std::string, HValue> fields;  // the "projection" attachment: sorted names, like Go's map marshalling
-        std::vector<HValue> sort;
-    };
-    std::vector<Row> rows;
+    // Three phases, so that a million groups cost what HAVING, the sort keys and the surviving rows cost - not a
+    // projected object per group: (A) per group: LETTING, HAVING, the explicitly aliased terms ORDER BY may name and the
+    // sort keys (all host cores for large results); (B) ORDER BY / OFFSET / LIMIT over group indices (a partial sort when
+    // LIMIT bounds the output); (C) the projection of the rows that are left, as JSON.
     std::vector<std::string> alias_names;
-    for (auto& t : terms) if (!t.as.empty()) alias_names.push_back(t.as);
-    for (i64 g = 0; g < r.ngroups; ++g) {
-        Env env;
-        env.r = &r;
-        env.g = g;
-        std::vector<HValue> lets;
+    std::vector<int> alias_term;  // the LAST term carrying each explicit alias: later terms override (project_initial.go:104-111)
+    for (size_t t = 0; t < terms.size(); ++t) {
+        if (terms[t].as.empty()) continue;
+        const int i = index_of(alias_names, terms[t].as);
+        if (i < 0) { alias_names.push_back(terms[t].as); alias_term.push_back((int)t); } else alias_term[(size_t)i] = (int)t;
+    }
+    const size_t nsort = order.size();
+    struct Part { std::vector<i64> g; std::vector<HValue> keys; };  // surviving groups and their nsort sort keys each
+    auto eval_lets = [&](Env& env, std::vector<HValue>& lets) {
+        lets.clear();
         for (auto& b : letting) lets.push_back(eval(*b.e, env));
         env.lets = &lets;
-        if (having_e && !truth(eval(*having_e, env))) continue;  // filter.go:49-61
-        Row row;
-        std::vector<HValue> aliases(alias_names.size());
-        for (auto& t : terms) {  // project_initial.go:98-117
-            const HValue v = eval(*t.e, env);
-            if (v.cls == C_MISSING) row.fields.erase(t.alias); else row.fields[t.alias] = v;
-            if (!t.as.empty()) aliases[(size_t)index_of(alias_names, t.as)] = v;  // explicit aliases override data
+    };
+    auto phase_a = [&](i64 g0, i64 g1, Part& out) {
+        std::vector<HValue> lets, aliases(alias_names.size());
+        for (i64 g = g0; g < g1; ++g) {
+            Env env;
+            env.r = &r;
+            env.g = g;
+            eval_lets(env, lets);
+            if (having_e && !truth(eval(*having_e, env))) continue;  // filter.go:49-61
+            out.g.push_back(g);
+            if (nsort) {
+                for (size_t i = 0; i < alias_term.size(); ++i) aliases[i] = eval(*terms[(size_t)alias_term[i]].e, env);
+                env.aliases = &aliases;
+                for (auto& s : order) out.keys.push_back(eval(*s.e, env));
+            }
         }
-        env.aliases = &aliases;
-        for (auto& s : order) row.sort.push_back(eval(*s.e, env));
-        rows.push_back(std::move(row));
-    }
-    if (!order.empty())  // order.go:119-166 (sort.Sort leaves ties in no particular order; here they keep theirs)
-        std::stable_sort(rows.begin(), rows.end(), [&](const Row& a, const Row& b) {
-            for (size_t i = 0; i < order.size(); ++i) {
-                const int c = collate_values(a.sort[i], b.sort[i]);
+    };
+    auto in_threads = [&](i64 n, const std::function<void(int, i64, i64)>& fn) -> int {
+        const int nthr = n < 65536 ? 1 : (int)std::min<i64>(std::max(1u, std::thread::hardware_concurrency()), 32);
+        if (nthr <= 1) { fn(0, 0, n); return 1; }
+        std::vector<std::string> errs((size_t)nthr);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthr; ++t)
+            pool.emplace_back([&, t] { try { fn(t, n * t / nthr, n * (t + 1) / nthr); } catch (const std::exception& e) { errs[(size_t)t] = e.what(); } });
+        for (auto& th : pool) th.join();
+        for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_INVALID, "%s", e.c_str());
+        return nthr;
+    };
+    const bool trace = getenv("N1GPU_TRACE") != nullptr;
+    double tp = now_sec();
+    auto phase = [&](const char* name) { if (trace) { const double t = now_sec(); fprintf(stderr, "[n1gpu tail] %-28s %8.3f ms\n", name, (t - tp) * 1e3); tp = t; } };
+    // survivors stay in the per-thread parts (no merge copy): a survivor is (part << 40 | index in part), which is also
+    // its position in group order
+    std::vector<Part> parts(32);
+    const int nparts = in_threads(r.ngroups, [&](int t, i64 g0, i64 g1) {
+        const size_t room = std::min<size_t>((size_t)(g1 - g0), having_e ? (size_t)1 << 16 : (size_t)1 << 22);  // HAVING usually drops most
+        parts[(size_t)t].g.reserve(room);
+        parts[(size_t)t].keys.reserve(room * nsort);
+        phase_a(g0, g1, parts[(size_t)t]);
+    });
+    phase("LETTING / HAVING / sort keys");
+    size_t nsurv = 0;
+    for (int t = 0; t < nparts; ++t) nsurv += parts[(size_t)t].g.size();
+    size_t first = 0, last = nsurv;
+    if (has_offset && offset > 0) first = (size_t)std::min<i64>(offset, (i64)nsurv);  // offset.go:75-83
+    if (has_limit) last = std::min(last, first + (size_t)std::max<i64>(limit, 0));   // limit.go:74-81
+    std::vector<u64> idx;
+    idx.reserve(nsurv);
+    for (int t = 0; t < nparts; ++t)
+        for (size_t j = 0; j < parts[(size_t)t].g.size(); ++j) idx.push_back(((u64)t << 40) | (u64)j);
+    const u64 JMASK = ((u64)1 << 40) - 1;
+    if (nsort) {
+        // order.go:119-166: Collate per term, descending flips it.  The reference's sort.Sort leaves ties in no particular
+        // order; here they keep group order (the survivor id is the last sort key), which also makes a partial sort exact.
+        const HValue* kbase[32];
+        for (int t = 0; t < 32; ++t) kbase[t] = parts[(size_t)t].keys.data();
+        auto less = [&](u64 a, u64 b) {
+            const HValue* ka = kbase[a >> 40] + (size_t)(a & JMASK) * nsort;
+            const HValue* kb = kbase[b >> 40] + (size_t)(b & JMASK) * nsort;
+            for (size_t i = 0; i < nsort; ++i) {
+                const int c = collate_values(ka[i], kb[i]);
                 if (c == 0) continue;
                 return order[i].desc ? c > 0 : c < 0;
             }
-            return false;
-        });
-    size_t first = 0, last = rows.size();
-    if (has_offset && offset > 0) first = (size_t)std::min<i64>(offset, (i64)rows.size());  // offset.go:75-83
-    if (has_limit) last = std::min(last, first + (size_t)std::max<i64>(limit, 0));         // limit.go:74-81
-    std::string s = "[";
-    for (size_t i = first; i < last; ++i) {
-        if (i > first) s += ",";
-        s += "{";
-        bool sep = false;
-        for (auto& kv : rows[i].fields) {
-            if (sep) s += ",";
-            sep = true;
-            json::quote(kv.first, s);
-            s += ":";
-            s += value_to_json(kv.second);
-        }
-        s += "}";
+            return a < b;
+        };
+        if (last < nsurv) std::partial_sort(idx.begin(), idx.begin() + (std::ptrdiff_t)last, idx.end(), less);
+        else std::sort(idx.begin(), idx.end(), less);
     }
+    phase("ORDER BY / OFFSET / LIMIT");
+    auto render = [&](i64 i0, i64 i1, std::string& s) {
+        std::vector<HValue> lets;
+        std::vector<std::pair<const std::string*, HValue>> fields;  // the "projection" attachment of one row
+        for (i64 i = i0; i < i1; ++i) {
+            Env env;
+            env.r = &r;
+            const u64 id = idx[first + (size_t)i];
+            env.g = parts[(size_t)(id >> 40)].g[(size_t)(id & JMASK)];
+            eval_lets(env, lets);
+            fields.clear();
+            for (auto& t : terms) {  // project_initial.go:98-117; a MISSING value unsets the field (value/object.go:246-255)
+                HValue v = eval(*t.e, env);
+                size_t at = 0;
+                while (at < fields.size() && *fields[at].first != t.alias) ++at;
+                if (v.cls == C_MISSING) { if (at < fields.size()) fields.erase(fields.begin() + (std::ptrdiff_t)at); continue; }
+                if (at < fields.size()) fields[at].second = std::move(v); else fields.emplace_back(&t.alias, std::move(v));
+            }
+            std::sort(fields.begin(), fields.end(), [](const auto& a, const auto& b) { return *a.first < *b.first; });  // Go marshals maps by sorted name
+            s += i == 0 ? "{" : ",{";
+            for (size_t f = 0; f < fields.size(); ++f) {
+                if (f) s += ",";
+                json::quote(*fields[f].first, s);
+                s += ":";
+                s += value_to_json(fields[f].second);
+            }
+            s += "}";
+        }
+    };
+    std::string s = "[";
+    {
+        std::vector<std::string> chunks(32);
+        const int used = in_threads((i64)(last - first), [&](int t, i64 i0, i64 i1) { render(i0, i1, chunks[(size_t)t]); });
+        for (int t = 0; t < used; ++t) s += chunks[(size_t)t];
+    }
+    phase("projection + JSON");
     if (rows_out) *rows_out = (i64)(last - first);
     return s + "]";
 }
