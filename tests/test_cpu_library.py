@@ -285,3 +285,20 @@ def test_random_expression_trees_compile_for_sm100a():
         except q.Ineligible:
             pass
     assert compiled >= 12
+
+
+def test_fast_count_plan_is_left_alone(tmp_path):
+    """SELECT COUNT(*) FROM ks without WHERE is planned as CountScan + the group operators (golden EXPLAIN:
+    test/filestore/json/default/cases/case_by_id.json:297-366) and must not be touched - there is no PrimaryScan / Fetch
+    to replace."""
+    from util_n1 import write_keyspace
+    write_keyspace(str(tmp_path), "default", "game", keyspaces()["filestore/game"])
+    grp = lambda name: {"#operator": name, "aggregates": ["count(*)"], "group_keys": []}
+    plan = {"#operator": "Sequence", "~children": [
+        {"#operator": "CountScan", "keyspace": "game", "namespace": "default"},
+        {"#operator": "Parallel", "maxParallelism": 1, "~child": {"#operator": "Sequence", "~children": [grp("InitialGroup")]}},
+        grp("IntermediateGroup"), grp("FinalGroup"),
+        {"#operator": "Parallel", "maxParallelism": 1, "~child": {"#operator": "Sequence", "~children": [
+            {"#operator": "InitialProject", "result_terms": [{"as": "c", "expr": "count(*)"}]}, {"#operator": "FinalProject"}]}}]}
+    for tail in (False, True):
+        _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(plan, str(tmp_path), tail=tail))
