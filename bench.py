@@ -382,7 +382,15 @@ def run_reference(args):
     sample = args.cpu_sample
     buf, offs = cref.gen_docs(2, 42, 0, sample)
     K, W = args.steps, max(1, min(args.warmup, 2))
+    t0 = time.perf_counter()
     for _ in range(W):
+        cref.run(buf, offs, ALIAS, WHERE, KEYS, AGGS, threads=cores)
+    rate = sample * W / max(time.perf_counter() - t0, 1e-9)
+    # keep the whole run bounded (~90 s) whatever K the caller asks for: a step is a sample of the same workload
+    fit = int(rate * 90.0 / max(K, 1))
+    if fit < sample:
+        sample = max(50_000, fit)
+        buf, offs = cref.gen_docs(2, 42, 0, sample)
         cref.run(buf, offs, ALIAS, WHERE, KEYS, AGGS, threads=cores)
     t0 = time.perf_counter()
     for _ in range(K):
