@@ -10,6 +10,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import full_size as fs  # noqa: E402
+import workloads as wl  # noqa: E402
 import query_b200 as q  # noqa: E402
 
 KNOBS = ["N1GPU_NO_PACK", "N1GPU_MMCHECK", "N1GPU_CACHE_BLOCK", "N1GPU_MIN_BLOCKS", "N1GPU_CACHE_KB", "N1GPU_NO_CACHE",
@@ -42,8 +43,9 @@ VARIANTS = [
 def main():
     q.init(0)
     n = int(os.environ.get("ROWS", "200000000"))
-    t, words, tensors = fs.config5_table(n)
-    ref = fs.config5_reference(words, tensors)
+    w = wl.Config5(rows=n)
+    t = w.sealed_table()
+    ref = w.reference()
     only = os.environ.get("ONLY")
     if os.environ.get("EXTRA"):  # ad-hoc variants: EXTRA='[["name", {"N1GPU_...": "..."}], ...]' replaces the list
         VARIANTS[:] = [(n_, e_) for n_, e_ in json.loads(os.environ["EXTRA"])]
@@ -53,9 +55,9 @@ def main():
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
-        qq = q.Query(t, "d", "((`d`.`v`) is not missing)", ["(`d`.`k`)"], fs.CONFIG5_AGGS)
+        qq = w.query(t)
         res, scan_ns, wall, ng = fs.timed(qq, reps=5)
-        fs.config5_check(res, words, ref)
+        w.check(res, ref)
         info = qq.info
         gbs = info["scan_bytes_per_row"] * n / scan_ns
         print(json.dumps({"variant": name, "knobs": env, "rows": n, "words": info["words"], "registers": info["registers"], "grid": info["grid"],
