@@ -6,17 +6,23 @@
                                                             Go chain (oracle/oracle_ref.c; the Go reference itself
                                                             cannot be built in this image), all host cores
 
-Workload (config.workload = "config2"): BASELINE.json configs[1] - 10 M flat documents
-{"id","n" int64 U[0,1e6),"f" float64 U[0,1),"type"} per GPU and step,
-  SELECT COUNT(*),COUNT(n),SUM(n),AVG(n),MIN(n),MAX(n),SUM(f) FROM d WHERE n BETWEEN 250000 AND 749999   (50 % selectivity)
-A step = one pass of Filter + InitialGroup/IntermediateGroup/FinalGroup over one 10 M-row batch.
-  value : rows/s with the shredded columns already resident in HBM (4 table copies are rotated so that no step
-          finds its 160 MB of input in the 126 MB L2), timed with CUDA events on the launching stream, max over ranks.
-  e2e   : rows/s through the public API from HOST buffers: JSON documents -> shredder (host threads) -> H2D ->
-          scan -> result on the host, every step.
-  roofline: the scan kernel nq_scan (+ its 1-block partial reduction) - column bytes it must read / its mean
-          CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline: oracle_ref.c (kind "port") on a bounded sample of the same documents, all host cores.
+Headline workload (config.workload = "config5", the north-star 1 B-row GROUP BY, BASELINE.json configs[4]):
+  1 B documents {"k": Zipf(s=1.1) string over a 100 k vocabulary, "v": int64 U[-1e3,1e6)}, 10 % of k and of v MISSING
+  and 10 % null;  SELECT k,COUNT(*),COUNT(v),SUM(v),MIN(v),MAX(v) FROM d WHERE v IS NOT MISSING GROUP BY k
+  STRONG scaling: the same 1 B-row keyspace is range-partitioned over the N ranks (tools/workloads.py generates the
+  shredded columns on the device, chunk-seeded, so the data does not depend on N).
+A step = one pass of the whole chain over the whole keyspace: every rank's scan of its row range, the
+Intermediate -> Final merge across ranks, and the finalisation of all groups into host result arrays.
+  value : rows/s, columns resident in HBM (14 GB / N per GPU, far beyond the 126 MB L2), K steps between two CUDA
+          events on the launching stream, max over ranks; the merged result is checked in the run at every N against
+          torch reductions over the same data (exact).
+  e2e   : the same chain through the public API from HOST buffers every step: raw JSON documents of the same shape in
+          pinned host memory -> H2D -> device shredder -> seal -> compile (cached) -> scan -> merge -> result on the host.
+  roofline : the scan kernel nq_scan - column bytes it must read / its mean CUDA-event duration over the timed steps,
+          against MEASURED_PEAKS.json hbm_gbs.
+  configs : the other BASELINE configs at full size (2: 10 M ungrouped, 3: 60 M TPC-H Q1, 4: 200 M rows / 1 M groups with
+          COUNT+SUM DISTINCT), sharded over the same ranks, each with scan time, rows/s, roofline fraction and check.
+  cpu_baseline : oracle_ref.c (kind "port") on a bounded sample of config-5 documents, all host cores (N = 1 only).
 """
 from __future__ import annotations
 
@@ -31,24 +37,30 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-ROWS = 10_000_000
+# the config-5 chain in the reference's serialised form (Stringer text, as plan JSON carries it)
 ALIAS = "d"
-WHERE = "((`d`.`n`) between 250000 and 749999)"
-AGGS = ["count(*)", "count((`d`.`n`))", "sum((`d`.`n`))", "avg((`d`.`n`))", "min((`d`.`n`))", "max((`d`.`n`))", "sum((`d`.`f`))"]
-KEYS = []
+WHERE = "((`d`.`v`) is not missing)"
+KEYS = ["(`d`.`k`)"]
+AGGS = ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))"]
 METRIC = "filter+GROUP BY rows/sec (columns resident in HBM)"
 UNIT = "rows/s"
-CONFIG = {"workload": "config2", "rows_per_gpu_per_step": ROWS, "query": "SELECT COUNT(*),COUNT(n),SUM(n),AVG(n),MIN(n),MAX(n),SUM(f) "
-          "FROM d WHERE n BETWEEN 250000 AND 749999", "selectivity": 0.5, "partitioning": "row ranges, one per GPU", "pipelining": "independent steps overlap on 4 CUDA streams",
-          "l2": "4 rotating table copies per GPU (640 MB) > 126 MB L2"}
+ROWS = 1_000_000_000
+# identical in both arms (the reference arm states its per-step sample under cpu_baseline.sample)
+CONFIG = {"workload": "config5", "rows": ROWS,
+          "query": "SELECT k,COUNT(*),COUNT(v),SUM(v),MIN(v),MAX(v) FROM d WHERE v IS NOT MISSING GROUP BY k",
+          "documents": "k: Zipf(s=1.1) string over a 100k vocabulary, v: int64 U[-1e3,1e6); 10% MISSING + 10% null on each, independently",
+          "groups": 100002, "partitioning": "contiguous row ranges of one keyspace, one per GPU (strong scaling)",
+          "step": "scan of every row range + Intermediate->Final merge across ranks + finalisation of all groups to host arrays",
+          "l2": "inputs larger than L2: 14 GB of columns / N per GPU vs 126 MB"}
 
 
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
 
@@ -102,14 +114,40 @@ class ClockSampler:
         return out
 
 
-def synth_columns(seed):
+def gen_docs_parallel(cref, config, seed, first, n, threads=8):
+    """documents [first, first + n) of a config from the C generator, on several host threads (deterministic per row)"""
     import numpy as np
-    rng = np.random.default_rng(seed)
-    n = rng.integers(0, 1_000_000, ROWS, dtype=np.int64)
-    n[0], n[1] = 0, 999_999  # identical column statistics for every copy -> one compiled kernel serves them all
-    f = rng.integers(0, 1_000_000, ROWS).astype(np.float64) / 1e6
-    f[f == 0.0] = 0.5        # keep the column purely float64 (an integral value would be an int: value.NewValue)
-    return n, f
+    parts = [None] * threads
+    bounds = [first + n * i // threads for i in range(threads + 1)]
+
+    def work(i):
+        parts[i] = cref.gen_docs(config, seed, bounds[i], bounds[i + 1] - bounds[i])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    total = sum(int(o[-1]) for _b, o in parts)
+    buf = np.empty(total + 1, dtype=np.uint8)
+    offs = np.empty(n + 1, dtype=np.int64)
+    at, row = 0, 0
+    for b, o in parts:
+        m = len(o) - 1
+        buf[at:at + int(o[-1])] = b[: int(o[-1])]
+        offs[row:row + m] = o[:-1] + at
+        at += int(o[-1])
+        row += m
+    offs[n] = at
+    buf[at] = 0
+    return buf, offs
+
+
+def same_value(a, b, tol=1e-12):
+    """bit-exact, the int / float class of a value included; float64 sums within the north-star tolerance"""
+    if isinstance(a, float) and isinstance(b, float):
+        return a == b or abs(a - b) <= tol * max(abs(a), abs(b))
+    return type(a) is type(b) and a == b
 
 
 def run_ours(args):
@@ -117,280 +155,346 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import query_b200 as q
+    import workloads as wl
     from query_b200 import dist as qd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     q.init(local)
-    K, W = args.steps, max(args.warmup, 3)
+    K, W = max(1, args.steps), max(args.warmup, 3)
+    peak, peak_src = peaks()
+    trace = bool(os.environ.get("N1GPU_TRACE"))
 
-    # ---- resident columns: NT rotating copies ------------------------------------------------------------------
-    NT = 4
-    tables = []
-    for c in range(NT):
-        n, f = synth_columns(1000 * rank + c + 1)
-        t = q.Table(["n", "f"])
-        t.set_column("n", n)
-        t.set_column("f", f, tags=np.full(ROWS, 5, dtype=np.uint8))
-        t.seal()
-        tables.append(t)
-    NQ = 8
-    NS = args.streams  # scans of independent batches overlap on NS CUDA streams (tails hide behind the next scan)
-    side = [torch.cuda.Stream() for _ in range(NS)]
-    queries = []
-    for i in range(NQ):
-        qq = q.Query(tables[i % NT], ALIAS, WHERE, KEYS, AGGS)
-        qq.set_stream(side[i % NS].cuda_stream)
-        qq.set_timing(False)  # the timed region is bracketed by our own events; per-launch events only cost front-end time
-        queries.append(qq)
-    # N > 1: the Intermediate->Final merge is fused into the scan kernel (peer stores over NVLink into every rank's
-    # mailbox + a 1-block fold); --merge nccl switches to the NCCL all_gather of the accumulator words instead
-    mailbox = qd.make_mailbox(max_words=1024) if (world > 1 and args.merge == "fused") else None
-    dqs = [qd.DistributedQuery(qq, stream=side[i % NS], mailbox=mailbox) for i, qq in enumerate(queries)]
-    info = queries[0].info
+    def log(msg):
+        if trace and rank == 0:
+            sys.stderr.write("[bench] %s\n" % msg)
+
+    def maxrank(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed_steps(step, k):
+        """k steps between two CUDA events on the current stream, barrier + synchronize on both sides; max over ranks (ms)"""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for _ in range(k):
+            res = step()
+        ev1.record()
+        sync_all()
+        return maxrank(ev0.elapsed_time(ev1)), res
+
+    def make(w):
+        """table + compiled chain + distributed wrapper of a workload, on torch's current stream"""
+        t = w.sealed_table()
+        qq = w.query(t)
+        qq.set_stream(torch.cuda.current_stream().cuda_stream)
+        qq.set_timing(True)
+        return t, qq, qd.DistributedQuery(qq)
+
+    def checked(w, dq, res):
+        ref = w.reference()
+        how = w.check(res, ref)
+        if world > 1 and not dq.replicated:
+            w.check_partition(res, ref["cnt"] > 0)
+            how += "; every group finalised by exactly one of the %d ranks" % world
+        elif world > 1:
+            how += "; merged result replicated on every rank, each rank checked its copy"
+        return how
+
+    # ---- headline: config 5, the whole keyspace over the ranks ----------------------------------------------------------
+    t_setup = time.perf_counter()
+    w5 = wl.Config5(rows=args.rows, dev=dev)
+    assert (w5.alias, w5.where, list(w5.keys), list(w5.aggs)) == (ALIAS, WHERE, KEYS, AGGS)
+    t5, q5, dq5 = make(w5)
+    info = q5.info
     bytes_per_row = info["scan_bytes_per_row"]
+    log("config5 table of %d rows on this rank in %.1f s" % (w5.n, time.perf_counter() - t_setup))
 
-    def step_sync(i):
-        """one step, blocking (used for warm-up and for N > 1 where every step ends in the merge exchange)"""
-        return dqs[i % NQ].execute()
+    def step5():
+        res = dq5.execute()
+        res.num_groups  # the groups are finalised and on the host
+        return res
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for i in range(W):
-        r = step_sync(i)
-    # soak: keep scanning for ~1 s (untimed warm-up) so that clocks are ramped and nvidia-smi has samples under load
-    t_soak = time.perf_counter()
-    soak_steps = 0
+    for _ in range(W):
+        res = step5()
+    # soak: keep stepping (untimed, under its own key) so that clocks are ramped and nvidia-smi has samples under load
+    soak_steps, t_soak = 0, time.perf_counter()
     while args.soak > 0:
-        for _ in range(50):
-            r = step_sync(soak_steps)
+        for _ in range(5):
+            res = step5()
             soak_steps += 1
         done = time.perf_counter() - t_soak >= args.soak
         if world > 1:  # every rank must run the same number of (collective) steps: rank 0 decides
-            flag = torch.tensor([1 if done else 0], device="cuda")
+            flag = torch.tensor([1 if done else 0], device=dev)
             dist.broadcast(flag, 0)
             done = bool(flag.item())
         if done:
             break
-    W += soak_steps
-    check_rows = r.rows() if rank == 0 else None
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     launches0 = q.launch_count()
     scan_ns = []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    main = torch.cuda.current_stream()
-    ev0.record(main)
-    for s_ in side:
-        s_.wait_event(ev0)   # device-side bracket: no scan starts before ev0 ...
-    # pipelined: up to NQ steps in flight over the streams; results are collected in order.  For N > 1 a step is
-    # scan -> all_gather of the accumulator words (NCCL, stream-ordered) -> merge kernel: no host round trip.
-    inflight = []
-    for s in range(K):
-        h = s % NQ
-        if len(inflight) == NQ:
-            j = inflight.pop(0)
-            dqs[j].collect()
-            scan_ns.append(queries[j].last_scan_ns)
-        dqs[h].launch()
-        inflight.append(h)
-    for j in inflight:
-        dqs[j].collect()
-        scan_ns.append(queries[j].last_scan_ns)
-    for s_ in side:
-        main.wait_stream(s_)  # ... and ev1 is recorded after every stream drained
-    ev1.record(main)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
+
+    def step5_timed():
+        r = step5()
+        scan_ns.append(q5.last_scan_ns)
+        return r
+
+    ms, res = timed_steps(step5_timed, K)
     launches = q.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    value = w5.rows * K / (ms / 1e3)
+    mean_scan_ns = maxrank(sum(scan_ns) / len(scan_ns))
+    check5 = checked(w5, dq5, res)
+    merge5 = dq5.describe()
+    groups5 = res.num_groups
     if world > 1:
-        tms = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    value = world * ROWS * K / (ms / 1e3)
+        g = torch.tensor([0 if dq5.replicated and rank else groups5], device=dev)
+        dist.all_reduce(g)
+        groups5 = int(g.item())
+    log("config5: %.3f ms/step, scan %.3f ms" % (ms / K, mean_scan_ns / 1e6))
 
-    # the dominant kernel alone: serialised steps on one stream, CUDA events around the nq_scan launch itself
-    # (launches are queued NQ deep on ONE stream so that the events bracket the kernel, not the launch latency
-    # of an idle queue; the kernels themselves run strictly one after another)
-    # NK independent query handles are launched back to back on ONE stream with no per-launch events (an event
-    # record costs the GPU front-end several microseconds - a tiny kernel between two events measures 8-10 us on
-    # this system); two events bracket the whole run, the kernels execute strictly one after another, and the
-    # average launch duration is elapsed / launches.  Tables rotate, so no launch finds its input in L2.
-    # Measured twice: as shipped (ungrouped scans are launched with programmatic stream serialization, so the
-    # ramp-up of launch i+1 fills the SMs that launch i's tail has left idle), and with N1GPU_NO_PDL=1 (every launch
-    # waits for the full completion of the one before: the fixed launch/ramp/tail cost shows up in every launch).
-    NK = 32
-    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- the other configs at full size, sharded over the same ranks ----------------------------------------------------------
+    configs = {"config5": {"rows": w5.rows, "rows_per_gpu": w5.n, "mode": info["mode"], "scan_us": mean_scan_ns / 1e3, "step_ms": ms / K,
+                           "rows_per_s": value, "scan_bytes_per_row": bytes_per_row,
+                           "roofline_frac": bytes_per_row * w5.n / mean_scan_ns / peak, "groups": groups5, "check": check5}}
+    del dq5, q5, t5, res
+    torch.cuda.empty_cache()
+    for name in [c for c in args.configs.split(",") if c]:
+        t0 = time.perf_counter()
+        w = wl.CONFIGS[name](dev=dev, scale=args.configs_scale)
+        t, qq, dq = make(w)
+        r = dq.execute()
+        r.num_groups
+        sns = []
 
-    def kernel_alone():
-        kq = []
-        for i in range(NK):
-            qq = q.Query(tables[i % NT], ALIAS, WHERE, KEYS, AGGS)
-            qq.set_stream(side[0].cuda_stream)
-            qq.set_timing(False)
-            kq.append(qq)
-        for qq in kq:
-            qq.execute()
-        out = []
-        for rep in range(5):
-            torch.cuda.synchronize()
-            ka.record(side[0])
-            for qq in kq:
-                qq.launch()
-            kb.record(side[0])
-            for qq in kq:
-                qq.collect()
-            torch.cuda.synchronize()
-            out.append(ka.elapsed_time(kb) * 1e6 / NK)
-        return out
+        def step():
+            rr = dq.execute()
+            rr.num_groups
+            sns.append(qq.last_scan_ns)
+            return rr
 
-    scan_ns = kernel_alone()
-    os.environ["N1GPU_NO_PDL"] = "1"
-    try:
-        serial_ns = kernel_alone()
-    finally:
-        del os.environ["N1GPU_NO_PDL"]
+        for _ in range(2):
+            step()
+        sns.clear()
+        cms, r = timed_steps(step, args.configs_steps)
+        cscan = maxrank(sum(sns) / len(sns))
+        inf = qq.info
+        entry = {"rows": w.rows, "rows_per_gpu": w.n, "mode": inf["mode"], "scan_us": cscan / 1e3, "step_ms": cms / args.configs_steps,
+                 "rows_per_s": w.rows * args.configs_steps / (cms / 1e3), "scan_rows_per_s": w.rows / (cscan * 1e-9),
+                 "scan_bytes_per_row": inf["scan_bytes_per_row"], "survey_bytes_per_row": w.survey_bytes_per_row,
+                 "roofline_frac": inf["scan_bytes_per_row"] * w.n / cscan / peak, "query": w.sql, "check": checked(w, dq, r)}
+        if name == "config2":
+            # a 26 us kernel between two events mostly measures the events: 32 launches back to back, elapsed / 32
+            entry["scan_us_back_to_back"] = kernel_back_to_back(q, torch, w, t, 32)
+            entry["roofline_frac_back_to_back"] = inf["scan_bytes_per_row"] * w.n / (entry["scan_us_back_to_back"] * 1e3) / peak
+        groups = r.num_groups
+        if world > 1:
+            g = torch.tensor([0 if dq.replicated and rank else groups], device=dev)
+            dist.all_reduce(g)
+            groups = int(g.item())
+        entry["groups"] = groups
+        configs[name] = entry
+        log("%s: %.3f ms/step, scan %.3f ms (%.1f s with setup and check)" % (name, entry["step_ms"], cscan / 1e6, time.perf_counter() - t0))
+        del dq, qq, t, r, w
+        torch.cuda.empty_cache()
 
-    # ---- end to end from host JSON ---------------------------------------------------------------------------------
+    # ---- end to end from host JSON, config-5 shaped documents ---------------------------------------------------------------------
     from oracle import cref  # document generator + CPU baseline only (never the measured path of this arm)
-    e2e_rows = args.e2e_rows
-    buf, offs = cref.gen_docs(2, 42 + rank, rank * e2e_rows, e2e_rows)
+    e2e_total = args.e2e_rows
+    lo, hi = qd.row_range(e2e_total, rank, world)
+    buf, offs = gen_docs_parallel(cref, 5, 42, lo, hi - lo)
     pinned = torch.from_numpy(buf).pin_memory()   # the step's inputs live in pinned host memory
     hbuf = pinned.numpy()
     pinned_offs = torch.from_numpy(offs).pin_memory()
     hoffs = pinned_offs.numpy()
     e2e_steps = max(1, min(args.e2e_steps, K))
-
-    trace = bool(os.environ.get("N1GPU_TRACE"))
+    phases = []
 
     def e2e_step():
         ts = [time.perf_counter()]
-        t = q.Table(["n", "f"])
+        t = q.Table(["k", "v"])
         t.append_json((hbuf, hoffs), threads=args.shred_threads)
         ts.append(time.perf_counter())
+        if world > 1:
+            qd.agree_dictionaries_and_stats(t)
+        else:
+            t.set_global_rows(t.num_rows)
         t.seal()
         qq = q.Query(t, ALIAS, WHERE, KEYS, AGGS)
         ts.append(time.perf_counter())
-        res = qd.DistributedQuery(qq, mailbox=mailbox).execute()
-        rows = res.rows()
+        dq = qd.DistributedQuery(qq)
+        r = dq.execute()
+        ng = r.num_groups
         ts.append(time.perf_counter())
-        if trace:
-            sys.stderr.write("[bench e2e] shred %.2f ms, seal+compile %.2f ms, scan+result %.2f ms\n" % tuple(
-                (b - a) * 1e3 for a, b in zip(ts, ts[1:])))
-        if args.shred_threads < 0:
-            h2d = int(hoffs[-1]) + 8 * (e2e_rows + 1)          # raw JSON + document offsets
-        else:
-            h2d = sum(t.scan_bytes(c) for c in ("n", "f")) * e2e_rows  # shredded columns
-        d2h = info["words"] * 8
-        return rows, h2d, d2h
+        phases.append([(b - a) * 1e3 for a, b in zip(ts, ts[1:])])
+        return r, ng, dq.replicated
 
-    rows_e2e, h2d, d2h = e2e_step()  # warm-up (JIT cache, allocator)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    r_e2e, ng_e2e, rep_e2e = e2e_step()  # warm-up (JIT cache, allocator)
+    phases.clear()
+    sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        rows_e2e, h2d, d2h = e2e_step()
-    torch.cuda.synchronize()
+        r_e2e, ng_e2e, rep_e2e = e2e_step()
+    sync_all()
+    e2e_s = maxrank(time.perf_counter() - t0)
+    e2e_value = e2e_total * e2e_steps / e2e_s
+    h2d = int(hoffs[-1]) + 8 * (len(hoffs))                       # raw JSON + document offsets of this rank
+    d2h = ng_e2e * (1 + len(w5.aggs)) * 9                         # class byte + 8-byte payload per key / aggregate value
+    ph = [sum(p[i] for p in phases) / len(phases) for i in range(3)]
     if world > 1:
-        dist.barrier()
-    e2e_s = time.perf_counter() - t0
+        tt = torch.tensor([float(h2d), float(d2h)] + ph, device=dev, dtype=torch.float64)
+        mx = tt.clone()
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        h2d, d2h = int(tt[0].item()), int(tt[1].item())
+        ph = [float(x) for x in mx[2:].tolist()]
+    # parity of the e2e result against the CPU restatement over the very same documents (rank 0 regenerates all of them)
+    mine = [(k[0] if k[0] is not q.MISSING else "\0MISSING", a) for k, a in r_e2e.rows()]
     if world > 1:
-        ts = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        e2e_s = float(ts.item())
-    e2e_value = world * e2e_rows * e2e_steps / e2e_s
+        allrows = [None] * world
+        dist.gather_object(mine, allrows if rank == 0 else None, dst=0)
+        if rank == 0:
+            merged = {}
+            for i, part in enumerate(allrows):
+                if rep_e2e and i:
+                    continue  # a replicated merge leaves the complete result on every rank
+                for k, a in part:
+                    assert k not in merged, "group %r finalised by two ranks" % (k,)
+                    merged[k] = a
+    else:
+        merged = dict(mine)
+    parity = None
+    cpu = None
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        if world > 1:
+            buf_all, offs_all = gen_docs_parallel(cref, 5, 42, 0, e2e_total)
+        else:
+            buf_all, offs_all = buf, offs
+        groups, cpu_s, _passed = cref.run(buf_all, offs_all, ALIAS, WHERE, KEYS, AGGS, threads=cores)
+        from oracle import n1ql_oracle as O
+        exp = {(k[0] if k[0] is not O.MISSING else "\0MISSING"): a for k, a in groups}
+        bad = [k for k in exp if k not in merged or not all(same_value(x, y) for x, y in zip(exp[k], merged[k]))]
+        parity = "ok: %d groups of the e2e result equal oracle_ref.c over the same %d documents" % (len(exp), e2e_total) \
+            if not bad and len(exp) == len(merged) else "MISMATCH %d groups, e.g. %r: %r vs %r" % (len(bad), bad[:1], [exp[k] for k in bad[:1]], [merged.get(k) for k in bad[:1]])
+        if world == 1:
+            sample = min(args.cpu_sample, e2e_total)
+            sbuf, soffs = (buf_all, offs_all) if sample == e2e_total else gen_docs_parallel(cref, 5, 42, 0, sample)
+            if sample != e2e_total:
+                groups, cpu_s, _passed = cref.run(sbuf, soffs, ALIAS, WHERE, KEYS, AGGS, threads=cores)
+            cpu = {"value": sample / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d config5-shaped JSON documents, oracle/oracle_ref.c (reference-shaped C restatement of the Go chain), %d threads" % (sample, cores)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ----------------------------------------------------------------------------
-    peak, peak_src = peaks()
-    mean_ns = sum(scan_ns) / max(1, len(scan_ns))
-    achieved = bytes_per_row * ROWS / mean_ns  # bytes/ns == GB/s
-    traffic = None
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------------------------------
+    achieved = bytes_per_row * w5.n / mean_scan_ns  # bytes/ns == GB/s
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("nq_scan_config2_dram_bytes_per_launch")
+            tj = json.load(f)
+        per_row = tj.get("nq_scan_config5_dram_bytes_per_row")
+        if per_row:
+            traffic = per_row * w5.n
+            traffic_src = "static: %s (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per row, scaled to this launch)" % tj.get("nq_scan_config5_source")
     except Exception:
         pass
-
-    # ---- CPU baseline on a bounded sample, and a parity check of the e2e result against it ---------------------------
-    cores = os.cpu_count() or 1
-    sample = min(args.cpu_sample, e2e_rows)
-    sbuf, soffs = cref.gen_docs(2, 42, 0, sample)
-    groups, cpu_s, _passed = cref.run(sbuf, soffs, ALIAS, WHERE, KEYS, AGGS, threads=cores)
-    parity = "skipped"
-    if world == 1:
-        full, _s, _p = cref.run(buf, offs, ALIAS, WHERE, KEYS, AGGS, threads=cores)
-        exp, got = full[0][1], rows_e2e[0][1]
-        ok = all((abs(a - b) <= 1e-12 * max(abs(a), abs(b))) if isinstance(a, float) or isinstance(b, float) else a == b
-                 for a, b in zip(exp, got))
-        parity = "ok" if ok else "MISMATCH %r vs %r" % (exp, got)
-
+    merge = "none (one rank)" if world == 1 else merge5
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int64+f64", "data": "synthetic", "config": dict(CONFIG, kernel_mode=info["mode"], registers=info["registers"],
-                                                                   grid=info["grid"], scan_bytes_per_row=bytes_per_row,
-                                                                   survey_bytes_per_row=18, merge=("none" if world == 1 else "fused into nq_scan: peer stores over NVLink into every rank's mailbox + 1-block fold"
-                                                                          if args.merge == "fused" else "NCCL all_gather of the accumulator words + merge kernel, stream-ordered")),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "warmup_run": W, "soak_steps": soak_steps,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int64 (u32 dictionary ranks, u8 classes)", "data": "synthetic", "config": CONFIG,
+        "result_check": check5, "groups": groups5,
+        "kernel": {"mode": info["mode"], "registers": info["registers"], "grid": info["grid"], "block": info["block"],
+                   "scan_bytes_per_row": bytes_per_row, "survey_bytes_per_row": 14, "rows_per_launch": w5.n, "merge": merge},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "rows_per_step": e2e_rows, "includes": ("H2D of the raw JSON + device shredder (shred.cu) + scan + result on the host" if args.shred_threads < 0
-                             else "JSON shredding on host threads + column H2D + scan + result on the host"),
-                "json_bytes_per_step": int(offs[-1])},
+                "rows_per_step": e2e_total, "json_bytes_per_step": h2d - 8 * (e2e_total + world),
+                "includes": ("H2D of the raw JSON from pinned host memory + device shredder (shred.cu)" if args.shred_threads < 0 else "JSON shredding on host threads + column H2D")
+                + " + dictionary / statistics agreement across ranks + seal + compile (cached) + scan + merge + finalisation to host arrays",
+                "phase_ms_max_over_ranks": {"shred": ph[0], "agree+seal+compile": ph[1], "scan+merge+finalize": ph[2]},
+                "parity_vs_cpu_baseline": parity},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "nq_scan (filter + aggregation + fused final reduction), timed alone", "peak_source": peak_src, "mean_kernel_us": mean_ns / 1e3,
-                     "timing": "32 launches back to back on one stream between two CUDA events, elapsed / 32, 5 repetitions; launches use programmatic stream serialization (PDL)",
-                     "serialized_kernel_us": sum(serial_ns) / len(serial_ns) / 1e3,
-                     "frac_serialized": bytes_per_row * ROWS / (sum(serial_ns) / len(serial_ns)) / peak,
-                     "algorithmic_bytes_per_launch": bytes_per_row * ROWS},
-        "cpu_baseline": {"value": sample / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d of the same config2 documents, oracle/oracle_ref.c (reference-shaped C restatement), %d threads" % (sample, cores)},
-        "parity_vs_cpu_baseline": parity,
-        "result_check": check_rows[0][1] if check_rows else None,
+                     "traffic_source": traffic_src, "kernel": "nq_scan (filter + group key + hash aggregation of config 5)", "peak_source": peak_src,
+                     "mean_kernel_us": mean_scan_ns / 1e3, "algorithmic_bytes_per_launch": bytes_per_row * w5.n,
+                     "timing": "CUDA events around the nq_scan launch on its stream, mean over the %d timed steps, max over ranks" % K,
+                     "accumulator_updates_per_s": None},
+        "cpu_baseline": cpu,
+        "configs": configs,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def kernel_back_to_back(q, torch, w, table, nk):
+    """mean duration (us) of nk launches of the scan queued back to back on one stream between two CUDA events"""
+    s = torch.cuda.Stream()
+    kq = []
+    for _ in range(nk):
+        qq = w.query(table)
+        qq.set_stream(s.cuda_stream)
+        qq.set_timing(False)
+        kq.append(qq)
+    for qq in kq:
+        qq.execute()
+    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        ka.record(s)
+        for qq in kq:
+            qq.launch()
+        kb.record(s)
+        for qq in kq:
+            qq.collect()
+        torch.cuda.synchronize()
+        best.append(ka.elapsed_time(kb) * 1e3 / nk)
+    return sorted(best)[len(best) // 2]
+
+
 def run_reference(args):
     """The CPU arm: the reference's own algorithm for the path (document-at-a-time interpreter over raw JSON, string
-    group keys, 3-phase merge) restated in C because Go is not in this image; all host threads; bounded sample/step."""
+    group keys, 3-phase merge) restated in C because Go is not in this image; all host threads; each step a bounded
+    sample of the same workload (config-5 shaped documents), sized so that the whole run ends within ~90 s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import cref
     cores = os.cpu_count() or 1
+    K, W = max(1, args.steps), max(1, args.warmup)
     sample = args.cpu_sample
-    buf, offs = cref.gen_docs(2, 42, 0, sample)
-    K, W = args.steps, max(1, min(args.warmup, 2))
+    buf, offs = gen_docs_parallel(cref, 5, 42, 0, sample)
     t0 = time.perf_counter()
-    for _ in range(W):
-        cref.run(buf, offs, ALIAS, WHERE, KEYS, AGGS, threads=cores)
-    rate = sample * W / max(time.perf_counter() - t0, 1e-9)
-    # keep the whole run bounded (~90 s) whatever K the caller asks for: a step is a sample of the same workload
-    fit = int(rate * 90.0 / max(K, 1))
+    cref.run(buf, offs, ALIAS, WHERE, KEYS, AGGS, threads=cores)
+    rate = sample / max(time.perf_counter() - t0, 1e-9)
+    fit = int(rate * 90.0 / max(K + W, 1))
     if fit < sample:
         sample = max(50_000, fit)
-        buf, offs = cref.gen_docs(2, 42, 0, sample)
+        buf, offs = gen_docs_parallel(cref, 5, 42, 0, sample)
+    for _ in range(W):
         cref.run(buf, offs, ALIAS, WHERE, KEYS, AGGS, threads=cores)
     t0 = time.perf_counter()
     for _ in range(K):
@@ -398,13 +502,14 @@ def run_reference(args):
     el = time.perf_counter() - t0
     value = sample * K / el
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-        "ms_per_step": el / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
-        "data": "synthetic", "config": dict(CONFIG, rows_per_step=sample),
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+        "ms_per_step": el / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int64 (u32 dictionary ranks, u8 classes)", "data": "synthetic", "config": CONFIG,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d config2 documents per step, oracle/oracle_ref.c with %d threads (Go reference not buildable here)" % (sample, cores)},
+                         "sample": "%d config5-shaped JSON documents per step (a bounded sample of the 1 B-document workload), oracle/oracle_ref.c with %d threads "
+                                   "(the Go reference is not buildable here)" % (sample, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "result_check": groups[0][1],
+        "groups": len(groups),
     }
     print(json.dumps(line))
 
@@ -412,16 +517,18 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-rows", type=int, default=ROWS)
+    ap.add_argument("--rows", type=int, default=ROWS, help="documents of the config-5 keyspace (all ranks together)")
+    ap.add_argument("--configs", default="config2,config3,config4", help="other BASELINE configs reported in the `configs` block")
+    ap.add_argument("--configs-scale", type=float, default=1.0)
+    ap.add_argument("--configs-steps", type=int, default=5)
+    ap.add_argument("--e2e-rows", type=int, default=16_000_000, help="config-5 shaped JSON documents per e2e step (all ranks together)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=16_000_000)
     ap.add_argument("--shred-threads", type=int, default=-1, help="-1: device shredder (shred.cu); >= 0: host threads (0 = all cores)")
-    ap.add_argument("--merge", default="fused", choices=["fused", "nccl"], help="N > 1: how the per-step partial states are merged")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the resident-column steps are pipelined over")
-    ap.add_argument("--soak", type=float, default=1.0, help="seconds of untimed scanning before the timed region")
+    ap.add_argument("--soak", type=float, default=1.0, help="seconds of untimed stepping before the timed region")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that print banners to fd 1 (NCCL's version line) are sent to
     # stderr for the duration of the run, and the JSON line goes to the real stdout at the end.

@@ -676,6 +676,15 @@ void oracle_free(char* p) { free(p); }
 /* ---- synthetic documents of the BASELINE.json configs (deterministic per (seed, row), thread-count independent) ----------- */
 static unsigned long long splitmix(unsigned long long x) { x += 0x9e3779b97f4a7c15ULL; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL; x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL; return x ^ (x >> 31); }
 typedef struct { int config; long long first, lo, hi; unsigned long long seed; char* buf; long long* offs; long long base; } GenJob;
+#define ZIPF_VOCAB 100000
+static double zipf_cdf[ZIPF_VOCAB];
+static pthread_once_t zipf_once = PTHREAD_ONCE_INIT;
+static void zipf_init(void) {
+    double tot = 0, acc = 0;
+    for (int i = 0; i < ZIPF_VOCAB; ++i) tot += pow((double)(i + 1), -1.1);
+    for (int i = 0; i < ZIPF_VOCAB; ++i) { acc += pow((double)(i + 1), -1.1) / tot; zipf_cdf[i] = acc; }
+    zipf_cdf[ZIPF_VOCAB - 1] = 1.0;
+}
 static int gen_doc(int config, unsigned long long seed, long long row, char* out) {
     unsigned long long r1 = splitmix(seed ^ (unsigned long long)row * 0x2545F4914F6CDD1DULL), r2 = splitmix(r1), r3 = splitmix(r2), r4 = splitmix(r3);
     if (config == 2)  /* {"id":i,"n":U[0,1e6),"f":U[0,1) 6 decimals,"type":"t0..15"} */
@@ -690,10 +699,14 @@ static int gen_doc(int config, unsigned long long seed, long long row, char* out
     }
     if (config == 4)  /* {"g":U[0,1e6),"x":U[0,1000),"y":float} */
         return sprintf(out, "{\"g\":%llu,\"x\":%llu,\"y\":%llu.%03llu}", r1 % 1000000ULL, r2 % 1000ULL, r3 % 1000ULL, r4 % 1000ULL);
-    /* config 5: Zipf-ish string key over a 100k vocabulary, 10% MISSING + 10% null on k and v */
+    /* config 5: Zipf(s = 1.1) string key over a 100k vocabulary (inverse CDF, as tools/workloads.py generates the device
+       columns), 10% MISSING + 10% null on k and v */
     {
         double u = (double)(r1 >> 11) / 9007199254740992.0;
-        unsigned long long w = (unsigned long long)(pow(100000.0, u)) - 1;  /* log-uniform rank ~ Zipf(s=1) */
+        pthread_once(&zipf_once, zipf_init);
+        int zlo = 0, zhi = ZIPF_VOCAB - 1;  /* first rank whose cumulative probability reaches u */
+        while (zlo < zhi) { int mid = (zlo + zhi) >> 1; if (zipf_cdf[mid] >= u) zhi = mid; else zlo = mid + 1; }
+        unsigned long long w = (unsigned long long)zlo;
         char k[64], v[64];
         unsigned long long mk = r2 % 10ULL, mv = r3 % 10ULL;
         if (mk == 0) k[0] = 0; else if (mk == 1) sprintf(k, "\"k\":null,"); else sprintf(k, "\"k\":\"w%06llu-%llx\",", w, splitmix(w) & 0xffffffULL);

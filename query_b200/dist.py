@@ -163,6 +163,23 @@ class DistributedQuery:
         self._runs = None
         self._launched = False
 
+    @property
+    def replicated(self):
+        """True when the merge leaves the complete result on EVERY rank (small state: element-wise merge), False when every
+        group is finalised by exactly one owner rank (or there is one rank)."""
+        return world() > 1 and self.small
+
+    def describe(self):
+        if world() == 1:
+            return "none (one rank)"
+        if self.fused:
+            return "fused into nq_scan: peer stores over NVLink into every rank's mailbox + 1-block fold"
+        if self.small and self.q.info["mode"] == "hbm-direct":
+            return "in-place NCCL all-reduce of the direct-indexed table, one call per run of sum / min / max words, stream-ordered; replicated finalisation"
+        if self.small:
+            return "NCCL all_gather of the accumulator words + merge kernel, stream-ordered"
+        return "owner-bucketed record / DISTINCT-entry export + NCCL all_to_all + merge kernel; every owner finalises its groups"
+
     def launch(self):
         q = self.q
         w = world()
@@ -222,10 +239,10 @@ class DistributedQuery:
     def _buffers(self, ng, nd, rw):
         need = max(1, ng) * rw
         if self._recs is None or self._recs.numel() < need:
-            self._recs = torch.zeros(need, dtype=torch.int64, device="cuda")
+            self._recs = torch.empty(need, dtype=torch.int64, device="cuda")  # no fill: nothing here may race the export kernels
         need = max(1, nd) * 2
         if self._dents is None or self._dents.numel() < need:
-            self._dents = torch.zeros(need, dtype=torch.int64, device="cuda")
+            self._dents = torch.empty(need, dtype=torch.int64, device="cuda")
 
     def execute(self):
         """Returns a Result holding this rank's share of the groups (small state: rank 0 holds all, others none)."""
