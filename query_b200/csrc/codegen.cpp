@@ -254,8 +254,50 @@ PackComp make_comp(const Table& t, const Expr& e, const char* what) {
     return pc;
 }
 
-// Emits code packing Val `v` as component pc into (lo,hi,pos) variables.
-void emit_pack(Gen& g, const PackComp& pc, const std::string& v, const char* lo, const char* hi, const char* pos) {
+// number of distinct packed values of a component (0: too many to matter)
+u64 comp_values(const Table& t, const PackComp& pc) {
+    if (pc.bits() > 20) return 0;
+    if (pc.nfree >= 0) return (u64)pc.nfree + pc.range;
+    if (pc.cbits == 0 && pc.classes.size() == 1) {
+        if (pc.classes[0] == C_STRING) return (u64)std::max<i64>(1, t.cols[pc.dict_col].stats.ndict);
+        if (pc.classes[0] != C_INT && pc.classes[0] != C_FLOAT) return 1;
+    }
+    return (u64)1 << pc.bits();
+}
+
+// Emits code packing Val `v` as component pc into (lo,hi,pos) variables; with `radix` also adds the component's packed
+// value times `radix_stride` to the variable of that name (mixed-radix slot of a dense shared-memory table).
+void emit_pack(Gen& g, const PackComp& pc, const std::string& v, const char* lo, const char* hi, const char* pos,
+               const char* radix = nullptr, u64 radix_stride = 0) {
+    if (radix && pc.bits() > 0) {
+        // the whole component as one value: class index in the low cbits, payload above
+        std::string cv = g.nv("cv");
+        std::string ci = "0ULL", pv = "0ULL";
+        if (pc.nfree >= 0) {
+            const int pcls = pc.classes.back();
+            std::string pay = pcls == C_STRING ? strf("((u64)%s.b >> 1)", v.c_str()) : strf("((u64)%s.b - (u64)%s)", v.c_str(), lit_i64(pc.bias).c_str());
+            pv = strf("(%dULL + %s)", pc.nfree, pay.c_str());
+            for (int k = pc.nfree - 1; k >= 0; --k) pv = strf("(%s.c == %s ? %dULL : %s)", v.c_str(), cls_name(pc.classes[k]), k, pv.c_str());
+            g.line(strf("const u64 %s = %s;", cv.c_str(), pv.c_str()));
+        } else {
+            if (pc.cbits) {
+                ci = strf("%dULL", (int)pc.classes.size() - 1);
+                for (int k = (int)pc.classes.size() - 2; k >= 0; --k) ci = strf("(%s.c == %s ? %dULL : %s)", v.c_str(), cls_name(pc.classes[k]), k, ci.c_str());
+            }
+            if (pc.pbits) {
+                if (pc.mask & bit(C_STRING)) pv = strf("(%s.c == C_STRING ? ((u64)%s.b >> 1) : %s)", v.c_str(), v.c_str(), pv.c_str());
+                if (pc.mask & bit(C_FLOAT)) pv = strf("(%s.c == C_FLOAT ? (u64)%s.b : %s)", v.c_str(), v.c_str(), pv.c_str());
+                if (pc.mask & bit(C_INT)) {
+                    std::string iv = pc.biased ? strf("((u64)%s.b - (u64)%s)", v.c_str(), lit_i64(pc.bias).c_str()) : strf("(u64)%s.b", v.c_str());
+                    pv = strf("(%s.c == C_INT ? %s : %s)", v.c_str(), iv.c_str(), pv.c_str());
+                }
+            }
+            g.line(strf("const u64 %s = %s | (%s << %d);", cv.c_str(), ci.c_str(), pv.c_str(), pc.cbits));
+        }
+        g.line(strf("pack_bits(%s, %s, %s, %s, %d);", lo, hi, pos, cv.c_str(), pc.bits()));
+        g.line(strf("%s += %s * %lluULL;", radix, cv.c_str(), (unsigned long long)radix_stride));
+        return;
+    }
     if (pc.nfree >= 0) {
         const int pcls = pc.classes.back();
         std::string pay = pcls == C_STRING ? strf("((u64)%s.b >> 1)", v.c_str()) : strf("((u64)%s.b - (u64)%s)", v.c_str(), lit_i64(pc.bias).c_str());
@@ -324,6 +366,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     std::map<std::string, int> dset_of;  // DISTINCT operand text -> entry-set id
     std::vector<bool> dset_any;          // set id -> holds every value > NULL (else numbers only)
     int ndistinct_aggs = 0;
+    std::map<std::string, std::pair<int, int>> flag_of;  // float-carried operand text -> (OR word, first of its three bits)
+    int flag_word = -1, flag_next = 0;
     int w_rows = -1;
     if (!keys.empty()) w_rows = add_word(OP_ADD_U64, "rows", true);  // word 0: rows per group (group existence)
     auto rows_word = [&]() { if (w_rows < 0) w_rows = add_word(OP_ADD_U64, "rows", true); return w_rows; };
@@ -363,6 +407,20 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             const u32 counted = ap.kind == AggKind::COUNT ? ~(bit(C_MISSING) | bit(C_NULL)) : M_NUM;
             if (ap.star || (ap.opmask & ~counted) == 0) ap.w_cnt = rows_word();  // every selected row counts
             else ap.w_cnt = add_word(OP_ADD_U64, (ap.kind == AggKind::COUNT ? "cnt:" : "cntn:") + ot, true);
+        } else if ((ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) && (ap.opmask & bit(C_INT)) && (ap.opmask & bit(C_FLOAT)) &&
+                   opnd->ti.imax * std::max(1.0, total_rows_bound) < 9.0e15 && !(getenv("N1GPU_NO_FCARRY") && *getenv("N1GPU_NO_FCARRY") == '1')) {
+            // INT and FLOAT values mixed, ints provably small: one float64 word carries both (see AggPlan::fcarry)
+            const std::string ot = opnd->str();
+            ap.fcarry = true;
+            ap.w_fsum = add_word(OP_ADD_F64, "fsum:" + ot);
+            ap.w_nnum = (ap.opmask & ~M_NUM) == 0 ? rows_word() : add_word(OP_ADD_U64, "cntn:" + ot, true);
+            if (!flag_of.count(ot)) {
+                if (flag_word < 0 || flag_next + 3 > 30) { flag_word = add_word(OP_OR_U64, strf("flags:%d", (int)flag_of.size())); flag_next = 0; }
+                flag_of[ot] = {flag_word, flag_next};
+                flag_next += 3;
+            }
+            ap.w_flags = flag_of[ot].first;
+            ap.flag_shift = flag_of[ot].second;
         } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
             const std::string ot = opnd->str();
             if (ap.opmask & bit(C_INT)) {
@@ -420,6 +478,13 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     else if (kp.key_bits <= 13 && ((i64)1 << kp.key_bits) * W * 8 <= 40 * 1024) {
         kp.mode = MODE_DENSE;
         kp.dense_slots = (i64)1 << kp.key_bits;
+        {   // slots numbered by the mixed-radix value of the components when that is tighter than the bit-packed key
+            u64 tight = 1;
+            std::vector<u64> dom;
+            for (auto& pc : kp.keys) { const u64 d = comp_values(t, pc); dom.push_back(d); tight = d ? tight * d : 0; }
+            const char* nt = getenv("N1GPU_NO_TIGHT");
+            if (tight > 0 && (i64)tight < kp.dense_slots && kp.ndistinct == 0 && !(nt && *nt == '1')) { kp.dense_dom = dom; kp.dense_slots = (i64)tight; }
+        }
         // A handful of groups (TPC-H Q1: 6) would serialise every row on the same few shared-memory words.  When the
         // whole table is <= 48 words, every thread keeps its own copy in shared memory (bank = thread: conflict-free
         // plain read-modify-write, no atomics) and the copies are folded once per block.
@@ -576,6 +641,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     g.ind = "                    ";
     if (kp.mode != MODE_UNGROUPED) {
         g.line("u64 klo = 0, khi = 0; int kpos = 0;");
+        const bool radix = !kp.dense_dom.empty();
+        if (radix) g.line("u64 kslot = 0;");
+        u64 radix_stride = 1;
         for (size_t k = 0; k < keys.size(); ++k) {
             std::string kv = g.emit(*keys[k], nullptr);
             if (!keys[k]->ti.plain_col && (keys[k]->ti.mask & bit(C_FLOAT))) {
@@ -583,9 +651,10 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 g.line(strf("const Val %s = canon_num(%s);", cv.c_str(), kv.c_str()));
                 kv = cv;
             }
-            emit_pack(g, kp.keys[k], kv, "klo", "khi", "kpos");
+            emit_pack(g, kp.keys[k], kv, "klo", "khi", "kpos", radix ? "kslot" : nullptr, radix_stride);
+            if (radix) radix_stride *= kp.dense_dom[k];
         }
-        if (kp.mode == MODE_DENSE && !cached) g.line("const i64 slot = (i64)klo;");
+        if (kp.mode == MODE_DENSE && !cached) g.line(radix ? "const i64 slot = (i64)kslot;" : "const i64 slot = (i64)klo;");
         else if (cached) {
             // the kernel is assembled in phases (keys + cache probe / cached updates / table updates, see below):
             // the key code ends here, the update code starts from an empty body
@@ -648,6 +717,16 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             else ACCIF(strf("%s.c > C_NULL", o.c_str()), ap.w_cnt, OP_ADD_U64, "1");
         } else if (ap.kind == AggKind::COUNTN) {
             ACCIF(strf("is_num(%s.c)", o.c_str()), ap.w_cnt, OP_ADD_U64, "1");
+        } else if (ap.fcarry) {
+            if (!emitted.count(ap.w_fsum)) {  // SUM(x) and AVG(x) share the words: fed once
+                g.line(strf("if (is_num(%s.c)) {", o.c_str()));
+                g.ind += "    ";
+                ACC(ap.w_fsum, OP_ADD_F64, strf("(u64)__double_as_longlong(num_f(%s))", o.c_str()));
+                g.line(strf("ACC(%d, OP_OR_U64, (%s.c == C_FLOAT ? 1ULL : (%s.b < 0 ? 2ULL : 4ULL)) << %d);", ap.w_flags, o.c_str(), o.c_str(), ap.flag_shift));
+                ACC(ap.w_nnum, OP_ADD_U64, "1");
+                g.ind = save_ind + "    ";
+                g.line("}");
+            }
         } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
             if (ap.opmask & bit(C_INT)) {
                 g.line(strf("if (%s.c == C_INT) {", o.c_str()));

@@ -41,6 +41,12 @@ struct AggPlan {
     int w_ilo = -1, w_ihi = -1;  // split int sum: sum of low 32 bits / sum of (x >> 32)
     int w_nint = -1, w_neg = -1;  // ints summed / negative ints among them (intValue.Add: mixed signs -> float64)
     int w_fsum = -1, w_nflt = -1;
+    // "float-carried" sum of an operand that mixes INT and FLOAT values whose ints are provably small (|x| * rows < 2^53):
+    // every number is added to ONE float64 word (integers that small add exactly in float64, so an all-INT group still
+    // gets its exact int64 sum), w_nnum counts the numbers, and three bits of a shared OR word remember whether a float,
+    // a negative int or a non-negative int was seen (the int / float class of the result: value/integer.go:266-277).
+    bool fcarry = false;
+    int w_nnum = -1, w_flags = -1, flag_shift = 0;
     int w_seen = -1, w_mi = -1, w_mf = -1, w_ms = -1;
     int w_seen_cnt = -1, seen_class = -1;  // single-class operand: "seen" = (this count word > 0) ? bit(seen_class) : 0
     int dict_col = -1;
@@ -66,6 +72,9 @@ struct KernelPlan {
     std::vector<PackComp> keys;
     int key_bits = 0;
     i64 dense_slots = 0;
+    // shared-memory dense tables index slots by the mixed-radix number of the key components (TPC-H Q1: 3 x 2 = 6 slots
+    // instead of the 2^3 = 8 of the bit-packed key); dense_dom[i] = values component i takes (empty: slot == packed key)
+    std::vector<u64> dense_dom;
     bool dense_global = false;   // MODE_DENSE whose table is too large for shared memory: direct-indexed in HBM (slot = packed
                                  // key, no key array, no probing) behind the shared-memory front cache of the hash mode
     bool dense_priv = false;     // tiny dense table: one private copy per THREAD in shared memory (no atomics at all)

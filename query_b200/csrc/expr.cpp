@@ -1,6 +1,8 @@
 // expr.cpp — Stringer-text parser, binder and static type analysis for the eligible expression subset.
 #include "expr.hpp"
 
+#include <cmath>
+
 #include <algorithm>
 #include <charconv>
 
@@ -333,6 +335,7 @@ void bind_and_analyze(Expr& e, const std::string& alias, const Table& t) {
         ti.mask = st.class_mask ? st.class_mask : bit(C_MISSING);
         ti.plain_col = true;
         if (st.has_int) { ti.ranged = true; ti.lo = st.int_min; ti.hi = st.int_max; }
+        ti.imax = !(ti.mask & bit(C_INT)) ? 0.0 : (st.has_int ? std::max(std::fabs((double)st.int_min), std::fabs((double)st.int_max)) : 1e300);
         if (ti.mask & bit(C_STRING)) ti.dict_col = c;
         return;
     }
@@ -360,6 +363,7 @@ void bind_and_analyze(Expr& e, const std::string& alias, const Table& t) {
         case EK::CONST:
             ti.mask = bit(e.cval.cls);
             if (e.cval.cls == C_INT) { ti.ranged = true; ti.lo = ti.hi = e.cval.bits; }
+            ti.imax = e.cval.cls == C_INT ? std::fabs((double)e.cval.bits) : 0.0;
             break;
         case EK::ARRAY:
             ti.mask = 0;  // only meaningful as the right side of IN
@@ -425,6 +429,16 @@ void bind_and_analyze(Expr& e, const std::string& alias, const Table& t) {
                 } else m |= M_NUM;
             }
             ti.mask = m;
+            // magnitude bound of INT results.  + - * neg yield an INT only from INT operands (a float operand makes a
+            // floatValue, integral or not: value/float.go:331-381), so interval arithmetic over the operands' INT bounds
+            // holds; / and % canonicalise integral quotients to INT (arith_div.go:46-64) - no bound there.
+            if (!(m & bit(C_INT))) ti.imax = 0.0;
+            else if (e.kind == EK::DIV || e.kind == EK::MOD) ti.imax = 1e300;
+            else {
+                double b = e.kind == EK::MULT ? 1.0 : 0.0;
+                for (auto& o : e.ops) b = e.kind == EK::MULT ? b * o->ti.imax : b + o->ti.imax;
+                ti.imax = std::min(b, 1e300);
+            }
             break;
         }
         case EK::EQ: case EK::LT: case EK::LE: case EK::BETWEEN: {

@@ -31,6 +31,7 @@ struct TypeInfo {
     u32 mask = 0;          // classes the value may take
     bool ranged = false;   // INT values proven within [lo, hi]
     i64 lo = 0, hi = 0;
+    double imax = 1e300;   // every INT value satisfies |x| <= imax (1e300: unknown); 0 when the value is never an INT
     int dict_col = -1;     // STRING values are ranks in this column's dictionary (-1: none / constant)
     bool plain_col = false;
 };

@@ -388,6 +388,16 @@ HValue sum_value(const SumState& s, bool from_zero) {
 
 }  // namespace
 
+// slot of a shared-memory dense table -> the bit-packed group key (slots are the mixed-radix number of the components
+// when that is tighter than the packed key: KernelPlan::dense_dom)
+u64 Query::dense_key(u64 slot) const {
+    if (kp.dense_dom.empty()) return slot;
+    u64 key = 0;
+    int pos = 0;
+    for (size_t k = 0; k < kp.keys.size(); ++k) { key |= (slot % kp.dense_dom[k]) << pos; slot /= kp.dense_dom[k]; pos += kp.keys[k].bits(); }
+    return key;
+}
+
 std::unique_ptr<Result> Query::finalize() {
     const int W = ops.n;
     const int LW = (int)kp.word_ops.size();
@@ -423,7 +433,7 @@ std::unique_ptr<Result> Query::finalize() {
         for (u64 i = 0; i < cap; ++i) {
             if (kp.mode == MODE_DENSE && h[i] == 0) continue;  // word 0 = rows in group
             if (kp.mode == MODE_UNGROUPED && !ungrouped_live) continue;
-            recs.push_back(i); recs.push_back(0);
+            recs.push_back(dense_key(i)); recs.push_back(0);
             for (int w = 0; w < W; ++w) recs.push_back(h[(u64)w * cap + i]);
             ++ngroups;
         }
@@ -438,6 +448,7 @@ std::unique_ptr<Result> Query::finalize() {
             count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, W, 1, 0, kp.key_bits, d_records.as<u64>(), ngroups, c2);
             recs.resize((size_t)ngroups * rw);
             CK(cudaMemcpy(recs.data(), d_records.p, recs.size() * 8, cudaMemcpyDeviceToHost));
+            if (!kp.dense_dom.empty()) for (i64 g = 0; g < ngroups; ++g) recs[(size_t)g * rw] = dense_key(recs[(size_t)g * rw]);
         }
     }
 
@@ -496,6 +507,18 @@ std::unique_ptr<Result> Query::finalize() {
                 }
             } else if (ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) {
                 out = HValue::integer((i64)w[ap.w_cnt]);
+            } else if (ap.fcarry) {
+                // float-carried sum: integers this small add exactly in float64, so an all-INT group has its exact total
+                const u64 count = w[ap.w_nnum], flags = (w[ap.w_flags] >> ap.flag_shift) & 7;
+                double fs;
+                memcpy(&fs, &w[ap.w_fsum], 8);
+                HValue sv;
+                if (count == 0) sv = HValue::null();
+                else if (flags & 1) sv = HValue::flt(fs);
+                else if ((flags & 2) && (flags & 4)) sv = HValue::flt(fs);   // ints of both signs: intValue.Add went float
+                else sv = HValue::integer((i64)fs);
+                if (ap.kind == AggKind::SUM || sv.cls == C_NULL) out = sv;
+                else out = new_num(sv.num() / (double)count);
             } else if (ap.kind == AggKind::SUM || ap.kind == AggKind::AVG) {
                 SumState s;
                 if (ap.w_isum >= 0) s.itotal = (i64)w[ap.w_isum];

@@ -95,6 +95,7 @@ struct Query {
     void partial_reset();
     void partial_import(const void* dev_records, i64 n, const void* dev_distinct, i64 nd);
     std::unique_ptr<Result> finalize();
+    u64 dense_key(u64 slot) const;
     void rebind(Table* t);
 };
 

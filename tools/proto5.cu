@@ -86,7 +86,30 @@ struct Smem {
 __device__ __forceinline__ void red_add_u64(u64* p, u64 v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void red_max_s64(u64* p, i64 v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
-template <int NT, int NS, int K0, int L0T>
+// probe of the block's front cache with WAYS keys per bucket (4: one LDS.128, 2: one LDS.64, 1: direct-mapped LDS.32)
+template <int WAYS>
+__device__ __forceinline__ int cache_claim_w(u32* ckeys, u32 nslots, u32 hash, u32 key) {
+    if (WAYS == 4) return cache_claim_b4(ckeys, nslots / 4, hash, key);
+    if (WAYS == 2) {
+        const u32 b = __umulhi(hash, nslots / 2) * 2u;
+        u32 k0, k1;
+        asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(k0), "=r"(k1) : "r"((u32)__cvta_generic_to_shared(ckeys + b)) : "memory");
+        if (k0 == key) return (int)b;
+        if (k1 == key) return (int)b + 1;
+        if (k1 != 0xffffffffu) return -1;  // slots fill in order: the last one taken = full
+        if (k0 == 0xffffffffu) { const u32 old = atomicCAS(&ckeys[b], 0xffffffffu, key); if (old == 0xffffffffu || old == key) return (int)b; }
+        const u32 old = atomicCAS(&ckeys[b + 1], 0xffffffffu, key);
+        return (old == 0xffffffffu || old == key) ? (int)b + 1 : -1;
+    }
+    const u32 b = __umulhi(hash, nslots);
+    const u32 k0 = *(volatile u32*)&ckeys[b];
+    if (k0 == key) return (int)b;
+    if (k0 != 0xffffffffu) return -1;
+    const u32 old = atomicCAS(&ckeys[b], 0xffffffffu, key);
+    return (old == 0xffffffffu || old == key) ? (int)b : -1;
+}
+
+template <int NT, int NS, int K0, int L0T, int WAYS, int CHECK, int PREF, int MNREG>
 __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef Smem<NT, NS, K0> S;
@@ -128,7 +151,7 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
         const u32 key = active ? qk[idx] : 0u, val = active ? qv[idx] : 0u;
         qhead += n;
         int slot = -2;
-        if (active) slot = cache_claim_b4(s.ckey, NS / 4, key * 0x9E3779B1u, key);
+        if (active) slot = cache_claim_w<WAYS>(s.ckey, NS, key * 0x9E3779B1u, key);
         if (slot >= 0) {
             const bool isnull = val >> 31;
             const u32 vb = val & 0xfffffu;
@@ -138,8 +161,8 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
                 const u32 so = atomicAdd(&s.c_sum[slot], vb);
                 if ((u32)(so + vb) < vb) red_add_u64(table + (u64)key * 4 + 1, 1ULL << 32);  // carry out of the 32-bit cell (rare)
                 const u32 a = vb + 1u, b = 0x100000u - vb;
-                if (a > *(volatile u32*)&s.c_max[slot]) atomicMax(&s.c_max[slot], a);
-                if (b > *(volatile u32*)&s.c_nmin[slot]) atomicMax(&s.c_nmin[slot], b);
+                if (!CHECK || a > *(volatile u32*)&s.c_max[slot]) atomicMax(&s.c_max[slot], a);
+                if (!CHECK || b > *(volatile u32*)&s.c_nmin[slot]) atomicMax(&s.c_nmin[slot], b);
             }
             if (K0 && old >= (u32)L0T) {  // hot in this block: give it a conflict-free home in this lane's L0 column
                 const unsigned e = (key * 0x9E3779B1u) >> 16 & (K0 - 1);
@@ -157,29 +180,38 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
 
     const i64 nrows = p.nrows;
     const i64 stride = (i64)gridDim.x * (NT * 4);
-    for (i64 wbase = (i64)blockIdx.x * (NT * 4) + w * 128; wbase < nrows; wbase += stride) {
+    u32 n0[4]; int nt0[4]; i64 n1[4]; int nt1[4];  // next tile (software prefetch)
+    i64 wbase = (i64)blockIdx.x * (NT * 4) + w * 128;
+    if (PREF && wbase < nrows) { const i64 b = wbase + lane * 4; ld_rows4_b32(p.code + b, n0); ld_rows4_b8(p.ktag + b, nt0); ld_rows4_b64(p.v + b, n1); ld_rows4_b8(p.vtag + b, nt1); }
+    for (; wbase < nrows; wbase += stride) {
         const i64 base = wbase + lane * 4;
-        u32 c0[4]; ld_rows4_b32(p.code + base, c0);
-        int t0[4]; ld_rows4_b8(p.ktag + base, t0);
-        i64 c1[4]; ld_rows4_b64(p.v + base, c1);
-        int t1[4]; ld_rows4_b8(p.vtag + base, t1);
+        u32 c0[4]; int t0[4]; i64 c1[4]; int t1[4];
+        if (PREF) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c0[j] = n0[j]; t0[j] = nt0[j]; c1[j] = n1[j]; t1[j] = nt1[j]; }
+            if (wbase + stride < nrows) { const i64 b = base + stride; ld_rows4_b32(p.code + b, n0); ld_rows4_b8(p.ktag + b, nt0); ld_rows4_b64(p.v + b, n1); ld_rows4_b8(p.vtag + b, nt1); }
+        } else {
+            ld_rows4_b32(p.code + base, c0); ld_rows4_b8(p.ktag + base, t0); ld_rows4_b64(p.v + base, c1); ld_rows4_b8(p.vtag + base, t1);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const bool pass = base + j < nrows && t1[j] != C_MISSING;
             const bool isnull = t1[j] == C_NULL;
             const u32 vb = isnull ? 0u : (u32)(c1[j] + VBIAS);
+            if (MNREG) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const bool hit = pass && t0[j] == g;
-                const bool hv = hit && !isnull;
-                r_rows[g] += hit;
-                r_cnull[g] += hit && isnull;
-                r_sum[g] += hv ? vb : 0u;
-                r_max[g] = max(r_max[g], hv ? vb + 1u : 0u);
-                r_nmin[g] = max(r_nmin[g], hv ? 0x100000u - vb : 0u);
+                for (int g = 0; g < 2; ++g) {
+                    const bool hit = pass && t0[j] == g;
+                    const bool hv = hit && !isnull;
+                    r_rows[g] += hit;
+                    r_cnull[g] += hit && isnull;
+                    r_sum[g] += hv ? vb : 0u;
+                    r_max[g] = max(r_max[g], hv ? vb + 1u : 0u);
+                    r_nmin[g] = max(r_nmin[g], hv ? 0x100000u - vb : 0u);
+                }
             }
-            bool tostr = pass && t0[j] == C_STRING;
-            const u32 key = c0[j] + 2u;
+            bool tostr = pass && (MNREG ? t0[j] == C_STRING : true);
+            const u32 key = t0[j] == C_STRING ? c0[j] + 2u : (u32)t0[j];
             if (K0) {
                 const unsigned e = (key * 0x9E3779B1u) >> 16 & (K0 - 1);
                 if (tostr && !isnull && s.l0key[e][lane] == key) {  // bank == lane: no conflicts inside the warp
@@ -259,15 +291,15 @@ static bool check(const char* name, const Ref& r, const std::vector<u64>& rows, 
     return bad == 0;
 }
 
-template <int NT, int NS, int K0, int L0T>
+template <int NT, int NS, int K0, int L0T, int WAYS = 4, int CHECK = 1, int PREF = 0, int MNREG = 1>
 static void run_q(const char* name, const QParams& qp0, u64* d_tab, const Ref& ref, i64 n, int sms) {
     typedef Smem<NT, NS, K0> S;
     const size_t smem = sizeof(S);
-    CKE(cudaFuncSetAttribute(k_scan_q<NT, NS, K0, L0T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CKE(cudaFuncSetAttribute(k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa;
-    CKE(cudaFuncGetAttributes(&fa, k_scan_q<NT, NS, K0, L0T>));
+    CKE(cudaFuncGetAttributes(&fa, k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG>));
     int occ = 0;
-    CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_q<NT, NS, K0, L0T>, NT, smem));
+    CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG>, NT, smem));
     QParams qp = qp0;
     qp.table = d_tab;
     cudaEvent_t e0, e1;
@@ -277,7 +309,7 @@ static void run_q(const char* name, const QParams& qp0, u64* d_tab, const Ref& r
         k_fill4<<<592, 256>>>(d_tab, SLOTS, 0, 0, (u64)NQ_I64_MIN, (u64)NQ_I64_MIN);
         CKE(cudaDeviceSynchronize());
         CKE(cudaEventRecord(e0));
-        k_scan_q<NT, NS, K0, L0T><<<sms * occ, NT, smem>>>(qp);
+        k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG><<<sms * occ, NT, smem>>>(qp);
         CKE(cudaEventRecord(e1));
         CKE(cudaDeviceSynchronize());
         CKE(cudaGetLastError());
@@ -293,8 +325,8 @@ static void run_q(const char* name, const QParams& qp0, u64* d_tab, const Ref& r
         mn[i] = ~(i64)t[4 * i + 2]; mx[i] = (i64)t[4 * i + 3];
     }
     const bool ok = check(name, ref, rows, cnull, sum, mn, mx);
-    printf("{\"variant\": \"%s\", \"threads\": %d, \"cache_slots\": %d, \"l0\": %d, \"smem\": %zu, \"regs\": %d, \"blocks_per_sm\": %d, \"ms\": %.4f, \"rows_per_s\": %.4g, \"gb_per_s\": %.1f, \"frac\": %.3f, \"check\": \"%s\"}\n",
-           name, NT, NS, K0, smem, fa.numRegs, occ, best, n / (best * 1e-3), 14.0 * n / (best * 1e6), 14.0 * n / (best * 1e6) / 6547.8, ok ? "ok" : "MISMATCH");
+    printf("{\"variant\": \"%s\", \"ways\": %d, \"check\": %d, \"prefetch\": %d, \"mnreg\": %d, \"threads\": %d, \"cache_slots\": %d, \"l0\": %d, \"smem\": %zu, \"regs\": %d, \"blocks_per_sm\": %d, \"ms\": %.4f, \"rows_per_s\": %.4g, \"gb_per_s\": %.1f, \"frac\": %.3f, \"check\": \"%s\"}\n",
+           name, WAYS, CHECK, PREF, MNREG, NT, NS, K0, smem, fa.numRegs, occ, best, n / (best * 1e-3), 14.0 * n / (best * 1e6), 14.0 * n / (best * 1e6) / 6547.8, ok ? "ok" : "MISMATCH");
     fflush(stdout);
 }
 
@@ -372,11 +404,17 @@ int main(int argc, char** argv) {
     u64* d_tab; CKE(cudaMalloc(&d_tab, SLOTS * 4 * 8));
     QParams qp; qp.code = d_code; qp.ktag = d_ktag; qp.v = d_v; qp.vtag = d_vtag; qp.nrows = n; qp.table = d_tab;
     // cache slots: (budget - queues - L0) / 24 bytes, a multiple of 4
-    run_q<1024, 8200, 0, 0>("q 1024x1", qp, d_tab, ref, n, sms);
-    run_q<512, 8960, 0, 0>("q 512x1", qp, d_tab, ref, n, sms);
-    run_q<1024, 6560, 64, 256>("q+l0(64) 1024x1", qp, d_tab, ref, n, sms);
-    run_q<1024, 4880, 128, 256>("q+l0(128) 1024x1", qp, d_tab, ref, n, sms);
-    run_q<1024, 4880, 128, 64>("q+l0(128,T64) 1024x1", qp, d_tab, ref, n, sms);
-    run_q<512, 5560, 128, 256>("q+l0(128) 512x1", qp, d_tab, ref, n, sms);
+    const char* only = getenv("ONLY");
+#define RUN(name, ...) if (!only || strstr(name, only)) run_q<__VA_ARGS__>(name, qp, d_tab, ref, n, sms)
+    RUN("q", 1024, 8200, 0, 0);
+    RUN("q ways2", 1024, 8200, 0, 0, 2);
+    RUN("q ways1", 1024, 8200, 0, 0, 1);
+    RUN("q nocheck", 1024, 8200, 0, 0, 4, 0);
+    RUN("q pref", 1024, 8200, 0, 0, 4, 1, 1);
+    RUN("q pref 768", 768, 8520, 0, 0, 4, 1, 1);
+    RUN("q 768", 768, 8520, 0, 0, 4, 1, 0);
+    RUN("q nomnreg", 1024, 8200, 0, 0, 4, 1, 0, 0);
+    RUN("q ways2 pref", 1024, 8200, 0, 0, 2, 1, 1);
+    RUN("q ways1 pref", 1024, 8200, 0, 0, 1, 1, 1);
     return 0;
 }
