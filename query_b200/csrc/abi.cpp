@@ -497,7 +497,7 @@ int n1gpu_operator_import_result(const n1gpu_operator* op, int64_t ngroups, cons
         r->key_cls.assign(key_cls, key_cls + nk); r->key_val.assign(key_val, key_val + nk);
         r->agg_cls.assign(agg_cls, agg_cls + na); r->agg_val.assign(agg_val, agg_val + na);
         for (int64_t i = 0; i < nstrings; ++i) r->strings.emplace_back(blob + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
-        auto check = [&](const std::vector<u8>& cls, const std::vector<i64>& val) {
+        auto check = [&](const FlatArr<u8>& cls, const FlatArr<i64>& val) {
             for (size_t i = 0; i < cls.size(); ++i) {
                 if (cls[i] > C_STRING) N1_THROW(N1GPU_E_INVALID, "value class %d is not a scalar class", (int)cls[i]);
                 if (cls[i] == C_STRING && (val[i] < 0 || val[i] >= nstrings)) N1_THROW(N1GPU_E_INVALID, "string index out of range");

@@ -23,6 +23,35 @@ struct DistinctDescs {
     int n;
     DistinctDesc d[16];
 };
+// ---- device-side FinalGroup (ComputeFinal of every aggregate + key decoding), see k_finalize_groups -----------------------
+// How the table is addressed: word w of slot i lives at acc[w * ws + i * ss] (word-major: ws = capacity, ss = 1).
+struct FinalComp {   // PackComp as plain data
+    int cbits, pbits, nfree, biased, dict_col, nclasses;
+    i64 bias;
+    int classes[8];
+};
+struct FinalAgg {    // AggPlan as plain data (word indices are LOGICAL words, -1 = absent)
+    signed char kind, distinct, fcarry, seen_class;
+    short dict_col;
+    signed char w_cnt, w_isum, w_ilo, w_ihi, w_nint, w_neg, w_fsum, w_nflt, w_seen, w_mi, w_mf, w_ms, w_seen_cnt, w_nnum, w_flags, flag_shift;
+};
+struct FinalDesc {
+    int nkeys, naggs, LW, PW;
+    unsigned char phys_of[64], shift_of[64], bits_of[64], complement[64];
+    FinalComp keys[16];
+    FinalAgg aggs[24];
+};
+// The partial tables the groups are read from: one (this rank's) or one per rank, combined word by word with the merge
+// operations on the fly (IntermediateGroup fused into FinalGroup; peers are mapped over NVLink).
+struct PeerTables {
+    int n;
+    const u64* acc[16];
+};
+// Finalises the live groups of slots [slot0, slot1) into compact flat arrays (n1gpu_result_fetch layout); *counter
+// (zeroed by the caller) ends as the number of groups written; groups beyond out_cap are counted but not written.
+void launch_finalize_groups(const FinalDesc& D, int kw, const u64* keys, const PeerTables& T, const OpsArr& ops, u64 ws, u64 ss, u64 slot0,
+                            u64 slot1, unsigned long long* counter, u64 out_cap, u8* key_cls, i64* key_val, u8* agg_cls, i64* agg_val,
+                            cudaStream_t s);
 void launch_distinct_finalize(const u64* set_keys, u64 set_cap, int set128, int abits, int key_bits, int kw, const u64* keys, u64 cap,
                               u64* acc, const DistinctDescs& D, cudaStream_t s);
 void launch_merge_mailbox(const u64* mail, int nranks, u64 slot_base, u64 stride, u64 words, u64 seq, u64 cap, const OpsArr& ops,

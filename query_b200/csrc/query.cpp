@@ -398,6 +398,83 @@ u64 Query::dense_key(u64 slot) const {
     return key;
 }
 
+FinalDesc Query::final_desc() const {
+    FinalDesc D;
+    memset(&D, 0, sizeof D);
+    D.nkeys = (int)keys.size();
+    D.naggs = (int)aggs.size();
+    D.LW = (int)kp.word_ops.size();
+    D.PW = ops.n;
+    for (int l = 0; l < D.LW; ++l) {
+        D.phys_of[l] = (unsigned char)kp.phys_of[l]; D.shift_of[l] = (unsigned char)kp.shift_of[l];
+        D.bits_of[l] = (unsigned char)kp.bits_of[l]; D.complement[l] = kp.word_complement[l] ? 1 : 0;
+    }
+    for (int k = 0; k < D.nkeys; ++k) {
+        const PackComp& pc = kp.keys[k];
+        FinalComp& c = D.keys[k];
+        c.cbits = pc.cbits; c.pbits = pc.pbits; c.nfree = pc.nfree; c.biased = pc.biased; c.dict_col = pc.dict_col; c.bias = pc.bias;
+        c.nclasses = (int)std::min<size_t>(8, pc.classes.size());
+        for (int i = 0; i < 8; ++i) c.classes[i] = i < c.nclasses ? pc.classes[i] : C_MISSING;
+    }
+    for (int a = 0; a < D.naggs; ++a) {
+        const AggPlan& ap = kp.aggs[a];
+        FinalAgg& f = D.aggs[a];
+        f.kind = (signed char)ap.kind; f.distinct = ap.distinct; f.fcarry = ap.fcarry; f.seen_class = (signed char)ap.seen_class;
+        f.dict_col = (short)ap.dict_col;
+        f.w_cnt = (signed char)ap.w_cnt; f.w_isum = (signed char)ap.w_isum; f.w_ilo = (signed char)ap.w_ilo; f.w_ihi = (signed char)ap.w_ihi;
+        f.w_nint = (signed char)ap.w_nint; f.w_neg = (signed char)ap.w_neg; f.w_fsum = (signed char)ap.w_fsum; f.w_nflt = (signed char)ap.w_nflt;
+        f.w_seen = (signed char)ap.w_seen; f.w_mi = (signed char)ap.w_mi; f.w_mf = (signed char)ap.w_mf; f.w_ms = (signed char)ap.w_ms;
+        f.w_seen_cnt = (signed char)ap.w_seen_cnt; f.w_nnum = (signed char)ap.w_nnum; f.w_flags = (signed char)ap.w_flags;
+        f.flag_shift = (signed char)ap.flag_shift;
+    }
+    return D;
+}
+
+i64 Query::finalize_device(Result& res, const PeerTables& tables, u64 slot0, u64 slot1) {
+    const size_t nk = keys.size(), na = aggs.size();
+    const u64 span = slot1 > slot0 ? slot1 - slot0 : 0;
+    // Output capacity: every slot could hold a group.  When that worst case is large (sparse hash tables) the live slots
+    // are counted first; the count needs a host round trip either way (the result arrays are sized by it).
+    u64 out_cap = span;
+    unsigned long long* counter = d_counts.as<unsigned long long>();
+    const FinalDesc D = final_desc();
+    const size_t per_group = (nk + na) * 9;
+    if (span * per_group > ((size_t)256 << 20) && tables.n == 1) {
+        i64 c[1] = {0};
+        CK(cudaMemsetAsync(d_counts.p, 0, 64, stream));
+        launch_count_owners(kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, 1, 0, std::max(kp.key_bits, 0), counter, stream);
+        CK(cudaMemcpyAsync(h_counts.p, d_counts.p, 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        c[0] = (i64)h_counts.as<unsigned long long>()[0];
+        out_cap = (u64)c[0];
+    }
+    auto up8 = [](size_t n) { return (n + 7) & ~(size_t)7; };
+    const size_t o_kc = 0, o_ac = o_kc + up8(out_cap * nk), o_kv = o_ac + up8(out_cap * na), o_av = o_kv + out_cap * nk * 8;
+    const size_t total = o_av + out_cap * na * 8;
+    d_final.ensure(std::max<size_t>(total, 64));
+    char* d = d_final.as<char>();
+    CK(cudaMemsetAsync(d_counts.p, 0, 64, stream));
+    launch_finalize_groups(D, kw(), d_keys.as<u64>(), tables, ops, cap, 1, slot0, slot1, counter, out_cap, (u8*)(d + o_kc), (i64*)(d + o_kv),
+                           (u8*)(d + o_ac), (i64*)(d + o_av), stream);
+    CK(cudaMemcpyAsync(h_counts.p, d_counts.p, 8, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const u64 ng = h_counts.as<unsigned long long>()[0];
+    if (ng > out_cap) N1_THROW(N1GPU_E_INVALID, "finalisation found %llu groups in a table counted at %llu", (unsigned long long)ng, (unsigned long long)out_cap);
+    const size_t h_kc = 0, h_ac = h_kc + up8(ng * nk), h_kv = h_ac + up8(ng * na), h_av = h_kv + ng * nk * 8;
+    res.pinned.ensure(std::max<size_t>(h_av + ng * na * 8, 64));
+    char* h = res.pinned.as<char>();
+    if (ng) {
+        if (nk) { CK(cudaMemcpyAsync(h + h_kc, d + o_kc, ng * nk, cudaMemcpyDeviceToHost, stream)); CK(cudaMemcpyAsync(h + h_kv, d + o_kv, ng * nk * 8, cudaMemcpyDeviceToHost, stream)); }
+        if (na) { CK(cudaMemcpyAsync(h + h_ac, d + o_ac, ng * na, cudaMemcpyDeviceToHost, stream)); CK(cudaMemcpyAsync(h + h_av, d + o_av, ng * na * 8, cudaMemcpyDeviceToHost, stream)); }
+        CK(cudaStreamSynchronize(stream));
+    }
+    res.key_cls.view((u8*)(h + h_kc), ng * nk);
+    res.key_val.view((i64*)(h + h_kv), ng * nk);
+    res.agg_cls.view((u8*)(h + h_ac), ng * na);
+    res.agg_val.view((i64*)(h + h_av), ng * na);
+    return (i64)ng;
+}
+
 std::unique_ptr<Result> Query::finalize() {
     const int W = ops.n;
     const int LW = (int)kp.word_ops.size();
@@ -427,7 +504,31 @@ std::unique_ptr<Result> Query::finalize() {
                                  d_acc.as<u64>(), D, stream);
         CK(cudaStreamSynchronize(stream));
     }
-    if (small_state() && h_records.p && !import_dirty() && !kp.ndistinct) {
+    std::unique_ptr<Result> res(new Result());
+    res->nkeys = (int)keys.size();
+    res->naggs = (int)aggs.size();
+    res->agg_texts = agg_texts;
+    res->key_texts = key_texts;
+    res->alias = alias;
+    for (auto& k : keys) {
+        std::vector<std::string> path;
+        if (k->kind == EK::FIELD && k->col >= 0) path = table->cols[k->col].path;
+        res->key_paths.push_back(path);
+    }
+    const bool host_words = small_state() && h_records.p && !import_dirty() && !kp.ndistinct;
+    // Everything but the few-slot states is finalised ON THE DEVICE (k_finalize_groups): a scan of 10^9 rows leaves up
+    // to 10^6 groups, and ComputeFinal + key decoding of those on host cores took 17x the scan itself.
+    const bool on_device = !host_words && kp.mode != MODE_UNGROUPED && device_final_ok() && kp.dense_dom.empty();
+    if (on_device) {
+        PeerTables T;
+        memset(&T, 0, sizeof T);
+        T.n = 1;
+        T.acc[0] = d_acc.as<u64>();
+        ngroups = finalize_device(*res, T, 0, cap);
+        res->ngroups = ngroups;
+        phase("device finalize + D2H");
+    } else {
+    if (host_words) {
         // small state: the scan already published the table words to pinned host memory
         const u64* h = h_records.as<u64>();
         for (u64 i = 0; i < cap; ++i) {
@@ -453,18 +554,7 @@ std::unique_ptr<Result> Query::finalize() {
     }
 
     phase("distinct + export");
-    std::unique_ptr<Result> res(new Result());
-    res->nkeys = (int)keys.size();
-    res->naggs = (int)aggs.size();
     res->ngroups = ngroups;
-    res->agg_texts = agg_texts;
-    res->key_texts = key_texts;
-    res->alias = alias;
-    for (auto& k : keys) {
-        std::vector<std::string> path;
-        if (k->kind == EK::FIELD && k->col >= 0) path = table->cols[k->col].path;
-        res->key_paths.push_back(path);
-    }
     res->key_cls.resize((size_t)ngroups * res->nkeys);
     res->key_val.resize((size_t)ngroups * res->nkeys);
     res->agg_cls.resize((size_t)ngroups * res->naggs);
@@ -577,10 +667,14 @@ std::unique_ptr<Result> Query::finalize() {
             for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_INVALID, "%s", e.c_str());
         }
     }
-    {   // strings: (column, rank) references -> the result's own string table (it may outlive the table)
+    }  // host finalisation
+    bool any_string = false;  // can a key or an aggregate be a string at all?
+    for (auto& pc : kp.keys) any_string = any_string || (pc.mask & bit(C_STRING));
+    for (auto& ap : kp.aggs) any_string = any_string || ap.w_ms >= 0;
+    if (any_string) {   // strings: (column, rank) references -> the result's own string table (it may outlive the table)
         std::vector<std::vector<i64>> pool(table->cols.size());  // [column][rank] -> index in res->strings, -1 = not yet
         i64 empty_at = -1;
-        auto resolve = [&](std::vector<u8>& cls, std::vector<i64>& val) {
+        auto resolve = [&](FlatArr<u8>& cls, FlatArr<i64>& val) {
             for (size_t i = 0; i < cls.size(); ++i) {
                 if (cls[i] != C_STRING) continue;
                 const size_t col = (size_t)((u64)val[i] >> 40);

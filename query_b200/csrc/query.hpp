@@ -11,13 +11,31 @@
 
 namespace n1 {
 
+// A flat result array: owns its storage, or views a region of the result's pinned buffer (the device finalisation lands
+// there with one copy per array and nothing is copied again until n1gpu_result_fetch).
+template <class T> struct FlatArr {
+    std::vector<T> own;
+    T* p = nullptr;
+    size_t n = 0;
+    void resize(size_t k) { own.resize(k); p = own.data(); n = k; }
+    template <class U> void assign(const U* a, const U* b) { own.assign(a, b); p = own.data(); n = own.size(); }
+    void view(T* ptr, size_t k) { std::vector<T>().swap(own); p = ptr; n = k; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct Result {
     int nkeys = 0, naggs = 0;
     i64 ngroups = 0;
     // [ngroups][nkeys] / [ngroups][naggs] as class byte + 64-bit payload (int / float bits / index into `strings`):
     // flat arrays, so that a million-group result costs two allocations, not four million string-carrying objects
-    std::vector<u8> key_cls, agg_cls;
-    std::vector<i64> key_val, agg_val;
+    FlatArr<u8> key_cls, agg_cls;
+    FlatArr<i64> key_val, agg_val;
+    PinnedBuf pinned;  // backing store of the arrays when the groups were finalised on the device
     std::vector<std::string> strings;
     HValue value(u8 cls, i64 val) const {
         HValue v;
@@ -66,7 +84,7 @@ struct Query {
     u64 set_cap = 0;  // DISTINCT entry set capacity: hash slots, or bits when the set is a bitmap
     size_t set_bytes() const { return kp.set_bitmap ? (size_t)(set_cap >> 3) : (size_t)set_cap * (kp.set128 ? 16 : 8); }
     int set_kw() const { return kp.set_bitmap ? 4 : (kp.set128 ? 2 : 1); }  // how kernels.cu enumerates the set
-    DevBuf d_partials, d_acc, d_accum, d_keys, d_set, d_status, d_counts, d_records, d_drecords, d_ticket;
+    DevBuf d_partials, d_acc, d_accum, d_keys, d_set, d_status, d_counts, d_records, d_drecords, d_ticket, d_final;
     PinnedBuf h_status, h_counts, h_records, h_drecords;
     std::atomic<bool> cancelled{false};
     bool launched = false;
@@ -95,6 +113,11 @@ struct Query {
     void partial_reset();
     void partial_import(const void* dev_records, i64 n, const void* dev_distinct, i64 nd);
     std::unique_ptr<Result> finalize();
+    // FinalGroup on the device over slots [slot0, slot1) of `tables` (this rank's table, or every rank's, peer-mapped):
+    // fills res' flat arrays; returns the number of groups
+    i64 finalize_device(Result& res, const PeerTables& tables, u64 slot0, u64 slot1);
+    FinalDesc final_desc() const;
+    bool device_final_ok() const { return keys.size() <= 16 && aggs.size() <= 24 && kp.word_ops.size() <= 64 && table->cols.size() < 32768; }
     u64 dense_key(u64 slot) const;
     void rebind(Table* t);
 };
