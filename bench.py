@@ -199,13 +199,17 @@ def run_ours(args):
         sync_all()
         return maxrank(ev0.elapsed_time(ev1)), res
 
+    # one peer mailbox + arena per process: small states are merged by peer stores fused into the scan, direct-indexed
+    # tables are folded owner-sharded by the finalisation kernel over NVLink; NCCL only moves hash / DISTINCT records
+    mailbox = qd.make_mailbox(max_words=8192, arena_bytes=256 << 20) if world > 1 else None
+
     def make(w):
         """table + compiled chain + distributed wrapper of a workload, on torch's current stream"""
         t = w.sealed_table()
         qq = w.query(t)
         qq.set_stream(torch.cuda.current_stream().cuda_stream)
         qq.set_timing(True)
-        return t, qq, qd.DistributedQuery(qq)
+        return t, qq, qd.DistributedQuery(qq, stream=torch.cuda.current_stream(), mailbox=mailbox)
 
     def checked(w, dq, res):
         ref = w.reference()
@@ -340,7 +344,7 @@ def run_ours(args):
         t.seal()
         qq = q.Query(t, ALIAS, WHERE, KEYS, AGGS)
         ts.append(time.perf_counter())
-        dq = qd.DistributedQuery(qq)
+        dq = qd.DistributedQuery(qq, mailbox=mailbox if args.e2e_peer else None)
         r = dq.execute()
         ng = r.num_groups
         ts.append(time.perf_counter())
@@ -528,6 +532,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=16_000_000)
     ap.add_argument("--shred-threads", type=int, default=-1, help="-1: device shredder (shred.cu); >= 0: host threads (0 = all cores)")
+    ap.add_argument("--e2e-peer", type=int, default=1, help="0: the e2e steps merge with NCCL instead of the peer arena")
     ap.add_argument("--soak", type=float, default=1.0, help="seconds of untimed stepping before the timed region")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that print banners to fd 1 (NCCL's version line) are sent to

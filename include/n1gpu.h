@@ -218,7 +218,19 @@ int n1gpu_query_word_ops(const n1gpu_query* q, int* ops, int cap);
  * steps on a mailbox.  A peer that never delivers makes collect fail with N1GPU_E_CUDA after ~10 s.           */
 typedef struct n1gpu_mailbox n1gpu_mailbox;
 int n1gpu_mailbox_create(int nranks, int rank, int64_t max_words, n1gpu_mailbox** out);
+/* The same with an ARENA of arena_bytes behind the mailbox cells, mapped into every rank like the cells.  A query whose
+ * group table is direct-indexed in HBM (slot == packed key on every rank; no DISTINCT) places its table there when the
+ * mailbox is set on it (double-buffered: 2 x slots x words x 8 bytes; every rank must set its queries in the same order),
+ * and the Intermediate -> Final merge becomes owner-sharded and collective-free: each rank raises a flag in every peer's
+ * flag row when its scan is complete, and n1gpu_query_collect on rank r waits for all flags, then folds slot range r of
+ * EVERY rank's table with plain loads over NVLink while it finalises (ComputeFinal) exactly those groups - rank r's result
+ * holds its 1/nranks of the groups.  Replaces execution/group_intermediate.go:56-104 + group_final.go:55-118 across ranks. */
+int n1gpu_mailbox_create_arena(int nranks, int rank, int64_t max_words, int64_t arena_bytes, n1gpu_mailbox** out);
 int n1gpu_mailbox_ipc_handle(n1gpu_mailbox* mb, uint8_t handle[64]);
+/* In-process wiring (several ranks driven by one process, peer access enabled by the caller - or one device in tests):
+ * the device base pointer of rank `rank`'s mailbox buffer, instead of an IPC handle.                                   */
+int n1gpu_mailbox_set_peer(n1gpu_mailbox* mb, int rank, void* dev_base);
+void* n1gpu_mailbox_base(n1gpu_mailbox* mb);
 int n1gpu_mailbox_open_peers(n1gpu_mailbox* mb, const uint8_t* handles);
 int n1gpu_mailbox_free(n1gpu_mailbox* mb);
 int n1gpu_query_set_mailbox(n1gpu_query* q, n1gpu_mailbox* mb);

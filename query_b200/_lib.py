@@ -80,6 +80,9 @@ _SIGS = {
     "n1gpu_query_word_ops": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
     "n1gpu_query_merge_words": (C.c_int, [_P, _P, C.c_int]),
     "n1gpu_mailbox_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
+    "n1gpu_mailbox_create_arena": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    "n1gpu_mailbox_set_peer": (C.c_int, [_P, C.c_int, _P]),
+    "n1gpu_mailbox_base": (_P, [_P]),
     "n1gpu_mailbox_ipc_handle": (C.c_int, [_P, C.c_char_p]),
     "n1gpu_mailbox_open_peers": (C.c_int, [_P, C.c_char_p]),
     "n1gpu_mailbox_free": (C.c_int, [_P]),

@@ -455,12 +455,21 @@ class Query:
 
 
 class Mailbox:
-    """Peer mailbox for the fused small-state multi-GPU merge (n1gpu_mailbox_*)."""
+    """Peer mailbox for the fused small-state multi-GPU merge, optionally with an arena for peer-readable direct-indexed
+    group tables (owner-sharded, collective-free merge + finalisation): n1gpu_mailbox_*."""
 
-    def __init__(self, nranks, rank, max_words=8192):
+    def __init__(self, nranks, rank, max_words=8192, arena_bytes=0):
         self._h = C.c_void_p()
-        self.nranks, self.rank = nranks, rank
-        check(lib().n1gpu_mailbox_create(nranks, rank, max_words, C.byref(self._h)))
+        self.nranks, self.rank, self.arena_bytes = nranks, rank, int(arena_bytes)
+        check(lib().n1gpu_mailbox_create_arena(nranks, rank, max_words, int(arena_bytes), C.byref(self._h)))
+
+    @property
+    def base(self):
+        return lib().n1gpu_mailbox_base(self._h)
+
+    def set_peer(self, rank, dev_base):
+        """in-process wiring: the device base pointer of another rank's mailbox (same process)"""
+        check(lib().n1gpu_mailbox_set_peer(self._h, rank, C.c_void_p(dev_base)))
 
     def ipc_handle(self):
         buf = C.create_string_buffer(64)

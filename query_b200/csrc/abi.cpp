@@ -283,14 +283,20 @@ int n1gpu_query_free(n1gpu_query* q) { delete q; return N1GPU_OK; }
 // ---- peer mailbox (fused small-state all-gather over NVLink) ----------------------------------------------------
 struct n1gpu_mailbox { Mailbox m; };
 int n1gpu_mailbox_create(int nranks, int rank, int64_t max_words, n1gpu_mailbox** out) {
+    return n1gpu_mailbox_create_arena(nranks, rank, max_words, 0, out);
+}
+int n1gpu_mailbox_create_arena(int nranks, int rank, int64_t max_words, int64_t arena_bytes, n1gpu_mailbox** out) {
     return guard([&] {
         REQUIRE(out);
-        if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks || max_words < 1) N1_THROW(N1GPU_E_INVALID, "bad mailbox geometry");
+        if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks || max_words < 1 || arena_bytes < 0) N1_THROW(N1GPU_E_INVALID, "bad mailbox geometry");
         if (!have_device()) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
         std::unique_ptr<n1gpu_mailbox> mb(new n1gpu_mailbox());
         Mailbox& m = mb->m;
         m.nranks = nranks; m.rank = rank; m.stride = (u64)max_words + 1;
-        m.bytes = (size_t)m.slots * nranks * m.stride * 8;
+        m.flags_off = ((size_t)m.slots * nranks * m.stride * 8 + 255) & ~(size_t)255;
+        m.arena_off = (m.flags_off + (size_t)64 * nranks * 8 + 255) & ~(size_t)255;
+        m.arena_bytes = (size_t)arena_bytes;
+        m.bytes = m.arena_off + m.arena_bytes;
         CK(cudaMalloc(&m.base, m.bytes));
         CK(cudaMemset(m.base, 0, m.bytes));
         CK(cudaDeviceSynchronize());
@@ -324,13 +330,28 @@ int n1gpu_mailbox_open_peers(n1gpu_mailbox* mb, const uint8_t* handles) {
         CK(cudaMemcpy(m.d_peers.p, m.peers.data(), (size_t)m.nranks * 8, cudaMemcpyHostToDevice));
     });
 }
+int n1gpu_mailbox_set_peer(n1gpu_mailbox* mb, int rank, void* dev_base) {
+    return guard([&] {
+        REQUIRE(mb);
+        Mailbox& m = mb->m;
+        if (rank < 0 || rank >= m.nranks || !dev_base) N1_THROW(N1GPU_E_INVALID, "bad peer");
+        if (rank != m.rank) m.peers[(size_t)rank] = dev_base;
+        bool all = true;
+        for (void* p : m.peers) all = all && p;
+        if (all) {
+            m.d_peers.alloc((size_t)m.nranks * 8);
+            CK(cudaMemcpy(m.d_peers.p, m.peers.data(), (size_t)m.nranks * 8, cudaMemcpyHostToDevice));
+        }
+    });
+}
+void* n1gpu_mailbox_base(n1gpu_mailbox* mb) { return mb ? mb->m.base : nullptr; }
 int n1gpu_mailbox_free(n1gpu_mailbox* mb) { delete mb; return N1GPU_OK; }
 int n1gpu_query_set_mailbox(n1gpu_query* q, n1gpu_mailbox* mb) {
     return guard([&] {
         REQUIRE(q);
         if (q->q->launched) N1_THROW(N1GPU_E_INVALID, "a scan is outstanding");
         if (mb && mb->m.nranks > 1 && !mb->m.d_peers.p) N1_THROW(N1GPU_E_INVALID, "mailbox peers are not opened");
-        q->q->mailbox = mb ? &mb->m : nullptr;
+        q->q->attach_mailbox(mb ? &mb->m : nullptr);
     });
 }
 
@@ -367,7 +388,7 @@ int n1gpu_query_state_words(n1gpu_query* q, void** dev_words, int64_t* nwords) {
         if (!Q.kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
         if (!(Q.kp.mode == MODE_UNGROUPED || Q.kp.mode == MODE_DENSE) || Q.kp.ndistinct)
             N1_THROW(N1GPU_E_INVALID, "state_words is for ungrouped / dense chains without DISTINCT; use partial_export");
-        *dev_words = Q.d_acc.p;
+        *dev_words = Q.acc();
         *nwords = (int64_t)(Q.cap * (u64)Q.ops.n);
     });
 }
@@ -378,7 +399,7 @@ int n1gpu_query_merge_words(n1gpu_query* q, const void* dev_all_words, int nrank
         if (!Q.kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
         if (!(Q.kp.mode == MODE_UNGROUPED || Q.kp.mode == MODE_DENSE) || Q.kp.ndistinct) N1_THROW(N1GPU_E_INVALID, "not a small-state chain");
         if (nranks < 1) N1_THROW(N1GPU_E_INVALID, "nranks must be >= 1");
-        launch_merge_words((const u64*)dev_all_words, nranks, Q.cap, Q.ops, Q.d_acc.as<u64>(), Q.h_records.as<u64>(), Q.stream);
+        launch_merge_words((const u64*)dev_all_words, nranks, Q.cap, Q.ops, Q.acc(), Q.h_records.as<u64>(), Q.stream);
     });
 }
 int n1gpu_query_word_ops(const n1gpu_query* q, int* ops, int cap) {

@@ -340,6 +340,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                            const std::vector<ExprP>& aggs, const std::vector<std::string>& agg_texts,
                            double total_rows_bound) {
     KernelPlan kp;
+    // rows that layout decisions shared by all partitions are based on: the declared keyspace rows, else this table's
+    const i64 layout_rows = t.global_rows > 0 ? std::max(t.global_rows, t.nrows) : t.nrows;
     // ---- group key layout ------------------------------------------------------------------------------
     double est = 1;
     for (auto& k : keys) {
@@ -497,7 +499,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         // multi-GPU merge is element-wise (all_gather + k_merge_words, stream-ordered) instead of a record exchange.
         const char* nd = getenv("N1GPU_NO_DIRECT");
         const double slots = kp.key_bits <= 22 ? (double)((i64)1 << kp.key_bits) : 1e30;
-        if (!(nd && *nd == '1') && slots * W * 8 <= 256.0 * 1024 * 1024 && slots <= 8.0 * std::max<double>((double)t.nrows, 131072.0)) {
+        // (every partition must take the same decision - their states are merged slot by slot - so it is based on the rows
+        // of the whole keyspace when they are declared, never on this partition's own share)
+        if (!(nd && *nd == '1') && slots * W * 8 <= 256.0 * 1024 * 1024 && slots <= 8.0 * std::max<double>((double)layout_rows, 131072.0)) {
             kp.mode = MODE_DENSE;
             kp.dense_global = true;
             kp.dense_slots = (i64)1 << kp.key_bits;
@@ -603,7 +607,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         // Chosen when the bitmap is no larger than the hash set would be.
         const char* nb = getenv("N1GPU_NO_BITMAP");
         const double bitmap_bytes = kp.entry_bits <= 36 ? (double)((u64)1 << kp.entry_bits) / 8.0 : 1e30;
-        kp.set_bitmap = !(nb && *nb == '1') && bitmap_bytes <= std::max(65536.0, 16.0 * (double)std::max<i64>(t.nrows, 1) * kp.ndistinct);
+        kp.set_bitmap = !(nb && *nb == '1') && bitmap_bytes <= std::max(65536.0, 16.0 * (double)std::max<i64>(layout_rows, 1) * kp.ndistinct);
         // A bitmap the size of the L2 (config 4: 128 MiB) turns every row into a random DRAM sector read-modify-write.
         // The scan then runs in passes over slices of the entry range small enough to stay L2-resident: the columns
         // are streamed once per pass (cheap next to random DRAM), the bits land in L2.

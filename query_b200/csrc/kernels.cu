@@ -299,8 +299,8 @@ __global__ void __launch_bounds__(256) k_finalize_groups(const FinalDesc D, int 
         }
         if (live) {
             for (int P = 0; P < D.PW; ++P) {
-                u64 v = T.acc[0][(u64)P * ws + i * ss];
-                for (int t = 1; t < T.n; ++t) v = word_combine(ops.op[P], v, T.acc[t][(u64)P * ws + i * ss]);
+                u64 v = __ldcg(&T.acc[0][(u64)P * ws + i * ss]);
+                for (int t = 1; t < T.n; ++t) v = word_combine(ops.op[P], v, __ldcg(&T.acc[t][(u64)P * ws + i * ss]));
                 pw[P] = v;
             }
             if (kw == 0) {  // direct-indexed: a slot holds a group iff its row counter (logical word 0) is not zero
@@ -412,9 +412,40 @@ void launch_distinct_finalize(const u64* set_keys, u64 set_cap, int set128, int 
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }
+// One block: returns once every rank's flag of this step has arrived (acquire at system scope; bounded spin -> status 3).
+// A kernel of its own, so that the only thing that ever spins on a GPU is one block - the finalisation that follows it in
+// stream order starts with the tables complete and visible.
+__global__ void k_peer_wait(const u64* flags, int nranks, u64 seq, int* status) {
+    if ((int)threadIdx.x < nranks) {
+        u64 v = 0;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v == seq) break;
+            if (clock64() - t0 > 20000000000LL) { status[0] = 3; break; }  // ~10 s: a peer never arrived
+            __nanosleep(200);
+        }
+    }
+}
+__global__ void k_peer_signal(u64* const* peers, int nranks, int rank, u64 flags_word_off, u64 seq) {
+    if ((int)threadIdx.x < nranks) {
+        __threadfence_system();
+        u64* flag = peers[threadIdx.x] + flags_word_off + (seq % 64) * (u64)nranks + (u64)rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    }
+}
+void launch_peer_signal(u64* const* peers, int nranks, int rank, u64 flags_word_off, u64 seq, cudaStream_t s) {
+    k_peer_signal<<<1, 64, 0, s>>>(peers, nranks, rank, flags_word_off, seq);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
 void launch_finalize_groups(const FinalDesc& D, int kw, const u64* keys, const PeerTables& T, const OpsArr& ops, u64 ws, u64 ss, u64 slot0,
                             u64 slot1, unsigned long long* counter, u64 out_cap, u8* key_cls, i64* key_val, u8* agg_cls, i64* agg_val,
                             cudaStream_t s) {
+    if (T.wait_flags) {
+        k_peer_wait<<<1, 32, 0, s>>>(T.wait_flags, T.n, T.wait_seq, T.status);
+        g_launches.fetch_add(1);
+    }
     if (slot1 <= slot0) return;
     k_finalize_groups<<<grid_for(slot1 - slot0), 256, 0, s>>>(D, kw, keys, T, ops, ws, ss, slot0, slot1, counter, out_cap, key_cls, key_val,
                                                               agg_cls, agg_val);

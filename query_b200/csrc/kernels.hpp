@@ -46,7 +46,14 @@ struct FinalDesc {
 struct PeerTables {
     int n;
     const u64* acc[16];
+    // peer merge only: a one-block kernel ahead of the finalisation waits until wait_flags[r] == wait_seq for all r < n (the
+    // ranks' scans of this step are complete and visible); a peer that never arrives sets status[0] = 3 after ~10 s
+    const u64* wait_flags;
+    u64 wait_seq;
+    int* status;
 };
+// Raises this rank's flag of step `seq` in every rank's flag row: peers[r][flags_word_off + (seq % 64) * nranks + rank] = seq.
+void launch_peer_signal(u64* const* peers, int nranks, int rank, u64 flags_word_off, u64 seq, cudaStream_t s);
 // Finalises the live groups of slots [slot0, slot1) into compact flat arrays (n1gpu_result_fetch layout); *counter
 // (zeroed by the caller) ends as the number of groups written; groups beyond out_cap are counted but not written.
 void launch_finalize_groups(const FinalDesc& D, int kw, const u64* keys, const PeerTables& T, const OpsArr& ops, u64 ws, u64 ss, u64 slot0,

@@ -54,6 +54,8 @@ bool have_device() {
 }
 
 Query::~Query() {
+    if (launched && stream) cudaStreamSynchronize(stream);  // nothing of this query may still be running when its buffers are recycled
+    if (peer_table && mailbox) { mailbox->arena_free(peer_off[1], peer_bytes); mailbox->arena_free(peer_off[0], peer_bytes); }
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -155,6 +157,21 @@ void Query::alloc_state() {
 
 bool Query::uses_status() const { return kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128 || kp.ndistinct > 0 || mailbox != nullptr; }
 
+void Query::attach_mailbox(Mailbox* mb) {
+    if (launched) N1_THROW(N1GPU_E_INVALID, "a scan is outstanding");
+    if (peer_table && mailbox) { mailbox->arena_free(peer_off[1], peer_bytes); mailbox->arena_free(peer_off[0], peer_bytes); }
+    mailbox = mb;
+    peer_table = false;
+    peer_seq = 0;
+    // a direct-indexed table (slot == packed key on every rank) moves into the arena: peers fold it slot range by slot range
+    if (mb && mb->arena_bytes && kp.mode == MODE_DENSE && kp.dense_global && kp.ndistinct == 0 && device_final_ok()) {
+        peer_bytes = (size_t)cap * ops.n * 8;
+        peer_off[0] = mb->arena_alloc(peer_bytes);
+        peer_off[1] = mb->arena_alloc(peer_bytes);
+        peer_table = true;
+    }
+}
+
 Mailbox::~Mailbox() {
     for (int r = 0; r < (int)peers.size(); ++r)
         if (r != rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
@@ -163,7 +180,7 @@ Mailbox::~Mailbox() {
 
 void Query::reset_state() {
     if (uses_status()) CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
-    if (kp.mode != MODE_UNGROUPED) launch_init_words(d_acc.as<u64>(), cap, ops, stream);
+    if (kp.mode != MODE_UNGROUPED) launch_init_words(acc(), cap, ops, stream);
     if (kp.mode == MODE_HASH64 || kp.mode == MODE_HASH128) CK(cudaMemsetAsync(d_keys.p, 0xff, (size_t)cap * (kp.mode == MODE_HASH128 ? 16 : 8), stream));
     if (kp.ndistinct) CK(cudaMemsetAsync(d_set.p, kp.set_bitmap ? 0 : 0xff, set_bytes(), stream));
 }
@@ -172,10 +189,11 @@ void Query::launch_scan() {
     if (!kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device: libn1gpu has no CPU fallback");
     if (launched) N1_THROW(N1GPU_E_INVALID, "a scan is already outstanding on this query");
     launches_at_start = g_launches.load();
+    if (peer_table) peer_seq = ++mailbox->seq;  // the step number also selects the table buffer of this step (acc())
     NqParamsHost p{};
     p.nrows = table->nrows;
     for (size_t c = 0; c < table->cols.size(); ++c) { p.col[c] = table->cols[c].d_payload.p; p.tag[c] = table->cols[c].d_tags.as<u8>(); }
-    p.acc = kp.mode == MODE_UNGROUPED ? d_accum.as<u64>() : d_acc.as<u64>();
+    p.acc = kp.mode == MODE_UNGROUPED ? d_accum.as<u64>() : acc();
     p.partials = d_partials.as<u64>();
     p.keys = d_keys.as<u64>();
     p.cap_mask = cap - 1;
@@ -183,7 +201,7 @@ void Query::launch_scan() {
     p.set_mask = set_cap ? set_cap - 1 : 0;
     p.status = d_status.as<int>();
     p.dense_groups = (u64)kp.dense_slots;
-    p.final_dev = d_acc.as<u64>();
+    p.final_dev = acc();
     p.final_host = h_records.as<u64>();  // pinned memory is device-addressable under UVA: zero-copy result
     p.ticket = d_ticket.as<unsigned>();
     const bool small = small_state() && kp.ndistinct == 0;
@@ -214,9 +232,11 @@ void Query::launch_scan() {
     }
     if (timing) CK(cudaEventRecord(ev1, stream));
     timed_launch = timing;
+    if (peer_merge())  // this rank's table of step peer_seq is complete: tell every peer (stores over NVLink, release at system scope)
+        launch_peer_signal((u64* const*)mailbox->d_peers.p, mailbox->nranks, mailbox->rank, mailbox->flags_off / 8, peer_seq, stream);
     if (mb_seq)  // receive side of the fused all-gather: fold every rank's words once they have landed
         launch_merge_mailbox((const u64*)mailbox->base, mailbox->nranks, mb_slot_base, mailbox->stride, cap * (u64)ops.n, mb_seq, cap, ops,
-                             d_acc.as<u64>(), h_records.as<u64>(), d_status.as<int>(), stream);
+                             acc(), h_records.as<u64>(), d_status.as<int>(), stream);
     if (uses_status()) CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
     launched = true;
     ungrouped_live = true;
@@ -279,7 +299,7 @@ static void count_and_export(Query& q, int kw, const u64* keys, const u64* acc, 
 
 void Query::partial_counts(i64* ngroups, i64* ndistinct) {
     i64 c[1] = {0};
-    count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, ops.n, 1, 0, std::max(kp.key_bits, 0), nullptr, 0, c);
+    count_and_export(*this, kw(), d_keys.as<u64>(), acc(), cap, ops.n, 1, 0, std::max(kp.key_bits, 0), nullptr, 0, c);
     if (kp.mode == MODE_UNGROUPED && !ungrouped_live) c[0] = 0;
     *ngroups = c[0];
     i64 d[1] = {0};
@@ -288,7 +308,7 @@ void Query::partial_counts(i64* ngroups, i64* ndistinct) {
 }
 
 void Query::partial_export(int nranks, void* dev_records, i64 cap_records, i64* counts, void* dev_distinct, i64 cap_distinct, i64* dcounts) {
-    count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, ops.n, nranks, 0, kp.key_bits, (u64*)dev_records, cap_records, counts);
+    count_and_export(*this, kw(), d_keys.as<u64>(), acc(), cap, ops.n, nranks, 0, kp.key_bits, (u64*)dev_records, cap_records, counts);
     if (kp.ndistinct)
         count_and_export(*this, set_kw(), d_set.as<u64>(), nullptr, set_cap, 0, nranks, kp.abits, kp.key_bits, (u64*)dev_distinct, cap_distinct, dcounts);
     else for (int r = 0; r < nranks; ++r) dcounts[r] = 0;
@@ -297,7 +317,7 @@ void Query::partial_export(int nranks, void* dev_records, i64 cap_records, i64* 
 void Query::partial_reset() {
     if (!kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device");
     reset_state();
-    if (kp.mode == MODE_UNGROUPED) launch_init_words(d_acc.as<u64>(), cap, ops, stream);
+    if (kp.mode == MODE_UNGROUPED) launch_init_words(acc(), cap, ops, stream);
     CK(cudaStreamSynchronize(stream));
     ungrouped_live = false;
     host_acc_valid = false;
@@ -308,7 +328,7 @@ void Query::partial_import(const void* dev_records, i64 n, const void* dev_disti
     host_acc_valid = false;
     for (;;) {
         CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
-        if (n > 0) launch_merge_records(kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, ops, (const u64*)dev_records, (u64)n, d_status.as<int>(), stream);
+        if (n > 0) launch_merge_records(kw(), d_keys.as<u64>(), acc(), cap, ops, (const u64*)dev_records, (u64)n, d_status.as<int>(), stream);
         if (nd > 0) {
             OpsArr none{};
             none.n = 0;
@@ -442,7 +462,7 @@ i64 Query::finalize_device(Result& res, const PeerTables& tables, u64 slot0, u64
     if (span * per_group > ((size_t)256 << 20) && tables.n == 1) {
         i64 c[1] = {0};
         CK(cudaMemsetAsync(d_counts.p, 0, 64, stream));
-        launch_count_owners(kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, 1, 0, std::max(kp.key_bits, 0), counter, stream);
+        launch_count_owners(kw(), d_keys.as<u64>(), acc(), cap, 1, 0, std::max(kp.key_bits, 0), counter, stream);
         CK(cudaMemcpyAsync(h_counts.p, d_counts.p, 8, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         c[0] = (i64)h_counts.as<unsigned long long>()[0];
@@ -459,6 +479,10 @@ i64 Query::finalize_device(Result& res, const PeerTables& tables, u64 slot0, u64
     CK(cudaMemcpyAsync(h_counts.p, d_counts.p, 8, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     const u64 ng = h_counts.as<unsigned long long>()[0];
+    if (tables.wait_flags) {
+        CK(cudaMemcpy(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost));
+        if (h_status.as<int>()[0] == 3) N1_THROW(N1GPU_E_CUDA, "multi-GPU merge timed out: a peer rank never signalled its partial table");
+    }
     if (ng > out_cap) N1_THROW(N1GPU_E_INVALID, "finalisation found %llu groups in a table counted at %llu", (unsigned long long)ng, (unsigned long long)out_cap);
     const size_t h_kc = 0, h_ac = h_kc + up8(ng * nk), h_kv = h_ac + up8(ng * na), h_av = h_kv + ng * nk * 8;
     res.pinned.ensure(std::max<size_t>(h_av + ng * na * 8, 64));
@@ -498,10 +522,10 @@ std::unique_ptr<Result> Query::finalize() {
             d.nfree = ap.dcomp.nfree;
             for (int k = 0; k < 8; ++k) d.classes[k] = k < (int)ap.dcomp.classes.size() ? ap.dcomp.classes[k] : C_MISSING;
             for (int w : {ap.w_cnt, ap.w_ilo, ap.w_ihi, ap.w_neg, ap.w_fsum, ap.w_nflt})
-                if (w >= 0) launch_fill_u64(d_acc.as<u64>() + (u64)w * cap, cap, 0, stream);  // idempotent finalize
+                if (w >= 0) launch_fill_u64(acc() + (u64)w * cap, cap, 0, stream);  // idempotent finalize
         }
         launch_distinct_finalize(d_set.as<u64>(), set_cap, kp.set_bitmap ? 2 : (kp.set128 ? 1 : 0), kp.abits, kp.key_bits, kw(), d_keys.as<u64>(), cap,
-                                 d_acc.as<u64>(), D, stream);
+                                 acc(), D, stream);
         CK(cudaStreamSynchronize(stream));
     }
     std::unique_ptr<Result> res(new Result());
@@ -523,8 +547,19 @@ std::unique_ptr<Result> Query::finalize() {
         PeerTables T;
         memset(&T, 0, sizeof T);
         T.n = 1;
-        T.acc[0] = d_acc.as<u64>();
-        ngroups = finalize_device(*res, T, 0, cap);
+        T.acc[0] = acc();
+        u64 s0 = 0, s1 = cap;
+        if (peer_merge() && peer_seq) {
+            // IntermediateGroup + FinalGroup fused and owner-sharded: this rank folds ITS slot range of every rank's table
+            T.n = mailbox->nranks;
+            for (int r = 0; r < T.n; ++r) T.acc[r] = (const u64*)((const char*)mailbox->peers[(size_t)r] + peer_off[peer_seq & 1]);
+            s0 = cap * (u64)mailbox->rank / (u64)T.n;
+            s1 = cap * (u64)(mailbox->rank + 1) / (u64)T.n;
+            T.wait_flags = (const u64*)((const char*)mailbox->base + mailbox->flags_off) + (peer_seq % 64) * (u64)T.n;
+            T.wait_seq = peer_seq;
+            T.status = d_status.as<int>();
+        }
+        ngroups = finalize_device(*res, T, s0, s1);
         res->ngroups = ngroups;
         phase("device finalize + D2H");
     } else {
@@ -540,13 +575,13 @@ std::unique_ptr<Result> Query::finalize() {
         }
     } else {
         i64 c[1];
-        count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, W, 1, 0, kp.key_bits, nullptr, 0, c);
+        count_and_export(*this, kw(), d_keys.as<u64>(), acc(), cap, W, 1, 0, kp.key_bits, nullptr, 0, c);
         if (kp.mode == MODE_UNGROUPED && !ungrouped_live) c[0] = 0;
         ngroups = c[0];
         if (ngroups) {
             d_records.ensure((size_t)ngroups * rw * 8);
             i64 c2[1];
-            count_and_export(*this, kw(), d_keys.as<u64>(), d_acc.as<u64>(), cap, W, 1, 0, kp.key_bits, d_records.as<u64>(), ngroups, c2);
+            count_and_export(*this, kw(), d_keys.as<u64>(), acc(), cap, W, 1, 0, kp.key_bits, d_records.as<u64>(), ngroups, c2);
             recs.resize((size_t)ngroups * rw);
             CK(cudaMemcpy(recs.data(), d_records.p, recs.size() * 8, cudaMemcpyDeviceToHost));
             if (!kp.dense_dom.empty()) for (i64 g = 0; g < ngroups; ++g) recs[(size_t)g * rw] = dense_key(recs[(size_t)g * rw]);

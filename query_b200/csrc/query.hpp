@@ -1,6 +1,7 @@
 // query.hpp — a compiled Filter + InitialGroup/IntermediateGroup/FinalGroup chain bound to a table.
 #pragma once
 #include <atomic>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -54,11 +55,32 @@ struct Result {
 // Peer mailbox for the fused small-state all-gather: every rank owns slots x nranks cells of (stride) words in
 // HBM, exported to the other ranks' processes through CUDA IPC; scan kernels store into the peers' cells over
 // NVLink, k_merge_mailbox folds the own mailbox.
+//
+// The same IPC-mapped buffer can carry an ARENA behind the mailbox cells: direct-indexed HBM group tables are placed
+// there (double-buffered), so that every rank can read every other rank's partial table with plain loads over NVLink.
+// The owner-sharded merge + finalisation (k_finalize_groups over PeerTables) then replaces the collective: a rank raises
+// a flag in every peer's flag row when its scan is complete (k_peer_signal), and rank r's finalisation kernel waits for
+// all flags of the step before it folds slot range r of all tables.  Layout: [cells | flags 64 x nranks | arena].
 struct Mailbox {
     int nranks = 1, rank = 0, slots = 64;
     u64 stride = 0;              // words per cell = max_words + 1 (sequence flag)
     void* base = nullptr;        // own buffer (plain cudaMalloc: IPC-exported, never pooled)
     size_t bytes = 0;
+    size_t flags_off = 0;        // byte offset of the step flags (64 slots x nranks u64)
+    size_t arena_off = 0, arena_bytes = 0, arena_used = 0;
+    // bump allocation with exact-size recycling; every rank must set / free its peer-table queries in the same order
+    // (same sizes -> same offsets on every rank)
+    std::map<size_t, std::vector<size_t>> arena_bins;
+    void arena_free(size_t at, size_t n) { arena_bins[(n + 255) & ~(size_t)255].push_back(at); }
+    size_t arena_alloc(size_t n) {
+        n = (n + 255) & ~(size_t)255;
+        auto it = arena_bins.find(n);
+        if (it != arena_bins.end() && !it->second.empty()) { const size_t at = it->second.back(); it->second.pop_back(); return at; }
+        if (arena_used + n > arena_bytes) N1_THROW(N1GPU_E_NOMEM, "peer arena of %zu bytes is exhausted (%zu used, %zu wanted)", arena_bytes, arena_used, n);
+        const size_t at = arena_off + arena_used;
+        arena_used += n;
+        return at;
+    }
     std::vector<void*> peers;    // [nranks], own entry = base
     DevBuf d_peers;              // the same pointers in device memory
     u64 seq = 0;
@@ -93,6 +115,16 @@ struct Query {
     bool ungrouped_live = true;
     bool host_acc_valid = false;  // h_records holds the table words of the last scan (small-state modes)
     bool import_dirty() const { return !host_acc_valid; }
+    // direct-indexed table kept in the mailbox arena (peer-readable), double-buffered by step parity
+    bool peer_table = false;
+    size_t peer_off[2] = {0, 0}, peer_bytes = 0;
+    u64 peer_seq = 0;            // step whose table the next finalisation folds (0: none outstanding)
+    u64* acc() const {           // the group table of the current step
+        if (peer_table) return (u64*)((char*)mailbox->base + peer_off[peer_seq & 1]);
+        return d_acc.as<u64>();
+    }
+    bool peer_merge() const { return peer_table && mailbox && mailbox->nranks > 1; }
+    void attach_mailbox(Mailbox* mb);
     double last_scan_ms = 0;
     u64 launches_at_start = 0;
 

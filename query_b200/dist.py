@@ -79,6 +79,22 @@ def gather_all(records: torch.Tensor, count: int, words_per_record: int, group=N
     return torch.cat(parts) if parts else out[:0], cs
 
 
+def _merged_stats(allst, ndict):
+    """the union of per-partition column statistics (n1gpu_table_stats_get layout)"""
+    g = np.array(allst[0], dtype=np.int64)
+    has = [s[1] != 0 for s in allst]
+    g[0] = int(np.bitwise_or.reduce([s[0] for s in allst]))
+    g[1] = int(any(has))
+    mins = [s[2] for s, h in zip(allst, has) if h]
+    maxs = [s[3] for s, h in zip(allst, has) if h]
+    g[2] = min(mins) if mins else 0
+    g[3] = max(maxs) if maxs else 0
+    g[4] = int(any(s[4] != 0 for s in allst))
+    g[5] = ndict
+    g[7] = sum(s[7] for s in allst)  # MISSING / NULL rows of the whole keyspace
+    return g
+
+
 def agree_dictionaries_and_stats(table, group=None):
     """Before seal: merge every column's dictionary across ranks into the global sorted dictionary and take
     the union of the statistics, so that all ranks compile the same kernel and pack keys identically."""
@@ -97,30 +113,35 @@ def agree_dictionaries_and_stats(table, group=None):
         st = table.stats(c)
         allst = [None] * w
         dist.all_gather_object(allst, st.tolist(), group=group)
-        g = np.array(allst[0], dtype=np.int64)
-        has = [s[1] != 0 for s in allst]
-        g[0] = int(np.bitwise_or.reduce([s[0] for s in allst]))
-        g[1] = int(any(has))
-        mins = [s[2] for s, h in zip(allst, has) if h]
-        maxs = [s[3] for s, h in zip(allst, has) if h]
-        g[2] = min(mins) if mins else 0
-        g[3] = max(maxs) if maxs else 0
-        g[4] = int(any(s[4] != 0 for s in allst))
-        g[5] = len(merged)
-        g[7] = sum(s[7] for s in allst)  # MISSING / NULL rows of the whole keyspace
         if merged != list(local):  # identical dictionaries (e.g. handed in with the columns): nothing to remap
             table.import_dictionary(c, merged)
-        table.set_stats(c, g)
+        table.set_stats(c, _merged_stats(allst, len(merged)))
 
 
-def make_mailbox(max_words=8192, group=None):
-    """Creates this rank's peer mailbox and wires it to every other rank's (CUDA IPC handles exchanged through
-    torch.distributed).  Returns None for a single rank."""
+def agree_local(tables):
+    """The same agreement between the partitions of one keyspace held by ONE process (several ranks driven in-process)."""
+    total = sum(int(t.num_rows) for t in tables)
+    for t in tables:
+        t.set_global_rows(total)
+    for c in range(len(tables[0].columns)):
+        dicts = [t.dictionary(c) for t in tables]
+        merged = sorted(set().union(*[set(d) for d in dicts]))
+        allst = [t.stats(c).tolist() for t in tables]
+        g = _merged_stats(allst, len(merged))
+        for t, d in zip(tables, dicts):
+            if merged != list(d):
+                t.import_dictionary(c, merged)
+            t.set_stats(c, g)
+
+
+def make_mailbox(max_words=8192, group=None, arena_bytes=64 << 20):
+    """Creates this rank's peer mailbox (+ arena for peer-readable direct-indexed group tables) and wires it to every
+    other rank's (CUDA IPC handles exchanged through torch.distributed).  Returns None for a single rank."""
     from .api import Mailbox
     w = world()
     if w == 1:
         return None
-    mb = Mailbox(w, rank(), max_words)
+    mb = Mailbox(w, rank(), max_words, arena_bytes)
     handles = [None] * w
     dist.all_gather_object(handles, mb.ipc_handle(), group=group)
     mb.open_peers(handles)
@@ -149,10 +170,25 @@ class DistributedQuery:
         # slot == group key on every rank (one slot / dense table / direct-indexed HBM table): the merge is element-wise
         self.small = query.info["mode"] in ("ungrouped", "dense-shared-memory", "hbm-direct") and "distinct" not in " ".join(query.aggregates)
         # with a peer mailbox the merge of a small-state chain is fused into the scan: launch()/collect() only
-        # (a direct-indexed HBM table is megabytes: it takes the all_gather + merge-kernel path)
         self.fused = bool(mailbox is not None and self.small and world() > 1 and query.info["mode"] != "hbm-direct")
-        if self.fused:
+        # a direct-indexed HBM table (megabytes, slot == key on every rank) lives in the mailbox arena: every rank folds and
+        # finalises its slot range of all ranks' tables over NVLink - no collective, no replicated finalisation
+        self.peer = bool(mailbox is not None and getattr(mailbox, "arena_bytes", 0) and self.small and world() > 1
+                         and query.info["mode"] == "hbm-direct")
+        if world() > 1:
+            # ranks whose kernels differ (a layout threshold crossed on one rank only) would enter different collectives and
+            # merge slot-indexed words with hashed records: refuse that here, where it is an error message and not a hang
+            import hashlib
+            mine = (query.info["mode"], tuple(query.word_ops()), hashlib.sha1(query.kernel_source.encode()).hexdigest())
+            every = [None] * world()
+            dist.all_gather_object(every, mine, group=group)
+            if any(e != every[0] for e in every):
+                raise RuntimeError("ranks compiled different kernels for one chain (declare the keyspace rows and agree the "
+                                   "statistics before seal: agree_dictionaries_and_stats): %r" % ([e[:2] for e in every],))
+        if self.fused or self.peer:
             query.set_mailbox(mailbox)
+        if self.peer:
+            self.small = False  # the result is owner-sharded, not replicated
         elif self.small and world() > 1 and stream is None:
             # the NCCL all_gather is ordered against torch's current stream: the scan must run on that stream too
             query.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -172,6 +208,9 @@ class DistributedQuery:
     def describe(self):
         if world() == 1:
             return "none (one rank)"
+        if self.peer:
+            return ("owner-sharded and collective-free: direct-indexed tables in a CUDA-IPC peer arena, a release flag per rank and step, "
+                    "rank r's k_finalize_groups folds slot range r of every rank's table over NVLink and finalises those groups")
         if self.fused:
             return "fused into nq_scan: peer stores over NVLink into every rank's mailbox + 1-block fold"
         if self.small and self.q.info["mode"] == "hbm-direct":
@@ -183,9 +222,11 @@ class DistributedQuery:
     def launch(self):
         q = self.q
         w = world()
-        if w == 1 or not self.small:
-            if w == 1:
-                q.launch()
+        if w == 1 or self.peer:
+            q.launch()   # peer: the flag that publishes this rank's table is enqueued behind the scan by the library
+            self._launched = True
+            return
+        if not self.small:
             self._launched = True
             return
         q.launch()
@@ -232,7 +273,7 @@ class DistributedQuery:
 
     def collect(self):
         self._launched = False
-        if world() == 1 or self.small:
+        if world() == 1 or self.small or self.peer:
             return self.q.collect()
         return self.execute()
 
@@ -248,7 +289,7 @@ class DistributedQuery:
         """Returns a Result holding this rank's share of the groups (small state: rank 0 holds all, others none)."""
         q = self.q
         w = world()
-        if w > 1 and self.small:
+        if w > 1 and (self.small or self.peer):
             self.launch()
             return self.q.collect()
         q.scan_partial()

@@ -115,3 +115,36 @@ QUERIES = [
     ("const_const_compare", "((1 < 2) and (\"a\" < \"b\"))", [], ["count(*)"]),
 ]
 # max("z" < s) applies MAX to a boolean expression; keep it: MIN/MAX collate any type.
+
+
+def config5_docs(n, vocab, seed):
+    """BASELINE config 5 shape at oracle size: Zipf(1.1) string keys, 10 % MISSING + 10 % null on k and on v"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    w = np.arange(1, vocab + 1, dtype=np.float64) ** -1.1
+    ranks = rng.choice(vocab, size=n, p=w / w.sum())
+    perm = rng.permutation(vocab)
+    docs = []
+    for i in range(n):
+        parts = []
+        r = rng.integers(0, 10)
+        if r == 1:
+            parts.append('"k": null')
+        elif r > 1:
+            parts.append('"k": "w%05d"' % perm[ranks[i]])
+        r = rng.integers(0, 10)
+        if r == 1:
+            parts.append('"v": null')
+        elif r > 1:
+            parts.append('"v": %d' % rng.integers(-1000, 1000000))
+        docs.append("{" + ", ".join(parts) + "}")
+    return docs
+
+
+def config4_docs(n, groups, seed):
+    """BASELINE config 4 shape at oracle size: many groups, few distinct values per group"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, groups, n)
+    x = rng.integers(0, 1000, n)
+    return ['{"g": %d, "x": %d, "y": %.3f}' % (g[i], x[i], rng.random() * 1000) for i in range(n)]

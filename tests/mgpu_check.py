@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import query_b200 as q  # noqa: E402
-from gen_n1 import QUERIES, make_docs  # noqa: E402
+from gen_n1 import QUERIES, config4_docs, config5_docs, make_docs  # noqa: E402
 from query_b200 import dist as qd  # noqa: E402
 from util_n1 import assert_same, gpu_rows, make_table, oracle_rows  # noqa: E402
 
@@ -67,6 +67,39 @@ def main():
                             got[kk] = v
                     assert_same(exp, got, "%s [%s, %d ranks]" % (name, strategy, world))
             checked += 1
+    # BASELINE config 5 and config 4 shapes: a direct-indexed table merged owner-sharded through the peer arena (and through
+    # NCCL without it), and a 1 M-group-shaped COUNT / SUM DISTINCT whose entries travel to the owner of their group
+    shaped = [("config5 shape", config5_docs(16000, 3000, 23), "((`d`.`v`) is not missing)", ["(`d`.`k`)"],
+               ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))", "avg((`d`.`v`))"], "hbm-direct"),
+              ("config4 shape", config4_docs(16000, 40000, 29), None, ["(`d`.`g`)"],
+               ["count(distinct (`d`.`x`))", "sum(distinct (`d`.`x`))", "count(*)"], None)]
+    for name, sdocs, where, keys, aggs, mode in shaped:
+        lo, hi = qd.row_range(len(sdocs))
+        exp = oracle_rows(sdocs, "d", where, keys, aggs) if rank == 0 else None
+        for strategy in ("peer", "nccl"):
+            t = make_table(sdocs[lo:hi], where, keys, aggs)
+            qd.agree_dictionaries_and_stats(t)
+            t.seal()
+            qq = q.Query(t, "d", where, keys, aggs)
+            assert mode is None or qq.info["mode"] == mode, qq.info
+            dq = qd.DistributedQuery(qq, mailbox=mailbox if strategy == "peer" else None)
+            for step in range(3):  # both table buffers of the arena, and their reuse
+                res = dq.execute()
+            part = gpu_rows(res, aggs)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, {json.dumps(k): v for k, v in part.items()})
+            if rank == 0:
+                got = {}
+                for i, g in enumerate(gathered):
+                    if dq.replicated and i:
+                        continue
+                    for k, v in g.items():
+                        kk = tuple(json.loads(k))
+                        assert kk not in got, "group %r finalised by two ranks (%s, %s)" % (kk, name, strategy)
+                        got[kk] = v
+                assert_same(exp, got, "%s [%s, %d ranks]" % (name, strategy, world))
+            checked += 1
+            del dq, qq, t
     # pipelined fused steps on several streams: results stay correct and ordered
     name, where, keys, aggs = QUERIES[0]
     t = make_table(mine, where, keys, aggs)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import query_b200 as q
-from gen_n1 import QUERIES, F, make_docs
+from gen_n1 import QUERIES, F, config5_docs, make_docs
 from golden_plans import CASES, WHERE_CASES, _MISSING, keyspaces, normalise
 from plans_n1 import distinct_plan, explain_plan
 from util_n1 import assert_same, gpu_rows, make_table, oracle_rows, run_both, write_keyspace
@@ -127,27 +127,46 @@ def test_skewed_string_keys_with_missing_and_null(block, monkeypatch):
     the front cache holds (misses take the table path), both block shapes; bit-exact against the oracle."""
     monkeypatch.setenv("N1GPU_CACHE_BLOCK", block)
     monkeypatch.setenv("N1GPU_CACHE_KB", "2")  # a 2 KiB cache: most of the 3 000 keys miss
-    rng = np.random.default_rng(11)
-    n, vocab = 20000, 3000
-    w = np.arange(1, vocab + 1, dtype=np.float64) ** -1.1
-    ranks = rng.choice(vocab, size=n, p=w / w.sum())
-    perm = rng.permutation(vocab)
-    docs = []
-    for i in range(n):
-        parts = []
-        r = rng.integers(0, 10)
-        if r == 1:
-            parts.append('"k": null')
-        elif r > 1:
-            parts.append('"k": "w%05d"' % perm[ranks[i]])
-        r = rng.integers(0, 10)
-        if r == 1:
-            parts.append('"v": null')
-        elif r > 1:
-            parts.append('"v": %d' % rng.integers(-1000, 1000000))
-        docs.append("{" + ", ".join(parts) + "}")
+    docs = config5_docs(20000, 3000, 11)
     run_both(docs, "d", "((`d`.`v`) is not missing)", ["(`d`.`k`)"],
              ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))", "avg((`d`.`v`))"], "config5 shape block=" + block)
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_peer_arena_merge_owner_sharded(nranks):
+    """The collective-free multi-GPU merge of direct-indexed tables, with all ranks driven by this one process on one
+    device (n1gpu_mailbox_set_peer instead of CUDA IPC): every rank scans its row range into a table inside its arena,
+    raises its flag, and rank r's finalisation folds slot range r of ALL tables - the union of the ranks' results must be
+    the oracle's groups over the whole keyspace, each group finalised by exactly one rank.  Two steps: both table buffers."""
+    from query_b200 import dist as qd
+    docs = config5_docs(12000, 3000, 17)
+    where, keys = "((`d`.`v`) is not missing)", ["(`d`.`k`)"]
+    aggs = ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))", "avg((`d`.`v`))"]
+    parts = [docs[len(docs) * r // nranks: len(docs) * (r + 1) // nranks] for r in range(nranks)]
+    tables = [make_table(p, where, keys, aggs) for p in parts]
+    qd.agree_local(tables)
+    mbs = [q.Mailbox(nranks, r, 1024, arena_bytes=8 << 20) for r in range(nranks)]
+    for r in range(nranks):
+        for o in range(nranks):
+            mbs[r].set_peer(o, mbs[o].base)
+    qs = []
+    for r in range(nranks):
+        tables[r].seal()
+        qq = q.Query(tables[r], "d", where, keys, aggs)
+        assert qq.info["mode"] == "hbm-direct"
+        qq.set_mailbox(mbs[r])
+        qs.append(qq)
+    assert len({x.kernel_source for x in qs}) == 1, "ranks must compile the same kernel"
+    exp = oracle_rows(docs, "d", where, keys, aggs)
+    for step in range(3):
+        for qq in qs:
+            qq.launch()      # every rank's scan + flag first: the finalisations below wait for all flags of the step
+        got = {}
+        for r, qq in enumerate(qs):
+            part = gpu_rows(qq.collect(), aggs)
+            assert not (set(part) & set(got)), "a group was finalised by two ranks"
+            got.update(part)
+        assert_same(exp, got, "peer merge, %d ranks, step %d" % (nranks, step))
 
 
 @pytest.mark.parametrize("n", [0, 1, 3, 127, 128, 129, 1023, 1024, 1025, 4097])
