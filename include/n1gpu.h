@@ -156,6 +156,9 @@ int n1gpu_query_collect(n1gpu_query* q, n1gpu_result** out);
 int n1gpu_query_cancel(n1gpu_query* q);
 /* The generated CUDA source / kernel facts, for EXPLAIN-style inspection and tests.                 */
 const char* n1gpu_query_kernel_source(const n1gpu_query* q);
+/* The partitioning kernel of a chain that runs as a partitioned DISTINCT aggregation ("" otherwise): many groups, one
+ * DISTINCT operand of few bits, no other per-row accumulator than COUNT(*) - BASELINE config 4's shape.                */
+const char* n1gpu_query_part_source(const n1gpu_query* q);
 /* info[0]=mode (0 ungrouped, 1 dense shared-memory table, 2 HBM hash 64-bit keys, 3 HBM hash 128-bit)
  * info[1]=accumulator words per group  info[2]=registers/thread  info[3]=grid  info[4]=block
  * info[5]=scan bytes per row  info[6]=static shared bytes  info[7]=dense slots / hash capacity      */

@@ -64,6 +64,7 @@ _SIGS = {
     "n1gpu_query_collect": (C.c_int, [_P, C.POINTER(_P)]),
     "n1gpu_query_cancel": (C.c_int, [_P]),
     "n1gpu_query_kernel_source": (C.c_char_p, [_P]),
+    "n1gpu_query_part_source": (C.c_char_p, [_P]),
     "n1gpu_query_info": (C.c_int, [_P, _I64P]),
     "n1gpu_query_last_scan_ns": (C.c_int64, [_P]),
     "n1gpu_query_rebind": (C.c_int, [_P, _P]),

@@ -385,6 +385,10 @@ class Query:
         return lib().n1gpu_query_kernel_source(self._h).decode("utf-8")
 
     @property
+    def part_source(self):
+        return lib().n1gpu_query_part_source(self._h).decode("utf-8")
+
+    @property
     def info(self):
         a = np.zeros(8, dtype=np.int64)
         check(lib().n1gpu_query_info(self._h, a.ctypes.data_as(_lib._I64P)))

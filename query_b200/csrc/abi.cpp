@@ -251,6 +251,7 @@ int n1gpu_query_cancel(n1gpu_query* q) {
     return N1GPU_OK;
 }
 const char* n1gpu_query_kernel_source(const n1gpu_query* q) { return q ? q->q->kp.source.c_str() : ""; }
+const char* n1gpu_query_part_source(const n1gpu_query* q) { return q ? q->q->kp.part_source.c_str() : ""; }
 int n1gpu_query_info(const n1gpu_query* q, int64_t info[8]) {
     return guard([&] {
         REQUIRE(q); REQUIRE(info);
@@ -357,7 +358,13 @@ int n1gpu_query_set_mailbox(n1gpu_query* q, n1gpu_mailbox* mb) {
 
 // ---- multi-GPU partial state ----------------------------------------------------------------------------------
 int n1gpu_query_scan_partial(n1gpu_query* q) {
-    return guard([&] { REQUIRE(q); q->q->scan_blocking(); });
+    return guard([&] {
+        REQUIRE(q);
+        // the record / DISTINCT-entry exchange that follows reads the general scan's tables and sets: the partitioned
+        // DISTINCT aggregation (which leaves finished words instead) is for handles whose groups are finalised in place
+        q->q->part_disabled = true;
+        q->q->scan_blocking();
+    });
 }
 int n1gpu_query_partial_counts(n1gpu_query* q, int64_t* ngroups, int64_t* ndistinct, int* record_words) {
     return guard([&] {

@@ -772,6 +772,53 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     }
     std::string agg_code = g.body;
 
+    // ---- partitioned DISTINCT aggregation (see KernelPlan::part) --------------------------------------------------
+    std::string part_value_code;
+    {
+        const char* np = getenv("N1GPU_NO_PART");
+        bool ok = kp.mode == MODE_DENSE && kp.dense_global && kp.ndistinct == 1 && kp.cache_slots > 0 && !(np && *np == '1');
+        const AggPlan* da = nullptr;
+        const Expr* dexpr = nullptr;
+        for (size_t a = 0; a < kp.aggs.size() && ok; ++a) {
+            const AggPlan& ap = kp.aggs[a];
+            if (ap.distinct) { if (!da) { da = &ap; dexpr = aggs[a]->ops[0].get(); } continue; }
+            // every other aggregate must be the group's row count
+            if (!((ap.kind == AggKind::COUNT || ap.kind == AggKind::COUNTN) && ap.w_cnt == w_rows)) ok = false;
+        }
+        ok = ok && da && w_rows == 0;
+        // the value component must be one class with a small payload: a ranged INT (sums from popcounts) or a STRING rank
+        ok = ok && da->dcomp.classes.size() == 1 && da->dcomp.cbits == 0 && da->dcomp.nfree < 0 &&
+             ((da->dcomp.classes[0] == C_INT && da->dcomp.biased) || (da->dcomp.classes[0] == C_STRING && da->w_ilo < 0));
+        if (ok) for (auto& ap : kp.aggs) if (ap.distinct && (ap.w_fsum >= 0 || ap.w_nflt >= 0)) ok = false;
+        if (ok) {
+            const int KB = kp.key_bits, VB = da->dcomp.bits();
+            int PB = std::max(1, std::max(KB + VB - 20, KB - 12));   // a partition's bitmap <= 2^20 bits, <= 4096 groups
+            const char* fp = getenv("N1GPU_PART");                   // "1": also for keyspaces too small to profit (tests)
+            const bool force = fp && *fp == '1';
+            ok = VB >= 1 && VB <= 12 && PB <= 10 && PB < KB && (KB - PB) + 1 + VB <= 32 && (force || layout_rows >= ((i64)1 << (PB + 12)));
+            if (ok) {
+                kp.part = true;
+                kp.part_bits = PB; kp.part_gbits = KB - PB; kp.part_vbits = VB;
+                kp.part_bincap = std::max(8, std::min(48, (int)((192 * 1024) / (4 << PB))));
+                kp.part_smem = (4 << PB) * (1 + kp.part_bincap);
+                g.body.clear();
+                g.ind = "                    ";
+                std::string o = g.emit(*dexpr, nullptr);
+                std::string cv = o;
+                if (!dexpr->ti.plain_col && (dexpr->ti.mask & bit(C_FLOAT))) { cv = g.nv("d"); g.line(strf("const Val %s = canon_num(%s);", cv.c_str(), o.c_str())); }
+                g.line(strf("const bool hasv = %s;", dset_any[da->distinct_id] ? strf("%s.c > C_NULL", cv.c_str()).c_str() : strf("is_num(%s.c)", cv.c_str()).c_str()));
+                g.line("u64 vlo = 0, vhi = 0; int vpos = 0;");
+                g.line("if (hasv) {");
+                g.ind += "    ";
+                emit_pack(g, da->dcomp, cv, "vlo", "vhi", "vpos");
+                g.ind = "                    ";
+                g.line("}");
+                part_value_code = g.body;
+                g.body.clear();
+            }
+        }
+    }
+
     // ---- used columns -----------------------------------------------------------------------------------------
     for (auto& kv : g.colvar) kp.used_cols.push_back(kv.first);
     for (int c : kp.used_cols) kp.scan_bytes_per_row += t.scan_bytes(c);
@@ -1116,6 +1163,75 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     if (kp.pdl) s += "    asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");  // complete in stream order\n";
     s += "}\n";
     kp.source = s;
+    if (kp.part) {
+        std::string q;
+        q += "// generated by libn1gpu codegen: the partitioning kernel of this chain's partitioned DISTINCT aggregation\n";
+        q += "#include \"n1ql_device.cuh\"\n";
+        q += "#define NQ_BLOCK 1024\n";
+        q += strf("#define NP %d\n#define BINCAP %d\n#define GBITS %d\n#define ROUND_TILES 8\n", 1 << kp.part_bits, kp.part_bincap, kp.part_gbits);
+        q += "extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, 1) nq_scan(const NqParams p) {\n";
+        q += "    extern __shared__ u32 s_part[];\n";
+        q += "    u32* const s_cnt = s_part;        // [NP] records staged per partition in this round\n";
+        q += "    u32* const s_bin = s_part + NP;   // [NP][BINCAP]\n";
+        q += "    u32* const g_recs = (u32*)p.set_keys;  // [NP][part_cap] partitioned records\n";
+        q += "    u32* const g_cur = (u32*)p.keys;       // [NP] records written per partition\n";
+        q += "    const u64 part_cap = p.set_mask;\n";
+        q += "    const i64 nrows = p.nrows;\n";
+        q += "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
+        q += "    const i64 tile = NQ_BLOCK * 4;\n";
+        q += "    const i64 ntiles = (nrows + tile - 1) / tile;\n";
+        q += "    for (i64 t0 = (i64)blockIdx.x * ROUND_TILES; t0 < ntiles; t0 += (i64)gridDim.x * ROUND_TILES) {\n";
+        q += "        for (int i = threadIdx.x; i < NP; i += NQ_BLOCK) s_cnt[i] = 0;\n";
+        q += "        __syncthreads();\n";
+        q += "        for (int tt = 0; tt < ROUND_TILES && t0 + tt < ntiles; ++tt) {\n";
+        q += "        const i64 base = (t0 + tt) * tile + threadIdx.x * 4;\n";
+        for (int c : kp.used_cols) {
+            const Column& col = t.cols[c];
+            if (col.width == 8) q += strf("        i64 c%d[4]; ld_rows4_b64((const i64*)p.col[%d] + base, c%d);\n", c, c, c);
+            else if (col.width == 4) q += strf("        u32 c%d[4]; ld_rows4_b32((const u32*)p.col[%d] + base, c%d);\n", c, c, c);
+            if (!col.stats.uniform_tag() && col.stats.class_mask) q += strf("        int t%d[4]; ld_rows4_b8(p.tag[%d] + base, t%d);\n", c, c, c);
+        }
+        q += "#pragma unroll\n";
+        q += "        for (int j = 0; j < 4; ++j) {\n";
+        q += "            bool pass = base + j < nrows;\n";
+        q += g.decls;
+        if (where) {
+            q += filter_code;
+            q += "                pass = pass && w_true;\n";
+        }
+        q += "            if (pass) {\n";
+        q += key_code;
+        q += part_value_code;
+        q += "                    const u32 rec = (u32)(klo & ((1ULL << GBITS) - 1)) | ((u32)hasv << GBITS) | ((u32)vlo << (GBITS + 1));\n";
+        q += "                    const u32 part = (u32)(klo >> GBITS);\n";
+        q += "                    const u32 pos = atomicAdd(&s_cnt[part], 1u);\n";
+        q += "                    if (pos < BINCAP) s_bin[part * BINCAP + pos] = rec;\n";
+        q += "                    else {  // the bin is full for this round: straight to the partition (rare unless the keys are skewed)\n";
+        q += "                        const u32 at = atomicAdd(&g_cur[part], 1u);\n";
+        q += "                        if (at < part_cap) g_recs[(u64)part * part_cap + at] = rec; else p.status[0] = 4;\n";
+        q += "                    }\n";
+        q += "            }\n";
+        q += "        }\n";
+        q += "        }\n";
+        q += "        __syncthreads();\n";
+        q += "        // flush: lane l of warp w reserves room for partition w * 32 + l (32 reservations in flight per warp), then the\n";
+        q += "        // warp copies the 32 bins one after the other, a contiguous run of records each\n";
+        q += "        for (int p0 = warp * 32; p0 < NP; p0 += NQ_BLOCK) {\n";
+        q += "            const int mine = p0 + lane;\n";
+        q += "            u32 n = mine < NP ? min(s_cnt[mine], (u32)BINCAP) : 0u, gb = 0;\n";
+        q += "            if (n) gb = atomicAdd(&g_cur[mine], n);\n";
+        q += "            for (int k = 0; k < 32; ++k) {\n";
+        q += "                const u32 nk = __shfl_sync(0xffffffffu, n, k), bk = __shfl_sync(0xffffffffu, gb, k);\n";
+        q += "                for (u32 i = lane; i < nk; i += 32) {\n";
+        q += "                    if (bk + i < part_cap) g_recs[(u64)(p0 + k) * part_cap + bk + i] = s_bin[(p0 + k) * BINCAP + i]; else p.status[0] = 4;\n";
+        q += "                }\n";
+        q += "            }\n";
+        q += "        }\n";
+        q += "        __syncthreads();\n";
+        q += "    }\n";
+        q += "}\n";
+        kp.part_source = q;
+    }
     return kp;
 }
 

@@ -91,6 +91,19 @@ struct KernelPlan {
     bool set128 = false;
     int set_passes = 1;          // bitmap beyond what the L2 keeps: scan passes, each filling one L2-resident slice of it
     bool set_bitmap = false;     // DISTINCT entries are few bits: the set is a bitmap indexed by the entry (no hashing)
+    // Partitioned DISTINCT aggregation (config 4's shape: a direct-indexed table of many groups, ONE distinct operand of few
+    // bits, and no other per-row accumulator than the row count).  Instead of one scattered L2 atomic per row for the
+    // DISTINCT bitmap and one for the group table, a first kernel (part_source) only filters, packs (group, value) into a
+    // 4-byte record and radix-partitions the records by the high bits of the group key through shared-memory bins; a second
+    // (static) kernel gives every partition to one block, whose share of the bitmap and of the counters fits shared memory,
+    // and leaves the finished accumulator words in the group table.  part_* describe the record.
+    bool part = false;
+    std::string part_source;     // the partitioning kernel (entry nq_scan, 1024 threads)
+    int part_bits = 0;           // partitions = 2^part_bits, taken from the top of the packed group key
+    int part_gbits = 0;          // record bits [0, gbits): group key inside its partition; bit gbits: has a value
+    int part_vbits = 0;          // record bits above: the packed DISTINCT value
+    int part_bincap = 48;        // records a block stages per partition and round in shared memory
+    int part_smem = 0;           // dynamic shared memory of the partitioning kernel
     std::vector<int> used_cols;
     int scan_bytes_per_row = 0;
     std::string source;

@@ -3,6 +3,8 @@
 // multi-GPU IntermediateGroup exchange, also the compaction step of finalisation), record -> table merging
 // (CumulateIntermediate: algebra/agg_*.go, execution/group_intermediate.go:56-104), the element-wise merges of
 // small-state chains and the device-side ComputeFinal of DISTINCT aggregates.
+#include <algorithm>
+
 #include "kernels.hpp"
 #include "n1ql_device.cuh"
 
@@ -397,6 +399,89 @@ __global__ void __launch_bounds__(256) k_finalize_groups(const FinalDesc D, int 
             agg_val[g * D.naggs + a] = out.bits;
         }
     }
+}
+
+// ---- partitioned DISTINCT aggregation: one partition per block, state in shared memory -----------------------------------
+// (replaces, for this shape, one scattered L2 atomic per row on the DISTINCT bitmap + one on the group table + the per-entry
+// atomics of k_distinct_finalize: InitialGroup's per-row work of execution/group_initial.go:56-108 with the value.Set of
+// algebra/agg_util.go:30-101 as bits, and ComputeFinal of algebra/agg_count_distinct.go / agg_sum_distinct.go per group)
+__global__ void __launch_bounds__(1024, 1) k_part_aggregate(const PartPeers P, u64 part_cap, int part0, int part1, int gbits, int vbits, int w_rows,
+                                                            const DistinctDescs D, int value_is_int, i64 value_bias, u64* acc, u64 cap) {
+    extern __shared__ u32 s_pa[];
+    const u32 G = 1u << gbits;
+    const int wshift = vbits > 5 ? vbits - 5 : 0;   // 32-bit bitmap words per group = 1 << wshift
+    const u32 WPG = 1u << wshift;
+    u32* const s_cnt = s_pa;       // [G] rows per group
+    u32* const s_bm = s_pa + G;    // [G][WPG] values seen per group
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const u32 gmask = G - 1;
+    for (int part = part0 + blockIdx.x; part < part1; part += gridDim.x) {
+        for (u32 i = threadIdx.x; i < G * (1 + WPG); i += blockDim.x) s_pa[i] = 0;
+        __syncthreads();
+        for (int t = 0; t < P.n; ++t) {
+            const u64 n = min((u64)__ldcg(&P.cur[t][part]), part_cap);
+            const u32* __restrict__ r = P.recs[t] + (u64)part * part_cap;
+            for (u64 i = threadIdx.x; i < n; i += blockDim.x) {
+                const u32 rec = __ldcg(&r[i]);
+                const u32 g = rec & gmask;
+                atomicAdd(&s_cnt[g], 1u);
+                if ((rec >> gbits) & 1u) {
+                    const u32 v = rec >> (gbits + 1);
+                    atomicOr(&s_bm[(g << wshift) + (v >> 5)], 1u << (v & 31));
+                }
+            }
+        }
+        __syncthreads();
+        // a warp per group: lane k folds bitmap words k, k + 32, ... (bank == lane), then a shuffle reduction
+        const i64 neg_below = value_is_int ? (value_bias < 0 ? -value_bias : 0) : 0;  // codes below this are negative values
+        for (u32 g = warp; g < G; g += nwarps) {
+            u64 cnt = 0, code_sum = 0, nneg = 0;
+            for (u32 k = lane; k < WPG; k += 32) {
+                const u32 w = s_bm[(g << wshift) + k];
+                if (!w) continue;
+                cnt += __popc(w);
+                if (value_is_int) {
+                    // sum of the set bit positions: 32 * k * popc + sum over j of 2^j * popc(w & bits whose position has bit j)
+                    code_sum += (u64)(32u * k) * __popc(w) + __popc(w & 0xaaaaaaaau) + 2u * __popc(w & 0xccccccccu) + 4u * __popc(w & 0xf0f0f0f0u) +
+                                8u * __popc(w & 0xff00ff00u) + 16u * __popc(w & 0xffff0000u);
+                    const i64 lo = (i64)(32u * k);
+                    if (neg_below > lo) nneg += neg_below >= lo + 32 ? (u64)__popc(w) : (u64)__popc(w & ((1u << (u32)(neg_below - lo)) - 1u));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                code_sum += __shfl_xor_sync(0xffffffffu, code_sum, o);
+                nneg += __shfl_xor_sync(0xffffffffu, nneg, o);
+            }
+            if (lane == 0) {
+                const u64 slot = ((u64)part << gbits) | g;
+                acc[(u64)w_rows * cap + slot] = s_cnt[g];
+                const __int128 total = (__int128)value_bias * (__int128)cnt + (__int128)code_sum;
+                for (int a = 0; a < D.n; ++a) {
+                    const DistinctDesc& d = D.d[a];
+                    acc[(u64)d.w_cnt * cap + slot] = cnt;
+                    if (d.w_ilo >= 0) {
+                        acc[(u64)d.w_ilo * cap + slot] = (u64)total & 0xffffffffULL;
+                        acc[(u64)d.w_ihi * cap + slot] = (u64)(i64)(total >> 32);
+                        acc[(u64)d.w_neg * cap + slot] = nneg;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+void launch_part_aggregate(const PartPeers& P, u64 part_cap, int part0, int part1, int gbits, int vbits, int w_rows, const DistinctDescs& D,
+                           int value_is_int, i64 value_bias, u64* acc, u64 cap, cudaStream_t s) {
+    if (part1 <= part0) return;
+    const size_t smem = ((size_t)4 << gbits) * (1 + ((size_t)1 << (vbits > 5 ? vbits - 5 : 0)));
+    static size_t configured = 0;
+    if (smem > configured) { CK(cudaFuncSetAttribute(k_part_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+    const int grid = std::min(part1 - part0, 148 * (smem <= 100 * 1024 ? 2 : 1));
+    k_part_aggregate<<<grid, 1024, smem, s>>>(P, part_cap, part0, part1, gbits, vbits, w_rows, D, value_is_int, value_bias, acc, cap);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
 }
 
 static int grid_for(u64 n) {

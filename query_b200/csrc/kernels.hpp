@@ -59,6 +59,19 @@ void launch_peer_signal(u64* const* peers, int nranks, int rank, u64 flags_word_
 void launch_finalize_groups(const FinalDesc& D, int kw, const u64* keys, const PeerTables& T, const OpsArr& ops, u64 ws, u64 ss, u64 slot0,
                             u64 slot1, unsigned long long* counter, u64 out_cap, u8* key_cls, i64* key_val, u8* agg_cls, i64* agg_val,
                             cudaStream_t s);
+// ---- partitioned DISTINCT aggregation, second kernel (KernelPlan::part) --------------------------------------------------
+// Records of partition `part` written by rank t: recs[t][part * part_cap .. + min(cur[t][part], part_cap)).
+struct PartPeers {
+    int n;
+    const u32* recs[16];
+    const u32* cur[16];
+};
+// One block per partition in [part0, part1): folds the records of all ranks into a shared-memory bitmap (group x value)
+// and per-group row counters, then leaves the finished words of every group of the partition in the table acc[w * cap + slot]
+// (slot = part << gbits | group): rows in word w_rows and, per DISTINCT aggregate of D, its count / exact split int sum /
+// negative count.  value_is_int: the value component is a biased INT (else a string rank: counts only).
+void launch_part_aggregate(const PartPeers& P, u64 part_cap, int part0, int part1, int gbits, int vbits, int w_rows, const DistinctDescs& D,
+                           int value_is_int, i64 value_bias, u64* acc, u64 cap, cudaStream_t s);
 void launch_distinct_finalize(const u64* set_keys, u64 set_cap, int set128, int abits, int key_bits, int kw, const u64* keys, u64 cap,
                               u64* acc, const DistinctDescs& D, cudaStream_t s);
 void launch_merge_mailbox(const u64* mail, int nranks, u64 slot_base, u64 stride, u64 words, u64 seq, u64 cap, const OpsArr& ops,

@@ -87,6 +87,7 @@ std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const 
     for (int w = 0; w < q->ops.n; ++w) q->ops.op[w] = q->kp.phys_ops[w];
     if (have_device()) {
         q->kernel = jit_load(q->kp.source, q->kp.dyn_smem, q->kp.block);
+        if (q->kp.part) q->part_kernel = jit_load(q->kp.part_source, q->kp.part_smem, 1024);
         CK(cudaStreamCreateWithFlags(&q->own_stream, cudaStreamNonBlocking));
         q->stream = q->own_stream;
         CK(cudaEventCreate(&q->ev0));
@@ -96,6 +97,7 @@ std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const 
         // no GPU in this process (build / CPU test container): still prove the kernel compiles for sm_100a
         std::string log;
         jit_compile_cubin(q->kp.source, &log);
+        if (q->kp.part) jit_compile_cubin(q->kp.part_source, &log);
     }
     return q;
 }
@@ -145,6 +147,14 @@ void Query::alloc_state() {
             set_cap = pow2_at_least((u64)std::min(std::max(want, 1024.0), 4294967296.0));
         }
         d_set.ensure(set_bytes());
+    }
+    if (part_kernel) {
+        // every partition gets its expected share of this table's rows plus a quarter and a constant: uniform keys never
+        // come near it, skewed ones overflow it and the handle falls back to the general scan (status 4)
+        const u64 np = (u64)1 << kp.part_bits;
+        part_cap = ((u64)std::max<i64>(table->nrows, 1) / np) * 5 / 4 + 4096;
+        d_part_recs.ensure((size_t)(np * part_cap) * 4);
+        d_part_cur.ensure((size_t)np * 4);
     }
     d_status.ensure(64);
     h_status.ensure(64);
@@ -219,6 +229,36 @@ void Query::launch_scan() {
         p.mail_words = words;
         p.mail_seq = mb_seq;
     }
+    part_done = false;
+    if (use_part()) {
+        // partitioned DISTINCT aggregation: records partitioned by group range, then one block per partition
+        const int np = 1 << kp.part_bits;
+        CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
+        CK(cudaMemsetAsync(d_part_cur.p, 0, (size_t)np * 4, stream));
+        if (timing) CK(cudaEventRecord(ev0, stream));
+        p.set_keys = d_part_recs.as<u64>();
+        p.keys = d_part_cur.as<u64>();
+        p.set_mask = part_cap;
+        const i64 tiles = (table->nrows + 4095) / 4096;
+        const int pgrid = (int)std::max<i64>(1, std::min<i64>((tiles + 7) / 8, device_sm_count()));
+        jit_launch(*part_kernel, pgrid, stream, &p, sizeof p, false);
+        PartPeers P;
+        memset(&P, 0, sizeof P);
+        P.n = 1;
+        P.recs[0] = d_part_recs.as<u32>();
+        P.cur[0] = d_part_cur.as<u32>();
+        const DistinctDescs D = distinct_descs();
+        const PackComp* dc = nullptr;
+        for (auto& ap : kp.aggs) if (ap.distinct) { dc = &ap.dcomp; break; }
+        launch_part_aggregate(P, part_cap, 0, np, kp.part_gbits, kp.part_vbits, kp.phys_of[0], D, dc->classes[0] == C_INT, dc->bias, acc(), cap, stream);
+        if (timing) CK(cudaEventRecord(ev1, stream));
+        timed_launch = timing;
+        CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
+        launched = true;
+        ungrouped_live = true;
+        part_done = true;
+        return;
+    }
     reset_state();
     if (timing) CK(cudaEventRecord(ev0, stream));
     // ungrouped / dense: the whole step is this one launch.  Programmatic dependent launch only when nothing this
@@ -253,6 +293,11 @@ bool Query::wait_scan() {
     }
     int st = uses_status() ? h_status.as<int>()[0] : 0;
     if (st == 3) N1_THROW(N1GPU_E_CUDA, "multi-GPU merge timed out: a peer rank never delivered its partial state");
+    if (st == 4) {  // a partition overflowed (skewed group keys): the general one-kernel scan takes over for this handle
+        part_disabled = true;
+        part_done = false;
+        return false;
+    }
     if (st == 1) {
         if (cap >= ((u64)1 << 31)) N1_THROW(N1GPU_E_NOMEM, "group table would exceed 2^31 slots");
         cap *= 4;
@@ -418,6 +463,22 @@ u64 Query::dense_key(u64 slot) const {
     return key;
 }
 
+DistinctDescs Query::distinct_descs() const {
+    DistinctDescs D{};
+    D.n = 0;
+    for (auto& ap : kp.aggs) {
+        if (!ap.distinct) continue;
+        DistinctDesc& d = D.d[D.n++];
+        d.sid = ap.distinct_id;
+        d.numbers_only = ap.kind != AggKind::COUNT;
+        d.w_cnt = ap.w_cnt; d.w_ilo = ap.w_ilo; d.w_ihi = ap.w_ihi; d.w_neg = ap.w_neg; d.w_fsum = ap.w_fsum; d.w_nflt = ap.w_nflt;
+        d.cbits = ap.dcomp.cbits; d.pbits = ap.dcomp.pbits; d.biased = ap.dcomp.biased; d.bias = ap.dcomp.bias;
+        d.nfree = ap.dcomp.nfree;
+        for (int k = 0; k < 8; ++k) d.classes[k] = k < (int)ap.dcomp.classes.size() ? ap.dcomp.classes[k] : C_MISSING;
+    }
+    return D;
+}
+
 FinalDesc Query::final_desc() const {
     FinalDesc D;
     memset(&D, 0, sizeof D);
@@ -508,19 +569,11 @@ std::unique_ptr<Result> Query::finalize() {
     const bool trace = getenv("N1GPU_TRACE") != nullptr;
     double tp = now_sec();
     auto phase = [&](const char* name) { if (trace) { double t = now_sec(); fprintf(stderr, "[n1gpu finalize] %-22s %8.3f ms\n", name, (t - tp) * 1e3); tp = t; } };
-    if (kp.ndistinct) {
+    if (kp.ndistinct && !part_done) {
         // DISTINCT aggregates are finalised on the device: every set entry adds itself to its group's result words
-        DistinctDescs D{};
-        D.n = 0;
+        const DistinctDescs D = distinct_descs();
         for (auto& ap : kp.aggs) {
             if (!ap.distinct) continue;
-            DistinctDesc& d = D.d[D.n++];
-            d.sid = ap.distinct_id;
-            d.numbers_only = ap.kind != AggKind::COUNT;
-            d.w_cnt = ap.w_cnt; d.w_ilo = ap.w_ilo; d.w_ihi = ap.w_ihi; d.w_neg = ap.w_neg; d.w_fsum = ap.w_fsum; d.w_nflt = ap.w_nflt;
-            d.cbits = ap.dcomp.cbits; d.pbits = ap.dcomp.pbits; d.biased = ap.dcomp.biased; d.bias = ap.dcomp.bias;
-            d.nfree = ap.dcomp.nfree;
-            for (int k = 0; k < 8; ++k) d.classes[k] = k < (int)ap.dcomp.classes.size() ? ap.dcomp.classes[k] : C_MISSING;
             for (int w : {ap.w_cnt, ap.w_ilo, ap.w_ihi, ap.w_neg, ap.w_fsum, ap.w_nflt})
                 if (w >= 0) launch_fill_u64(acc() + (u64)w * cap, cap, 0, stream);  // idempotent finalize
         }

@@ -96,6 +96,13 @@ struct Query {
     std::vector<ExprP> keys, aggs;
     KernelPlan kp;
     std::shared_ptr<JitKernel> kernel;
+    std::shared_ptr<JitKernel> part_kernel;  // KernelPlan::part: the partitioning kernel (null: not this shape)
+    bool part_disabled = false;              // a partition overflowed its share (skewed keys): this handle scans the general way
+    bool part_done = false;                  // the last scan left finished DISTINCT words in the table (no k_distinct_finalize)
+    u64 part_cap = 0;                        // records a partition holds
+    DevBuf d_part_recs, d_part_cur;
+    bool use_part() const { return part_kernel && !part_disabled; }
+    DistinctDescs distinct_descs() const;
     OpsArr ops{};
 
     cudaStream_t stream = nullptr;

@@ -107,7 +107,7 @@ _GROUPED = [x for x in QUERIES if x[2]]
 
 @pytest.mark.parametrize("knob", ["N1GPU_NO_DIRECT", "N1GPU_NO_BITMAP", "N1GPU_NO_OFFSET_PACK", "N1GPU_NO_CACHE", "N1GPU_NO_PACK",
                                   "N1GPU_NO_KEY32", "N1GPU_NO_COMPLEMENT", "N1GPU_CACHE_BLOCK=1024", "N1GPU_CACHE_BLOCK=256",
-                                  "N1GPU_MMCHECK=1", "N1GPU_MMCHECK=2", "N1GPU_SET_PASSES=4", "N1GPU_NO_FCARRY", "N1GPU_NO_TIGHT"])
+                                  "N1GPU_MMCHECK=1", "N1GPU_MMCHECK=2", "N1GPU_SET_PASSES=4", "N1GPU_NO_FCARRY", "N1GPU_NO_TIGHT", "N1GPU_PART"])
 @pytest.mark.parametrize("name,where,keys,aggs", _GROUPED, ids=[x[0] for x in _GROUPED])
 def test_grouped_matrix_through_the_alternate_layouts(name, where, keys, aggs, knob, monkeypatch):
     """The planner picks direct-indexed tables, DISTINCT bitmaps, offset-packed keys, the shared-memory front cache
@@ -130,6 +130,25 @@ def test_skewed_string_keys_with_missing_and_null(block, monkeypatch):
     docs = config5_docs(20000, 3000, 11)
     run_both(docs, "d", "((`d`.`v`) is not missing)", ["(`d`.`k`)"],
              ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))", "avg((`d`.`v`))"], "config5 shape block=" + block)
+
+
+@pytest.mark.parametrize("groups,skew", [(40000, False), (3000, False), (40000, True)])
+def test_partitioned_distinct_aggregation(groups, skew, monkeypatch):
+    """BASELINE config 4 shape at oracle size through the partitioned DISTINCT aggregation (forced: the planner only picks it
+    for keyspaces large enough to profit): records radix-partitioned by group range, one block per partition; with skewed
+    group keys a partition overflows its share and the handle falls back to the general scan - same rows either way."""
+    from gen_n1 import config4_docs
+    monkeypatch.setenv("N1GPU_PART", "1")
+    docs = config4_docs(30000, groups, 41)
+    if skew:  # most rows in a handful of neighbouring groups: one partition receives far more than its share
+        docs = docs[:2000] + ['{"g": %d, "x": %d}' % (7 + i % 3, i % 1000) for i in range(28000)]
+    where, keys = None, ["(`d`.`g`)"]
+    aggs = ["count(distinct (`d`.`x`))", "sum(distinct (`d`.`x`))", "count(*)", "avg(distinct (`d`.`x`))"]
+    qq, res = run_both(docs, "d", where, keys, aggs, "partitioned distinct groups=%d skew=%s" % (groups, skew))
+    assert "NP " in qq.part_source and qq.info["mode"] == "hbm-direct"
+    # negative values: SUM(DISTINCT) counts them for the int / float class of the result (0 + negative -> float)
+    docs2 = ['{"g": %d, "x": %d}' % (i % 5000, (i * 7) % 600 - 300) for i in range(30000)]
+    run_both(docs2, "d", None, keys, aggs, "partitioned distinct, negative values")
 
 
 @pytest.mark.parametrize("nranks", [2, 3])
