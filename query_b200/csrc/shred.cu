@@ -259,6 +259,7 @@ __global__ void k_dict_insert(const unsigned char* __restrict__ buf, const unsig
                               const i64* __restrict__ payload, i64* __restrict__ slots, i64 nrows, u64* keys, u64 cap_mask, int* status) {
     for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (i64)gridDim.x * blockDim.x) {
         if (tags[row] != C_STRING) continue;
+        if (*(volatile int*)status) return;  // the table proved too small: the host grows it and reruns, nothing here is kept
         const u64 ref = (u64)payload[row];
         const unsigned char* p = ref_ptr(ref, buf, extra);
         const u64 len = ref & 0xffffff;
@@ -266,7 +267,8 @@ __global__ void k_dict_insert(const unsigned char* __restrict__ buf, const unsig
         for (u64 i = 0; i < len; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
         u64 slot = ::mix64(h) & cap_mask;
         bool done = false;
-        for (u64 probe = 0; probe <= cap_mask && probe < 8192; ++probe) {
+        // (a probe sequence this long means the table is far too dense: every step compares string bytes)
+        for (u64 probe = 0; probe <= cap_mask && probe < 128; ++probe) {
             u64 cur = *(volatile u64*)&keys[slot];
             if (cur == NQ_U64_MAX) {
                 const u64 old = atomicCAS(&keys[slot], NQ_U64_MAX, ref);
@@ -288,6 +290,10 @@ __global__ void k_dict_collect(const u64* __restrict__ keys, u64 cap, unsigned* 
         const unsigned at = atomicAdd(count, 1u);
         if (at < out_cap) { out_slots[at] = i; out_refs[at] = k; }
     }
+}
+// rank[slot_of_rank[r]] = r: the ranks of the occupied dictionary slots (only those are ever read)
+__global__ void k_dict_ranks(const u64* __restrict__ slot_of_rank, u64 n, u32* rank) {
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (u64)gridDim.x * blockDim.x) rank[slot_of_rank[r]] = (u32)r;
 }
 // slot -> rank; writes 8-byte payload in place, or the narrow 4-byte array when out32 != null
 __global__ void k_dict_remap(const u8* __restrict__ tags, const i64* __restrict__ slots, i64* payload, u32* out32, i64 nrows,
@@ -360,6 +366,12 @@ void launch_dict_insert(const unsigned char* buf, const unsigned char* extra, co
 }
 void launch_dict_collect(const u64* keys, u64 cap, unsigned* count, u64* out_slots, u64* out_refs, u64 out_cap, cudaStream_t s) {
     k_dict_collect<<<sgrid((i64)cap, 256), 256, 0, s>>>(keys, cap, count, out_slots, out_refs, out_cap);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_dict_ranks(const u64* slot_of_rank, u64 n, u32* rank, cudaStream_t s) {
+    if (n == 0) return;
+    k_dict_ranks<<<sgrid((i64)n, 256), 256, 0, s>>>(slot_of_rank, n, rank);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }

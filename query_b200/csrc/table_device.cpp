@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <map>
+#include <thread>
 
 #include "shred.hpp"
 #include "table.hpp"
@@ -191,7 +192,8 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
         col.width = (st.class_mask & M_NUM) ? 8 : (has_str ? 4 : 0);
         if (has_str) {
             d_slots.ensure((size_t)pad * 8);
-            u64 cap = 1 << 16;
+            // (a sparse table is cheap - 8 bytes per slot, cleared by a memset - a dense one costs string compares per probe)
+            u64 cap = std::max<u64>((u64)1 << 16, std::min<u64>((u64)1 << 21, pow2_at_least((u64)ndocs / 4)));
             std::vector<u64> oslots, orefs;
             for (;;) {
                 d_keys.ensure((size_t)cap * 8);
@@ -224,6 +226,7 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
                 if (cap > ((u64)1 << 33)) N1_THROW(N1GPU_E_NOMEM, "dictionary table too large");
                 cap *= 8;
             }
+            phase("  dictionary insert");
             // sort the distinct strings bytewise on the host: rank = N1QL collation order (value/string.go:116-126)
             struct Ent { const char* p; u32 len; u64 slot; };
             std::vector<Ent> ents(oslots.size());
@@ -234,15 +237,38 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
                 ents[i].len = (u32)(ref & 0xffffff);
                 ents[i].slot = oslots[i];
             }
-            std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) {
+            auto less = [](const Ent& a, const Ent& b) {
                 const int c = memcmp(a.p, b.p, std::min(a.len, b.len));
                 return c != 0 ? c < 0 : a.len < b.len;
-            });
-            std::vector<u32> rank((size_t)cap, 0);
+            };
+            {   // sorted runs on all cores, then pairwise merges (10^5 strings: ~35 ms on one core)
+                const size_t n = ents.size();
+                size_t nthr = n < 20000 ? 1 : std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+                size_t runs = 1;
+                while (runs * 2 <= nthr) runs *= 2;
+                auto bound = [&](size_t r) { return n * r / runs; };
+                std::vector<std::thread> pool;
+                for (size_t r = 1; r < runs; ++r) pool.emplace_back([&, r] { std::sort(ents.begin() + (i64)bound(r), ents.begin() + (i64)bound(r + 1), less); });
+                std::sort(ents.begin(), ents.begin() + (i64)bound(1), less);
+                for (auto& th : pool) th.join();
+                for (size_t width = 1; width < runs; width *= 2) {
+                    pool.clear();
+                    for (size_t r = 0; r + width < runs; r += 2 * width)
+                        pool.emplace_back([&, r, width] {
+                            std::inplace_merge(ents.begin() + (i64)bound(r), ents.begin() + (i64)bound(r + width), ents.begin() + (i64)bound(std::min(runs, r + 2 * width)), less);
+                        });
+                    for (auto& th : pool) th.join();
+                }
+            }
+            phase("  dictionary sort");
+            // rank of every occupied slot: the (few) slots travel in rank order and a kernel scatters their ranks
+            std::vector<u64> slot_of_rank(ents.size());
             col.dict.reserve(ents.size());
-            for (size_t r = 0; r < ents.size(); ++r) { rank[(size_t)ents[r].slot] = (u32)r; col.dict.emplace_back(ents[r].p, ents[r].len); }
+            for (size_t r = 0; r < ents.size(); ++r) { slot_of_rank[r] = ents[r].slot; col.dict.emplace_back(ents[r].p, ents[r].len); }
             d_rank.ensure((size_t)cap * 4);
-            CK(cudaMemcpyAsync(d_rank.p, rank.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, s));
+            d_oslots.ensure(std::max<size_t>(slot_of_rank.size() * 8, 64));
+            if (!slot_of_rank.empty()) CK(cudaMemcpyAsync(d_oslots.p, slot_of_rank.data(), slot_of_rank.size() * 8, cudaMemcpyHostToDevice, s));
+            launch_dict_ranks(d_oslots.as<u64>(), (u64)slot_of_rank.size(), d_rank.as<u32>(), s);
             u32* out32 = nullptr;
             if (col.width == 4) {
                 col.d_payload.alloc((size_t)pad * 4);
@@ -251,6 +277,7 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
             }
             launch_dict_remap(col.d_tags.as<u8>(), d_slots.as<i64>(), pay8[c].as<i64>(), out32, ndocs, d_rank.as<u32>(), s);
             CK(cudaStreamSynchronize(s));
+            phase("  dictionary remap");
         }
         if (col.width == 8) col.d_payload = std::move(pay8[c]);
         else { pay8[c].release(); if (col.width == 0) col.d_payload.alloc(256); }
