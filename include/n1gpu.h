@@ -102,6 +102,10 @@ int n1gpu_table_column_scan_bytes(const n1gpu_table* t, int col);
 int n1gpu_table_dict_export(n1gpu_table* t, int col, char* blob, int64_t blob_cap, int64_t* offsets,
                             int64_t offsets_cap, int64_t* ndict, int64_t* blob_bytes);
 int n1gpu_table_dict_import(n1gpu_table* t, int col, const char* blob, const int64_t* offsets, int64_t ndict);
+/* The same in one call: merges nparts sorted, unique dictionaries (e.g. every rank's export, gathered by the caller) with
+ * the column's own into the global sorted dictionary and remaps the column's ranks - on the host while the column is
+ * staged, by a kernel when its rows already live in HBM (device shredder, set_column_device).                          */
+int n1gpu_table_dict_merge(n1gpu_table* t, int col, int nparts, const char* const* blobs, const int64_t* const* offsets, const int64_t* ndicts);
 /* Column statistics exchange (int range / class mask) so that every rank compiles the same kernel. */
 int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]);
 int n1gpu_table_stats_set(n1gpu_table* t, int col, const int64_t stats[8]);

@@ -48,6 +48,7 @@ _SIGS = {
     "n1gpu_table_column_scan_bytes": (C.c_int, [_P, C.c_int]),
     "n1gpu_table_dict_export": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int64, _I64P, C.c_int64, _I64P, _I64P]),
     "n1gpu_table_dict_import": (C.c_int, [_P, C.c_int, C.c_char_p, _I64P, C.c_int64]),
+    "n1gpu_table_dict_merge": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(_I64P), _I64P]),
     "n1gpu_table_stats_get": (C.c_int, [_P, C.c_int, _I64P]),
     "n1gpu_table_stats_set": (C.c_int, [_P, C.c_int, _I64P]),
     "n1gpu_table_set_global_rows": (C.c_int, [_P, C.c_int64]),

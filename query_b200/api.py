@@ -166,6 +166,29 @@ class Table:
         raw = blob.raw
         return [raw[offs[i]:offs[i + 1]] for i in range(nd.value)]
 
+    def dictionary_raw(self, col):
+        """(blob uint8[bytes], offsets int64[n + 1]) of the column's sorted dictionary - no Python object per string"""
+        idx = col if isinstance(col, int) else self.find_column(col)
+        nd, nb = C.c_int64(), C.c_int64()
+        check(lib().n1gpu_table_dict_export(self._h, idx, None, 0, None, 0, C.byref(nd), C.byref(nb)))
+        blob = np.zeros(max(1, nb.value), dtype=np.uint8)
+        offs = np.zeros(nd.value + 1, dtype=np.int64)
+        check(lib().n1gpu_table_dict_export(self._h, idx, blob.ctypes.data_as(C.c_char_p), nb.value, offs.ctypes.data_as(_lib._I64P), nd.value + 1,
+                                            C.byref(nd), C.byref(nb)))
+        return blob[: nb.value], offs
+
+    def merge_dictionaries(self, col, parts):
+        """parts: [(blob uint8 array, offsets int64 array)] - sorted dictionaries (every rank's export): merged natively with
+        the column's own into the global sorted dictionary, ranks remapped (on the device when the column lives there)."""
+        idx = col if isinstance(col, int) else self.find_column(col)
+        n = len(parts)
+        blobs = [np.ascontiguousarray(b, dtype=np.uint8) for b, _o in parts]
+        offs = [np.ascontiguousarray(o, dtype=np.int64) for _b, o in parts]
+        bp = (C.c_char_p * n)(*[C.cast(b.ctypes.data_as(C.c_void_p), C.c_char_p) if b.size else C.c_char_p(b"") for b in blobs])
+        op = (_lib._I64P * n)(*[o.ctypes.data_as(_lib._I64P) for o in offs])
+        nd = np.array([len(o) - 1 for o in offs], dtype=np.int64)
+        check(lib().n1gpu_table_dict_merge(self._h, idx, n, bp, op, nd.ctypes.data_as(_lib._I64P)))
+
     def import_dictionary(self, col, strings):
         idx = col if isinstance(col, int) else self.find_column(col)
         enc = [s.encode("utf-8") if isinstance(s, str) else s for s in strings]

@@ -1,6 +1,7 @@
 // abi.cpp — the extern "C" surface declared in include/n1gpu.h.  Exceptions never cross it.
 #include <cstring>
 #include <mutex>
+#include <string_view>
 
 #include "execution.hpp"
 #include "query.hpp"
@@ -117,24 +118,45 @@ int n1gpu_table_dict_import(n1gpu_table* t, int col, const char* blob, const int
         REQUIRE(t); REQUIRE(offsets);
         if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
         if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "dictionary exchange happens before seal");
-        if (t->t.device_shredded && !t->t.cols[col].dict.empty())
-            N1_THROW(N1GPU_E_INVALID, "dictionary import into a device-shredded string column is not supported yet (shred with host threads)");
         t->t.build_dictionary(col);
-        Column& c = t->t.cols[col];
         std::vector<std::string> global;
         global.reserve((size_t)ndict);
         for (i64 i = 0; i < ndict; ++i) global.emplace_back(blob + offsets[i], blob + offsets[i + 1]);
         for (size_t i = 1; i < global.size(); ++i)
             if (!(global[i - 1] < global[i])) N1_THROW(N1GPU_E_INVALID, "global dictionary must be sorted bytewise and unique");
-        std::vector<u32> remap(c.dict.size());
-        for (size_t i = 0; i < c.dict.size(); ++i) {
-            auto it = std::lower_bound(global.begin(), global.end(), c.dict[i]);
-            if (it == global.end() || *it != c.dict[i]) N1_THROW(N1GPU_E_INVALID, "global dictionary lacks a local string");
-            remap[i] = (u32)(it - global.begin());
+        t->t.adopt_dictionary(col, global);
+    });
+}
+int n1gpu_table_dict_merge(n1gpu_table* t, int col, int nparts, const char* const* blobs, const int64_t* const* offsets, const int64_t* ndicts) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(blobs); REQUIRE(offsets); REQUIRE(ndicts);
+        if (col < 0 || col >= (int)t->t.cols.size()) N1_THROW(N1GPU_E_INVALID, "no such column");
+        if (t->t.sealed) N1_THROW(N1GPU_E_INVALID, "dictionary exchange happens before seal");
+        if (nparts < 1) N1_THROW(N1GPU_E_INVALID, "no dictionaries to merge");
+        t->t.build_dictionary(col);
+        // k-way merge of the sorted, unique dictionaries (the column's own included) into the global sorted dictionary
+        struct Cur { const char* blob; const int64_t* off; i64 n, at; };
+        std::vector<Cur> cur;
+        for (int p = 0; p < nparts; ++p) if (ndicts[p] > 0) cur.push_back(Cur{blobs[p], offsets[p], (i64)ndicts[p], 0});
+        const auto& own = t->t.cols[col].dict;
+        std::vector<std::string> global;
+        size_t own_at = 0;
+        auto view = [](const Cur& c) { return std::string_view(c.blob + c.off[c.at], (size_t)(c.off[c.at + 1] - c.off[c.at])); };
+        for (;;) {
+            bool any = false;
+            std::string_view best;
+            for (auto& c : cur) if (c.at < c.n) { const std::string_view v = view(c); if (!any || v < best) { best = v; any = true; } }
+            if (own_at < own.size()) { const std::string_view v(own[own_at]); if (!any || v < best) { best = v; any = true; } }
+            if (!any) break;
+            global.emplace_back(best);
+            const std::string& g = global.back();
+            for (auto& c : cur) {
+                if (c.at < c.n && view(c) == std::string_view(g)) ++c.at;
+                if (c.at < c.n && !(std::string_view(g) < view(c))) N1_THROW(N1GPU_E_INVALID, "dictionaries to merge must be sorted bytewise and unique");
+            }
+            if (own_at < own.size() && own[own_at] == g) ++own_at;
         }
-        for (size_t r = 0; r < c.tags.size(); ++r) if (c.tags[r] == C_STRING) c.payload[r] = remap[(size_t)c.payload[r]];
-        c.dict.swap(global);
-        c.dict_global = true;
+        t->t.adopt_dictionary(col, global);
     });
 }
 int n1gpu_table_stats_get(n1gpu_table* t, int col, int64_t stats[8]) {

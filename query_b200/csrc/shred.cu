@@ -369,6 +369,20 @@ void launch_dict_collect(const u64* keys, u64 cap, unsigned* count, u64* out_slo
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }
+// ranks of one dictionary -> ranks of a sorted superset (multi-GPU dictionary agreement on columns that live in HBM)
+__global__ void k_rank_remap(const u8* __restrict__ tags, i64* pay8, u32* pay4, i64 nrows, const u32* __restrict__ remap, u32 n) {
+    for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (i64)gridDim.x * blockDim.x) {
+        if (tags[row] != C_STRING) continue;
+        if (pay4) { const u32 r = pay4[row]; if (r < n) pay4[row] = remap[r]; }
+        else { const u64 r = (u64)pay8[row]; if (r < n) pay8[row] = (i64)remap[r]; }
+    }
+}
+void launch_rank_remap(const u8* tags, i64* pay8, u32* pay4, i64 nrows, const u32* remap, u32 n, cudaStream_t s) {
+    if (nrows == 0 || n == 0) return;
+    k_rank_remap<<<sgrid(nrows, 256), 256, 0, s>>>(tags, pay8, pay4, nrows, remap, n);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
 void launch_dict_ranks(const u64* slot_of_rank, u64 n, u32* rank, cudaStream_t s) {
     if (n == 0) return;
     k_dict_ranks<<<sgrid((i64)n, 256), 256, 0, s>>>(slot_of_rank, n, rank);

@@ -17,6 +17,7 @@ void launch_shred_json(const unsigned char* buf, const i64* offs, i64 ndocs, con
 void launch_dict_insert(const unsigned char* buf, const unsigned char* extra, const u8* tags, const i64* payload, i64* slots, i64 nrows,
                         u64* keys, u64 cap, int* status, cudaStream_t s);
 void launch_dict_collect(const u64* keys, u64 cap, unsigned* count, u64* out_slots, u64* out_refs, u64 out_cap, cudaStream_t s);
+void launch_rank_remap(const u8* tags, i64* pay8, u32* pay4, i64 nrows, const u32* remap, u32 n, cudaStream_t s);
 void launch_dict_ranks(const u64* slot_of_rank, u64 n, u32* rank, cudaStream_t s);
 void launch_dict_remap(const u8* tags, const i64* slots, i64* payload, u32* out32, i64 nrows, const u32* rank, cudaStream_t s);
 void launch_col_stats(const u8* tags, const i64* payload, i64 nrows, u64* stats, cudaStream_t s);

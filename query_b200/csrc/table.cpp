@@ -372,6 +372,26 @@ void Table::set_column(int c, int width, const void* payload, const u8* tags, i6
     nrows = n;
 }
 
+void Table::adopt_dictionary(int ci, std::vector<std::string>& global) {
+    Column& c = cols[(size_t)ci];
+    std::vector<u32> remap(c.dict.size());
+    size_t g = 0;  // both sorted: one walk
+    for (size_t i = 0; i < c.dict.size(); ++i) {
+        while (g < global.size() && global[g] < c.dict[i]) ++g;
+        if (g == global.size() || global[g] != c.dict[i]) N1_THROW(N1GPU_E_INVALID, "global dictionary lacks a local string");
+        remap[i] = (u32)g;
+    }
+    bool identity = remap.size() == global.size();
+    if (!identity || !remap.empty()) for (size_t i = 0; i < remap.size() && identity; ++i) identity = remap[i] == (u32)i;
+    if (!identity && !remap.empty()) {
+        if (c.d_payload.p && (device_shredded || c.device_set)) remap_ranks_device(ci, remap);
+        else for (size_t r = 0; r < c.tags.size(); ++r) if (c.tags[r] == C_STRING) c.payload[r] = remap[(size_t)c.payload[r]];
+    }
+    c.dict.swap(global);
+    c.dict_global = true;
+    if (device_shredded || c.device_set) { c.stats.ndict = (i64)c.dict.size(); c.stats.empty_rank = (!c.dict.empty() && c.dict[0].empty()) ? 0 : -1; }
+}
+
 void Table::build_dictionary(int c) {
     Column& col = cols[c];
     if (col.codes_are_ranks) return;

@@ -70,6 +70,10 @@ struct Table {
     void set_column_device(int col, int width, const void* dev_payload, const u8* dev_tags, i64 nrows, const char* blob,
                            const i64* offs, i64 ndict);
     void build_dictionary(int col);  // local strings -> sorted dict, codes -> ranks
+    // Replaces the column's (sorted) dictionary by a sorted superset and remaps the rows' ranks - staged on the host, or
+    // already in HBM (device shredder, set_column_device).  Multi-GPU: the dictionary every partition agrees on.
+    void adopt_dictionary(int col, std::vector<std::string>& global);
+    void remap_ranks_device(int col, const std::vector<u32>& remap);  // rows of a column resident in HBM: rank -> remap[rank]
     void seal();
     int scan_bytes(int col) const;
     i64 padded_rows() const { return (nrows + ROW_PAD - 1) / ROW_PAD * ROW_PAD; }

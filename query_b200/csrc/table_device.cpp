@@ -293,6 +293,16 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     shred_sec += now_sec() - t0;
 }
 
+void Table::remap_ranks_device(int ci, const std::vector<u32>& remap) {
+    Column& c = cols[(size_t)ci];
+    DevBuf d_map;
+    d_map.alloc(std::max<size_t>(remap.size() * 4, 64));
+    CK(cudaMemcpy(d_map.p, remap.data(), remap.size() * 4, cudaMemcpyHostToDevice));
+    launch_rank_remap(c.d_tags.as<u8>(), c.width == 8 ? c.d_payload.as<i64>() : nullptr, c.width == 4 ? c.d_payload.as<u32>() : nullptr, nrows,
+                      d_map.as<u32>(), (u32)remap.size(), nullptr);
+    CK(cudaDeviceSynchronize());
+}
+
 void Table::set_column_device(int c, int width, const void* dev_payload, const u8* dev_tags, i64 n, const char* blob,
                               const i64* offs, i64 ndict) {
     if (!have_device()) N1_THROW(N1GPU_E_CUDA, "no CUDA device: device columns need one");

@@ -97,25 +97,27 @@ def _merged_stats(allst, ndict):
 
 def agree_dictionaries_and_stats(table, group=None):
     """Before seal: merge every column's dictionary across ranks into the global sorted dictionary and take
-    the union of the statistics, so that all ranks compile the same kernel and pack keys identically."""
+    the union of the statistics, so that all ranks compile the same kernel and pack keys identically.
+    One collective for everything (rows, raw dictionary blobs, statistics of all columns); the merge and the remapping of
+    ranks are native (n1gpu_table_dict_merge: a kernel when the column already lives in HBM)."""
     w = world()
     if w == 1:
         table.set_global_rows(table.num_rows)
         return
-    rows = [None] * w
-    dist.all_gather_object(rows, int(table.num_rows), group=group)
-    table.set_global_rows(sum(rows))  # exact bound for the overflow proofs (packed counters, one-word int sums)
-    for c in range(len(table.columns)):
-        local = table.dictionary(c)
-        gathered = [None] * w
-        dist.all_gather_object(gathered, local, group=group)
-        merged = sorted(set().union(*[set(g) for g in gathered]))
-        st = table.stats(c)
-        allst = [None] * w
-        dist.all_gather_object(allst, st.tolist(), group=group)
-        if merged != list(local):  # identical dictionaries (e.g. handed in with the columns): nothing to remap
-            table.import_dictionary(c, merged)
-        table.set_stats(c, _merged_stats(allst, len(merged)))
+    ncols = len(table.columns)
+    mine = [int(table.num_rows)] + [table.dictionary_raw(c) + (table.stats(c).tolist(),) for c in range(ncols)]
+    every = [None] * w
+    dist.all_gather_object(every, mine, group=group)
+    table.set_global_rows(sum(e[0] for e in every))  # exact bound for the overflow proofs (packed counters, one-word int sums)
+    me = rank()
+    for c in range(ncols):
+        parts = [(e[1 + c][0], e[1 + c][1]) for e in every]
+        same = all(len(o) == len(parts[0][1]) and b.size == parts[0][0].size and np.array_equal(o, parts[0][1]) and np.array_equal(b, parts[0][0])
+                   for b, o in parts[1:])
+        if not same:  # identical dictionaries (e.g. handed in with the columns): nothing to remap
+            table.merge_dictionaries(c, [p for i, p in enumerate(parts) if i != me])
+        ndict = len(parts[0][1]) - 1 if same else len(table.dictionary_raw(c)[1]) - 1
+        table.set_stats(c, _merged_stats([e[1 + c][2] for e in every], ndict))
 
 
 def agree_local(tables):
