@@ -201,7 +201,7 @@ def run_ours(args):
 
     # one peer mailbox + arena per process: small states are merged by peer stores fused into the scan, direct-indexed
     # tables are folded owner-sharded by the finalisation kernel over NVLink; NCCL only moves hash / DISTINCT records
-    mailbox = qd.make_mailbox(max_words=8192, arena_bytes=256 << 20) if world > 1 else None
+    mailbox = qd.make_mailbox(max_words=8192, arena_bytes=(1536 << 20)) if world > 1 else None
 
     def make(w):
         """table + compiled chain + distributed wrapper of a workload, on torch's current stream"""

@@ -241,6 +241,12 @@ void* n1gpu_mailbox_base(n1gpu_mailbox* mb);
 int n1gpu_mailbox_open_peers(n1gpu_mailbox* mb, const uint8_t* handles);
 int n1gpu_mailbox_free(n1gpu_mailbox* mb);
 int n1gpu_query_set_mailbox(n1gpu_query* q, n1gpu_mailbox* mb);
+/* How the query merges across the ranks of its mailbox: 0 = not through the arena (small states are pushed through the
+ * mailbox cells, hash tables / DISTINCT sets are exported as records for the caller to exchange), 1 = its direct-indexed
+ * table lives in the arena and collect() folds + finalises this rank's slot range of every rank's table, 2 = partitioned
+ * DISTINCT aggregation whose records live in the arena: this rank aggregates and finalises its range of partitions.
+ * With 1 and 2 a step is launch() + collect() on every rank, and each rank's result holds its share of the groups.      */
+int n1gpu_query_peer_mode(const n1gpu_query* q);
 
 /* ---- result: what FinalGroup sends downstream ---------------------------------------------------------
  * Per group: the group-key values and, per aggregate (in the order given to compile), the final value

@@ -89,6 +89,7 @@ _SIGS = {
     "n1gpu_mailbox_open_peers": (C.c_int, [_P, C.c_char_p]),
     "n1gpu_mailbox_free": (C.c_int, [_P]),
     "n1gpu_query_set_mailbox": (C.c_int, [_P, _P]),
+    "n1gpu_query_peer_mode": (C.c_int, [_P]),
     "n1gpu_result_num_groups": (C.c_int64, [_P]),
     "n1gpu_result_num_keys": (C.c_int, [_P]),
     "n1gpu_result_num_aggregates": (C.c_int, [_P]),

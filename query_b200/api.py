@@ -469,6 +469,11 @@ class Query:
         check(lib().n1gpu_query_set_mailbox(self._h, mailbox._h if mailbox is not None else None))
         self._mailbox = mailbox
 
+    @property
+    def peer_mode(self):
+        """0: no arena merge, 1: direct-indexed table folded owner-sharded, 2: partitioned DISTINCT aggregation over peers"""
+        return check(lib().n1gpu_query_peer_mode(self._h))
+
     def close(self):
         if self._h:
             lib().n1gpu_query_free(self._h)

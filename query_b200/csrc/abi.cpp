@@ -317,7 +317,7 @@ int n1gpu_mailbox_create_arena(int nranks, int rank, int64_t max_words, int64_t 
         Mailbox& m = mb->m;
         m.nranks = nranks; m.rank = rank; m.stride = (u64)max_words + 1;
         m.flags_off = ((size_t)m.slots * nranks * m.stride * 8 + 255) & ~(size_t)255;
-        m.arena_off = (m.flags_off + (size_t)64 * nranks * 8 + 255) & ~(size_t)255;
+        m.arena_off = (m.flags_off + (size_t)2 * 64 * nranks * 8 + 255) & ~(size_t)255;  // rows 0-63: table complete, 64-127: records consumed
         m.arena_bytes = (size_t)arena_bytes;
         m.bytes = m.arena_off + m.arena_bytes;
         CK(cudaMalloc(&m.base, m.bytes));
@@ -376,6 +376,15 @@ int n1gpu_query_set_mailbox(n1gpu_query* q, n1gpu_mailbox* mb) {
         if (mb && mb->m.nranks > 1 && !mb->m.d_peers.p) N1_THROW(N1GPU_E_INVALID, "mailbox peers are not opened");
         q->q->attach_mailbox(mb ? &mb->m : nullptr);
     });
+}
+
+int n1gpu_query_peer_mode(const n1gpu_query* q) {
+    if (!q) return N1GPU_E_INVALID;
+    const Query& Q = *q->q;
+    if (!Q.mailbox || Q.mailbox->nranks < 2) return 0;
+    if (Q.peer_part && Q.use_part()) return 2;
+    if (Q.peer_table) return 1;
+    return 0;
 }
 
 // ---- multi-GPU partial state ----------------------------------------------------------------------------------

@@ -519,6 +519,11 @@ __global__ void k_peer_signal(u64* const* peers, int nranks, int rank, u64 flags
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
     }
 }
+void launch_peer_wait(const u64* flags, int nranks, u64 seq, int* status, cudaStream_t s) {
+    k_peer_wait<<<1, 32, 0, s>>>(flags, nranks, seq, status);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
 void launch_peer_signal(u64* const* peers, int nranks, int rank, u64 flags_word_off, u64 seq, cudaStream_t s) {
     k_peer_signal<<<1, 64, 0, s>>>(peers, nranks, rank, flags_word_off, seq);
     g_launches.fetch_add(1);

@@ -54,6 +54,8 @@ struct PeerTables {
 };
 // Raises this rank's flag of step `seq` in every rank's flag row: peers[r][flags_word_off + (seq % 64) * nranks + rank] = seq.
 void launch_peer_signal(u64* const* peers, int nranks, int rank, u64 flags_word_off, u64 seq, cudaStream_t s);
+// One block that returns once flags[r] == seq for every r < nranks (bounded spin: status[0] = 3 after ~10 s).
+void launch_peer_wait(const u64* flags, int nranks, u64 seq, int* status, cudaStream_t s);
 // Finalises the live groups of slots [slot0, slot1) into compact flat arrays (n1gpu_result_fetch layout); *counter
 // (zeroed by the caller) ends as the number of groups written; groups beyond out_cap are counted but not written.
 void launch_finalize_groups(const FinalDesc& D, int kw, const u64* keys, const PeerTables& T, const OpsArr& ops, u64 ws, u64 ss, u64 slot0,

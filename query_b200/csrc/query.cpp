@@ -56,6 +56,7 @@ bool have_device() {
 Query::~Query() {
     if (launched && stream) cudaStreamSynchronize(stream);  // nothing of this query may still be running when its buffers are recycled
     if (peer_table && mailbox) { mailbox->arena_free(peer_off[1], peer_bytes); mailbox->arena_free(peer_off[0], peer_bytes); }
+    if (peer_part && mailbox) { mailbox->arena_free(peer_cur_off, peer_cur_bytes); mailbox->arena_free(peer_recs_off, peer_recs_bytes); }
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -170,6 +171,8 @@ bool Query::uses_status() const { return kp.mode == MODE_HASH64 || kp.mode == MO
 void Query::attach_mailbox(Mailbox* mb) {
     if (launched) N1_THROW(N1GPU_E_INVALID, "a scan is outstanding");
     if (peer_table && mailbox) { mailbox->arena_free(peer_off[1], peer_bytes); mailbox->arena_free(peer_off[0], peer_bytes); }
+    if (peer_part && mailbox) { mailbox->arena_free(peer_cur_off, peer_cur_bytes); mailbox->arena_free(peer_recs_off, peer_recs_bytes); }
+    peer_part = false;
     mailbox = mb;
     peer_table = false;
     peer_seq = 0;
@@ -179,6 +182,17 @@ void Query::attach_mailbox(Mailbox* mb) {
         peer_off[0] = mb->arena_alloc(peer_bytes);
         peer_off[1] = mb->arena_alloc(peer_bytes);
         peer_table = true;
+    }
+    if (mb && mb->arena_bytes && mb->nranks > 1 && use_part() && table->global_rows > 0) {
+        // every rank must lay its records out alike (peers index them): the share is derived from agreed numbers only
+        const u64 np = (u64)1 << kp.part_bits;
+        part_cap = ((u64)table->global_rows / (u64)mb->nranks / np + 1) * 3 / 2 + 4096;
+        peer_recs_bytes = (size_t)(np * part_cap) * 4;
+        peer_cur_bytes = (size_t)np * 4;
+        peer_recs_off = mb->arena_alloc(peer_recs_bytes);
+        peer_cur_off = mb->arena_alloc(peer_cur_bytes);
+        peer_part = true;
+        part_seq = 0;
     }
 }
 
@@ -233,24 +247,49 @@ void Query::launch_scan() {
     if (use_part()) {
         // partitioned DISTINCT aggregation: records partitioned by group range, then one block per partition
         const int np = 1 << kp.part_bits;
+        const bool peers = peer_part_merge();
+        u32* recs = peers ? (u32*)((char*)mailbox->base + peer_recs_off) : d_part_recs.as<u32>();
+        u32* cur = peers ? (u32*)((char*)mailbox->base + peer_cur_off) : d_part_cur.as<u32>();
+        const u64 nr = peers ? (u64)mailbox->nranks : 1;
+        const u64* flags = peers ? (const u64*)((const char*)mailbox->base + mailbox->flags_off) : nullptr;
         CK(cudaMemsetAsync(d_status.p, 0, 64, stream));
-        CK(cudaMemsetAsync(d_part_cur.p, 0, (size_t)np * 4, stream));
+        u64 seq = 0;
+        if (peers) {
+            seq = ++mailbox->seq;
+            // the records of this rank's previous step may still be read by a peer: wait for everybody's "consumed" flag
+            if (part_seq) launch_peer_wait(flags + (64 + part_seq % 64) * nr, (int)nr, part_seq, d_status.as<int>(), stream);
+        }
+        CK(cudaMemsetAsync(cur, 0, (size_t)np * 4, stream));
         if (timing) CK(cudaEventRecord(ev0, stream));
-        p.set_keys = d_part_recs.as<u64>();
-        p.keys = d_part_cur.as<u64>();
+        p.set_keys = (u64*)recs;
+        p.keys = (u64*)cur;
         p.set_mask = part_cap;
         const i64 tiles = (table->nrows + 4095) / 4096;
         const int pgrid = (int)std::max<i64>(1, std::min<i64>((tiles + 7) / 8, device_sm_count()));
         jit_launch(*part_kernel, pgrid, stream, &p, sizeof p, false);
         PartPeers P;
         memset(&P, 0, sizeof P);
-        P.n = 1;
-        P.recs[0] = d_part_recs.as<u32>();
-        P.cur[0] = d_part_cur.as<u32>();
+        P.n = (int)nr;
+        P.recs[0] = recs;
+        P.cur[0] = cur;
+        if (peers) {
+            launch_peer_signal((u64* const*)mailbox->d_peers.p, (int)nr, mailbox->rank, mailbox->flags_off / 8, seq, stream);
+            launch_peer_wait(flags + (seq % 64) * nr, (int)nr, seq, d_status.as<int>(), stream);
+            for (int r = 0; r < (int)nr; ++r) {
+                P.recs[r] = (const u32*)((const char*)mailbox->peers[(size_t)r] + peer_recs_off);
+                P.cur[r] = (const u32*)((const char*)mailbox->peers[(size_t)r] + peer_cur_off);
+            }
+        }
+        int part0, part1;
+        part_range(&part0, &part1);
         const DistinctDescs D = distinct_descs();
         const PackComp* dc = nullptr;
         for (auto& ap : kp.aggs) if (ap.distinct) { dc = &ap.dcomp; break; }
-        launch_part_aggregate(P, part_cap, 0, np, kp.part_gbits, kp.part_vbits, kp.phys_of[0], D, dc->classes[0] == C_INT, dc->bias, acc(), cap, stream);
+        launch_part_aggregate(P, part_cap, part0, part1, kp.part_gbits, kp.part_vbits, kp.phys_of[0], D, dc->classes[0] == C_INT, dc->bias, acc(), cap, stream);
+        if (peers) {
+            launch_peer_signal((u64* const*)mailbox->d_peers.p, (int)nr, mailbox->rank, mailbox->flags_off / 8 + 64 * nr, seq, stream);
+            part_seq = seq;
+        }
         if (timing) CK(cudaEventRecord(ev1, stream));
         timed_launch = timing;
         CK(cudaMemcpyAsync(h_status.p, d_status.p, 8, cudaMemcpyDeviceToHost, stream));
@@ -293,6 +332,8 @@ bool Query::wait_scan() {
     }
     int st = uses_status() ? h_status.as<int>()[0] : 0;
     if (st == 3) N1_THROW(N1GPU_E_CUDA, "multi-GPU merge timed out: a peer rank never delivered its partial state");
+    if (st == 4 && peer_part_merge())
+        N1_THROW(N1GPU_E_NOMEM, "a partition of the partitioned DISTINCT aggregation overflowed its share (skewed group keys): run this chain with N1GPU_NO_PART=1 on every rank");
     if (st == 4) {  // a partition overflowed (skewed group keys): the general one-kernel scan takes over for this handle
         part_disabled = true;
         part_done = false;
@@ -602,6 +643,12 @@ std::unique_ptr<Result> Query::finalize() {
         T.n = 1;
         T.acc[0] = acc();
         u64 s0 = 0, s1 = cap;
+        if (part_done && peer_part_merge()) {  // this rank aggregated (and now finalises) its range of partitions only
+            int part0, part1;
+            part_range(&part0, &part1);
+            s0 = (u64)part0 << kp.part_gbits;
+            s1 = std::min<u64>(cap, (u64)part1 << kp.part_gbits);
+        }
         if (peer_merge() && peer_seq) {
             // IntermediateGroup + FinalGroup fused and owner-sharded: this rank folds ITS slot range of every rank's table
             T.n = mailbox->nranks;

@@ -102,6 +102,18 @@ struct Query {
     u64 part_cap = 0;                        // records a partition holds
     DevBuf d_part_recs, d_part_cur;
     bool use_part() const { return part_kernel && !part_disabled; }
+    // multi-GPU: the partitioned records live in the mailbox arena; rank r aggregates partition range r reading every
+    // rank's records of those partitions over NVLink, and finalises the groups of that range
+    bool peer_part = false;
+    size_t peer_recs_off = 0, peer_cur_off = 0, peer_recs_bytes = 0, peer_cur_bytes = 0;
+    u64 part_seq = 0;   // step whose records this rank last published (its consumption is awaited before they are overwritten)
+    bool peer_part_merge() const { return peer_part && mailbox && mailbox->nranks > 1 && use_part(); }
+    void part_range(int* p0, int* p1) const {
+        const int np = 1 << kp.part_bits;
+        if (!peer_part_merge()) { *p0 = 0; *p1 = np; return; }
+        *p0 = (int)((i64)np * mailbox->rank / mailbox->nranks);
+        *p1 = (int)((i64)np * (mailbox->rank + 1) / mailbox->nranks);
+    }
     DistinctDescs distinct_descs() const;
     OpsArr ops{};
 

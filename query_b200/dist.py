@@ -173,10 +173,6 @@ class DistributedQuery:
         self.small = query.info["mode"] in ("ungrouped", "dense-shared-memory", "hbm-direct") and "distinct" not in " ".join(query.aggregates)
         # with a peer mailbox the merge of a small-state chain is fused into the scan: launch()/collect() only
         self.fused = bool(mailbox is not None and self.small and world() > 1 and query.info["mode"] != "hbm-direct")
-        # a direct-indexed HBM table (megabytes, slot == key on every rank) lives in the mailbox arena: every rank folds and
-        # finalises its slot range of all ranks' tables over NVLink - no collective, no replicated finalisation
-        self.peer = bool(mailbox is not None and getattr(mailbox, "arena_bytes", 0) and self.small and world() > 1
-                         and query.info["mode"] == "hbm-direct")
         if world() > 1:
             # ranks whose kernels differ (a layout threshold crossed on one rank only) would enter different collectives and
             # merge slot-indexed words with hashed records: refuse that here, where it is an error message and not a hang
@@ -187,11 +183,19 @@ class DistributedQuery:
             if any(e != every[0] for e in every):
                 raise RuntimeError("ranks compiled different kernels for one chain (declare the keyspace rows and agree the "
                                    "statistics before seal: agree_dictionaries_and_stats): %r" % ([e[:2] for e in every],))
-        if self.fused or self.peer:
+        # A direct-indexed HBM table (megabytes, slot == key on every rank) lives in the mailbox arena: every rank folds and
+        # finalises its slot range of all ranks' tables over NVLink.  A partitioned DISTINCT aggregation keeps its records
+        # there: rank r aggregates and finalises partition range r.  Neither needs a collective or a replicated finalisation.
+        self.peer = self.peer_part = False
+        if mailbox is not None and world() > 1:
             query.set_mailbox(mailbox)
+            self.peer_part = query.peer_mode == 2
+            self.peer = query.peer_mode in (1, 2)
+            if not (self.fused or self.peer):
+                query.set_mailbox(None)
         if self.peer:
             self.small = False  # the result is owner-sharded, not replicated
-        elif self.small and world() > 1 and stream is None:
+        elif self.small and world() > 1 and stream is None and not self.fused:
             # the NCCL all_gather is ordered against torch's current stream: the scan must run on that stream too
             query.set_stream(torch.cuda.current_stream().cuda_stream)
         self._recs = None
@@ -210,6 +214,9 @@ class DistributedQuery:
     def describe(self):
         if world() == 1:
             return "none (one rank)"
+        if self.peer_part:
+            return ("owner-sharded and collective-free: (group, value) records partitioned by group range into a CUDA-IPC peer arena, flags per rank "
+                    "and step, rank r aggregates partition range r from every rank's records over NVLink and finalises those groups")
         if self.peer:
             return ("owner-sharded and collective-free: direct-indexed tables in a CUDA-IPC peer arena, a release flag per rank and step, "
                     "rank r's k_finalize_groups folds slot range r of every rank's table over NVLink and finalises those groups")

@@ -188,6 +188,43 @@ def test_peer_arena_merge_owner_sharded(nranks):
         assert_same(exp, got, "peer merge, %d ranks, step %d" % (nranks, step))
 
 
+def test_peer_arena_partitioned_distinct(monkeypatch):
+    """BASELINE config 4 across ranks, all driven by this process on one device: every rank partitions its rows' (group,
+    value) records into its arena, rank r aggregates partition range r from every rank's records and finalises exactly
+    those groups; three steps reuse the single record buffer behind the "consumed" flags."""
+    from gen_n1 import config4_docs
+    from query_b200 import dist as qd
+    monkeypatch.setenv("N1GPU_PART", "1")
+    nranks = 3
+    docs = config4_docs(24000, 30000, 43)
+    where, keys = None, ["(`d`.`g`)"]
+    aggs = ["count(distinct (`d`.`x`))", "sum(distinct (`d`.`x`))", "count(*)"]
+    parts = [docs[len(docs) * r // nranks: len(docs) * (r + 1) // nranks] for r in range(nranks)]
+    tables = [make_table(p, where, keys, aggs) for p in parts]
+    qd.agree_local(tables)
+    mbs = [q.Mailbox(nranks, r, 1024, arena_bytes=16 << 20) for r in range(nranks)]
+    for r in range(nranks):
+        for o in range(nranks):
+            mbs[r].set_peer(o, mbs[o].base)
+    qs = []
+    for r in range(nranks):
+        tables[r].seal()
+        qq = q.Query(tables[r], "d", where, keys, aggs)
+        qq.set_mailbox(mbs[r])
+        assert qq.peer_mode == 2 and qq.part_source
+        qs.append(qq)
+    exp = oracle_rows(docs, "d", where, keys, aggs)
+    for step in range(3):
+        for qq in qs:
+            qq.launch()
+        got = {}
+        for qq in qs:
+            part = gpu_rows(qq.collect(), aggs)
+            assert not (set(part) & set(got)), "a group was finalised by two ranks"
+            got.update(part)
+        assert_same(exp, got, "partitioned distinct over peers, step %d" % step)
+
+
 @pytest.mark.parametrize("n", [0, 1, 3, 127, 128, 129, 1023, 1024, 1025, 4097])
 def test_ragged_sizes(n):
     docs = make_docs(n, seed=100 + n)
