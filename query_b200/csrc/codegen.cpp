@@ -1180,17 +1180,30 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         q += "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
         q += "    const i64 tile = NQ_BLOCK * 4;\n";
         q += "    const i64 ntiles = (nrows + tile - 1) / tile;\n";
-        q += "    for (i64 t0 = (i64)blockIdx.x * ROUND_TILES; t0 < ntiles; t0 += (i64)gridDim.x * ROUND_TILES) {\n";
+        // columns of the tile being processed (c*, t*) and of the next tile this block will process (nc*, nt*): the next
+        // tile's loads are in flight while this one is partitioned - also across the flush at the end of a round
+        std::string load_next, take_next;
+        for (int c : kp.used_cols) {
+            const Column& col = t.cols[c];
+            const bool tags = !col.stats.uniform_tag() && col.stats.class_mask;
+            if (col.width == 8) { q += strf("    i64 c%d[4], nc%d[4];\n", c, c); load_next += strf("ld_rows4_b64((const i64*)p.col[%d] + nb, nc%d); ", c, c); }
+            else if (col.width == 4) { q += strf("    u32 c%d[4], nc%d[4];\n", c, c); load_next += strf("ld_rows4_b32((const u32*)p.col[%d] + nb, nc%d); ", c, c); }
+            if (col.width) take_next += strf("c%d[j] = nc%d[j]; ", c, c);
+            if (tags) { q += strf("    int t%d[4], nt%d[4];\n", c, c); load_next += strf("ld_rows4_b8(p.tag[%d] + nb, nt%d); ", c, c); take_next += strf("t%d[j] = nt%d[j]; ", c, c); }
+        }
+        q += "    const i64 round_stride = (i64)gridDim.x * ROUND_TILES;\n";
+        q += "    { const i64 nt_ = (i64)blockIdx.x * ROUND_TILES; if (nt_ < ntiles) { const i64 nb = nt_ * tile + threadIdx.x * 4; " + load_next + "} }\n";
+        q += "    for (i64 t0 = (i64)blockIdx.x * ROUND_TILES; t0 < ntiles; t0 += round_stride) {\n";
         q += "        for (int i = threadIdx.x; i < NP; i += NQ_BLOCK) s_cnt[i] = 0;\n";
         q += "        __syncthreads();\n";
         q += "        for (int tt = 0; tt < ROUND_TILES && t0 + tt < ntiles; ++tt) {\n";
         q += "        const i64 base = (t0 + tt) * tile + threadIdx.x * 4;\n";
-        for (int c : kp.used_cols) {
-            const Column& col = t.cols[c];
-            if (col.width == 8) q += strf("        i64 c%d[4]; ld_rows4_b64((const i64*)p.col[%d] + base, c%d);\n", c, c, c);
-            else if (col.width == 4) q += strf("        u32 c%d[4]; ld_rows4_b32((const u32*)p.col[%d] + base, c%d);\n", c, c, c);
-            if (!col.stats.uniform_tag() && col.stats.class_mask) q += strf("        int t%d[4]; ld_rows4_b8(p.tag[%d] + base, t%d);\n", c, c, c);
-        }
+        q += "#pragma unroll\n";
+        q += "        for (int j = 0; j < 4; ++j) { " + take_next + "}\n";
+        q += "        {   // the tile after this one: the next of the round, or the first of this block's next round\n";
+        q += "            const i64 nt_ = (tt + 1 < ROUND_TILES && t0 + tt + 1 < ntiles) ? t0 + tt + 1 : t0 + round_stride;\n";
+        q += "            if (nt_ < ntiles) { const i64 nb = nt_ * tile + threadIdx.x * 4; " + load_next + "}\n";
+        q += "        }\n";
         q += "#pragma unroll\n";
         q += "        for (int j = 0; j < 4; ++j) {\n";
         q += "            bool pass = base + j < nrows;\n";

@@ -421,13 +421,19 @@ __global__ void __launch_bounds__(1024, 1) k_part_aggregate(const PartPeers P, u
         for (int t = 0; t < P.n; ++t) {
             const u64 n = min((u64)__ldcg(&P.cur[t][part]), part_cap);
             const u32* __restrict__ r = P.recs[t] + (u64)part * part_cap;
-            for (u64 i = threadIdx.x; i < n; i += blockDim.x) {
-                const u32 rec = __ldcg(&r[i]);
-                const u32 g = rec & gmask;
-                atomicAdd(&s_cnt[g], 1u);
-                if ((rec >> gbits) & 1u) {
-                    const u32 v = rec >> (gbits + 1);
-                    atomicOr(&s_bm[(g << wshift) + (v >> 5)], 1u << (v & 31));
+            for (u64 i0 = threadIdx.x; i0 < n; i0 += (u64)blockDim.x * 8) {
+                u32 rec[8];  // eight loads in flight per thread before the first is used
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const u64 i = i0 + (u64)k * blockDim.x; rec[k] = i < n ? __ldcg(&r[i]) : 0u; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (i0 + (u64)k * blockDim.x >= n) break;
+                    const u32 g = rec[k] & gmask;
+                    atomicAdd(&s_cnt[g], 1u);
+                    if ((rec[k] >> gbits) & 1u) {
+                        const u32 v = rec[k] >> (gbits + 1);
+                        atomicOr(&s_bm[(g << wshift) + (v >> 5)], 1u << (v & 31));
+                    }
                 }
             }
         }
