@@ -147,9 +147,12 @@ def rows(docs_or_packed, alias, where, keys, aggs, threads=1):
     return out
 
 
-def gen_docs(config, seed, first, n):
-    """Synthetic documents of BASELINE.json config 2..5 as (uint8 buffer, int64 offsets)."""
+def gen_docs(config, seed, first, n, newline=False):
+    """Synthetic documents of BASELINE.json config 2..5 as (uint8 buffer, int64 offsets); newline=True ends every document
+    with a line end (NDJSON: the buffer is then a packed keyspace file as it stands)."""
     L = lib()
+    if newline:
+        config |= 0x100
     cap = int(n) * 320 + 1024
     buf = np.empty(cap, dtype=np.uint8)
     offs = np.empty(int(n) + 1, dtype=np.int64)

@@ -717,10 +717,13 @@ static int gen_doc(int config, unsigned long long seed, long long row, char* out
 /* Fills buf/offs with docs [first, first+n); returns bytes used (or -1 when cap is too small). Single-threaded per call. */
 long long oracle_gen_docs(int config, unsigned long long seed, long long first, long long n, char* buf, long long cap, long long* offs) {
     long long at = 0;
+    const int newline = config & 0x100;  /* NDJSON: a line end closes every document (trailing white space of the document) */
+    config &= 0xff;
     for (long long i = 0; i < n; ++i) {
         if (at + 512 > cap) return -1;
         offs[i] = at;
         at += gen_doc(config, seed, first + i, buf + at);
+        if (newline) buf[at++] = '\n';
     }
     offs[n] = at;
     return at;

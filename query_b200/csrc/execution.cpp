@@ -189,8 +189,16 @@ std::shared_ptr<Table> resident_table(const std::string& dir, std::vector<std::s
     std::string key = dir;
     for (auto& p : paths) { key.push_back('\n'); key += p; }
     struct stat st;
-    if (stat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) N1_THROW(N1GPU_E_IO, "keyspace directory %s not found", dir.c_str());
-    const std::string tag = keyspace_source_tag(dir);  // the resident table and the segment live as long as this holds
+    // A keyspace too large for one file per document (file.go:312-353) is kept packed: <namespace>/<keyspace>.ndjson, one
+    // document per line in primary-key order, takes the place of the directory <namespace>/<keyspace>/.
+    const std::string packed = dir + ".ndjson";
+    const bool is_dir = stat(dir.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+    struct stat pst;
+    const bool is_packed = !is_dir && stat(packed.c_str(), &pst) == 0 && S_ISREG(pst.st_mode);
+    if (!is_dir && !is_packed) N1_THROW(N1GPU_E_IO, "keyspace directory %s not found", dir.c_str());
+    // the resident table and the segment live as long as this tag holds
+    const std::string tag = is_dir ? keyspace_source_tag(dir)
+                                   : strf("ndjson mtime=%lld.%09lld bytes=%lld", (long long)pst.st_mtim.tv_sec, (long long)pst.st_mtim.tv_nsec, (long long)pst.st_size);
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_tables.find(key);
@@ -205,7 +213,14 @@ std::shared_ptr<Table> resident_table(const std::string& dir, std::vector<std::s
         from_segment = t->load_segment(file, tag);
         if (!from_segment) { t->segment_out = file; t->segment_source = tag; }
     }
-    if (!from_segment) t->load_dir(dir, 0);
+    if (!from_segment) {
+        // The documents are shredded on the device (raw text -> HBM once, no column crosses PCIe) unless a segment is to be
+        // written from the host shredder's staging, or N1GPU_OPERATOR_SHRED=host asks for the host threads.
+        const char* how = getenv("N1GPU_OPERATOR_SHRED");
+        const bool host = !have_device() || !t->segment_out.empty() || (how && std::string(how) == "host") || paths.empty();
+        const int threads = host ? 0 : -1;
+        if (is_dir) t->load_dir(dir, threads); else t->load_ndjson(packed, threads);
+    }
     t->global_rows = t->nrows;  // the operator runs the whole keyspace in this process: one partition
     t->seal();
     std::lock_guard<std::mutex> lk(g_cache_mu);

@@ -16,6 +16,9 @@
 #include <fstream>
 
 #include "json.hpp"
+#include <fcntl.h>
+#include <unistd.h>
+#include <thread>
 #include "table.hpp"
 
 namespace n1 {
@@ -134,54 +137,71 @@ bool Table::load_segment(const std::string& file, const std::string& source) {
 // A packed document source: one JSON document per line (NDJSON), in primary-key order - the form a keyspace of more
 // than a few million documents takes when one file per document (file.go) stops being practical.
 void Table::load_ndjson(const std::string& file, int threads) {
-    FILE* fp = fopen(file.c_str(), "rb");
-    if (!fp) N1_THROW(N1GPU_E_IO, "cannot read %s", file.c_str());
-    std::string buf;
+    const int fd = open(file.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) N1_THROW(N1GPU_E_IO, "cannot read %s", file.c_str());
+    struct FdGuard { int fd; ~FdGuard() { close(fd); } } fg{fd};
     struct stat st;
-    if (fstat(fileno(fp), &st) == 0 && st.st_size > 0) buf.resize((size_t)st.st_size);
-    size_t got = buf.empty() ? 0 : fread(&buf[0], 1, buf.size(), fp);
-    buf.resize(got);
-    for (char chunk[1 << 16];;) {  // whatever a growing file (or a pipe) still holds
-        size_t n = fread(chunk, 1, sizeof chunk, fp);
-        if (n == 0) break;
-        buf.append(chunk, n);
-    }
-    fclose(fp);
-    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r'; };
-    if (threads >= 0) {
-        // host shredder, in place: document i = [start of its line, start of the next non-blank line) - the line end and
-        // blank lines are trailing white space of the document (value/parsed.go:76-98 skips leading ' ', '\t', '\n')
-        std::vector<i64> offsets;
-        size_t i = 0;
-        while (i < buf.size()) {
-            size_t e = buf.find('\n', i);
-            if (e == std::string::npos) e = buf.size();
-            size_t a = i;
-            while (a < e && blank(buf[a])) ++a;
-            if (a < e) offsets.push_back((i64)i);
-            i = e + 1;
+    size_t size = 0;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) size = (size_t)st.st_size;
+    // The text goes straight into pinned memory when the device shredder will take it (the H2D copy then runs at PCIe
+    // speed without a staging copy), read and scanned for line starts by all cores: a keyspace of 10^7 documents is
+    // hundreds of megabytes, and one core reads and scans ~8 GB/s.
+    const bool device = threads < 0;
+    PinnedBuf pin;
+    std::string heap;
+    char* data = nullptr;
+    if (device && have_device()) { pin.ensure(size + 64); data = pin.as<char>(); }
+    else { heap.resize(size + 64); data = &heap[0]; }
+    int nthr = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if ((size_t)nthr > size / ((size_t)4 << 20) + 1) nthr = (int)(size / ((size_t)4 << 20) + 1);
+    auto slice = [&](int t) { return size * (size_t)t / (size_t)nthr; };
+    std::vector<std::string> errs((size_t)nthr);
+    auto run = [&](auto&& fn) {
+        if (nthr == 1) { fn(0); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthr; ++t) pool.emplace_back(fn, t);
+        for (auto& th : pool) th.join();
+    };
+    run([&](int t) {
+        size_t at = slice(t);
+        const size_t end = slice(t + 1);
+        while (at < end) {
+            const ssize_t got = pread(fd, data + at, end - at, (off_t)at);
+            if (got <= 0) { errs[(size_t)t] = "short read of " + file; return; }
+            at += (size_t)got;
         }
-        const i64 ndocs = (i64)offsets.size();
-        offsets.push_back((i64)buf.size());
-        if (ndocs == 0) offsets.assign(1, 0);
-        append_json(buf.data(), offsets.data(), ndocs, threads);
-        return;
-    }
+    });
+    for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_IO, "%s", e.c_str());
+    // document i = [start of its line, start of the next non-blank line): the line end and blank lines are trailing white
+    // space of the document before them (value/parsed.go:76-98 skips leading ' ', '\t', '\n'; JSON allows trailing space)
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r'; };
+    std::vector<std::vector<i64>> starts((size_t)nthr);
+    run([&](int t) {
+        auto& out = starts[(size_t)t];
+        auto consider = [&](size_t s0) {  // a line that begins at s0: a document unless it is blank
+            size_t a = s0;
+            while (a < size && blank(data[a])) ++a;
+            if (a < size && data[a] != '\n') out.push_back((i64)s0);
+        };
+        const size_t lo = slice(t), hi = slice(t + 1);
+        if (t == 0 && size) consider(0);
+        const char* p = data + lo;
+        while (p < data + hi) {
+            const char* e = (const char*)memchr(p, '\n', (size_t)(data + hi - p));
+            if (!e) break;
+            if ((size_t)(e + 1 - data) < size) consider((size_t)(e + 1 - data));
+            p = e + 1;
+        }
+    });
     std::vector<i64> offsets;
-    std::string packed;
-    packed.reserve(buf.size());
-    offsets.push_back(0);
-    size_t i = 0;
-    while (i < buf.size()) {
-        size_t e = buf.find('\n', i);
-        if (e == std::string::npos) e = buf.size();
-        size_t a = i, b = e;
-        while (a < b && blank(buf[a])) ++a;
-        while (b > a && blank(buf[b - 1])) --b;
-        if (b > a) { packed.append(buf, a, b - a); offsets.push_back((i64)packed.size()); }  // blank lines are not documents
-        i = e + 1;
-    }
-    append_json_device(packed.data(), offsets.data(), (i64)offsets.size() - 1);
+    size_t ndocs = 0;
+    for (auto& v : starts) ndocs += v.size();
+    offsets.reserve(ndocs + 1);
+    for (auto& v : starts) offsets.insert(offsets.end(), v.begin(), v.end());
+    offsets.push_back((i64)size);
+    if (ndocs == 0) offsets.assign(1, 0);
+    if (device) append_json_device(data, offsets.data(), (i64)ndocs);
+    else append_json(data, offsets.data(), (i64)ndocs, threads);
 }
 
 }  // namespace n1

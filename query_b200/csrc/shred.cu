@@ -228,9 +228,9 @@ __device__ int sh_document(const unsigned char* base, i64 b, i64 e, const ShredT
     }
 }
 
-__global__ void __launch_bounds__(128) k_shred_json(const unsigned char* __restrict__ buf, const i64* __restrict__ offs, i64 ndocs, const ShredTrie* __restrict__ Tp,
+__global__ void __launch_bounds__(128) k_shred_json(const unsigned char* __restrict__ buf, const i64* __restrict__ offs, i64 first, i64 ndocs, const ShredTrie* __restrict__ Tp,
                                                     u8* const* tags, i64* const* payload, int ncols, unsigned* fix_count, i64* fix_rows, i64 fix_cap) {
-    for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < ndocs; row += (i64)gridDim.x * blockDim.x) {
+    for (i64 row = first + (i64)blockIdx.x * blockDim.x + threadIdx.x; row < first + ndocs; row += (i64)gridDim.x * blockDim.x) {
         Out out{tags, payload, row};
         const int rc = sh_document(buf, offs[row], offs[row + 1], *Tp, out);
         if (rc != 0) {
@@ -352,9 +352,10 @@ static int sgrid(i64 n, int block) {
     return (int)g;
 }
 
-void launch_shred_json(const unsigned char* buf, const i64* offs, i64 ndocs, const ShredTrie* T, u8* const* tags, i64* const* payload,
+void launch_shred_json(const unsigned char* buf, const i64* offs, i64 first, i64 ndocs, const ShredTrie* T, u8* const* tags, i64* const* payload,
                        int ncols, unsigned* fix_count, i64* fix_rows, i64 fix_cap, cudaStream_t s) {
-    k_shred_json<<<sgrid(ndocs, 128), 128, 0, s>>>(buf, offs, ndocs, T, tags, payload, ncols, fix_count, fix_rows, fix_cap);
+    if (ndocs <= 0) return;
+    k_shred_json<<<sgrid(ndocs, 128), 128, 0, s>>>(buf, offs, first, ndocs, T, tags, payload, ncols, fix_count, fix_rows, fix_cap);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }

@@ -12,7 +12,7 @@ struct ShredTrie {
     char names[2048];
 };
 
-void launch_shred_json(const unsigned char* buf, const i64* offs, i64 ndocs, const ShredTrie* T, u8* const* tags, i64* const* payload,
+void launch_shred_json(const unsigned char* buf, const i64* offs, i64 first, i64 ndocs, const ShredTrie* T, u8* const* tags, i64* const* payload,
                        int ncols, unsigned* fix_count, i64* fix_rows, i64 fix_cap, cudaStream_t s);
 void launch_dict_insert(const unsigned char* buf, const unsigned char* extra, const u8* tags, const i64* payload, i64* slots, i64 nrows,
                         u64* keys, u64 cap, int* status, cudaStream_t s);

@@ -289,6 +289,15 @@ void Table::load_dir(const std::string& dir, int threads) {
     }
     closedir(d);
     std::sort(names.begin(), names.end());  // ioutil.ReadDir order
+    // The primary index scans IDS, not files: every non-directory entry yields the id "name minus its last extension"
+    // (documentPathToId, file.go:757-761), and Fetch reads <id>.json (file.go:346) - a missing file is silently no document
+    // (file.go:319-322), an unreadable one is an error the request reports while it carries on.  So foo.txt is a document only
+    // if foo.json exists (and a.json + a.txt are TWO rows of a.json), .DS_Store and editor backups are none.
+    for (auto& n : names) {
+        const size_t dot = n.rfind('.');
+        if (dot != std::string::npos) n.resize(dot);
+        n += ".json";
+    }
     // The reference opens and reads one file per document, serially (file.go:732-743).  Here the reads of contiguous
     // ranges of the sorted names run on all cores - they are system calls on (mostly cached) small files - and the
     // documents are then laid end to end in primary-key order for the shredder.
@@ -306,20 +315,21 @@ void Table::load_dir(const std::string& dir, int threads) {
         for (size_t i = lo; i < hi; ++i) {
             path.assign(dir).append("/").append(names[i]);
             const int fd = open(path.c_str(), O_RDONLY | O_CLOEXEC);
-            if (fd < 0) { part.err = "cannot read " + path; return; }
+            if (fd < 0) continue;  // ENOENT: the id denotes no document; anything else: the reference reports and continues
             const size_t before = part.bytes.size();
             size_t cap = 4096;
             struct stat st;
             if (fstat(fd, &st) == 0 && st.st_size > 0) cap = (size_t)st.st_size + 1;
+            bool failed = false;
             for (;;) {
                 part.bytes.resize(part.bytes.size() + cap);
                 const ssize_t got = read(fd, &part.bytes[part.bytes.size() - cap], cap);
-                if (got < 0) { close(fd); part.err = "cannot read " + path; return; }
+                if (got < 0) { part.bytes.resize(before); failed = true; break; }  // (a directory named x.json, an I/O error): no document
                 part.bytes.resize(part.bytes.size() - cap + (size_t)got);
                 if (got == 0) break;
             }
             close(fd);
-            part.sizes.push_back((i64)(part.bytes.size() - before));
+            if (!failed) part.sizes.push_back((i64)(part.bytes.size() - before));
         }
     };
     if (nthreads == 1) read_range(0);
@@ -330,17 +340,27 @@ void Table::load_dir(const std::string& dir, int threads) {
     }
     size_t total = 0;
     for (auto& part : parts) { if (!part.err.empty()) N1_THROW(N1GPU_E_IO, "%s", part.err.c_str()); total += part.bytes.size(); }
-    std::string buf;
-    buf.reserve(total);
+    // laid end to end - in pinned memory when the device shredder takes the text (its H2D copy then needs no staging)
+    PinnedBuf pin;
+    std::string heap;
+    char* buf = nullptr;
+    if (threads < 0 && have_device()) { pin.ensure(total + 64); buf = pin.as<char>(); }
+    else { heap.resize(total + 64); buf = &heap[0]; }
     std::vector<i64> offsets;
     offsets.reserve(nfiles + 1);
     offsets.push_back(0);
-    for (auto& part : parts) {
-        buf += part.bytes;
-        std::string().swap(part.bytes);
-        for (i64 sz : part.sizes) offsets.push_back(offsets.back() + sz);
+    std::vector<size_t> part_at(parts.size() + 1, 0);
+    for (size_t i = 0; i < parts.size(); ++i) {
+        part_at[i + 1] = part_at[i] + parts[i].bytes.size();
+        for (i64 sz : parts[i].sizes) offsets.push_back(offsets.back() + sz);
     }
-    append_json(buf.data(), offsets.data(), (i64)nfiles, threads);
+    {
+        std::vector<std::thread> pool;
+        for (size_t i = 0; i < parts.size(); ++i)
+            pool.emplace_back([&, i] { if (!parts[i].bytes.empty()) memcpy(buf + part_at[i], parts[i].bytes.data(), parts[i].bytes.size()); std::string().swap(parts[i].bytes); });
+        for (auto& th : pool) th.join();
+    }
+    append_json(buf, offsets.data(), (i64)offsets.size() - 1, threads);  // ids without a document were skipped
 }
 
 void Table::set_column(int c, int width, const void* payload, const u8* tags, i64 n, const char* blob,

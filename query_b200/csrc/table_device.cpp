@@ -83,7 +83,6 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     CK(cudaMemcpyAsync(d_trie.p, &trie, sizeof trie, cudaMemcpyHostToDevice, s));
     d_buf.alloc((size_t)nbytes + 64);
     d_offs.alloc((size_t)(ndocs + 1) * 8);
-    if (nbytes) CK(cudaMemcpyAsync(d_buf.p, buf + base_off, (size_t)nbytes, cudaMemcpyHostToDevice, s));
     std::vector<i64> rel;
     const i64* offs_src = offsets;
     if (base_off != 0) {  // device offsets are relative to d_buf
@@ -91,8 +90,7 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
         for (i64 i = 0; i <= ndocs; ++i) rel[(size_t)i] = offsets[i] - base_off;
         offs_src = rel.data();
     }
-    if (ndocs) CK(cudaMemcpyAsync(d_offs.p, offs_src, (size_t)(ndocs + 1) * 8, cudaMemcpyHostToDevice, s));
-    else { i64 z = 0; CK(cudaMemcpyAsync(d_offs.p, &z, 8, cudaMemcpyHostToDevice, s)); }
+    if (!ndocs) { i64 z = 0; CK(cudaMemcpyAsync(d_offs.p, &z, 8, cudaMemcpyHostToDevice, s)); }
 
     nrows = ndocs;
     i64 pad = padded_rows();
@@ -116,9 +114,40 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     CK(cudaMemsetAsync(d_fixcount.p, 0, 64, s));
     d_fixrows.alloc((size_t)fix_cap * 8);
 
-    if (ndocs)
-        launch_shred_json((const unsigned char*)d_buf.p, d_offs.as<i64>(), ndocs, (const ShredTrie*)d_trie.p, (u8* const*)d_ptrs.p,
-                          (i64* const*)((char*)d_ptrs.p + (size_t)ncols * 8), ncols, d_fixcount.as<unsigned>(), d_fixrows.as<i64>(), fix_cap, s);
+    // The raw JSON crosses PCIe in chunks on a copy stream while the parse kernel of the chunks that have landed runs on
+    // `s`: the document bytes and their offsets of chunk i+1 travel while chunk i is shredded (the H2D of the text is what
+    // bounds this path - 13 ms per 664 MB - so the ~4 ms of parsing hide behind it).
+    if (ndocs) {
+        cudaStream_t cs = nullptr;
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        struct CopyGuard { cudaStream_t s; ~CopyGuard() { cudaStreamDestroy(s); } } cg{cs};
+        cudaEvent_t ready_to_copy, landed;
+        CK(cudaEventCreateWithFlags(&ready_to_copy, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+        CK(cudaEventRecord(ready_to_copy, s));       // allocations / clears above are ordered before the first copy
+        CK(cudaStreamWaitEvent(cs, ready_to_copy, 0));
+        const i64 chunk_bytes = (i64)48 << 20;
+        i64 d0 = 0;
+        while (d0 < ndocs) {
+            i64 d1 = d0;  // documents [d0, d1): about chunk_bytes of text
+            {
+                const i64 want = offs_src[d0] + chunk_bytes;
+                i64 lo = d0 + 1, hi = ndocs;
+                while (lo < hi) { const i64 mid = (lo + hi) >> 1; if (offs_src[mid] >= want) hi = mid; else lo = mid + 1; }
+                d1 = lo;
+            }
+            CK(cudaMemcpyAsync(d_offs.as<i64>() + d0, offs_src + d0, (size_t)(d1 - d0 + 1) * 8, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync((char*)d_buf.p + offs_src[d0], buf + base_off + offs_src[d0], (size_t)(offs_src[d1] - offs_src[d0]), cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(landed, cs));
+            CK(cudaStreamWaitEvent(s, landed, 0));
+            launch_shred_json((const unsigned char*)d_buf.p, d_offs.as<i64>(), d0, d1 - d0, (const ShredTrie*)d_trie.p, (u8* const*)d_ptrs.p,
+                              (i64* const*)((char*)d_ptrs.p + (size_t)ncols * 8), ncols, d_fixcount.as<unsigned>(), d_fixrows.as<i64>(), fix_cap, s);
+            d0 = d1;
+        }
+        CK(cudaStreamSynchronize(cs));
+        CK(cudaEventDestroy(ready_to_copy));
+        CK(cudaEventDestroy(landed));
+    }
     unsigned nfix = 0;
     CK(cudaMemcpyAsync(&nfix, d_fixcount.p, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

@@ -302,3 +302,24 @@ def test_fast_count_plan_is_left_alone(tmp_path):
             {"#operator": "InitialProject", "result_terms": [{"as": "c", "expr": "count(*)"}]}, {"#operator": "FinalProject"}]}}]}
     for tail in (False, True):
         _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(plan, str(tmp_path), tail=tail))
+
+
+def test_keyspace_directory_follows_the_reference_id_rule(tmp_path):
+    """datastore/file/file.go: the primary index scans ids = file name minus its LAST extension (:711-730, :757-761) in name
+    order and Fetch reads <id>.json (:346); an id without such a file is silently no document (:319-322).  So a.txt next to
+    a.json yields a.json twice, foo.txt / .DS_Store / editor backups alone yield nothing, b.tar.json is the id b.tar."""
+    d = tmp_path / "default" / "ks"
+    d.mkdir(parents=True)
+    (d / "a.json").write_text('{"n": 1}')
+    (d / "a.txt").write_text("not json")            # id "a" again -> a.json a second time
+    (d / "foo.txt").write_text("no foo.json here")   # id "foo" -> foo.json missing -> nothing
+    (d / ".DS_Store").write_text("x")                # id "" -> ".json" missing -> nothing
+    (d / "b.tar.json").write_text('{"n": 10}')       # id "b.tar" -> b.tar.json
+    (d / "c.json~").write_text('{"n": 100}')         # id "c" -> c.json missing -> nothing
+    (d / "e.json").write_text("")                    # an empty file IS a document (not JSON: every field MISSING)
+    (d / "sub").mkdir()                              # directories are not entries
+    t = q.Table(["n"])
+    t.load_dir(str(d))
+    assert t.num_rows == 4
+    pay, tags = t.peek("n")
+    assert sorted(zip(tags.tolist(), pay.tolist())) == [(0, 0), (4, 1), (4, 1), (4, 10)]

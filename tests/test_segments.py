@@ -125,3 +125,29 @@ def test_queries_through_segment_loaded_tables(tmp_path):
     for threads in (0, -1):
         c = q.Table(COLS).load_ndjson(path, threads=threads).seal()
         assert_same(exp, gpu_rows(q.Query(c, "d", WHERE, KEYS, AGGS).execute(), AGGS), "ndjson threads=%d" % threads)
+
+
+@pytest.mark.gpu
+def test_operator_reads_a_packed_ndjson_keyspace(tmp_path):
+    """<namespace>/<keyspace>.ndjson (one document per line, primary-key order) stands in for the directory of one file per
+    document: the operator shreds it on the device (pinned parallel read, chunked H2D) and returns what the oracle computes;
+    a rewritten file invalidates the resident table."""
+    import query_b200 as q
+    from gen_n1 import F, make_docs
+    from oracle import n1ql_oracle as O
+    from plans_n1 import explain_plan
+    from util_n1 import assert_same, gpu_rows, oracle_rows
+    docs = make_docs(4000, seed=77)
+    ns = tmp_path / "default"
+    ns.mkdir()
+    (ns / "d.ndjson").write_text("\n".join(docs[:3000]) + "\n\n  \n")  # trailing blank lines are not documents
+    keys, aggs = [F("t")], sorted({"count(*)", "sum(%s)" % F("p"), "max(%s)" % F("s")})
+    plan = explain_plan("default", "d", "d", "(%s is not missing)" % F("p"), keys, aggs)
+    got = gpu_rows(q.Operator(plan, str(tmp_path)).run_once(), aggs)
+    assert_same(oracle_rows(docs[:3000], "d", "(%s is not missing)" % F("p"), keys, aggs), got, "packed keyspace")
+    import os
+    import time
+    time.sleep(0.01)
+    (ns / "d.ndjson").write_text("\n".join(docs) + "\n")
+    got = gpu_rows(q.Operator(plan, str(tmp_path)).run_once(), aggs)
+    assert_same(oracle_rows(docs, "d", "(%s is not missing)" % F("p"), keys, aggs), got, "packed keyspace, rewritten")
