@@ -16,6 +16,7 @@
 #include <fstream>
 
 #include "json.hpp"
+#include <cstdint>
 #include <fcntl.h>
 #include <unistd.h>
 #include <thread>
@@ -147,6 +148,9 @@ void Table::load_ndjson(const std::string& file, int threads) {
     // speed without a staging copy), read and scanned for line starts by all cores: a keyspace of 10^7 documents is
     // hundreds of megabytes, and one core reads and scans ~8 GB/s.
     const bool device = threads < 0;
+    const bool trace = getenv("N1GPU_TRACE") != nullptr;
+    double tp = now_sec();
+    auto phase = [&](const char* name) { if (trace) { double t = now_sec(); fprintf(stderr, "[n1gpu ndjson] %-22s %8.3f ms\n", name, (t - tp) * 1e3); tp = t; } };
     PinnedBuf pin;
     std::string heap;
     char* data = nullptr;
@@ -172,36 +176,59 @@ void Table::load_ndjson(const std::string& file, int threads) {
         }
     });
     for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_IO, "%s", e.c_str());
+    phase("alloc + parallel read");
     // document i = [start of its line, start of the next non-blank line): the line end and blank lines are trailing white
     // space of the document before them (value/parsed.go:76-98 skips leading ' ', '\t', '\n'; JSON allows trailing space)
     auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r'; };
     std::vector<std::vector<i64>> starts((size_t)nthr);
     run([&](int t) {
         auto& out = starts[(size_t)t];
+        const size_t lo = slice(t), hi = slice(t + 1);
+        out.reserve((hi - lo) / 24 + 16);
         auto consider = [&](size_t s0) {  // a line that begins at s0: a document unless it is blank
             size_t a = s0;
             while (a < size && blank(data[a])) ++a;
             if (a < size && data[a] != '\n') out.push_back((i64)s0);
         };
-        const size_t lo = slice(t), hi = slice(t + 1);
         if (t == 0 && size) consider(0);
-        const char* p = data + lo;
-        while (p < data + hi) {
-            const char* e = (const char*)memchr(p, '\n', (size_t)(data + hi - p));
-            if (!e) break;
-            if ((size_t)(e + 1 - data) < size) consider((size_t)(e + 1 - data));
-            p = e + 1;
+        size_t i = lo;
+        // eight bytes at a time: a zero byte of (word ^ 0x0a..0a) is a line end (the classic has-zero-byte test)
+        while (i < hi && (reinterpret_cast<uintptr_t>(data + i) & 7)) { if (data[i] == '\n' && i + 1 < size) consider(i + 1); ++i; }
+        for (; i + 8 <= hi; i += 8) {
+            u64 w;
+            memcpy(&w, data + i, 8);
+            const u64 x = w ^ 0x0a0a0a0a0a0a0a0aULL;
+            u64 z = (x - 0x0101010101010101ULL) & ~x & 0x8080808080808080ULL;
+            while (z) {
+                const size_t e = i + (size_t)(__builtin_ctzll(z) >> 3);
+                // (the borrow of the subtraction can flag the byte above a real line end: check it)
+                if (data[e] == '\n' && e + 1 < size) {
+                    const char c = data[e + 1];
+                    if (c == '{') out.push_back((i64)(e + 1)); else consider(e + 1);
+                }
+                z &= z - 1;
+            }
         }
+        for (; i < hi; ++i) if (data[i] == '\n' && i + 1 < size) consider(i + 1);
     });
-    std::vector<i64> offsets;
+    phase("line starts");
+    // the offsets go into pinned memory too (they cross PCIe with the text), each thread's run copied in place
     size_t ndocs = 0;
-    for (auto& v : starts) ndocs += v.size();
-    offsets.reserve(ndocs + 1);
-    for (auto& v : starts) offsets.insert(offsets.end(), v.begin(), v.end());
-    offsets.push_back((i64)size);
-    if (ndocs == 0) offsets.assign(1, 0);
-    if (device) append_json_device(data, offsets.data(), (i64)ndocs);
-    else append_json(data, offsets.data(), (i64)ndocs, threads);
+    std::vector<size_t> run_at((size_t)nthr + 1, 0);
+    for (int t = 0; t < nthr; ++t) { run_at[(size_t)t + 1] = run_at[(size_t)t] + starts[(size_t)t].size(); }
+    ndocs = run_at[(size_t)nthr];
+    PinnedBuf pin_offs;
+    std::vector<i64> heap_offs;
+    i64* offsets = nullptr;
+    if (device && have_device()) { pin_offs.ensure((ndocs + 1) * 8 + 64); offsets = pin_offs.as<i64>(); }
+    else { heap_offs.resize(ndocs + 1); offsets = heap_offs.data(); }
+    run([&](int t) { auto& v = starts[(size_t)t]; if (!v.empty()) memcpy(offsets + run_at[(size_t)t], v.data(), v.size() * 8); std::vector<i64>().swap(v); });
+    offsets[ndocs] = (i64)size;
+    if (ndocs == 0) offsets[0] = 0;
+    phase("offsets");
+    if (device) append_json_device(data, offsets, (i64)ndocs);
+    else append_json(data, offsets, (i64)ndocs, threads);
+    phase("shred");
 }
 
 }  // namespace n1
