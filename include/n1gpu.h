@@ -150,6 +150,17 @@ int n1gpu_table_free(n1gpu_table* t);
  * outside the subset of SURVEY.md section 8b; the caller then runs its own operators.                */
 int n1gpu_query_compile(n1gpu_table* t, const char* alias, const char* where, const char* const* group_keys,
                         int nkeys, const char* const* aggregates, int naggs, n1gpu_query** out);
+/* The same for a prepared statement: `$name` / `$1` in the expressions (algebra/param_named.go:63, param_positional.go;
+ * Stringer text expression/stringer.go:611-620) take the values of the request (execution.Context.NamedArg /
+ * PositionalArg, execution/context.go): param_names[i] ("name", "$name", "1") is bound to the JSON scalar text
+ * param_values[i] ("10", "2.5", "\"abc\"", "true", "null").  A parameter without a value fails like the reference's
+ * Evaluate ("No value for named parameter $x.").  Constants and parameter values reach the kernel as ARGUMENTS - the
+ * generated source only fixes their class - so every binding of a statement, and statements that differ in a bound,
+ * share one compiled kernel (n1gpu_jit_stats counts compilations and reuses).                                       */
+int n1gpu_query_compile_params(n1gpu_table* t, const char* alias, const char* where, const char* const* group_keys,
+                               int nkeys, const char* const* aggregates, int naggs, const char* const* param_names,
+                               const char* const* param_values, int nparams, n1gpu_query** out);
+int n1gpu_jit_stats(uint64_t* compiled, uint64_t* reused);
 /* Runs the chain over the whole table and finalises (FinalGroup).  Blocking.                        */
 int n1gpu_query_execute(n1gpu_query* q, n1gpu_result** out);
 /* Asynchronous pair for pipelined use: launch enqueues the scan on the query's stream and returns;

@@ -60,6 +60,9 @@ _SIGS = {
     "n1gpu_table_free": (C.c_int, [_P]),
     "n1gpu_query_compile": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int,
                                       C.POINTER(C.c_char_p), C.c_int, C.POINTER(_P)]),
+    "n1gpu_query_compile_params": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int,
+                                             C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.POINTER(_P)]),
+    "n1gpu_jit_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "n1gpu_query_execute": (C.c_int, [_P, C.POINTER(_P)]),
     "n1gpu_query_launch": (C.c_int, [_P]),
     "n1gpu_query_collect": (C.c_int, [_P, C.POINTER(_P)]),

@@ -46,6 +46,13 @@ def launch_count():
     return int(lib().n1gpu_launch_count())
 
 
+def jit_stats():
+    """(kernels compiled by NVRTC, requests served from the in-process kernel caches) since load"""
+    c, r = C.c_uint64(), C.c_uint64()
+    check(lib().n1gpu_jit_stats(C.byref(c), C.byref(r)))
+    return int(c.value), int(r.value)
+
+
 def set_segment_dir(path):
     """Directory in which plan-level operators keep persistent columnar segments ("" = none)."""
     check(lib().n1gpu_set_segment_dir(path.encode("utf-8") if path else None))
@@ -365,13 +372,22 @@ MODES = {0: "ungrouped", 1: "dense-shared-memory", 2: "hbm-hash-64", 3: "hbm-has
 class Query:
     """A compiled Filter + InitialGroup/IntermediateGroup/FinalGroup chain (n1gpu_query)."""
 
-    def __init__(self, table, alias, where, group_keys, aggregates):
+    def __init__(self, table, alias, where, group_keys, aggregates, params=None):
+        """params: {name or position: python scalar} for the `$name` / `$1` parameters of a prepared statement"""
         self.table = table
         self.aggregates = list(aggregates)
         self.group_keys = list(group_keys)
         self._h = C.c_void_p()
         karr = (C.c_char_p * max(1, len(self.group_keys)))(*[k.encode("utf-8") for k in self.group_keys])
         aarr = (C.c_char_p * max(1, len(self.aggregates)))(*[a.encode("utf-8") for a in self.aggregates])
+        if params:
+            names = [str(k).encode("utf-8") for k in params]
+            values = [json.dumps(v).encode("utf-8") for v in params.values()]
+            narr = (C.c_char_p * len(names))(*names)
+            varr = (C.c_char_p * len(values))(*values)
+            check(lib().n1gpu_query_compile_params(table._h, alias.encode("utf-8"), where.encode("utf-8") if where else None, karr,
+                                                   len(self.group_keys), aarr, len(self.aggregates), narr, varr, len(names), C.byref(self._h)))
+            return
         check(lib().n1gpu_query_compile(table._h, alias.encode("utf-8"), where.encode("utf-8") if where else None,
                                         karr, len(self.group_keys), aarr, len(self.aggregates), C.byref(self._h)))
 

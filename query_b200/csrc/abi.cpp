@@ -250,6 +250,32 @@ int n1gpu_query_compile(n1gpu_table* t, const char* alias, const char* where, co
         *out = new n1gpu_query{std::move(q)};
     });
 }
+int n1gpu_query_compile_params(n1gpu_table* t, const char* alias, const char* where, const char* const* group_keys, int nkeys,
+                               const char* const* aggregates, int naggs, const char* const* param_names, const char* const* param_values,
+                               int nparams, n1gpu_query** out) {
+    return guard([&] {
+        REQUIRE(t); REQUIRE(alias); REQUIRE(out);
+        if (nkeys < 0 || naggs < 0 || nparams < 0) N1_THROW(N1GPU_E_INVALID, "negative count");
+        std::vector<std::string> keys, aggs;
+        for (int i = 0; i < nkeys; ++i) { REQUIRE(group_keys && group_keys[i]); keys.push_back(group_keys[i]); }
+        for (int i = 0; i < naggs; ++i) { REQUIRE(aggregates && aggregates[i]); aggs.push_back(aggregates[i]); }
+        std::vector<ParamValue> params;
+        for (int i = 0; i < nparams; ++i) {
+            REQUIRE(param_names && param_names[i] && param_values && param_values[i]);
+            const char* n = param_names[i];
+            params.push_back(ParamValue{n[0] == '$' ? n + 1 : n, parse_param_value(param_values[i])});
+        }
+        auto q = Query::compile(&t->t, alias, where, keys, aggs, params);
+        *out = new n1gpu_query{std::move(q)};
+    });
+}
+int n1gpu_jit_stats(uint64_t* compiled, uint64_t* reused) {
+    if (!compiled || !reused) return N1GPU_E_INVALID;
+    unsigned long long c = 0, r = 0;
+    jit_stats(&c, &r);
+    *compiled = c; *reused = r;
+    return N1GPU_OK;
+}
 int n1gpu_query_execute(n1gpu_query* q, n1gpu_result** out) {
     return guard([&] {
         REQUIRE(q); REQUIRE(out);

@@ -48,7 +48,17 @@ struct Gen {
     int tmp = 0;
     std::string ind = "                ";
     std::map<int, std::string> colvar;  // per-row cache of column Val variables
-    explicit Gen(const Table& tt) : t(tt) {}
+    std::vector<i64> consts;            // payloads handed to the kernel as p.cst[k] (at most 32; more stay literals)
+    bool const_args = true;
+    explicit Gen(const Table& tt) : t(tt) { const char* e = getenv("N1GPU_CONST_LITERALS"); const_args = !(e && *e == '1'); }
+    // the payload of a constant as an expression: a kernel argument slot (shared by equal payloads), else a literal
+    std::string payload_ref(i64 bits) {
+        if (const_args) {
+            for (size_t k = 0; k < consts.size(); ++k) if (consts[k] == bits) return strf("p.cst[%d]", (int)k);
+            if (consts.size() < 32) { consts.push_back(bits); return strf("p.cst[%d]", (int)consts.size() - 1); }
+        }
+        return lit_i64(bits);
+    }
 
     std::string nv(const char* p = "v") { return strf("%s%d", p, tmp++); }
     void line(const std::string& s) { body += ind + s + "\n"; }
@@ -126,8 +136,8 @@ struct Gen {
             case EK::CONST: {
                 std::string v = nv();
                 const HValue& c = e.cval;
-                if (c.cls == C_STRING) line(strf("const Val %s = mkv(C_STRING, %lldLL);", v.c_str(), (long long)const_code(c.s, cx)));
-                else if (c.cls == C_INT || c.cls == C_FLOAT) line(strf("const Val %s = mkv(%s, %s);", v.c_str(), cls_name(c.cls), lit_i64(c.bits).c_str()));
+                if (c.cls == C_STRING) line(strf("const Val %s = mkv(C_STRING, %s);", v.c_str(), payload_ref(const_code(c.s, cx)).c_str()));
+                else if (c.cls == C_INT || c.cls == C_FLOAT) line(strf("const Val %s = mkv(%s, %s);", v.c_str(), cls_name(c.cls), payload_ref(c.bits).c_str()));
                 else line(strf("const Val %s = mkv(%s, 0);", v.c_str(), cls_name(c.cls)));
                 return v;
             }
@@ -203,6 +213,7 @@ struct Gen {
             case EK::AGG: N1_THROW(N1GPU_E_INELIGIBLE, "nested aggregate");
             case EK::IDENT: N1_THROW(N1GPU_E_INELIGIBLE, "bare identifier");
             case EK::ROUND: N1_THROW(N1GPU_E_INELIGIBLE, "round() on the GPU path");
+            case EK::PARAM: N1_THROW(N1GPU_E_INVALID, "No value for parameter $%s.", e.name.c_str());
         }
         N1_THROW(N1GPU_E_INVALID, "unhandled expression kind");
     }
@@ -1163,6 +1174,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     if (kp.pdl) s += "    asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");  // complete in stream order\n";
     s += "}\n";
     kp.source = s;
+    kp.consts = g.consts;
     if (kp.part) {
         std::string q;
         q += "// generated by libn1gpu codegen: the partitioning kernel of this chain's partitioned DISTINCT aggregation\n";

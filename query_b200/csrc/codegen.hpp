@@ -104,6 +104,8 @@ struct KernelPlan {
     int part_vbits = 0;          // record bits above: the packed DISTINCT value
     int part_bincap = 48;        // records a block stages per partition and round in shared memory
     int part_smem = 0;           // dynamic shared memory of the partitioning kernel
+    // payloads of constants / bound parameters, passed to the kernel as NqParams::cst (the source only names the slot)
+    std::vector<i64> consts;
     std::vector<int> used_cols;
     int scan_bytes_per_row = 0;
     std::string source;

@@ -32,7 +32,8 @@ static std::string nary(const Expr& e, const char* sym) {
 
 std::string Expr::str() const {
     switch (kind) {
-        case EK::CONST: return const_text(cval);
+        case EK::CONST: return param.empty() ? const_text(cval) : "$" + param;
+        case EK::PARAM: return "$" + name;
         case EK::IDENT: return "`" + name + "`";
         case EK::FIELD: return "(" + ops[0]->str() + ".`" + name + "`)";
         case EK::ADD: return nary(*this, "+");
@@ -157,7 +158,16 @@ struct P {
             return e;
         }
         if (c == '{') inel("object construction");
-        if (c == '$') inel("query parameter");
+        if (c == '$') {  // named / positional parameter: bound to a constant before analysis (bind_params)
+            ++i;
+            size_t j = i;
+            while (j < s.size() && (isalnum((unsigned char)s[j]) || s[j] == '_')) ++j;
+            if (j == i) bad("parameter name expected after '$'");
+            ExprP e = mk(EK::PARAM);
+            e->name = s.substr(i, j - i);
+            i = j;
+            return e;
+        }
         std::string w = word();
         if (w.empty()) bad("unexpected character");
         i += w.size();
@@ -321,6 +331,42 @@ static bool add_fits(__int128 v) { return v >= (__int128)INT64_MIN && v <= (__in
 
 static u32 nonnum_bits(u32 m) { return m & (bit(C_NULL) | M_BOOL | bit(C_STRING)); }
 
+void bind_params(Expr& e, const std::vector<ParamValue>& params) {
+    if (e.kind == EK::PARAM) {
+        for (auto& pv : params)
+            if (pv.name == e.name) { e.kind = EK::CONST; e.cval = pv.value; e.param = e.name; return; }
+        N1_THROW(N1GPU_E_INVALID, "No value for %s parameter $%s.", isdigit((unsigned char)e.name[0]) ? "positional" : "named", e.name.c_str());
+    }
+    for (auto& o : e.ops) bind_params(*o, params);
+}
+
+HValue parse_param_value(const std::string& text) {
+    json::Scanner sc(text.data(), text.data() + text.size());
+    sc.ws();
+    if (sc.p >= sc.end) N1_THROW(N1GPU_E_INVALID, "empty parameter value");
+    HValue v;
+    const char c = *sc.p;
+    if (c == '"') {
+        const char *rb, *re; bool esc;
+        if (!sc.string_raw(rb, re, esc)) N1_THROW(N1GPU_E_PARSE, "bad string parameter value");
+        v.cls = C_STRING;
+        if (esc) json::Scanner::unescape(rb, re, v.s); else v.s.assign(rb, re);
+    } else if (c == '-' || isdigit((unsigned char)c)) {
+        bool ii; i64 iv; double dv;
+        if (!sc.number(ii, iv, dv)) N1_THROW(N1GPU_E_PARSE, "bad number parameter value");
+        v = ii ? HValue::integer(iv) : new_num(dv);
+    } else {
+        const std::string w(sc.p, sc.end);
+        if (w.compare(0, 4, "true") == 0) { v = HValue::boolean(true); sc.p += 4; }
+        else if (w.compare(0, 5, "false") == 0) { v = HValue::boolean(false); sc.p += 5; }
+        else if (w.compare(0, 4, "null") == 0) { v = HValue::null(); sc.p += 4; }
+        else N1_THROW(N1GPU_E_INELIGIBLE, "parameter value %s is not a scalar (arrays / objects stay on the Go operators)", text.c_str());
+    }
+    sc.ws();
+    if (sc.p != sc.end) N1_THROW(N1GPU_E_PARSE, "trailing characters in parameter value %s", text.c_str());
+    return v;
+}
+
 void bind_and_analyze(Expr& e, const std::string& alias, const Table& t) {
     TypeInfo& ti = e.ti;
     if (e.kind == EK::FIELD) {
@@ -340,6 +386,7 @@ void bind_and_analyze(Expr& e, const std::string& alias, const Table& t) {
         return;
     }
     if (e.kind == EK::IDENT) N1_THROW(N1GPU_E_INELIGIBLE, "bare identifier %s", e.str().c_str());
+    if (e.kind == EK::PARAM) N1_THROW(N1GPU_E_INVALID, "No value for parameter $%s.", e.name.c_str());
     for (auto& o : e.ops) bind_and_analyze(*o, alias, t);
     auto any_has = [&](u32 bits) { for (auto& o : e.ops) if (o->ti.mask & bits) return true; return false; };
     auto string_dict = [&]() {  // the one dictionary string operands of a comparison live in

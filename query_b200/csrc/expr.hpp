@@ -16,6 +16,7 @@ struct Table;
 
 enum class EK {
     CONST, IDENT, FIELD,  // navigation
+    PARAM,                // $name / $1 (algebra/param_named.go:63, param_positional.go; expression/stringer.go:611-620)
     ADD, MULT, SUB, DIV, MOD, NEG,
     EQ, LT, LE, BETWEEN, IN,
     AND, OR, NOT,
@@ -40,7 +41,8 @@ struct Expr {
     EK kind;
     std::vector<std::unique_ptr<Expr>> ops;
     HValue cval;             // CONST
-    std::string name;        // IDENT / FIELD name
+    std::string name;        // IDENT / FIELD name; PARAM: the name or position after '$'
+    std::string param;       // CONST that stands for a bound parameter: its name (the Stringer text stays "$name")
     AggKind agg = AggKind::COUNT;
     bool distinct = false;
     bool star = false;       // count(*)
@@ -60,6 +62,13 @@ ExprP parse_expr(const std::string& text);
 // Collects the field paths (joined with '\x1f') referenced below `alias`; throws INELIGIBLE for a bare
 // alias reference (whole document), foreign identifiers or navigation on non-identifiers.
 void collect_paths(const Expr& e, const std::string& alias, std::vector<std::string>& out);
+
+// Replaces every PARAM by the constant bound to it (execution.Context.NamedArg / PositionalArg); a parameter without a
+// value throws N1GPU_E_INVALID ("No value for named parameter $x", algebra/param_named.go:70-72).
+struct ParamValue { std::string name; HValue value; };
+void bind_params(Expr& e, const std::vector<ParamValue>& params);
+// a JSON scalar (number, string, true, false, null) as a constant; arrays / objects are outside the subset
+HValue parse_param_value(const std::string& json_text);
 
 // Binds FIELD chains to columns of `t` and computes TypeInfo bottom-up.
 void bind_and_analyze(Expr& e, const std::string& alias, const Table& t);

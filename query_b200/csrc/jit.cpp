@@ -1,6 +1,8 @@
 // jit.cpp — see jit.hpp
 #include "jit.hpp"
 
+#include <atomic>
+
 #include <cuda.h>
 #include <dlfcn.h>
 #include <unistd.h>
@@ -141,12 +143,16 @@ JitKernel::~JitKernel() {
     if (module && g_drv.ModuleUnload) g_drv.ModuleUnload((CUmodule)module);
 }
 
+std::atomic<unsigned long long> g_jit_compiled{0}, g_jit_reused{0};
+void jit_stats(unsigned long long* compiled, unsigned long long* reused) { *compiled = g_jit_compiled.load(); *reused = g_jit_reused.load(); }
+
 std::string jit_compile_cubin(const std::string& source, std::string* log) {
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_cubin_cache.find(source);
-        if (it != g_cubin_cache.end()) return it->second;
+        if (it != g_cubin_cache.end()) { g_jit_reused.fetch_add(1); return it->second; }
     }
+    g_jit_compiled.fetch_add(1);
     Nvrtc& rt = nvrtc();
     // Optional on-disk kernel cache (N1GPU_KERNEL_CACHE_DIR): NVRTC + ptxas cost 0.25-0.45 s per new query shape, which a
     // restarted server would otherwise pay again for every prepared statement.  The key covers everything the cubin
@@ -218,7 +224,7 @@ std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem, int
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_cache.find(source);
-        if (it != g_cache.end()) return it->second;
+        if (it != g_cache.end()) { g_jit_reused.fetch_add(1); return it->second; }
     }
     std::string cubin = jit_compile_cubin(source, nullptr);
     Driver& d = driver();

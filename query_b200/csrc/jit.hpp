@@ -28,6 +28,9 @@ std::shared_ptr<JitKernel> jit_load(const std::string& source, int dyn_smem = 0,
 // Launches nq_scan<<<grid, k.block, k.dyn_smem, stream>>>(params) where params is a by-value struct of `bytes` bytes.
 void jit_launch(const JitKernel& k, int grid, cudaStream_t stream, void* params, size_t bytes, bool pdl = false);
 
+// kernels compiled by NVRTC / requests served from the in-process caches (by source text) since load
+void jit_stats(unsigned long long* compiled, unsigned long long* reused);
+
 int device_sm_count();
 
 }  // namespace n1

@@ -508,6 +508,9 @@ struct NqParams {
     // bits (entry >> set_shift) equal k - a slice of the bitmap that stays L2-resident - and only pass 0 feeds the
     // group table
     int set_pass, set_shift;
+    // payloads of the chain's constants and bound parameters (int64 / float64 bits / 2 * dictionary rank): the kernel text
+    // only fixes their CLASS, so statements that differ in a bound - or bindings of one prepared statement - share a cubin
+    i64 cst[32];
 };
 
 // Pushes `words` final words at src to every peer's mailbox and raises the flag word behind them.

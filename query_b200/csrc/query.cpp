@@ -40,8 +40,9 @@ struct NqParamsHost {
     u64 mail_words;
     u64 mail_seq;
     int set_pass, set_shift;
+    i64 cst[32];
 };
-static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 17, "NqParams layout");
+static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 17 + 256, "NqParams layout");
 
 u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
 
@@ -63,7 +64,8 @@ Query::~Query() {
 }
 
 std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const char* where,
-                                      const std::vector<std::string>& key_texts, const std::vector<std::string>& agg_texts) {
+                                      const std::vector<std::string>& key_texts, const std::vector<std::string>& agg_texts,
+                                      const std::vector<ParamValue>& params) {
     if (!t || !t->sealed) N1_THROW(N1GPU_E_INVALID, "table must be sealed before a query is compiled");
     std::unique_ptr<Query> q(new Query());
     q->table = t;
@@ -73,6 +75,11 @@ std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const 
     if (where && *where) { q->where_text = where; q->where = parse_expr(where); }
     for (auto& k : key_texts) q->keys.push_back(parse_expr(k));
     for (auto& a : agg_texts) q->aggs.push_back(parse_expr(a));
+    // named / positional parameters take their values now (execution.Context.NamedArg / PositionalArg); the kernel text only
+    // depends on their classes, the payloads are kernel arguments: re-binding a prepared statement reuses the cubin
+    if (q->where) bind_params(*q->where, params);
+    for (auto& k : q->keys) bind_params(*k, params);
+    for (auto& a : q->aggs) bind_params(*a, params);
     if (q->where) bind_and_analyze(*q->where, alias, *t);
     for (auto& k : q->keys) {
         if (k->kind == EK::AGG) N1_THROW(N1GPU_E_INELIGIBLE, "aggregate as a group key");
@@ -217,6 +224,7 @@ void Query::launch_scan() {
     NqParamsHost p{};
     p.nrows = table->nrows;
     for (size_t c = 0; c < table->cols.size(); ++c) { p.col[c] = table->cols[c].d_payload.p; p.tag[c] = table->cols[c].d_tags.as<u8>(); }
+    for (size_t k = 0; k < kp.consts.size() && k < 32; ++k) p.cst[k] = kp.consts[k];
     p.acc = kp.mode == MODE_UNGROUPED ? d_accum.as<u64>() : acc();
     p.partials = d_partials.as<u64>();
     p.keys = d_keys.as<u64>();

@@ -149,7 +149,8 @@ struct Query {
 
     ~Query();
     static std::unique_ptr<Query> compile(Table* t, const std::string& alias, const char* where,
-                                          const std::vector<std::string>& keys, const std::vector<std::string>& aggs);
+                                          const std::vector<std::string>& keys, const std::vector<std::string>& aggs,
+                                          const std::vector<ParamValue>& params = {});
     // the scan publishes the whole table to pinned host memory (and may push it through the peer mailbox)
     bool small_state() const { return kp.mode == MODE_UNGROUPED || (kp.mode == MODE_DENSE && !kp.dense_global); }
     int kw() const { return kp.mode == MODE_UNGROUPED ? 3 : (kp.mode == MODE_DENSE ? 0 : (kp.mode == MODE_HASH64 ? 1 : 2)); }

@@ -323,3 +323,31 @@ def test_keyspace_directory_follows_the_reference_id_rule(tmp_path):
     assert t.num_rows == 4
     pay, tags = t.peek("n")
     assert sorted(zip(tags.tolist(), pay.tolist())) == [(0, 0), (4, 1), (4, 1), (4, 10)]
+
+
+def test_parameters_and_constants_are_kernel_arguments():
+    """algebra/param_named.go:63, param_positional.go (Stringer text $name / $1, expression/stringer.go:611-620): a prepared
+    statement's parameters take the request's values when the chain is built; constants and parameter values reach the
+    kernel as arguments, so every binding - and the same statement with literals - shares ONE compiled kernel."""
+    docs = make_docs(1500, seed=5)
+    where = "((%s between $lo and $2) and (%s = $t))" % (F("p"), F("t"))
+    keys, aggs = [F("t")], ["count(*)", "sum(%s)" % F("p"), "max(%s)" % F("s")]
+    t = make_table(docs, "((%s between 1 and 2) and (%s = \"x\"))" % (F("p"), F("t")), keys, aggs)
+    t.seal()
+    c0, _r0 = q.jit_stats()
+    a = q.Query(t, "d", where, keys, aggs, params={"lo": 10, "2": 500, "t": "t1"})
+    c1, r1 = q.jit_stats()
+    b = q.Query(t, "d", where, keys, aggs, params={"$lo": -7, "2": 90000, "t": "t3"})
+    lit = q.Query(t, "d", "((%s between 11 and 499) and (%s = \"t2\"))" % (F("p"), F("t")), keys, aggs)
+    c2, r2 = q.jit_stats()
+    assert a.kernel_source == b.kernel_source == lit.kernel_source and "p.cst[" in a.kernel_source
+    assert c1 - c0 <= 1 and c2 == c1 and r2 >= r1 + 2, "re-binding must not compile"
+    with pytest.raises(q.N1GpuError, match="No value for named parameter"):
+        q.Query(t, "d", where, keys, aggs, params={"lo": 10, "2": 5})
+    with pytest.raises(q.N1GpuError, match="No value for positional parameter"):
+        q.Query(t, "d", where, keys, aggs, params={"lo": 10, "t": "x"})
+    with pytest.raises(q.Ineligible):  # non-scalar values stay with the caller's operators
+        q.Query(t, "d", where, keys, aggs, params={"lo": [1, 2], "2": 5, "t": "x"})
+    # a float where an int stood changes the class: another kernel, same statement
+    f = q.Query(t, "d", where, keys, aggs, params={"lo": 10.5, "2": 500, "t": "t1"})
+    assert f.kernel_source != a.kernel_source

@@ -188,6 +188,26 @@ def test_peer_arena_merge_owner_sharded(nranks):
         assert_same(exp, got, "peer merge, %d ranks, step %d" % (nranks, step))
 
 
+def test_prepared_statement_parameters_against_the_oracle():
+    """$name / $1 bound at build time (execution.Context.NamedArg / PositionalArg): the same rows as the statement with the
+    values written out, for several bindings that all run the one compiled kernel."""
+    docs = make_docs(4000, seed=61)
+    keys = [F("t")]
+    aggs = ["count(*)", "sum(%s)" % F("p"), "min(%s)" % F("s"), "avg((%s + $1))" % F("i")]
+    where = "(((%s between $lo and $hi) or (%s in [$a, \"zz\", $b])) and (%s >= $f))" % (F("p"), F("s"), F("f"))
+    t = make_table(docs, "(((%s < 1) or (%s = \"x\")) and (%s > 1))" % (F("p"), F("s"), F("f")), keys, ["sum(%s)" % F("i")] + aggs[:3])
+    t.seal()
+    sources = set()
+    for lo, hi, a, b, f, one in [(100, 700, "s3", "s7", -2.5, 1), (-50, 20, "s1", "nope", 0.25, 40), (300, 300, "", "s2", -100, -3)]:
+        qq = q.Query(t, "d", where, keys, aggs, params={"lo": lo, "hi": hi, "a": a, "b": b, "f": f, "1": one})
+        sources.add(qq.kernel_source)
+        lit_where = where.replace("$lo", str(lo)).replace("$hi", str(hi)).replace("$a", json.dumps(a)).replace("$b", json.dumps(b)).replace("$f", repr(f) if isinstance(f, float) else str(f))
+        lit_aggs = [x.replace("$1", str(one)) for x in aggs]
+        got = {k: {lit_aggs[i]: v for i, v in enumerate(d.values())} for k, d in gpu_rows(qq.execute(), aggs).items()}
+        assert_same(oracle_rows(docs, "d", lit_where, keys, lit_aggs), got, "parameters %r" % ((lo, hi, a, b, f, one),))
+    assert len(sources) <= 2  # (int / float class of $f is the only thing that may differ between the bindings)
+
+
 def test_peer_arena_partitioned_distinct(monkeypatch):
     """BASELINE config 4 across ranks, all driven by this process on one device: every rank partitions its rows' (group,
     value) records into its arena, rank r aggregates partition range r from every rank's records and finalises exactly
