@@ -295,7 +295,7 @@ int n1gpu_query_collect(n1gpu_query* q, n1gpu_result** out) {
 }
 int n1gpu_query_cancel(n1gpu_query* q) {
     if (!q) return N1GPU_E_INVALID;
-    q->q->cancelled.store(true);
+    q->q->cancel();
     return N1GPU_OK;
 }
 const char* n1gpu_query_kernel_source(const n1gpu_query* q) { return q ? q->q->kp.source.c_str() : ""; }

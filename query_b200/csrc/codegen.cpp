@@ -953,7 +953,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     s += "    const int lane = threadIdx.x & 31;\n";
     s += "    const i64 stride = (i64)gridDim.x * (NQ_BLOCK * 4);\n";
     s += "    // warp-uniform trip count: every lane of a warp stays in the loop while the warp has rows\n";
+    s += "    int nq_tile = 0;\n";
     s += "    for (i64 wbase = (i64)blockIdx.x * (NQ_BLOCK * 4) + (threadIdx.x >> 5) * 128; wbase < nrows; wbase += stride) {\n";
+    s += "        if ((++nq_tile & 31) == 0 && nq_cancelled(p, lane)) break;  // SendStop: the host discards whatever was aggregated\n";
     s += "        const i64 base = wbase + lane * 4;\n";
     for (int c : kp.used_cols) {
         const Column& col = t.cols[c];
@@ -1183,6 +1185,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         q += strf("#define NP %d\n#define BINCAP %d\n#define GBITS %d\n#define ROUND_TILES 8\n", 1 << kp.part_bits, kp.part_bincap, kp.part_gbits);
         q += "extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, 1) nq_scan(const NqParams p) {\n";
         q += "    extern __shared__ u32 s_part[];\n";
+        q += "    __shared__ int s_stop;\n";
         q += "    u32* const s_cnt = s_part;        // [NP] records staged per partition in this round\n";
         q += "    u32* const s_bin = s_part + NP;   // [NP][BINCAP]\n";
         q += "    u32* const g_recs = (u32*)p.set_keys;  // [NP][part_cap] partitioned records\n";
@@ -1207,7 +1210,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         q += "    { const i64 nt_ = (i64)blockIdx.x * ROUND_TILES; if (nt_ < ntiles) { const i64 nb = nt_ * tile + threadIdx.x * 4; " + load_next + "} }\n";
         q += "    for (i64 t0 = (i64)blockIdx.x * ROUND_TILES; t0 < ntiles; t0 += round_stride) {\n";
         q += "        for (int i = threadIdx.x; i < NP; i += NQ_BLOCK) s_cnt[i] = 0;\n";
+        q += "        if (threadIdx.x == 0) s_stop = *(volatile const int*)p.cancel;  // SendStop while the scan runs\n";
         q += "        __syncthreads();\n";
+        q += "        if (s_stop) break;\n";
         q += "        for (int tt = 0; tt < ROUND_TILES && t0 + tt < ntiles; ++tt) {\n";
         q += "        const i64 base = (t0 + tt) * tile + threadIdx.x * 4;\n";
         q += "#pragma unroll\n";

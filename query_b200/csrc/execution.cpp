@@ -482,7 +482,7 @@ std::unique_ptr<Result> GpuGroupAggregate::RunOnce() {
     return r;
 }
 
-void GpuGroupAggregate::SendStop() { if (query) query->cancelled.store(true); }
+void GpuGroupAggregate::SendStop() { if (query) query->cancel(); }
 
 std::string GpuGroupAggregate::MarshalJSON() const {
     std::string s = "{\"#operator\":\"GpuGroupAggregate\"";

@@ -511,7 +511,15 @@ struct NqParams {
     // payloads of the chain's constants and bound parameters (int64 / float64 bits / 2 * dictionary rank): the kernel text
     // only fixes their CLASS, so statements that differ in a bound - or bindings of one prepared statement - share a cubin
     i64 cst[32];
+    // execution.Operator.SendStop while the scan runs: a word in pinned host memory (mapped) that n1gpu_query_cancel sets;
+    // lane 0 of every warp polls it once per 32 tiles and the warp leaves the loop
+    const int* cancel;
 };
+NQ_DEV bool nq_cancelled(const NqParams& p, int lane) {
+    int c = 0;
+    if (lane == 0) c = *(volatile const int*)p.cancel;
+    return __shfl_sync(0xffffffffu, c, 0) != 0;
+}
 
 // Pushes `words` final words at src to every peer's mailbox and raises the flag word behind them.
 NQ_DEV void mailbox_push(const NqParams& p, const u64* src) {

@@ -41,8 +41,9 @@ struct NqParamsHost {
     u64 mail_seq;
     int set_pass, set_shift;
     i64 cst[32];
+    const int* cancel;
 };
-static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 17 + 256, "NqParams layout");
+static_assert(sizeof(NqParamsHost) == 8 + 128 + 128 + 8 * 17 + 256 + 8, "NqParams layout");
 
 u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
 
@@ -164,6 +165,7 @@ void Query::alloc_state() {
         d_part_recs.ensure((size_t)(np * part_cap) * 4);
         d_part_cur.ensure((size_t)np * 4);
     }
+    if (!h_cancel.p) { h_cancel.ensure(64); memset(h_cancel.p, 0, 64); }
     d_status.ensure(64);
     h_status.ensure(64);
     memset(h_status.p, 0, 64);
@@ -225,6 +227,7 @@ void Query::launch_scan() {
     p.nrows = table->nrows;
     for (size_t c = 0; c < table->cols.size(); ++c) { p.col[c] = table->cols[c].d_payload.p; p.tag[c] = table->cols[c].d_tags.as<u8>(); }
     for (size_t k = 0; k < kp.consts.size() && k < 32; ++k) p.cst[k] = kp.consts[k];
+    p.cancel = h_cancel.as<int>();
     p.acc = kp.mode == MODE_UNGROUPED ? d_accum.as<u64>() : acc();
     p.partials = d_partials.as<u64>();
     p.keys = d_keys.as<u64>();
@@ -338,6 +341,7 @@ bool Query::wait_scan() {
         CK(cudaEventElapsedTime(&ms, ev0, ev1));
         last_scan_ms = ms;
     }
+    if (cancelled.load()) N1_THROW(N1GPU_E_CANCELLED, "query cancelled");  // (the running kernel saw the flag and stopped early)
     int st = uses_status() ? h_status.as<int>()[0] : 0;
     if (st == 3) N1_THROW(N1GPU_E_CUDA, "multi-GPU merge timed out: a peer rank never delivered its partial state");
     if (st == 4 && peer_part_merge())
@@ -432,7 +436,23 @@ void Query::partial_import(const void* dev_records, i64 n, const void* dev_disti
         CK(cudaStreamSynchronize(stream));
         int s0 = h_status.as<int>()[0], s1 = h_status.as<int>()[1];
         if (!s0 && !s1) break;
-        N1_THROW(N1GPU_E_NOMEM, "merge overflowed the %s table; reset with a larger capacity", s0 ? "group" : "DISTINCT");
+        // The owner's table (sized for its own partition's groups) is too small for everybody's records: grow what
+        // overflowed, clear the state (a half-applied merge cannot be kept: additions are not idempotent) and merge again -
+        // the records are still in the caller's buffers.
+        if (s0) {
+            if (kp.mode != MODE_HASH64 && kp.mode != MODE_HASH128) N1_THROW(N1GPU_E_INVALID, "a record does not belong to this rank's table (bad key)");
+            if (cap >= ((u64)1 << 31)) N1_THROW(N1GPU_E_NOMEM, "group table would exceed 2^31 slots");
+            cap *= 4;
+            d_keys.alloc((size_t)cap * (kp.mode == MODE_HASH128 ? 16 : 8));
+            d_acc.alloc((size_t)cap * ops.n * 8);
+        }
+        if (s1) {
+            if (kp.set_bitmap) N1_THROW(N1GPU_E_INVALID, "a DISTINCT entry lies outside this rank's bitmap");
+            if (set_cap >= ((u64)1 << 32)) N1_THROW(N1GPU_E_NOMEM, "DISTINCT set would exceed 2^32 slots");
+            set_cap *= 4;
+            d_set.alloc(set_bytes());
+        }
+        reset_state();
     }
     if (n > 0) ungrouped_live = true;
 }

@@ -128,6 +128,8 @@ struct Query {
     DevBuf d_partials, d_acc, d_accum, d_keys, d_set, d_status, d_counts, d_records, d_drecords, d_ticket, d_final;
     PinnedBuf h_status, h_counts, h_records, h_drecords;
     std::atomic<bool> cancelled{false};
+    PinnedBuf h_cancel;          // the word the running kernel polls (mapped pinned memory)
+    void cancel() { cancelled.store(true); if (h_cancel.p) *(volatile int*)h_cancel.p = 1; }
     bool launched = false;
     bool timing = true;        // record CUDA events around the scan (each record costs GPU front-end time)
     bool timed_launch = false;

@@ -180,15 +180,15 @@ void Table::load_ndjson(const std::string& file, int threads) {
     // document i = [start of its line, start of the next non-blank line): the line end and blank lines are trailing white
     // space of the document before them (value/parsed.go:76-98 skips leading ' ', '\t', '\n'; JSON allows trailing space)
     auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r'; };
-    std::vector<std::vector<i64>> starts((size_t)nthr);
-    run([&](int t) {
-        auto& out = starts[(size_t)t];
+    // Two passes over the text, both store-free on the way (a growing vector per thread spends more time faulting fresh pages
+    // in than the scan itself): pass 1 counts the documents of every slice, pass 2 writes their line starts at their final
+    // positions - in pinned memory when the offsets cross PCIe with the text.
+    auto scan = [&](int t, auto&& emit) {
         const size_t lo = slice(t), hi = slice(t + 1);
-        out.reserve((hi - lo) / 24 + 16);
         auto consider = [&](size_t s0) {  // a line that begins at s0: a document unless it is blank
             size_t a = s0;
             while (a < size && blank(data[a])) ++a;
-            if (a < size && data[a] != '\n') out.push_back((i64)s0);
+            if (a < size && data[a] != '\n') emit((i64)s0);
         };
         if (t == 0 && size) consider(0);
         size_t i = lo;
@@ -203,26 +203,24 @@ void Table::load_ndjson(const std::string& file, int threads) {
                 const size_t e = i + (size_t)(__builtin_ctzll(z) >> 3);
                 // (the borrow of the subtraction can flag the byte above a real line end: check it)
                 if (data[e] == '\n' && e + 1 < size) {
-                    const char c = data[e + 1];
-                    if (c == '{') out.push_back((i64)(e + 1)); else consider(e + 1);
+                    if (data[e + 1] == '{') emit((i64)(e + 1)); else consider(e + 1);
                 }
                 z &= z - 1;
             }
         }
         for (; i < hi; ++i) if (data[i] == '\n' && i + 1 < size) consider(i + 1);
-    });
-    phase("line starts");
-    // the offsets go into pinned memory too (they cross PCIe with the text), each thread's run copied in place
-    size_t ndocs = 0;
+    };
     std::vector<size_t> run_at((size_t)nthr + 1, 0);
-    for (int t = 0; t < nthr; ++t) { run_at[(size_t)t + 1] = run_at[(size_t)t] + starts[(size_t)t].size(); }
-    ndocs = run_at[(size_t)nthr];
+    run([&](int t) { size_t n = 0; scan(t, [&](i64) { ++n; }); run_at[(size_t)t + 1] = n; });
+    for (int t = 0; t < nthr; ++t) run_at[(size_t)t + 1] += run_at[(size_t)t];
+    const size_t ndocs = run_at[(size_t)nthr];
+    phase("count documents");
     PinnedBuf pin_offs;
     std::vector<i64> heap_offs;
     i64* offsets = nullptr;
     if (device && have_device()) { pin_offs.ensure((ndocs + 1) * 8 + 64); offsets = pin_offs.as<i64>(); }
     else { heap_offs.resize(ndocs + 1); offsets = heap_offs.data(); }
-    run([&](int t) { auto& v = starts[(size_t)t]; if (!v.empty()) memcpy(offsets + run_at[(size_t)t], v.data(), v.size() * 8); std::vector<i64>().swap(v); });
+    run([&](int t) { i64* out = offsets + run_at[(size_t)t]; scan(t, [&](i64 s0) { *out++ = s0; }); });
     offsets[ndocs] = (i64)size;
     if (ndocs == 0) offsets[0] = 0;
     phase("offsets");

@@ -1,5 +1,7 @@
 """n1gpu_table_set_column_device: columns handed over in device memory give the same table (statistics, widths,
 results) as the same columns handed over in host memory."""
+import os
+
 import numpy as np
 import pytest
 
@@ -88,3 +90,32 @@ def test_host_and_device_columns_do_not_mix():
     t2.set_column_device("a", torch.arange(10, dtype=torch.int64, device="cuda:0"))
     with pytest.raises(q.N1GpuError):
         t2.seal()  # column b never set
+
+
+def test_send_stop_aborts_a_running_scan(monkeypatch):
+    """execution/base.go:313-338: SendStop may arrive from any goroutine at any time and must make the operator stop.  A scan
+    in flight polls the cancel word (mapped pinned memory) once per 32 tiles per warp: n1gpu_query_cancel during a long scan
+    makes collect fail with N1GPU_E_CANCELLED well before the scan would have finished."""
+    import sys
+    import time
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import torch
+    import workloads as wl
+    monkeypatch.setenv("N1GPU_NO_CACHE", "1")  # every row of a hot Zipf key is an L2 atomic on one address: a slow scan
+    w = wl.Config5(scale=0.1)
+    t = w.sealed_table()
+    qq = w.query(t)
+    qq.execute()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    qq.execute()
+    full = time.perf_counter() - t0
+    qq.launch()
+    time.sleep(min(0.002, full / 20))
+    t0 = time.perf_counter()
+    qq.cancel()
+    with pytest.raises(q.N1GpuError) as e:
+        qq.collect()
+    stopped = time.perf_counter() - t0
+    assert e.value.code == -6, e.value  # N1GPU_E_CANCELLED
+    assert full > 0.01 and stopped < full / 3, (full, stopped)

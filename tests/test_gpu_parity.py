@@ -188,6 +188,36 @@ def test_peer_arena_merge_owner_sharded(nranks):
         assert_same(exp, got, "peer merge, %d ranks, step %d" % (nranks, step))
 
 
+def test_partial_import_grows_the_owners_table():
+    """An owner whose own partition holds a handful of groups imports thousands from a peer: its hash table (sized for its
+    own rows) and DISTINCT set grow and the merge is redone - CumulateIntermediate must not fail for lack of slots."""
+    import torch
+    from query_b200 import dist as qd
+    docs = make_docs(6000, seed=91)
+    where, keys = None, [F("g")]   # a high-cardinality key: hash table mode
+    aggs = ["count(*)", "sum(%s)" % F("p"), "count(distinct %s)" % F("i")]
+    small, big = make_table(docs[:8], where, keys, aggs), make_table(docs[8:], where, keys, aggs)
+    qd.agree_local([small, big])
+    small.seal()
+    big.seal()
+    qs, qb = q.Query(small, "d", where, keys, aggs), q.Query(big, "d", where, keys, aggs)
+    assert qs.info["mode"].startswith("hbm-hash")
+    parts = []
+    for qq in (qs, qb):
+        qq.scan_partial()
+        ng, nd, rw = qq.partial_counts()
+        recs = torch.empty(max(1, ng) * rw, dtype=torch.int64, device="cuda")
+        dents = torch.empty(max(1, nd) * 2, dtype=torch.int64, device="cuda")
+        counts, dcounts = qq.partial_export(1, recs.data_ptr(), ng, dents.data_ptr(), nd)
+        parts.append((recs[: int(counts[0]) * rw], dents[: int(dcounts[0]) * 2], int(counts[0]), int(dcounts[0])))
+    assert parts[1][2] > 2000
+    allrec = torch.cat([p[0] for p in parts])
+    alld = torch.cat([p[1] for p in parts])
+    qs.partial_reset()
+    qs.partial_import(allrec.data_ptr(), parts[0][2] + parts[1][2], alld.data_ptr(), parts[0][3] + parts[1][3])
+    assert_same(oracle_rows(docs, "d", where, keys, aggs), gpu_rows(qs.finalize(), aggs), "import into a small owner")
+
+
 def test_prepared_statement_parameters_against_the_oracle():
     """$name / $1 bound at build time (execution.Context.NamedArg / PositionalArg): the same rows as the statement with the
     values written out, for several bindings that all run the one compiled kernel."""
@@ -198,14 +228,16 @@ def test_prepared_statement_parameters_against_the_oracle():
     t = make_table(docs, "(((%s < 1) or (%s = \"x\")) and (%s > 1))" % (F("p"), F("s"), F("f")), keys, ["sum(%s)" % F("i")] + aggs[:3])
     t.seal()
     sources = set()
-    for lo, hi, a, b, f, one in [(100, 700, "s3", "s7", -2.5, 1), (-50, 20, "s1", "nope", 0.25, 40), (300, 300, "", "s2", -100, -3)]:
+    for lo, hi, a, b, f, one in [(100, 700, "s3", "s7", -2.5, 1), (-50, 20, "s1", "nope", 0.25, 1), (300, 300, "", "s2", -100, 1), (5, 9, "a", "b", 1, 40)]:
         qq = q.Query(t, "d", where, keys, aggs, params={"lo": lo, "hi": hi, "a": a, "b": b, "f": f, "1": one})
         sources.add(qq.kernel_source)
         lit_where = where.replace("$lo", str(lo)).replace("$hi", str(hi)).replace("$a", json.dumps(a)).replace("$b", json.dumps(b)).replace("$f", repr(f) if isinstance(f, float) else str(f))
         lit_aggs = [x.replace("$1", str(one)) for x in aggs]
         got = {k: {lit_aggs[i]: v for i, v in enumerate(d.values())} for k, d in gpu_rows(qq.execute(), aggs).items()}
         assert_same(oracle_rows(docs, "d", lit_where, keys, lit_aggs), got, "parameters %r" % ((lo, hi, a, b, f, one),))
-    assert len(sources) <= 2  # (int / float class of $f is the only thing that may differ between the bindings)
+    # bounds and string constants never change the kernel; the class of $f (int / float) and a constant that feeds the range
+    # proof of a sum (avg(i + $1): the proof is part of the generated layout) may
+    assert len(sources) <= 3
 
 
 def test_peer_arena_partitioned_distinct(monkeypatch):
