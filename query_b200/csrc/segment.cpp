@@ -177,6 +177,11 @@ void Table::load_ndjson(const std::string& file, int threads) {
     });
     for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_IO, "%s", e.c_str());
     phase("alloc + parallel read");
+    if (device && have_device()) {  // the device finds the line starts itself (shred.cu k_ndjson_lines)
+        append_ndjson_device(data, (i64)size);
+        phase("shred");
+        return;
+    }
     // document i = [start of its line, start of the next non-blank line): the line end and blank lines are trailing white
     // space of the document before them (value/parsed.go:76-98 skips leading ' ', '\t', '\n'; JSON allows trailing space)
     auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r'; };

@@ -243,6 +243,84 @@ __global__ void __launch_bounds__(128) k_shred_json(const unsigned char* __restr
     }
 }
 
+// ---- NDJSON: document offsets computed on the device -----------------------------------------------------------------
+// A document starts where a line starts (position 0 or behind a line end) unless the line is blank (only ' ', '\t', '\r'
+// before its end).  One thread per 256-byte segment counts / writes the document starts of its segment; a scan over the
+// segment counts in between gives every segment its first document index.  The text is read at HBM speed twice - the
+// host would spend a pass of its memory bandwidth per step, and the offsets (8 bytes per document) never cross PCIe.
+#define NL_SEG 256
+__device__ __forceinline__ bool nl_doc_start(const unsigned char* __restrict__ t, i64 size, i64 p) {
+    for (i64 a = p; a < size; ++a) {
+        const unsigned char c = t[a];
+        if (c == ' ' || c == '\t' || c == '\r') continue;
+        return c != '\n';
+    }
+    return false;
+}
+template <bool WRITE>
+__global__ void k_ndjson_lines(const unsigned char* __restrict__ t, i64 size, i64 nseg, unsigned* __restrict__ counts, const i64* __restrict__ first,
+                               i64* __restrict__ offs) {
+    for (i64 seg = (i64)blockIdx.x * blockDim.x + threadIdx.x; seg < nseg; seg += (i64)gridDim.x * blockDim.x) {
+        const i64 lo = seg * NL_SEG, hi = lo + NL_SEG < size ? lo + NL_SEG : size;
+        unsigned n = 0;
+        i64 at = WRITE ? first[seg] : 0;
+        if (seg == 0 && size > 0 && nl_doc_start(t, size, 0)) { if (WRITE) offs[at++] = 0; ++n; }
+        for (i64 p = lo; p < hi; p += 16) {
+            const uint4 v = *reinterpret_cast<const uint4*>(t + p);  // (the buffer is padded: reading past `size` is harmless)
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned x = w[k] ^ 0x0a0a0a0au;
+                unsigned z = (x - 0x01010101u) & ~x & 0x80808080u;
+                while (z) {
+                    const i64 e = p + 4 * k + ((__ffs((int)z) - 1) >> 3);
+                    z &= z - 1;
+                    if (e < hi && t[e] == '\n' && e + 1 < size && nl_doc_start(t, size, e + 1)) { if (WRITE) offs[at++] = e + 1; ++n; }
+                }
+            }
+        }
+        if (!WRITE) counts[seg] = n;
+    }
+}
+// exclusive scan of the segment counts (one block, 1024 threads, sequential over tiles): first[seg], first[nseg] = total
+__global__ void __launch_bounds__(1024) k_scan_counts(const unsigned* __restrict__ counts, i64 nseg, i64* __restrict__ first) {
+    __shared__ i64 s_warp[32];
+    __shared__ i64 s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (i64 t0 = 0; t0 < nseg; t0 += 1024 * 8) {
+        // every thread owns 8 consecutive segments of the tile
+        const i64 mine = t0 + (i64)threadIdx.x * 8;
+        i64 v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = mine + k < nseg ? (i64)counts[mine + k] : 0; sum += v[k]; }
+        i64 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const i64 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            i64 w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const i64 up = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += up; }
+            s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        i64 run = s_base + s_warp[warp] + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { if (mine + k < nseg) first[mine + k] = run; run += v[k]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_base = run;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) first[nseg] = s_base;
+}
+// device offsets of the documents `rows` (fix-up rows): out[2 * i] = offs[rows[i]], out[2 * i + 1] = offs[rows[i] + 1]
+__global__ void k_gather_offsets(const i64* __restrict__ offs, const i64* __restrict__ rows, i64 n, i64* out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) { out[2 * i] = offs[rows[i]]; out[2 * i + 1] = offs[rows[i] + 1]; }
+}
+
 // ---- dictionary encoding ------------------------------------------------------------------------------------------
 __device__ __forceinline__ const unsigned char* ref_ptr(u64 ref, const unsigned char* buf, const unsigned char* extra) {
     return ((ref & REF_EXTRA_BIT) ? extra : buf) + ((ref & ~REF_EXTRA_BIT) >> 24);
@@ -356,6 +434,32 @@ void launch_shred_json(const unsigned char* buf, const i64* offs, i64 first, i64
                        int ncols, unsigned* fix_count, i64* fix_rows, i64 fix_cap, cudaStream_t s) {
     if (ndocs <= 0) return;
     k_shred_json<<<sgrid(ndocs, 128), 128, 0, s>>>(buf, offs, first, ndocs, T, tags, payload, ncols, fix_count, fix_rows, fix_cap);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+i64 ndjson_segments(i64 size) { return (size + NL_SEG - 1) / NL_SEG; }
+void launch_ndjson_count(const unsigned char* text, i64 size, unsigned* counts, cudaStream_t s) {
+    const i64 nseg = ndjson_segments(size);
+    if (!nseg) return;
+    k_ndjson_lines<false><<<sgrid(nseg, 128), 128, 0, s>>>(text, size, nseg, counts, nullptr, nullptr);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_ndjson_scan(const unsigned* counts, i64 nseg, i64* first, cudaStream_t s) {
+    k_scan_counts<<<1, 1024, 0, s>>>(counts, nseg, first);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_ndjson_write(const unsigned char* text, i64 size, const i64* first, i64* offs, cudaStream_t s) {
+    const i64 nseg = ndjson_segments(size);
+    if (!nseg) return;
+    k_ndjson_lines<true><<<sgrid(nseg, 128), 128, 0, s>>>(text, size, nseg, nullptr, first, offs);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+}
+void launch_gather_offsets(const i64* offs, const i64* rows, i64 n, i64* out, cudaStream_t s) {
+    if (n == 0) return;
+    k_gather_offsets<<<sgrid(n, 256), 256, 0, s>>>(offs, rows, n, out);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
 }

@@ -17,6 +17,13 @@ void launch_shred_json(const unsigned char* buf, const i64* offs, i64 first, i64
 void launch_dict_insert(const unsigned char* buf, const unsigned char* extra, const u8* tags, const i64* payload, i64* slots, i64 nrows,
                         u64* keys, u64 cap, int* status, cudaStream_t s);
 void launch_dict_collect(const u64* keys, u64 cap, unsigned* count, u64* out_slots, u64* out_refs, u64 out_cap, cudaStream_t s);
+// NDJSON text resident in HBM -> offsets of its documents (see shred.cu): counts per 256-byte segment, their exclusive scan
+// (first[nseg] = number of documents), the offsets themselves; the caller appends offs[ndocs] = size
+i64 ndjson_segments(i64 size);
+void launch_ndjson_count(const unsigned char* text, i64 size, unsigned* counts, cudaStream_t s);
+void launch_ndjson_scan(const unsigned* counts, i64 nseg, i64* first, cudaStream_t s);
+void launch_ndjson_write(const unsigned char* text, i64 size, const i64* first, i64* offs, cudaStream_t s);
+void launch_gather_offsets(const i64* offs, const i64* rows, i64 n, i64* out, cudaStream_t s);
 void launch_rank_remap(const u8* tags, i64* pay8, u32* pay4, i64 nrows, const u32* remap, u32 n, cudaStream_t s);
 void launch_dict_ranks(const u64* slot_of_rank, u64 n, u32* rank, cudaStream_t s);
 void launch_dict_remap(const u8* tags, const i64* slots, i64* payload, u32* out32, i64 nrows, const u32* rank, cudaStream_t s);

@@ -58,6 +58,8 @@ struct Table {
 
     // threads >= 0: host threads (0 = all cores); threads == -1: the device shredder (shred.cu)
     void append_json_device(const char* buf, const i64* offsets, i64 ndocs);
+    void append_ndjson_device(const char* text, i64 size);  // one document per line; offsets computed on the device
+    void append_text_device(const char* buf, const i64* offsets, i64 ndocs, i64 text_size);
     int add_column(const std::string& path);
     int find_column(const std::string& path) const;
     void append_json(const char* buf, const i64* offsets, i64 ndocs, int threads);

@@ -55,10 +55,20 @@ u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
 }  // namespace
 
 void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
+    if (ndocs < 0) N1_THROW(N1GPU_E_INVALID, "negative document count");
+    append_text_device(buf, offsets, ndocs, 0);
+}
+
+// One JSON document per line, `size` bytes at text (readable up to text + size + 64): the document offsets are computed on
+// the device from the text itself (k_ndjson_lines) - no host pass over the text, no offsets over PCIe.
+void Table::append_ndjson_device(const char* text, i64 size) { append_text_device(text, nullptr, -1, size); }
+
+void Table::append_text_device(const char* buf, const i64* offsets, i64 ndocs, i64 text_size) {
+    const bool lines = offsets == nullptr;  // NDJSON: offsets come from the device
     if (sealed) N1_THROW(N1GPU_E_INVALID, "table is sealed");
     if (!have_device()) N1_THROW(N1GPU_E_CUDA, "the device shredder needs a CUDA device (there is no CPU fallback for it; use host threads explicitly)");
     if (appended || nrows != 0) N1_THROW(N1GPU_E_INVALID, "the device shredder takes the whole keyspace in one append");
-    if (ndocs < 0) N1_THROW(N1GPU_E_INVALID, "negative document count");
+    if (cols.empty() && lines) N1_THROW(N1GPU_E_INVALID, "a table without columns cannot split lines on the device");
     if (cols.empty()) {  // a chain that references no field (COUNT(*) only): rows are all that matters
         nrows = ndocs;
         appended = true;
@@ -69,8 +79,8 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     const bool trace = getenv("N1GPU_TRACE") != nullptr;
     double tp = t0;
     auto phase = [&](const char* name) { if (trace) { double t = now_sec(); fprintf(stderr, "[n1gpu shred] %-22s %8.3f ms\n", name, (t - tp) * 1e3); tp = t; } };
-    const i64 base_off = ndocs ? offsets[0] : 0;
-    const i64 nbytes = ndocs ? offsets[ndocs] - base_off : 0;
+    const i64 base_off = lines ? 0 : (ndocs ? offsets[0] : 0);
+    const i64 nbytes = lines ? text_size : (ndocs ? offsets[ndocs] - base_off : 0);
     const int ncols = (int)cols.size();
     cudaStream_t s = nullptr;
     CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -82,15 +92,37 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     d_trie.alloc(sizeof trie);
     CK(cudaMemcpyAsync(d_trie.p, &trie, sizeof trie, cudaMemcpyHostToDevice, s));
     d_buf.alloc((size_t)nbytes + 64);
-    d_offs.alloc((size_t)(ndocs + 1) * 8);
     std::vector<i64> rel;
     const i64* offs_src = offsets;
-    if (base_off != 0) {  // device offsets are relative to d_buf
-        rel.resize((size_t)ndocs + 1);
-        for (i64 i = 0; i <= ndocs; ++i) rel[(size_t)i] = offsets[i] - base_off;
-        offs_src = rel.data();
+    if (lines) {
+        // the whole text, then its line starts: counts per segment, scan, offsets (all on `s`, one host round trip for ndocs)
+        CK(cudaMemsetAsync((char*)d_buf.p + nbytes, '\n', 64, s));
+        const i64 chunk = (i64)64 << 20;
+        for (i64 at = 0; at < nbytes; at += chunk) CK(cudaMemcpyAsync((char*)d_buf.p + at, buf + at, (size_t)std::min(chunk, nbytes - at), cudaMemcpyHostToDevice, s));
+        const i64 nseg = ndjson_segments(nbytes);
+        DevBuf d_counts, d_first;
+        d_counts.alloc((size_t)(nseg + 1) * 4);
+        d_first.alloc((size_t)(nseg + 1) * 8);
+        launch_ndjson_count((const unsigned char*)d_buf.p, nbytes, d_counts.as<unsigned>(), s);
+        launch_ndjson_scan(d_counts.as<unsigned>(), nseg, d_first.as<i64>(), s);
+        i64 total = 0;
+        CK(cudaMemcpyAsync(&total, d_first.as<i64>() + nseg, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ndocs = total;
+        d_offs.alloc((size_t)(ndocs + 1) * 8);
+        launch_ndjson_write((const unsigned char*)d_buf.p, nbytes, d_first.as<i64>(), d_offs.as<i64>(), s);
+        CK(cudaMemcpyAsync(d_offs.as<i64>() + ndocs, &nbytes, 8, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));  // (&nbytes and the temporaries above go out of scope)
+        phase("h2d + line starts");
+    } else {
+        d_offs.alloc((size_t)(ndocs + 1) * 8);
+        if (base_off != 0) {  // device offsets are relative to d_buf
+            rel.resize((size_t)ndocs + 1);
+            for (i64 i = 0; i <= ndocs; ++i) rel[(size_t)i] = offsets[i] - base_off;
+            offs_src = rel.data();
+        }
+        if (!ndocs) { i64 z = 0; CK(cudaMemcpyAsync(d_offs.p, &z, 8, cudaMemcpyHostToDevice, s)); }
     }
-    if (!ndocs) { i64 z = 0; CK(cudaMemcpyAsync(d_offs.p, &z, 8, cudaMemcpyHostToDevice, s)); }
 
     nrows = ndocs;
     i64 pad = padded_rows();
@@ -117,7 +149,10 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     // The raw JSON crosses PCIe in chunks on a copy stream while the parse kernel of the chunks that have landed runs on
     // `s`: the document bytes and their offsets of chunk i+1 travel while chunk i is shredded (the H2D of the text is what
     // bounds this path - 13 ms per 664 MB - so the ~4 ms of parsing hide behind it).
-    if (ndocs) {
+    if (lines)
+        launch_shred_json((const unsigned char*)d_buf.p, d_offs.as<i64>(), 0, ndocs, (const ShredTrie*)d_trie.p, (u8* const*)d_ptrs.p,
+                          (i64* const*)((char*)d_ptrs.p + (size_t)ncols * 8), ncols, d_fixcount.as<unsigned>(), d_fixrows.as<i64>(), fix_cap, s);
+    else if (ndocs) {
         cudaStream_t cs = nullptr;
         CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         struct CopyGuard { cudaStream_t s; ~CopyGuard() { cudaStreamDestroy(s); } } cg{cs};
@@ -163,6 +198,23 @@ void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
         CK(cudaMemcpy(rows.data(), d_fixrows.p, (size_t)nfix * 8, cudaMemcpyDeviceToHost));
         std::sort(rows.begin(), rows.end());
         std::vector<HostShredOut> fx;
+        if (lines) {
+            // the documents' offsets live on the device: fetch those of the fix-up rows and shred them as a compact list
+            DevBuf d_r, d_o;
+            d_r.alloc((size_t)nfix * 8);
+            d_o.alloc((size_t)nfix * 16);
+            CK(cudaMemcpyAsync(d_r.p, rows.data(), (size_t)nfix * 8, cudaMemcpyHostToDevice, s));
+            launch_gather_offsets(d_offs.as<i64>(), d_r.as<i64>(), (i64)nfix, d_o.as<i64>(), s);
+            std::vector<i64> pairs((size_t)nfix * 2), idx(nfix);
+            CK(cudaMemcpyAsync(pairs.data(), d_o.p, pairs.size() * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            // host_shred_docs reads document i as [offs[i], offs[i + 1]): lay the pairs out as their own offset list
+            std::vector<i64> fo;
+            std::string ftext;
+            fo.push_back(0);
+            for (unsigned i = 0; i < nfix; ++i) { ftext.append(buf + pairs[2 * i], (size_t)(pairs[2 * i + 1] - pairs[2 * i])); fo.push_back((i64)ftext.size()); idx[i] = (i64)i; }
+            host_shred_docs(cols, ftext.data(), fo.data(), idx.data(), (i64)nfix, fx);
+        } else
         host_shred_docs(cols, buf, offsets, rows.data(), (i64)nfix, fx);
         std::vector<std::vector<i64>> pays((size_t)ncols);
         for (int c = 0; c < ncols; ++c) {

@@ -194,7 +194,7 @@ def test_partial_import_grows_the_owners_table():
     import torch
     from query_b200 import dist as qd
     docs = make_docs(6000, seed=91)
-    where, keys = None, [F("g")]   # a high-cardinality key: hash table mode
+    where, keys = None, [F("h")]   # a high-cardinality key: hash table mode
     aggs = ["count(*)", "sum(%s)" % F("p"), "count(distinct %s)" % F("i")]
     small, big = make_table(docs[:8], where, keys, aggs), make_table(docs[8:], where, keys, aggs)
     qd.agree_local([small, big])
