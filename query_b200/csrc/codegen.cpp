@@ -51,12 +51,10 @@ struct Gen {
     std::vector<i64> consts;            // payloads handed to the kernel as p.cst[k] (at most 32; more stay literals)
     bool const_args = true;
     explicit Gen(const Table& tt) : t(tt) { const char* e = getenv("N1GPU_CONST_LITERALS"); const_args = !(e && *e == '1'); }
-    // the payload of a constant as an expression: a kernel argument slot (shared by equal payloads), else a literal
+    // the payload of a constant as an expression: a kernel argument slot of its own (numbered by occurrence, never by
+    // value: the text must not depend on the payloads), else a literal
     std::string payload_ref(i64 bits) {
-        if (const_args) {
-            for (size_t k = 0; k < consts.size(); ++k) if (consts[k] == bits) return strf("p.cst[%d]", (int)k);
-            if (consts.size() < 32) { consts.push_back(bits); return strf("p.cst[%d]", (int)consts.size() - 1); }
-        }
+        if (const_args && consts.size() < 32) { consts.push_back(bits); return strf("p.cst[%d]", (int)consts.size() - 1); }
         return lit_i64(bits);
     }
 

@@ -503,6 +503,32 @@ std::string GpuGroupAggregate::MarshalJSON() const {
     json::quote(term.keyspace, s);
     s += ",\"namespace\":";
     json::quote(term.nspace, s);
+    // EXPLAIN in the shape the reference uses when somebody else computes the groups (plan/scan_index_groupagg.go:188-222,
+    // IndexGroupAggregates: name / group [{id, keypos, expr}] / aggregates [{aggregate, id, keypos, expr, distinct}]; ids number
+    // the group keys first, then the aggregates; keypos -1 = an expression, not an index key position; complete groups,
+    // so no "partial")
+    if (query) {
+        s += ",\"group_aggs\":{\"name\":\"GpuGroupAggregate\"";
+        if (!keys.empty()) {
+            s += ",\"group\":[";
+            for (size_t i = 0; i < keys.size(); ++i) { s += strf("%s{\"id\":%d,\"keypos\":-1,\"expr\":", i ? "," : "", (int)i); json::quote(keys[i], s); s += "}"; }
+            s += "]";
+        }
+        if (!query->aggs.empty()) {
+            static const char* ops[] = {"COUNT", "COUNTN", "SUM", "AVG", "MIN", "MAX"};
+            s += ",\"aggregates\":[";
+            for (size_t i = 0; i < query->aggs.size(); ++i) {
+                const Expr& a = *query->aggs[i];
+                s += strf("%s{\"aggregate\":\"%s\",\"id\":%d,\"keypos\":-1", i ? "," : "", ops[(int)a.agg], (int)(keys.size() + i));
+                if (a.distinct) s += ",\"distinct\":true";
+                s += ",\"expr\":";
+                json::quote(a.star ? std::string("*") : a.ops[0]->str(), s);
+                s += "}";
+            }
+            s += "]";
+        }
+        s += "}";
+    }
     if (!tail.empty()) {  // the operators behind FinalGroup this operator also stands for
         s += ",\"tail\":[";
         for (size_t i = 0; i < tail.operators.size(); ++i) { if (i) s += ","; json::quote(tail.operators[i], s); }

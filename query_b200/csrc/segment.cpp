@@ -166,22 +166,29 @@ void Table::load_ndjson(const std::string& file, int threads) {
         for (int t = 0; t < nthr; ++t) pool.emplace_back(fn, t);
         for (auto& th : pool) th.join();
     };
-    run([&](int t) {
-        size_t at = slice(t);
-        const size_t end = slice(t + 1);
-        while (at < end) {
-            const ssize_t got = pread(fd, data + at, end - at, (off_t)at);
-            if (got <= 0) { errs[(size_t)t] = "short read of " + file; return; }
-            at += (size_t)got;
-        }
-    });
-    for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_IO, "%s", e.c_str());
-    phase("alloc + parallel read");
-    if (device && have_device()) {  // the device finds the line starts itself (shred.cu k_ndjson_lines)
-        append_ndjson_device(data, (i64)size);
-        phase("shred");
+    // bytes [lo, hi) of the file, read by all threads at once
+    auto read_range = [&](size_t lo, size_t hi) {
+        const size_t span = hi - lo;
+        run([&](int t) {
+            size_t at = lo + span * (size_t)t / (size_t)nthr;
+            const size_t end = lo + span * (size_t)(t + 1) / (size_t)nthr;
+            while (at < end) {
+                const ssize_t got = pread(fd, data + at, end - at, (off_t)at);
+                if (got <= 0) { errs[(size_t)t] = "short read of " + file; return; }
+                at += (size_t)got;
+            }
+        });
+        for (auto& e : errs) if (!e.empty()) N1_THROW(N1GPU_E_IO, "%s", e.c_str());
+    };
+    if (device && have_device()) {
+        // the device finds the line starts itself (shred.cu k_ndjson_lines); the file is read chunk by chunk while the chunks
+        // before it cross PCIe
+        append_ndjson_device(data, (i64)size, [&](i64 lo, i64 hi) { read_range((size_t)lo, (size_t)hi); });
+        phase("read + shred");
         return;
     }
+    read_range(0, size);
+    phase("alloc + parallel read");
     // document i = [start of its line, start of the next non-blank line): the line end and blank lines are trailing white
     // space of the document before them (value/parsed.go:76-98 skips leading ' ', '\t', '\n'; JSON allows trailing space)
     auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r'; };

@@ -1,6 +1,7 @@
 // table.hpp — a shredded keyspace: typed columns + per-column sorted dictionaries, resident in HBM.
 #pragma once
 #include <map>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -58,8 +59,10 @@ struct Table {
 
     // threads >= 0: host threads (0 = all cores); threads == -1: the device shredder (shred.cu)
     void append_json_device(const char* buf, const i64* offsets, i64 ndocs);
-    void append_ndjson_device(const char* text, i64 size);  // one document per line; offsets computed on the device
-    void append_text_device(const char* buf, const i64* offsets, i64 ndocs, i64 text_size);
+    // one document per line; offsets computed on the device.  `fill(lo, hi)` (optional) makes bytes [lo, hi) of text valid just
+    // before they are copied: a file is read chunk by chunk while the chunks before it cross PCIe
+    void append_ndjson_device(const char* text, i64 size, const std::function<void(i64, i64)>& fill = nullptr);
+    void append_text_device(const char* buf, const i64* offsets, i64 ndocs, i64 text_size, const std::function<void(i64, i64)>& fill);
     int add_column(const std::string& path);
     int find_column(const std::string& path) const;
     void append_json(const char* buf, const i64* offsets, i64 ndocs, int threads);

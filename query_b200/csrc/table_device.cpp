@@ -56,14 +56,14 @@ u64 pow2_at_least(u64 n) { u64 p = 1; while (p < n) p <<= 1; return p; }
 
 void Table::append_json_device(const char* buf, const i64* offsets, i64 ndocs) {
     if (ndocs < 0) N1_THROW(N1GPU_E_INVALID, "negative document count");
-    append_text_device(buf, offsets, ndocs, 0);
+    append_text_device(buf, offsets, ndocs, 0, nullptr);
 }
 
 // One JSON document per line, `size` bytes at text (readable up to text + size + 64): the document offsets are computed on
 // the device from the text itself (k_ndjson_lines) - no host pass over the text, no offsets over PCIe.
-void Table::append_ndjson_device(const char* text, i64 size) { append_text_device(text, nullptr, -1, size); }
+void Table::append_ndjson_device(const char* text, i64 size, const std::function<void(i64, i64)>& fill) { append_text_device(text, nullptr, -1, size, fill); }
 
-void Table::append_text_device(const char* buf, const i64* offsets, i64 ndocs, i64 text_size) {
+void Table::append_text_device(const char* buf, const i64* offsets, i64 ndocs, i64 text_size, const std::function<void(i64, i64)>& fill) {
     const bool lines = offsets == nullptr;  // NDJSON: offsets come from the device
     if (sealed) N1_THROW(N1GPU_E_INVALID, "table is sealed");
     if (!have_device()) N1_THROW(N1GPU_E_CUDA, "the device shredder needs a CUDA device (there is no CPU fallback for it; use host threads explicitly)");
@@ -98,7 +98,11 @@ void Table::append_text_device(const char* buf, const i64* offsets, i64 ndocs, i
         // the whole text, then its line starts: counts per segment, scan, offsets (all on `s`, one host round trip for ndocs)
         CK(cudaMemsetAsync((char*)d_buf.p + nbytes, '\n', 64, s));
         const i64 chunk = (i64)64 << 20;
-        for (i64 at = 0; at < nbytes; at += chunk) CK(cudaMemcpyAsync((char*)d_buf.p + at, buf + at, (size_t)std::min(chunk, nbytes - at), cudaMemcpyHostToDevice, s));
+        for (i64 at = 0; at < nbytes; at += chunk) {
+            const i64 hi = std::min(at + chunk, nbytes);
+            if (fill) fill(at, hi);  // (the copy of the chunk before this one is in flight meanwhile)
+            CK(cudaMemcpyAsync((char*)d_buf.p + at, buf + at, (size_t)(hi - at), cudaMemcpyHostToDevice, s));
+        }
         const i64 nseg = ndjson_segments(nbytes);
         DevBuf d_counts, d_first;
         d_counts.alloc((size_t)(nseg + 1) * 4);

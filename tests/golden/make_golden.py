@@ -77,6 +77,8 @@ def main():
             keyspaces["multistore/%s/%s" % (area, name)] = docs
     # config 1 of BASELINE.json: data/sampledb/dimestore/product (the same 900 products, no test_id)
     keyspaces["sampledb/dimestore/product"] = file_keyspace(os.path.join(REF, "data/sampledb/dimestore/product"))
+    # ... and its second query: data/sampledb/dimestore/review (10 000 reviews, int `rating`), SURVEY.md 8d.1
+    keyspaces["sampledb/dimestore/review"] = file_keyspace(os.path.join(REF, "data/sampledb/dimestore/review"))
 
     golden = {
         "filestore/case_group_by_having": cases(os.path.join(fs, "cases/case_group_by_having.json")),

@@ -44,6 +44,62 @@ def test_golden_filters_through_query_abi(case):
     assert res.rows() == [([], [len(case.golden["results"])])]
 
 
+def _with_row_id(text, i):
+    """the document with a unique field `__row` (the statements of case_where project whole documents: row identity)"""
+    t = text.strip()
+    if not t.startswith("{"):
+        return text
+    rest = t[1:].lstrip()
+    return '{"__row": %d%s%s' % (i, "" if rest.startswith("}") else ", ", rest)
+
+
+@pytest.mark.parametrize("case", WHERE_CASES, ids=lambda c: c.id)
+def test_golden_filters_select_the_same_documents(case):
+    """Row identity, not only the row count: every document gets a unique `__row`; GROUP BY it under the golden statement's
+    WHERE yields one group per selected document - the same documents as the oracle selects, as many as the golden holds."""
+    docs = [_with_row_id(t, i) for i, (_k, t) in enumerate(case.docs())]
+    key = "(`%s`.`__row`)" % case.alias
+    qq, res = run_both(docs, case.alias, case.where, [key], ["count(*)"], case.id + " rows")
+    rows = res.rows()
+    assert len(rows) == len(case.golden["results"]) and all(a == [1] for _k, a in rows), case.golden["statements"]
+
+
+@pytest.mark.parametrize("ks,alias,sql,where,keys,aggs,tail", [
+    ("sampledb/dimestore/product", "product",
+     "SELECT color, COUNT(*), SUM(unitPrice), AVG(unitPrice), MIN(unitPrice), MAX(unitPrice) FROM product WHERE unitPrice > 10 GROUP BY color",
+     "(10 < (`product`.`unitPrice`))", ["(`product`.`color`)"],
+     ["count(*)", "sum((`product`.`unitPrice`))", "avg((`product`.`unitPrice`))", "min((`product`.`unitPrice`))", "max((`product`.`unitPrice`))"],
+     dict(terms=[("(`product`.`color`)", None), ("count(*)", None), ("sum((`product`.`unitPrice`))", None), ("avg((`product`.`unitPrice`))", None),
+                 ("min((`product`.`unitPrice`))", None), ("max((`product`.`unitPrice`))", None)], order=[("(`product`.`color`)", False)])),
+    ("sampledb/dimestore/review", "review", "SELECT rating, COUNT(*) FROM review WHERE rating > 1 GROUP BY rating",
+     "(1 < (`review`.`rating`))", ["(`review`.`rating`)"], ["count(*)"],
+     dict(terms=[("(`review`.`rating`)", None), ("count(*)", None)], order=[("(`review`.`rating`)", False)])),
+], ids=["product", "review"])
+def test_baseline_config1_statements_through_the_operator(ks, alias, sql, where, keys, aggs, tail, tmp_path):
+    """BASELINE.json configs[0]: the two statements on data/sampledb/dimestore - 900 products (float
+    unitPrice, 31 colours) and 10 000 reviews (int rating) - from the reference's plan JSON through the operator and its tail,
+    against the oracle's chain + tail over the same documents (the oracle is pinned to the reference's golden rows over these
+    very products: test/multistore/test_cases/aggregate_functions/case_group_by_having.json)."""
+    from oracle import n1ql_oracle as O
+    docs = keyspaces()[ks]
+    name = ks.split("/")[-1]
+    write_keyspace(str(tmp_path), "dimestore", name, docs)
+    aggs_sorted = sorted(set(aggs))
+    op = q.Operator(explain_plan("dimestore", name, alias, where, keys, aggs_sorted, tail=tail), str(tmp_path), tail=True)
+    got = op.run_tail(op.run_once())
+    groups = O.run_chain([O.parse_document(t) for _k, t in docs], alias, where, keys, aggs_sorted)
+    want = O.run_tail(groups, terms=tail["terms"], order=tail["order"])
+    assert len(got) == len(want) > 3
+    for g, w in zip(got, want):
+        assert g.keys() == w.keys()
+        for k in g:
+            a, b = normalise(g[k]), normalise(w[k])
+            if isinstance(a, float) or isinstance(b, float):
+                assert abs(a - b) <= 1e-12 * max(abs(a), abs(b)), (sql, k, a, b)
+            else:
+                assert a == b, (sql, k, a, b)
+
+
 @pytest.mark.parametrize("case", CASES[:6] + CASES[10:14], ids=lambda c: c.id)
 def test_golden_through_plan_operator(case, tmp_path):
     """The reference-facing entry: plan JSON in EXPLAIN shape + a file-datastore directory."""
@@ -58,6 +114,13 @@ def test_golden_through_plan_operator(case, tmp_path):
     assert normalise(got) == normalise(case.golden["results"])
     m = op.marshal_json()
     assert m["#operator"] == "GpuGroupAggregate" and m["#stats"]["#itemsIn"] == len(case.docs())
+    # EXPLAIN in the reference's group-aggregate pushdown shape (plan/scan_index_groupagg.go:188-222)
+    ga = m["group_aggs"]
+    assert ga["name"] == "GpuGroupAggregate" and [g["expr"] for g in ga.get("group", [])] == list(case.keys)
+    assert [g["id"] for g in ga.get("group", [])] == list(range(len(case.keys)))
+    assert len(ga["aggregates"]) == len(aggs) and all(a["aggregate"] in ("COUNT", "COUNTN", "SUM", "AVG", "MIN", "MAX") for a in ga["aggregates"])
+    assert [a["id"] for a in ga["aggregates"]] == list(range(len(case.keys), len(case.keys) + len(aggs)))
+    assert all(bool(a.get("distinct")) == ("distinct" in t) for a, t in zip(ga["aggregates"], aggs))
     rows = res.to_json()
     assert len(rows) == res.num_groups
     for r in rows:
