@@ -325,17 +325,26 @@ class Result:
 
     def arrays(self):
         """(key_cls, key_val, agg_cls, agg_val, strings): the flat result arrays and the string table (utf-8 bytes) that
-        string payloads index - what Operator.import_arrays takes."""
+        string payloads index - what Operator.import_arrays takes.  (Inside the library a string payload may be a
+        (dictionary column, rank) reference; here every distinct one gets an index of the returned table.)"""
         self._fetch()
-        strings = []
-        for cls, val in ((self.key_cls, self.key_val), (self.agg_cls, self.agg_val)):
-            if cls.size and (cls == C_STRING).any():
-                top = int(val[cls == C_STRING].max())
-                while len(strings) <= top:
+        kc, kv, ac, av = self.key_cls.copy(), self.key_val.copy(), self.agg_cls.copy(), self.agg_val.copy()
+        strings, index = [], {}
+        for cls, val in ((kc, kv), (ac, av)):
+            if not (cls.size and (cls == C_STRING).any()):
+                continue
+            mask = cls == C_STRING
+            uniq, inv = np.unique(val[mask], return_inverse=True)
+            remap = np.empty(len(uniq), dtype=np.int64)
+            for i, u in enumerate(uniq.tolist()):
+                if u not in index:
                     p, n = C.c_char_p(), C.c_int64()
-                    check(lib().n1gpu_result_string(self._h, len(strings), C.byref(p), C.byref(n)))
+                    check(lib().n1gpu_result_string(self._h, int(u), C.byref(p), C.byref(n)))
+                    index[u] = len(strings)
                     strings.append(C.string_at(p, n.value))
-        return self.key_cls.copy(), self.key_val.copy(), self.agg_cls.copy(), self.agg_val.copy(), strings
+                remap[i] = index[u]
+            val[mask] = remap[inv]
+        return kc, kv, ac, av, strings
 
     def rows(self):
         """[(keys list, aggregates list)] with python values (int / float / str / bool / None / MISSING)."""

@@ -493,9 +493,10 @@ int n1gpu_result_fetch(const n1gpu_result* r, uint8_t* key_cls, int64_t* key_val
 int n1gpu_result_string(const n1gpu_result* r, int64_t index, const char** ptr, int64_t* len) {
     return guard([&] {
         REQUIRE(r); REQUIRE(ptr); REQUIRE(len);
-        if (index < 0 || index >= (i64)r->r->strings.size()) N1_THROW(N1GPU_E_INVALID, "string index out of range");
-        *ptr = r->r->strings[(size_t)index].data();
-        *len = (int64_t)r->r->strings[(size_t)index].size();
+        if (!r->r->string_ok(index)) N1_THROW(N1GPU_E_INVALID, "string index out of range");
+        const std::string& str = r->r->string_at(index);
+        *ptr = str.data();
+        *len = (int64_t)str.size();
     });
 }
 int n1gpu_result_stats(const n1gpu_result* r, int64_t stats[8]) {

@@ -834,28 +834,11 @@ std::unique_ptr<Result> Query::finalize() {
     bool any_string = false;  // can a key or an aggregate be a string at all?
     for (auto& pc : kp.keys) any_string = any_string || (pc.mask & bit(C_STRING));
     for (auto& ap : kp.aggs) any_string = any_string || ap.w_ms >= 0;
-    if (any_string) {   // strings: (column, rank) references -> the result's own string table (it may outlive the table)
-        std::vector<std::vector<i64>> pool(table->cols.size());  // [column][rank] -> index in res->strings, -1 = not yet
-        i64 empty_at = -1;
-        auto resolve = [&](FlatArr<u8>& cls, FlatArr<i64>& val) {
-            for (size_t i = 0; i < cls.size(); ++i) {
-                if (cls[i] != C_STRING) continue;
-                const size_t col = (size_t)((u64)val[i] >> 40);
-                const u64 rank = (u64)val[i] & 0xffffffffffULL;
-                const auto& d = table->cols[col].dict;
-                if (rank >= d.size()) {
-                    if (empty_at < 0) { empty_at = (i64)res->strings.size(); res->strings.emplace_back(); }
-                    val[i] = empty_at;
-                    continue;
-                }
-                auto& slots = pool[col];
-                if (slots.empty()) slots.assign(d.size(), -1);
-                if (slots[rank] < 0) { slots[rank] = (i64)res->strings.size(); res->strings.push_back(d[rank]); }
-                val[i] = slots[rank];
-            }
-        };
-        resolve(res->key_cls, res->key_val);
-        resolve(res->agg_cls, res->agg_val);
+    if (any_string) {   // strings stay (column, rank) references: the result shares the dictionaries, nothing is copied
+        res->string_refs = true;
+        res->dicts.resize(table->cols.size());
+        for (auto& pc : kp.keys) if (pc.dict_col >= 0) res->dicts[(size_t)pc.dict_col] = table->cols[(size_t)pc.dict_col].dict.share();
+        for (auto& ap : kp.aggs) if (ap.w_ms >= 0 && ap.dict_col >= 0) res->dicts[(size_t)ap.dict_col] = table->cols[(size_t)ap.dict_col].dict.share();
     }
     phase("ComputeFinal");
     i64 scan_bytes = (i64)kp.scan_bytes_per_row * table->nrows;

@@ -38,10 +38,22 @@ struct Result {
     FlatArr<i64> key_val, agg_val;
     PinnedBuf pinned;  // backing store of the arrays when the groups were finalised on the device
     std::vector<std::string> strings;
+    // Strings of groups finalised here are REFERENCES (dictionary column << 40 | rank) into the table's dictionaries, which
+    // the result keeps alive; nothing is copied until a string is asked for.  Imported results own `strings` instead.
+    bool string_refs = false;
+    std::vector<std::shared_ptr<const std::vector<std::string>>> dicts;  // [column]
+    const std::string& string_at(i64 val) const {
+        static const std::string empty;
+        if (!string_refs) return strings[(size_t)val];
+        const size_t col = (size_t)((u64)val >> 40), rank = (size_t)((u64)val & 0xffffffffffULL);
+        if (col >= dicts.size() || !dicts[col] || rank >= dicts[col]->size()) return empty;
+        return (*dicts[col])[rank];
+    }
+    bool string_ok(i64 val) const { return string_refs ? val >= 0 : (val >= 0 && (size_t)val < strings.size()); }
     HValue value(u8 cls, i64 val) const {
         HValue v;
         v.cls = cls;
-        if (cls == C_STRING) v.s = strings[(size_t)val]; else v.bits = val;
+        if (cls == C_STRING) v.s = string_at(val); else v.bits = val;
         return v;
     }
     HValue key(i64 g, int k) const { const size_t i = (size_t)g * nkeys + k; return value(key_cls[i], key_val[i]); }

@@ -2,6 +2,7 @@
 #pragma once
 #include <map>
 #include <functional>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -11,6 +12,32 @@
 namespace n1 {
 
 const i64 ROW_PAD = 4096;  // device arrays are padded to a multiple of this many rows (vector loads never fault)
+
+// A column's dictionary: a vector of strings that results can keep alive after the table is gone (a result refers to its
+// strings as (column, rank) and resolves them on demand - a million-group result copies no string at finalisation).
+// The table is immutable once sealed, so sharing needs no copy-on-write.
+class SharedDict {
+    std::shared_ptr<std::vector<std::string>> p = std::make_shared<std::vector<std::string>>();
+public:
+    typedef std::vector<std::string>::const_iterator const_iterator;
+    size_t size() const { return p->size(); }
+    bool empty() const { return p->empty(); }
+    const std::string& operator[](size_t i) const { return (*p)[i]; }
+    std::string& operator[](size_t i) { return (*p)[i]; }
+    const_iterator begin() const { return p->begin(); }
+    const_iterator end() const { return p->end(); }
+    void clear() { p = std::make_shared<std::vector<std::string>>(); }
+    void reserve(size_t n) { p->reserve(n); }
+    void resize(size_t n) { p->resize(n); }
+    template <class... A> void emplace_back(A&&... a) { p->emplace_back(std::forward<A>(a)...); }
+    void push_back(const std::string& s) { p->push_back(s); }
+    void swap(std::vector<std::string>& o) { auto n = std::make_shared<std::vector<std::string>>(); n->swap(o); o.swap(*p); p = n; }
+    SharedDict& operator=(std::vector<std::string>&& o) { p = std::make_shared<std::vector<std::string>>(std::move(o)); return *this; }
+    bool operator!=(const SharedDict& o) const { return *p != *o.p; }
+    bool operator==(const SharedDict& o) const { return *p == *o.p; }
+    const std::vector<std::string>& vec() const { return *p; }
+    std::shared_ptr<const std::vector<std::string>> share() const { return p; }
+};
 
 struct ColumnStats {
     u32 class_mask = 0;  // classes that occur (bit per C_*)
@@ -29,7 +56,7 @@ struct Column {
     // host staging (dropped after seal unless keep_host)
     std::vector<i64> payload;            // 8 bytes per row while staging
     std::vector<u8> tags;
-    std::vector<std::string> dict;       // sorted, unique (after seal / import)
+    SharedDict dict;                     // sorted, unique (after seal / import); results keep it alive (share())
     bool dict_global = false;            // dictionary imported (multi-GPU): do not rebuild at seal
     std::vector<std::string> local_strings;  // staging: distinct strings, codes index this until seal
     bool codes_are_ranks = false;        // set_column supplied ranks into `dict` already
