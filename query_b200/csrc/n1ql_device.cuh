@@ -511,7 +511,7 @@ struct NqParams {
     // payloads of the chain's constants and bound parameters (int64 / float64 bits / 2 * dictionary rank): the kernel text
     // only fixes their CLASS, so statements that differ in a bound - or bindings of one prepared statement - share a cubin
     i64 cst[32];
-    // execution.Operator.SendStop while the scan runs: a word in pinned host memory (mapped) that n1gpu_query_cancel sets;
+    // execution.Operator.SendStop while the scan runs: a word in HBM that n1gpu_query_cancel sets with an asynchronous copy;
     // lane 0 of every warp polls it once per 32 tiles and the warp leaves the loop
     const int* cancel;
 };

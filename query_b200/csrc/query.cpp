@@ -62,6 +62,17 @@ Query::~Query() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (cancel_stream) cudaStreamDestroy(cancel_stream);
+}
+
+void Query::cancel() {
+    cancelled.store(true);
+    if (!d_cancel.p) return;
+    int prev = 0;  // SendStop may come from any thread: the copy must be issued on this query's device
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = device;
+    if (prev != device) cudaSetDevice(device);
+    cudaMemcpyAsync(d_cancel.p, h_cancel.p, 4, cudaMemcpyHostToDevice, cancel_stream);
+    if (prev != device) cudaSetDevice(prev);
 }
 
 std::unique_ptr<Query> Query::compile(Table* t, const std::string& alias, const char* where,
@@ -165,7 +176,14 @@ void Query::alloc_state() {
         d_part_recs.ensure((size_t)(np * part_cap) * 4);
         d_part_cur.ensure((size_t)np * 4);
     }
-    if (!h_cancel.p) { h_cancel.ensure(64); memset(h_cancel.p, 0, 64); }
+    if (!d_cancel.p) {
+        CK(cudaGetDevice(&device));
+        d_cancel.alloc(64);
+        CK(cudaMemset(d_cancel.p, 0, 64));
+        h_cancel.ensure(64);
+        *h_cancel.as<int>() = 1;
+        CK(cudaStreamCreateWithFlags(&cancel_stream, cudaStreamNonBlocking));
+    }
     d_status.ensure(64);
     h_status.ensure(64);
     memset(h_status.p, 0, 64);
@@ -227,7 +245,7 @@ void Query::launch_scan() {
     p.nrows = table->nrows;
     for (size_t c = 0; c < table->cols.size(); ++c) { p.col[c] = table->cols[c].d_payload.p; p.tag[c] = table->cols[c].d_tags.as<u8>(); }
     for (size_t k = 0; k < kp.consts.size() && k < 32; ++k) p.cst[k] = kp.consts[k];
-    p.cancel = h_cancel.as<int>();
+    p.cancel = d_cancel.as<int>();
     p.acc = kp.mode == MODE_UNGROUPED ? d_accum.as<u64>() : acc();
     p.partials = d_partials.as<u64>();
     p.keys = d_keys.as<u64>();

@@ -140,8 +140,13 @@ struct Query {
     DevBuf d_partials, d_acc, d_accum, d_keys, d_set, d_status, d_counts, d_records, d_drecords, d_ticket, d_final;
     PinnedBuf h_status, h_counts, h_records, h_drecords;
     std::atomic<bool> cancelled{false};
-    PinnedBuf h_cancel;          // the word the running kernel polls (mapped pinned memory)
-    void cancel() { cancelled.store(true); if (h_cancel.p) *(volatile int*)h_cancel.p = 1; }
+    // The word a running kernel polls lives in HBM (polling host memory over PCIe cost 40x the scan); cancel() sets it with
+    // an asynchronous copy on a stream of its own, which the copy engine executes while the scan runs.
+    DevBuf d_cancel;
+    PinnedBuf h_cancel;          // the value 1, in pinned memory (source of that copy)
+    cudaStream_t cancel_stream = nullptr;
+    int device = 0;
+    void cancel();
     bool launched = false;
     bool timing = true;        // record CUDA events around the scan (each record costs GPU front-end time)
     bool timed_launch = false;
