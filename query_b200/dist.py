@@ -298,12 +298,10 @@ class DistributedQuery:
         """Returns a Result holding this rank's share of the groups (small state: rank 0 holds all, others none)."""
         q = self.q
         w = world()
-        if w > 1 and (self.small or self.peer):
+        if w == 1 or self.small or self.peer:
             self.launch()
             return self.q.collect()
         q.scan_partial()
-        if w == 1:
-            return q.finalize()
         ng, nd, rw = q.partial_counts()
         self._buffers(ng, nd, rw)
         has_distinct = nd > 0 or "distinct" in " ".join(q.aggregates)

@@ -74,12 +74,12 @@ __global__ void k_fill4(u64* p, u64 nslots, u64 a, u64 b, u64 c, u64 d) {
 #define QCAP 64
 struct QParams { const u32* code; const u8* ktag; const i64* v; const u8* vtag; i64 nrows; u64* table; };
 
-template <int NT, int NS, int K0>
+template <int NT, int NS, int K0, int QUEUES = 1>
 struct Smem {
     u32 ckey[NS];
     u32 c_rows[NS], c_cnull[NS], c_sum[NS], c_nmin[NS], c_max[NS];
-    u32 qkey[NT / 32][QCAP], qval[NT / 32][QCAP];
-    u32 mkey[NT / 32][QCAP], mval[NT / 32][QCAP];
+    u32 qkey[QUEUES ? NT / 32 : 1][QCAP], qval[QUEUES ? NT / 32 : 1][QCAP];
+    u32 mkey[QUEUES ? NT / 32 : 1][QCAP], mval[QUEUES ? NT / 32 : 1][QCAP];
     u32 l0key[K0 ? K0 : 1][32], l0n[K0 ? K0 : 1][32], l0sum[K0 ? K0 : 1][32], l0nmin[K0 ? K0 : 1][32], l0max[K0 ? K0 : 1][32];
 };
 
@@ -109,10 +109,10 @@ __device__ __forceinline__ int cache_claim_w(u32* ckeys, u32 nslots, u32 hash, u
     return (old == 0xffffffffu || old == key) ? (int)b : -1;
 }
 
-template <int NT, int NS, int K0, int L0T, int WAYS, int CHECK, int PREF, int MNREG>
+template <int NT, int NS, int K0, int L0T, int WAYS, int CHECK, int PREF, int MNREG, int QROWS, int PAIR, int SOA>
 __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef Smem<NT, NS, K0> S;
+    typedef Smem<NT, NS, K0, (QROWS || PAIR)> S;
     S& s = *reinterpret_cast<S*>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -123,9 +123,11 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
     u32 r_rows[2] = {0, 0}, r_cnull[2] = {0, 0}, r_nmin[2] = {0, 0}, r_max[2] = {0, 0};
     u64 r_sum[2] = {0, 0};
     unsigned qhead = 0, qtail = 0, mhead = 0, mtail = 0;  // warp-uniform ring cursors
-    u32* const qk = s.qkey[w]; u32* const qv = s.qval[w];
-    u32* const mk = s.mkey[w]; u32* const mv = s.mval[w];
+    u32* const qk = s.qkey[(QROWS || PAIR) ? w : 0]; u32* const qv = s.qval[(QROWS || PAIR) ? w : 0];
+    u32* const mk = s.mkey[(QROWS || PAIR) ? w : 0]; u32* const mv = s.mval[(QROWS || PAIR) ? w : 0];
     u64* const table = p.table;
+    // word w of group `key`: one 32-byte sector per group (slot-major), or word planes (SOA: the round-1 layout)
+    auto word = [&](u32 key, int w) -> u64* { return SOA ? table + (u64)w * SLOTS + key : table + (u64)key * 4 + w; };
 
     auto flush_miss = [&](bool all) {
         // lane pairs: lane 2e works on word (lane & 1) of entry e's slot: one RED per operation class
@@ -145,11 +147,7 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
             mhead += n;
         }
     };
-    auto drain = [&](unsigned n) {
-        const bool active = (unsigned)lane < n;
-        const unsigned idx = (qhead + lane) & (QCAP - 1);
-        const u32 key = active ? qk[idx] : 0u, val = active ? qv[idx] : 0u;
-        qhead += n;
+    auto process = [&](bool active, u32 key, u32 val) {
         int slot = -2;
         if (active) slot = cache_claim_w<WAYS>(s.ckey, NS, key * 0x9E3779B1u, key);
         if (slot >= 0) {
@@ -159,7 +157,7 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
             if (isnull) atomicAdd(&s.c_cnull[slot], 1u);
             else {
                 const u32 so = atomicAdd(&s.c_sum[slot], vb);
-                if ((u32)(so + vb) < vb) red_add_u64(table + (u64)key * 4 + 1, 1ULL << 32);  // carry out of the 32-bit cell (rare)
+                if ((u32)(so + vb) < vb) red_add_u64(word(key, 1), 1ULL << 32);  // carry out of the 32-bit cell (rare)
                 const u32 a = vb + 1u, b = 0x100000u - vb;
                 if (!CHECK || a > *(volatile u32*)&s.c_max[slot]) atomicMax(&s.c_max[slot], a);
                 if (!CHECK || b > *(volatile u32*)&s.c_nmin[slot]) atomicMax(&s.c_nmin[slot], b);
@@ -169,6 +167,15 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
                 if (*(volatile u32*)&s.l0key[e][lane] == 0xffffffffu) atomicCAS(&s.l0key[e][lane], 0xffffffffu, key);
             }
         }
+        if (!PAIR) {  // every missed lane reduces its own words, one RED per word
+            if (slot == -1) {
+                const bool isnull = val >> 31;
+                const u32 vb = val & 0xfffffu;
+                red_add_u64(word(key, 0), 1ULL | ((u64)isnull << 32));
+                if (!isnull) { red_add_u64(word(key, 1), (u64)vb); const i64 vv = (i64)vb - VBIAS; red_max_s64(word(key, 2), ~vv); red_max_s64(word(key, 3), vv); }
+            }
+            return;
+        }
         const unsigned mm = __ballot_sync(0xffffffffu, slot == -1);
         if (mm) {
             if (slot == -1) { const unsigned at = (mtail + __popc(mm & lt)) & (QCAP - 1); mk[at] = key; mv[at] = val; }
@@ -176,6 +183,13 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
             __syncwarp();
             flush_miss(false);
         }
+    };
+    auto drain = [&](unsigned n) {
+        const bool active = (unsigned)lane < n;
+        const unsigned idx = (qhead + lane) & (QCAP - 1);
+        const u32 key = active ? qk[idx] : 0u, val = active ? qv[idx] : 0u;
+        qhead += n;
+        process(active, key, val);
     };
 
     const i64 nrows = p.nrows;
@@ -224,6 +238,10 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
                     if (b > *(volatile u32*)&s.l0nmin[e][lane]) atomicMax(&s.l0nmin[e][lane], b);
                 }
             }
+            if (!QROWS) {  // no compaction: the rows of this warp-row go to the cache as they are (partial warps)
+                if (__ballot_sync(0xffffffffu, tostr)) process(tostr, key, vb | ((u32)isnull << 31));
+                continue;
+            }
             const unsigned m = __ballot_sync(0xffffffffu, tostr);
             if (tostr) { const unsigned at = (qtail + __popc(m & lt)) & (QCAP - 1); qk[at] = key; qv[at] = vb | ((u32)isnull << 31); }
             qtail += __popc(m);
@@ -244,23 +262,21 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
             mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); nm = max(nm, __shfl_xor_sync(0xffffffffu, nm, o));
         }
         if (lane == 0 && rows) {
-            u64* const slot = table + (u64)g * 4;
-            red_add_u64(slot, rows | (cn << 32));
-            if (sm) red_add_u64(slot + 1, sm);
-            if (mx) red_max_s64(slot + 3, (i64)(mx - 1u) - VBIAS);
-            if (nm) red_max_s64(slot + 2, ~((i64)(0x100000u - nm) - VBIAS));
+            red_add_u64(word(g, 0), rows | (cn << 32));
+            if (sm) red_add_u64(word(g, 1), sm);
+            if (mx) red_max_s64(word(g, 3), (i64)(mx - 1u) - VBIAS);
+            if (nm) red_max_s64(word(g, 2), ~((i64)(0x100000u - nm) - VBIAS));
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NS; i += NT) {
         const u32 key = s.ckey[i];
         if (key == 0xffffffffu) continue;
-        u64* const slot = table + (u64)key * 4;
         const u64 w0 = (u64)s.c_rows[i] | ((u64)s.c_cnull[i] << 32);
-        if (w0) red_add_u64(slot, w0);
-        if (s.c_sum[i]) red_add_u64(slot + 1, (u64)s.c_sum[i]);
-        if (s.c_max[i]) red_max_s64(slot + 3, (i64)(s.c_max[i] - 1u) - VBIAS);
-        if (s.c_nmin[i]) red_max_s64(slot + 2, ~((i64)(0x100000u - s.c_nmin[i]) - VBIAS));
+        if (w0) red_add_u64(word(key, 0), w0);
+        if (s.c_sum[i]) red_add_u64(word(key, 1), (u64)s.c_sum[i]);
+        if (s.c_max[i]) red_max_s64(word(key, 3), (i64)(s.c_max[i] - 1u) - VBIAS);
+        if (s.c_nmin[i]) red_max_s64(word(key, 2), ~((i64)(0x100000u - s.c_nmin[i]) - VBIAS));
     }
     if (K0) for (int i = threadIdx.x; i < K0 * 32; i += NT) {
         const u32 key = (&s.l0key[0][0])[i];
@@ -291,25 +307,26 @@ static bool check(const char* name, const Ref& r, const std::vector<u64>& rows, 
     return bad == 0;
 }
 
-template <int NT, int NS, int K0, int L0T, int WAYS = 4, int CHECK = 1, int PREF = 0, int MNREG = 1>
+template <int NT, int NS, int K0, int L0T, int WAYS = 4, int CHECK = 1, int PREF = 0, int MNREG = 1, int QROWS = 1, int PAIR = 1, int SOA = 0>
 static void run_q(const char* name, const QParams& qp0, u64* d_tab, const Ref& ref, i64 n, int sms) {
-    typedef Smem<NT, NS, K0> S;
+    typedef Smem<NT, NS, K0, (QROWS || PAIR)> S;
     const size_t smem = sizeof(S);
-    CKE(cudaFuncSetAttribute(k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CKE(cudaFuncSetAttribute(k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG, QROWS, PAIR, SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa;
-    CKE(cudaFuncGetAttributes(&fa, k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG>));
+    CKE(cudaFuncGetAttributes(&fa, k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG, QROWS, PAIR, SOA>));
     int occ = 0;
-    CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG>, NT, smem));
+    CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG, QROWS, PAIR, SOA>, NT, smem));
     QParams qp = qp0;
     qp.table = d_tab;
     cudaEvent_t e0, e1;
     CKE(cudaEventCreate(&e0)); CKE(cudaEventCreate(&e1));
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
-        k_fill4<<<592, 256>>>(d_tab, SLOTS, 0, 0, (u64)NQ_I64_MIN, (u64)NQ_I64_MIN);
+        if (SOA) { k_fill<<<592, 256>>>(d_tab, 2 * SLOTS, 0); k_fill<<<592, 256>>>(d_tab + 2 * SLOTS, 2 * SLOTS, (u64)NQ_I64_MIN); }
+        else k_fill4<<<592, 256>>>(d_tab, SLOTS, 0, 0, (u64)NQ_I64_MIN, (u64)NQ_I64_MIN);
         CKE(cudaDeviceSynchronize());
         CKE(cudaEventRecord(e0));
-        k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG><<<sms * occ, NT, smem>>>(qp);
+        k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG, QROWS, PAIR, SOA><<<sms * occ, NT, smem>>>(qp);
         CKE(cudaEventRecord(e1));
         CKE(cudaDeviceSynchronize());
         CKE(cudaGetLastError());
@@ -320,13 +337,14 @@ static void run_q(const char* name, const QParams& qp0, u64* d_tab, const Ref& r
     CKE(cudaMemcpy(t.data(), d_tab, t.size() * 8, cudaMemcpyDeviceToHost));
     std::vector<u64> rows(SLOTS), cnull(SLOTS); std::vector<i64> sum(SLOTS), mn(SLOTS), mx(SLOTS);
     for (u64 i = 0; i < SLOTS; ++i) {
-        rows[i] = t[4 * i] & 0xffffffffULL; cnull[i] = t[4 * i] >> 32;
-        sum[i] = (i64)t[4 * i + 1] - (i64)VBIAS * (i64)(rows[i] - cnull[i]);
-        mn[i] = ~(i64)t[4 * i + 2]; mx[i] = (i64)t[4 * i + 3];
+        const u64 w0 = SOA ? t[i] : t[4 * i], w1 = SOA ? t[SLOTS + i] : t[4 * i + 1], w2 = SOA ? t[2 * SLOTS + i] : t[4 * i + 2], w3 = SOA ? t[3 * SLOTS + i] : t[4 * i + 3];
+        rows[i] = w0 & 0xffffffffULL; cnull[i] = w0 >> 32;
+        sum[i] = (i64)w1 - (i64)VBIAS * (i64)(rows[i] - cnull[i]);
+        mn[i] = ~(i64)w2; mx[i] = (i64)w3;
     }
     const bool ok = check(name, ref, rows, cnull, sum, mn, mx);
-    printf("{\"variant\": \"%s\", \"ways\": %d, \"check\": %d, \"prefetch\": %d, \"mnreg\": %d, \"threads\": %d, \"cache_slots\": %d, \"l0\": %d, \"smem\": %zu, \"regs\": %d, \"blocks_per_sm\": %d, \"ms\": %.4f, \"rows_per_s\": %.4g, \"gb_per_s\": %.1f, \"frac\": %.3f, \"check\": \"%s\"}\n",
-           name, WAYS, CHECK, PREF, MNREG, NT, NS, K0, smem, fa.numRegs, occ, best, n / (best * 1e-3), 14.0 * n / (best * 1e6), 14.0 * n / (best * 1e6) / 6547.8, ok ? "ok" : "MISMATCH");
+    printf("{\"variant\": \"%s\", \"soa\": %d, \"qrows\": %d, \"pair\": %d, \"ways\": %d, \"check\": %d, \"prefetch\": %d, \"mnreg\": %d, \"threads\": %d, \"cache_slots\": %d, \"l0\": %d, \"smem\": %zu, \"regs\": %d, \"blocks_per_sm\": %d, \"ms\": %.4f, \"rows_per_s\": %.4g, \"gb_per_s\": %.1f, \"frac\": %.3f, \"check\": \"%s\"}\n",
+           name, SOA, QROWS, PAIR, WAYS, CHECK, PREF, MNREG, NT, NS, K0, smem, fa.numRegs, occ, best, n / (best * 1e-3), 14.0 * n / (best * 1e6), 14.0 * n / (best * 1e6) / 6547.8, ok ? "ok" : "MISMATCH");
     fflush(stdout);
 }
 
@@ -406,15 +424,12 @@ int main(int argc, char** argv) {
     // cache slots: (budget - queues - L0) / 24 bytes, a multiple of 4
     const char* only = getenv("ONLY");
 #define RUN(name, ...) if (!only || strstr(name, only)) run_q<__VA_ARGS__>(name, qp, d_tab, ref, n, sms)
-    RUN("q", 1024, 8200, 0, 0);
-    RUN("q ways2", 1024, 8200, 0, 0, 2);
-    RUN("q ways1", 1024, 8200, 0, 0, 1);
-    RUN("q nocheck", 1024, 8200, 0, 0, 4, 0);
-    RUN("q pref", 1024, 8200, 0, 0, 4, 1, 1);
-    RUN("q pref 768", 768, 8520, 0, 0, 4, 1, 1);
-    RUN("q 768", 768, 8520, 0, 0, 4, 1, 0);
-    RUN("q nomnreg", 1024, 8200, 0, 0, 4, 1, 0, 0);
-    RUN("q ways2 pref", 1024, 8200, 0, 0, 2, 1, 1);
-    RUN("q ways1 pref", 1024, 8200, 0, 0, 1, 1, 1);
+    RUN("simple w1 aos", 1024, 8200, 0, 0, 1, 1, 0, 1, 0, 0, 0);
+    RUN("simple w1 soa", 1024, 8200, 0, 0, 1, 1, 0, 1, 0, 0, 1);
+    RUN("simple w1 aos nocheck", 1024, 8200, 0, 0, 1, 0, 0, 1, 0, 0, 0);
+    RUN("simple w1 aos 7040 slots", 1024, 7040, 0, 0, 1, 1, 0, 1, 0, 0, 0);
+    RUN("simple w1 aos 9300 slots (no queues)", 1024, 9300, 0, 0, 1, 1, 0, 1, 0, 0, 0);
+    RUN("simple w2 aos", 1024, 8200, 0, 0, 2, 1, 0, 1, 0, 0, 0);
+    RUN("simple w1 soa 7040", 1024, 7040, 0, 0, 1, 1, 0, 1, 0, 0, 1);
     return 0;
 }
