@@ -383,6 +383,20 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     if (!keys.empty()) w_rows = add_word(OP_ADD_U64, "rows", true);  // word 0: rows per group (group existence)
     auto rows_word = [&]() { if (w_rows < 0) w_rows = add_word(OP_ADD_U64, "rows", true); return w_rows; };
 
+    // does the chain also compute plain MIN and MAX of this (INT-or-absent) operand?  Then a SUM over it reads the sign mix
+    // of its ints off them (value/integer.go:266-277 only asks whether both signs occurred)
+    auto int_minmax_of = [&](const std::string& ot) {
+        const char* ns = getenv("N1GPU_NO_SIGN_FROM_MINMAX");
+        if (ns && *ns == '1') return false;
+        bool mn = false, mx = false;
+        for (auto& x : aggs) {
+            if (x->kind != EK::AGG || x->distinct || x->star || x->ops.empty() || x->ops[0]->str() != ot) continue;
+            if ((x->ops[0]->ti.mask & ~(bit(C_INT) | bit(C_MISSING) | bit(C_NULL))) != 0) continue;
+            mn = mn || x->agg == AggKind::MIN;
+            mx = mx || x->agg == AggKind::MAX;
+        }
+        return mn && mx;
+    };
     // ---- aggregate layout --------------------------------------------------------------------------------
     for (size_t a = 0; a < aggs.size(); ++a) {
         const Expr& e = *aggs[a];
@@ -441,7 +455,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                     double mx = std::max(std::fabs((double)ti.lo), std::fabs((double)ti.hi));
                     exact1 = mx * std::max(1.0, total_rows_bound) < 2.3e18;  // < 2^61: no int64 overflow possible
                 }
-                if (exact1) ap.w_isum = add_word(OP_ADD_U64, "isum:" + ot);
+                if (exact1) ap.w_isum = add_word(OP_ADD_U64, "isum:" + ot, false, ti.lo, ti.hi);
                 else { ap.w_ilo = add_word(OP_ADD_U64, "ilo:" + ot); ap.w_ihi = add_word(OP_ADD_U64, "ihi:" + ot); }
                 // how many ints were summed, and how many of them were negative; the int counter is whichever existing
                 // counter provably counts the same rows (every selected row / rows > NULL / numbers), else its own word
@@ -450,7 +464,8 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 else if ((ap.opmask & ~(M_ABSENT | bit(C_INT))) == 0) ap.w_nint = add_word(OP_ADD_U64, "cnt:" + ot, true);
                 else if ((ap.opmask & bit(C_FLOAT)) == 0) ap.w_nint = add_word(OP_ADD_U64, "cntn:" + ot, true);
                 else ap.w_nint = add_word(OP_ADD_U64, "nint:" + ot, true);
-                if (can_neg) ap.w_neg = can_nonneg ? add_word(OP_ADD_U64, "nneg:" + ot, true) : ap.w_nint;
+                if (can_neg && can_nonneg && int_minmax_of(ot)) ap.w_sgn_min = -2;  // resolved below: MIN / MAX of this operand exist
+                else if (can_neg) ap.w_neg = can_nonneg ? add_word(OP_ADD_U64, "nneg:" + ot, true) : ap.w_nint;
             }
             if (ap.opmask & bit(C_FLOAT)) {
                 ap.w_fsum = add_word(OP_ADD_F64, "fsum:" + ot);
@@ -480,6 +495,18 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         kp.aggs.push_back(ap);
     }
     if (kp.word_ops.empty()) rows_word();  // keep at least one word (only DISTINCT aggregates)
+    for (auto& ap : kp.aggs) {
+        if (ap.w_sgn_min != -2) continue;
+        ap.w_sgn_min = ap.w_sgn_max = -1;
+        const std::string ot = aggs[(size_t)(&ap - &kp.aggs[0])]->ops[0]->str();
+        for (size_t b = 0; b < kp.aggs.size(); ++b) {
+            const AggPlan& o = kp.aggs[b];
+            if (o.distinct || o.star || aggs[b]->ops.empty() || aggs[b]->ops[0]->str() != ot || o.w_mi < 0) continue;
+            if (o.kind == AggKind::MIN) ap.w_sgn_min = o.w_mi;
+            if (o.kind == AggKind::MAX) ap.w_sgn_max = o.w_mi;
+        }
+        if (ap.w_sgn_min < 0 || ap.w_sgn_max < 0) N1_THROW(N1GPU_E_INVALID, "internal: MIN / MAX words of %s not found", ot.c_str());
+    }
     const int W = (int)kp.word_ops.size();
     kp.word_complement.assign(W, false);
     std::vector<const Expr*> complement_opnd((size_t)W, nullptr);
@@ -522,7 +549,10 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             for (int w = 0; w < W; ++w) {
                 const int op = kp.word_ops[w];
                 int kind = CK_64;
-                if (op == OP_ADD_U64) kind = kp.word_count[w] ? CK_CNT : CK_WIDE;
+                // an integer sum whose addends are within +-2^31: ONE 32-bit cell, the (rare) carries go straight to the table word
+                const char* nw1 = getenv("N1GPU_NO_WIDE1");
+                const bool small_addends = kp.word_lo[w] <= kp.word_hi[w] && kp.word_lo[w] > -((i64)1 << 31) && kp.word_hi[w] < ((i64)1 << 31);
+                if (op == OP_ADD_U64) kind = kp.word_count[w] ? CK_CNT : ((small_addends && kp.dense_global && !(nw1 && *nw1 == '1')) ? CK_WIDE1 : CK_WIDE);
                 else if (op == OP_OR_U64) kind = CK_OR32;
                 else if (op != OP_ADD_F64 && kp.word_lo[w] <= kp.word_hi[w] && (u64)kp.word_hi[w] - (u64)kp.word_lo[w] <= 0xfffffffcULL) kind = CK_MM32;
                 kp.cell_kind.push_back(kind);
@@ -879,11 +909,39 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             switch (kp.cell_kind[w]) {
                 case CK_CNT: hit = strf("atomicAdd(&s_c32[%d * NQ_CS + cslot], (u32)(val_))", ci); break;
                 case CK_WIDE: hit = strf("cache_add_wide(&s_c32[%d * NQ_CS + cslot], &s_c32[%d * NQ_CS + cslot], (u64)(val_))", ci, ci + 1); break;
+                case CK_WIDE1: hit = strf("cache_add_carry(&s_c32[%d * NQ_CS + cslot], (u64)(val_), &p.acc[%dULL * cap + klo])", ci, kp.phys_of[w]); break;
                 case CK_MM32: hit = strf("cache_mm32<OP>(&s_c32[%d * NQ_CS + cslot], (u64)(val_), %lluULL)", ci, (unsigned long long)kp.word_lo[w]); break;
                 case CK_OR32: hit = strf("cache_or32(&s_c32[%d * NQ_CS + cslot], (u32)(val_))", ci); break;
                 default: hit = strf("cache_word64<OP>(&s_c64[%d * NQ_CS + cslot], (u64)(val_))", ci); break;
             }
             s += strf("#define ACCH_%d(OP, val_) %s\n", w, hit.c_str());
+        }
+        // Register groups (experiment knob N1GPU_REG_GROUPS=1, off by default).  When the single key component has
+        // payload-free classes (MISSING / NULL / a boolean), those few groups take a large share of the rows (config 5: one
+        // row in five has no string key) and every one of them is a shared-memory atomic on the same few cells.  Each
+        // thread can keep their accumulators in registers instead; warps reduce them at the end of the kernel and lane 0
+        // applies one atomic per word to the direct-indexed table (slot = packed key = class index).
+        // Measured per 1 B config-5 rows: the hand-written prototype (tools/proto5.cu, 32-bit keys and values) gains 15 %
+        // from it (5.33 -> 4.55 ms); in the generated kernel the same idea LOSES 16 % (4.93 -> 5.72 ms straight-line
+        // and masked, 5.63 predicated under the `pass` branch, 5.89 branched): ~55 extra instructions per row against the
+        // prototype's ~16, on a kernel that is already issue-limited.  Kept under test for narrower aggregate lists.
+        {
+            const char* nr = getenv("N1GPU_REG_GROUPS");
+            const PackComp& pc0 = kp.keys[0];
+            if (nr && *nr == '1' && kp.keys.size() == 1 && kp.dense_global && kp.ndistinct == 0 && kp.set_passes <= 1 && pc0.nfree >= 1 &&
+                pc0.nfree <= 2 && W * pc0.nfree <= 16)
+                kp.reg_groups = pc0.nfree;
+        }
+        for (int w = 0; w < W && kp.reg_groups; ++w) {
+            std::string upd;
+            switch (kp.cell_kind[w]) {
+                case CK_CNT: upd = strf("rg##G##_%d += (u32)(val_) & rgm##G", w); break;
+                case CK_WIDE: case CK_WIDE1: upd = strf("rg##G##_%d += (u64)(val_) & (((u64)rgm##G << 32) | rgm##G)", w); break;
+                case CK_MM32: upd = strf("if (rgh##G) reg_mm32<OP>(rg##G##_%d, (u64)(val_), %lluULL)", w, (unsigned long long)kp.word_lo[w]); break;
+                case CK_OR32: upd = strf("rg##G##_%d |= (u32)(val_) & rgm##G", w); break;
+                default: upd = strf("if (rgh##G) rg##G##_%d = word_combine(OP, rg##G##_%d, (u64)(val_))", w, w); break;
+            }
+            s += strf("#define RACC_%d(G, OP, val_) %s\n", w, upd.c_str());
         }
     }
     else s += "#define ACC(k, OP, x) if (nq_first) atomic_word<OP>(&p.acc[(u64)(k) * cap + (u64)slot], (u64)(x))\n";
@@ -946,6 +1004,16 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += "    bool cache_on = nq_first;  // per warp: switched off after 4 tiles when fewer than 1 in 4 rows hit\n";
             s += "    unsigned nlook = 0, nhit = 0; int tiles = 0;\n";
         }
+        for (int gi = 0; gi < kp.reg_groups; ++gi)
+            for (int w = 0; w < W; ++w) {
+                const int op = kp.word_ops[w];
+                switch (kp.cell_kind[w]) {
+                    case CK_CNT: case CK_OR32: s += strf("    u32 rg%d_%d = 0;\n", gi, w); break;
+                    case CK_WIDE: case CK_WIDE1: s += strf("    u64 rg%d_%d = 0;\n", gi, w); break;
+                    case CK_MM32: s += strf("    u32 rg%d_%d = %s;\n", gi, w, (op == OP_MIN_I64 || op == OP_MIN_U64) ? "0xffffffffu" : "0u"); break;
+                    default: s += strf("    u64 rg%d_%d = word_identity(%s);\n", gi, w, op_name(op)); break;
+                }
+            }
     }
     s += "    const i64 nrows = p.nrows;\n";
     s += "    const int lane = threadIdx.x & 31;\n";
@@ -977,14 +1045,40 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += "                pass = pass && w_true;\n";
         }
         s += "            cs[j] = -2; kk[j] = 0;\n";
-        s += "            if (pass) {\n";
-        s += key_code;
-        s += "                    kk[j] = klo;\n";
+        if (kp.reg_groups) {
+            // Straight-line and predicated, outside the `pass` branch: one row in five takes this path in config 5, so
+            // nearly every warp would run both sides of a branch, and accumulators updated under a branch cost a register
+            // move per update at the join (measured: branched 5.89 ms, predicated under the branch 5.63 ms per 1 B rows,
+            // against 4.94 ms without register groups).
+            s += "            {\n";
+            s += key_code;
+            for (int gi = 0; gi < kp.reg_groups; ++gi) {
+                s += strf("                    { const bool rgh%d = pass && klo == %dULL; const u32 rgm%d = rgh%d ? 0xffffffffu : 0u; (void)rgm%d;\n", gi, gi, gi, gi, gi);
+                s += strf("#define ACC(k, OP, val_) RACC_##k(%d, OP, val_)\n", gi);
+                s += agg_code;
+                s += "#undef ACC\n";
+                s += "                    }\n";
+            }
+            s += "            if (pass) {\n";
+            s += "                    kk[j] = klo;\n";
+            s += strf("                    if (klo < %dULL) cs[j] = -3;  // register group: no probe, no atomic\n", kp.reg_groups);
+            s += "                    else {\n";
+        } else {
+            s += "            if (pass) {\n";
+            s += key_code;
+            s += "                    kk[j] = klo;\n";
+        }
         s += "                    ++nlook;\n";
-        if (kp.cache_key32) s += "                    cs[j] = cache_on ? cache_claim_b4(s_ckey, NQ_CS / 4, (u32)klo * 0x9E3779B1u, (u32)klo) : -1;\n";
+        {
+            const char* cw = getenv("N1GPU_CACHE_WAYS");  // 4: buckets of four keys (one LDS.128), default: direct-mapped
+            if (kp.cache_key32 && cw && atoi(cw) == 4) s += "                    cs[j] = cache_on ? cache_claim_b4(s_ckey, NQ_CS / 4, (u32)klo * 0x9E3779B1u, (u32)klo) : -1;\n";
+            else if (kp.cache_key32) s += "                    cs[j] = cache_on ? cache_claim_1(s_ckey, NQ_CS, (u32)klo * 0x9E3779B1u, (u32)klo) : -1;\n";
+        }
+        if (kp.cache_key32) {}
         else if (kp.key_bits <= 32) s += "                    cs[j] = cache_on ? cache_claim_n(s_ckey, NQ_CS, (u32)klo * 0x9E3779B1u, klo) : -1;\n";
         else s += "                    cs[j] = cache_on ? cache_claim_n(s_ckey, NQ_CS, (u32)(mix64(klo) >> 32), klo) : -1;\n";
         s += "                    nhit += cs[j] >= 0;\n";
+        if (kp.reg_groups) s += "                    }\n            }\n";
         s += "            }\n";
         s += "        }\n";
         if (!pre_words.empty()) {
@@ -1094,6 +1188,44 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             }
         }
         s += "    }\n";
+        // register groups: warp reduction, then one atomic per word from lane 0
+        for (int gi = 0; gi < kp.reg_groups; ++gi) {
+            s += "    {\n";
+            for (int P = 0; P < PW; ++P) {
+                std::string v;
+                for (int w = 0; w < W; ++w)
+                    if (kp.phys_of[w] == P && kp.bits_of[w] != 64) {
+                        // counters (row counts of one warp fit 32 bits) and class-seen bits
+                        const char* red = kp.cell_kind[w] == CK_OR32 ? "__reduce_or_sync" : "__reduce_add_sync";
+                        v += strf("%s((u64)%s(0xffffffffu, rg%d_%d) << %d)", v.empty() ? "" : " | ", red, gi, w, kp.shift_of[w]);
+                    }
+                if (!v.empty()) s += strf("        { const u64 v = %s; if (lane == 0 && v) atomicAdd(&p.acc[%dULL * cap + %dULL], v); }\n", v.c_str(), P, gi);
+            }
+            for (int w = 0; w < W; ++w) {
+                if (kp.bits_of[w] != 64) continue;
+                const int op = kp.word_ops[w];
+                const std::string dst = strf("&p.acc[%dULL * cap + %dULL]", kp.phys_of[w], gi);
+                const bool mn = op == OP_MIN_I64 || op == OP_MIN_U64;
+                switch (kp.cell_kind[w]) {
+                    case CK_CNT:
+                        s += strf("        { const u64 v = __reduce_add_sync(0xffffffffu, rg%d_%d); if (lane == 0 && v) atomic_word<%s>(%s, v); }\n", gi, w, op_name(op), dst.c_str());
+                        break;
+                    case CK_OR32:
+                        s += strf("        { const u64 v = __reduce_or_sync(0xffffffffu, rg%d_%d); if (lane == 0 && v) atomic_word<%s>(%s, v); }\n", gi, w, op_name(op), dst.c_str());
+                        break;
+                    case CK_MM32:
+                        s += strf("        { const u32 c = %s(0xffffffffu, rg%d_%d); if (lane == 0 && c != %s) atomic_word<%s>(%s, (u64)(c - 1u) + %lluULL); }\n",
+                                  mn ? "__reduce_min_sync" : "__reduce_max_sync", gi, w, mn ? "0xffffffffu" : "0u", op_name(op), dst.c_str(),
+                                  (unsigned long long)kp.word_lo[w]);
+                        break;
+                    default:  // 64-bit sums and unranged words
+                        s += strf("        { const u64 v = warp_reduce_word<%s>(rg%d_%d); if (lane == 0 && v != word_identity(%s)) atomic_word<%s>(%s, v); }\n",
+                                  op_name(op), gi, w, op_name(op), op_name(op), dst.c_str());
+                        break;
+                }
+            }
+            s += "    }\n";
+        }
     }
     const char* nhw = getenv("N1GPU_NO_HOSTWRITE");  // experiment knob: skip the zero-copy result store
     const bool hostw = !(nhw && *nhw == '1');

@@ -11,7 +11,7 @@
 namespace n1 {
 
 enum : int { MODE_UNGROUPED = 0, MODE_DENSE = 1, MODE_HASH64 = 2, MODE_HASH128 = 3 };
-enum : int { CK_CNT = 0, CK_WIDE = 1, CK_MM32 = 2, CK_OR32 = 3, CK_64 = 4 };
+enum : int { CK_CNT = 0, CK_WIDE = 1, CK_MM32 = 2, CK_OR32 = 3, CK_64 = 4, CK_WIDE1 = 5 };
 
 // One bit-packed component: a group-key value or the value of a DISTINCT entry.
 struct PackComp {
@@ -45,6 +45,9 @@ struct AggPlan {
     // every number is added to ONE float64 word (integers that small add exactly in float64, so an all-INT group still
     // gets its exact int64 sum), w_nnum counts the numbers, and three bits of a shared OR word remember whether a float,
     // a negative int or a non-negative int was seen (the int / float class of the result: value/integer.go:266-277).
+    // the sign mix of the summed ints read off MIN / MAX of the same operand (any negative <=> min < 0, any non-negative
+    // <=> max >= 0) instead of a counter of negatives: one accumulator word (and one cache cell) less
+    int w_sgn_min = -1, w_sgn_max = -1;
     bool fcarry = false;
     int w_nnum = -1, w_flags = -1, flag_shift = 0;
     int w_seen = -1, w_mi = -1, w_mf = -1, w_ms = -1;
@@ -86,6 +89,9 @@ struct KernelPlan {
     // front-cache cell of every word: kind (CK_*) and index of its first cell among the 32-bit / 64-bit cell arrays
     std::vector<int> cell_kind, cell_idx;
     int cache_n32 = 0, cache_n64 = 0;
+    // groups whose key is one of the first `reg_groups` packed values (the payload-free classes of a single key component:
+    // MISSING / NULL keys - 20 % of config 5's rows on two groups) are aggregated in per-thread REGISTERS, outside the cache
+    int reg_groups = 0;
     std::vector<AggPlan> aggs;
     int ndistinct = 0, abits = 0, entry_bits = 0;
     bool set128 = false;

@@ -365,6 +365,11 @@ __global__ void __launch_bounds__(256) k_finalize_groups(const FinalDesc D, int 
                 else if (ap.w_ilo >= 0) itotal = (((__int128)(i64)w[ap.w_ihi]) << 32) + (__int128)w[ap.w_ilo];
                 if (ap.w_neg >= 0) n_neg = w[ap.w_neg];
                 if (ap.w_nint >= 0) n_nonneg = w[ap.w_nint] - n_neg;
+                if (ap.w_sgn_min >= 0 && ap.w_nint >= 0 && w[ap.w_nint]) {  // the sign mix from MIN / MAX of the operand
+                    const bool any_neg = (i64)w[ap.w_sgn_min] < 0, any_nonneg = (i64)w[ap.w_sgn_max] >= 0;
+                    n_neg = any_neg ? (any_nonneg ? 1 : w[ap.w_nint]) : 0;
+                    n_nonneg = w[ap.w_nint] - n_neg;
+                }
                 if (ap.w_nflt >= 0) n_flt = w[ap.w_nflt];
                 if (ap.w_fsum >= 0) fsum = __longlong_as_double((i64)w[ap.w_fsum]);
                 const HV sv = sum_value(itotal, n_nonneg, n_neg, n_flt, fsum, false);

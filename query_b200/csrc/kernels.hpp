@@ -34,6 +34,7 @@ struct FinalAgg {    // AggPlan as plain data (word indices are LOGICAL words, -
     signed char kind, distinct, fcarry, seen_class;
     short dict_col;
     signed char w_cnt, w_isum, w_ilo, w_ihi, w_nint, w_neg, w_fsum, w_nflt, w_seen, w_mi, w_mf, w_ms, w_seen_cnt, w_nnum, w_flags, flag_shift;
+    signed char w_sgn_min, w_sgn_max;
 };
 struct FinalDesc {
     int nkeys, naggs, LW, PW;

@@ -594,6 +594,7 @@ FinalDesc Query::final_desc() const {
         f.w_seen = (signed char)ap.w_seen; f.w_mi = (signed char)ap.w_mi; f.w_mf = (signed char)ap.w_mf; f.w_ms = (signed char)ap.w_ms;
         f.w_seen_cnt = (signed char)ap.w_seen_cnt; f.w_nnum = (signed char)ap.w_nnum; f.w_flags = (signed char)ap.w_flags;
         f.flag_shift = (signed char)ap.flag_shift;
+        f.w_sgn_min = (signed char)ap.w_sgn_min; f.w_sgn_max = (signed char)ap.w_sgn_max;
     }
     return D;
 }
@@ -796,6 +797,11 @@ std::unique_ptr<Result> Query::finalize() {
                 else if (ap.w_ilo >= 0) s.itotal = (((__int128)(i64)w[ap.w_ihi]) << 32) + (__int128)w[ap.w_ilo];
                 if (ap.w_neg >= 0) s.n_neg = w[ap.w_neg];
                 if (ap.w_nint >= 0) s.n_nonneg = w[ap.w_nint] - s.n_neg;
+                if (ap.w_sgn_min >= 0 && ap.w_nint >= 0 && w[ap.w_nint]) {  // the sign mix from MIN / MAX of the operand
+                    const bool any_neg = (i64)w[ap.w_sgn_min] < 0, any_nonneg = (i64)w[ap.w_sgn_max] >= 0;
+                    s.n_neg = any_neg ? (any_nonneg ? 1 : w[ap.w_nint]) : 0;
+                    s.n_nonneg = w[ap.w_nint] - s.n_neg;
+                }
                 if (ap.w_nflt >= 0) s.n_flt = w[ap.w_nflt];
                 if (ap.w_fsum >= 0) memcpy(&s.fsum, &w[ap.w_fsum], 8);
                 HValue sv = sum_value(s, false);

@@ -72,7 +72,7 @@ __global__ void k_fill4(u64* p, u64 nslots, u64 a, u64 b, u64 c, u64 d) {
 //   W2 max of ~v  (= ~min v)             (max s64)   W3 max of v                     (max s64)
 #define VBIAS 1000
 #define QCAP 64
-struct QParams { const u32* code; const u8* ktag; const i64* v; const u8* vtag; i64 nrows; u64* table; };
+struct QParams { const u32* code; const u8* ktag; const i64* v; const u8* vtag; i64 nrows; u64* table; const u32* hot; };
 
 template <int NT, int NS, int K0, int QUEUES = 1>
 struct Smem {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
     S& s = *reinterpret_cast<S*>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    for (int i = threadIdx.x; i < NS; i += NT) { s.ckey[i] = 0xffffffffu; s.c_rows[i] = 0; s.c_cnull[i] = 0; s.c_sum[i] = 0; s.c_nmin[i] = 0; s.c_max[i] = 0; }
+    for (int i = threadIdx.x; i < NS; i += NT) { s.ckey[i] = p.hot ? p.hot[i] : 0xffffffffu; s.c_rows[i] = 0; s.c_cnull[i] = 0; s.c_sum[i] = 0; s.c_nmin[i] = 0; s.c_max[i] = 0; }
     if (K0) for (int i = threadIdx.x; i < K0 * 32; i += NT) { (&s.l0key[0][0])[i] = 0xffffffffu; (&s.l0n[0][0])[i] = 0; (&s.l0sum[0][0])[i] = 0; (&s.l0nmin[0][0])[i] = 0; (&s.l0max[0][0])[i] = 0; }
     __syncthreads();
     // register groups: key classes without a payload (0 MISSING, 1 NULL)
@@ -318,6 +318,17 @@ static void run_q(const char* name, const QParams& qp0, u64* d_tab, const Ref& r
     CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_q<NT, NS, K0, L0T, WAYS, CHECK, PREF, MNREG, QROWS, PAIR, SOA>, NT, smem));
     QParams qp = qp0;
     qp.table = d_tab;
+    qp.hot = nullptr;
+    if (getenv("HOT") && WAYS == 1) {  // most-common-values statistic: every cache slot starts out owned by the hottest key that maps to it
+        std::vector<u32> hot(NS, 0xffffffffu); std::vector<u64> cnt(NS, 0);
+        for (u64 key = 2; key < SLOTS; ++key) {
+            if (!ref.rows[key]) continue;
+            const u32 b = (u32)(((u64)((u32)key * 0x9E3779B1u) * (u64)NS) >> 32);
+            if (ref.rows[key] > cnt[b]) { cnt[b] = ref.rows[key]; hot[b] = (u32)key; }
+        }
+        u32* d_hot; CKE(cudaMalloc(&d_hot, NS * 4)); CKE(cudaMemcpy(d_hot, hot.data(), NS * 4, cudaMemcpyHostToDevice));
+        qp.hot = d_hot;
+    }
     cudaEvent_t e0, e1;
     CKE(cudaEventCreate(&e0)); CKE(cudaEventCreate(&e1));
     float best = 1e30f;
@@ -425,6 +436,8 @@ int main(int argc, char** argv) {
     const char* only = getenv("ONLY");
 #define RUN(name, ...) if (!only || strstr(name, only)) run_q<__VA_ARGS__>(name, qp, d_tab, ref, n, sms)
     RUN("simple w1 aos", 1024, 8200, 0, 0, 1, 1, 0, 1, 0, 0, 0);
+    RUN("simple w1 aos nomnreg", 1024, 8200, 0, 0, 1, 1, 0, 0, 0, 0, 0);
+    RUN("simple w1 aos nomnreg 9300", 1024, 9300, 0, 0, 1, 1, 0, 0, 0, 0, 0);
     RUN("simple w1 soa", 1024, 8200, 0, 0, 1, 1, 0, 1, 0, 0, 1);
     RUN("simple w1 aos nocheck", 1024, 8200, 0, 0, 1, 0, 0, 1, 0, 0, 0);
     RUN("simple w1 aos 7040 slots", 1024, 7040, 0, 0, 1, 1, 0, 1, 0, 0, 0);
