@@ -176,13 +176,18 @@ class DistributedQuery:
         if world() > 1:
             # ranks whose kernels differ (a layout threshold crossed on one rank only) would enter different collectives and
             # merge slot-indexed words with hashed records: refuse that here, where it is an error message and not a hang
+            # (one small all-reduce of a digest: min == max on every rank <=> all digests are equal)
             import hashlib
-            mine = (query.info["mode"], tuple(query.word_ops()), hashlib.sha1(query.kernel_source.encode()).hexdigest())
-            every = [None] * world()
-            dist.all_gather_object(every, mine, group=group)
-            if any(e != every[0] for e in every):
-                raise RuntimeError("ranks compiled different kernels for one chain (declare the keyspace rows and agree the "
-                                   "statistics before seal: agree_dictionaries_and_stats): %r" % ([e[:2] for e in every],))
+            text = "%s|%r|%s" % (query.info["mode"], tuple(query.word_ops()), query.kernel_source)
+            h = int.from_bytes(hashlib.sha1(text.encode()).digest()[:7], "little")
+            dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+            d = torch.tensor([h, -h], dtype=torch.int64, device=dev)
+            dist.all_reduce(d, op=dist.ReduceOp.MAX, group=group)
+            hi, neg_lo = (int(x) for x in d.tolist())
+            if hi != -neg_lo:
+                raise RuntimeError("ranks compiled different kernels for one chain (declare the keyspace rows and agree the statistics "
+                                   "before seal: agree_dictionaries_and_stats); this rank: mode %s, %d accumulator words"
+                                   % (query.info["mode"], len(query.word_ops())))
         # A direct-indexed HBM table (megabytes, slot == key on every rank) lives in the mailbox arena: every rank folds and
         # finalises its slot range of all ranks' tables over NVLink.  A partitioned DISTINCT aggregation keeps its records
         # there: rank r aggregates and finalises partition range r.  Neither needs a collective or a replicated finalisation.

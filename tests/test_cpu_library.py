@@ -351,3 +351,39 @@ def test_parameters_and_constants_are_kernel_arguments():
     # a float where an int stood changes the class: another kernel, same statement
     f = q.Query(t, "d", where, keys, aggs, params={"lo": 10.5, "2": 500, "t": "t1"})
     assert f.kernel_source != a.kernel_source
+
+
+def test_dictionaries_of_many_ranks_merge_in_parallel_cuts():
+    """n1gpu_table_dict_merge: the column's own sorted dictionary and those of 7 other ranks (60 000-string vocabulary, each
+    rank saw ~70 % of it) merge into the bytewise sorted union - the range is cut across threads - and the column's ranks
+    are remapped; unsorted or repeated input is refused."""
+    import numpy as np
+    rng = np.random.default_rng(9)
+    vocab = sorted({("w%06d" % i).encode() for i in range(60000)} | {b"", "é".encode(), b"z" * 40, b"w000010\x00x"})
+
+    def some(frac):
+        return [s for s, keep in zip(vocab, rng.random(len(vocab)) < frac) if keep]
+
+    def raw(strings):
+        offs = np.zeros(len(strings) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in strings], out=offs[1:])
+        return np.frombuffer(b"".join(strings) or b"\0", dtype=np.uint8), offs
+
+    own = some(0.7)
+    codes = rng.integers(0, len(own), 5000).astype(np.uint32)
+    t = q.Table(["k"])
+    t.set_column("k", codes, dictionary=[s.decode() for s in own])
+    others = [some(0.7) for _ in range(6)] + [[]]
+    t.merge_dictionaries("k", [raw(o) for o in others])
+    union = sorted(set(own).union(*others))
+    assert t.dictionary("k") == union
+    pay, tags = t.peek("k")
+    assert [union[int(r)] for r in pay[:500]] == [own[int(c)] for c in codes[:500]]
+    t2 = q.Table(["k"])
+    t2.set_column("k", codes, dictionary=[s.decode() for s in own])
+    bad = list(others[0])
+    bad[30000], bad[30001] = bad[30001], bad[30000]
+    with pytest.raises(q.N1GpuError):
+        t2.merge_dictionaries("k", [raw(bad)])
+    with pytest.raises(q.N1GpuError):
+        t2.merge_dictionaries("k", [raw(others[1][:100] + others[1][99:])])
