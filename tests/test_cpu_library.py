@@ -387,3 +387,21 @@ def test_dictionaries_of_many_ranks_merge_in_parallel_cuts():
         t2.merge_dictionaries("k", [raw(bad)])
     with pytest.raises(q.N1GpuError):
         t2.merge_dictionaries("k", [raw(others[1][:100] + others[1][99:])])
+
+
+def test_plain_filter_project_is_not_substituted(tmp_path):
+    """SURVEY 8 f4 decision: a Filter -> Project scan without GROUP BY / DISTINCT returns every selected
+    row - nothing to aggregate, output as large as the input - so the plan builder leaves it to the caller's operators
+    (the shape is the reference's EXPLAIN of `SELECT name FROM game WHERE score > 5`, plan/build_select_sub.go order)."""
+    from util_n1 import write_keyspace
+    write_keyspace(str(tmp_path), "default", "game", keyspaces()["filestore/game"])
+    term = {"keyspace": "game", "namespace": "default"}
+    plan = {"#operator": "Sequence", "~children": [{"#operator": "Sequence", "~children": [
+        dict({"#operator": "PrimaryScan", "index": "#primary", "using": "default"}, **term), dict({"#operator": "Fetch"}, **term),
+        {"#operator": "Parallel", "~child": {"#operator": "Sequence", "~children": [
+            {"#operator": "Filter", "condition": "((`game`.`score`) > 5)"},
+            {"#operator": "InitialProject", "result_terms": [{"expr": "(`game`.`name`)"}]}, {"#operator": "FinalProject"}]}}]},
+        {"#operator": "Stream"}]}
+    for tail in (False, True):
+        e = _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(plan, str(tmp_path), tail=tail))
+        assert isinstance(e, q.Ineligible)
