@@ -146,6 +146,12 @@ JitKernel::~JitKernel() {
 std::atomic<unsigned long long> g_jit_compiled{0}, g_jit_reused{0};
 void jit_stats(unsigned long long* compiled, unsigned long long* reused) { *compiled = g_jit_compiled.load(); *reused = g_jit_reused.load(); }
 
+static u64 fnv1a(const char* p, size_t n) {
+    u64 h = 1469598103934665603ULL;
+    for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
 std::string jit_compile_cubin(const std::string& source, std::string* log) {
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -173,7 +179,17 @@ std::string jit_compile_cubin(const std::string& source, std::string* log) {
                 char buf[1 << 16];
                 for (size_t n; (n = fread(buf, 1, sizeof buf, f)) > 0;) cubin.append(buf, n);
                 fclose(f);
-                if (cubin.size() > 64 && memcmp(cubin.data(), "\x7f" "ELF", 4) == 0) {
+                // an entry = the ELF cubin + 16 trailing bytes ("N1CUBIN1" + FNV-1a of the cubin): a truncated or damaged file
+                // (or any other ELF that happens to sit under this name) is ignored and replaced by a fresh compile
+                bool good = cubin.size() > 64 + 16 && memcmp(cubin.data(), "\x7f" "ELF", 4) == 0 &&
+                            memcmp(cubin.data() + cubin.size() - 16, "N1CUBIN1", 8) == 0;
+                if (good) {
+                    u64 want;
+                    memcpy(&want, cubin.data() + cubin.size() - 8, 8);
+                    cubin.resize(cubin.size() - 16);
+                    good = want == fnv1a(cubin.data(), cubin.size());
+                }
+                if (good) {
                     if (log) log->clear();
                     std::lock_guard<std::mutex> lk(g_mu);
                     g_cubin_cache[source] = cubin;
@@ -211,7 +227,11 @@ std::string jit_compile_cubin(const std::string& source, std::string* log) {
         const std::string tmp = cache_file + strf(".%d.tmp", (int)getpid());
         FILE* f = fopen(tmp.c_str(), "wb");
         if (f) {
-            const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            char trailer[16];
+            memcpy(trailer, "N1CUBIN1", 8);
+            const u64 sum = fnv1a(cubin.data(), cubin.size());
+            memcpy(trailer + 8, &sum, 8);
+            const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size() && fwrite(trailer, 1, 16, f) == 16;
             if (fclose(f) != 0 || !ok || rename(tmp.c_str(), cache_file.c_str()) != 0) remove(tmp.c_str());
         }
     }

@@ -8,11 +8,14 @@
 // tag (the operator uses directory mtime + file count + newest file mtime + total bytes, see execution.cpp) and only
 // loads under the very same tag - the counterpart of the invalidation on performOp / Delete (file.go:375-471).
 //
-// Layout (little endian): "N1SEG01\n" | u64 header bytes | header JSON | per column: dictionary offsets i64[ndict+1],
-// dictionary bytes, payload (nrows x width bytes: int64 / float64 bits, or u32 ranks), class bytes (nrows).
+// Layout (little endian): "N1SEG02\n" | u64 header bytes | header JSON | per column: dictionary offsets i64[ndict+1],
+// dictionary bytes, payload (nrows x width bytes: int64 / float64 bits, or u32 ranks), class bytes (nrows) | u64 FNV-1a
+// checksum of everything after the magic.  A loader checks every size the header claims against the file size before
+// it allocates, the checksum, and that dictionaries are strictly increasing (string constants are binary-searched).
 #include <sys/stat.h>
 
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 
 #include "json.hpp"
@@ -25,10 +28,38 @@
 namespace n1 {
 
 namespace {
-const char MAGIC[8] = {'N', '1', 'S', 'E', 'G', '0', '1', '\n'};
+const char MAGIC[8] = {'N', '1', 'S', 'E', 'G', '0', '2', '\n'};
 
-void put(std::ofstream& f, const void* p, size_t n) { f.write((const char*)p, (std::streamsize)n); }
-bool get(std::ifstream& f, void* p, size_t n) { f.read((char*)p, (std::streamsize)n); return (size_t)f.gcount() == n; }
+// FNV-1a over 8-byte words (the tail bytewise): a corruption check, not a cryptographic one, at memory speed
+struct Sum {
+    u64 h = 0xcbf29ce484222325ULL;
+    unsigned char pend[8];
+    int np = 0;  // bytes waiting for a full word: the sum must not depend on how the stream is cut into calls
+    void word(const unsigned char* b) { u64 w; memcpy(&w, b, 8); h = (h ^ w) * 0x100000001b3ULL; }
+    void add(const void* p, size_t n) {
+        const unsigned char* b = (const unsigned char*)p;
+        size_t i = 0;
+        while (np && i < n) { pend[np++] = b[i++]; if (np == 8) { word(pend); np = 0; } }
+        for (; i + 8 <= n; i += 8) word(b + i);
+        for (; i < n; ++i) pend[np++] = b[i];
+    }
+    u64 done() const { u64 r = h; for (int i = 0; i < np; ++i) r = (r ^ pend[i]) * 0x100000001b3ULL; return r; }
+};
+struct Writer {
+    std::ofstream& f; Sum sum;
+    void put(const void* p, size_t n) { f.write((const char*)p, (std::streamsize)n); sum.add(p, n); }
+};
+struct Reader {
+    std::ifstream& f; Sum sum; u64 left;  // bytes of the file not yet consumed
+    bool get(void* p, size_t n) {
+        if (n > left) return false;
+        f.read((char*)p, (std::streamsize)n);
+        if ((size_t)f.gcount() != n) return false;
+        left -= n; sum.add(p, n);
+        return true;
+    }
+    bool room(u64 n) const { return n <= left; }  // asked BEFORE allocating what a header field claims
+};
 }  // namespace
 
 // Called by seal() once dictionaries are sorted and payloads hold ranks, before the host staging is dropped.
@@ -36,7 +67,7 @@ void Table::write_segment() const {
     const std::string tmp = segment_out + ".tmp";
     std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
     if (!f) N1_THROW(N1GPU_E_IO, "cannot write segment %s", tmp.c_str());
-    std::string h = "{\"version\":1,\"nrows\":" + std::to_string(nrows) + ",\"source\":";
+    std::string h = "{\"version\":2,\"nrows\":" + std::to_string(nrows) + ",\"source\":";
     json::quote(segment_source, h);
     h += ",\"columns\":[";
     for (size_t c = 0; c < cols.size(); ++c) {
@@ -50,7 +81,9 @@ void Table::write_segment() const {
     }
     h += "]}";
     const u64 hl = h.size();
-    put(f, MAGIC, 8);
+    f.write(MAGIC, 8);
+    Writer w{f, {}};
+    auto put = [&](std::ofstream&, const void* p, size_t n) { w.put(p, n); };
     put(f, &hl, 8);
     put(f, h.data(), h.size());
     for (auto& col : cols) {
@@ -66,62 +99,80 @@ void Table::write_segment() const {
         }
         put(f, col.tags.data(), (size_t)nrows);
     }
+    const u64 total = w.sum.done();
+    f.write((const char*)&total, 8);
     f.close();
     if (!f || rename(tmp.c_str(), segment_out.c_str()) != 0) { remove(tmp.c_str()); N1_THROW(N1GPU_E_IO, "cannot write segment %s", segment_out.c_str()); }
 }
 
 // Fills the (unsealed, empty) table from a segment written for the same columns under the same source tag.
 // Returns false - and leaves the table untouched - when the file is absent, foreign, truncated or stale.
+// a refused segment is not an error (the caller shreds the documents instead); N1GPU_TRACE says which check refused it
+#define REFUSE(check) do { if (getenv("N1GPU_TRACE")) fprintf(stderr, "[n1gpu segment] %s not loaded (check %d)\n", file.c_str(), check); return false; } while (0)
 bool Table::load_segment(const std::string& file, const std::string& source) {
     if (sealed || appended || nrows) N1_THROW(N1GPU_E_INVALID, "a segment loads into an empty, unsealed table");
     std::ifstream f(file, std::ios::binary);
-    if (!f) return false;
+    if (!f) REFUSE(3);
+    f.seekg(0, std::ios::end);
+    const std::streamoff fsize = f.tellg();
+    f.seekg(0, std::ios::beg);
+    if (fsize < 24) REFUSE(7);
     char magic[8];
     u64 hl = 0;
-    if (!get(f, magic, 8) || memcmp(magic, MAGIC, 8) != 0 || !get(f, &hl, 8) || hl > (64u << 20)) return false;
+    f.read(magic, 8);
+    if ((size_t)f.gcount() != 8 || memcmp(magic, MAGIC, 8) != 0) REFUSE(11);
+    Reader rd{f, {}, (u64)fsize - 8 - 8};  // the trailing checksum is not payload
+    auto get = [&](std::ifstream&, void* p, size_t n) { return rd.get(p, n); };
+    if (!get(f, &hl, 8) || hl > (64u << 20) || !rd.room(hl)) REFUSE(14);
     std::string h((size_t)hl, '\0');
-    if (!get(f, &h[0], h.size())) return false;
+    if (!get(f, &h[0], h.size())) REFUSE(16);
     json::Node root;
-    if (!json::parse(h, root) || root.kind != json::Node::OBJ) return false;
+    if (!json::parse(h, root) || root.kind != json::Node::OBJ) REFUSE(18);
     const json::Node* ver = root.get("version");
     const json::Node* nr = root.get("nrows");
     const json::Node* cs = root.get("columns");
-    if (!ver || ver->kind != json::Node::INT || ver->i != 1 || !nr || nr->kind != json::Node::INT || nr->i < 0) return false;
-    if (root.str_or("source", "\x01") != source) return false;  // the keyspace changed since the segment was written
-    if (!cs || cs->kind != json::Node::ARR || cs->arr.size() != cols.size()) return false;
+    if (!ver || ver->kind != json::Node::INT || ver->i != 2 || !nr || nr->kind != json::Node::INT || nr->i < 0) REFUSE(22);
+    if (root.str_or("source", "\x01") != source) REFUSE(23);  // the keyspace changed since the segment was written
+    if (!cs || cs->kind != json::Node::ARR || cs->arr.size() != cols.size()) REFUSE(24);
     const i64 n = nr->i;
     struct Staged { std::vector<std::string> dict; std::vector<i64> payload; std::vector<u8> tags; };
     std::vector<Staged> staged(cols.size());
     for (size_t c = 0; c < cols.size(); ++c) {
         const json::Node& cn = cs->arr[c];
-        if (cn.kind != json::Node::OBJ || cn.str_or("path", "\x01") != join_path(cols[c].path, '\x1f')) return false;
+        if (cn.kind != json::Node::OBJ || cn.str_or("path", "\x01") != join_path(cols[c].path, '\x1f')) REFUSE(30);
         const json::Node *w = cn.get("width"), *nd = cn.get("ndict"), *db = cn.get("dict_bytes");
-        if (!w || !nd || !db || w->kind != json::Node::INT || nd->kind != json::Node::INT || db->kind != json::Node::INT) return false;
-        if ((w->i != 8 && w->i != 4 && w->i != 0) || nd->i < 0 || db->i < 0) return false;
+        if (!w || !nd || !db || w->kind != json::Node::INT || nd->kind != json::Node::INT || db->kind != json::Node::INT) REFUSE(32);
+        if ((w->i != 8 && w->i != 4 && w->i != 0) || nd->i < 0 || db->i < 0) REFUSE(33);
         Staged& st = staged[c];
+        // sizes the header claims, against what the file still holds - before anything is allocated for them
+        if (!rd.room(((u64)nd->i + 1) * 8) || !rd.room((u64)db->i) || !rd.room((u64)n * (u64)(w->i + 1))) REFUSE(36);
         std::vector<i64> offs((size_t)nd->i + 1);
-        if (!get(f, offs.data(), offs.size() * 8) || offs[0] != 0 || offs.back() != db->i) return false;
+        if (!get(f, offs.data(), offs.size() * 8) || offs[0] != 0 || offs.back() != db->i) REFUSE(38);
         std::string blob((size_t)db->i, '\0');
-        if (db->i && !get(f, &blob[0], blob.size())) return false;
+        if (db->i && !get(f, &blob[0], blob.size())) REFUSE(40);
         st.dict.reserve((size_t)nd->i);
         for (i64 i = 0; i < nd->i; ++i) {
-            if (offs[(size_t)i + 1] < offs[(size_t)i] || offs[(size_t)i + 1] > db->i) return false;
+            if (offs[(size_t)i + 1] < offs[(size_t)i] || offs[(size_t)i + 1] > db->i) REFUSE(43);
             st.dict.emplace_back(blob.data() + offs[(size_t)i], (size_t)(offs[(size_t)i + 1] - offs[(size_t)i]));
+            if (i && !(st.dict[(size_t)i - 1] < st.dict[(size_t)i])) REFUSE(45);  // sorted bytewise, unique
         }
         st.payload.assign((size_t)n, 0);
-        if (w->i == 8) { if (n && !get(f, st.payload.data(), (size_t)n * 8)) return false; }
+        if (w->i == 8) { if (n && !get(f, st.payload.data(), (size_t)n * 8)) REFUSE(48); }
         else if (w->i == 4) {
             std::vector<u32> narrow((size_t)n);
-            if (n && !get(f, narrow.data(), narrow.size() * 4)) return false;
+            if (n && !get(f, narrow.data(), narrow.size() * 4)) REFUSE(51);
             for (i64 i = 0; i < n; ++i) st.payload[(size_t)i] = narrow[(size_t)i];
         }
         st.tags.resize((size_t)n);
-        if (n && !get(f, st.tags.data(), (size_t)n)) return false;
+        if (n && !get(f, st.tags.data(), (size_t)n)) REFUSE(55);
         for (i64 i = 0; i < n; ++i) {
             const u8 t = st.tags[(size_t)i];
-            if (t > C_OTHER || (t == C_STRING && (u64)st.payload[(size_t)i] >= (u64)nd->i)) return false;
+            if (t > C_OTHER || (t == C_STRING && (u64)st.payload[(size_t)i] >= (u64)nd->i)) REFUSE(58);
         }
     }
+    u64 total = 0;
+    f.read((char*)&total, 8);
+    if ((size_t)f.gcount() != 8 || rd.left != 0 || total != rd.sum.done()) REFUSE(63);
     for (size_t c = 0; c < cols.size(); ++c) {
         Column& col = cols[c];
         col.dict = std::move(staged[c].dict);
@@ -134,6 +185,8 @@ bool Table::load_segment(const std::string& file, const std::string& source) {
     appended = true;  // like appended documents: no further input may be mixed in
     return true;
 }
+
+#undef REFUSE
 
 // A packed document source: one JSON document per line (NDJSON), in primary-key order - the form a keyspace of more
 // than a few million documents takes when one file per document (file.go) stops being practical.

@@ -256,10 +256,13 @@ def test_on_disk_kernel_cache(tmp_path):
     assert len(files) == 1 and open(os.path.join(str(tmp_path), files[0]), "rb").read(4) == b"\x7fELF"
     warm = float(subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True).stdout.split()[-1])
     assert len(os.listdir(str(tmp_path))) == 1 and warm < cold / 3, (cold, warm)
-    # a damaged file is ignored and replaced
-    open(os.path.join(str(tmp_path), files[0]), "wb").write(b"garbage")
-    subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True)
-    assert open(os.path.join(str(tmp_path), files[0]), "rb").read(4) == b"\x7fELF"
+    # a damaged file is ignored and replaced - also one that is still an ELF but fails the entry's checksum
+    good = open(os.path.join(str(tmp_path), files[0]), "rb").read()
+    assert good[-16:-8] == b"N1CUBIN1"
+    for bad in (b"garbage", good[:len(good) // 2] + bytes([good[len(good) // 2] ^ 1]) + good[len(good) // 2 + 1:], good[:-16]):
+        open(os.path.join(str(tmp_path), files[0]), "wb").write(bad)
+        subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True)
+        assert open(os.path.join(str(tmp_path), files[0]), "rb").read() == good
 
 
 def test_random_expression_trees_compile_for_sm100a():

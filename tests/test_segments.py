@@ -76,6 +76,22 @@ def test_segment_round_trip_and_invalidation(tmp_path):
         open(bad, "wb").write(blob[:cut])
         t = q.Table(COLS)
         assert not t.load_segment(bad, "v1") and t.num_rows == 0
+    # a flipped payload byte fails the checksum; a header that claims more rows / dictionary bytes than the file holds is
+    # refused before anything is allocated for it; a dictionary out of order is refused (constants are binary-searched)
+    flipped = bytearray(blob)
+    flipped[len(blob) - 100] ^= 0x40
+    open(str(tmp_path / "flipped"), "wb").write(bytes(flipped))
+    assert not q.Table(COLS).load_segment(str(tmp_path / "flipped"), "v1")
+    import re
+    import struct
+    hl = struct.unpack("<Q", blob[8:16])[0]
+    header = blob[16:16 + hl].decode()
+    for pat, repl in ((r'"nrows":800', '"nrows":80000000000'), (r'"dict_bytes":(\d+)', '"dict_bytes":9\\g<1>')):
+        h2 = re.sub(pat, repl, header, count=1).encode()
+        assert h2 != header.encode()
+        open(str(tmp_path / "lying"), "wb").write(blob[:8] + struct.pack("<Q", len(h2)) + h2 + blob[16 + hl:])
+        t = q.Table(COLS)
+        assert not t.load_segment(str(tmp_path / "lying"), "v1") and t.num_rows == 0
     open(str(tmp_path / "junk"), "wb").write(b"not a segment at all" * 10)
     assert not q.Table(COLS).load_segment(str(tmp_path / "junk"), "v1")
     with pytest.raises(q.N1GpuError):
