@@ -951,7 +951,15 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         int minb = lb ? atoi(lb) : 0;
         s += strf("#define NQ_BLOCK %d\n", kp.block);
         if (minb == 0 && cached) minb = cache_blocks;  // the front cache is sized for this many resident blocks
-        if (minb > 0) s += strf("extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, %d) nq_scan(const NqParams p) {\n", minb);
+        // One 1024-thread block per SM at 64 registers per thread owns the whole register file: no other kernel - the next
+        // step's table re-arm, the flag wait and the finalisation of the step before - can start on that SM until the scan
+        // ends.  Capped at 56 registers the scan leaves 8 K registers per SM, enough for a 256-thread block of those, so a
+        // second step in flight overlaps its merge and finalisation with this scan.  (__maxnreg__ replaces
+        // __launch_bounds__: the two cannot be combined.)
+        const char* mr = getenv("N1GPU_MAXREG");
+        const int cap_regs = mr ? atoi(mr) : (cached && kp.block == 1024 ? 56 : 0);
+        if (cap_regs > 0 && cap_regs * kp.block <= 65536) s += strf("extern \"C\" __global__ void __maxnreg__(%d) nq_scan(const NqParams p) {\n", cap_regs);
+        else if (minb > 0) s += strf("extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, %d) nq_scan(const NqParams p) {\n", minb);
         else s += "extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK) nq_scan(const NqParams p) {\n";
     }
     {

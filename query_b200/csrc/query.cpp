@@ -203,6 +203,7 @@ void Query::attach_mailbox(Mailbox* mb) {
     mailbox = mb;
     peer_table = false;
     peer_seq = 0;
+    peer_steps = 0;
     // a direct-indexed table (slot == packed key on every rank) moves into the arena: peers fold it slot range by slot range
     if (mb && mb->arena_bytes && kp.mode == MODE_DENSE && kp.dense_global && kp.ndistinct == 0 && device_final_ok()) {
         peer_bytes = (size_t)cap * ops.n * 8;
@@ -240,7 +241,7 @@ void Query::launch_scan() {
     if (!kernel) N1_THROW(N1GPU_E_CUDA, "no CUDA device: libn1gpu has no CPU fallback");
     if (launched) N1_THROW(N1GPU_E_INVALID, "a scan is already outstanding on this query");
     launches_at_start = g_launches.load();
-    if (peer_table) peer_seq = ++mailbox->seq;  // the step number also selects the table buffer of this step (acc())
+    if (peer_table) { peer_seq = ++mailbox->seq; ++peer_steps; }  // flags are numbered per mailbox, table buffers alternate per query (acc())
     NqParamsHost p{};
     p.nrows = table->nrows;
     for (size_t c = 0; c < table->cols.size(); ++c) { p.col[c] = table->cols[c].d_payload.p; p.tag[c] = table->cols[c].d_tags.as<u8>(); }
@@ -699,7 +700,7 @@ std::unique_ptr<Result> Query::finalize() {
         if (peer_merge() && peer_seq) {
             // IntermediateGroup + FinalGroup fused and owner-sharded: this rank folds ITS slot range of every rank's table
             T.n = mailbox->nranks;
-            for (int r = 0; r < T.n; ++r) T.acc[r] = (const u64*)((const char*)mailbox->peers[(size_t)r] + peer_off[peer_seq & 1]);
+            for (int r = 0; r < T.n; ++r) T.acc[r] = (const u64*)((const char*)mailbox->peers[(size_t)r] + peer_off[peer_steps & 1]);
             s0 = cap * (u64)mailbox->rank / (u64)T.n;
             s1 = cap * (u64)(mailbox->rank + 1) / (u64)T.n;
             T.wait_flags = (const u64*)((const char*)mailbox->base + mailbox->flags_off) + (peer_seq % 64) * (u64)T.n;

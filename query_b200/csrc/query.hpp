@@ -157,8 +157,11 @@ struct Query {
     bool peer_table = false;
     size_t peer_off[2] = {0, 0}, peer_bytes = 0;
     u64 peer_seq = 0;            // step whose table the next finalisation folds (0: none outstanding)
+    u64 peer_steps = 0;          // steps THIS query launched: their parity selects the buffer (the mailbox-wide seq numbers the
+                                 // flags; with several queries in flight on one mailbox its parity would not alternate per query,
+                                 // and a step could overwrite the table a slower peer is still folding)
     u64* acc() const {           // the group table of the current step
-        if (peer_table) return (u64*)((char*)mailbox->base + peer_off[peer_seq & 1]);
+        if (peer_table) return (u64*)((char*)mailbox->base + peer_off[peer_steps & 1]);
         return d_acc.as<u64>();
     }
     bool peer_merge() const { return peer_table && mailbox && mailbox->nranks > 1; }

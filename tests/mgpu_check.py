@@ -83,22 +83,43 @@ def main():
             qq = q.Query(t, "d", where, keys, aggs)
             assert mode is None or qq.info["mode"] == mode, qq.info
             dq = qd.DistributedQuery(qq, mailbox=mailbox if strategy == "peer" else None)
+            def check_sharded(res, what):
+                part = gpu_rows(res, aggs)
+                gathered = [None] * world
+                dist.all_gather_object(gathered, {json.dumps(k): v for k, v in part.items()})
+                if rank == 0:
+                    got = {}
+                    for i, g in enumerate(gathered):
+                        if dq.replicated and i:
+                            continue
+                        for k, v in g.items():
+                            kk = tuple(json.loads(k))
+                            assert kk not in got, "group %r finalised by two ranks (%s, %s)" % (kk, name, what)
+                            got[kk] = v
+                    assert_same(exp, got, "%s [%s, %d ranks]" % (name, what, world))
+
             for step in range(3):  # both table buffers of the arena, and their reuse
                 res = dq.execute()
-            part = gpu_rows(res, aggs)
-            gathered = [None] * world
-            dist.all_gather_object(gathered, {json.dumps(k): v for k, v in part.items()})
-            if rank == 0:
-                got = {}
-                for i, g in enumerate(gathered):
-                    if dq.replicated and i:
-                        continue
-                    for k, v in g.items():
-                        kk = tuple(json.loads(k))
-                        assert kk not in got, "group %r finalised by two ranks (%s, %s)" % (kk, name, strategy)
-                        got[kk] = v
-                assert_same(exp, got, "%s [%s, %d ranks]" % (name, strategy, world))
+            check_sharded(res, strategy)
             checked += 1
+            if strategy == "peer" and dq.peer and not dq.peer_part:
+                # two prepared instances of the chain share the mailbox and keep two steps in flight on two streams (bench.py):
+                # flags are numbered per mailbox, table buffers alternate per instance
+                s2 = torch.cuda.Stream()
+                with torch.cuda.stream(s2):
+                    qq2 = q.Query(t, "d", where, keys, aggs)
+                    qq2.set_stream(s2.cuda_stream)
+                    dq2 = qd.DistributedQuery(qq2, stream=s2, mailbox=mailbox)
+                pair, results = [dq, dq2], []
+                pair[0].launch()
+                for i in range(1, 9):
+                    pair[i % 2].launch()
+                    results.append(pair[(i - 1) % 2].collect())
+                results.append(pair[0].collect())
+                for r_ in results[-3:]:
+                    check_sharded(r_, "peer, two steps in flight")
+                checked += 1
+                del dq2, qq2
             del dq, qq, t
     # pipelined fused steps on several streams: results stay correct and ordered
     name, where, keys, aggs = QUERIES[0]
