@@ -45,28 +45,60 @@ __device__ __forceinline__ bool slot_key(int kw, const u64* keys, const u64* acc
 // pass 1: count live slots per owner.  gk_pos/gk_bits: where the group key sits inside the stored key
 // (DISTINCT entries embed it after the aggregate id; group tables store it at bit 0).
 // kw == 4: `keys` is a DISTINCT bitmap of `cap` bits (a multiple of 64); bit e set = entry e present.
+// Warp-aggregated cursor: the lanes of a warp that bump the same counter elect a leader, which adds their number once;
+// every lane gets its own position.  With 10^6 live slots and <= 8 owners a plain atomicAdd per slot serialises on 8
+// addresses.  Called by all 32 lanes (lanes with nothing to claim pass live = false).
+__device__ __forceinline__ u64 warp_claim(unsigned long long* counters, int owner, bool live) {
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __match_any_sync(0xffffffffu, live ? owner : -1);
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (live && lane == leader) base = atomicAdd(&counters[owner], (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (u64)__popc(m & ((1u << lane) - 1u));
+}
+
 __global__ void k_count_owners(int kw, const u64* keys, const u64* acc, u64 cap, int nranks, int gk_pos, int gk_bits,
                                unsigned long long* counts) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
     if (kw == 4) {
-        for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < (cap >> 6); w += (u64)gridDim.x * blockDim.x) {
-            u64 bits = keys[w];
-            if (nranks <= 1) { if (bits) atomicAdd(&counts[0], (unsigned long long)__popcll(bits)); continue; }
-            while (bits) {
-                const u64 lo = (w << 6) | (u64)(__ffsll((long long)bits) - 1);
-                bits &= bits - 1;
-                u64 glo, ghi;
-                extract_bits(lo, 0, gk_pos, gk_bits, glo, ghi);
-                atomicAdd(&counts[owner_of(glo, ghi, nranks)], 1ULL);
+        const u64 nw = cap >> 6;
+        for (u64 w0 = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < nw; w0 += stride) {  // warp-uniform trip count
+            const u64 w = w0 + lane;
+            u64 bits = w < nw ? keys[w] : 0;
+            if (nranks <= 1) {
+                const unsigned long long n = (unsigned long long)__popcll(bits);
+                const unsigned long long tot = warp_reduce_word<OP_ADD_U64>(n);
+                if (lane == 0 && tot) atomicAdd(&counts[0], tot);
+                continue;
+            }
+            while (__any_sync(0xffffffffu, bits != 0)) {
+                const bool live = bits != 0;
+                int owner = 0;
+                if (live) {
+                    const u64 lo = (w << 6) | (u64)(__ffsll((long long)bits) - 1);
+                    bits &= bits - 1;
+                    u64 glo, ghi;
+                    extract_bits(lo, 0, gk_pos, gk_bits, glo, ghi);
+                    owner = owner_of(glo, ghi, nranks);
+                }
+                warp_claim(counts, owner, live);
             }
         }
         return;
     }
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
-        u64 lo, hi;
-        if (!slot_key(kw, keys, acc, i, lo, hi)) continue;
-        u64 glo, ghi;
-        extract_bits(lo, hi, gk_pos, gk_bits, glo, ghi);
-        atomicAdd(&counts[owner_of(glo, ghi, nranks)], 1ULL);
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < cap; i0 += stride) {
+        const u64 i = i0 + lane;
+        u64 lo = 0, hi = 0;
+        const bool live = i < cap && slot_key(kw, keys, acc, i, lo, hi);
+        int owner = 0;
+        if (live) {
+            u64 glo, ghi;
+            extract_bits(lo, hi, gk_pos, gk_bits, glo, ghi);
+            owner = owner_of(glo, ghi, nranks);
+        }
+        warp_claim(counts, owner, live);
     }
 }
 
@@ -74,28 +106,42 @@ __global__ void k_count_owners(int kw, const u64* keys, const u64* acc, u64 cap,
 __global__ void k_export_records(int kw, const u64* keys, const u64* acc, u64 cap, int W, int nranks, int gk_pos, int gk_bits,
                                  unsigned long long* cursor, u64* out, u64 out_cap) {
     const int rw = 2 + W;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
     if (kw == 4) {
-        for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < (cap >> 6); w += (u64)gridDim.x * blockDim.x) {
-            u64 bits = keys[w];
-            while (bits) {
-                const u64 lo = (w << 6) | (u64)(__ffsll((long long)bits) - 1);
-                bits &= bits - 1;
-                u64 glo, ghi;
-                extract_bits(lo, 0, gk_pos, gk_bits, glo, ghi);
-                const u64 at = atomicAdd(&cursor[owner_of(glo, ghi, nranks)], 1ULL);
-                if (at >= out_cap) continue;
-                out[at * rw] = lo; out[at * rw + 1] = 0;
+        const u64 nw = cap >> 6;
+        for (u64 w0 = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < nw; w0 += stride) {
+            const u64 w = w0 + lane;
+            u64 bits = w < nw ? keys[w] : 0;
+            while (__any_sync(0xffffffffu, bits != 0)) {
+                const bool live = bits != 0;
+                int owner = 0;
+                u64 lo = 0;
+                if (live) {
+                    lo = (w << 6) | (u64)(__ffsll((long long)bits) - 1);
+                    bits &= bits - 1;
+                    u64 glo, ghi;
+                    extract_bits(lo, 0, gk_pos, gk_bits, glo, ghi);
+                    owner = owner_of(glo, ghi, nranks);
+                }
+                const u64 at = warp_claim(cursor, owner, live);
+                if (live && at < out_cap) { out[at * rw] = lo; out[at * rw + 1] = 0; }
             }
         }
         return;
     }
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
-        u64 lo, hi;
-        if (!slot_key(kw, keys, acc, i, lo, hi)) continue;
-        u64 glo, ghi;
-        extract_bits(lo, hi, gk_pos, gk_bits, glo, ghi);
-        u64 at = atomicAdd(&cursor[owner_of(glo, ghi, nranks)], 1ULL);
-        if (at >= out_cap) continue;
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < cap; i0 += stride) {
+        const u64 i = i0 + lane;
+        u64 lo = 0, hi = 0;
+        const bool live = i < cap && slot_key(kw, keys, acc, i, lo, hi);
+        int owner = 0;
+        if (live) {
+            u64 glo, ghi;
+            extract_bits(lo, hi, gk_pos, gk_bits, glo, ghi);
+            owner = owner_of(glo, ghi, nranks);
+        }
+        const u64 at = warp_claim(cursor, owner, live);
+        if (!live || at >= out_cap) continue;
         u64* r = out + at * rw;
         r[0] = lo; r[1] = hi;
         for (int w = 0; w < W; ++w) r[2 + w] = acc[(u64)w * cap + i];
