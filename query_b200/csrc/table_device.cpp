@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <map>
+#include <functional>
 #include <thread>
 
 #include "shred.hpp"
@@ -313,43 +314,89 @@ void Table::append_text_device(const char* buf, const i64* offsets, i64 ndocs, i
             }
             phase("  dictionary insert");
             // sort the distinct strings bytewise on the host: rank = N1QL collation order (value/string.go:116-126)
-            struct Ent { const char* p; u32 len; u64 slot; };
-            std::vector<Ent> ents(oslots.size());
-            for (size_t i = 0; i < oslots.size(); ++i) {
-                const u64 ref = orefs[i];
-                const u64 off = (ref & ~0x8000000000000000ULL) >> 24;
-                ents[i].p = (ref >> 63) ? extra.data() + off : buf + base_off + off;
-                ents[i].len = (u32)(ref & 0xffffff);
-                ents[i].slot = oslots[i];
-            }
-            auto less = [](const Ent& a, const Ent& b) {
-                const int c = memcmp(a.p, b.p, std::min(a.len, b.len));
+            // The distinct strings lie scattered over the raw text (hundreds of megabytes): every compare of a sort over
+            // them would be two cache misses.  They are gathered once, on all cores, into one compact blob together with
+            // their first 8 bytes as a big-endian integer; the sort compares those integers and touches the (compact)
+            // bytes only for ties.  10^5 strings of config 5: 6.8 ms -> about 1.5 ms.
+            struct Ent { u64 prefix; u32 at; u32 len; u64 slot; };
+            const size_t nent = oslots.size();
+            std::vector<Ent> ents(nent);
+            std::vector<u32> starts(nent + 1, 0);
+            for (size_t i = 0; i < nent; ++i) starts[i + 1] = starts[i] + (u32)(orefs[i] & 0xffffff);
+            std::string compact((size_t)starts[nent], '\0');
+            const size_t nthr = nent < 20000 ? 1 : std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+            auto parallel = [&](size_t parts, const std::function<void(size_t)>& fn) {
+                if (parts <= 1) { fn(0); return; }
+                std::vector<std::thread> pool;
+                for (size_t r = 1; r < parts; ++r) pool.emplace_back(fn, r);
+                fn(0);
+                for (auto& th : pool) th.join();
+            };
+            parallel(nthr, [&](size_t r) {
+                for (size_t i = nent * r / nthr; i < nent * (r + 1) / nthr; ++i) {
+                    const u64 ref = orefs[i];
+                    const u64 off = (ref & ~0x8000000000000000ULL) >> 24;
+                    const char* src = (ref >> 63) ? extra.data() + off : buf + base_off + off;
+                    const u32 len = (u32)(ref & 0xffffff);
+                    memcpy(&compact[starts[i]], src, len);
+                    u64 pre = 0;
+                    for (u32 k = 0; k < 8; ++k) pre = (pre << 8) | (k < len ? (unsigned char)src[k] : 0u);
+                    ents[i] = Ent{pre, starts[i], len, oslots[i]};
+                }
+            });
+            phase("    strings gathered");
+            const char* cb = compact.data();
+            auto less = [cb](const Ent& a, const Ent& b) {
+                if (a.prefix != b.prefix) return a.prefix < b.prefix;  // big-endian image of the first 8 bytes: bytewise order
+                if (a.len <= 8 || b.len <= 8) return a.len < b.len;    // equal padded prefixes: the shorter one is a prefix of the other
+                const int c = memcmp(cb + a.at + 8, cb + b.at + 8, std::min(a.len, b.len) - 8);
                 return c != 0 ? c < 0 : a.len < b.len;
             };
-            {   // sorted runs on all cores, then pairwise merges (10^5 strings: ~35 ms on one core)
-                const size_t n = ents.size();
-                size_t nthr = n < 20000 ? 1 : std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
-                size_t runs = 1;
-                while (runs * 2 <= nthr) runs *= 2;
-                auto bound = [&](size_t r) { return n * r / runs; };
-                std::vector<std::thread> pool;
-                for (size_t r = 1; r < runs; ++r) pool.emplace_back([&, r] { std::sort(ents.begin() + (i64)bound(r), ents.begin() + (i64)bound(r + 1), less); });
-                std::sort(ents.begin(), ents.begin() + (i64)bound(1), less);
-                for (auto& th : pool) th.join();
-                for (size_t width = 1; width < runs; width *= 2) {
-                    pool.clear();
-                    for (size_t r = 0; r + width < runs; r += 2 * width)
-                        pool.emplace_back([&, r, width] {
-                            std::inplace_merge(ents.begin() + (i64)bound(r), ents.begin() + (i64)bound(r + width), ents.begin() + (i64)bound(std::min(runs, r + 2 * width)), less);
-                        });
-                    for (auto& th : pool) th.join();
-                }
+            if (nthr > 1) {
+                // sample sort: buckets by splitters drawn from the prefixes (equal prefixes share a bucket), every bucket sorted on
+                // its own core - no merge levels.  Strings that all share their first 8 bytes degenerate to one bucket.
+                const size_t B = nthr, S = 64 * B;
+                std::vector<u64> sample(S);
+                for (size_t i = 0; i < S; ++i) sample[i] = ents[nent * i / S].prefix;
+                std::sort(sample.begin(), sample.end());
+                std::vector<u64> split(B - 1);
+                for (size_t k = 0; k + 1 < B; ++k) split[k] = sample[(k + 1) * S / B];
+                std::vector<u32> bucket(nent);
+                std::vector<std::vector<size_t>> cnt(B, std::vector<size_t>(B, 0));  // [thread][bucket]
+                parallel(B, [&](size_t r) {
+                    for (size_t i = nent * r / B; i < nent * (r + 1) / B; ++i) {
+                        const u32 k = (u32)(std::upper_bound(split.begin(), split.end(), ents[i].prefix) - split.begin());
+                        bucket[i] = k;
+                        ++cnt[r][k];
+                    }
+                });
+                // bucket k = [count[k], count[k + 1]); inside it thread r's entries follow those of the threads before it
+                std::vector<size_t> count(B + 1, 0);
+                for (size_t k = 0; k < B; ++k) { size_t tot = 0; for (size_t r = 0; r < B; ++r) tot += cnt[r][k]; count[k + 1] = count[k] + tot; }
+                phase("    buckets counted");
+                std::vector<Ent> sorted(nent);
+                parallel(B, [&](size_t r) {
+                    std::vector<size_t> cursor(B);
+                    for (size_t k = 0; k < B; ++k) { size_t at = count[k]; for (size_t q = 0; q < r; ++q) at += cnt[q][k]; cursor[k] = at; }
+                    for (size_t i = nent * r / B; i < nent * (r + 1) / B; ++i) sorted[cursor[bucket[i]]++] = ents[i];
+                });
+                phase("    buckets filled");
+                parallel(B, [&](size_t k) { std::sort(sorted.begin() + (i64)count[k], sorted.begin() + (i64)count[k + 1], less); });
+                ents.swap(sorted);
+            } else {
+                std::sort(ents.begin(), ents.end(), less);
             }
             phase("  dictionary sort");
             // rank of every occupied slot: the (few) slots travel in rank order and a kernel scatters their ranks
             std::vector<u64> slot_of_rank(ents.size());
-            col.dict.reserve(ents.size());
-            for (size_t r = 0; r < ents.size(); ++r) { slot_of_rank[r] = ents[r].slot; col.dict.emplace_back(ents[r].p, ents[r].len); }
+            col.dict.resize(ents.size());
+            parallel(nthr, [&](size_t t) {
+                for (size_t r = ents.size() * t / nthr; r < ents.size() * (t + 1) / nthr; ++r) {
+                    slot_of_rank[r] = ents[r].slot;
+                    col.dict[r].assign(cb + ents[r].at, ents[r].len);
+                }
+            });
+            phase("    dictionary strings");
             d_rank.ensure((size_t)cap * 4);
             d_oslots.ensure(std::max<size_t>(slot_of_rank.size() * 8, 64));
             if (!slot_of_rank.empty()) CK(cudaMemcpyAsync(d_oslots.p, slot_of_rank.data(), slot_of_rank.size() * 8, cudaMemcpyHostToDevice, s));
