@@ -72,7 +72,7 @@ __global__ void k_fill4(u64* p, u64 nslots, u64 a, u64 b, u64 c, u64 d) {
 //   W2 max of ~v  (= ~min v)             (max s64)   W3 max of v                     (max s64)
 #define VBIAS 1000
 #define QCAP 64
-struct QParams { const u32* code; const u8* ktag; const i64* v; const u8* vtag; i64 nrows; u64* table; const u32* hot; };
+struct QParams { const u32* code; const u8* ktag; const i64* v; const u8* vtag; i64 nrows; u64* table; const u32* hot; int match; };
 
 template <int NT, int NS, int K0, int QUEUES = 1>
 struct Smem {
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
     u32* const qk = s.qkey[(QROWS || PAIR) ? w : 0]; u32* const qv = s.qval[(QROWS || PAIR) ? w : 0];
     u32* const mk = s.mkey[(QROWS || PAIR) ? w : 0]; u32* const mv = s.mval[(QROWS || PAIR) ? w : 0];
     u64* const table = p.table;
+    const bool g_match = p.match != 0;
     // word w of group `key`: one 32-byte sector per group (slot-major), or word planes (SOA: the round-1 layout)
     auto word = [&](u32 key, int w) -> u64* { return SOA ? table + (u64)w * SLOTS + key : table + (u64)key * 4 + w; };
 
@@ -149,6 +150,43 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
     };
     auto process = [&](bool active, u32 key, u32 val) {
         int slot = -2;
+        if (g_match) {
+            // warp-cooperative pre-aggregation: lanes holding the same key combine their row in the lowest of them
+            // (__match_any_sync), which alone probes the cache and updates it with the combined count / sum / min / max
+            const bool isnull0 = val >> 31;
+            const u32 vb0 = val & 0xfffffu;
+            const unsigned m = __match_any_sync(0xffffffffu, active ? key : 0xffffff00u + (u32)lane);
+            const int leader = __ffs(m) - 1;
+            u32 a_cs = active ? (isnull0 ? (1u << 26) : vb0) : 0u;              // sum | null count << 26: both additive
+            u32 a_cnt = active ? 1u : 0u;
+            u32 a_mx = (active && !isnull0) ? vb0 + 1u : 0u, a_nm = (active && !isnull0) ? 0x100000u - vb0 : 0u;
+            const unsigned size_max = __reduce_max_sync(0xffffffffu, (unsigned)__popc(m));
+            unsigned rest = m & ~(1u << leader);
+            const u32 my_cs = a_cs, my_mx = a_mx, my_nm = a_nm;
+            for (unsigned r = 1; r < size_max; ++r) {
+                const int src = rest ? __ffs(rest) - 1 : lane;
+                rest &= rest - 1;
+                const u32 o_cs = __shfl_sync(0xffffffffu, my_cs, src), o_mx = __shfl_sync(0xffffffffu, my_mx, src), o_nm = __shfl_sync(0xffffffffu, my_nm, src);
+                if (src != lane) { a_cs += o_cs; a_cnt += 1u; a_mx = max(a_mx, o_mx); a_nm = max(a_nm, o_nm); }
+            }
+            const bool lead = active && lane == leader;
+            if (lead) slot = cache_claim_w<WAYS>(s.ckey, NS, key * 0x9E3779B1u, key);
+            const u32 cn = a_cs >> 26, sm = a_cs & 0x3ffffffu;
+            if (slot >= 0) {
+                atomicAdd(&s.c_rows[slot], a_cnt);
+                if (cn) atomicAdd(&s.c_cnull[slot], cn);
+                if (a_cnt > cn) {
+                    const u32 so = atomicAdd(&s.c_sum[slot], sm);
+                    if ((u32)(so + sm) < sm) red_add_u64(word(key, 1), 1ULL << 32);
+                    if (!CHECK || a_mx > *(volatile u32*)&s.c_max[slot]) atomicMax(&s.c_max[slot], a_mx);
+                    if (!CHECK || a_nm > *(volatile u32*)&s.c_nmin[slot]) atomicMax(&s.c_nmin[slot], a_nm);
+                }
+            } else if (slot == -1) {
+                red_add_u64(word(key, 0), (u64)a_cnt | ((u64)cn << 32));
+                if (a_cnt > cn) { red_add_u64(word(key, 1), (u64)sm); red_max_s64(word(key, 2), ~((i64)(0x100000u - a_nm) - VBIAS)); red_max_s64(word(key, 3), (i64)(a_mx - 1u) - VBIAS); }
+            }
+            return;
+        }
         if (active) slot = cache_claim_w<WAYS>(s.ckey, NS, key * 0x9E3779B1u, key);
         if (slot >= 0) {
             const bool isnull = val >> 31;
@@ -319,6 +357,7 @@ static void run_q(const char* name, const QParams& qp0, u64* d_tab, const Ref& r
     QParams qp = qp0;
     qp.table = d_tab;
     qp.hot = nullptr;
+    qp.match = getenv("MATCH") ? 1 : 0;
     if (getenv("HOT") && WAYS == 1) {  // most-common-values statistic: every cache slot starts out owned by the hottest key that maps to it
         std::vector<u32> hot(NS, 0xffffffffu); std::vector<u64> cnt(NS, 0);
         for (u64 key = 2; key < SLOTS; ++key) {
