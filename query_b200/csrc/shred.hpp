@@ -21,7 +21,8 @@ void launch_dict_collect(const u64* keys, u64 cap, unsigned* count, u64* out_slo
 // (first[nseg] = number of documents), the offsets themselves; the caller appends offs[ndocs] = size
 i64 ndjson_segments(i64 size);
 void launch_ndjson_count(const unsigned char* text, i64 size, unsigned* counts, cudaStream_t s);
-void launch_ndjson_scan(const unsigned* counts, i64 nseg, i64* first, cudaStream_t s);
+i64 ndjson_scan_tiles(i64 nseg);  // launch_ndjson_scan needs (tiles + 1) x 8 bytes of device scratch
+void launch_ndjson_scan(const unsigned* counts, i64 nseg, i64* first, i64* tile_scratch, cudaStream_t s);
 void launch_ndjson_write(const unsigned char* text, i64 size, const i64* first, i64* offs, cudaStream_t s);
 void launch_gather_offsets(const i64* offs, const i64* rows, i64 n, i64* out, cudaStream_t s);
 void launch_rank_remap(const u8* tags, i64* pay8, u32* pay4, i64 nrows, const u32* remap, u32 n, cudaStream_t s);

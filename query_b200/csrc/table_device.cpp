@@ -109,7 +109,9 @@ void Table::append_text_device(const char* buf, const i64* offsets, i64 ndocs, i
         d_counts.alloc((size_t)(nseg + 1) * 4);
         d_first.alloc((size_t)(nseg + 1) * 8);
         launch_ndjson_count((const unsigned char*)d_buf.p, nbytes, d_counts.as<unsigned>(), s);
-        launch_ndjson_scan(d_counts.as<unsigned>(), nseg, d_first.as<i64>(), s);
+        DevBuf d_tiles;
+        d_tiles.alloc((size_t)(ndjson_scan_tiles(nseg) + 1) * 8);
+        launch_ndjson_scan(d_counts.as<unsigned>(), nseg, d_first.as<i64>(), d_tiles.as<i64>(), s);
         i64 total = 0;
         CK(cudaMemcpyAsync(&total, d_first.as<i64>() + nseg, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
