@@ -153,6 +153,68 @@ def same_value(a, b, tol=1e-12):
     return type(a) is type(b) and a == b
 
 
+CONFIG1 = [  # BASELINE.json configs[0]: the reference's own CPU-runnable case, data/sampledb/dimestore
+    ("product", "SELECT color, COUNT(*), SUM(unitPrice), AVG(unitPrice), MIN(unitPrice), MAX(unitPrice) FROM product WHERE unitPrice > 10 GROUP BY color",
+     "(10 < (`product`.`unitPrice`))", ["(`product`.`color`)"],
+     ["count(*)", "sum((`product`.`unitPrice`))", "avg((`product`.`unitPrice`))", "min((`product`.`unitPrice`))", "max((`product`.`unitPrice`))"]),
+    ("review", "SELECT rating, COUNT(*) FROM review WHERE rating > 1 GROUP BY rating", "(1 < (`review`.`rating`))", ["(`review`.`rating`)"], ["count(*)"]),
+]
+
+
+def config1_entry(q, cref, np):
+    """Config 1 through the reference-facing operator: the two sampledb statements over the file-datastore layout (one file
+    per document; the documents are the fixture tests/golden/keyspaces.json.gz extracted from the reference's data/sampledb),
+    timed cold (files read + shredded + kernel compiled or fetched) and warm (resident table), checked against oracle_ref.c.
+    A latency figure: 900 / 10 000 documents do not fill a GPU."""
+    import gzip
+    import shutil
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "keyspaces.json.gz"), "rb") as f:
+        ks = json.loads(f.read().decode("utf-8"))
+    root = tempfile.mkdtemp(prefix="n1gpu_config1_")
+    out = {}
+    try:
+        for name, sql, where, keys, aggs in CONFIG1:
+            docs = ks["sampledb/dimestore/" + name]
+            d = os.path.join(root, "dimestore", name)
+            os.makedirs(d)
+            for key, text in docs:
+                with open(os.path.join(d, key + ".json"), "w", encoding="utf-8") as f:
+                    f.write(text)
+            term = {"keyspace": name, "namespace": "dimestore"}
+            aggs_sorted = sorted(set(aggs))
+            plan = {"#operator": "Sequence", "~children": [{"#operator": "Sequence", "~children": [
+                dict({"#operator": "PrimaryScan", "index": "#primary", "using": "default"}, **term), dict({"#operator": "Fetch"}, **term),
+                {"#operator": "Parallel", "~child": {"#operator": "Sequence", "~children": [
+                    {"#operator": "Filter", "condition": where}, {"#operator": "InitialGroup", "aggregates": aggs_sorted, "group_keys": keys}]}},
+                {"#operator": "IntermediateGroup", "aggregates": aggs_sorted, "group_keys": keys},
+                {"#operator": "FinalGroup", "aggregates": aggs_sorted, "group_keys": keys},
+                {"#operator": "Parallel", "~child": {"#operator": "Sequence", "~children": [
+                    {"#operator": "InitialProject", "result_terms": [{"expr": a} for a in aggs_sorted]}, {"#operator": "FinalProject"}]}}]},
+                {"#operator": "Stream"}]}
+
+            def once():
+                t0 = time.perf_counter()
+                r = q.Operator(plan, root).run_once()
+                r.num_groups
+                return r, (time.perf_counter() - t0) * 1e3
+
+            r, cold_ms = once()
+            warm = sorted(once()[1] for _ in range(20))
+            enc = [t.encode("utf-8") for _k, t in sorted(docs)]
+            offs = np.zeros(len(enc) + 1, dtype=np.int64)
+            np.cumsum([len(e) for e in enc], out=offs[1:])
+            groups, cpu_s, _p = cref.run(np.frombuffer(b"".join(enc), dtype=np.uint8).copy(), offs, name, where, keys, aggs_sorted, threads=1)
+            from oracle import n1ql_oracle as O
+            exp = {tuple("\0MISSING" if k is O.MISSING else k for k in kk): a for kk, a in groups}
+            got = {tuple("\0MISSING" if k is q.MISSING else k for k in kk): a for kk, a in r.rows()}
+            ok = exp.keys() == got.keys() and all(all(same_value(x, y) for x, y in zip(exp[k], got[k])) for k in exp)
+            out[name] = {"query": sql, "documents": len(docs), "groups": len(got), "cold_ms": cold_ms, "warm_ms_median": warm[len(warm) // 2],
+                         "cpu_port_ms_one_thread": cpu_s * 1e3, "check": "every group equals oracle_ref.c" if ok else "MISMATCH"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -324,7 +386,7 @@ def run_ours(args):
                            "roofline_frac": bytes_per_row * w5.n / mean_scan_ns / peak, "groups": groups5, "check": check5}}
     del dq5, q5, t5, res, dq5s, q5s
     torch.cuda.empty_cache()
-    for name in [c for c in args.configs.split(",") if c]:
+    for name in [c for c in args.configs.split(",") if c and c != "config1"]:  # (config 1 runs through the operator, below)
         t0 = time.perf_counter()
         w = wl.CONFIGS[name](dev=dev, scale=args.configs_scale)
         t, qq, dq = make(w)
@@ -453,6 +515,8 @@ def run_ours(args):
             cpu = {"value": sample / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d config5-shaped JSON documents, oracle/oracle_ref.c (reference-shaped C restatement of the Go chain), %d threads" % (sample, cores)}
 
+    if rank == 0 and "config1" in args.configs.split(","):
+        configs["config1"] = config1_entry(q, cref, np)
     # ---- the same end to end through the reference-facing operator (plan JSON + datastore root), one GPU ----------------------------
     e2e_op = None
     if world == 1 and args.e2e_operator:
@@ -623,7 +687,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS, help="documents of the config-5 keyspace (all ranks together)")
-    ap.add_argument("--configs", default="config2,config3,config4", help="other BASELINE configs reported in the `configs` block")
+    ap.add_argument("--configs", default="config1,config2,config3,config4", help="other BASELINE configs reported in the `configs` block")
     ap.add_argument("--configs-scale", type=float, default=1.0)
     ap.add_argument("--configs-steps", type=int, default=5)
     ap.add_argument("--inflight", type=int, default=3, help="steps of the headline config in flight (prepared instances of the chain on their own streams)")
