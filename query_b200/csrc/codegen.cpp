@@ -527,7 +527,30 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         // whole table is <= 48 words, every thread keeps its own copy in shared memory (bank = thread: conflict-free
         // plain read-modify-write, no atomics) and the copies are folded once per block.
         const char* np = getenv("N1GPU_NO_PRIV");
-        if (kp.dense_slots * W <= 48 && !(np && *np == '1')) { kp.dense_priv = true; kp.dyn_smem = (int)(kp.dense_slots * W * 256 * 8); }
+        if (kp.dense_slots * W <= 48 && !(np && *np == '1')) {
+            kp.dense_priv = true;
+            // Block shape: cells x 8 bytes per thread decide how many threads an SM holds (config 3: 42 cells = 336 bytes ->
+            // 2 blocks x 256 threads = 16 warps, a quarter of the SM: ncu shows the scan latency-bound, issue 53 %, DRAM 48 %).
+            // When fewer than four 256-thread blocks fit, the block size that packs the most warps into 227 KiB is taken
+            // instead (config 3: 1 x 640 threads = 20 warps; 718 -> 645 us per 60 M rows).  The private cells stay conflict-free
+            // for any multiple of 32.
+            const i64 cells = kp.dense_slots * W;
+            const char* pb = getenv("N1GPU_PRIV_BLOCK");
+            auto blocks_of = [&](int block) {  // private cells + the per-warp fold buffer + the reserved KiB of every block
+                return (int)std::min<i64>((i64)(227 * 1024) / (cells * 8 * block + cells * 8 * (block / 32) + 1536), 2048 / block);
+            };
+            int best_block = 256;
+            if (pb && atoi(pb) >= 32 && atoi(pb) <= 1024 && atoi(pb) % 32 == 0) best_block = atoi(pb);
+            else if (blocks_of(256) < 4) {
+                int best_warps = blocks_of(256) * 8;
+                for (int block = 128; block <= 1024; block += 32) {
+                    const int warps = blocks_of(block) * (block / 32);
+                    if (warps >= best_warps && warps > 0) { best_warps = warps; best_block = block; }  // ties: the larger block (fewer folds; measured 645 vs 665 us)
+                }
+            }
+            kp.block = best_block;
+            kp.dyn_smem = (int)(cells * kp.block * 8);
+        }
     }
     else if (kp.key_bits <= 63) {
         // A packed key of few bits indexes the HBM table directly: no key array, no hash probe, no insert race, the
@@ -879,7 +902,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     s += "};\n";
     if (kp.mode == MODE_UNGROUPED) s += "#define ACC(k, OP, x) a##k = word_combine(OP, a##k, (u64)(x))\n";
     else if (smem_dense && kp.dense_priv)
-        s += "#define ACC(k, OP, val_) { u64* c_ = &s_priv[(((k) * NQ_G + slot) << 8) + threadIdx.x]; *c_ = word_combine(OP, *c_, (u64)(val_)); }\n";
+        s += "#define ACC(k, OP, val_) { u64* c_ = &s_priv[((k) * NQ_G + slot) * NQ_BLOCK + threadIdx.x]; *c_ = word_combine(OP, *c_, (u64)(val_)); }\n";
     else if (smem_dense) s += "#define ACC(k, OP, x) atomic_word<OP>(&s_tab[(k) * NQ_G + slot], (u64)(x))\n";
     else if (cached) {
         s += strf("#define NQ_CS %d\n", kp.cache_slots);
@@ -975,9 +998,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
     if (kp.mode == MODE_UNGROUPED) {
         for (int w = 0; w < W; ++w) s += strf("    u64 a%d = word_identity(%s);\n", w, op_name(kp.word_ops[w]));
     } else if (smem_dense && kp.dense_priv) {
-        s += "    extern __shared__ u64 s_priv[];  // [NQ_W * NQ_G cells][256 threads]: cell c of thread t at (c << 8) + t\n";
+        s += "    extern __shared__ u64 s_priv[];  // [NQ_W * NQ_G cells][NQ_BLOCK threads]: cell c of thread t at c * NQ_BLOCK + t\n";
         s += "#pragma unroll\n";
-        s += "    for (int c = 0; c < NQ_W * NQ_G; ++c) s_priv[(c << 8) + threadIdx.x] = word_identity(nq_ops[c / NQ_G]);\n";
+        s += "    for (int c = 0; c < NQ_W * NQ_G; ++c) s_priv[c * NQ_BLOCK + threadIdx.x] = word_identity(nq_ops[c / NQ_G]);\n";
     } else if (smem_dense) {
         s += "    __shared__ u64 s_tab[NQ_W * NQ_G];\n";
         s += "    for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) s_tab[i] = word_identity(nq_ops[i / NQ_G]);\n";
@@ -1284,18 +1307,18 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "    }\n";
     } else if (smem_dense) {
         if (kp.dense_priv) {
-            // fold the 256 private copies of every cell: 8 warp-shuffle reductions per cell, then thread c folds cell c's
-            // 8 warp values in order and applies one global atomic per (block, cell)
-            s += "    __shared__ u64 s_wpart[NQ_W * NQ_G][8];\n";
+            // fold the private copies of every cell: one warp-shuffle reduction per warp and cell, then thread c folds cell c's
+            // warp values in order and applies one global atomic per (block, cell)
+            s += "    __shared__ u64 s_wpart[NQ_W * NQ_G][NQ_BLOCK / 32];\n";
             s += "    for (int c = 0; c < NQ_W * NQ_G; ++c) {\n";
-            s += "        const u64 r = warp_reduce_dyn(nq_ops[c / NQ_G], s_priv[(c << 8) + threadIdx.x]);\n";
+            s += "        const u64 r = warp_reduce_dyn(nq_ops[c / NQ_G], s_priv[c * NQ_BLOCK + threadIdx.x]);\n";
             s += "        if (lane == 0) s_wpart[c][threadIdx.x >> 5] = r;\n";
             s += "    }\n";
             s += "    __syncthreads();\n";
             s += "    if (threadIdx.x < NQ_W * NQ_G) {\n";
             s += "        const int op = nq_ops[threadIdx.x / NQ_G];\n";
             s += "        u64 v = s_wpart[threadIdx.x][0];\n";
-            s += "        for (int k = 1; k < 8; ++k) v = word_combine(op, v, s_wpart[threadIdx.x][k]);\n";
+            s += "        for (int k = 1; k < NQ_BLOCK / 32; ++k) v = word_combine(op, v, s_wpart[threadIdx.x][k]);\n";
             s += "        if (v != word_identity(op)) atomic_word_dyn(op, &p.acc[threadIdx.x], v);\n";
             s += "    }\n";
         } else {
@@ -1307,7 +1330,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             s += "    }\n";
         }
         s += "    if (last_block_arrives(p.ticket)) {\n";
-        s += "        for (int i = threadIdx.x; i < NQ_W * NQ_G; i += 256) p.final_host[i] = __ldcg(&p.acc[i]);\n";
+        s += "        for (int i = threadIdx.x; i < NQ_W * NQ_G; i += NQ_BLOCK) p.final_host[i] = __ldcg(&p.acc[i]);\n";
         s += "        if (p.peer_mail) mailbox_push(p, p.acc);\n";
         s += "    }\n";
     }
