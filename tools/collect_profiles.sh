@@ -27,7 +27,7 @@ ROWS=1000000000 EXTRA="$(cat tools/config5_ablation.json)" python tools/sweep_co
 if [ -x tools/_build/proto5 ]; then
   tools/_build/proto5 2>/dev/null | grep -v '"variant": "base' > $O/r02_proto5_ablation.jsonl
   HOT=1 ONLY="simple w1 aos" tools/_build/proto5 2>/dev/null | grep -v "base\|nomnreg" | sed 's/"variant": "/"variant": "hot keys preloaded: /' >> $O/r02_proto5_ablation.jsonl
-  MATCH=1 ONLY="simple w1 aos" tools/_build/proto5 2>/dev/null | head -3 | grep -v base | sed 's/"variant": "/"variant": "warp-cooperative __match_any_sync: /' >> $O/r02_proto5_ablation.jsonl
+  for m in 1 2; do [ -x tools/_build/proto5_m$m ] && ONLY="simple w1 aos" tools/_build/proto5_m$m 2>/dev/null | grep -v "base\|nomnreg\|nocheck\|7040" | sed "s/\"variant\": \"/\"variant\": \"-DPROTO_MODE=$m: /" >> $O/r02_proto5_ablation.jsonl; done
 fi
 rm -f $O/*.ncu-rep
 ls -la $O

@@ -4,6 +4,7 @@
 //
 //   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a --fmad=false -Iquery_b200/csrc \
 //        -o tools/_build/proto5 tools/proto5.cu && tools/_build/proto5 [rows]
+//   (-DPROTO_MODE=1 / 2 builds the two experiment modes described at k_scan_q's g_match / g_pack)
 //
 // Variants
 //   base   the kernel codegen.cpp emits today for this query (tools/_build/k5.cu, SoA table, per-row phases)
@@ -72,6 +73,9 @@ __global__ void k_fill4(u64* p, u64 nslots, u64 a, u64 b, u64 c, u64 d) {
 //   W2 max of ~v  (= ~min v)             (max s64)   W3 max of v                     (max s64)
 #define VBIAS 1000
 #define QCAP 64
+#ifndef PROTO_MODE
+#define PROTO_MODE 0
+#endif
 struct QParams { const u32* code; const u8* ktag; const i64* v; const u8* vtag; i64 nrows; u64* table; const u32* hot; int match; };
 
 template <int NT, int NS, int K0, int QUEUES = 1>
@@ -126,7 +130,10 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
     u32* const qk = s.qkey[(QROWS || PAIR) ? w : 0]; u32* const qv = s.qval[(QROWS || PAIR) ? w : 0];
     u32* const mk = s.mkey[(QROWS || PAIR) ? w : 0]; u32* const mv = s.mval[(QROWS || PAIR) ? w : 0];
     u64* const table = p.table;
-    const bool g_match = p.match != 0;
+    // experiment modes are compile-time (-DPROTO_MODE=1: warp-cooperative __match_any_sync pre-aggregation, 2: row counter and
+    // sum packed into one shared-memory atomic) so that the plain variants keep their code and register allocation
+    constexpr bool g_match = PROTO_MODE == 1;
+    constexpr bool g_pack = PROTO_MODE == 2;
     // word w of group `key`: one 32-byte sector per group (slot-major), or word planes (SOA: the round-1 layout)
     auto word = [&](u32 key, int w) -> u64* { return SOA ? table + (u64)w * SLOTS + key : table + (u64)key * 4 + w; };
 
@@ -188,6 +195,23 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
             return;
         }
         if (active) slot = cache_claim_w<WAYS>(s.ckey, NS, key * 0x9E3779B1u, key);
+        if (slot >= 0 && g_pack) {
+            // ONE shared-memory atomic for the row counter (low 8 bits) and the sum (high 24 bits): whatever a field carries
+            // out is seen in the returned old value by the thread that caused it and compensated in the table
+            const bool isnull = val >> 31;
+            const u32 vb = val & 0xfffffu;
+            const u32 addv = isnull ? 0u : vb;
+            const u32 old = atomicAdd(&s.c_rows[slot], 1u | (addv << 8));
+            const bool cw = (old & 0xffu) == 0xffu;  // the count wrapped: 256 rows to the table, and its carry sits in the sum field
+            if (cw) { red_add_u64(word(key, 0), 256ULL); red_add_u64(word(key, 1), ~0ULL); }
+            if ((old >> 8) + addv + (cw ? 1u : 0u) >= (1u << 24)) red_add_u64(word(key, 1), 1ULL << 24);
+            if (isnull) atomicAdd(&s.c_cnull[slot], 1u);
+            else {
+                const u32 a = vb + 1u, b = 0x100000u - vb;
+                if (!CHECK || a > *(volatile u32*)&s.c_max[slot]) atomicMax(&s.c_max[slot], a);
+                if (!CHECK || b > *(volatile u32*)&s.c_nmin[slot]) atomicMax(&s.c_nmin[slot], b);
+            }
+        } else
         if (slot >= 0) {
             const bool isnull = val >> 31;
             const u32 vb = val & 0xfffffu;
@@ -310,9 +334,10 @@ __global__ void __launch_bounds__(NT, 1) k_scan_q(const QParams p) {
     for (int i = threadIdx.x; i < NS; i += NT) {
         const u32 key = s.ckey[i];
         if (key == 0xffffffffu) continue;
-        const u64 w0 = (u64)s.c_rows[i] | ((u64)s.c_cnull[i] << 32);
+        const u64 w0 = (u64)(g_pack ? (s.c_rows[i] & 0xffu) : s.c_rows[i]) | ((u64)s.c_cnull[i] << 32);
         if (w0) red_add_u64(word(key, 0), w0);
-        if (s.c_sum[i]) red_add_u64(word(key, 1), (u64)s.c_sum[i]);
+        const u32 fs = g_pack ? (s.c_rows[i] >> 8) : s.c_sum[i];
+        if (fs) red_add_u64(word(key, 1), (u64)fs);
         if (s.c_max[i]) red_max_s64(word(key, 3), (i64)(s.c_max[i] - 1u) - VBIAS);
         if (s.c_nmin[i]) red_max_s64(word(key, 2), ~((i64)(0x100000u - s.c_nmin[i]) - VBIAS));
     }
@@ -357,7 +382,7 @@ static void run_q(const char* name, const QParams& qp0, u64* d_tab, const Ref& r
     QParams qp = qp0;
     qp.table = d_tab;
     qp.hot = nullptr;
-    qp.match = getenv("MATCH") ? 1 : 0;
+    qp.match = PROTO_MODE;
     if (getenv("HOT") && WAYS == 1) {  // most-common-values statistic: every cache slot starts out owned by the hottest key that maps to it
         std::vector<u32> hot(NS, 0xffffffffu); std::vector<u64> cnt(NS, 0);
         for (u64 key = 2; key < SLOTS; ++key) {
