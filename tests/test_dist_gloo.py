@@ -98,6 +98,29 @@ def test_dictionary_and_statistics_agreement_gives_identical_kernels():
     assert out[0][3] == out[1][3], "ranks must compile the same kernel (same packing, same constants)"
 
 
+def _disagree(rank, world):
+    import query_b200 as q
+    from query_b200 import dist as qd
+    # no agreement before seal: rank 1's dictionary and integer range differ, so the ranks compile different kernels
+    docs = ['{"s":"b","n":5}', '{"s":"a","n":-2}'] if rank == 0 else ['{"s":"c","n":40000000000}', '{"s":"a"}', '{"n":1.5}']
+    t = q.Table(["s", "n"])
+    t.append_json(docs)
+    t.seal()
+    qq = q.Query(t, "d", None, ["(`d`.`s`)"], ["count(*)", "sum((`d`.`n`))"])
+    try:
+        qd.DistributedQuery(qq)
+    except RuntimeError as e:
+        return str(e)
+    return "accepted"
+
+
+def test_ranks_with_different_kernels_are_refused_not_hung():
+    """DistributedQuery compares a digest of (mode, word ops, kernel text) across ranks with one all-reduce: ranks that would
+    enter different collectives or merge differently laid out words get an error on every rank instead of a hang."""
+    out = _run(_disagree)
+    assert all("different kernels" in o for o in out), out
+
+
 def _gathered_tail(rank, world):
     """Each rank holds the groups whose key hashes to it (what the owner-bucketed merge leaves); the tail runs over the
     gathered result on every rank."""
