@@ -345,6 +345,13 @@ double comp_domain(const Table& t, const PackComp& pc) {
 
 }  // namespace
 
+// index of word w's 32-bit cache cell of slot `slot` inside s_c32 (see KernelPlan::cell_pair)
+static std::string cell32(const KernelPlan& kp, int w, const char* slot) {
+    if (kp.cell_pair[(size_t)w] == 1) return strf("%d * NQ_CS + 2 * (%s)", kp.cell_idx[(size_t)w], slot);
+    if (kp.cell_pair[(size_t)w] == 2) return strf("%d * NQ_CS + 2 * (%s) + 1", kp.cell_idx[(size_t)w - 1], slot);
+    return strf("%d * NQ_CS + %s", kp.cell_idx[(size_t)w], slot);
+}
+
 KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<ExprP>& keys,
                            const std::vector<ExprP>& aggs, const std::vector<std::string>& agg_texts,
                            double total_rows_bound) {
@@ -581,6 +588,16 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 kp.cell_kind.push_back(kind);
                 if (kind == CK_64) kp.cell_idx.push_back(kp.cache_n64++);
                 else { kp.cell_idx.push_back(kp.cache_n32); kp.cache_n32 += kind == CK_WIDE ? 2 : 1; }
+            }
+            kp.cell_pair.assign((size_t)W, 0);
+            {
+                const char* npair = getenv("N1GPU_NO_MM_PAIR");
+                const char* ncheck = getenv("N1GPU_NO_CELL_CHECK");
+                if (!(npair && *npair == '1') && !(ncheck && *ncheck == '1'))
+                    for (int w = 0; w + 1 < W; ++w)
+                        if (kp.cell_kind[w] == CK_MM32 && kp.cell_kind[w + 1] == CK_MM32 && kp.cell_idx[w + 1] == kp.cell_idx[w] + 1 && kp.cell_pair[w] == 0) {
+                            kp.cell_pair[w] = 1; kp.cell_pair[w + 1] = 2; ++w;
+                        }
             }
             const char* nk = getenv("N1GPU_NO_KEY32");
             kp.cache_key32 = kp.key_bits <= 31 && !(nk && *nk == '1');  // u32 keys in buckets of four (cache_claim_b4)
@@ -929,6 +946,14 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         for (int w = 0; w < W; ++w) {
             std::string hit;
             const int ci = kp.cell_idx[w];
+            if (kp.cell_kind[w] == CK_MM32 && kp.cell_pair[w]) {
+                // interleaved with its neighbour: the hit phase has loaded both cells of the slot with one 64-bit load (mmpN)
+                const int first = kp.cell_pair[w] == 1 ? w : w - 1;
+                hit = strf("cache_mm32_cur<OP>(&s_c32[%s], (u64)(val_), %lluULL, (u32)(mmp%d%s))", cell32(kp, w, "cslot").c_str(), (unsigned long long)kp.word_lo[w],
+                           first, kp.cell_pair[w] == 1 ? "" : " >> 32");
+                s += strf("#define ACCH_%d(OP, val_) %s\n", w, hit.c_str());
+                continue;
+            }
             switch (kp.cell_kind[w]) {
                 case CK_CNT: hit = strf("atomicAdd(&s_c32[%d * NQ_CS + cslot], (u32)(val_))", ci); break;
                 case CK_WIDE: hit = strf("cache_add_wide(&s_c32[%d * NQ_CS + cslot], &s_c32[%d * NQ_CS + cslot], (u64)(val_))", ci, ci + 1); break;
@@ -1025,7 +1050,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                 const int ci = kp.cell_idx[w], op = kp.word_ops[w];
                 switch (kp.cell_kind[w]) {
                     case CK_WIDE: s += strf("        s_c32[%d * NQ_CS + i] = 0; s_c32[%d * NQ_CS + i] = 0;\n", ci, ci + 1); break;
-                    case CK_MM32: s += strf("        s_c32[%d * NQ_CS + i] = %s;\n", ci, (op == OP_MIN_I64 || op == OP_MIN_U64) ? "0xffffffffu" : "0u"); break;
+                    case CK_MM32: s += strf("        s_c32[%s] = %s;\n", cell32(kp, w, "i").c_str(), (op == OP_MIN_I64 || op == OP_MIN_U64) ? "0xffffffffu" : "0u"); break;
                     case CK_64: s += strf("        s_c64[%d * NQ_CS + i] = word_identity(%s);\n", ci, op_name(op)); break;
                     default: s += strf("        s_c32[%d * NQ_CS + i] = 0;\n", ci); break;
                 }
@@ -1129,6 +1154,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         s += "            if (__ballot_sync(0xffffffffu, cs[j] >= 0) == 0) continue;\n";
         s += "            if (cs[j] >= 0) {\n";
         s += "                    const int cslot = cs[j]; const u64 klo = kk[j]; (void)klo;\n";
+        for (int w = 0; w < W; ++w)
+            if (kp.cell_pair[w] == 1)
+                s += strf("                    const u64 mmp%d = *(volatile u64*)&s_c32[%d * NQ_CS + 2 * cslot];  // both cells of the slot: one LDS.64\n", w, kp.cell_idx[w]);
         s += g.decls;
         s += agg_code;
         s += "            }\n";
@@ -1206,7 +1234,7 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
                               ci + 1, ci, op_name(op), dst.c_str());
                     break;
                 case CK_MM32:
-                    s += strf("        { const u32 c = s_c32[%d * NQ_CS + i]; if (c != %s) atomic_word<%s>(%s, (u64)(c - 1u) + %lluULL); }\n", ci,
+                    s += strf("        { const u32 c = s_c32[%s]; if (c != %s) atomic_word<%s>(%s, (u64)(c - 1u) + %lluULL); }\n", cell32(kp, w, "i").c_str(),
                               (op == OP_MIN_I64 || op == OP_MIN_U64) ? "0xffffffffu" : "0u", op_name(op), dst.c_str(), (unsigned long long)kp.word_lo[w]);
                     break;
                 case CK_64:

@@ -88,6 +88,9 @@ struct KernelPlan {
     int cache_slots = 0;         // HASH64: slots of the per-block shared-memory front cache (0 = none)
     // front-cache cell of every word: kind (CK_*) and index of its first cell among the 32-bit / 64-bit cell arrays
     std::vector<int> cell_kind, cell_idx;
+    // two neighbouring ranged min / max cells (MIN(x) and MAX(x)) interleaved per slot - [first, second] at 2 * slot - so
+    // that ONE 64-bit shared-memory load fetches both for the read-before-atomic check: 0 none, 1 first of a pair, 2 second
+    std::vector<int> cell_pair;
     int cache_n32 = 0, cache_n64 = 0;
     // groups whose key is one of the first `reg_groups` packed values (the payload-free classes of a single key component:
     // MISSING / NULL keys - 20 % of config 5's rows on two groups) are aggregated in per-thread REGISTERS, outside the cache

@@ -484,6 +484,11 @@ template <int OP> NQ_DEV void cache_mm32(u32* c, u64 x, u64 bias) {
 #endif
     if (OP == OP_MIN_I64 || OP == OP_MIN_U64) { if (v < cur) atomicMin(c, v); } else { if (v > cur) atomicMax(c, v); }
 }
+// the same with the cell's current value already in a register (two interleaved cells fetched by one 64-bit load)
+template <int OP> NQ_DEV void cache_mm32_cur(u32* c, u64 x, u64 bias, u32 cur) {
+    const u32 v = (u32)(x - bias) + 1u;
+    if (OP == OP_MIN_I64 || OP == OP_MIN_U64) { if (v < cur) atomicMin(c, v); } else { if (v > cur) atomicMax(c, v); }
+}
 NQ_DEV void cache_or32(u32* c, u32 bits) {
     if ((*(volatile u32*)c & bits) != bits) atomicOr(c, bits);
 }

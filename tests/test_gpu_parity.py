@@ -172,7 +172,7 @@ _GROUPED = [x for x in QUERIES if x[2]]
                                   "N1GPU_NO_KEY32", "N1GPU_NO_COMPLEMENT", "N1GPU_CACHE_BLOCK=1024", "N1GPU_CACHE_BLOCK=256",
                                   "N1GPU_MMCHECK=1", "N1GPU_MMCHECK=2", "N1GPU_SET_PASSES=4", "N1GPU_NO_FCARRY", "N1GPU_NO_TIGHT", "N1GPU_PART",
                                   "N1GPU_CACHE_WAYS=4", "N1GPU_NO_WIDE1", "N1GPU_NO_SIGN_FROM_MINMAX", "N1GPU_REG_GROUPS",
-                                  "N1GPU_PRIV_BLOCK=640", "N1GPU_PRIV_BLOCK=96"])
+                                  "N1GPU_PRIV_BLOCK=640", "N1GPU_PRIV_BLOCK=96", "N1GPU_NO_MM_PAIR"])
 @pytest.mark.parametrize("name,where,keys,aggs", _GROUPED, ids=[x[0] for x in _GROUPED])
 def test_grouped_matrix_through_the_alternate_layouts(name, where, keys, aggs, knob, monkeypatch):
     """The planner picks direct-indexed tables, DISTINCT bitmaps, offset-packed keys, the shared-memory front cache

@@ -15,7 +15,7 @@ import query_b200 as q  # noqa: E402
 
 KNOBS = ["N1GPU_NO_PACK", "N1GPU_MMCHECK", "N1GPU_CACHE_BLOCK", "N1GPU_MIN_BLOCKS", "N1GPU_CACHE_KB", "N1GPU_NO_CACHE",
          "N1GPU_NO_KEY32", "N1GPU_NO_COMPLEMENT", "N1GPU_NO_CELL_CHECK", "N1GPU_CACHE_WAYS", "N1GPU_NO_WIDE1", "N1GPU_NO_SIGN_FROM_MINMAX",
-         "N1GPU_REG_GROUPS"]
+         "N1GPU_REG_GROUPS", "N1GPU_NO_MM_PAIR"]
 R1 = {"N1GPU_NO_PACK": "1", "N1GPU_NO_KEY32": "1", "N1GPU_NO_COMPLEMENT": "1", "N1GPU_NO_CELL_CHECK": "1"}
 
 
