@@ -878,7 +878,11 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
             if (ok) {
                 kp.part = true;
                 kp.part_bits = PB; kp.part_gbits = KB - PB; kp.part_vbits = VB;
-                kp.part_bincap = std::max(8, std::min(48, (int)((192 * 1024) / (4 << PB))));
+                {
+                    const char* pbk = getenv("N1GPU_PART_BLOCK");
+                    if (pbk && (atoi(pbk) == 512 || atoi(pbk) == 256)) kp.part_block = atoi(pbk);
+                }
+                kp.part_bincap = std::max(8, std::min(48, (int)((192 * 1024 / (1024 / kp.part_block)) / (4 << PB))));
                 kp.part_smem = (4 << PB) * (1 + kp.part_bincap);
                 g.body.clear();
                 g.ind = "                    ";
@@ -1370,9 +1374,9 @@ KernelPlan generate_kernel(const Table& t, const Expr* where, const std::vector<
         std::string q;
         q += "// generated by libn1gpu codegen: the partitioning kernel of this chain's partitioned DISTINCT aggregation\n";
         q += "#include \"n1ql_device.cuh\"\n";
-        q += "#define NQ_BLOCK 1024\n";
+        q += strf("#define NQ_BLOCK %d\n", kp.part_block);
         q += strf("#define NP %d\n#define BINCAP %d\n#define GBITS %d\n#define ROUND_TILES 8\n", 1 << kp.part_bits, kp.part_bincap, kp.part_gbits);
-        q += "extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, 1) nq_scan(const NqParams p) {\n";
+        q += strf("extern \"C\" __global__ void __launch_bounds__(NQ_BLOCK, %d) nq_scan(const NqParams p) {\n", 1024 / kp.part_block);
         q += "    extern __shared__ u32 s_part[];\n";
         q += "    __shared__ int s_stop;\n";
         q += "    u32* const s_cnt = s_part;        // [NP] records staged per partition in this round\n";

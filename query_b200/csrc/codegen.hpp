@@ -112,6 +112,7 @@ struct KernelPlan {
     int part_gbits = 0;          // record bits [0, gbits): group key inside its partition; bit gbits: has a value
     int part_vbits = 0;          // record bits above: the packed DISTINCT value
     int part_bincap = 48;        // records a block stages per partition and round in shared memory
+    int part_block = 1024;       // threads per block of the partition kernel (N1GPU_PART_BLOCK: 512 = two blocks per SM with half the bins)
     int part_smem = 0;           // dynamic shared memory of the partitioning kernel
     // payloads of constants / bound parameters, passed to the kernel as NqParams::cst (the source only names the slot)
     std::vector<i64> consts;
