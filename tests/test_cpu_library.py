@@ -408,3 +408,47 @@ def test_plain_filter_project_is_not_substituted(tmp_path):
     for tail in (False, True):
         e = _expect(q._lib.E_INELIGIBLE, lambda: q.Operator(plan, str(tmp_path), tail=tail))
         assert isinstance(e, q.Ineligible)
+
+
+def test_kernel_shapes_follow_the_table_statistics():
+    """Layout decisions that the B200 measurements settled, pinned on the generated text (no GPU needed): the skewed string
+    GROUP BY of config 5 gets one 1024-thread block per SM capped at 56 registers (room for the merge / finalisation kernels
+    of the neighbouring steps), a direct-mapped u32 front cache, MIN / MAX cells interleaved for one 64-bit load and a
+    one-cell sum that sends its carries to the table; Q1's 6 groups x 7 words get thread-private tables in a 640-thread block."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    n, vocab = 200000, 100000
+    words = ["w%06d" % i for i in range(vocab)]
+    t = q.Table(["k", "v"])
+    kt = np.where(rng.integers(0, 10, n) == 0, 0, 6).astype(np.uint8)
+    t.set_column("k", rng.integers(0, vocab, n).astype(np.uint32), tags=kt, dictionary=words)
+    vt = np.where(rng.integers(0, 10, n) == 0, 1, 4).astype(np.uint8)
+    t.set_column("v", rng.integers(-1000, 1000000, n, dtype=np.int64), tags=vt)
+    t.set_global_rows(1_000_000_000)
+    t.seal()
+    qq = q.Query(t, "d", "((`d`.`v`) is not missing)", ["(`d`.`k`)"],
+                 ["count(*)", "count((`d`.`v`))", "sum((`d`.`v`))", "min((`d`.`v`))", "max((`d`.`v`))"])
+    src = qq.kernel_source
+    assert qq.info["mode"] == "hbm-direct" and qq.info["block"] == 1024 and qq.info["words"] == 4
+    assert "__maxnreg__(56)" in src and "cache_claim_1(" in src and "cache_add_carry(" in src and "mmp" in src and "volatile u64*" in src
+    # TPC-H Q1 shape: two low-cardinality string keys, mixed INT / FLOAT money columns
+    m = 60000
+    t3 = q.Table(["f", "s", "qty", "price", "disc"])
+    t3.set_column("f", rng.integers(0, 3, m).astype(np.uint32), dictionary=["A", "N", "R"])
+    t3.set_column("s", rng.integers(0, 2, m).astype(np.uint32), dictionary=["F", "O"])
+    t3.set_column("qty", rng.integers(1, 51, m, dtype=np.int64))
+    cents = rng.integers(90000, 10500000, m)
+    whole = cents % 100 == 0
+    price = np.where(whole, cents // 100, 0).astype(np.int64)
+    price[~whole] = np.array(cents[~whole] / 100.0).view(np.int64)
+    t3.set_column("price", price, tags=np.where(whole, 4, 5).astype(np.uint8))
+    pct = rng.integers(0, 11, m)
+    disc = np.zeros(m, dtype=np.int64)
+    disc[pct != 0] = np.array(pct[pct != 0] / 100.0).view(np.int64)
+    t3.set_column("disc", disc, tags=np.where(pct == 0, 4, 5).astype(np.uint8))
+    t3.set_global_rows(60_000_000)
+    t3.seal()
+    q3 = q.Query(t3, "l", None, ["(`l`.`f`)", "(`l`.`s`)"],
+                 ["sum((`l`.`qty`))", "sum((`l`.`price`))", "sum(((`l`.`price`) * (1 - (`l`.`disc`))))", "avg((`l`.`disc`))", "count(*)"])
+    assert q3.info["mode"] == "dense-shared-memory" and q3.info["slots"] == 6
+    assert "s_priv" in q3.kernel_source and q3.info["block"] >= 512 and q3.info["block"] % 32 == 0
